@@ -1,0 +1,921 @@
+// avb_api.cpp -- host side of the C ABI declared in include/avatar_b200.h.
+//
+// Owns the model preparation (the data layout the kernels read), device buffers, the per-call
+// kernel schedule of AvatarOptimizer::optimize (AvatarOptimizer.cpp:1246-1517) and the transfers.
+// There is no CPU compute path here: every fit entry point enqueues the CUDA kernels of
+// avb_kernels.cu and fails with AVB_ERR_CUDA if that is impossible.
+#include "../../include/avatar_b200.h"
+#include "avb_kernels.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace avb;
+
+static_assert(sizeof(avb_stats) == sizeof(FrameStats), "avb_stats must mirror FrameStats");
+static_assert(AVB_MAX_ASSIGN == AVB_MAX_ASSIGN_, "assign width");
+static_assert(AVB_MAX_JOINTS == kMaxJ && AVB_MAX_SHAPE_KEYS == kMaxK, "limits");
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(AVB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+
+// dense lower Cholesky, row-major; false if not positive definite
+bool chol_lower(const std::vector<double>& A, int n, std::vector<double>& L) {
+    L.assign((size_t)n * n, 0.0);
+    for (int j = 0; j < n; ++j) {
+        double d = A[(size_t)j * n + j];
+        for (int k = 0; k < j; ++k) d -= L[(size_t)j * n + k] * L[(size_t)j * n + k];
+        if (!(d > 0.0)) return false;
+        d = std::sqrt(d);
+        L[(size_t)j * n + j] = d;
+        for (int i = j + 1; i < n; ++i) {
+            double s = A[(size_t)i * n + j];
+            for (int k = 0; k < j; ++k) s -= L[(size_t)i * n + k] * L[(size_t)j * n + k];
+            L[(size_t)i * n + j] = s / d;
+        }
+    }
+    return true;
+}
+
+template <class T>
+cudaError_t dev_upload(T** dst, const std::vector<T>& src) {
+    *dst = nullptr;
+    const size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dst), bytes);
+    if (e != cudaSuccess) return e;
+    if (!src.empty()) e = cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+}  // namespace
+
+/* ------------------------------------------------------------------------------------------ */
+struct avb_model {
+    int V = 0, J = 0, K = 0, F = 0, P = 0, nx = 0, max_depth = 0;
+    std::vector<double> vt, sk_w, jbase, jreg, Sp;
+    std::vector<float> sd;
+    std::vector<uint8_t> sk_j, sk_n;
+    std::vector<uint32_t> anc_mask;
+    std::vector<int> parent, depth, faces;
+    std::vector<int> main_joint;  // assignedJoints[v][0].second
+    int gmmC = 0, gmmD = 0;
+    std::vector<double> gmm_mean, gmm_prec, gmm_prec_cho, gmm_clog;
+};
+
+struct avb_fitter {
+    const avb_model* model = nullptr;
+    int device = 0, max_batch = 0, num_sms = 148;
+    int64_t max_points = 0;
+    int num_parts = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    DevModel dm{};
+    DevParts dp{};
+    std::vector<void*> allocs;  // everything cudaMalloc'ed, freed in destroy
+    std::vector<void*> pinned;
+    // per-batch device buffers
+    double* d_data = nullptr; int* d_labels = nullptr;
+    double* d_x = nullptr; double* d_xdbg = nullptr;
+    double* d_cloud = nullptr; double* d_jpos = nullptr; double* d_jtrans = nullptr;
+    uint8_t* d_vis = nullptr; int* d_pv_idx = nullptr; double* d_pv_xyz = nullptr; int* d_pv_start = nullptr;
+    long long pv_stride = 0;
+    int* d_nn = nullptr; int* d_cnt = nullptr; unsigned long long* d_sum = nullptr; double* d_qpart = nullptr;
+    int* d_range = nullptr; double* d_Hcur = nullptr; FrameStats* d_stats = nullptr;
+    int *d_chunk_frame = nullptr, *d_chunk_count = nullptr, *d_chunk_qblock = nullptr, *d_frame_qblock = nullptr;
+    long long* d_chunk_begin = nullptr;
+    double *d_dump_cost = nullptr, *d_dump_grad = nullptr, *d_dump_H = nullptr;
+    // pinned host staging
+    double* h_x = nullptr; FrameStats* h_stats = nullptr;
+    int *h_chunk_frame = nullptr, *h_chunk_count = nullptr, *h_chunk_qblock = nullptr, *h_frame_qblock = nullptr;
+    long long* h_chunk_begin = nullptr;
+    int max_chunks = 0;
+    int64_t max_qblocks = 0;
+    // state of the uploaded batch
+    int batch = 0, num_chunks = 0;
+    int64_t total_points = 0;
+    std::vector<int64_t> offsets;
+    int launches = 0;
+    int n_events = 0;
+    int last_icp = 0;
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(avb_fitter* ft, T** p, size_t count) {
+    *p = nullptr;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) return fail(AVB_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    ft->allocs.push_back(*p);
+    return AVB_OK;
+}
+template <class T>
+int pin_alloc(avb_fitter* ft, T** p, size_t count) {
+    *p = nullptr;
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T), cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(AVB_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    ft->pinned.push_back(*p);
+    return AVB_OK;
+}
+template <class T>
+int dev_put(avb_fitter* ft, const T** p, const std::vector<T>& src) {
+    T* d = nullptr;
+    cudaError_t e = dev_upload(&d, src);
+    if (d) ft->allocs.push_back(d);
+    if (e != cudaSuccess) return fail(AVB_ERR_CUDA, std::string("model upload: ") + cudaGetErrorString(e));
+    *p = d;
+    return AVB_OK;
+}
+
+// Static column-group schedule.  Vertices whose skinning joints share the same ancestor set get
+// the same sparse Jacobian column pattern; groups are merged greedily until at most `max_groups`
+// remain, minimising sum_g |g| * Lp(g)^2 (the dense-within-group J^T J work).
+void build_groups(const avb_model& m, int max_groups, std::vector<int>& gorder, std::vector<int>& gvstart,
+                  std::vector<int>& gjoints, std::vector<int>& gnj) {
+    const int V = m.V, J = m.J, K = m.K;
+    std::vector<uint32_t> sig(V);
+    for (int v = 0; v < V; ++v) {
+        uint32_t s = 0;
+        for (int q = 0; q < m.sk_n[v]; ++q) s |= m.anc_mask[m.sk_j[4 * (size_t)v + q]];
+        sig[v] = s;
+    }
+    struct Grp { uint32_t mask; long long n; };
+    std::vector<Grp> groups;
+    {
+        std::vector<uint32_t> u(sig);
+        std::sort(u.begin(), u.end());
+        u.erase(std::unique(u.begin(), u.end()), u.end());
+        for (uint32_t s : u) groups.push_back({s, 0});
+        for (int v = 0; v < V; ++v)
+            for (auto& g : groups)
+                if (g.mask == sig[v]) { ++g.n; break; }
+    }
+    auto lp = [&](uint32_t mask) {
+        const int L = 3 + 3 * __builtin_popcount(mask) + K;
+        return (L + 7) & ~7;
+    };
+    auto cost = [&](uint32_t mask, long long n) { return (double)n * lp(mask) * lp(mask); };
+    while ((int)groups.size() > max_groups) {
+        double best = 1e300;
+        int bi = 0, bj = 1;
+        for (size_t i = 0; i < groups.size(); ++i)
+            for (size_t j = i + 1; j < groups.size(); ++j) {
+                const uint32_t mm = groups[i].mask | groups[j].mask;
+                const double inc = cost(mm, groups[i].n + groups[j].n) - cost(groups[i].mask, groups[i].n) -
+                                   cost(groups[j].mask, groups[j].n);
+                if (inc < best) { best = inc; bi = (int)i; bj = (int)j; }
+            }
+        groups[bi].mask |= groups[bj].mask;
+        groups[bi].n += groups[bj].n;
+        groups.erase(groups.begin() + bj);
+        // absorb groups that became subsets for free
+        for (size_t j = 0; j < groups.size();) {
+            if ((int)j != bi && (groups[j].mask | groups[bi].mask) == groups[bi].mask &&
+                lp(groups[j].mask) == lp(groups[bi].mask)) {
+                groups[bi].n += groups[j].n;
+                if ((int)j < bi) --bi;
+                groups.erase(groups.begin() + j);
+            } else {
+                ++j;
+            }
+        }
+    }
+    std::sort(groups.begin(), groups.end(), [&](const Grp& a, const Grp& b) {
+        const int pa = __builtin_popcount(a.mask), pb = __builtin_popcount(b.mask);
+        return pa != pb ? pa < pb : a.mask < b.mask;
+    });
+    const int G = (int)groups.size();
+    // assign every vertex to the cheapest group that covers its signature
+    std::vector<int> vg(V, -1);
+    for (int v = 0; v < V; ++v) {
+        int best = -1;
+        for (int g = 0; g < G; ++g)
+            if ((sig[v] | groups[g].mask) == groups[g].mask && (best < 0 || lp(groups[g].mask) < lp(groups[best].mask))) best = g;
+        vg[v] = best;
+    }
+    gorder.clear();
+    gvstart.assign(G + 1, 0);
+    for (int g = 0; g < G; ++g) {
+        gvstart[g] = (int)gorder.size();
+        for (int v = 0; v < V; ++v)
+            if (vg[v] == g) gorder.push_back(v);
+    }
+    gvstart[G] = (int)gorder.size();
+    gjoints.assign((size_t)G * kMaxJ, 0);
+    gnj.assign(G, 0);
+    for (int g = 0; g < G; ++g)
+        for (int j = 0; j < J; ++j)
+            if ((groups[g].mask >> j) & 1u) gjoints[(size_t)g * kMaxJ + gnj[g]++] = j;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* avb_last_error(void) { return g_err.c_str(); }
+
+void avb_default_options(avb_options* o) {
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+    o->icp_iters = 1;            // AvatarOptimizer.h:19
+    o->max_iters_per_icp = 10;   // AvatarOptimizer.h:36
+    o->beta_pose = 0.1;          // AvatarOptimizer.h:27
+    o->beta_shape = 1.0;
+    o->enable_occlusion = 1;     // AvatarOptimizer.h:39
+    o->nn_step = 20;             // AvatarOptimizer.h:33 (unused by the inverted NN mode)
+    o->function_tolerance = 1e-4;  // AvatarOptimizer.cpp:1333
+    o->solver = AVB_SOLVER_GN_LM;
+    o->jtj_precision = AVB_JTJ_FP32;
+}
+
+int avb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int avb_model_create(const avb_model_desc* d, avb_model** out) {
+    if (!d || !out) return fail(AVB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    const int V = d->num_points, J = d->num_joints, K = d->num_shape_keys, F = d->num_faces;
+    if (V <= 0 || V > 65535 || J <= 0 || J > kMaxJ || K < 0 || K > kMaxK || F < 0)
+        return fail(AVB_ERR_INVALID, "unsupported model dimensions (V<=65535, J<=32, K<=16)");
+    if (!d->base_cloud || !d->parent || !d->assign_start || !d->assign_joint || !d->assign_weight ||
+        !d->joint_shape_reg_base || (K > 0 && (!d->key_clouds || !d->joint_shape_reg)) || (F > 0 && !d->mesh))
+        return fail(AVB_ERR_INVALID, "null model array");
+    auto m = new avb_model;
+    m->V = V; m->J = J; m->K = K; m->F = F;
+    m->P = 3 + 3 * J + K;
+    m->nx = 3 + 4 * J + K;
+    m->vt.assign(d->base_cloud, d->base_cloud + 3 * (size_t)V);
+    m->sd.resize(3 * (size_t)V * K);
+    for (size_t i = 0; i < m->sd.size(); ++i) m->sd[i] = (float)d->key_clouds[i];
+    m->jbase.assign(d->joint_shape_reg_base, d->joint_shape_reg_base + 3 * (size_t)J);
+    m->jreg.assign(d->joint_shape_reg, d->joint_shape_reg + 3 * (size_t)J * K);
+    m->parent.assign(d->parent, d->parent + J);
+    m->faces.assign(d->mesh, d->mesh + 3 * (size_t)F);
+    for (int i = 0; i < 3 * F; ++i)
+        if (m->faces[i] < 0 || m->faces[i] >= V) { delete m; return fail(AVB_ERR_INVALID, "face index out of range"); }
+    // kinematic tree: depth and ancestor-or-self masks
+    m->depth.assign(J, 0);
+    m->anc_mask.assign(J, 0);
+    for (int j = 0; j < J; ++j) {
+        int dep = 0;
+        uint32_t mask = 0;
+        for (int a = j; a != -1; a = m->parent[a]) {
+            if (a < 0 || a >= J || dep > J) { delete m; return fail(AVB_ERR_INVALID, "bad kinematic tree"); }
+            mask |= 1u << a;
+            ++dep;
+        }
+        m->depth[j] = dep - 1;
+        m->anc_mask[j] = mask;
+        m->max_depth = std::max(m->max_depth, dep - 1);
+    }
+    // Sp[j] = S[j] - S[parent j], Sp[0] = 0 (AvatarOptimizer.cpp:240-243)
+    m->Sp.assign((size_t)J * 3 * K, 0.0);
+    for (int j = 0; j < J; ++j) {
+        if (m->parent[j] < 0) continue;
+        for (int e = 0; e < 3 * K; ++e)
+            m->Sp[(size_t)j * 3 * K + e] = m->jreg[(size_t)3 * j * K + e] - m->jreg[(size_t)3 * m->parent[j] * K + e];
+    }
+    // skinning (assignedJoints, at most 4 per vertex)
+    m->sk_w.assign(4 * (size_t)V, 0.0);
+    m->sk_j.assign(4 * (size_t)V, 0);
+    m->sk_n.assign(V, 0);
+    m->main_joint.assign(V, 0);
+    for (int v = 0; v < V; ++v) {
+        const int s = d->assign_start[v], e = d->assign_start[v + 1];
+        if (e - s < 1 || e - s > AVB_MAX_ASSIGN) {
+            delete m;
+            return fail(AVB_ERR_INVALID, "every vertex needs 1..4 assigned joints (MAX_ASSIGN, AvatarOptimizer.cpp:164)");
+        }
+        m->sk_n[v] = (uint8_t)(e - s);
+        for (int q = s; q < e; ++q) {
+            if (d->assign_joint[q] < 0 || d->assign_joint[q] >= J) { delete m; return fail(AVB_ERR_INVALID, "assigned joint out of range"); }
+            m->sk_j[4 * (size_t)v + q - s] = (uint8_t)d->assign_joint[q];
+            m->sk_w[4 * (size_t)v + q - s] = d->assign_weight[q];
+        }
+        m->main_joint[v] = d->assign_joint[s];
+    }
+    // GaussianMixture::load maths (GaussianMixture.cpp:22-76)
+    if (d->gmm_components > 0) {
+        const int C = d->gmm_components, D = d->gmm_dims;
+        if (D != 3 * (J - 1) || !d->gmm_weight || !d->gmm_mean || !d->gmm_cov) {
+            delete m;
+            return fail(AVB_ERR_INVALID, "pose prior must have 3(J-1) dimensions");
+        }
+        m->gmmC = C; m->gmmD = D;
+        m->gmm_mean.assign(d->gmm_mean, d->gmm_mean + (size_t)C * D);
+        m->gmm_clog.assign(C, 0.0);
+        m->gmm_prec.assign((size_t)C * D * D, 0.0);
+        m->gmm_prec_cho.assign((size_t)C * D * D, 0.0);
+        const double log_sqrt_2_pi_n = D * 0.5 * std::log(2 * M_PI);
+        double minDet = 1.79769313486231570e308;
+        std::vector<double> cov((size_t)D * D), L, Linv((size_t)D * D), inv((size_t)D * D), Lp;
+        for (int c = 0; c < C; ++c) {
+            std::copy(d->gmm_cov + (size_t)c * D * D, d->gmm_cov + (size_t)(c + 1) * D * D, cov.begin());
+            if (!chol_lower(cov, D, L)) { delete m; return fail(AVB_ERR_NUMERIC, "pose prior covariance is not positive definite"); }
+            // Sigma^-1 = L^-T L^-1
+            std::fill(Linv.begin(), Linv.end(), 0.0);
+            for (int col = 0; col < D; ++col)
+                for (int i = col; i < D; ++i) {
+                    double s = (i == col) ? 1.0 : 0.0;
+                    for (int k = col; k < i; ++k) s -= L[(size_t)i * D + k] * Linv[(size_t)k * D + col];
+                    Linv[(size_t)i * D + col] = s / L[(size_t)i * D + i];
+                }
+            for (int a = 0; a < D; ++a)
+                for (int b = 0; b <= a; ++b) {
+                    double s = 0;
+                    for (int k = a; k < D; ++k) s += Linv[(size_t)k * D + a] * Linv[(size_t)k * D + b];
+                    inv[(size_t)a * D + b] = inv[(size_t)b * D + a] = s;
+                }
+            if (!chol_lower(inv, D, Lp)) { delete m; return fail(AVB_ERR_NUMERIC, "pose prior precision is not positive definite"); }
+            std::copy(Lp.begin(), Lp.end(), m->gmm_prec_cho.begin() + (size_t)c * D * D);
+            // the matrix the reference's residual and Jacobian imply is prec_cho prec_cho^T
+            for (int a = 0; a < D; ++a)
+                for (int b = 0; b <= a; ++b) {
+                    double s = 0;
+                    for (int k = 0; k <= b; ++k) s += Lp[(size_t)a * D + k] * Lp[(size_t)b * D + k];
+                    m->gmm_prec[((size_t)c * D + a) * D + b] = m->gmm_prec[((size_t)c * D + b) * D + a] = s;
+                }
+            double det = 1.0;
+            for (int k = 0; k < D; ++k) det *= L[(size_t)k * D + k];
+            minDet = std::min(minDet, det);
+            m->gmm_clog[c] = std::log(d->gmm_weight[c]) - log_sqrt_2_pi_n - std::log(det);
+        }
+        for (int c = 0; c < C; ++c) m->gmm_clog[c] += std::log(minDet);
+    }
+    *out = m;
+    return AVB_OK;
+}
+
+void avb_model_destroy(avb_model* m) { delete m; }
+
+int avb_model_dims(const avb_model* m, int32_t* V, int32_t* J, int32_t* K, int32_t* F) {
+    if (!m) return fail(AVB_ERR_INVALID, "null model");
+    if (V) *V = m->V;
+    if (J) *J = m->J;
+    if (K) *K = m->K;
+    if (F) *F = m->F;
+    return AVB_OK;
+}
+int avb_param_dim(const avb_model* m) { return m ? m->nx : 0; }
+int avb_tangent_dim(const avb_model* m) { return m ? m->P : 0; }
+
+int avb_model_get_prior(const avb_model* m, double* prec_cho, double* consts_log) {
+    if (!m || m->gmmC <= 0) return fail(AVB_ERR_PRIOR, "model has no pose prior");
+    if (prec_cho) std::copy(m->gmm_prec_cho.begin(), m->gmm_prec_cho.end(), prec_cho);
+    if (consts_log) std::copy(m->gmm_clog.begin(), m->gmm_clog.end(), consts_log);
+    return AVB_OK;
+}
+
+/* Eigen conventions: AngleAxisd::fromRotationMatrix -> Quaterniond */
+void avb_rotmat_to_quat(const double* m, double* q) {
+    double t = m[0] + m[4] + m[8];
+    double x, y, z, w;
+    if (t > 0) {
+        t = std::sqrt(t + 1.0);
+        w = 0.5 * t;
+        t = 0.5 / t;
+        x = (m[7] - m[5]) * t;
+        y = (m[2] - m[6]) * t;
+        z = (m[3] - m[1]) * t;
+    } else {
+        int i = 0;
+        if (m[4] > m[0]) i = 1;
+        if (m[8] > m[4 * i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        double qq[3];
+        t = std::sqrt(m[4 * i] - m[4 * j] - m[4 * k] + 1.0);
+        qq[i] = 0.5 * t;
+        t = 0.5 / t;
+        w = (m[3 * k + j] - m[3 * j + k]) * t;
+        qq[j] = (m[3 * j + i] + m[3 * i + j]) * t;
+        qq[k] = (m[3 * k + i] + m[3 * i + k]) * t;
+        x = qq[0]; y = qq[1]; z = qq[2];
+    }
+    // quaternion -> angle-axis (angle in [0, pi]) -> quaternion: canonical w >= 0
+    double n = std::sqrt(x * x + y * y + z * z);
+    if (n != 0) {
+        const double angle = 2 * std::atan2(n, std::fabs(w));
+        if (w < 0) n = -n;
+        const double ha = 0.5 * angle, s = std::sin(ha);
+        q[0] = s * (x / n); q[1] = s * (y / n); q[2] = s * (z / n); q[3] = std::cos(ha);
+    } else {
+        q[0] = 0; q[1] = 0; q[2] = 0; q[3] = 1;
+    }
+}
+void avb_quat_to_rotmat(const double* q, double* R) {
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x;
+    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+    R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+
+void* avb_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        g_err = "cudaHostAlloc failed";
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void avb_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+void avb_fitter_destroy(avb_fitter* ft) {
+    if (!ft) return;
+    cudaSetDevice(ft->device);
+    if (ft->stream) cudaStreamSynchronize(ft->stream);
+    for (void* p : ft->allocs) cudaFree(p);
+    for (void* p : ft->pinned) cudaFreeHost(p);
+    for (auto& e : ft->ev)
+        if (e) cudaEventDestroy(e);
+    if (ft->stream) cudaStreamDestroy(ft->stream);
+    delete ft;
+}
+
+int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitter** out) {
+    if (!m || !cfg || !out) return fail(AVB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->num_parts <= 0 || cfg->num_parts > kMaxParts || !cfg->part_map)
+        return fail(AVB_ERR_INVALID, "num_parts must be in 1..64 and part_map non-null");
+    if (cfg->max_batch <= 0 || cfg->max_total_points <= 0) return fail(AVB_ERR_INVALID, "capacities must be positive");
+    for (int j = 0; j < m->J; ++j)
+        if (cfg->part_map[j] < 0 || cfg->part_map[j] >= cfg->num_parts) return fail(AVB_ERR_INVALID, "part_map entry out of range");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(AVB_ERR_CUDA, "no CUDA device available: avatar_b200 has no CPU fallback");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(AVB_ERR_INVALID, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) return fail(AVB_ERR_CUDA, "avatar_b200 kernels are built for sm_100a only");
+
+    auto ft = new avb_fitter;
+    ft->model = m;
+    ft->device = cfg->device;
+    ft->max_batch = cfg->max_batch;
+    ft->max_points = cfg->max_total_points;
+    ft->num_parts = cfg->num_parts;
+    ft->num_sms = prop.multiProcessorCount;
+    int rc = AVB_OK;
+#define TRY(expr)                     \
+    do {                              \
+        rc = (expr);                  \
+        if (rc != AVB_OK) {           \
+            avb_fitter_destroy(ft);   \
+            return rc;                \
+        }                             \
+    } while (0)
+#define CUDA_TRY_FT(expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            avb_fitter_destroy(ft);                                                               \
+            return fail(AVB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+        }                                                                                         \
+    } while (0)
+    CUDA_TRY_FT(cudaStreamCreateWithFlags(&ft->stream, cudaStreamNonBlocking));
+    for (auto& e : ft->ev) CUDA_TRY_FT(cudaEventCreate(&e));
+
+    // ---- model -> device ----
+    DevModel& dm = ft->dm;
+    dm.V = m->V; dm.J = m->J; dm.K = m->K; dm.F = m->F; dm.P = m->P; dm.nx = m->nx; dm.max_depth = m->max_depth;
+    TRY(dev_put(ft, &dm.vt, m->vt));
+    TRY(dev_put(ft, &dm.sd, m->sd));
+    TRY(dev_put(ft, &dm.sk_w, m->sk_w));
+    TRY(dev_put(ft, &dm.sk_j, m->sk_j));
+    TRY(dev_put(ft, &dm.sk_n, m->sk_n));
+    TRY(dev_put(ft, &dm.anc_mask, m->anc_mask));
+    TRY(dev_put(ft, &dm.parent, m->parent));
+    TRY(dev_put(ft, &dm.depth, m->depth));
+    TRY(dev_put(ft, &dm.jbase, m->jbase));
+    TRY(dev_put(ft, &dm.jreg, m->jreg));
+    TRY(dev_put(ft, &dm.Sp, m->Sp));
+    TRY(dev_put(ft, &dm.faces, m->faces));
+    dm.gmmC = m->gmmC; dm.gmmD = m->gmmD;
+    TRY(dev_put(ft, &dm.gmm_mean, m->gmm_mean));
+    TRY(dev_put(ft, &dm.gmm_prec, m->gmm_prec));
+    TRY(dev_put(ft, &dm.gmm_clog, m->gmm_clog));
+
+    // ---- part tables (AvatarOptimizer.cpp:1223-1243) ----
+    const int V = m->V, NP = cfg->num_parts;
+    std::vector<int> part_start(NP + 1, 0), part_verts, first_part_at(V + 1, -1);
+    for (int p = 0; p < NP; ++p) {
+        part_start[p] = (int)part_verts.size();
+        for (int v = 0; v < V; ++v)
+            if (cfg->part_map[m->main_joint[v]] == p) part_verts.push_back(v);
+    }
+    part_start[NP] = (int)part_verts.size();
+    for (int p = NP - 1; p >= 0; --p) first_part_at[part_start[p]] = p;
+    DevParts& dp = ft->dp;
+    dp.numParts = NP;
+    TRY(dev_put(ft, &dp.part_start, part_start));
+    TRY(dev_put(ft, &dp.part_verts, part_verts));
+    TRY(dev_put(ft, &dp.first_part_at, first_part_at));
+    int max_groups = 1;
+    if (const char* e = std::getenv("AVB_GROUPS")) max_groups = std::max(1, std::min(kMaxGroups, std::atoi(e)));
+    std::vector<int> gorder, gvstart, gjoints, gnj;
+    build_groups(*m, max_groups, gorder, gvstart, gjoints, gnj);
+    dp.numGroups = (int)gnj.size();
+    TRY(dev_put(ft, &dp.gorder, gorder));
+    TRY(dev_put(ft, &dp.gvstart, gvstart));
+    TRY(dev_put(ft, &dp.gjoints, gjoints));
+    TRY(dev_put(ft, &dp.gnj, gnj));
+
+    // ---- batch buffers ----
+    const size_t B = (size_t)cfg->max_batch, NT = (size_t)cfg->max_total_points;
+    const size_t P = m->P, nx = m->nx, J = m->J;
+    ft->pv_stride = (3 * (long long)V + 2 + 1) & ~1LL;
+    TRY(dev_alloc(ft, &ft->d_data, 3 * NT));
+    TRY(dev_alloc(ft, &ft->d_labels, NT));
+    TRY(dev_alloc(ft, &ft->d_x, B * nx));
+    TRY(dev_alloc(ft, &ft->d_xdbg, B * nx));
+    TRY(dev_alloc(ft, &ft->d_cloud, B * 3 * V));
+    TRY(dev_alloc(ft, &ft->d_jpos, B * 3 * J));
+    TRY(dev_alloc(ft, &ft->d_jtrans, B * 12 * J));
+    TRY(dev_alloc(ft, &ft->d_vis, B * V));
+    TRY(dev_alloc(ft, &ft->d_pv_idx, B * V));
+    TRY(dev_alloc(ft, &ft->d_pv_xyz, B * (size_t)ft->pv_stride));
+    TRY(dev_alloc(ft, &ft->d_pv_start, B * (NP + 1)));
+    TRY(dev_alloc(ft, &ft->d_nn, NT));
+    TRY(dev_alloc(ft, &ft->d_cnt, B * V));
+    TRY(dev_alloc(ft, &ft->d_sum, B * 3 * V));
+    TRY(dev_alloc(ft, &ft->d_range, B));
+    TRY(dev_alloc(ft, &ft->d_Hcur, B * P * P));
+    TRY(dev_alloc(ft, &ft->d_stats, B));
+    ft->max_chunks = (int)std::min<size_t>(NT / 512 + B + 8, (size_t)8 * ft->num_sms + 2 * B + 8);
+    ft->max_qblocks = (int64_t)(NT / kQBlock + B + 8);
+    TRY(dev_alloc(ft, &ft->d_qpart, (size_t)ft->max_qblocks));
+    TRY(dev_alloc(ft, &ft->d_chunk_frame, (size_t)ft->max_chunks));
+    TRY(dev_alloc(ft, &ft->d_chunk_count, (size_t)ft->max_chunks));
+    TRY(dev_alloc(ft, &ft->d_chunk_qblock, (size_t)ft->max_chunks));
+    TRY(dev_alloc(ft, &ft->d_chunk_begin, (size_t)ft->max_chunks));
+    TRY(dev_alloc(ft, &ft->d_frame_qblock, B + 1));
+    TRY(pin_alloc(ft, &ft->h_x, B * nx));
+    TRY(pin_alloc(ft, &ft->h_stats, B));
+    TRY(pin_alloc(ft, &ft->h_chunk_frame, (size_t)ft->max_chunks));
+    TRY(pin_alloc(ft, &ft->h_chunk_count, (size_t)ft->max_chunks));
+    TRY(pin_alloc(ft, &ft->h_chunk_qblock, (size_t)ft->max_chunks));
+    TRY(pin_alloc(ft, &ft->h_chunk_begin, (size_t)ft->max_chunks));
+    TRY(pin_alloc(ft, &ft->h_frame_qblock, B + 1));
+    CUDA_TRY_FT(cudaMemsetAsync(ft->d_stats, 0, B * sizeof(FrameStats), ft->stream));
+    CUDA_TRY_FT(cudaStreamSynchronize(ft->stream));
+#undef TRY
+#undef CUDA_TRY_FT
+    *out = ft;
+    return AVB_OK;
+}
+
+/* -------- batch upload: data + the NN chunk schedule -------- */
+int avb_upload_batch(avb_fitter* ft, int32_t batch, const double* clouds, const int32_t* labels, const int64_t* offsets) {
+    if (!ft || !offsets || batch <= 0) return fail(AVB_ERR_INVALID, "null argument or empty batch");
+    if (batch > ft->max_batch) return fail(AVB_ERR_CAPACITY, "batch exceeds fitter capacity");
+    const int64_t total = offsets[batch] - offsets[0];
+    if (total < 0 || total > ft->max_points) return fail(AVB_ERR_CAPACITY, "point count exceeds fitter capacity");
+    if (total > 0 && (!clouds || !labels)) return fail(AVB_ERR_INVALID, "null cloud or labels");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    ft->offsets.assign(offsets, offsets + batch + 1);
+    for (int f = 0; f < batch; ++f)
+        if (offsets[f + 1] < offsets[f] || offsets[f + 1] - offsets[f] > (int64_t)1 << 21)
+            return fail(AVB_ERR_INVALID, "offsets must be non-decreasing and a frame may hold at most 2^21 points");
+    const int64_t o0 = offsets[0];
+    // NN chunk schedule: every frame is cut into equal chunks (multiples of 512 points) so that the
+    // grid has about 4 CTAs per SM; |d|^2 partials are always per 256 points, independent of the cut.
+    const int64_t target = std::max<int64_t>(512, (total / (4 * (int64_t)ft->num_sms) + 511) / 512 * 512);
+    int nc = 0;
+    int qb = 0;
+    for (int f = 0; f < batch; ++f) {
+        const int64_t n = offsets[f + 1] - offsets[f];
+        ft->h_frame_qblock[f] = qb;
+        if (n > 0) {
+            const int64_t k = (n + target - 1) / target;
+            const int64_t per = ((n + k - 1) / k + 511) / 512 * 512;
+            for (int64_t b = 0; b < n; b += per) {
+                if (nc >= ft->max_chunks) return fail(AVB_ERR_CAPACITY, "too many NN chunks");
+                ft->h_chunk_frame[nc] = f;
+                ft->h_chunk_begin[nc] = offsets[f] - o0 + b;
+                ft->h_chunk_count[nc] = (int)std::min<int64_t>(per, n - b);
+                ft->h_chunk_qblock[nc] = qb + (int)(b / kQBlock);
+                ++nc;
+            }
+            qb += (int)((n + kQBlock - 1) / kQBlock);
+        }
+    }
+    ft->h_frame_qblock[batch] = qb;
+    if (qb > ft->max_qblocks) return fail(AVB_ERR_CAPACITY, "too many |d|^2 blocks");
+    ft->batch = batch;
+    ft->num_chunks = nc;
+    ft->total_points = total;
+    cudaStream_t st = ft->stream;
+    if (total > 0) {
+        CUDA_TRY(cudaMemcpyAsync(ft->d_data, clouds + 3 * o0, (size_t)total * 24, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ft->d_labels, labels + o0, (size_t)total * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (nc > 0) {
+        CUDA_TRY(cudaMemcpyAsync(ft->d_chunk_frame, ft->h_chunk_frame, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ft->d_chunk_begin, ft->h_chunk_begin, (size_t)nc * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ft->d_chunk_count, ft->h_chunk_count, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ft->d_chunk_qblock, ft->h_chunk_qblock, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaMemcpyAsync(ft->d_frame_qblock, ft->h_frame_qblock, (size_t)(batch + 1) * 4, cudaMemcpyHostToDevice, st));
+    return AVB_OK;
+}
+
+namespace {
+
+int check_options(const avb_fitter* ft, const avb_options* o) {
+    if (!o) return fail(AVB_ERR_INVALID, "null options");
+    if (o->icp_iters < 0 || o->max_iters_per_icp < 0) return fail(AVB_ERR_INVALID, "negative iteration count");
+    if (o->solver != AVB_SOLVER_GN_LM) return fail(AVB_ERR_INVALID, "unknown solver");
+    if (o->jtj_precision != AVB_JTJ_FP32) return fail(AVB_ERR_INVALID, "jtj_precision: only AVB_JTJ_FP32 is implemented");
+    if (o->beta_pose > 0.0 && ft->model->gmmC <= 0)
+        return fail(AVB_ERR_PRIOR, "betaPose > 0 but the model has no pose prior");
+    return AVB_OK;
+}
+
+PoseArgs pose_args(avb_fitter* ft, const double* dx, bool vis, const avb_options* o) {
+    PoseArgs a{};
+    a.x = dx;
+    a.cloud = ft->d_cloud;
+    a.joint_pos = nullptr;
+    a.joint_trans = nullptr;
+    a.do_visibility = vis ? 1 : 0;
+    a.enable_occlusion = o ? o->enable_occlusion : 1;
+    a.visible = ft->d_vis;
+    a.pv_idx = ft->d_pv_idx;
+    a.pv_xyz = ft->d_pv_xyz;
+    a.pv_start = ft->d_pv_start;
+    a.pv_stride = ft->pv_stride;
+    return a;
+}
+
+int enqueue_correspond(avb_fitter* ft, const double* dx, const avb_options* o) {
+    cudaStream_t st = ft->stream;
+    const int B = ft->batch, V = ft->model->V;
+    PoseArgs pa = pose_args(ft, dx, true, o);
+    CUDA_TRY(launch_pose_visibility(ft->dm, ft->dp, pa, B, st));
+    ++ft->launches;
+    CUDA_TRY(cudaMemsetAsync(ft->d_cnt, 0, (size_t)B * V * 4, st));
+    CUDA_TRY(cudaMemsetAsync(ft->d_sum, 0, (size_t)B * V * 24, st));
+    CUDA_TRY(cudaMemsetAsync(ft->d_range, 0, (size_t)B * 4, st));
+    NNArgs na{};
+    na.V = V;
+    na.data = ft->d_data;
+    na.labels = ft->d_labels;
+    na.chunk_frame = ft->d_chunk_frame;
+    na.chunk_begin = ft->d_chunk_begin;
+    na.chunk_count = ft->d_chunk_count;
+    na.chunk_qblock = ft->d_chunk_qblock;
+    na.pv_idx = ft->d_pv_idx;
+    na.pv_xyz = ft->d_pv_xyz;
+    na.pv_start = ft->d_pv_start;
+    na.pv_stride = ft->pv_stride;
+    na.nn_idx = ft->d_nn;
+    na.cnt = ft->d_cnt;
+    na.sum = ft->d_sum;
+    na.qpart = ft->d_qpart;
+    na.range_flag = ft->d_range;
+    CUDA_TRY(launch_nn(ft->dp, na, ft->num_chunks, st));
+    if (ft->num_chunks > 0) ++ft->launches;
+    return AVB_OK;
+}
+
+LmArgs lm_args(avb_fitter* ft, double* dx, const avb_options* o) {
+    LmArgs a{};
+    a.x = dx;
+    a.cnt = ft->d_cnt;
+    a.sum = ft->d_sum;
+    a.qpart = ft->d_qpart;
+    a.frame_qblock = ft->d_frame_qblock;
+    a.Hcur = ft->d_Hcur;
+    a.beta_pose = o->beta_pose;
+    a.beta_shape = o->beta_shape;
+    a.function_tolerance = o->function_tolerance;
+    a.max_iters = o->max_iters_per_icp;
+    a.stats = ft->d_stats;
+    a.range_flag = ft->d_range;
+    return a;
+}
+
+}  // namespace
+
+int avb_fit_resident(avb_fitter* ft, const double* x_in, const avb_options* o) {
+    if (!ft || !x_in) return fail(AVB_ERR_INVALID, "null argument");
+    if (ft->batch <= 0) return fail(AVB_ERR_INVALID, "no batch uploaded");
+    int rc = check_options(ft, o);
+    if (rc != AVB_OK) return rc;
+    CUDA_TRY(cudaSetDevice(ft->device));
+    cudaStream_t st = ft->stream;
+    const int B = ft->batch;
+    const size_t nx = ft->model->nx;
+    std::memcpy(ft->h_x, x_in, (size_t)B * nx * 8);
+    CUDA_TRY(cudaMemcpyAsync(ft->d_x, ft->h_x, (size_t)B * nx * 8, cudaMemcpyHostToDevice, st));
+    ft->launches = 0;
+    ft->last_icp = o->icp_iters;
+    CUDA_TRY(cudaEventRecord(ft->ev[0], st));
+    for (int icp = 0; icp < o->icp_iters; ++icp) {
+        const bool timed = (icp == o->icp_iters - 1);
+        rc = enqueue_correspond(ft, ft->d_x, o);
+        if (rc != AVB_OK) return rc;
+        if (timed) CUDA_TRY(cudaEventRecord(ft->ev[1], st));
+        LmArgs la = lm_args(ft, ft->d_x, o);
+        CUDA_TRY(launch_lm(ft->dm, ft->dp, la, B, st));
+        ++ft->launches;
+        if (timed) CUDA_TRY(cudaEventRecord(ft->ev[2], st));
+    }
+    // trailing ava.update() (AvatarOptimizer.cpp:1497)
+    PoseArgs pa = pose_args(ft, ft->d_x, false, o);
+    CUDA_TRY(launch_pose_visibility(ft->dm, ft->dp, pa, B, st));
+    ++ft->launches;
+    CUDA_TRY(cudaEventRecord(ft->ev[3], st));
+    return AVB_OK;
+}
+
+int avb_synchronize(avb_fitter* ft) {
+    if (!ft) return fail(AVB_ERR_INVALID, "null fitter");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    CUDA_TRY(cudaStreamSynchronize(ft->stream));
+    return AVB_OK;
+}
+
+int avb_last_device_ms(avb_fitter* ft, float* total_ms, float* per4) {
+    if (!ft) return fail(AVB_ERR_INVALID, "null fitter");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    CUDA_TRY(cudaEventSynchronize(ft->ev[3]));
+    if (total_ms) CUDA_TRY(cudaEventElapsedTime(total_ms, ft->ev[0], ft->ev[3]));
+    if (per4) {
+        per4[0] = per4[1] = per4[2] = per4[3] = 0.f;
+        if (ft->last_icp > 0) {
+            float a = 0, b = 0, c = 0;
+            CUDA_TRY(cudaEventElapsedTime(&a, ft->ev[0], ft->ev[1]));  // pose+vis+nn (all but last ICP's LM)
+            CUDA_TRY(cudaEventElapsedTime(&b, ft->ev[1], ft->ev[2]));
+            CUDA_TRY(cudaEventElapsedTime(&c, ft->ev[2], ft->ev[3]));
+            per4[0] = a; per4[1] = 0.f; per4[2] = b; per4[3] = c;
+        }
+    }
+    return AVB_OK;
+}
+
+int avb_last_launch_count(avb_fitter* ft) { return ft ? ft->launches : 0; }
+
+int avb_download_results(avb_fitter* ft, double* x_out, avb_stats* stats, double* cloud_out) {
+    if (!ft) return fail(AVB_ERR_INVALID, "null fitter");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    cudaStream_t st = ft->stream;
+    const int B = ft->batch;
+    const size_t nx = ft->model->nx, V = ft->model->V;
+    if (x_out) CUDA_TRY(cudaMemcpyAsync(ft->h_x, ft->d_x, (size_t)B * nx * 8, cudaMemcpyDeviceToHost, st));
+    if (stats) CUDA_TRY(cudaMemcpyAsync(ft->h_stats, ft->d_stats, (size_t)B * sizeof(FrameStats), cudaMemcpyDeviceToHost, st));
+    if (cloud_out) CUDA_TRY(cudaMemcpyAsync(cloud_out, ft->d_cloud, (size_t)B * 3 * V * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (x_out) std::memcpy(x_out, ft->h_x, (size_t)B * nx * 8);
+    int worst = AVB_OK;
+    if (stats) {
+        for (int f = 0; f < B; ++f) {
+            std::memcpy(&stats[f], &ft->h_stats[f], sizeof(avb_stats));
+            stats[f].num_points = (int32_t)(ft->offsets[f + 1] - ft->offsets[f]);
+            if (stats[f].status != AVB_OK) worst = stats[f].status;
+        }
+    }
+    if (worst != AVB_OK) return fail(AVB_ERR_NUMERIC, "a frame held non-finite / out-of-range input (see stats[f].status)");
+    return AVB_OK;
+}
+
+int avb_fit_batch(avb_fitter* ft, int32_t batch, const double* clouds, const int32_t* labels, const int64_t* offsets,
+                  double* x, const avb_options* o, avb_stats* stats, double* cloud_out) {
+    if (!x) return fail(AVB_ERR_INVALID, "null parameter vector");
+    int rc = avb_upload_batch(ft, batch, clouds, labels, offsets);
+    if (rc != AVB_OK) return rc;
+    rc = avb_fit_resident(ft, x, o);
+    if (rc != AVB_OK) return rc;
+    std::vector<avb_stats> tmp;
+    if (!stats) {
+        tmp.resize(batch);
+        stats = tmp.data();
+    }
+    return avb_download_results(ft, x, stats, cloud_out);
+}
+
+int avb_fit(avb_fitter* ft, const double* cloud, const int32_t* labels, int32_t n, double* x, const avb_options* o,
+            avb_stats* stats, double* cloud_out) {
+    if (n < 0) return fail(AVB_ERR_INVALID, "negative point count");
+    const int64_t offsets[2] = {0, n};
+    return avb_fit_batch(ft, 1, cloud, labels, offsets, x, o, stats, cloud_out);
+}
+
+int avb_avatar_update(avb_fitter* ft, int batch, const double* x, double* cloud, double* joint_pos, double* joint_trans) {
+    if (!ft || !x || batch <= 0) return fail(AVB_ERR_INVALID, "null argument");
+    if (batch > ft->max_batch) return fail(AVB_ERR_CAPACITY, "batch exceeds fitter capacity");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    cudaStream_t st = ft->stream;
+    const size_t nx = ft->model->nx, V = ft->model->V, J = ft->model->J;
+    CUDA_TRY(cudaMemcpyAsync(ft->d_xdbg, x, (size_t)batch * nx * 8, cudaMemcpyHostToDevice, st));
+    PoseArgs pa = pose_args(ft, ft->d_xdbg, false, nullptr);
+    pa.joint_pos = ft->d_jpos;
+    pa.joint_trans = ft->d_jtrans;
+    CUDA_TRY(launch_pose_visibility(ft->dm, ft->dp, pa, batch, st));
+    if (cloud) CUDA_TRY(cudaMemcpyAsync(cloud, ft->d_cloud, (size_t)batch * 3 * V * 8, cudaMemcpyDeviceToHost, st));
+    if (joint_pos) CUDA_TRY(cudaMemcpyAsync(joint_pos, ft->d_jpos, (size_t)batch * 3 * J * 8, cudaMemcpyDeviceToHost, st));
+    if (joint_trans) CUDA_TRY(cudaMemcpyAsync(joint_trans, ft->d_jtrans, (size_t)batch * 12 * J * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return AVB_OK;
+}
+
+/* ---------------- parity taps ---------------- */
+int avb_debug_correspond(avb_fitter* ft, const double* x_in, const avb_options* o) {
+    if (!ft || !x_in) return fail(AVB_ERR_INVALID, "null argument");
+    if (ft->batch <= 0) return fail(AVB_ERR_INVALID, "no batch uploaded");
+    int rc = check_options(ft, o);
+    if (rc != AVB_OK) return rc;
+    CUDA_TRY(cudaSetDevice(ft->device));
+    const size_t nx = ft->model->nx;
+    CUDA_TRY(cudaMemcpyAsync(ft->d_xdbg, x_in, (size_t)ft->batch * nx * 8, cudaMemcpyHostToDevice, ft->stream));
+    ft->launches = 0;
+    rc = enqueue_correspond(ft, ft->d_xdbg, o);
+    if (rc != AVB_OK) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ft->stream));
+    return AVB_OK;
+}
+
+int avb_debug_read(avb_fitter* ft, int what, void* out, uint64_t bytes) {
+    if (!ft || !out) return fail(AVB_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    const size_t B = ft->batch, V = ft->model->V;
+    const void* src = nullptr;
+    size_t need = 0;
+    switch (what) {
+        case AVB_TAP_VISIBLE: src = ft->d_vis; need = B * V; break;
+        case AVB_TAP_NN: src = ft->d_nn; need = (size_t)ft->total_points * 4; break;
+        case AVB_TAP_CLOUD: src = ft->d_cloud; need = B * 3 * V * 8; break;
+        case AVB_TAP_COUNT: src = ft->d_cnt; need = B * V * 4; break;
+        case AVB_TAP_SUM: need = B * 3 * V * 8; break;
+        default: return fail(AVB_ERR_INVALID, "unknown tap");
+    }
+    if (bytes < need) return fail(AVB_ERR_INVALID, "tap buffer too small");
+    CUDA_TRY(cudaStreamSynchronize(ft->stream));
+    if (what == AVB_TAP_SUM) {
+        std::vector<long long> tmp(B * 3 * V);
+        CUDA_TRY(cudaMemcpy(tmp.data(), ft->d_sum, need, cudaMemcpyDeviceToHost));
+        double* o = static_cast<double*>(out);
+        for (size_t i = 0; i < tmp.size(); ++i) o[i] = (double)tmp[i] * kFixInv;
+        return AVB_OK;
+    }
+    CUDA_TRY(cudaMemcpy(out, src, need, cudaMemcpyDeviceToHost));
+    return AVB_OK;
+}
+
+int avb_debug_evaluate(avb_fitter* ft, const double* x_in, const avb_options* o, double* cost, double* grad, double* H) {
+    if (!ft || !x_in || !cost || !grad || !H) return fail(AVB_ERR_INVALID, "null argument");
+    if (ft->batch <= 0) return fail(AVB_ERR_INVALID, "no batch uploaded");
+    int rc = check_options(ft, o);
+    if (rc != AVB_OK) return rc;
+    CUDA_TRY(cudaSetDevice(ft->device));
+    const size_t B = ft->batch, nx = ft->model->nx, P = ft->model->P;
+    if (!ft->d_dump_cost) {
+        rc = dev_alloc(ft, &ft->d_dump_cost, (size_t)ft->max_batch);
+        if (rc == AVB_OK) rc = dev_alloc(ft, &ft->d_dump_grad, (size_t)ft->max_batch * P);
+        if (rc == AVB_OK) rc = dev_alloc(ft, &ft->d_dump_H, (size_t)ft->max_batch * P * P);
+        if (rc != AVB_OK) return rc;
+    }
+    cudaStream_t st = ft->stream;
+    CUDA_TRY(cudaMemcpyAsync(ft->d_xdbg, x_in, B * nx * 8, cudaMemcpyHostToDevice, st));
+    LmArgs la = lm_args(ft, ft->d_xdbg, o);
+    la.max_iters = 0;
+    la.dump_cost = ft->d_dump_cost;
+    la.dump_grad = ft->d_dump_grad;
+    la.dump_H = ft->d_dump_H;
+    CUDA_TRY(launch_lm(ft->dm, ft->dp, la, (int)B, st));
+    CUDA_TRY(cudaMemcpyAsync(cost, ft->d_dump_cost, B * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(grad, ft->d_dump_grad, B * P * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(H, ft->d_dump_H, B * P * P * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return AVB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,204 @@
+"""Avatar / AvatarOptimizer: host-side mirrors of ark::Avatar (include/Avatar.h:155-220) and
+ark::AvatarOptimizer (include/AvatarOptimizer.h:11-54) over the C ABI.  Same member names, same
+argument meaning, same in-place result semantics; all arithmetic runs in the CUDA library."""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check, ptr
+
+
+def rotmat_to_quat(R):
+    """AvatarOptimizer.cpp:1250-1254 (AngleAxisd::fromRotationMatrix -> Quaterniond), xyzw"""
+    R = np.ascontiguousarray(R, dtype=np.float64)
+    q = np.zeros(4)
+    lib.avb_rotmat_to_quat(ptr(R), ptr(q))
+    return q
+
+
+def quat_to_rotmat(q):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    R = np.zeros((3, 3))
+    lib.avb_quat_to_rotmat(ptr(q), ptr(R))
+    return R
+
+
+class Fitter:
+    """Owns one avb_fitter (device buffers + stream) -- the device side of an AvatarOptimizer."""
+
+    def __init__(self, model, num_parts, part_map, max_batch=1, max_total_points=1 << 18, device=0):
+        self.model = model
+        self.part_map = np.ascontiguousarray(part_map, dtype=np.int32)
+        assert self.part_map.shape[0] == model.numJoints(), "partMap must have one entry per joint"
+        cfg = _lib.FitterConfig(device, max_batch, max_total_points, num_parts, ptr(self.part_map))
+        h = C.c_void_p()
+        check(lib.avb_fitter_create(model.handle, C.byref(cfg), C.byref(h)))
+        self.handle = h
+        self.max_batch, self.max_total_points = max_batch, max_total_points
+        self.nx = lib.avb_param_dim(model.handle)
+        self.P = lib.avb_tangent_dim(model.handle)
+        self.batch = 0
+        self.total_points = 0
+
+    def close(self):
+        if getattr(self, "handle", None) is not None:
+            lib.avb_fitter_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    def avatar_update(self, x):
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        B, V, J = x.shape[0], self.model.numPoints(), self.model.numJoints()
+        cloud, jp, jt = np.zeros((B, V, 3)), np.zeros((B, J, 3)), np.zeros((B, J, 12))
+        check(lib.avb_avatar_update(self.handle, B, ptr(x), ptr(cloud), ptr(jp), ptr(jt)))
+        return cloud, jp, jt
+
+    def upload(self, clouds, labels, offsets):
+        clouds = np.ascontiguousarray(clouds, dtype=np.float64)
+        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self._keep = (clouds, labels, offsets)
+        self.batch = offsets.shape[0] - 1
+        self.total_points = int(offsets[-1] - offsets[0])
+        check(lib.avb_upload_batch(self.handle, self.batch, ptr(clouds), ptr(labels), ptr(offsets)))
+
+    def fit_resident(self, x, opt):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        check(lib.avb_fit_resident(self.handle, ptr(x), C.byref(opt)))
+
+    def download(self, want_cloud=False):
+        x = np.zeros((self.batch, self.nx))
+        stats = (_lib.Stats * self.batch)()
+        cloud = np.zeros((self.batch, self.model.numPoints(), 3)) if want_cloud else None
+        check(lib.avb_download_results(self.handle, ptr(x), stats, ptr(cloud)))
+        return x, list(stats), cloud
+
+    def fit_batch(self, clouds, labels, offsets, x, opt, want_cloud=False):
+        clouds = np.ascontiguousarray(clouds, dtype=np.float64)
+        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        x = np.array(x, dtype=np.float64, order="C", copy=True).reshape(offsets.shape[0] - 1, self.nx)
+        B = x.shape[0]
+        stats = (_lib.Stats * B)()
+        cloud = np.zeros((B, self.model.numPoints(), 3)) if want_cloud else None
+        check(lib.avb_fit_batch(self.handle, B, ptr(clouds), ptr(labels), ptr(offsets), ptr(x), C.byref(opt), stats,
+                                ptr(cloud)))
+        self.batch = B
+        self.total_points = int(offsets[-1] - offsets[0])
+        return x, list(stats), cloud
+
+    # parity taps
+    def debug_correspond(self, x, opt):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        check(lib.avb_debug_correspond(self.handle, ptr(x), C.byref(opt)))
+
+    def debug_read(self, what):
+        B, V = self.batch, self.model.numPoints()
+        shape, dt = {_lib.TAP_VISIBLE: ((B, V), np.uint8), _lib.TAP_NN: ((self.total_points,), np.int32),
+                     _lib.TAP_CLOUD: ((B, V, 3), np.float64), _lib.TAP_COUNT: ((B, V), np.int32),
+                     _lib.TAP_SUM: ((B, V, 3), np.float64)}[what]
+        out = np.zeros(shape, dtype=dt)
+        check(lib.avb_debug_read(self.handle, what, ptr(out), out.nbytes))
+        return out
+
+    def debug_evaluate(self, x, opt):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        B, P = self.batch, self.P
+        cost, grad, H = np.zeros(B), np.zeros((B, P)), np.zeros((B, P, P))
+        check(lib.avb_debug_evaluate(self.handle, ptr(x), C.byref(opt), ptr(cost), ptr(grad), ptr(H)))
+        return cost, grad, H
+
+    def device_ms(self):
+        tot = C.c_float()
+        per = (C.c_float * 4)()
+        check(lib.avb_last_device_ms(self.handle, C.byref(tot), per))
+        return tot.value, list(per)
+
+    def launch_count(self):
+        return lib.avb_last_launch_count(self.handle)
+
+
+class Avatar:
+    """ark::Avatar: p, r (rotation matrices), w in; cloud, jointPos, jointTrans out (update())."""
+
+    def __init__(self, model):
+        self.model = model
+        self.w = np.zeros(model.numShapeKeys())
+        self.p = np.zeros(3)
+        self.r = [np.eye(3) for _ in range(model.numJoints())]
+        self.cloud = np.zeros((3, 0))
+        self.jointPos = np.zeros((3, 0))
+        self.jointTrans = np.zeros((12, 0))
+        self._fitter = None
+
+    def _updater(self):
+        if self._fitter is None:
+            self._fitter = Fitter(self.model, 1, np.zeros(self.model.numJoints(), dtype=np.int32), 1, 16)
+        return self._fitter
+
+    def params(self):
+        """x = [p | q (xyzw per joint, via the reference's R->AngleAxis->Quaternion prologue) | w]"""
+        q = np.concatenate([rotmat_to_quat(R) for R in self.r])
+        return np.concatenate([self.p, q, self.w])
+
+    def set_params(self, x):
+        J = self.model.numJoints()
+        self.p = np.array(x[:3])
+        self.r = [quat_to_rotmat(x[3 + 4 * j:7 + 4 * j]) for j in range(J)]  # AvatarOptimizer.cpp:1494-1496
+        self.w = np.array(x[3 + 4 * J:])
+
+    def update(self, fitter=None):
+        """Avatar::update (Avatar.cpp:22-75) on the GPU"""
+        cloud, jp, jt = (fitter or self._updater()).avatar_update(self.params())
+        self.cloud, self.jointPos, self.jointTrans = cloud[0].T.copy(), jp[0].T.copy(), jt[0].T.copy()
+
+    def smplParams(self):
+        """Avatar::smplParams (Avatar.cpp:128-137): axis-angle of joints 1..J-1"""
+        out = []
+        for R in self.r[1:]:
+            q = rotmat_to_quat(R)
+            n = np.linalg.norm(q[:3])
+            out.append(np.zeros(3) if n == 0 else q[:3] / n * (2 * np.arctan2(n, abs(q[3]))))
+        return np.concatenate(out)
+
+
+class AvatarOptimizer:
+    """ark::AvatarOptimizer (include/AvatarOptimizer.h): optimize(data_cloud, data_part_labels, icp_iters, num_threads)"""
+    ROT_SIZE = 4
+
+    def __init__(self, ava, intrin, image_size, num_parts, part_map, max_points=1 << 18, device=0):
+        self.ava, self.intrin, self.imageSize = ava, intrin, image_size
+        self.numParts, self.partMap = num_parts, part_map
+        self.betaPose, self.betaShape = 0.1, 1.0     # AvatarOptimizer.h:27
+        self.nnStep = 20                              # :33
+        self.maxItersPerICP = 10                      # :36
+        self.enableOcclusion = True                   # :39
+        self.functionTolerance = 1e-4                 # AvatarOptimizer.cpp:1333
+        self.r = [np.array([0.0, 0.0, 0.0, 1.0]) for _ in range(ava.model.numJoints())]
+        self.fitter = Fitter(ava.model, num_parts, part_map, 1, max_points, device)
+        self.last_stats = None
+
+    def options(self, icp_iters):
+        o = _lib.default_options()
+        o.icp_iters, o.max_iters_per_icp = icp_iters, self.maxItersPerICP
+        o.beta_pose, o.beta_shape = self.betaPose, self.betaShape
+        o.enable_occlusion, o.nn_step = int(self.enableOcclusion), self.nnStep
+        o.function_tolerance = self.functionTolerance
+        return o
+
+    def optimize(self, data_cloud, data_part_labels, icp_iters=1, num_threads=4):
+        """data_cloud: 3 x N (column = point), as Eigen::Matrix<double,3,Dynamic>; labels: N ints.
+        num_threads is accepted for source compatibility and unused (the GPU does the work)."""
+        data_cloud = np.asarray(data_cloud, dtype=np.float64)
+        assert data_cloud.shape[0] == 3
+        pts = np.ascontiguousarray(data_cloud.T)       # column-major 3xN == row-major Nx3
+        labels = np.ascontiguousarray(data_part_labels, dtype=np.int32)
+        x = self.ava.params()                          # prologue :1250-1254
+        N = pts.shape[0]
+        xs, stats, cloud = self.fitter.fit_batch(pts, labels, np.array([0, N]), x[None], self.options(icp_iters), True)
+        J = self.ava.model.numJoints()
+        self.r = [xs[0, 3 + 4 * j:7 + 4 * j].copy() for j in range(J)]
+        self.ava.set_params(xs[0])                     # :1494-1496
+        self.ava.update(self.fitter)                   # :1497
+        self.last_stats = stats[0]

@@ -1,0 +1,90 @@
+"""Synthetic smplsynth-style frames: the recipe of Avatar::randomize
+(Avatar.cpp:77-126), the optim.cpp:74-145 scenario (render -> back-project -> perturbed start) and
+the fixed 640x576 intrinsics.  Harness code: the rasteriser is host C++ (avb_synth_*), the fit is not."""
+import numpy as np
+
+from ._lib import lib, ptr, check
+
+WIDTH, HEIGHT = 640, 576
+FX = FY = 504.0
+CX, CY = 320.0, 288.0
+
+
+def _aa_quat(axis, angle):
+    axis = np.asarray(axis, dtype=np.float64)
+    return np.concatenate([np.sin(0.5 * angle) * axis, [np.cos(0.5 * angle)]])
+
+
+def _qmul(a, b):
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by + ay * bw + az * bx - ax * bz,
+                     aw * bz + az * bw + ax * by - ay * bx, aw * bw - ax * bx - ay * by - az * bz])
+
+
+def _from_spherical(rho, theta, phi):  # AvatarHelpers.cpp fromSpherical
+    return np.array([rho * np.sin(phi) * np.cos(theta), rho * np.cos(phi), rho * np.sin(phi) * np.sin(theta)])
+
+
+def random_params(model, rng, pose_scale=1.0):
+    """GT parameters x = [p | q | w] following Avatar::randomize (Avatar.cpp:84-125)."""
+    J, K = model.numJoints(), model.numShapeKeys()
+    w = rng.standard_normal(K)
+    g = model.posePrior
+    comp = rng.choice(g.nComps, p=g.weight / g.weight.sum())
+    L = np.linalg.cholesky(g.cov[comp])
+    samp = g.mean[comp] + pose_scale * (L @ rng.standard_normal(g.nDims))
+    q = [None] * J
+    for i in range(J - 1):
+        a = samp[3 * i:3 * i + 3]
+        ang = np.linalg.norm(a)
+        q[i + 1] = _aa_quat(a / ang, ang) if ang > 0 else np.array([0, 0, 0, 1.0])
+    p = np.array([rng.uniform(-1.0, 1.0), rng.uniform(-0.5, 0.5), rng.uniform(2.2, 4.5)])
+    angle_up = rng.uniform(-np.pi / 3, np.pi / 3) + np.pi
+    q_up = _aa_quat([0, 1, 0], angle_up)
+    axis_p = _from_spherical(1.0, rng.uniform(0, 2 * np.pi), rng.uniform(-np.pi / 2, np.pi / 2))
+    q_pert = _aa_quat(axis_p, rng.normal(0.0, 0.2))
+    q[0] = _qmul(q_pert, q_up)
+    return np.concatenate([p, np.concatenate(q), w])
+
+
+def perturbed_start(model, x_gt, rng, rot_sigma=0.1):
+    """optim.cpp:122-145: every rotation right-multiplied by a N(0, 0.1 rad) twist, w = 0 except w[0] = -2.5"""
+    J, K = model.numJoints(), model.numShapeKeys()
+    x = x_gt.copy()
+    for j in range(J):
+        axis = _from_spherical(1.0, rng.uniform(0, 2 * np.pi), rng.uniform(-np.pi / 2, np.pi / 2))
+        dq = _aa_quat(axis, rng.normal(0.0, rot_sigma))
+        q = _qmul(x[3 + 4 * j:7 + 4 * j], dq)
+        if q[3] < 0:
+            q = -q   # the optimize() prologue always starts from w >= 0
+        x[3 + 4 * j:7 + 4 * j] = q
+    x[3 + 4 * J:] = 0.0
+    x[3 + 4 * J] = -2.5
+    return x
+
+
+def vertex_parts(model, part_map):
+    return np.array([part_map[pairs[0][1]] for pairs in model.assignedJoints], dtype=np.int32)
+
+
+def render_cloud(model, cloud_V3, part_map, width=WIDTH, height=HEIGHT, fx=FX, fy=FY, cx=CX, cy=CY, interval=1):
+    """z-buffer render of a posed mesh, then back-projection of every `interval`-th hit pixel."""
+    cloud = np.ascontiguousarray(cloud_V3, dtype=np.float64)
+    vp = vertex_parts(model, part_map)
+    faces = np.ascontiguousarray(model.mesh, dtype=np.int32)
+    depth = np.zeros((height, width), dtype=np.float32)
+    part = np.zeros((height, width), dtype=np.uint8)
+    check(lib.avb_synth_render(ptr(cloud), cloud.shape[0], ptr(faces), faces.shape[0], ptr(vp), width, height,
+                               fx, fy, cx, cy, ptr(depth), ptr(part)))
+    return backproject(depth, part, fx, fy, cx, cy, interval) + (depth, part)
+
+
+def backproject(depth, part, fx=FX, fy=FY, cx=CX, cy=CY, interval=1):
+    h, w = depth.shape
+    cap = int((depth > 0).sum()) + 1
+    pts = np.zeros((cap, 3))
+    lab = np.zeros(cap, dtype=np.int32)
+    n = lib.avb_synth_backproject(ptr(depth), ptr(part), w, h, fx, fy, cx, cy, interval, ptr(pts), ptr(lab), cap)
+    assert n >= 0
+    return pts[:n].copy(), lab[:n].copy()

@@ -1,0 +1,197 @@
+/* avatar_b200.h -- C ABI of the B200-native SMPL-to-point-cloud fitting engine.
+ *
+ * Drop-in boundary for ONE path of sxyu/avatar: ark::AvatarOptimizer::optimize and what it
+ * calls (Avatar::update, GaussianMixture, the nanoflann correspondence search, the Ceres solve).
+ * The reference has no FFI; its boundary is the C++ class API of include/Avatar.h and
+ * include/AvatarOptimizer.h.  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference tree).  The header-compatible C++ facade
+ * (include/ark_b200/*.h) and the Python mirror (avatar_b200/*.py) are thin callers of this ABI.
+ *
+ * Conventions: int return codes (AVB_OK = 0), no exceptions cross the ABI, caller owns host
+ * buffers, the library owns device buffers, plain pointers and sizes only.  All host arrays are
+ * fp64 / int32 exactly as the reference's Eigen types hold them.
+ *
+ * There is NO CPU fallback: every compute entry point fails with AVB_ERR_CUDA when no sm_100
+ * device is usable.
+ */
+#ifndef AVATAR_B200_H_
+#define AVATAR_B200_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVB_VERSION 100
+#define AVB_MAX_ASSIGN 4 /* AvatarEvaluationCommonData::MAX_ASSIGN, AvatarOptimizer.cpp:164 */
+#define AVB_MAX_JOINTS 32
+#define AVB_MAX_SHAPE_KEYS 16
+
+enum {
+    AVB_OK = 0,
+    AVB_ERR_INVALID = 1,   /* bad argument (null pointer, sizes, labels out of range, ...) */
+    AVB_ERR_CUDA = 2,      /* CUDA runtime / driver error, or no usable device */
+    AVB_ERR_CAPACITY = 3,  /* batch / point count exceeds what the fitter was created for */
+    AVB_ERR_NUMERIC = 4,   /* non-finite input, coordinate out of range (|x| >= 32 m), GMM not PD */
+    AVB_ERR_PRIOR = 5      /* betaPose > 0 but the model has no pose prior (the reference would
+                              dereference an empty GMM here, AvatarOptimizer.cpp:1465) */
+};
+
+typedef struct avb_model avb_model;   /* ~ ark::AvatarModel (immutable, shareable) */
+typedef struct avb_fitter avb_fitter; /* ~ ark::AvatarOptimizer (+ the device side of ark::Avatar) */
+
+/* Host description of an ark::AvatarModel (include/Avatar.h:64-151), in the reference's own
+ * member layouts.  num_points=V, num_joints=J, num_shape_keys=K, num_faces=F. */
+typedef struct {
+    int32_t num_points, num_joints, num_shape_keys, num_faces;
+    const double* base_cloud;           /* AvatarModel::baseCloud            [3V]  x0 y0 z0 x1 ... */
+    const double* key_clouds;           /* AvatarModel::keyClouds  (3V x K), row 3v+c, ROW-major [3V][K] */
+    const double* joint_shape_reg_base; /* AvatarModel::jointShapeRegBase    [3J] */
+    const double* joint_shape_reg;      /* AvatarModel::jointShapeReg (3J x K), ROW-major [3J][K] */
+    const int32_t* parent;              /* AvatarModel::parent               [J], parent[0] = -1 */
+    const int32_t* mesh;                /* AvatarModel::mesh (3 x F col-major) = [F][3] vertex ids */
+    /* AvatarModel::assignedJoints as CSR: per vertex (weight, joint) sorted descending
+     * (AvatarModel.cpp:74-94); at most AVB_MAX_ASSIGN entries per vertex. */
+    const int32_t* assign_start;        /* [V+1] */
+    const int32_t* assign_joint;        /* [assign_start[V]] */
+    const double* assign_weight;        /* [assign_start[V]] */
+    /* GaussianMixture posePrior as parsed from pose_prior.txt (GaussianMixture.cpp:20-58);
+     * gmm_components <= 0 means "no prior" (hasPosePrior() == false). gmm_dims must be 3(J-1). */
+    int32_t gmm_components, gmm_dims;
+    const double* gmm_weight;           /* [C] */
+    const double* gmm_mean;             /* [C][D] */
+    const double* gmm_cov;              /* [C][D][D] */
+} avb_model_desc;
+
+typedef struct {
+    int32_t device;             /* CUDA device ordinal */
+    int32_t max_batch;          /* frames per avb_fit_batch call */
+    int64_t max_total_points;   /* sum of N over a batch */
+    int32_t num_parts;          /* AvatarOptimizer ctor: num_parts */
+    const int32_t* part_map;    /* AvatarOptimizer ctor: part_map [J] joint -> part */
+} avb_fitter_config;
+
+enum { AVB_SOLVER_GN_LM = 1 };
+enum { AVB_JTJ_FP32 = 0, AVB_JTJ_BF16_TENSOR = 1 };
+
+/* Public tunables of ark::AvatarOptimizer (include/AvatarOptimizer.h:27-39) plus the solver
+ * controls the reference hard-codes in optimize() (AvatarOptimizer.cpp:1313-1341). */
+typedef struct {
+    int32_t icp_iters;          /* optimize(..., icp_iters = 1, ...) */
+    int32_t max_iters_per_icp;  /* maxItersPerICP = 10 */
+    double beta_pose;           /* betaPose = 0.1 */
+    double beta_shape;          /* betaShape = 1.0 */
+    int32_t enable_occlusion;   /* enableOcclusion = true */
+    int32_t nn_step;            /* nnStep = 20: accepted and ignored -- it only affects the
+                                   reference's unused forward-NN mode (AvatarOptimizer.cpp:933) */
+    double function_tolerance;  /* options.function_tolerance = 1e-4 (:1333) */
+    int32_t solver;             /* AVB_SOLVER_GN_LM (BASELINE.json north_star) */
+    int32_t jtj_precision;      /* AVB_JTJ_* */
+    int32_t reserved[4];
+} avb_options;
+
+/* Per-frame fit statistics. */
+typedef struct {
+    int32_t num_points;          /* N of this frame */
+    int32_t num_correspondences; /* data points matched in the last ICP iteration */
+    int32_t num_matched_vertices;
+    int32_t iterations;          /* LM iterations executed in the last ICP iteration */
+    int32_t accepted_steps;
+    int32_t status;              /* AVB_OK or AVB_ERR_NUMERIC */
+    double initial_cost;         /* last ICP iteration */
+    double final_cost;
+} avb_stats;
+
+void avb_default_options(avb_options* out);
+const char* avb_last_error(void); /* thread-local message of the last failing call */
+int avb_device_count(void);
+
+/* replaces: ark::AvatarModel::AvatarModel (AvatarModel.cpp:14-298) -- the data, not the file I/O;
+ * the GMM maths of GaussianMixture::load (GaussianMixture.cpp:22-76) runs here. */
+int avb_model_create(const avb_model_desc* desc, avb_model** out);
+void avb_model_destroy(avb_model* model);
+int avb_model_dims(const avb_model* model, int32_t* V, int32_t* J, int32_t* K, int32_t* F);
+/* taps for tests: prec_cho [C][D][D] (row-major, lower), consts_log [C] as GaussianMixture holds them */
+int avb_model_get_prior(const avb_model* model, double* prec_cho, double* consts_log);
+
+/* replaces: ark::AvatarOptimizer::AvatarOptimizer (AvatarOptimizer.cpp:1213-1244) */
+int avb_fitter_create(const avb_model* model, const avb_fitter_config* cfg, avb_fitter** out);
+void avb_fitter_destroy(avb_fitter* fitter);
+
+/* Parameter vector of one frame: x = [ p(3) | q_0..q_{J-1} (x,y,z,w each) | w(K) ], 3+4J+K doubles:
+ * ark::Avatar::p, AvatarOptimizer::r (Eigen::Quaterniond coeffs order), ark::Avatar::w. */
+int avb_param_dim(const avb_model* model);   /* 3 + 4J + K */
+int avb_tangent_dim(const avb_model* model); /* 3 + 3J + K */
+
+/* replaces: the R -> AngleAxis -> Quaternion prologue of optimize() (AvatarOptimizer.cpp:1250-1254)
+ * and its inverse at :1494-1496.  Host-side, row-major 3x3. */
+void avb_rotmat_to_quat(const double* R_rowmajor, double* q_xyzw);
+void avb_quat_to_rotmat(const double* q_xyzw, double* R_rowmajor);
+
+/* replaces: ark::Avatar::update (Avatar.cpp:22-75) for `batch` parameter vectors.
+ * Outputs (each nullable): cloud [batch][3V], joint_pos [batch][3J], joint_trans [batch][12J]
+ * (3x4 column-major per joint, as Avatar::jointTrans). */
+int avb_avatar_update(avb_fitter* fitter, int batch, const double* x, double* cloud,
+                      double* joint_pos, double* joint_trans);
+
+/* replaces: ark::AvatarOptimizer::optimize (AvatarOptimizer.cpp:1246-1517) for one frame.
+ * data_cloud: 3 x N column-major (x0 y0 z0 x1 ...), data_part_labels: [N] in [0, num_parts).
+ * x is read as the warm start and overwritten with the fit. cloud_out (nullable): ava.cloud [3V]
+ * after the trailing ava.update() (:1497). */
+int avb_fit(avb_fitter* fitter, const double* data_cloud, const int32_t* data_part_labels, int32_t n,
+            double* x, const avb_options* opt, avb_stats* stats, double* cloud_out);
+
+/* `batch` independent frames in one call (BASELINE.json configs[2]): clouds concatenated,
+ * frame f owns points [offsets[f], offsets[f+1]).  x: [batch][3+4J+K] in/out; stats: [batch]
+ * (nullable); cloud_out: [batch][3V] (nullable).  Host buffers; for peak transfer speed allocate
+ * them with avb_host_alloc (pinned). */
+int avb_fit_batch(avb_fitter* fitter, int32_t batch, const double* data_clouds,
+                  const int32_t* data_part_labels, const int64_t* offsets, double* x,
+                  const avb_options* opt, avb_stats* stats, double* cloud_out);
+
+/* Split form of avb_fit_batch for callers that keep inputs resident on the device
+ * (bench.py `value`): upload once, fit many times from different warm starts, download. */
+int avb_upload_batch(avb_fitter* fitter, int32_t batch, const double* data_clouds,
+                     const int32_t* data_part_labels, const int64_t* offsets);
+int avb_fit_resident(avb_fitter* fitter, const double* x_in, const avb_options* opt);  /* async enqueue */
+int avb_download_results(avb_fitter* fitter, double* x_out, avb_stats* stats, double* cloud_out);
+int avb_synchronize(avb_fitter* fitter);
+/* device time of the kernels enqueued by the last avb_fit_resident, measured with CUDA events on the
+ * fitter's stream; per-kernel breakdown [pose_visibility, nn, lm, final_pose] in ms (nullable). */
+int avb_last_device_ms(avb_fitter* fitter, float* total_ms, float* per_kernel_ms4);
+/* number of kernel launches enqueued by the last avb_fit_resident / avb_fit_batch */
+int avb_last_launch_count(avb_fitter* fitter);
+
+/* pinned host memory for the host-side batches (cudaHostAlloc) */
+void* avb_host_alloc(uint64_t bytes);
+void avb_host_free(void* p);
+
+/* Parity taps (tests only; they run the same kernels the fit runs, on the uploaded batch):
+ *   AVB_TAP_VISIBLE   uint8  [batch][V]   back-face visibility (AvatarOptimizer.cpp:1349-1367)
+ *   AVB_TAP_NN        int32  [total N]    matched model vertex per data point, -1 = none (:841-920)
+ *   AVB_TAP_CLOUD     double [batch][3V]  model cloud the NN pass searched
+ *   AVB_TAP_COUNT     int32  [batch][V]   #data points matched to each vertex
+ *   AVB_TAP_SUM       double [batch][3V]  sum of the data points matched to each vertex */
+enum { AVB_TAP_VISIBLE = 1, AVB_TAP_NN = 2, AVB_TAP_CLOUD = 3, AVB_TAP_COUNT = 4, AVB_TAP_SUM = 5 };
+/* run pose+visibility+NN once at x_in on the uploaded batch (no solve) so the taps can be read */
+int avb_debug_correspond(avb_fitter* fitter, const double* x_in, const avb_options* opt);
+int avb_debug_read(avb_fitter* fitter, int what, void* out, uint64_t bytes);
+/* one evaluation of the objective at x_in with the correspondences currently on the device:
+ * cost [batch], grad [batch][P] (tangent space), H [batch][P*P] (Gauss-Newton matrix incl. priors).
+ * Mirrors one Ceres evaluation (AvatarOptimizer.cpp:283-347, 505-582, 632-639, 661-692, 708-723). */
+int avb_debug_evaluate(avb_fitter* fitter, const double* x_in, const avb_options* opt, double* cost,
+                       double* grad, double* H);
+
+/* Synthetic-data harness (host CPU code, not on the fit path): functional stand-in for
+ * AvatarRenderer::renderDepth / renderPartMask (AvatarRenderer.cpp:72-216) and the depth ->
+ * cloud back-projection of optim.cpp:104-120 / demo.cpp:226-250 (float arithmetic, y negated). */
+int avb_synth_render(const double* cloud, int32_t V, const int32_t* faces, int32_t F,
+                     const int32_t* vertex_part, int32_t width, int32_t height, float fx, float fy,
+                     float cx, float cy, float* depth_out, uint8_t* part_out);
+int64_t avb_synth_backproject(const float* depth, const uint8_t* part, int32_t width, int32_t height,
+                              float fx, float fy, float cx, float cy, int32_t interval,
+                              double* cloud_out, int32_t* labels_out, int64_t max_points);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVATAR_B200_H_ */

@@ -1,0 +1,214 @@
+"""ctypes wrapper of oracle/libavatar_oracle.so -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The product (avatar_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libavatar_oracle.so")
+REF_NANOFLANN_PATH = os.path.join(_HERE, "_ref", "libref_nanoflann.so")
+
+SOLVER_BFGS_WOLFE, SOLVER_GN_LM = 0, 1
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+class Options(C.Structure):
+    _fields_ = [("icp_iters", C.c_int32), ("max_iters_per_icp", C.c_int32), ("beta_pose", C.c_double),
+                ("beta_shape", C.c_double), ("enable_occlusion", C.c_int32), ("solver", C.c_int32),
+                ("function_tolerance", C.c_double), ("num_threads", C.c_int32), ("nn_method", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("num_correspondences", C.c_int32), ("iterations", C.c_int32), ("evaluations", C.c_int32),
+                ("accepted_steps", C.c_int32), ("initial_cost", C.c_double), ("final_cost", C.c_double),
+                ("seconds", C.c_double)]
+
+
+def default_options(solver=SOLVER_GN_LM):
+    return Options(1, 10, 0.1, 1.0, 1, solver, 1e-4, 4, 1)
+
+
+if not os.path.exists(LIB_PATH):
+    build()
+_lib = C.CDLL(LIB_PATH)
+_P = C.c_void_p
+_sig = {
+    "orc_model_create": (_P, [C.c_int] * 4 + [_P] * 6),
+    "orc_model_destroy": (None, [_P]),
+    "orc_model_set_prior": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
+    "orc_model_load_prior_text": (C.c_int, [_P, C.c_char_p]),
+    "orc_model_get_joint_reg": (None, [_P, _P, _P, _P]),
+    "orc_model_get_assigned": (C.c_int, [_P, _P, _P, _P]),
+    "orc_model_get_prior": (None, [_P, _P, _P]),
+    "orc_avatar_update": (None, [_P] * 7),
+    "orc_rotmat_to_quat": (None, [_P, _P]),
+    "orc_quat_to_rotmat": (None, [_P, _P]),
+    "orc_gmm_residual": (C.c_int, [_P, _P, _P]),
+    "orc_optimizer_create": (_P, [_P, C.c_int, _P]),
+    "orc_optimizer_destroy": (None, [_P]),
+    "orc_visibility": (None, [_P, _P, _P]),
+    "orc_find_nn": (None, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "orc_evaluate": (C.c_double, [_P, _P, _P, _P, C.c_int, C.c_double, C.c_double, C.c_int, _P, _P]),
+    "orc_vertex_jacobian": (None, [_P, _P, C.c_int, _P, _P]),
+    "orc_vertex_position_chain": (None, [_P, _P, C.c_int, _P]),
+    "orc_retract": (None, [_P, _P, _P, _P]),
+    "orc_optimize": (C.c_int, [_P, _P, _P, C.c_int, _P, C.POINTER(Options), C.POINTER(Stats), _P, C.c_int,
+                               C.POINTER(C.c_int), _P]),
+    "orc_param_dim": (C.c_int, [_P]),
+    "orc_tangent_dim": (C.c_int, [_P]),
+}
+for _n, (_r, _a) in _sig.items():
+    getattr(_lib, _n).restype = _r
+    getattr(_lib, _n).argtypes = _a
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class OracleModel:
+    """ark::AvatarModel restated (npz branch)."""
+
+    def __init__(self, npz_path, prior=None):
+        z = np.load(npz_path)
+        vt, sd = _f64(z["v_template"]), _f64(z["shapedirs"])
+        jr, wt = _f64(z["J_regressor"]), _f64(z["weights"])
+        parents = np.ascontiguousarray(z["kintree_table"][0].astype(np.uint32).astype(np.int32))
+        faces = np.ascontiguousarray(np.asarray(z["f"]).astype(np.int64).astype(np.int32))
+        self.V, self.J, self.K, self.F = vt.shape[0], parents.shape[0], sd.shape[2], faces.shape[0]
+        self.faces, self.parents = faces, parents
+        self.h = _lib.orc_model_create(self.V, self.J, self.K, self.F, _p(vt), _p(sd), _p(jr), _p(wt), _p(parents),
+                                       _p(faces))
+        self.C = self.D = 0
+        if prior is not None:
+            w, mu, cov = (_f64(prior[k]) for k in ("weights", "means", "covs"))
+            self.C, self.D = mu.shape
+            assert _lib.orc_model_set_prior(self.h, self.C, self.D, _p(w), _p(mu), _p(cov)) == 0
+
+    def load_prior_text(self, path, C_, D_):
+        rc = _lib.orc_model_load_prior_text(self.h, path.encode())
+        self.C, self.D = C_, D_
+        return rc
+
+    def joint_reg(self):
+        base, reg, init = np.zeros(3 * self.J), np.zeros((3 * self.J, self.K)), np.zeros(3 * self.J)
+        _lib.orc_model_get_joint_reg(self.h, _p(base), _p(reg), _p(init))
+        return base, reg, init
+
+    def assigned(self):
+        n = _lib.orc_model_get_assigned(self.h, None, None, None)
+        start, joint, weight = np.zeros(self.V + 1, np.int32), np.zeros(n, np.int32), np.zeros(n)
+        _lib.orc_model_get_assigned(self.h, _p(start), _p(joint), _p(weight))
+        return start, joint, weight
+
+    def prior(self):
+        pc, cl = np.zeros((self.C, self.D, self.D)), np.zeros(self.C)
+        _lib.orc_model_get_prior(self.h, _p(pc), _p(cl))
+        return pc, cl
+
+    def gmm_residual(self, x):
+        out = np.zeros(self.D + 1)
+        comp = _lib.orc_gmm_residual(self.h, _p(_f64(x)), _p(out))
+        return out, comp
+
+    def update(self, p, R, w):
+        """Avatar::update: R (J,3,3). returns cloud (V,3), jointPos (J,3), jointTrans (J,12)"""
+        cloud, jp, jt = np.zeros((self.V, 3)), np.zeros((self.J, 3)), np.zeros((self.J, 12))
+        _lib.orc_avatar_update(self.h, _p(_f64(p)), _p(_f64(R)), _p(_f64(w)), _p(cloud), _p(jp), _p(jt))
+        return cloud, jp, jt
+
+    def update_x(self, x):
+        J = self.J
+        R = np.stack([quat_to_rotmat(x[3 + 4 * j:7 + 4 * j]) for j in range(J)])
+        return self.update(x[:3], R, x[3 + 4 * J:])
+
+
+def rotmat_to_quat(R):
+    q = np.zeros(4)
+    _lib.orc_rotmat_to_quat(_p(_f64(R)), _p(q))
+    return q
+
+
+def quat_to_rotmat(q):
+    R = np.zeros((3, 3))
+    _lib.orc_quat_to_rotmat(_p(_f64(q)), _p(R))
+    return R
+
+
+class OracleOptimizer:
+    """ark::AvatarOptimizer restated."""
+
+    def __init__(self, model, num_parts, part_map):
+        self.model = model
+        self.part_map = np.ascontiguousarray(part_map, dtype=np.int32)
+        self.h = _lib.orc_optimizer_create(model.h, num_parts, _p(self.part_map))
+        self.nx, self.P = _lib.orc_param_dim(self.h), _lib.orc_tangent_dim(self.h)
+
+    def visibility(self, cloud):
+        vis = np.zeros(self.model.V, dtype=np.uint8)
+        _lib.orc_visibility(self.h, _p(_f64(cloud)), _p(vis))
+        return vis
+
+    def find_nn(self, cloud, vis, data, labels, method=0):
+        data, labels = _f64(data), np.ascontiguousarray(labels, dtype=np.int32)
+        idx = np.zeros(data.shape[0], dtype=np.int32)
+        _lib.orc_find_nn(self.h, _p(_f64(cloud)), _p(np.ascontiguousarray(vis, dtype=np.uint8)), _p(data), _p(labels),
+                         data.shape[0], method, _p(idx))
+        return idx
+
+    def evaluate(self, x, data, idx, beta_pose=0.1, beta_shape=1.0, want_H=True, num_threads=1):
+        data, idx = _f64(data), np.ascontiguousarray(idx, dtype=np.int32)
+        grad = np.zeros(self.P)
+        H = np.zeros((self.P, self.P)) if want_H else None
+        cost = _lib.orc_evaluate(self.h, _p(_f64(x)), _p(data), _p(idx), data.shape[0], beta_pose, beta_shape,
+                                 num_threads, _p(grad), _p(H))
+        return cost, grad, H
+
+    def vertex_jacobian(self, x, v):
+        pos, jac = np.zeros(3), np.zeros((3, self.P))
+        _lib.orc_vertex_jacobian(self.h, _p(_f64(x)), v, _p(pos), _p(jac))
+        return pos, jac
+
+    def vertex_position_chain(self, x, v):
+        pos = np.zeros(3)
+        _lib.orc_vertex_position_chain(self.h, _p(_f64(x)), v, _p(pos))
+        return pos
+
+    def retract(self, x, delta):
+        xp = np.zeros(self.nx)
+        _lib.orc_retract(self.h, _p(_f64(x)), _p(_f64(delta)), _p(xp))
+        return xp
+
+    def optimize(self, data, labels, x, opt, trace_cap=0):
+        data, labels = _f64(data), np.ascontiguousarray(labels, dtype=np.int32)
+        x = np.array(x, dtype=np.float64, copy=True)
+        st = Stats()
+        trace = np.zeros((max(trace_cap, 1), self.nx))
+        tl = C.c_int(0)
+        nn = np.zeros(data.shape[0], dtype=np.int32)
+        _lib.orc_optimize(self.h, _p(data), _p(labels), data.shape[0], _p(x), C.byref(opt), C.byref(st),
+                          _p(trace) if trace_cap else None, trace_cap, C.byref(tl), _p(nn))
+        return x, st, trace[:tl.value], nn
+
+
+def ref_nanoflann_nn(points, queries):
+    """exact 1-NN through the reference's own vendored nanoflann (oracle/_ref); None if not built"""
+    if not os.path.exists(REF_NANOFLANN_PATH):
+        return None
+    lib = C.CDLL(REF_NANOFLANN_PATH)
+    lib.ref_nanoflann_nn.argtypes = [_P, C.c_int, _P, C.c_int, _P]
+    points, queries = _f64(points), _f64(queries)
+    out = np.zeros(queries.shape[0], dtype=np.int32)
+    lib.ref_nanoflann_nn(_p(points), points.shape[0], _p(queries), queries.shape[0], _p(out))
+    return out
