@@ -1,0 +1,39 @@
+"""Multi-GPU plumbing: independent frames shard one contiguous block per rank (no data-path collective);
+a single all_gather of the fitted parameters at the end (NCCL on GPUs, gloo in the CPU tests)."""
+import numpy as np
+
+
+def frame_range(n_frames, rank, world):
+    """contiguous, balanced block of frames for this rank"""
+    base, rem = divmod(n_frames, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_params(local, n_frames, rank, world, device=None):
+    """all_gather of [frames_per_rank, nx] float64 (padded to equal size) -> [n_frames, nx] on every rank"""
+    import torch
+    import torch.distributed as dist
+    nx = local.shape[1]
+    per = (n_frames + world - 1) // world
+    buf = torch.zeros((per, nx), dtype=torch.float64, device=device)
+    buf[:local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local)).to(buf.device)
+    out = [torch.zeros_like(buf) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(out, buf)
+    else:
+        out = [buf]
+    rows = []
+    for r in range(world):
+        lo, hi = frame_range(n_frames, r, world)
+        rows.append(out[r][:hi - lo].cpu().numpy())
+    return np.concatenate(rows, axis=0)
+
+
+def max_over_ranks(value, device=None):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
