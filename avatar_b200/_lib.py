@@ -69,6 +69,8 @@ SYMBOLS = [
     ("avb_download_results", C.c_int, [_P, _P, _P, _P]),
     ("avb_synchronize", C.c_int, [_P]),
     ("avb_last_device_ms", C.c_int, [_P, C.POINTER(C.c_float), _P]),
+    ("avb_timer_start", C.c_int, [_P]),
+    ("avb_timer_stop", C.c_int, [_P, C.POINTER(C.c_float)]),
     ("avb_last_launch_count", C.c_int, [_P]),
     ("avb_host_alloc", _P, [C.c_uint64]),
     ("avb_host_free", None, [_P]),
@@ -81,6 +83,7 @@ SYMBOLS = [
                                           C.c_int32, _P, _P, C.c_int64]),
 ]
 
+JTJ_FP64, JTJ_FP32, JTJ_BF16_TENSOR = 0, 1, 2
 TAP_VISIBLE, TAP_NN, TAP_CLOUD, TAP_COUNT, TAP_SUM = 1, 2, 3, 4, 5
 
 if not os.path.exists(LIB_PATH):

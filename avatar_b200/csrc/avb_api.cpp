@@ -239,7 +239,7 @@ void avb_default_options(avb_options* o) {
     o->nn_step = 20;             // AvatarOptimizer.h:33 (unused by the inverted NN mode)
     o->function_tolerance = 1e-4;  // AvatarOptimizer.cpp:1333
     o->solver = AVB_SOLVER_GN_LM;
-    o->jtj_precision = AVB_JTJ_FP32;
+    o->jtj_precision = AVB_JTJ_FP64;
 }
 
 int avb_device_count(void) {
@@ -653,7 +653,8 @@ int check_options(const avb_fitter* ft, const avb_options* o) {
     if (!o) return fail(AVB_ERR_INVALID, "null options");
     if (o->icp_iters < 0 || o->max_iters_per_icp < 0) return fail(AVB_ERR_INVALID, "negative iteration count");
     if (o->solver != AVB_SOLVER_GN_LM) return fail(AVB_ERR_INVALID, "unknown solver");
-    if (o->jtj_precision != AVB_JTJ_FP32) return fail(AVB_ERR_INVALID, "jtj_precision: only AVB_JTJ_FP32 is implemented");
+    if (o->jtj_precision != AVB_JTJ_FP64 && o->jtj_precision != AVB_JTJ_FP32)
+        return fail(AVB_ERR_INVALID, "jtj_precision: AVB_JTJ_FP64 and AVB_JTJ_FP32 are implemented");
     if (o->beta_pose > 0.0 && ft->model->gmmC <= 0)
         return fail(AVB_ERR_PRIOR, "betaPose > 0 but the model has no pose prior");
     return AVB_OK;
@@ -675,12 +676,13 @@ PoseArgs pose_args(avb_fitter* ft, const double* dx, bool vis, const avb_options
     return a;
 }
 
-int enqueue_correspond(avb_fitter* ft, const double* dx, const avb_options* o) {
+int enqueue_correspond(avb_fitter* ft, const double* dx, const avb_options* o, cudaEvent_t after_pose) {
     cudaStream_t st = ft->stream;
     const int B = ft->batch, V = ft->model->V;
     PoseArgs pa = pose_args(ft, dx, true, o);
     CUDA_TRY(launch_pose_visibility(ft->dm, ft->dp, pa, B, st));
     ++ft->launches;
+    if (after_pose) CUDA_TRY(cudaEventRecord(after_pose, st));
     CUDA_TRY(cudaMemsetAsync(ft->d_cnt, 0, (size_t)B * V * 4, st));
     CUDA_TRY(cudaMemsetAsync(ft->d_sum, 0, (size_t)B * V * 24, st));
     CUDA_TRY(cudaMemsetAsync(ft->d_range, 0, (size_t)B * 4, st));
@@ -741,19 +743,20 @@ int avb_fit_resident(avb_fitter* ft, const double* x_in, const avb_options* o) {
     CUDA_TRY(cudaEventRecord(ft->ev[0], st));
     for (int icp = 0; icp < o->icp_iters; ++icp) {
         const bool timed = (icp == o->icp_iters - 1);
-        rc = enqueue_correspond(ft, ft->d_x, o);
-        if (rc != AVB_OK) return rc;
         if (timed) CUDA_TRY(cudaEventRecord(ft->ev[1], st));
+        rc = enqueue_correspond(ft, ft->d_x, o, timed ? ft->ev[2] : nullptr);
+        if (rc != AVB_OK) return rc;
+        if (timed) CUDA_TRY(cudaEventRecord(ft->ev[3], st));
         LmArgs la = lm_args(ft, ft->d_x, o);
-        CUDA_TRY(launch_lm(ft->dm, ft->dp, la, B, st));
+        CUDA_TRY(launch_lm(ft->dm, ft->dp, la, B, o->jtj_precision == AVB_JTJ_FP64, st));
         ++ft->launches;
-        if (timed) CUDA_TRY(cudaEventRecord(ft->ev[2], st));
+        if (timed) CUDA_TRY(cudaEventRecord(ft->ev[4], st));
     }
     // trailing ava.update() (AvatarOptimizer.cpp:1497)
     PoseArgs pa = pose_args(ft, ft->d_x, false, o);
     CUDA_TRY(launch_pose_visibility(ft->dm, ft->dp, pa, B, st));
     ++ft->launches;
-    CUDA_TRY(cudaEventRecord(ft->ev[3], st));
+    CUDA_TRY(cudaEventRecord(ft->ev[5], st));
     return AVB_OK;
 }
 
@@ -767,18 +770,32 @@ int avb_synchronize(avb_fitter* ft) {
 int avb_last_device_ms(avb_fitter* ft, float* total_ms, float* per4) {
     if (!ft) return fail(AVB_ERR_INVALID, "null fitter");
     CUDA_TRY(cudaSetDevice(ft->device));
-    CUDA_TRY(cudaEventSynchronize(ft->ev[3]));
-    if (total_ms) CUDA_TRY(cudaEventElapsedTime(total_ms, ft->ev[0], ft->ev[3]));
+    CUDA_TRY(cudaEventSynchronize(ft->ev[5]));
+    if (total_ms) CUDA_TRY(cudaEventElapsedTime(total_ms, ft->ev[0], ft->ev[5]));
     if (per4) {
         per4[0] = per4[1] = per4[2] = per4[3] = 0.f;
         if (ft->last_icp > 0) {
-            float a = 0, b = 0, c = 0;
-            CUDA_TRY(cudaEventElapsedTime(&a, ft->ev[0], ft->ev[1]));  // pose+vis+nn (all but last ICP's LM)
-            CUDA_TRY(cudaEventElapsedTime(&b, ft->ev[1], ft->ev[2]));
-            CUDA_TRY(cudaEventElapsedTime(&c, ft->ev[2], ft->ev[3]));
-            per4[0] = a; per4[1] = 0.f; per4[2] = b; per4[3] = c;
+            CUDA_TRY(cudaEventElapsedTime(&per4[0], ft->ev[1], ft->ev[2]));
+            CUDA_TRY(cudaEventElapsedTime(&per4[1], ft->ev[2], ft->ev[3]));
+            CUDA_TRY(cudaEventElapsedTime(&per4[2], ft->ev[3], ft->ev[4]));
+            CUDA_TRY(cudaEventElapsedTime(&per4[3], ft->ev[4], ft->ev[5]));
         }
     }
+    return AVB_OK;
+}
+
+int avb_timer_start(avb_fitter* ft) {
+    if (!ft) return fail(AVB_ERR_INVALID, "null fitter");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    CUDA_TRY(cudaEventRecord(ft->ev[6], ft->stream));
+    return AVB_OK;
+}
+int avb_timer_stop(avb_fitter* ft, float* ms) {
+    if (!ft || !ms) return fail(AVB_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    CUDA_TRY(cudaEventRecord(ft->ev[7], ft->stream));
+    CUDA_TRY(cudaEventSynchronize(ft->ev[7]));
+    CUDA_TRY(cudaEventElapsedTime(ms, ft->ev[6], ft->ev[7]));
     return AVB_OK;
 }
 
@@ -857,7 +874,7 @@ int avb_debug_correspond(avb_fitter* ft, const double* x_in, const avb_options* 
     const size_t nx = ft->model->nx;
     CUDA_TRY(cudaMemcpyAsync(ft->d_xdbg, x_in, (size_t)ft->batch * nx * 8, cudaMemcpyHostToDevice, ft->stream));
     ft->launches = 0;
-    rc = enqueue_correspond(ft, ft->d_xdbg, o);
+    rc = enqueue_correspond(ft, ft->d_xdbg, o, nullptr);
     if (rc != AVB_OK) return rc;
     CUDA_TRY(cudaStreamSynchronize(ft->stream));
     return AVB_OK;
@@ -910,7 +927,7 @@ int avb_debug_evaluate(avb_fitter* ft, const double* x_in, const avb_options* o,
     la.dump_cost = ft->d_dump_cost;
     la.dump_grad = ft->d_dump_grad;
     la.dump_H = ft->d_dump_H;
-    CUDA_TRY(launch_lm(ft->dm, ft->dp, la, (int)B, st));
+    CUDA_TRY(launch_lm(ft->dm, ft->dp, la, (int)B, o->jtj_precision == AVB_JTJ_FP64, st));
     CUDA_TRY(cudaMemcpyAsync(cost, ft->d_dump_cost, B * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(grad, ft->d_dump_grad, B * P * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(H, ft->d_dump_H, B * P * P * 8, cudaMemcpyDeviceToHost, st));

@@ -524,6 +524,9 @@ __device__ __forceinline__ double vertex_rows(const DevModel& M, const Tables& T
 }
 
 // Objective at xs: fills S.Hs (P x P, reference tangent coordinates, priors included), S.gs, returns cost.
+// AccT = double: J^T J accumulated in fp64 from the fp32 Jacobian rows (default, parity path);
+// AccT = float : fp32 accumulation (AVB_JTJ_FP32, faster, ~1e-4 parameter drift over 10 iterations).
+template <typename AccT>
 __device__ double lm_evaluate(const DevModel& M, const DevParts& Pt, const LmArgs& a, LmSmem& S, const double* xs,
                               int f, double Qsum, double sbp, double sbs) {
     const int tid = threadIdx.x, P = M.P, J = M.J, K = M.K;
@@ -562,11 +565,11 @@ __device__ double lm_evaluate(const DevModel& M, const DevParts& Pt, const LmArg
         // gradient role: (column, row chunk)
         const int nch = kLmThreads / Lp;
         const int gcol = tid % Lp, gch = tid / Lp;
-        float acc[8][8];
+        AccT acc[8][8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+            for (int j = 0; j < 8; ++j) acc[i][j] = AccT(0);
         double gacc = 0.0;
 
         const int mbeg = S.gcount[g], mend = S.gcount[g + 1];
@@ -590,12 +593,14 @@ __device__ double lm_evaluate(const DevModel& M, const DevParts& Pt, const LmArg
                     const float4 a1 = *reinterpret_cast<const float4*>(Ab + (size_t)r * lda + 4);
                     const float4 b0 = *reinterpret_cast<const float4*>(Bb + (size_t)r * lda);
                     const float4 b1 = *reinterpret_cast<const float4*>(Bb + (size_t)r * lda + 4);
-                    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    const AccT av[8] = {AccT(a0.x), AccT(a0.y), AccT(a0.z), AccT(a0.w),
+                                        AccT(a1.x), AccT(a1.y), AccT(a1.z), AccT(a1.w)};
+                    const AccT bv[8] = {AccT(b0.x), AccT(b0.y), AccT(b0.z), AccT(b0.w),
+                                        AccT(b1.x), AccT(b1.y), AccT(b1.z), AccT(b1.w)};
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                        for (int j = 0; j < 8; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
                 }
             }
             // step 2b: gradient J^T r in fp64
@@ -779,6 +784,7 @@ __device__ void warp_chol_solve(const double* L, int P, double* b) {
     }
 }
 
+template <typename AccT>
 __global__ void __launch_bounds__(kLmThreads, 1)
 lm_fit_kernel(DevModel M, DevParts Pt, LmArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -844,7 +850,7 @@ lm_fit_kernel(DevModel M, DevParts Pt, LmArgs a) {
     const double sbp = a.beta_pose * sqrt((double)ncorr) / 15.0;
     const double sbs = a.beta_shape * sqrt((double)ncorr) / 15.0;
 
-    double cost = lm_evaluate(M, Pt, a, S, S.xs, f, Qsum, sbp, sbs);
+    double cost = lm_evaluate<AccT>(M, Pt, a, S, S.xs, f, Qsum, sbp, sbs);
     for (int i = tid; i < P * P; i += kLmThreads) Hcur[i] = S.Hs[i];
     for (int i = tid; i < P; i += kLmThreads) S.gcur[i] = S.gs[i];
     __syncthreads();
@@ -917,7 +923,7 @@ lm_fit_kernel(DevModel M, DevParts Pt, LmArgs a) {
                 }
             }
             __syncthreads();
-            const double cost_t = lm_evaluate(M, Pt, a, S, S.xt, f, Qsum, sbp, sbs);
+            const double cost_t = lm_evaluate<AccT>(M, Pt, a, S, S.xt, f, Qsum, sbp, sbs);
             const double rho = (cost - cost_t) / model_change;
             if (isfinite(cost_t) && rho > 1e-3) {
                 acc = true;
@@ -984,26 +990,26 @@ cudaError_t launch_pose_visibility(const DevModel& M, const DevParts& Pt, const 
 }
 
 cudaError_t launch_nn(const DevParts& Pt, const NNArgs& a, int num_chunks, cudaStream_t st) {
-    static bool configured = false;
     const size_t smem = (((size_t)a.V * 24 + 15) & ~(size_t)15) + 128;
-    if (!configured) {
+    {   // per device/context attribute: set on every launch (cheap host call)
         cudaError_t e = cudaFuncSetAttribute(nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     if (num_chunks > 0) nn_kernel<<<num_chunks, 512, smem, st>>>(Pt, a);
     return cudaGetLastError();
 }
 
-cudaError_t launch_lm(const DevModel& M, const DevParts& Pt, const LmArgs& a, int batch, cudaStream_t st) {
-    static bool configured = false;
+cudaError_t launch_lm(const DevModel& M, const DevParts& Pt, const LmArgs& a, int batch, bool acc64, cudaStream_t st) {
     const size_t smem = lm_smem_bytes(M.V, M.J, M.K, M.gmmC);
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(lm_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e = acc64 ? cudaFuncSetAttribute(lm_fit_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : cudaFuncSetAttribute(lm_fit_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
-    lm_fit_kernel<<<batch, kLmThreads, smem, st>>>(M, Pt, a);
+    if (acc64)
+        lm_fit_kernel<double><<<batch, kLmThreads, smem, st>>>(M, Pt, a);
+    else
+        lm_fit_kernel<float><<<batch, kLmThreads, smem, st>>>(M, Pt, a);
     return cudaGetLastError();
 }
 

@@ -61,6 +61,6 @@ struct LmArgs {
 size_t pose_smem_bytes(int V, int J, int K);
 cudaError_t launch_pose_visibility(const DevModel& M, const DevParts& Pt, const PoseArgs& a, int batch, cudaStream_t st);
 cudaError_t launch_nn(const DevParts& Pt, const NNArgs& a, int num_chunks, cudaStream_t st);
-cudaError_t launch_lm(const DevModel& M, const DevParts& Pt, const LmArgs& a, int batch, cudaStream_t st);
+cudaError_t launch_lm(const DevModel& M, const DevParts& Pt, const LmArgs& a, int batch, bool acc64, cudaStream_t st);
 
 }  // namespace avb

@@ -115,6 +115,17 @@ class Fitter:
         check(lib.avb_last_device_ms(self.handle, C.byref(tot), per))
         return tot.value, list(per)
 
+    def timer_start(self):
+        check(lib.avb_timer_start(self.handle))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(lib.avb_timer_stop(self.handle, C.byref(ms)))
+        return ms.value
+
+    def synchronize(self):
+        check(lib.avb_synchronize(self.handle))
+
     def launch_count(self):
         return lib.avb_last_launch_count(self.handle)
 

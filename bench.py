@@ -1,0 +1,341 @@
+#!/usr/bin/env python3
+"""bench.py -- SMPL fit frames/sec on synthetic 640x576 smplsynth-style clouds (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU algorithm (oracle port) on host cores
+
+A "step" is one pass of the hot path (AvatarOptimizer::optimize, icp_iters=1, 10 solver iterations) over one
+batch of independent synthetic frames (BASELINE.json configs[2]: 512-frame batch).  Scaling is weak: every rank
+fits its own 512 frames; no data-path collective; one NCCL all_gather of the fitted parameters per step.
+`value` times the fit with inputs already resident in HBM (CUDA events on the fitter's stream);
+`e2e` times the public call avb_fit_batch with pinned HOST buffers (H2D of clouds/labels/params, fit, D2H of
+parameters and statistics, and the NCCL gather) by wall clock around synchronised steps.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+METRIC = "SMPL fit frames/sec (640x576 synth cloud, 10 GN iters)"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def make_model():
+    from avatar_b200 import AvatarModel, GaussianMixture
+    pr = np.load(os.path.join(GOLD, "prior_synth.npz"))
+    g = GaussianMixture.from_arrays(pr["weights"], pr["means"], pr["covs"])
+    return AvatarModel(npz_path=os.path.join(GOLD, "model_synth.npz"), pose_prior=g), pr
+
+
+def gen_params(model, seeds):
+    from avatar_b200 import synth
+    xg, x0 = [], []
+    for s in seeds:
+        rng = np.random.default_rng(100000 + int(s))
+        g = synth.random_params(model, rng)
+        xg.append(g)
+        x0.append(synth.perturbed_start(model, g, rng))
+    return np.stack(xg), np.stack(x0)
+
+
+def render_frames(model, part_map, clouds_gt):
+    from avatar_b200 import synth
+    pts, labs = [], []
+    for c in clouds_gt:
+        p, l, _, _ = synth.render_cloud(model, c, part_map)
+        pts.append(p)
+        labs.append(l)
+    off = np.cumsum([0] + [len(p) for p in pts]).astype(np.int64)
+    return pts, labs, off
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                mx = float(f[2])
+                if t0 <= t <= t1 + 0.1:
+                    sm.append(float(f[1]))
+                    for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                        if val.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def pinned_array(lib, shape, dtype):
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = lib.avb_host_alloc(max(n, 8))
+    if not p:
+        raise RuntimeError("avb_host_alloc failed")
+    buf = (C.c_char * max(n, 8)).from_address(p)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+def cpu_reference_run(om_mod, oopt, frames, x0, solver, ftol, nthreads, repeat=1):
+    """fit `frames` with the CPU oracle, frame-parallel over `nthreads` host threads (ctypes releases the GIL);
+    returns wall seconds"""
+    pts, labs = frames
+    n = len(pts)
+    opts = om_mod.default_options(solver)
+    opts.function_tolerance = ftol
+    opts.num_threads = 1
+    nxt = [0]
+    lock = threading.Lock()
+
+    def work():
+        while True:
+            with lock:
+                i = nxt[0]
+                nxt[0] += 1
+            if i >= n * repeat:
+                return
+            oopt.optimize(pts[i % n], labs[i % n], x0[i % n], opts)
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work) for _ in range(nthreads)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU algorithm (BFGS line search, AvatarOptimizer.cpp:1313-1341)
+    restated in oracle/ (the reference binary cannot be built: Eigen/Ceres/OpenCV/Boost absent), on all host
+    threads, same synthetic frames and options."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    model, pr = make_model()
+    om = orc.OracleModel(os.path.join(GOLD, "model_synth.npz"), pr)
+    oo = orc.OracleOptimizer(om, int(pr["num_parts"]), pr["part_map"])
+    cores = os.cpu_count() or 1
+    nsample = max(cores, min(2 * cores, 32))
+    xg, x0 = gen_params(model, range(nsample))
+    clouds = [om.update_x(x)[0] for x in xg]
+    pts, labs, off = render_frames(model, pr["part_map"], clouds)
+    for _ in range(max(args.warmup, 1) - 1):
+        cpu_reference_run(orc, oo, (pts[:cores], labs[:cores]), x0, orc.SOLVER_BFGS_WOLFE, 1e-4, cores)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_reference_run(orc, oo, (pts, labs), x0, orc.SOLVER_BFGS_WOLFE, 1e-4, cores)
+    value = nsample * args.steps / t
+    sample = (f"{nsample} of the 512 synthetic frames per step, frame-parallel over {cores} host threads, "
+              "oracle bfgs_wolfe (Ceres-1.14-style BFGS + Wolfe/cubic line search), reference defaults "
+              "(icp_iters=1, maxItersPerICP=10, function_tolerance=1e-4)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "512-frame synthetic batch per GPU, 640x576 smplsynth-style clouds, "
+                                   "icp_iters=1, 10 solver iterations", "frames_per_step_sample": nsample,
+                       "mean_points_per_frame": float(np.mean(np.diff(off)))},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=512, help="frames per GPU per step")
+    ap.add_argument("--jtj", default="fp64", choices=["fp64", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from avatar_b200 import Fitter, default_options, shard, _lib
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model, pr = make_model()
+    part_map, num_parts = pr["part_map"], int(pr["num_parts"])
+    F = args.frames
+    nx = 3 + 4 * model.numJoints() + model.numShapeKeys()
+
+    # ---- synthetic frames of this rank (weak scaling: distinct seeds per rank) ----
+    xg, x0 = gen_params(model, range(rank * F, (rank + 1) * F))
+    pose_ft = Fitter(model, num_parts, part_map, F, 16, local_rank)
+    clouds_gt, _, _ = pose_ft.avatar_update(xg)
+    pose_ft.close()
+    pts, labs, off = render_frames(model, part_map, clouds_gt)
+    total = int(off[-1])
+    h_pts = pinned_array(_lib.lib, (total, 3), np.float64)
+    h_lab = pinned_array(_lib.lib, (total,), np.int32)
+    h_x = pinned_array(_lib.lib, (F, nx), np.float64)
+    h_pts[:] = np.concatenate(pts)
+    h_lab[:] = np.concatenate(labs)
+    ft = Fitter(model, num_parts, part_map, F, total + 16, local_rank)
+    opt = default_options()
+    opt.function_tolerance = 0.0      # run all 10 LM iterations: no early exit inside the timed region
+    opt.jtj_precision = _lib.JTJ_FP64 if args.jtj == "fp64" else _lib.JTJ_FP32
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ft.synchronize()
+
+    # ---- value: inputs resident in HBM ----
+    ft.upload(h_pts, h_lab, off)
+    for _ in range(args.warmup):
+        ft.fit_resident(x0, opt)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t0 = time.perf_counter()
+    ft.timer_start()
+    for _ in range(args.steps):
+        ft.fit_resident(x0, opt)
+    dev_ms = ft.timer_stop()
+    barrier()
+    t1 = time.perf_counter()
+    launches_per_step = ft.launch_count()
+    step_ms, per4 = ft.device_ms()
+    xr, stats, _ = ft.download()
+    dev_ms = shard.max_over_ranks(dev_ms, dev)
+    value = F * world * args.steps / (dev_ms * 1e-3)
+
+    # ---- e2e: host buffers in, parameters out, through the public batch call ----
+    def e2e_step():
+        h_x[:] = x0
+        x, st, _ = ft.fit_batch(h_pts, h_lab, off, h_x, opt)
+        full = shard.gather_params(x, F * world, rank, world, dev) if world > 1 else x
+        return full, st
+    e2e_step()
+    barrier()
+    t2 = time.perf_counter()
+    for _ in range(args.steps):
+        full, st = e2e_step()
+    barrier()
+    t3 = time.perf_counter()
+    e2e_s = shard.max_over_ranks(t3 - t2, dev)
+    e2e_value = F * world * args.steps / e2e_s
+    clocks = sampler.stop(t0, t3) if sampler else None
+    h2d = total * 24 + total * 4 + F * nx * 8 + (F + 1) * 8
+    d2h = F * nx * 8 + F * 40
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    iters = np.array([s.iterations for s in stats])
+    ncorr = np.array([s.num_correspondences for s in stats])
+    nmatch = np.array([s.num_matched_vertices for s in stats])
+    npts = np.diff(off)
+    # ---- roofline of the dominant kernel (share of the step from CUDA events of the last timed step) ----
+    names = ["pose_visibility_kernel", "nn_kernel", "lm_fit_kernel", "pose_visibility_kernel(final)"]
+    dom = int(np.argmax(per4))
+    V, K = model.numPoints(), model.numShapeKeys()
+    evals = float(np.mean(iters)) + 1.0
+    alg_bytes = {
+        # cloud write + compacted copy + visibility bytes, per frame
+        0: F * (24 * V + 24 * V + V),
+        # data 24 B + label 4 B read, index 4 B written per point; compacted model cloud read once per frame
+        1: 32.0 * total + F * 24.0 * V * 0.5,
+        # per evaluation and matched vertex: count 4 + sum 24 + v_template 24 + shapedirs 12K*... + skin 37
+        2: float(np.sum(nmatch)) * evals * (4 + 24 + 24 + 12 * K + 37) + F * evals * 2 * 8 * 85 * 85,
+        3: F * 24 * V,
+    }[dom]
+    peak, how = load_peaks()
+    achieved = alg_bytes / (per4[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": how,
+                "kernel_ms": {n: float(m) for n, m in zip(names, per4)}, "step_ms_device": float(step_ms),
+                "note": "lm_fit_kernel is fp64/fp32-FMA and latency bound, not HBM bound: see DESIGN.md"}
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64" if args.jtj == "fp64" else "f64 (J^T J accumulated in f32)",
+            "data": "synthetic",
+            "config": {"workload": "512-frame synthetic batch per GPU (BASELINE.json configs[2]), 640x576 "
+                                   "smplsynth-style clouds, icp_iters=1, 10 LM iterations (function_tolerance=0)",
+                       "frames_per_gpu": F, "mean_points_per_frame": float(npts.mean()),
+                       "mean_matched_vertices": float(nmatch.mean()), "mean_lm_iterations": float(iters.mean()),
+                       "mean_correspondences": float(ncorr.mean()), "solver": "gn_lm", "jtj": args.jtj,
+                       "l2": "inputs larger than L2: %.0f MB of clouds+labels per step" % (total * 28 / 1e6)},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "timer": "wall clock around synchronised steps"},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "clocks": clocks, "roofline": roofline, "wall_ms_per_step_resident": 1e3 * (t1 - t0) / args.steps}
+    # ---- CPU baseline: the oracle port on a bounded sample, N=1 only ----
+    if world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as orc
+        om = orc.OracleModel(os.path.join(GOLD, "model_synth.npz"), pr)
+        oo = orc.OracleOptimizer(om, num_parts, part_map)
+        cores = os.cpu_count() or 1
+        ns = max(cores, min(2 * cores, 32, F))
+        sub = (pts[:ns], labs[:ns])
+        cpu_reference_run(orc, oo, (pts[:cores], labs[:cores]), x0, orc.SOLVER_BFGS_WOLFE, 1e-4, cores)
+        tcpu = cpu_reference_run(orc, oo, sub, x0, orc.SOLVER_BFGS_WOLFE, 1e-4, cores)
+        line["cpu_baseline"] = {"value": ns / tcpu, "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": f"first {ns} of the {F} frames, frame-parallel over {cores} host threads, "
+                                          "oracle bfgs_wolfe restating the reference's Ceres line-search BFGS "
+                                          "(reference defaults incl. function_tolerance=1e-4); CPU restatement of "
+                                          "sxyu/avatar, not the Ceres binary"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -71,7 +71,9 @@ typedef struct {
 } avb_fitter_config;
 
 enum { AVB_SOLVER_GN_LM = 1 };
-enum { AVB_JTJ_FP32 = 0, AVB_JTJ_BF16_TENSOR = 1 };
+/* precision of the J^T J accumulation: FP64 (default; fitted parameters track the fp64 oracle to ~1e-6),
+ * FP32 (faster; ~1e-4 drift over 10 iterations), BF16_TENSOR (tcgen05 path, BASELINE.json configs[4]) */
+enum { AVB_JTJ_FP64 = 0, AVB_JTJ_FP32 = 1, AVB_JTJ_BF16_TENSOR = 2 };
 
 /* Public tunables of ark::AvatarOptimizer (include/AvatarOptimizer.h:27-39) plus the solver
  * controls the reference hard-codes in optimize() (AvatarOptimizer.cpp:1313-1341). */
@@ -156,8 +158,13 @@ int avb_fit_resident(avb_fitter* fitter, const double* x_in, const avb_options* 
 int avb_download_results(avb_fitter* fitter, double* x_out, avb_stats* stats, double* cloud_out);
 int avb_synchronize(avb_fitter* fitter);
 /* device time of the kernels enqueued by the last avb_fit_resident, measured with CUDA events on the
- * fitter's stream; per-kernel breakdown [pose_visibility, nn, lm, final_pose] in ms (nullable). */
+ * fitter's stream: total over all ICP iterations, and the per-kernel breakdown of the LAST ICP iteration
+ * [pose_visibility, nn (with its memsets), lm, final_pose] in ms (nullable). */
 int avb_last_device_ms(avb_fitter* fitter, float* total_ms, float* per_kernel_ms4);
+/* CUDA-event stopwatch on the fitter's stream (bench.py): start records an event, stop records another,
+ * synchronises and returns the elapsed device time between them. */
+int avb_timer_start(avb_fitter* fitter);
+int avb_timer_stop(avb_fitter* fitter, float* ms);
 /* number of kernel launches enqueued by the last avb_fit_resident / avb_fit_batch */
 int avb_last_launch_count(avb_fitter* fitter);
 
