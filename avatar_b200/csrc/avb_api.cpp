@@ -95,6 +95,10 @@ struct avb_fitter {
     long long pv_stride = 0;
     int* d_nn = nullptr; int* d_cnt = nullptr; unsigned long long* d_sum = nullptr; double* d_qpart = nullptr;
     int* d_range = nullptr; double* d_Hcur = nullptr; FrameStats* d_stats = nullptr;
+    double *d_xt = nullptr, *d_tab = nullptr, *d_part = nullptr, *d_cpart = nullptr, *d_gcur = nullptr;
+    unsigned short* d_mlist = nullptr; int4* d_chunks = nullptr; LmState* d_state = nullptr;
+    int maxc = 0, tabD = 0, max_nj = 0, chunk_verts = 128;
+    long long pstride = 0;
     int *d_chunk_frame = nullptr, *d_chunk_count = nullptr, *d_chunk_qblock = nullptr, *d_frame_qblock = nullptr;
     long long* d_chunk_begin = nullptr;
     double *d_dump_cost = nullptr, *d_dump_grad = nullptr, *d_dump_H = nullptr;
@@ -538,7 +542,7 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     TRY(dev_put(ft, &dp.part_start, part_start));
     TRY(dev_put(ft, &dp.part_verts, part_verts));
     TRY(dev_put(ft, &dp.first_part_at, first_part_at));
-    int max_groups = 1;
+    int max_groups = 4;
     if (const char* e = std::getenv("AVB_GROUPS")) max_groups = std::max(1, std::min(kMaxGroups, std::atoi(e)));
     std::vector<int> gorder, gvstart, gjoints, gnj;
     build_groups(*m, max_groups, gorder, gvstart, gjoints, gnj);
@@ -569,6 +573,19 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     TRY(dev_alloc(ft, &ft->d_range, B));
     TRY(dev_alloc(ft, &ft->d_Hcur, B * P * P));
     TRY(dev_alloc(ft, &ft->d_stats, B));
+    for (int g : gnj) ft->max_nj = std::max(ft->max_nj, g);
+    if (const char* e = std::getenv("AVB_CHUNK")) ft->chunk_verts = std::max(64, std::min(1024, std::atoi(e) / 64 * 64));
+    ft->maxc = (V + ft->chunk_verts - 1) / ft->chunk_verts + dp.numGroups + 1;
+    ft->tabD = lm_tab_doubles(m->J, m->K);
+    ft->pstride = lm_part_stride(ft->max_nj, m->K);
+    TRY(dev_alloc(ft, &ft->d_xt, B * nx));
+    TRY(dev_alloc(ft, &ft->d_tab, B * (size_t)ft->tabD));
+    TRY(dev_alloc(ft, &ft->d_part, B * (size_t)ft->maxc * (size_t)ft->pstride));
+    TRY(dev_alloc(ft, &ft->d_cpart, B * (size_t)ft->maxc));
+    TRY(dev_alloc(ft, &ft->d_gcur, B * P));
+    TRY(dev_alloc(ft, &ft->d_mlist, B * V));
+    TRY(dev_alloc(ft, &ft->d_chunks, B * (size_t)ft->maxc));
+    TRY(dev_alloc(ft, &ft->d_state, B));
     ft->max_chunks = (int)std::min<size_t>(NT / 512 + B + 8, (size_t)8 * ft->num_sms + 2 * B + 8);
     ft->max_qblocks = (int64_t)(NT / kQBlock + B + 8);
     TRY(dev_alloc(ft, &ft->d_qpart, (size_t)ft->max_qblocks));
@@ -708,21 +725,45 @@ int enqueue_correspond(avb_fitter* ft, const double* dx, const avb_options* o, c
     return AVB_OK;
 }
 
-LmArgs lm_args(avb_fitter* ft, double* dx, const avb_options* o) {
-    LmArgs a{};
+LmBuf lm_buf(avb_fitter* ft, double* dx, const avb_options* o) {
+    LmBuf a{};
     a.x = dx;
+    a.xt = ft->d_xt;
+    a.tab = ft->d_tab;
+    a.mlist = ft->d_mlist;
+    a.chunks = ft->d_chunks;
+    a.part = ft->d_part;
+    a.cpart = ft->d_cpart;
+    a.gcur = ft->d_gcur;
+    a.Hcur = ft->d_Hcur;
+    a.state = ft->d_state;
+    a.maxc = ft->maxc;
+    a.tabD = ft->tabD;
+    a.chunk_verts = ft->chunk_verts;
+    a.pstride = ft->pstride;
     a.cnt = ft->d_cnt;
     a.sum = ft->d_sum;
     a.qpart = ft->d_qpart;
     a.frame_qblock = ft->d_frame_qblock;
-    a.Hcur = ft->d_Hcur;
+    a.range_flag = ft->d_range;
     a.beta_pose = o->beta_pose;
     a.beta_shape = o->beta_shape;
     a.function_tolerance = o->function_tolerance;
     a.max_iters = o->max_iters_per_icp;
     a.stats = ft->d_stats;
-    a.range_flag = ft->d_range;
     return a;
+}
+
+// the inner solve of one ICP iteration: prep + (1 + max_iters) evaluations, all asynchronous
+int enqueue_solve(avb_fitter* ft, const LmBuf& la, const avb_options* o, int rounds) {
+    cudaStream_t st = ft->stream;
+    CUDA_TRY(launch_lm_prep(ft->dm, ft->dp, la, ft->batch, st));
+    ++ft->launches;
+    for (int r = 0; r < rounds; ++r) {
+        CUDA_TRY(launch_lm_eval(ft->dm, ft->dp, la, ft->batch, ft->max_nj, o->jtj_precision == AVB_JTJ_FP64, st));
+        ft->launches += 2;
+    }
+    return AVB_OK;
 }
 
 }  // namespace
@@ -747,9 +788,9 @@ int avb_fit_resident(avb_fitter* ft, const double* x_in, const avb_options* o) {
         rc = enqueue_correspond(ft, ft->d_x, o, timed ? ft->ev[2] : nullptr);
         if (rc != AVB_OK) return rc;
         if (timed) CUDA_TRY(cudaEventRecord(ft->ev[3], st));
-        LmArgs la = lm_args(ft, ft->d_x, o);
-        CUDA_TRY(launch_lm(ft->dm, ft->dp, la, B, o->jtj_precision == AVB_JTJ_FP64, st));
-        ++ft->launches;
+        LmBuf la = lm_buf(ft, ft->d_x, o);
+        rc = enqueue_solve(ft, la, o, 1 + o->max_iters_per_icp);
+        if (rc != AVB_OK) return rc;
         if (timed) CUDA_TRY(cudaEventRecord(ft->ev[4], st));
     }
     // trailing ava.update() (AvatarOptimizer.cpp:1497)
@@ -922,12 +963,13 @@ int avb_debug_evaluate(avb_fitter* ft, const double* x_in, const avb_options* o,
     }
     cudaStream_t st = ft->stream;
     CUDA_TRY(cudaMemcpyAsync(ft->d_xdbg, x_in, B * nx * 8, cudaMemcpyHostToDevice, st));
-    LmArgs la = lm_args(ft, ft->d_xdbg, o);
+    LmBuf la = lm_buf(ft, ft->d_xdbg, o);
     la.max_iters = 0;
     la.dump_cost = ft->d_dump_cost;
     la.dump_grad = ft->d_dump_grad;
     la.dump_H = ft->d_dump_H;
-    CUDA_TRY(launch_lm(ft->dm, ft->dp, la, (int)B, o->jtj_precision == AVB_JTJ_FP64, st));
+    rc = enqueue_solve(ft, la, o, 1);
+    if (rc != AVB_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(cost, ft->d_dump_cost, B * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(grad, ft->d_dump_grad, B * P * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(H, ft->d_dump_H, B * P * P * 8, cudaMemcpyDeviceToHost, st));

@@ -40,27 +40,47 @@ struct NNArgs {
     int* range_flag;             // [batch]
 };
 
-struct LmArgs {
-    double* x;                   // [batch][nx] in/out
-    const int* cnt;
-    const unsigned long long* sum;
+struct LmState {  // per-frame Levenberg-Marquardt state, lives in HBM between the kernels of one ICP iteration
+    double cost, radius, decrease, Qsum, sbp, sbs, initial_cost, model_change;
+    int done, iters, accepted, ncorr, nmatched, nchunks, evals, pad;
+};
+
+struct LmBuf {
+    double* x;                   // [batch][nx] current point (in/out)
+    double* xt;                  // [batch][nx] trial point
+    double* tab;                 // [batch][tabD] joint tables of the trial point: G | pos | tau | C
+    unsigned short* mlist;       // [batch][V] matched vertices grouped by Jacobian column group
+    int4* chunks;                // [batch][maxc] (group, start in mlist, count, -)
+    double* part;                // [batch][maxc][pstride] A^T A partial per chunk (8x4 blocks of the upper triangle)
+    double* cpart;               // [batch][maxc] cost partial per chunk
+    double* gcur;                // [batch][P]
+    double* Hcur;                // [batch][P*P]
+    LmState* state;              // [batch]
+    int maxc, tabD, chunk_verts;
+    long long pstride;
+    const int* cnt;              // [batch][V]
+    const unsigned long long* sum;  // [batch][V][3] fixed point 2^36
     const double* qpart;
     const int* frame_qblock;     // [batch+1]
-    double* Hcur;                // [batch][P*P] scratch
+    const int* range_flag;       // [batch]
     double beta_pose, beta_shape, function_tolerance;
     int max_iters;
-    double* dump_cost;           // nullable [batch]
+    double* dump_cost;           // nullable [batch]  (avb_debug_evaluate)
     double* dump_grad;           // [batch][P]
     double* dump_H;              // [batch][P*P]
     double* trace;               // nullable [batch][trace_cap][nx]
     int trace_cap;
     FrameStats* stats;           // [batch]
-    const int* range_flag;       // [batch]
 };
 
 size_t pose_smem_bytes(int V, int J, int K);
 cudaError_t launch_pose_visibility(const DevModel& M, const DevParts& Pt, const PoseArgs& a, int batch, cudaStream_t st);
 cudaError_t launch_nn(const DevParts& Pt, const NNArgs& a, int num_chunks, cudaStream_t st);
-cudaError_t launch_lm(const DevModel& M, const DevParts& Pt, const LmArgs& a, int batch, bool acc64, cudaStream_t st);
+cudaError_t launch_lm_prep(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, cudaStream_t st);
+// one evaluation: lm_jac_kernel (chunks x frames) + lm_solve_kernel (frames)
+cudaError_t launch_lm_eval(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, int max_nj, bool acc64,
+                           cudaStream_t st);
+long long lm_part_stride(int max_nj, int K);
+int lm_tab_doubles(int J, int K);
 
 }  // namespace avb

@@ -1,0 +1,780 @@
+// avb_lm.cu -- the inner solve of one ICP iteration (AvatarOptimizer.cpp:1398-1486) as grid-sized kernels.
+//
+//   lm_prep_kernel   grid = frames            matched-vertex lists per Jacobian column group, chunk list,
+//                                             #correspondences, sum |d|^2, LM state, joint tables at x.
+//   lm_jac_kernel    grid = chunks x frames   residual statistics + analytic Jacobian rows of up to 256 matched
+//                                             vertices (AvatarOptimizer.cpp:505-582 in closed form), and their
+//                                             contribution to J^T J and J^T r as register-tiled A^T A; one
+//                                             deterministic partial per chunk.
+//   lm_solve_kernel  grid = frames            partial reduction in chunk order, priors (:661-692, :708-723),
+//                                             Levenberg-Marquardt step control, damped Cholesky solve, retraction
+//                                             (:123-143), joint tables of the next trial point.
+//
+// One evaluation = lm_jac_kernel + lm_solve_kernel; 1 + maxItersPerICP evaluations per ICP iteration, enqueued
+// back to back on one stream with no host round trip (frames that converged early skip their CTAs).
+//
+// Numerics: geometry, residuals, cost, gradient and the linear algebra are fp64.  Jacobian rows are staged in
+// shared memory as fp32 (they only scale the residual in J^T r, so their 6e-8 rounding moves the fixed point by
+// ~1e-11) and J^T J is accumulated in fp64 (AccT = double) or fp32 (AccT = float, AVB_JTJ_FP32).
+#include "avb_device.cuh"
+#include "avb_kernels.h"
+#include "avb_tables.cuh"
+
+#include <math.h>
+
+namespace avb {
+
+constexpr int kJacThreads = 256;
+constexpr int kSolveThreads = 256;
+constexpr int kTile = 64;     // vertices per Jacobian tile (3 row-threads per vertex => 192 busy threads)
+
+__host__ __device__ inline int tab_doubles(int J, int K) { return J * (15 + 3 * K); }
+
+// column layout of a group's compact Jacobian: [ p(3) | 3 per group joint | K shape | rho_hi | rho_lo | pad ]
+__host__ __device__ inline int group_L(int nj, int K) { return 3 + 3 * nj + K + 2; }
+
+// ---------------------------------------------------------------------------------------------
+// lm_prep_kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lm_prep_kernel(DevModel M, DevParts Pt, LmBuf a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int f = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int V = M.V, J = M.J, K = M.K, nx = M.nx;
+    double* xs = reinterpret_cast<double*>(smem_raw);
+    double* tb = xs + ((nx + 1) & ~1);
+    double* scr = tb + tables_doubles(J, K, true);
+    int* iscr = reinterpret_cast<int*>(scr + 64);
+    Tables T = carve_tables(tb, J, K, true);
+
+    for (int i = tid; i < nx; i += nt) {
+        const double v = a.x[(size_t)f * nx + i];
+        xs[i] = v;
+        a.xt[(size_t)f * nx + i] = v;
+    }
+    const int* cnt = a.cnt + (size_t)f * V;
+    unsigned short* mlist = a.mlist + (size_t)f * V;
+    int4* chunks = a.chunks + (size_t)f * a.maxc;
+    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    int base = 0, ncorr = 0, nchunks = 0;
+    for (int g = 0; g < Pt.numGroups; ++g) {
+        const int b0 = Pt.gvstart[g], b1 = Pt.gvstart[g + 1];
+        const int gbase = base;
+        for (int i0 = b0; i0 < b1; i0 += nt) {
+            const int i = i0 + tid;
+            int v = 0, cv = 0;
+            if (i < b1) {
+                v = Pt.gorder[i];
+                cv = cnt[v];
+            }
+            ncorr += cv;
+            const unsigned bal = __ballot_sync(0xffffffffu, cv > 0);
+            const int wpre = __popc(bal & ((1u << lane) - 1));
+            if (lane == 0) iscr[wid] = __popc(bal);
+            __syncthreads();
+            int woff = 0, tot = 0;
+            for (int q = 0; q < nw; ++q) {
+                if (q < wid) woff += iscr[q];
+                tot += iscr[q];
+            }
+            if (cv > 0) mlist[base + woff + wpre] = (unsigned short)v;
+            base += tot;
+            __syncthreads();
+        }
+        // chunk list of this group (every thread computes the same numbers; thread 0 writes)
+        for (int s = gbase; s < base; s += a.chunk_verts) {
+            if (tid == 0 && nchunks < a.maxc) chunks[nchunks] = make_int4(g, s, min(a.chunk_verts, base - s), 0);
+            ++nchunks;
+        }
+    }
+    ncorr = warp_sum_i(ncorr);
+    if (lane == 0) iscr[32 + wid] = ncorr;
+    __syncthreads();
+    ncorr = 0;
+    for (int q = 0; q < nw; ++q) ncorr += iscr[32 + q];
+    double part = 0;
+    for (int i = a.frame_qblock[f] + tid; i < a.frame_qblock[f + 1]; i += nt) part += a.qpart[i];
+    const double Qsum = block_sum(part, scr);
+
+    build_tables(M, xs, T, true);
+    double* tab = a.tab + (size_t)f * a.tabD;
+    for (int i = tid; i < 9 * J; i += nt) tab[i] = T.G[i];
+    for (int i = tid; i < 3 * J; i += nt) {
+        tab[9 * J + i] = T.pos[i];
+        tab[12 * J + i] = T.tau[i];
+    }
+    for (int i = tid; i < 3 * J * K; i += nt) tab[15 * J + i] = T.C[i];
+
+    if (tid == 0) {
+        LmState& st = a.state[f];
+        st.cost = 0;
+        st.radius = 1e4;   // Ceres initial_trust_region_radius (the value the reference leaves commented at :1319)
+        st.decrease = 2.0;
+        st.Qsum = Qsum;
+        // scaledBeta{Pose,Shape} = beta * sqrt(#correspondences) / 15 (AvatarOptimizer.cpp:1457-1458)
+        st.sbp = a.beta_pose * sqrt((double)ncorr) / 15.0;
+        st.sbs = a.beta_shape * sqrt((double)ncorr) / 15.0;
+        st.initial_cost = 0;
+        st.model_change = 0;
+        st.done = (ncorr == 0) ? 1 : 0;
+        st.iters = 0;
+        st.accepted = 0;
+        st.ncorr = ncorr;
+        st.nmatched = base;
+        st.nchunks = min(nchunks, a.maxc);
+        st.evals = 0;
+        FrameStats& fs = a.stats[f];
+        fs.num_correspondences = ncorr;
+        fs.num_matched_vertices = base;
+        fs.iterations = 0;
+        fs.accepted_steps = 0;
+        fs.initial_cost = 0;
+        fs.final_cost = 0;
+        fs.status = a.range_flag[f] ? 4 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// lm_jac_kernel
+// ---------------------------------------------------------------------------------------------
+// One Jacobian row per thread (vertex t, coordinate r).  Tangent Jacobian in "global-frame rotation"
+// coordinates eta_j = G_parent(j) delta_j: block_j = R(-1,parent j) dRot Lq_j = -2 [y_j]x G_parent(j)
+// (AvatarOptimizer.cpp:529-565 in closed form); the change of coordinates is undone in lm_solve_kernel.
+__device__ __forceinline__ double jac_row(const DevModel& M, const double* tab, const double* w, int v, int r, int cntv,
+                                          const unsigned long long* sumv, const int* gj, int nj, float* Arow) {
+    const int J = M.J, K = M.K;
+    const double* G = tab;
+    const double* pos = tab + 9 * J;
+    const double* tau = tab + 12 * J;
+    const double* C = tab + 15 * J;
+    const float* sd = M.sd + (size_t)v * 3 * K;
+    double v0[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double s = 0;
+        for (int k = 0; k < K; ++k) s += (double)sd[c * K + k] * w[k];
+        v0[c] = M.vt[3 * (size_t)v + c] + s;
+    }
+    const int n = M.sk_n[v];
+    double xk[AVB_MAX_ASSIGN_][3], wk[AVB_MAX_ASSIGN_];
+    int jk[AVB_MAX_ASSIGN_];
+    uint32_t mk[AVB_MAX_ASSIGN_];
+    double x[3] = {0, 0, 0}, Br[3] = {0, 0, 0};
+#pragma unroll
+    for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
+        if (q < n) {
+            const int k = M.sk_j[4 * (size_t)v + q];
+            const double wt = M.sk_w[4 * (size_t)v + q];
+            const double* Gk = G + 9 * k;
+            jk[q] = k;
+            wk[q] = wt;
+            mk[q] = M.anc_mask[k];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                xk[q][c] = Gk[3 * c] * v0[0] + Gk[3 * c + 1] * v0[1] + Gk[3 * c + 2] * v0[2] + tau[3 * k + c];
+                x[c] += wt * xk[q][c];
+                Br[c] += wt * Gk[3 * r + c];   // row r of the blended rotation
+            }
+        } else {
+            jk[q] = 0; wk[q] = 0; mk[q] = 0;
+            xk[q][0] = xk[q][1] = xk[q][2] = 0;
+        }
+    }
+    const double cn = (double)cntv;
+    const double sc = sqrt(cn);
+    const float scf = (float)sc;
+    // root translation: identity (AvatarOptimizer.cpp:477-481)
+    Arow[0] = (r == 0) ? scf : 0.f;
+    Arow[1] = (r == 1) ? scf : 0.f;
+    Arow[2] = (r == 2) ? scf : 0.f;
+    for (int gi = 0; gi < nj; ++gi) {
+        const int j = gj[gi];
+        double y0 = 0, y1 = 0, y2 = 0, W = 0;
+#pragma unroll
+        for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
+            if ((mk[q] >> j) & 1u) {
+                W += wk[q];
+                y0 += wk[q] * xk[q][0];
+                y1 += wk[q] * xk[q][1];
+                y2 += wk[q] * xk[q][2];
+            }
+        }
+        const double s2 = 2.0 * sc;
+        const float f0 = (float)((y0 - W * pos[3 * j]) * s2);
+        const float f1 = (float)((y1 - W * pos[3 * j + 1]) * s2);
+        const float f2 = (float)((y2 - W * pos[3 * j + 2]) * s2);
+        const int c0 = 3 + 3 * gi;
+        // row r of -2 [y]x = [[0, 2y2, -2y1], [-2y2, 0, 2y0], [2y1, -2y0, 0]]
+        Arow[c0] = (r == 0) ? 0.f : (r == 1 ? -f2 : f1);
+        Arow[c0 + 1] = (r == 0) ? f2 : (r == 1 ? 0.f : -f0);
+        Arow[c0 + 2] = (r == 0) ? -f1 : (r == 1 ? f0 : 0.f);
+    }
+    // shape: row r of sum_k w_k (G_k (Delta_v - S_k) + H_k) = B Delta_v + sum_k w_k C_k  (AvatarOptimizer.cpp:568-580)
+    const int cs = 3 + 3 * nj;
+    for (int m = 0; m < K; ++m) {
+        double e = Br[0] * (double)sd[m] + Br[1] * (double)sd[K + m] + Br[2] * (double)sd[2 * K + m];
+#pragma unroll
+        for (int q = 0; q < AVB_MAX_ASSIGN_; ++q)
+            if (q < n) e += wk[q] * C[(size_t)jk[q] * 3 * K + r * K + m];
+        Arow[cs + m] = (float)(e * sc);
+    }
+    // residual sum of the vertex's correspondences, c x - sum d (AvatarOptimizer.cpp:632-639), split hi/lo
+    const double sr = (double)(long long)sumv[r] * kFixInv;
+    const double rho = (cn * x[r] - sr) / sc;
+    const float hi = (float)rho;
+    Arow[cs + K] = hi;
+    Arow[cs + K + 1] = (float)(rho - (double)hi);
+    // this coordinate's share of sum_i |x - d_i|^2 - sum_i |d_i|^2 = x . (c x - 2 s)
+    return x[r] * (cn * x[r] - 2.0 * sr);
+}
+
+// (block row of 8, block column of 4) pairs covering the upper triangle of an Lp x Lp matrix, Lp = 8 n
+__host__ __device__ inline int num_pairs(int n) { return n * n + n; }
+__device__ __forceinline__ void pair_to_blocks(int pair, int n, int& bi, int& bj) {
+    bi = 0;
+    int rowlen = 2 * n;
+    while (pair >= rowlen) {
+        pair -= rowlen;
+        ++bi;
+        rowlen -= 2;
+    }
+    bj = 2 * bi + pair;
+}
+
+template <typename AccT>
+__global__ void __launch_bounds__(kJacThreads, 2)
+lm_jac_kernel(DevModel M, DevParts Pt, LmBuf a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int c = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    const LmState& st = a.state[f];
+    if (st.done || c >= st.nchunks) return;
+    const int J = M.J, K = M.K;
+    const int4 ch = a.chunks[(size_t)f * a.maxc + c];
+    const int g = ch.x, start = ch.y, count = ch.z;
+    const int nj = Pt.gnj[g];
+    const int L = group_L(nj, K), Lp = (L + 7) & ~7, lda = Lp + 4;
+    double* tab = reinterpret_cast<double*>(smem_raw);
+    double* w = tab + a.tabD;
+    double* scr = w + ((K + 1) & ~1);
+    int* gj = reinterpret_cast<int*>(scr + 32);
+    float* A = reinterpret_cast<float*>(gj + kMaxJ);
+
+    const double* gtab = a.tab + (size_t)f * a.tabD;
+    for (int i = tid; i < a.tabD; i += kJacThreads) tab[i] = gtab[i];
+    for (int i = tid; i < K; i += kJacThreads) w[i] = a.xt[(size_t)f * M.nx + 3 + 4 * J + i];
+    for (int i = tid; i < nj; i += kJacThreads) gj[i] = Pt.gjoints[g * kMaxJ + i];
+
+    // syrk role: (block pair, row group); the row groups of a pair are adjacent lanes (shuffle reduction)
+    const int n = Lp >> 3, npairs = num_pairs(n);
+    int nrg = 1;
+    while (nrg < 32 && 2 * nrg * npairs <= kJacThreads) nrg <<= 1;
+    const int pair = tid / nrg, rg = tid % nrg;
+    const bool active = pair < npairs;
+    int bi = 0, bj = 0;
+    if (active) pair_to_blocks(pair, n, bi, bj);
+    AccT acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = AccT(0);
+    double cost_acc = 0.0;
+    const unsigned short* mlist = a.mlist + (size_t)f * M.V + start;
+    const int* cnt = a.cnt + (size_t)f * M.V;
+    const unsigned long long* sum = a.sum + (size_t)f * 3 * M.V;
+    __syncthreads();
+
+    for (int t0 = 0; t0 < count; t0 += kTile) {
+        const int nv = min(kTile, count - t0);
+        if (tid < 3 * nv) {
+            const int t = tid / 3, r = tid - 3 * t;
+            const int v = mlist[t0 + t];
+            float* Arow = A + (size_t)tid * lda;
+            for (int q = L; q < Lp; ++q) Arow[q] = 0.f;
+            cost_acc += jac_row(M, tab, w, v, r, cnt[v], sum + 3 * (size_t)v, gj, nj, Arow);
+        }
+        __syncthreads();
+        if (active) {
+            const int nrows = 3 * nv;
+            const float* Ab = A + 8 * bi;
+            const float* Bb = A + 4 * bj;
+#pragma unroll 2
+            for (int r = rg; r < nrows; r += nrg) {
+                const float4 a0 = *reinterpret_cast<const float4*>(Ab + (size_t)r * lda);
+                const float4 a1 = *reinterpret_cast<const float4*>(Ab + (size_t)r * lda + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(Bb + (size_t)r * lda);
+                const AccT av[8] = {AccT(a0.x), AccT(a0.y), AccT(a0.z), AccT(a0.w),
+                                    AccT(a1.x), AccT(a1.y), AccT(a1.z), AccT(a1.w)};
+                const AccT bv[4] = {AccT(b0.x), AccT(b0.y), AccT(b0.z), AccT(b0.w)};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+            }
+        }
+        __syncthreads();
+    }
+    // deterministic reduction over the row groups of each pair (fixed xor tree inside the warp)
+    for (int o = nrg >> 1; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], o);
+    }
+    double* part = a.part + ((size_t)f * a.maxc + c) * a.pstride;
+    if (active && rg == 0) {
+        double* p = part + (size_t)pair * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) p[i * 4 + j] = (double)acc[i][j];
+    }
+    const double cs = block_sum(cost_acc, scr);
+    if (tid == 0) a.cpart[(size_t)f * a.maxc + c] = cs;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lm_solve_kernel
+// ---------------------------------------------------------------------------------------------
+struct SolveSmem {
+    double *xs, *xt, *tb, *Hs, *gs, *glo, *gcur, *delta, *aa, *ycomp, *scr;
+    int* iscr;
+};
+__host__ __device__ inline size_t solve_smem_bytes(int J, int K, int C) {
+    const int P = 3 + 3 * J + K, nx = 3 + 4 * J + K, D = 3 * (J - 1);
+    size_t d = 2 * ((nx + 1) & ~1) + tables_doubles(J, K, true) + (size_t)P * P + 4 * ((P + 1) & ~1) + ((D + 1) & ~1) +
+               (size_t)(C > 0 ? C : 1) * ((D + 1) & ~1) + 64;
+    return d * 8 + 64 * 4 + 128;
+}
+__device__ inline SolveSmem carve_solve(unsigned char* raw, const DevModel& M) {
+    SolveSmem S;
+    const int P = M.P, nx = M.nx, D = 3 * (M.J - 1), C = M.gmmC > 0 ? M.gmmC : 1;
+    double* d = reinterpret_cast<double*>(raw);
+    S.xs = d; d += (nx + 1) & ~1;
+    S.xt = d; d += (nx + 1) & ~1;
+    S.tb = d; d += tables_doubles(M.J, M.K, true);
+    S.Hs = d; d += (size_t)P * P;
+    S.gs = d; d += (P + 1) & ~1;
+    S.glo = d; d += (P + 1) & ~1;
+    S.gcur = d; d += (P + 1) & ~1;
+    S.delta = d; d += (P + 1) & ~1;
+    S.aa = d; d += (D + 1) & ~1;
+    S.ycomp = d; d += (size_t)C * ((D + 1) & ~1);
+    S.scr = d; d += 64;
+    S.iscr = reinterpret_cast<int*>(d);
+    return S;
+}
+
+// CTA-wide Cholesky W = L L^T in place (lower triangle; 2-D thread map, one barrier per column).
+// Right-looking without scaling inside the loop: after step j the entries below the diagonal of column j hold
+// l_ij * sqrt(d_j); a final pass scales them.  Returns false when a pivot is not positive.
+__device__ bool block_cholesky(double* W, int P, int* flag) {
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    if (tid == 0) *flag = 1;
+    __syncthreads();
+    for (int j = 0; j < P; ++j) {
+        const double d = W[(size_t)j * P + j];
+        if (!(d > 0.0) || !isfinite(d)) {  // uniform: every thread reads the same value
+            if (tid == 0) *flag = 0;
+            break;
+        }
+        const double inv = 1.0 / d;
+        for (int i = j + 1 + ty; i < P; i += 16) {
+            const double lij = W[(size_t)i * P + j] * inv;
+            for (int k = j + 1 + tx; k <= i; k += 16) W[(size_t)i * P + k] -= lij * W[(size_t)k * P + j];
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (*flag == 0) return false;
+    for (int e = tid; e < P * P; e += blockDim.x) {
+        const int i = e / P, j = e - i * P;
+        if (j < i) W[e] *= 1.0 / sqrt(W[(size_t)j * P + j]);
+    }
+    __syncthreads();
+    for (int j = tid; j < P; j += blockDim.x) W[(size_t)j * P + j] = sqrt(W[(size_t)j * P + j]);
+    __syncthreads();
+    return true;
+}
+
+// solve L L^T x = b in place with one warp (column-oriented forward, row-oriented backward substitution)
+__device__ void warp_chol_solve(const double* L, int P, double* b) {
+    const int lane = threadIdx.x & 31;
+    for (int i = 0; i < P; ++i) {
+        const double yi = b[i] / L[(size_t)i * P + i];
+        __syncwarp();
+        if (lane == 0) b[i] = yi;
+        for (int e = i + 1 + lane; e < P; e += 32) b[e] -= L[(size_t)e * P + i] * yi;
+        __syncwarp();
+    }
+    for (int i = P - 1; i >= 0; --i) {
+        const double xi = b[i] / L[(size_t)i * P + i];
+        __syncwarp();
+        if (lane == 0) b[i] = xi;
+        for (int e = lane; e < i; e += 32) b[e] -= L[(size_t)i * P + e] * xi;
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(kSolveThreads, 2)
+lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    LmState& gst = a.state[f];
+    if (gst.done) return;
+    const int P = M.P, nx = M.nx, J = M.J, K = M.K;
+    SolveSmem S = carve_solve(smem_raw, M);
+    double* Hcur = a.Hcur + (size_t)f * P * P;
+    double* gcur_g = a.gcur + (size_t)f * P;
+    const LmState st = gst;  // snapshot (only thread 0 writes it back at the end)
+
+    for (int i = tid; i < nx; i += kSolveThreads) {
+        S.xs[i] = a.x[(size_t)f * nx + i];
+        S.xt[i] = a.xt[(size_t)f * nx + i];
+    }
+    for (int i = tid; i < P * P; i += kSolveThreads) S.Hs[i] = 0.0;
+    for (int i = tid; i < P; i += kSolveThreads) {
+        S.gs[i] = 0.0;
+        S.glo[i] = 0.0;
+        S.gcur[i] = gcur_g[i];
+    }
+    __syncthreads();
+    // ---- reduce the chunk partials in chunk order ----
+    double csum = 0.0;
+    for (int c = 0; c < st.nchunks; ++c) {
+        const int4 ch = a.chunks[(size_t)f * a.maxc + c];
+        const int g = ch.x, nj = Pt.gnj[g];
+        const int* gj = Pt.gjoints + g * kMaxJ;
+        const int L = group_L(nj, K), Lp = (L + 7) & ~7, n = Lp >> 3;
+        const int npairs = num_pairs(n);
+        const double* part = a.part + ((size_t)f * a.maxc + c) * a.pstride;
+        auto colmap = [&](int q) -> int {
+            if (q < 3) return q;
+            if (q < 3 + 3 * nj) return 3 + 3 * gj[(q - 3) / 3] + (q - 3) % 3;
+            if (q < L - 2) return 3 + 3 * J + (q - 3 - 3 * nj);
+            return -1;
+        };
+        for (int idx = tid; idx < npairs * 32; idx += kSolveThreads) {
+            const int pair = idx >> 5, e = idx & 31;
+            int bi, bj;
+            pair_to_blocks(pair, n, bi, bj);
+            const int qa = 8 * bi + (e >> 2), qb = 4 * bj + (e & 3);
+            if (qa > qb || qa >= L - 2 || qb >= L) continue;
+            const int ca = colmap(qa);
+            const double val = part[idx];
+            if (qb == L - 2) S.gs[ca] += val;
+            else if (qb == L - 1) S.glo[ca] += val;
+            else S.Hs[(size_t)ca * P + colmap(qb)] += val;
+        }
+        csum += a.cpart[(size_t)f * a.maxc + c];
+        __syncthreads();
+    }
+    double cost_t = 0.5 * (csum + st.Qsum);
+    for (int i = tid; i < P; i += kSolveThreads) S.gs[i] += S.glo[i];
+    for (int i = tid; i < P * P; i += kSolveThreads) {
+        const int r = i / P, c = i - r * P;
+        if (r > c) S.Hs[i] = S.Hs[(size_t)c * P + r];
+    }
+    __syncthreads();
+    // ---- eta -> delta coordinates: H = T^T Ht T, g = T^T gt, T_j = G_parent(j) at the trial point ----
+    const double* Gt = a.tab + (size_t)f * a.tabD;
+    for (int i = tid; i < P * (J - 1); i += kSolveThreads) {
+        const int j = 1 + i / P, c = i % P;
+        const double* Gp = Gt + 9 * M.parent[j];
+        double* h = S.Hs + (size_t)(3 + 3 * j) * P + c;
+        const double h0 = h[0], h1 = h[P], h2 = h[2 * P];
+        h[0] = Gp[0] * h0 + Gp[3] * h1 + Gp[6] * h2;
+        h[P] = Gp[1] * h0 + Gp[4] * h1 + Gp[7] * h2;
+        h[2 * P] = Gp[2] * h0 + Gp[5] * h1 + Gp[8] * h2;
+    }
+    __syncthreads();
+    for (int i = tid; i < P * (J - 1); i += kSolveThreads) {
+        const int j = 1 + i / P, r = i % P;
+        const double* Gp = Gt + 9 * M.parent[j];
+        double* h = S.Hs + (size_t)r * P + 3 + 3 * j;
+        const double h0 = h[0], h1 = h[1], h2 = h[2];
+        h[0] = h0 * Gp[0] + h1 * Gp[3] + h2 * Gp[6];
+        h[1] = h0 * Gp[1] + h1 * Gp[4] + h2 * Gp[7];
+        h[2] = h0 * Gp[2] + h1 * Gp[5] + h2 * Gp[8];
+    }
+    for (int j = 1 + tid; j < J; j += kSolveThreads) {
+        const double* Gp = Gt + 9 * M.parent[j];
+        double* gg = S.gs + 3 + 3 * j;
+        const double g0 = gg[0], g1 = gg[1], g2 = gg[2];
+        gg[0] = Gp[0] * g0 + Gp[3] * g1 + Gp[6] * g2;
+        gg[1] = Gp[1] * g0 + Gp[4] * g1 + Gp[7] * g2;
+        gg[2] = Gp[2] * g0 + Gp[5] * g1 + Gp[8] * g2;
+    }
+    __syncthreads();
+    // ---- pose prior (AvatarOptimizer.cpp:661-692, GaussianMixture.cpp:95-114) ----
+    const double sbp = st.sbp, sbs = st.sbs;
+    const double* w = S.xt + 3 + 4 * J;
+    if (sbp > 0.0 && M.gmmC > 0) {
+        const int D = M.gmmD, C = M.gmmC, Dp = (D + 1) & ~1;
+        for (int j = 1 + tid; j < J; j += kSolveThreads) {  // Eigen AngleAxisd(Quaterniond)
+            const double* q = S.xt + 3 + 4 * j;
+            double nn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+            double s = 0.0;
+            if (nn != 0.0) {
+                const double ang = 2.0 * atan2(nn, fabs(q[3]));
+                if (q[3] < 0) nn = -nn;
+                s = ang / nn;
+            }
+            S.aa[3 * (j - 1)] = q[0] * s;
+            S.aa[3 * (j - 1) + 1] = q[1] * s;
+            S.aa[3 * (j - 1) + 2] = q[2] * s;
+        }
+        __syncthreads();
+        for (int i = tid; i < C * D; i += kSolveThreads) {  // y_c = Sigma_c^-1 (x - mu_c)
+            const int cc = i / D, r = i % D;
+            const double* Pm = M.gmm_prec + ((size_t)cc * D + r) * D;
+            const double* mu = M.gmm_mean + (size_t)cc * D;
+            double s = 0;
+            for (int k = 0; k < D; ++k) s += Pm[k] * (S.aa[k] - mu[k]);
+            S.ycomp[cc * Dp + r] = s;
+        }
+        __syncthreads();
+        if (tid < 32) {  // p_c = 1/2 (x-mu)^T Sigma^-1 (x-mu) - consts_log[c]; first minimum wins (strict <)
+            double bestp = 1.79769313486231570e308, bestsq = 0;
+            int best = 0;
+            for (int cc = 0; cc < C; ++cc) {
+                double s = 0;
+                for (int k = tid; k < D; k += 32) s += (S.aa[k] - M.gmm_mean[(size_t)cc * D + k]) * S.ycomp[cc * Dp + k];
+                s = 0.5 * warp_sum(s);
+                const double p = s - M.gmm_clog[cc];
+                if (p < bestp) {
+                    bestp = p;
+                    bestsq = s;
+                    best = cc;
+                }
+            }
+            if (tid == 0) {
+                S.iscr[0] = best;
+                S.scr[40] = 0.5 * sbp * sbp * (bestsq - M.gmm_clog[best]);
+            }
+        }
+        __syncthreads();
+        const int best = S.iscr[0];
+        const double hb = 0.5 * sbp * sbp;
+        for (int i = tid; i < D * D; i += kSolveThreads) {
+            const int r = i / D, c = i % D;
+            S.Hs[(size_t)(6 + r) * P + 6 + c] += hb * M.gmm_prec[((size_t)best * D + r) * D + c];
+        }
+        for (int r = tid; r < D; r += kSolveThreads) S.gs[6 + r] += hb * S.ycomp[best * Dp + r];
+        cost_t += S.scr[40];
+    }
+    // ---- shape prior (AvatarOptimizer.cpp:708-723) ----
+    if (sbs > 0.0) {
+        double sq = 0;
+        for (int k = 0; k < K; ++k) sq += w[k] * w[k];
+        cost_t += 0.5 * sbs * sbs * sq;
+        for (int k = tid; k < K; k += kSolveThreads) {
+            S.Hs[(size_t)(3 + 3 * J + k) * P + 3 + 3 * J + k] += sbs * sbs;
+            S.gs[3 + 3 * J + k] += sbs * sbs * w[k];
+        }
+    }
+    __syncthreads();
+    if (a.dump_cost) {  // avb_debug_evaluate: report the objective at the evaluation point and stop
+        if (tid == 0) {
+            a.dump_cost[f] = cost_t;
+            gst.done = 1;
+        }
+        for (int i = tid; i < P; i += kSolveThreads) a.dump_grad[(size_t)f * P + i] = S.gs[i];
+        for (int i = tid; i < P * P; i += kSolveThreads) a.dump_H[(size_t)f * P * P + i] = S.Hs[i];
+        return;
+    }
+
+    // ---- Levenberg-Marquardt step control (Ceres-1.14-style trust region; DESIGN.md "solver") ----
+    double cost = st.cost, radius = st.radius, decrease = st.decrease, initial_cost = st.initial_cost;
+    int iters = st.iters, accepted = st.accepted;
+    bool done = false, have_cur_in_smem = false;
+    auto gmax = [&](const double* g) {
+        double m = 0;
+        for (int i = 0; i < P; ++i) m = fmax(m, fabs(g[i]));
+        return m;
+    };
+    auto trace_now = [&]() {
+        if (a.trace && iters >= 1) {
+            const int slot = min(iters - 1, a.trace_cap - 1);
+            for (int i = tid; i < nx; i += kSolveThreads) a.trace[((size_t)f * a.trace_cap + slot) * nx + i] = S.xs[i];
+        }
+    };
+    if (st.evals == 0) {
+        // first evaluation: the trial point is the start point
+        cost = initial_cost = cost_t;
+        for (int i = tid; i < P * P; i += kSolveThreads) Hcur[i] = S.Hs[i];
+        for (int i = tid; i < P; i += kSolveThreads) S.gcur[i] = S.gs[i];
+        __syncthreads();
+        have_cur_in_smem = true;
+        done = !(gmax(S.gcur) > 1e-10) || !isfinite(cost);
+    } else {
+        // finish iteration `iters`: accept or reject the trial point
+        const double rho = (cost - cost_t) / st.model_change;
+        if (isfinite(cost_t) && rho > 1e-3) {
+            ++accepted;
+            double dn = 0, xn = 0;
+            for (int i = 0; i < nx; ++i) {
+                const double dd = S.xt[i] - S.xs[i];
+                dn += dd * dd;
+                xn += S.xs[i] * S.xs[i];
+            }
+            const double cost_change = cost - cost_t, cost_old = cost;
+            __syncthreads();
+            for (int i = tid; i < nx; i += kSolveThreads) S.xs[i] = S.xt[i];
+            for (int i = tid; i < P * P; i += kSolveThreads) Hcur[i] = S.Hs[i];
+            for (int i = tid; i < P; i += kSolveThreads) S.gcur[i] = S.gs[i];
+            __syncthreads();
+            have_cur_in_smem = true;
+            cost = cost_t;
+            radius = fmin(1e16, radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rho - 1.0, 3.0)));
+            decrease = 2.0;
+            if (sqrt(dn) <= 1e-8 * (sqrt(xn) + 1e-8)) done = true;
+            if (fabs(cost_change) <= a.function_tolerance * cost_old) done = true;
+            if (!(gmax(S.gcur) > 1e-10)) done = true;
+        } else {
+            radius /= decrease;
+            decrease *= 2.0;
+            if (radius < 1e-32) done = true;
+        }
+        trace_now();
+    }
+    // ---- next iteration(s): damped solve until a usable step exists ----
+    double model_change = 0.0;
+    bool have_step = false;
+    while (!done && iters < a.max_iters && !have_step) {
+        ++iters;
+        if (!have_cur_in_smem) {
+            for (int i = tid; i < P * P; i += kSolveThreads) S.Hs[i] = Hcur[i];
+            __syncthreads();
+        }
+        have_cur_in_smem = false;  // the factorisation below overwrites S.Hs
+        // W = Hcur + D,  D_jj = clamp(s^2 h_jj, 1e-6, 1e32) / (s^2 radius),  s = 1 / (1 + sqrt(h_jj))
+        for (int j = tid; j < P; j += kSolveThreads) {
+            const double h = S.Hs[(size_t)j * P + j];
+            const double s = 1.0 / (1.0 + sqrt(h));
+            const double d = fmin(fmax(s * s * h, 1e-6), 1e32);
+            S.Hs[(size_t)j * P + j] = h + d / (s * s * radius);
+        }
+        __syncthreads();
+        bool ok = block_cholesky(S.Hs, P, &S.iscr[50]);
+        if (ok) {
+            for (int i = tid; i < P; i += kSolveThreads) S.delta[i] = -S.gcur[i];
+            __syncthreads();
+            if (tid < 32) warp_chol_solve(S.Hs, P, S.delta);
+            __syncthreads();
+            // model_cost_change = -delta^T (g + 1/2 H delta), H without damping
+            double part = 0;
+            for (int r = tid; r < P; r += kSolveThreads) {
+                double s = 0;
+                for (int c = 0; c < P; ++c) s += Hcur[(size_t)r * P + c] * S.delta[c];
+                part -= S.delta[r] * (S.gcur[r] + 0.5 * s);
+            }
+            model_change = block_sum(part, S.scr);
+            ok = model_change > 0.0 && isfinite(model_change);
+        }
+        if (ok) {
+            have_step = true;
+        } else {
+            radius /= decrease;
+            decrease *= 2.0;
+            if (radius < 1e-32) done = true;
+            trace_now();
+        }
+    }
+    if (!have_step) done = true;
+    if (!done) {
+        // retraction: p, w additive; q <- dq (x) q, |delta| is the half angle (AvatarOptimizer.cpp:123-143)
+        for (int i = tid; i < 3; i += kSolveThreads) S.xt[i] = S.xs[i] + S.delta[i];
+        for (int k = tid; k < K; k += kSolveThreads) S.xt[3 + 4 * J + k] = S.xs[3 + 4 * J + k] + S.delta[3 + 3 * J + k];
+        for (int j = tid; j < J; j += kSolveThreads) {
+            const double* d = S.delta + 3 + 3 * j;
+            const double* q = S.xs + 3 + 4 * j;
+            double* o = S.xt + 3 + 4 * j;
+            const double nd = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            if (nd > 0.0) {
+                const double sdd = sin(nd) / nd;
+                const double ax = sdd * d[0], ay = sdd * d[1], az = sdd * d[2], aw = cos(nd);
+                o[0] = aw * q[0] + ax * q[3] + ay * q[2] - az * q[1];
+                o[1] = aw * q[1] + ay * q[3] + az * q[0] - ax * q[2];
+                o[2] = aw * q[2] + az * q[3] + ax * q[1] - ay * q[0];
+                o[3] = aw * q[3] - ax * q[0] - ay * q[1] - az * q[2];
+            } else {
+                o[0] = q[0]; o[1] = q[1]; o[2] = q[2]; o[3] = q[3];
+            }
+        }
+        __syncthreads();
+        Tables T = carve_tables(S.tb, J, K, true);
+        build_tables(M, S.xt, T, true);
+        double* tab = a.tab + (size_t)f * a.tabD;
+        for (int i = tid; i < 9 * J; i += kSolveThreads) tab[i] = T.G[i];
+        for (int i = tid; i < 3 * J; i += kSolveThreads) {
+            tab[9 * J + i] = T.pos[i];
+            tab[12 * J + i] = T.tau[i];
+        }
+        for (int i = tid; i < 3 * J * K; i += kSolveThreads) tab[15 * J + i] = T.C[i];
+        for (int i = tid; i < nx; i += kSolveThreads) a.xt[(size_t)f * nx + i] = S.xt[i];
+    }
+    for (int i = tid; i < nx; i += kSolveThreads) a.x[(size_t)f * nx + i] = S.xs[i];
+    for (int i = tid; i < P; i += kSolveThreads) gcur_g[i] = S.gcur[i];
+    if (tid == 0) {
+        gst.cost = cost;
+        gst.radius = radius;
+        gst.decrease = decrease;
+        gst.initial_cost = initial_cost;
+        gst.model_change = model_change;
+        gst.iters = iters;
+        gst.accepted = accepted;
+        gst.evals = st.evals + 1;
+        gst.done = done ? 1 : 0;
+        FrameStats& fs = a.stats[f];
+        // an iteration whose trial point is still to be evaluated is counted once that evaluation is reduced
+        fs.iterations = done ? iters : iters - 1;
+        fs.accepted_steps = accepted;
+        fs.initial_cost = initial_cost;
+        fs.final_cost = cost;
+        if (!isfinite(cost)) fs.status = 4;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+size_t lm_prep_smem(const DevModel& M) {
+    return (size_t)(((M.nx + 1) & ~1) + tables_doubles(M.J, M.K, true) + 64) * 8 + 64 * 4 + 64;
+}
+size_t lm_jac_smem(const DevModel& M, int max_nj) {
+    const int L = group_L(max_nj, M.K), Lp = (L + 7) & ~7, lda = Lp + 4;
+    return (size_t)(tab_doubles(M.J, M.K) + ((M.K + 1) & ~1) + 32) * 8 + kMaxJ * 4 + (size_t)3 * kTile * lda * 4 + 64;
+}
+
+cudaError_t launch_lm_prep(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, cudaStream_t st) {
+    lm_prep_kernel<<<batch, 256, lm_prep_smem(M), st>>>(M, Pt, a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lm_eval(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, int max_nj, bool acc64,
+                           cudaStream_t st) {
+    const size_t jsm = lm_jac_smem(M, max_nj);
+    const size_t ssm = solve_smem_bytes(M.J, M.K, M.gmmC);
+    cudaError_t e = acc64 ? cudaFuncSetAttribute(lm_jac_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm)
+                          : cudaFuncSetAttribute(lm_jac_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(lm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
+    if (e != cudaSuccess) return e;
+    const dim3 grid(a.maxc, batch);
+    if (acc64)
+        lm_jac_kernel<double><<<grid, kJacThreads, jsm, st>>>(M, Pt, a);
+    else
+        lm_jac_kernel<float><<<grid, kJacThreads, jsm, st>>>(M, Pt, a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    lm_solve_kernel<<<batch, kSolveThreads, ssm, st>>>(M, Pt, a);
+    return cudaGetLastError();
+}
+
+long long lm_part_stride(int max_nj, int K) {
+    const int L = group_L(max_nj, K), Lp = (L + 7) & ~7;
+    return (long long)num_pairs(Lp >> 3) * 32;
+}
+int lm_tab_doubles(int J, int K) { return tab_doubles(J, K); }
+
+}  // namespace avb
