@@ -1,0 +1,263 @@
+// ark_b200.cpp -- implementation of the header-compatible C++ facade (include/ark_b200/*.h) over the C ABI.
+// Host-side only: file parsing and marshalling; every computation happens in libavatar_b200.so.
+#include "../../include/ark_b200/AvatarOptimizer.h"
+#include "../../include/ark_b200/npz.h"
+#include "../../include/avatar_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <stdexcept>
+
+namespace ark {
+namespace {
+[[noreturn]] void die(const std::string& what) { throw std::runtime_error("avatar_b200: " + what + ": " + avb_last_error()); }
+}
+
+// GaussianMixture.cpp:12-58 (parsing only)
+void GaussianMixture::load(const std::string& path) {
+    FILE* fp = std::fopen(path.c_str(), "r");
+    if (!fp) {
+        std::fprintf(stderr, "Warning: pose prior file at %s does not exist or cannot be read\n", path.c_str());
+        nComps = -1;
+        return;
+    }
+    bool ok = std::fscanf(fp, "%d %d", &nComps, &nDims) == 2;
+    weight.resize(nComps);
+    mean.resize(nComps, nDims);
+    cov.assign(nComps, Eigen::MatrixXd());
+    for (int i = 0; i < nComps && ok; ++i) ok = std::fscanf(fp, "%lf", &weight(i)) == 1;
+    for (int i = 0; i < nComps && ok; ++i)
+        for (int j = 0; j < nDims && ok; ++j) ok = std::fscanf(fp, "%lf", &mean(i, j)) == 1;
+    for (int i = 0; i < nComps && ok; ++i) {
+        cov[i].resize(nDims, nDims);
+        for (int j = 0; j < nDims && ok; ++j)
+            for (int k = 0; k < nDims && ok; ++k) ok = std::fscanf(fp, "%lf", &cov[i](j, k)) == 1;
+    }
+    std::fclose(fp);
+    if (!ok) throw std::runtime_error("pose prior file is truncated: " + path);
+}
+
+// AvatarModel.cpp:14-127 (npz branch) + :296
+AvatarModel::AvatarModel(const std::string& model_dir, bool /*limit_one_joint_per_point: ignored on the npz path*/)
+    : MODEL_DIR(model_dir) {
+    std::string root = model_dir;
+    if (root.empty()) {
+        const char* env = std::getenv("OPENARK_DIR");  // Util.cpp:70-96
+        root = std::string(env ? env : ".") + "/data/avatar-model";
+    }
+    auto npz = ark_b200::load_npz(root + "/model.npz");
+    const auto& vt = npz.at("v_template");
+    const auto& kt = npz.at("kintree_table");
+    const auto& fa = npz.at("f");
+    const auto& sd = npz.at("shapedirs");
+    const auto& jr = npz.at("J_regressor");
+    const auto& wt = npz.at("weights");
+    const size_t V = vt.shape[0], J = kt.shape[1], F = fa.shape[0], K = sd.shape[2];
+    parent.resize((long)J);
+    for (size_t j = 0; j < J; ++j) parent((long)j) = (int)kt.as<uint32_t>(j);  // cast<int>(): 0xFFFFFFFF -> -1
+    if (parent(0) != -1) throw std::runtime_error("model.npz: parent[0] must be -1");
+    baseCloud.resize((long)(3 * V));
+    for (size_t i = 0; i < 3 * V; ++i) baseCloud((long)i) = vt.as<double>(i);
+    mesh.resize(3, (long)F);
+    for (size_t f = 0; f < F; ++f)
+        for (int c = 0; c < 3; ++c) mesh(c, (long)f) = (int)fa.as<int64_t>(3 * f + c);
+    keyClouds.resize((long)(3 * V), (long)K);
+    for (size_t r = 0; r < 3 * V; ++r)
+        for (size_t k = 0; k < K; ++k) keyClouds((long)r, (long)k) = sd.as<double>(r * K + k);
+    assignedJoints.assign(V, {});
+    assignedPoints.assign(J, {});
+    for (size_t v = 0; v < V; ++v)
+        for (size_t j = 0; j < J; ++j) {
+            const double w = wt.as<double>(v * J + j);
+            if (w > 1e-12) {  // AvatarModel.cpp:81
+                assignedJoints[v].push_back({w, (int)j});
+                assignedPoints[j].push_back({w, (int)v});
+            }
+        }
+    for (auto& a : assignedPoints) std::sort(a.begin(), a.end(), std::greater<std::pair<double, int>>());
+    for (auto& a : assignedJoints) std::sort(a.begin(), a.end(), std::greater<std::pair<double, int>>());
+    // joint shape regressor (AvatarModel.cpp:105-127)
+    useJointShapeRegressor = true;
+    initialJointPos.resize(3, (long)J);
+    jointShapeReg.resize((long)(3 * J), (long)K);
+    initialJointPos.setZero();
+    jointShapeReg.setZero();
+    for (size_t j = 0; j < J; ++j)
+        for (size_t v = 0; v < V; ++v) {
+            const double rg = jr.as<double>(j * V + v);
+            if (rg == 0.0) continue;
+            for (int c = 0; c < 3; ++c) {
+                initialJointPos(c, (long)j) += baseCloud((long)(3 * v + c)) * rg;
+                for (size_t k = 0; k < K; ++k) jointShapeReg((long)(3 * j + c), (long)k) += keyClouds((long)(3 * v + c), (long)k) * rg;
+            }
+        }
+    jointShapeRegBase.resize((long)(3 * J));
+    for (size_t j = 0; j < J; ++j)
+        for (int c = 0; c < 3; ++c) jointShapeRegBase((long)(3 * j + c)) = initialJointPos(c, (long)j);
+    posePrior.load(root + "/pose_prior.txt");
+}
+
+AvatarModel::~AvatarModel() {
+    if (handle_) avb_model_destroy(handle_);
+}
+
+avb_model* AvatarModel::handle() const {
+    if (handle_) return handle_;
+    const int V = numPoints(), J = numJoints(), K = numShapeKeys(), F = numFaces();
+    std::vector<int32_t> start{0}, joint, faces(3 * (size_t)F), par(J);
+    std::vector<double> weight, key((size_t)3 * V * K), jsr((size_t)3 * J * K), mean, cov;
+    for (auto& pairs : assignedJoints) {
+        for (auto& wj : pairs) {
+            weight.push_back(wj.first);
+            joint.push_back(wj.second);
+        }
+        start.push_back((int32_t)joint.size());
+    }
+    for (int r = 0; r < 3 * V; ++r)
+        for (int k = 0; k < K; ++k) key[(size_t)r * K + k] = keyClouds(r, k);
+    for (int r = 0; r < 3 * J; ++r)
+        for (int k = 0; k < K; ++k) jsr[(size_t)r * K + k] = jointShapeReg(r, k);
+    for (int f = 0; f < F; ++f)
+        for (int c = 0; c < 3; ++c) faces[3 * (size_t)f + c] = mesh(c, f);
+    for (int j = 0; j < J; ++j) par[j] = parent(j);
+    avb_model_desc d{};
+    d.num_points = V; d.num_joints = J; d.num_shape_keys = K; d.num_faces = F;
+    d.base_cloud = baseCloud.data();
+    d.key_clouds = key.data();
+    d.joint_shape_reg_base = jointShapeRegBase.data();
+    d.joint_shape_reg = jsr.data();
+    d.parent = par.data();
+    d.mesh = faces.data();
+    d.assign_start = start.data(); d.assign_joint = joint.data(); d.assign_weight = weight.data();
+    if (hasPosePrior()) {
+        const int C = posePrior.nComps, D = posePrior.nDims;
+        mean.resize((size_t)C * D);
+        cov.resize((size_t)C * D * D);
+        for (int c = 0; c < C; ++c) {
+            for (int j = 0; j < D; ++j) mean[(size_t)c * D + j] = posePrior.mean(c, j);
+            for (int j = 0; j < D; ++j)
+                for (int k = 0; k < D; ++k) cov[((size_t)c * D + j) * D + k] = posePrior.cov[c](j, k);
+        }
+        d.gmm_components = C; d.gmm_dims = D;
+        d.gmm_weight = posePrior.weight.data(); d.gmm_mean = mean.data(); d.gmm_cov = cov.data();
+    }
+    if (avb_model_create(&d, &handle_) != AVB_OK) die("avb_model_create");
+    return handle_;
+}
+
+Avatar::Avatar(const AvatarModel& m) : model(m) {  // Avatar.cpp:12-20
+    w.resize(model.numShapeKeys());
+    r.resize(model.numJoints());
+    w.setZero();
+    p.setZero();
+    for (auto& R : r) R.setIdentity();
+}
+Avatar::~Avatar() {
+    if (updater_) avb_fitter_destroy(updater_);
+}
+
+std::vector<double> Avatar::packParams() const {
+    const int J = model.numJoints(), K = model.numShapeKeys();
+    std::vector<double> x(3 + 4 * (size_t)J + K);
+    for (int c = 0; c < 3; ++c) x[c] = p(c);
+    for (int j = 0; j < J; ++j) {
+        double R[9];
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) R[3 * a + b] = r[j](a, b);
+        avb_rotmat_to_quat(R, &x[3 + 4 * j]);
+    }
+    for (int k = 0; k < K; ++k) x[3 + 4 * J + k] = w(k);
+    return x;
+}
+void Avatar::unpackParams(const std::vector<double>& x) {
+    const int J = model.numJoints(), K = model.numShapeKeys();
+    for (int c = 0; c < 3; ++c) p(c) = x[c];
+    for (int j = 0; j < J; ++j) {
+        double R[9];
+        avb_quat_to_rotmat(&x[3 + 4 * j], R);
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) r[j](a, b) = R[3 * a + b];
+    }
+    for (int k = 0; k < K; ++k) w(k) = x[3 + 4 * J + k];
+}
+
+void Avatar::update() {
+    if (!updater_) {
+        std::vector<int32_t> pm(model.numJoints(), 0);
+        avb_fitter_config cfg{0, 1, 16, 1, pm.data()};
+        if (avb_fitter_create(model.handle(), &cfg, &updater_) != AVB_OK) die("avb_fitter_create");
+    }
+    const std::vector<double> x = packParams();
+    cloud.resize(3, model.numPoints());
+    jointPos.resize(3, model.numJoints());
+    jointTrans.resize(12, model.numJoints());
+    if (avb_avatar_update(updater_, 1, x.data(), cloud.data(), jointPos.data(), jointTrans.data()) != AVB_OK)
+        die("avb_avatar_update");
+}
+
+Eigen::VectorXd Avatar::smplParams() const {
+    const int J = model.numJoints();
+    Eigen::VectorXd res;
+    res.resize((J - 1) * 3);
+    const std::vector<double> x = packParams();
+    for (int j = 1; j < J; ++j) {
+        const double* q = &x[3 + 4 * j];
+        const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+        const double s = n == 0 ? 0.0 : 2.0 * std::atan2(n, std::fabs(q[3])) / (q[3] < 0 ? -n : n);
+        for (int c = 0; c < 3; ++c) res((j - 1) * 3 + c) = q[c] * s;
+    }
+    return res;
+}
+
+// AvatarOptimizer.cpp:1213-1244
+AvatarOptimizer::AvatarOptimizer(Avatar& a, const CameraIntrin& in, const cv::Size& image_size, int num_parts,
+                                 const std::vector<int>& part_map)
+    : ava(a), intrin(in), imageSize(image_size), numParts(num_parts), partMap(part_map) {
+    r.resize(ava.model.numJoints());
+}
+AvatarOptimizer::~AvatarOptimizer() {
+    if (fitter_) avb_fitter_destroy(fitter_);
+}
+
+// AvatarOptimizer.cpp:1246-1517
+void AvatarOptimizer::optimize(const Eigen::Matrix<double, 3, Eigen::Dynamic>& data_cloud,
+                               const Eigen::VectorXi& data_part_labels, int icp_iters, int /*num_threads*/) {
+    const int N = (int)data_cloud.cols();
+    if (!fitter_ || N > capacity_) {
+        if (fitter_) avb_fitter_destroy(fitter_);
+        capacity_ = std::max(N, 1 << 16) * 2;
+        std::vector<int32_t> pm(partMap.begin(), partMap.end());
+        avb_fitter_config cfg{0, 1, capacity_, numParts, pm.data()};
+        if (avb_fitter_create(ava.model.handle(), &cfg, &fitter_) != AVB_OK) die("avb_fitter_create");
+    }
+    std::vector<double> x = ava.packParams();
+    avb_options o;
+    avb_default_options(&o);
+    o.icp_iters = icp_iters;
+    o.max_iters_per_icp = maxItersPerICP;
+    o.beta_pose = betaPose;
+    o.beta_shape = betaShape;
+    o.enable_occlusion = enableOcclusion ? 1 : 0;
+    o.nn_step = nnStep;
+    avb_stats st{};
+    ava.cloud.resize(3, ava.model.numPoints());
+    std::vector<int32_t> labels(N);
+    for (int i = 0; i < N; ++i) labels[i] = data_part_labels(i);
+    if (avb_fit(fitter_, data_cloud.data(), labels.data(), N, x.data(), &o, &st, ava.cloud.data()) != AVB_OK)
+        die("avb_fit");
+    const int J = ava.model.numJoints();
+    for (int j = 0; j < J; ++j) r[j] = Eigen::Quaterniond(x[6 + 4 * j], x[3 + 4 * j], x[4 + 4 * j], x[5 + 4 * j]);
+    ava.unpackParams(x);                                                  // :1494-1496
+    ava.jointPos.resize(3, J);
+    ava.jointTrans.resize(12, J);
+    if (avb_avatar_update(fitter_, 1, x.data(), nullptr, ava.jointPos.data(), ava.jointTrans.data()) != AVB_OK)
+        die("avb_avatar_update");                                         // :1497 (cloud came back from avb_fit)
+    lastIterations = st.iterations;
+    lastCorrespondences = st.num_correspondences;
+    lastInitialCost = st.initial_cost;
+    lastFinalCost = st.final_cost;
+}
+}  // namespace ark

@@ -1,0 +1,41 @@
+// ark_b200/AvatarOptimizer.h -- header-compatible stand-in for include/AvatarOptimizer.h:11-54.
+#pragma once
+#include "Avatar.h"
+#if __has_include(<opencv2/core.hpp>)
+#include <opencv2/core.hpp>
+#endif
+
+namespace ark {
+#if !__has_include(<opencv2/core.hpp>)
+/** include/Calibration.h: pinhole intrinsics; stored by the optimizer and otherwise unused on this path */
+struct CameraIntrin {
+    float fx = 0, fy = 0, cx = 0, cy = 0;
+};
+#endif
+
+class AvatarOptimizer {
+   public:
+    AvatarOptimizer(Avatar& ava, const CameraIntrin& intrin, const cv::Size& image_size, int num_parts,
+                    const std::vector<int>& part_map);
+    ~AvatarOptimizer();
+    void optimize(const Eigen::Matrix<double, 3, Eigen::Dynamic>& data_cloud, const Eigen::VectorXi& data_part_labels,
+                  int icp_iters = 1, int num_threads = 4);
+    static const int ROT_SIZE = 4;
+    std::vector<Eigen::Quaterniond, Eigen::aligned_allocator<Eigen::Quaterniond>> r;
+    double betaPose = 0.1, betaShape = 1.0;
+    int nnStep = 20;
+    int maxItersPerICP = 10;
+    bool enableOcclusion = true;
+    Avatar& ava;
+    const CameraIntrin& intrin;
+    cv::Size imageSize;
+    int numParts;
+    const std::vector<int>& partMap;
+    /** extension: statistics of the last optimize() call */
+    int lastIterations = 0, lastCorrespondences = 0;
+    double lastInitialCost = 0, lastFinalCost = 0;
+   private:
+    avb_fitter* fitter_ = nullptr;
+    int capacity_ = 0;
+};
+}  // namespace ark

@@ -5,7 +5,7 @@
  * The reference has no FFI; its boundary is the C++ class API of include/Avatar.h and
  * include/AvatarOptimizer.h.  Each entry point below names the reference interface it replaces
  * (paths relative to the reference tree).  The header-compatible C++ facade
- * (include/ark_b200/, planned) and the Python mirror (avatar_b200/*.py) are thin callers of this ABI.
+ * (include/ark_b200/, avatar_b200/cpp/ark_b200.cpp) and the Python mirror (avatar_b200/*.py) are thin callers of this ABI.
  *
  * Conventions: int return codes (AVB_OK = 0), no exceptions cross the ABI, caller owns host
  * buffers, the library owns device buffers, plain pointers and sizes only.  All host arrays are

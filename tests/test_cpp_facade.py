@@ -1,0 +1,59 @@
+"""The header-compatible C++ facade (include/ark_b200/*.h, avatar_b200/cpp/ark_b200.cpp): a reference-style
+caller (tests/cpp/facade_demo.cpp, modelled on demo.cpp:135-143,254-268) compiled against it."""
+import os
+import shutil
+import struct
+import subprocess
+import numpy as np
+import pytest
+
+from conftest import ROOT, GOLDEN
+
+DEMO = os.path.join(ROOT, "tests", "cpp", "facade_demo")
+
+
+@pytest.fixture(scope="module")
+def model_dir(build_all, prior_arrays, tmp_path_factory):
+    """data/avatar-model layout of the reference: model.npz + pose_prior.txt (AvatarModel.cpp:18-23)"""
+    from avatar_b200 import GaussianMixture
+    d = tmp_path_factory.mktemp("avatar-model")
+    shutil.copy(os.path.join(GOLDEN, "model_synth.npz"), str(d / "model.npz"))
+    GaussianMixture.from_arrays(prior_arrays["weights"], prior_arrays["means"], prior_arrays["covs"]).save(
+        str(d / "pose_prior.txt"))
+    return str(d)
+
+
+def test_facade_reads_model_like_the_python_mirror(model_dir, model, prior_arrays):
+    out = subprocess.run([DEMO, model_dir, "--info", "0"], capture_output=True, text=True, check=True).stdout
+    f = out.split()
+    assert f[0] == "INFO" and [int(v) for v in f[1:7]] == [6890, 24, 10, 13776, 8, 69]
+    assert float(f[7]) == pytest.approx(model.baseCloud.sum(), rel=1e-12)
+    assert float(f[8]) == pytest.approx(model.jointShapeReg.sum(), rel=1e-11)
+    assert float(f[9]) == pytest.approx(sum(p[0][0] + p[0][1] for p in model.assignedJoints), rel=1e-12)
+    assert float(f[10]) == prior_arrays["covs"][1][3, 4]
+
+
+@pytest.mark.gpu
+def test_facade_optimize_matches_oracle(model_dir, oracle_mod, oopt, frames, prior_arrays, tmp_path):
+    x_gt, x0, pts, lab = frames[1]
+    J, K, nparts = 24, 10, int(prior_arrays["num_parts"])
+    path = str(tmp_path / "frame.bin")
+    with open(path, "wb") as fh:
+        fh.write(struct.pack("<4i", len(pts), J, K, nparts))
+        fh.write(np.asarray(prior_arrays["part_map"], dtype="<i4").tobytes())
+        fh.write(np.asarray(x0, dtype="<f8").tobytes())
+        fh.write(np.ascontiguousarray(pts, dtype="<f8").tobytes())
+        fh.write(np.asarray(lab, dtype="<i4").tobytes())
+    out = subprocess.run([DEMO, model_dir, path, "3"], capture_output=True, text=True, check=True).stdout
+    lines = {l.split()[0]: l.split()[1:] for l in out.strip().splitlines()}
+    x = np.array([float(v) for v in lines["PARAMS"]])
+    oo = oracle_mod.default_options(oracle_mod.SOLVER_GN_LM)
+    oo.icp_iters, oo.beta_pose, oo.beta_shape = 3, 0.05, 0.12
+    x_start = x0.copy()   # the facade goes through rotation matrices and the :1250-1254 prologue
+    for j in range(J):
+        x_start[3 + 4 * j:7 + 4 * j] = oracle_mod.rotmat_to_quat(oracle_mod.quat_to_rotmat(x0[3 + 4 * j:7 + 4 * j]))
+    xo, st, _, _ = oopt.optimize(pts, lab, x_start, oo)
+    assert np.abs(x - xo).max() < 1e-4
+    assert int(lines["STATS"][1]) == st.num_correspondences
+    cloud, _, _ = oopt.model.update_x(x)
+    np.testing.assert_allclose([float(v) for v in lines["CLOUD0"]], cloud[0], atol=1e-9)
