@@ -97,6 +97,7 @@ struct avb_fitter {
     int* d_range = nullptr; double* d_Hcur = nullptr; FrameStats* d_stats = nullptr;
     double *d_xt = nullptr, *d_tab = nullptr, *d_part = nullptr, *d_cpart = nullptr, *d_gcur = nullptr;
     unsigned short* d_mlist = nullptr; int4* d_chunks = nullptr; LmState* d_state = nullptr;
+    float* d_rec = nullptr; int* d_gstart = nullptr; int maxrb = 0, rec_stride = 0;
     int maxc = 0, tabD = 0, max_nj = 0, chunk_verts = 128;
     long long pstride = 0;
     int *d_chunk_frame = nullptr, *d_chunk_count = nullptr, *d_chunk_qblock = nullptr, *d_frame_qblock = nullptr;
@@ -581,7 +582,11 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     TRY(dev_alloc(ft, &ft->d_xt, B * nx));
     TRY(dev_alloc(ft, &ft->d_tab, B * (size_t)ft->tabD));
     TRY(dev_alloc(ft, &ft->d_part, B * (size_t)ft->maxc * (size_t)ft->pstride));
-    TRY(dev_alloc(ft, &ft->d_cpart, B * (size_t)ft->maxc));
+    ft->maxrb = (V + 255) / 256;
+    ft->rec_stride = lm_rec_floats(ft->max_nj, m->K);
+    TRY(dev_alloc(ft, &ft->d_cpart, B * (size_t)ft->maxrb));
+    TRY(dev_alloc(ft, &ft->d_rec, B * (size_t)V * (size_t)ft->rec_stride));
+    TRY(dev_alloc(ft, &ft->d_gstart, B * (size_t)(kMaxGroups + 1)));
     TRY(dev_alloc(ft, &ft->d_gcur, B * P));
     TRY(dev_alloc(ft, &ft->d_mlist, B * V));
     TRY(dev_alloc(ft, &ft->d_chunks, B * (size_t)ft->maxc));
@@ -734,6 +739,10 @@ LmBuf lm_buf(avb_fitter* ft, double* dx, const avb_options* o) {
     a.chunks = ft->d_chunks;
     a.part = ft->d_part;
     a.cpart = ft->d_cpart;
+    a.rec = ft->d_rec;
+    a.gstart = ft->d_gstart;
+    a.maxrb = ft->maxrb;
+    a.rec_stride = ft->rec_stride;
     a.gcur = ft->d_gcur;
     a.Hcur = ft->d_Hcur;
     a.state = ft->d_state;
@@ -761,7 +770,7 @@ int enqueue_solve(avb_fitter* ft, const LmBuf& la, const avb_options* o, int rou
     ++ft->launches;
     for (int r = 0; r < rounds; ++r) {
         CUDA_TRY(launch_lm_eval(ft->dm, ft->dp, la, ft->batch, ft->max_nj, o->jtj_precision == AVB_JTJ_FP64, st));
-        ft->launches += 2;
+        ft->launches += 3;
     }
     return AVB_OK;
 }

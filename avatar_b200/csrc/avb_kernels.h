@@ -52,7 +52,10 @@ struct LmBuf {
     unsigned short* mlist;       // [batch][V] matched vertices grouped by Jacobian column group
     int4* chunks;                // [batch][maxc] (group, start in mlist, count, -)
     double* part;                // [batch][maxc][pstride] A^T A partial per chunk (8x4 blocks of the upper triangle)
-    double* cpart;               // [batch][maxc] cost partial per chunk
+    double* cpart;               // [batch][maxrb] cost partial per 256 matched vertices
+    float* rec;                  // [batch][V][rec_stride] fp32 Jacobian records of the matched vertices
+    int* gstart;                 // [batch][kMaxGroups+1] group boundaries inside mlist
+    int maxrb, rec_stride;
     double* gcur;                // [batch][P]
     double* Hcur;                // [batch][P*P]
     LmState* state;              // [batch]
@@ -82,5 +85,6 @@ cudaError_t launch_lm_eval(const DevModel& M, const DevParts& Pt, const LmBuf& a
                            cudaStream_t st);
 long long lm_part_stride(int max_nj, int K);
 int lm_tab_doubles(int J, int K);
+int lm_rec_floats(int max_nj, int K);
 
 }  // namespace avb

@@ -60,6 +60,7 @@ lm_prep_kernel(DevModel M, DevParts Pt, LmBuf a) {
     for (int g = 0; g < Pt.numGroups; ++g) {
         const int b0 = Pt.gvstart[g], b1 = Pt.gvstart[g + 1];
         const int gbase = base;
+        if (tid == 0) a.gstart[(size_t)f * (kMaxGroups + 1) + g] = base;
         for (int i0 = b0; i0 < b1; i0 += nt) {
             const int i = i0 + tid;
             int v = 0, cv = 0;
@@ -87,6 +88,7 @@ lm_prep_kernel(DevModel M, DevParts Pt, LmBuf a) {
             ++nchunks;
         }
     }
+    if (tid == 0) a.gstart[(size_t)f * (kMaxGroups + 1) + Pt.numGroups] = base;
     ncorr = warp_sum_i(ncorr);
     if (lane == 0) iscr[32 + wid] = ncorr;
     __syncthreads();
@@ -135,99 +137,152 @@ lm_prep_kernel(DevModel M, DevParts Pt, LmBuf a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// lm_jac_kernel
+// lm_rows_kernel: one thread per matched vertex -> compact fp32 Jacobian record in HBM
 // ---------------------------------------------------------------------------------------------
-// One Jacobian row per thread (vertex t, coordinate r).  Tangent Jacobian in "global-frame rotation"
-// coordinates eta_j = G_parent(j) delta_j: block_j = R(-1,parent j) dRot Lq_j = -2 [y_j]x G_parent(j)
-// (AvatarOptimizer.cpp:529-565 in closed form); the change of coordinates is undone in lm_solve_kernel.
-__device__ __forceinline__ double jac_row(const DevModel& M, const double* tab, const double* w, int v, int r, int cntv,
-                                          const unsigned long long* sumv, const int* gj, int nj, float* Arow) {
+// Tangent Jacobian in "global-frame rotation" coordinates eta_j = G_parent(j) delta_j:
+// block_j = R(-1,parent j) dRot Lq_j = -2 [y_j]x G_parent(j) (AvatarOptimizer.cpp:529-565 in closed form); the
+// change of coordinates is undone in lm_solve_kernel.  Record of a vertex with count c (sc = sqrt(c)):
+//   [ 2 sc y_j (3 per group joint) | sc S (3 x K, row-major) | rho_hi(3) | rho_lo(3) | sc ],  rho = (c x - sum d)/sc
+__host__ __device__ inline int rec_floats(int nj, int K) { return 3 * nj + 3 * K + 7; }
+
+__global__ void __launch_bounds__(256)
+lm_rows_kernel(DevModel M, DevParts Pt, LmBuf a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int f = blockIdx.y, tid = threadIdx.x;
+    const LmState& st = a.state[f];
+    const int i = blockIdx.x * 256 + tid;
+    if (st.done || blockIdx.x * 256 >= st.nmatched) return;
     const int J = M.J, K = M.K;
+    double* tab = reinterpret_cast<double*>(smem_raw);
+    double* w = tab + a.tabD;
+    double* scr = w + ((K + 1) & ~1);
+    int* gstart = reinterpret_cast<int*>(scr + 32);
+    const double* gtab = a.tab + (size_t)f * a.tabD;
+    for (int q = tid; q < a.tabD; q += 256) tab[q] = gtab[q];
+    for (int q = tid; q < K; q += 256) w[q] = a.xt[(size_t)f * M.nx + 3 + 4 * J + q];
+    for (int q = tid; q <= Pt.numGroups; q += 256) gstart[q] = a.gstart[(size_t)f * (kMaxGroups + 1) + q];
+    // shapedirs rows of this block's vertices: one coalesced 3K-float row per warp pass, 8 rows in flight
+    float* s_sd = reinterpret_cast<float*>(gstart + kMaxGroups + 2);
+    int* s_v = reinterpret_cast<int*>(s_sd + 256 * 3 * K);
+    s_v[tid] = (i < st.nmatched) ? (int)a.mlist[(size_t)f * M.V + i] : -1;
+    __syncthreads();
+    {
+        const int lane = tid & 31, wid = tid >> 5, per = 3 * K;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const int t = wid * 32 + k;
+            const int vv = s_v[t];
+            if (vv >= 0)
+                for (int q = lane; q < per; q += 32) s_sd[t * per + q] = __ldg(M.sd + (size_t)vv * per + q);
+        }
+    }
+    __syncthreads();
     const double* G = tab;
     const double* pos = tab + 9 * J;
     const double* tau = tab + 12 * J;
     const double* C = tab + 15 * J;
-    const float* sd = M.sd + (size_t)v * 3 * K;
-    double v0[3];
+    double costv = 0.0;
+    if (i < st.nmatched) {
+        int g = 0;
+        while (g + 1 < Pt.numGroups && i >= gstart[g + 1]) ++g;
+        const int nj = Pt.gnj[g];
+        const int* gj = Pt.gjoints + g * kMaxJ;
+        const int v = s_v[tid];
+        float* rec = a.rec + (size_t)f * a.rec_stride * M.V + i;   // SoA: field q of vertex slot i at rec[q * V]
+        const size_t RS = (size_t)M.V;
+        const float* sd = s_sd + tid * 3 * K;
+        double v0[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        double s = 0;
-        for (int k = 0; k < K; ++k) s += (double)sd[c * K + k] * w[k];
-        v0[c] = M.vt[3 * (size_t)v + c] + s;
-    }
-    const int n = M.sk_n[v];
-    double xk[AVB_MAX_ASSIGN_][3], wk[AVB_MAX_ASSIGN_];
-    int jk[AVB_MAX_ASSIGN_];
-    uint32_t mk[AVB_MAX_ASSIGN_];
-    double x[3] = {0, 0, 0}, Br[3] = {0, 0, 0};
-#pragma unroll
-    for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
-        if (q < n) {
-            const int k = M.sk_j[4 * (size_t)v + q];
-            const double wt = M.sk_w[4 * (size_t)v + q];
-            const double* Gk = G + 9 * k;
-            jk[q] = k;
-            wk[q] = wt;
-            mk[q] = M.anc_mask[k];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                xk[q][c] = Gk[3 * c] * v0[0] + Gk[3 * c + 1] * v0[1] + Gk[3 * c + 2] * v0[2] + tau[3 * k + c];
-                x[c] += wt * xk[q][c];
-                Br[c] += wt * Gk[3 * r + c];   // row r of the blended rotation
-            }
-        } else {
-            jk[q] = 0; wk[q] = 0; mk[q] = 0;
-            xk[q][0] = xk[q][1] = xk[q][2] = 0;
+        for (int c = 0; c < 3; ++c) {
+            double s = 0;
+            for (int k = 0; k < K; ++k) s += (double)sd[c * K + k] * w[k];
+            v0[c] = M.vt[3 * (size_t)v + c] + s;
         }
-    }
-    const double cn = (double)cntv;
-    const double sc = sqrt(cn);
-    const float scf = (float)sc;
-    // root translation: identity (AvatarOptimizer.cpp:477-481)
-    Arow[0] = (r == 0) ? scf : 0.f;
-    Arow[1] = (r == 1) ? scf : 0.f;
-    Arow[2] = (r == 2) ? scf : 0.f;
-    for (int gi = 0; gi < nj; ++gi) {
-        const int j = gj[gi];
-        double y0 = 0, y1 = 0, y2 = 0, W = 0;
+        const int n = M.sk_n[v];
+        double xk[AVB_MAX_ASSIGN_][3], wk[AVB_MAX_ASSIGN_];
+        int jk[AVB_MAX_ASSIGN_];
+        uint32_t mk[AVB_MAX_ASSIGN_];
+        double x[3] = {0, 0, 0}, B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
         for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
-            if ((mk[q] >> j) & 1u) {
-                W += wk[q];
-                y0 += wk[q] * xk[q][0];
-                y1 += wk[q] * xk[q][1];
-                y2 += wk[q] * xk[q][2];
+            if (q < n) {
+                const int k = M.sk_j[4 * (size_t)v + q];
+                const double wt = M.sk_w[4 * (size_t)v + q];
+                const double* Gk = G + 9 * k;
+                jk[q] = k;
+                wk[q] = wt;
+                mk[q] = M.anc_mask[k];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    xk[q][c] = Gk[3 * c] * v0[0] + Gk[3 * c + 1] * v0[1] + Gk[3 * c + 2] * v0[2] + tau[3 * k + c];
+                    x[c] += wt * xk[q][c];
+                }
+#pragma unroll
+                for (int e = 0; e < 9; ++e) B[e] += wt * Gk[e];
+            } else {
+                jk[q] = 0; wk[q] = 0; mk[q] = 0;
+                xk[q][0] = xk[q][1] = xk[q][2] = 0;
             }
         }
-        const double s2 = 2.0 * sc;
-        const float f0 = (float)((y0 - W * pos[3 * j]) * s2);
-        const float f1 = (float)((y1 - W * pos[3 * j + 1]) * s2);
-        const float f2 = (float)((y2 - W * pos[3 * j + 2]) * s2);
-        const int c0 = 3 + 3 * gi;
-        // row r of -2 [y]x = [[0, 2y2, -2y1], [-2y2, 0, 2y0], [2y1, -2y0, 0]]
-        Arow[c0] = (r == 0) ? 0.f : (r == 1 ? -f2 : f1);
-        Arow[c0 + 1] = (r == 0) ? f2 : (r == 1 ? 0.f : -f0);
-        Arow[c0 + 2] = (r == 0) ? -f1 : (r == 1 ? f0 : 0.f);
-    }
-    // shape: row r of sum_k w_k (G_k (Delta_v - S_k) + H_k) = B Delta_v + sum_k w_k C_k  (AvatarOptimizer.cpp:568-580)
-    const int cs = 3 + 3 * nj;
-    for (int m = 0; m < K; ++m) {
-        double e = Br[0] * (double)sd[m] + Br[1] * (double)sd[K + m] + Br[2] * (double)sd[2 * K + m];
+        const double cn = (double)a.cnt[(size_t)f * M.V + v];
+        const double sc = sqrt(cn), s2 = 2.0 * sc;
+        for (int gi = 0; gi < nj; ++gi) {
+            const int j = gj[gi];
+            double y0 = 0, y1 = 0, y2 = 0, W = 0;
 #pragma unroll
-        for (int q = 0; q < AVB_MAX_ASSIGN_; ++q)
-            if (q < n) e += wk[q] * C[(size_t)jk[q] * 3 * K + r * K + m];
-        Arow[cs + m] = (float)(e * sc);
+            for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
+                if ((mk[q] >> j) & 1u) {
+                    W += wk[q];
+                    y0 += wk[q] * xk[q][0];
+                    y1 += wk[q] * xk[q][1];
+                    y2 += wk[q] * xk[q][2];
+                }
+            }
+            rec[(3 * gi) * RS] = (float)((y0 - W * pos[3 * j]) * s2);
+            rec[(3 * gi + 1) * RS] = (float)((y1 - W * pos[3 * j + 1]) * s2);
+            rec[(3 * gi + 2) * RS] = (float)((y2 - W * pos[3 * j + 2]) * s2);
+        }
+        // shape: sum_k w_k (G_k (Delta_v - S_k) + H_k) = B Delta_v + sum_k w_k C_k  (AvatarOptimizer.cpp:568-580)
+        float* rs = rec + (size_t)(3 * nj) * RS;
+        for (int m = 0; m < K; ++m) {
+            const double d0 = sd[m], d1 = sd[K + m], d2 = sd[2 * K + m];
+            double e0 = B[0] * d0 + B[1] * d1 + B[2] * d2;
+            double e1 = B[3] * d0 + B[4] * d1 + B[5] * d2;
+            double e2 = B[6] * d0 + B[7] * d1 + B[8] * d2;
+#pragma unroll
+            for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
+                if (q < n) {
+                    const double* Cq = C + (size_t)jk[q] * 3 * K;
+                    e0 += wk[q] * Cq[m];
+                    e1 += wk[q] * Cq[K + m];
+                    e2 += wk[q] * Cq[2 * K + m];
+                }
+            }
+            rs[m * RS] = (float)(e0 * sc);
+            rs[(K + m) * RS] = (float)(e1 * sc);
+            rs[(2 * K + m) * RS] = (float)(e2 * sc);
+        }
+        // residual sum of the vertex's correspondences, c x - sum d (AvatarOptimizer.cpp:632-639), split hi/lo
+        const unsigned long long* sumv = a.sum + 3 * ((size_t)f * M.V + v);
+        float* rr = rs + (size_t)(3 * K) * RS;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double sr = (double)(long long)sumv[c] * kFixInv;
+            const double rho = (cn * x[c] - sr) / sc;
+            const float hi = (float)rho;
+            rr[c * RS] = hi;
+            rr[(3 + c) * RS] = (float)(rho - (double)hi);
+            costv += x[c] * (cn * x[c] - 2.0 * sr);  // sum_i |x - d_i|^2 - sum_i |d_i|^2 = x . (c x - 2 s)
+        }
+        rr[6 * RS] = (float)sc;
     }
-    // residual sum of the vertex's correspondences, c x - sum d (AvatarOptimizer.cpp:632-639), split hi/lo
-    const double sr = (double)(long long)sumv[r] * kFixInv;
-    const double rho = (cn * x[r] - sr) / sc;
-    const float hi = (float)rho;
-    Arow[cs + K] = hi;
-    Arow[cs + K + 1] = (float)(rho - (double)hi);
-    // this coordinate's share of sum_i |x - d_i|^2 - sum_i |d_i|^2 = x . (c x - 2 s)
-    return x[r] * (cn * x[r] - 2.0 * sr);
+    const double cs = block_sum(costv, scr);
+    if (tid == 0) a.cpart[(size_t)f * a.maxrb + blockIdx.x] = cs;
 }
 
+// ---------------------------------------------------------------------------------------------
+// lm_syrk_kernel: A^T A of one chunk of Jacobian records (register-tiled, deterministic)
+// ---------------------------------------------------------------------------------------------
 // (block row of 8, block column of 4) pairs covering the upper triangle of an Lp x Lp matrix, Lp = 8 n
 __host__ __device__ inline int num_pairs(int n) { return n * n + n; }
 __device__ __forceinline__ void pair_to_blocks(int pair, int n, int& bi, int& bj) {
@@ -243,26 +298,17 @@ __device__ __forceinline__ void pair_to_blocks(int pair, int n, int& bi, int& bj
 
 template <typename AccT>
 __global__ void __launch_bounds__(kJacThreads, 2)
-lm_jac_kernel(DevModel M, DevParts Pt, LmBuf a) {
+lm_syrk_kernel(DevModel M, DevParts Pt, LmBuf a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int c = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
     const LmState& st = a.state[f];
     if (st.done || c >= st.nchunks) return;
-    const int J = M.J, K = M.K;
+    const int K = M.K;
     const int4 ch = a.chunks[(size_t)f * a.maxc + c];
     const int g = ch.x, start = ch.y, count = ch.z;
     const int nj = Pt.gnj[g];
     const int L = group_L(nj, K), Lp = (L + 7) & ~7, lda = Lp + 4;
-    double* tab = reinterpret_cast<double*>(smem_raw);
-    double* w = tab + a.tabD;
-    double* scr = w + ((K + 1) & ~1);
-    int* gj = reinterpret_cast<int*>(scr + 32);
-    float* A = reinterpret_cast<float*>(gj + kMaxJ);
-
-    const double* gtab = a.tab + (size_t)f * a.tabD;
-    for (int i = tid; i < a.tabD; i += kJacThreads) tab[i] = gtab[i];
-    for (int i = tid; i < K; i += kJacThreads) w[i] = a.xt[(size_t)f * M.nx + 3 + 4 * J + i];
-    for (int i = tid; i < nj; i += kJacThreads) gj[i] = Pt.gjoints[g * kMaxJ + i];
+    float* A = reinterpret_cast<float*>(smem_raw);   // [3 * kTile][lda] Jacobian rows of the current tile
 
     // syrk role: (block pair, row group); the row groups of a pair are adjacent lanes (shuffle reduction)
     const int n = Lp >> 3, npairs = num_pairs(n);
@@ -277,20 +323,53 @@ lm_jac_kernel(DevModel M, DevParts Pt, LmBuf a) {
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = AccT(0);
-    double cost_acc = 0.0;
-    const unsigned short* mlist = a.mlist + (size_t)f * M.V + start;
-    const int* cnt = a.cnt + (size_t)f * M.V;
-    const unsigned long long* sum = a.sum + (size_t)f * 3 * M.V;
+    const float* recs = a.rec + (size_t)f * a.rec_stride * M.V + start;
+    const size_t RS = (size_t)M.V;
+    const int cs = 3 + 3 * nj;
+    const int nf = rec_floats(nj, K);
+    // structural zeros of the tile (diagonal of every cross-product block, pad columns, off-diagonal of the
+    // translation block) are written once: the scatter below never touches them
+    for (int e = tid; e < 3 * kTile * lda; e += kJacThreads) A[e] = 0.f;
     __syncthreads();
 
     for (int t0 = 0; t0 < count; t0 += kTile) {
         const int nv = min(kTile, count - t0);
-        if (tid < 3 * nv) {
-            const int t = tid / 3, r = tid - 3 * t;
-            const int v = mlist[t0 + t];
-            float* Arow = A + (size_t)tid * lda;
-            for (int q = L; q < Lp; ++q) Arow[q] = 0.f;
-            cost_acc += jac_row(M, tab, w, v, r, cnt[v], sum + 3 * (size_t)v, gj, nj, Arow);
+        // coalesced load of the tile's SoA records (field q, vertex t), kLd loads in flight per thread, then
+        // scatter into Jacobian rows
+        constexpr int kLd = 10;
+        for (int e0 = tid; e0 < nf * kTile; e0 += kJacThreads * kLd) {
+            float vals[kLd];
+#pragma unroll
+            for (int k = 0; k < kLd; ++k) {
+                const int e = e0 + k * kJacThreads;
+                const int q = e / kTile, t = e - q * kTile;
+                vals[k] = (e < nf * kTile && t < nv) ? __ldg(recs + (size_t)q * RS + t0 + t) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < kLd; ++k) {
+                const int e = e0 + k * kJacThreads;
+                const int q = e / kTile, t = e - q * kTile;
+                if (e >= nf * kTile || t >= nv) continue;
+                const float val = vals[k];
+                float* A3 = A + (size_t)(3 * t) * lda;
+                if (q < 3 * nj) {
+                    // f_c of joint gi sits at (row (c+1)%3, col (c+2)%3) with + and at (row (c+2)%3, col (c+1)%3) with -
+                    const int gi = q / 3, cc = q - 3 * gi, c0 = 3 + 3 * gi;
+                    const int r1 = (cc + 1) % 3, r2 = (cc + 2) % 3;
+                    A3[(size_t)r1 * lda + c0 + r2] = val;
+                    A3[(size_t)r2 * lda + c0 + r1] = -val;
+                } else if (q < 3 * nj + 3 * K) {
+                    const int rm = q - 3 * nj, r = rm / K, m = rm - r * K;
+                    A3[(size_t)r * lda + cs + m] = val;
+                } else if (q < 3 * nj + 3 * K + 6) {
+                    const int e2 = q - 3 * nj - 3 * K, hl = e2 / 3, r = e2 - 3 * hl;
+                    A3[(size_t)r * lda + cs + K + hl] = val;
+                } else {  // sc: root translation block sc * I (AvatarOptimizer.cpp:477-481)
+                    A3[0] = val;
+                    A3[(size_t)lda + 1] = val;
+                    A3[(size_t)2 * lda + 2] = val;
+                }
+            }
         }
         __syncthreads();
         if (active) {
@@ -328,8 +407,6 @@ lm_jac_kernel(DevModel M, DevParts Pt, LmBuf a) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) p[i * 4 + j] = (double)acc[i][j];
     }
-    const double cs = block_sum(cost_acc, scr);
-    if (tid == 0) a.cpart[(size_t)f * a.maxc + c] = cs;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -465,9 +542,9 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
             else if (qb == L - 1) S.glo[ca] += val;
             else S.Hs[(size_t)ca * P + colmap(qb)] += val;
         }
-        csum += a.cpart[(size_t)f * a.maxc + c];
         __syncthreads();
     }
+    for (int b = 0; b * 256 < st.nmatched; ++b) csum += a.cpart[(size_t)f * a.maxrb + b];
     double cost_t = 0.5 * (csum + st.Qsum);
     for (int i = tid; i < P; i += kSolveThreads) S.gs[i] += S.glo[i];
     for (int i = tid; i < P * P; i += kSolveThreads) {
@@ -741,9 +818,13 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
 size_t lm_prep_smem(const DevModel& M) {
     return (size_t)(((M.nx + 1) & ~1) + tables_doubles(M.J, M.K, true) + 64) * 8 + 64 * 4 + 64;
 }
-size_t lm_jac_smem(const DevModel& M, int max_nj) {
+size_t lm_rows_smem(const DevModel& M) {
+    return (size_t)(tab_doubles(M.J, M.K) + ((M.K + 1) & ~1) + 32) * 8 + (kMaxGroups + 2) * 4 + (size_t)256 * 3 * M.K * 4 + 256 * 4 + 64;
+}
+size_t lm_syrk_smem(const DevModel& M, int max_nj, bool acc64) {
     const int L = group_L(max_nj, M.K), Lp = (L + 7) & ~7, lda = Lp + 4;
-    return (size_t)(tab_doubles(M.J, M.K) + ((M.K + 1) & ~1) + 32) * 8 + kMaxJ * 4 + (size_t)3 * kTile * lda * 4 + 64;
+    (void)acc64;
+    return (size_t)3 * kTile * lda * 4 + 64;
 }
 
 cudaError_t launch_lm_prep(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, cudaStream_t st) {
@@ -753,18 +834,21 @@ cudaError_t launch_lm_prep(const DevModel& M, const DevParts& Pt, const LmBuf& a
 
 cudaError_t launch_lm_eval(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, int max_nj, bool acc64,
                            cudaStream_t st) {
-    const size_t jsm = lm_jac_smem(M, max_nj);
+    const size_t jsm = lm_syrk_smem(M, max_nj, acc64);
     const size_t ssm = solve_smem_bytes(M.J, M.K, M.gmmC);
-    cudaError_t e = acc64 ? cudaFuncSetAttribute(lm_jac_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm)
-                          : cudaFuncSetAttribute(lm_jac_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm);
+    cudaError_t e = acc64 ? cudaFuncSetAttribute(lm_syrk_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm)
+                          : cudaFuncSetAttribute(lm_syrk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(lm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
     if (e != cudaSuccess) return e;
+    lm_rows_kernel<<<dim3(a.maxrb, batch), 256, lm_rows_smem(M), st>>>(M, Pt, a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
     const dim3 grid(a.maxc, batch);
     if (acc64)
-        lm_jac_kernel<double><<<grid, kJacThreads, jsm, st>>>(M, Pt, a);
+        lm_syrk_kernel<double><<<grid, kJacThreads, jsm, st>>>(M, Pt, a);
     else
-        lm_jac_kernel<float><<<grid, kJacThreads, jsm, st>>>(M, Pt, a);
+        lm_syrk_kernel<float><<<grid, kJacThreads, jsm, st>>>(M, Pt, a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     lm_solve_kernel<<<batch, kSolveThreads, ssm, st>>>(M, Pt, a);
@@ -776,5 +860,6 @@ long long lm_part_stride(int max_nj, int K) {
     return (long long)num_pairs(Lp >> 3) * 32;
 }
 int lm_tab_doubles(int J, int K) { return tab_doubles(J, K); }
+int lm_rec_floats(int max_nj, int K) { return (rec_floats(max_nj, K) + 3) & ~3; }
 
 }  // namespace avb
