@@ -98,7 +98,7 @@ struct avb_fitter {
     double *d_xt = nullptr, *d_tab = nullptr, *d_part = nullptr, *d_cpart = nullptr, *d_gcur = nullptr;
     unsigned short* d_mlist = nullptr; int4* d_chunks = nullptr; LmState* d_state = nullptr;
     float* d_rec = nullptr; int* d_gstart = nullptr; int maxrb = 0, rec_stride = 0;
-    int maxc = 0, tabD = 0, max_nj = 0, chunk_verts = 128;
+    int maxc = 0, tabD = 0, max_nj = 0, chunk_verts = 256;
     long long pstride = 0;
     int *d_chunk_frame = nullptr, *d_chunk_count = nullptr, *d_chunk_qblock = nullptr, *d_frame_qblock = nullptr;
     long long* d_chunk_begin = nullptr;
@@ -543,7 +543,7 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     TRY(dev_put(ft, &dp.part_start, part_start));
     TRY(dev_put(ft, &dp.part_verts, part_verts));
     TRY(dev_put(ft, &dp.first_part_at, first_part_at));
-    int max_groups = 4;
+    int max_groups = 8;
     if (const char* e = std::getenv("AVB_GROUPS")) max_groups = std::max(1, std::min(kMaxGroups, std::atoi(e)));
     std::vector<int> gorder, gvstart, gjoints, gnj;
     build_groups(*m, max_groups, gorder, gvstart, gjoints, gnj);

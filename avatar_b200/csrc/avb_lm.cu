@@ -2,16 +2,18 @@
 //
 //   lm_prep_kernel   grid = frames            matched-vertex lists per Jacobian column group, chunk list,
 //                                             #correspondences, sum |d|^2, LM state, joint tables at x.
-//   lm_jac_kernel    grid = chunks x frames   residual statistics + analytic Jacobian rows of up to 256 matched
-//                                             vertices (AvatarOptimizer.cpp:505-582 in closed form), and their
-//                                             contribution to J^T J and J^T r as register-tiled A^T A; one
-//                                             deterministic partial per chunk.
+//   lm_rows_kernel   grid = 256-vertex blocks x frames   one thread per matched vertex: position, residual
+//                                             statistics and the analytic Jacobian (AvatarOptimizer.cpp:505-582 in
+//                                             closed form) as a compact fp32 record (SoA) in HBM; cost partial.
+//   lm_syrk_kernel   grid = chunks x frames   expands the records of up to 256 matched vertices into Jacobian rows in
+//                                             shared memory and accumulates their J^T J / J^T r contribution as a
+//                                             register-tiled A^T A; one deterministic partial per chunk.
 //   lm_solve_kernel  grid = frames            partial reduction in chunk order, priors (:661-692, :708-723),
 //                                             Levenberg-Marquardt step control, damped Cholesky solve, retraction
 //                                             (:123-143), joint tables of the next trial point.
 //
-// One evaluation = lm_jac_kernel + lm_solve_kernel; 1 + maxItersPerICP evaluations per ICP iteration, enqueued
-// back to back on one stream with no host round trip (frames that converged early skip their CTAs).
+// One evaluation = rows + syrk + solve; 1 + maxItersPerICP evaluations per ICP iteration, enqueued back to back on
+// one stream with no host round trip (frames that converged early skip their CTAs).
 //
 // Numerics: geometry, residuals, cost, gradient and the linear algebra are fp64.  Jacobian rows are staged in
 // shared memory as fp32 (they only scale the residual in J^T r, so their 6e-8 rounding moves the fixed point by

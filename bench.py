@@ -194,6 +194,8 @@ def main():
     ap.add_argument("--frames", type=int, default=512, help="frames per GPU per step")
     ap.add_argument("--jtj", default="fp64", choices=["fp64", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("AVB_LANES", "2")),
+                    help="split the rank's batch over this many fitters (streams) that run concurrently")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -225,7 +227,16 @@ def main():
     h_x = pinned_array(_lib.lib, (F, nx), np.float64)
     h_pts[:] = np.concatenate(pts)
     h_lab[:] = np.concatenate(labs)
-    ft = Fitter(model, num_parts, part_map, F, total + 16, local_rank)
+    # lanes: contiguous sub-batches, one fitter (device buffers + stream) each; their kernels overlap on the GPU
+    NL = max(1, min(args.lanes, F))
+    bounds = [shard.frame_range(F, l, NL) for l in range(NL)]
+    lanes = []
+    for lo, hi in bounds:
+        npts = int(off[hi] - off[lo])
+        lanes.append(dict(ft=Fitter(model, num_parts, part_map, hi - lo, npts + 16, local_rank), lo=lo, hi=hi,
+                          pts=h_pts[off[lo]:off[hi]], lab=h_lab[off[lo]:off[hi]], off=(off[lo:hi + 1] - off[lo]).copy(),
+                          x0=np.ascontiguousarray(x0[lo:hi])))
+    ft = lanes[0]["ft"]
     opt = default_options()
     opt.function_tolerance = 0.0      # run all 10 LM iterations: no early exit inside the timed region
     opt.jtj_precision = _lib.JTJ_FP64 if args.jtj == "fp64" else _lib.JTJ_FP32
@@ -234,38 +245,53 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        ft.synchronize()
+        for ln in lanes:
+            ln["ft"].synchronize()
 
     # ---- value: inputs resident in HBM ----
-    ft.upload(h_pts, h_lab, off)
+    for ln in lanes:
+        ln["ft"].upload(ln["pts"], ln["lab"], ln["off"])
     for _ in range(args.warmup):
-        ft.fit_resident(x0, opt)
+        for ln in lanes:
+            ln["ft"].fit_resident(ln["x0"], opt)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     t0 = time.perf_counter()
-    ft.timer_start()
+    for ln in lanes:
+        ln["ft"].timer_start()
     for _ in range(args.steps):
-        ft.fit_resident(x0, opt)
-    dev_ms = ft.timer_stop()
+        for ln in lanes:
+            ln["ft"].fit_resident(ln["x0"], opt)
+    dev_ms = max(ln["ft"].timer_stop() for ln in lanes)
     barrier()
     t1 = time.perf_counter()
-    launches_per_step = ft.launch_count()
+    launches_per_step = sum(ln["ft"].launch_count() for ln in lanes)
     step_ms, per4 = ft.device_ms()
-    xr, stats, _ = ft.download()
+    stats = []
+    for ln in lanes:
+        stats += ln["ft"].download()[1]
     dev_ms = shard.max_over_ranks(dev_ms, dev)
     value = F * world * args.steps / (dev_ms * 1e-3)
 
     # ---- e2e: host buffers in, parameters out, through the public batch call ----
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(NL)
+
+    def lane_e2e(ln):
+        h_x[ln["lo"]:ln["hi"]] = ln["x0"]
+        x, st, _ = ln["ft"].fit_batch(ln["pts"], ln["lab"], ln["off"], h_x[ln["lo"]:ln["hi"]], opt)
+        return x
+
     def e2e_step():
-        h_x[:] = x0
-        x, st, _ = ft.fit_batch(h_pts, h_lab, off, h_x, opt)
+        xs = list(pool.map(lane_e2e, lanes)) if NL > 1 else [lane_e2e(lanes[0])]
+        x = np.concatenate(xs)
         full = shard.gather_params(x, F * world, rank, world, dev) if world > 1 else x
-        return full, st
+        return full
     e2e_step()
     barrier()
     t2 = time.perf_counter()
     for _ in range(args.steps):
-        full, st = e2e_step()
+        full = e2e_step()
     barrier()
     t3 = time.perf_counter()
     e2e_s = shard.max_over_ranks(t3 - t2, dev)
@@ -311,6 +337,7 @@ def main():
                        "frames_per_gpu": F, "mean_points_per_frame": float(npts.mean()),
                        "mean_matched_vertices": float(nmatch.mean()), "mean_lm_iterations": float(iters.mean()),
                        "mean_correspondences": float(ncorr.mean()), "solver": "gn_lm", "jtj": args.jtj,
+                       "lanes": NL,
                        "l2": "inputs larger than L2: %.0f MB of clouds+labels per step" % (total * 28 / 1e6)},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_s / args.steps, "timer": "wall clock around synchronised steps"},
