@@ -64,6 +64,7 @@ SYMBOLS = [
     ("avb_avatar_update", C.c_int, [_P, C.c_int, _P, _P, _P, _P]),
     ("avb_fit", C.c_int, [_P, _P, _P, C.c_int32, _P, C.POINTER(Options), _P, _P]),
     ("avb_fit_batch", C.c_int, [_P, C.c_int32, _P, _P, _P, _P, C.POINTER(Options), _P, _P]),
+    ("avb_track_sequence", C.c_int, [_P, C.c_int32, _P, _P, _P, _P, C.POINTER(Options), _P, _P]),
     ("avb_upload_batch", C.c_int, [_P, C.c_int32, _P, _P, _P]),
     ("avb_fit_resident", C.c_int, [_P, _P, C.POINTER(Options)]),
     ("avb_download_results", C.c_int, [_P, _P, _P, _P]),

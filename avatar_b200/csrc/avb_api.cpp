@@ -115,6 +115,11 @@ struct avb_fitter {
     std::vector<int64_t> offsets;
     int launches = 0;
     int n_events = 0;
+    // tracking mode (avb_track_sequence)
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> copied;
+    double* d_xseq = nullptr; FrameStats* d_stats_seq = nullptr; int seq_cap = 0;
+    FrameStats* h_stats_seq = nullptr; double* h_xseq = nullptr;
     int last_icp = 0;
 };
 
@@ -458,6 +463,8 @@ void avb_fitter_destroy(avb_fitter* ft) {
     for (void* p : ft->pinned) cudaFreeHost(p);
     for (auto& e : ft->ev)
         if (e) cudaEventDestroy(e);
+    for (auto& e : ft->copied) cudaEventDestroy(e);
+    if (ft->copy_stream) cudaStreamDestroy(ft->copy_stream);
     if (ft->stream) cudaStreamDestroy(ft->stream);
     delete ft;
 }
@@ -629,7 +636,7 @@ int avb_upload_batch(avb_fitter* ft, int32_t batch, const double* clouds, const 
     const int64_t o0 = offsets[0];
     // NN chunk schedule: every frame is cut into equal chunks (multiples of 512 points) so that the
     // grid has about 4 CTAs per SM; |d|^2 partials are always per 256 points, independent of the cut.
-    const int64_t target = std::max<int64_t>(512, (total / (4 * (int64_t)ft->num_sms) + 511) / 512 * 512);
+    int64_t target = std::max<int64_t>(512, (total / (4 * (int64_t)ft->num_sms) + 511) / 512 * 512);
     int nc = 0;
     int qb = 0;
     for (int f = 0; f < batch; ++f) {
@@ -911,6 +918,129 @@ int avb_avatar_update(avb_fitter* ft, int batch, const double* x, double* cloud,
     if (joint_pos) CUDA_TRY(cudaMemcpyAsync(joint_pos, ft->d_jpos, (size_t)batch * 3 * J * 8, cudaMemcpyDeviceToHost, st));
     if (joint_trans) CUDA_TRY(cudaMemcpyAsync(joint_trans, ft->d_jtrans, (size_t)batch * 12 * J * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return AVB_OK;
+}
+
+/* ---------------- tracking mode (BASELINE.json configs[3]) ---------------- */
+int avb_track_sequence(avb_fitter* ft, int32_t T, const double* clouds, const int32_t* labels, const int64_t* offsets,
+                       const double* x0, const avb_options* o, double* x_out, avb_stats* stats) {
+    if (!ft || !offsets || !x0 || !x_out || T <= 0) return fail(AVB_ERR_INVALID, "null argument or empty sequence");
+    int rc = check_options(ft, o);
+    if (rc != AVB_OK) return rc;
+    const int64_t total = offsets[T] - offsets[0], o0 = offsets[0];
+    if (total < 0 || total > ft->max_points) return fail(AVB_ERR_CAPACITY, "sequence point count exceeds fitter capacity");
+    if (total > 0 && (!clouds || !labels)) return fail(AVB_ERR_INVALID, "null cloud or labels");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    cudaStream_t st = ft->stream;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (!ft->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ft->copy_stream, cudaStreamNonBlocking));
+    while ((int)ft->copied.size() < T) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ft->copied.push_back(e);
+    }
+    const size_t nx = ft->model->nx, V = ft->model->V;
+    if (ft->seq_cap < T) {
+        rc = dev_alloc(ft, &ft->d_xseq, (size_t)T * nx);
+        if (rc == AVB_OK) rc = dev_alloc(ft, &ft->d_stats_seq, (size_t)T);
+        if (rc == AVB_OK) rc = pin_alloc(ft, &ft->h_xseq, (size_t)T * nx);
+        if (rc == AVB_OK) rc = pin_alloc(ft, &ft->h_stats_seq, (size_t)T);
+        if (rc != AVB_OK) return rc;
+        ft->seq_cap = T;
+    }
+    // per-frame NN chunk schedule; every frame is "frame 0" of a batch of one
+    std::vector<int> c0(T + 1, 0), q0(T + 1, 0);
+    int nc = 0, qb = 0;
+    for (int t = 0; t < T; ++t) {
+        const int64_t n = offsets[t + 1] - offsets[t];
+        if (n < 0 || n > ((int64_t)1 << 21)) return fail(AVB_ERR_INVALID, "bad offsets");
+        c0[t] = nc;
+        q0[t] = qb;
+        if (n > 0) {
+            const int64_t target = std::max<int64_t>(512, (n / (4 * (int64_t)ft->num_sms) + 511) / 512 * 512);
+            for (int64_t b = 0; b < n; b += target) {
+                if (nc >= ft->max_chunks) return fail(AVB_ERR_CAPACITY, "too many NN chunks for this fitter (raise max_total_points)");
+                ft->h_chunk_frame[nc] = 0;
+                ft->h_chunk_begin[nc] = offsets[t] - o0 + b;
+                ft->h_chunk_count[nc] = (int)std::min<int64_t>(target, n - b);
+                ft->h_chunk_qblock[nc] = (int)(b / kQBlock);   // relative to the frame's first |d|^2 block
+                ++nc;
+            }
+            qb += (int)((n + kQBlock - 1) / kQBlock);
+        }
+    }
+    c0[T] = nc;
+    q0[T] = qb;
+    if (qb > ft->max_qblocks) return fail(AVB_ERR_CAPACITY, "too many |d|^2 blocks");
+    if (nc > 0) {
+        CUDA_TRY(cudaMemcpyAsync(ft->d_chunk_frame, ft->h_chunk_frame, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ft->d_chunk_begin, ft->h_chunk_begin, (size_t)nc * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ft->d_chunk_count, ft->h_chunk_count, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ft->d_chunk_qblock, ft->h_chunk_qblock, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
+    }
+    std::memcpy(ft->h_x, x0, nx * 8);
+    CUDA_TRY(cudaMemcpyAsync(ft->d_x, ft->h_x, nx * 8, cudaMemcpyHostToDevice, st));
+    // uploads run ahead on the copy stream, one event per frame
+    for (int t = 0; t < T; ++t) {
+        const int64_t n = offsets[t + 1] - offsets[t], b = offsets[t] - o0;
+        if (n > 0) {
+            CUDA_TRY(cudaMemcpyAsync(ft->d_data + 3 * b, clouds + 3 * offsets[t], (size_t)n * 24, cudaMemcpyHostToDevice, ft->copy_stream));
+            CUDA_TRY(cudaMemcpyAsync(ft->d_labels + b, labels + offsets[t], (size_t)n * 4, cudaMemcpyHostToDevice, ft->copy_stream));
+        }
+        CUDA_TRY(cudaEventRecord(ft->copied[t], ft->copy_stream));
+    }
+    ft->batch = 1;
+    ft->launches = 0;
+    ft->last_icp = 0;
+    const int all_chunks = ft->num_chunks;
+    // the |d|^2 partials of frame t live at d_qpart[0 ..): frame_qblock = {0, nblocks_t}
+    for (int t = 0; t < T; ++t) {
+        CUDA_TRY(cudaStreamWaitEvent(st, ft->copied[t], 0));
+        const int fq[2] = {0, q0[t + 1] - q0[t]};
+        ft->h_frame_qblock[0] = fq[0];
+        ft->h_frame_qblock[1] = fq[1];
+        CUDA_TRY(cudaMemcpyAsync(ft->d_frame_qblock, ft->h_frame_qblock, 8, cudaMemcpyHostToDevice, st));
+        // h_frame_qblock is rewritten next iteration: the copy above must have been consumed (tiny; sync the copy only)
+        cudaEvent_t ev = ft->ev[6];
+        CUDA_TRY(cudaEventRecord(ev, st));
+        for (int icp = 0; icp < o->icp_iters; ++icp) {
+            // chunk views of this frame
+            int* sv_frame = ft->d_chunk_frame; long long* sv_begin = ft->d_chunk_begin;
+            int* sv_count = ft->d_chunk_count; int* sv_qb = ft->d_chunk_qblock;
+            ft->d_chunk_frame += c0[t]; ft->d_chunk_begin += c0[t]; ft->d_chunk_count += c0[t]; ft->d_chunk_qblock += c0[t];
+            ft->num_chunks = c0[t + 1] - c0[t];
+            rc = enqueue_correspond(ft, ft->d_x, o, nullptr);
+            ft->d_chunk_frame = sv_frame; ft->d_chunk_begin = sv_begin; ft->d_chunk_count = sv_count; ft->d_chunk_qblock = sv_qb;
+            if (rc != AVB_OK) { ft->num_chunks = all_chunks; return rc; }
+            LmBuf la = lm_buf(ft, ft->d_x, o);
+            rc = enqueue_solve(ft, la, o, 1 + o->max_iters_per_icp);
+            if (rc != AVB_OK) { ft->num_chunks = all_chunks; return rc; }
+        }
+        CUDA_TRY(cudaMemcpyAsync(ft->d_xseq + (size_t)t * nx, ft->d_x, nx * 8, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ft->d_stats_seq + t, ft->d_stats, sizeof(FrameStats), cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaEventSynchronize(ev));
+    }
+    ft->num_chunks = all_chunks;
+    // trailing ava.update() of the last frame so that AVB_TAP_CLOUD / avb_download_results see it
+    PoseArgs pa = pose_args(ft, ft->d_x, false, o);
+    CUDA_TRY(launch_pose_visibility(ft->dm, ft->dp, pa, 1, st));
+    CUDA_TRY(cudaMemcpyAsync(ft->h_xseq, ft->d_xseq, (size_t)T * nx * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ft->h_stats_seq, ft->d_stats_seq, (size_t)T * sizeof(FrameStats), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    std::memcpy(x_out, ft->h_xseq, (size_t)T * nx * 8);
+    ft->offsets.assign(2, 0);
+    ft->offsets[1] = offsets[T] - offsets[T - 1];
+    ft->total_points = ft->offsets[1];
+    (void)V;
+    int worst = AVB_OK;
+    for (int t = 0; t < T; ++t) {
+        if (stats) {
+            std::memcpy(&stats[t], &ft->h_stats_seq[t], sizeof(avb_stats));
+            stats[t].num_points = (int32_t)(offsets[t + 1] - offsets[t]);
+        }
+        if (ft->h_stats_seq[t].status != AVB_OK) worst = ft->h_stats_seq[t].status;
+    }
+    if (worst != AVB_OK) return fail(AVB_ERR_NUMERIC, "a frame held non-finite / out-of-range input (see stats[t].status)");
     return AVB_OK;
 }
 

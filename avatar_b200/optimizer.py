@@ -88,6 +88,21 @@ class Fitter:
         self.total_points = int(offsets[-1] - offsets[0])
         return x, list(stats), cloud
 
+    def track_sequence(self, clouds, labels, offsets, x0, opt):
+        """configs[3]: fit T frames in order, each warm-started from the previous fit; returns x [T][nx], stats"""
+        clouds = np.ascontiguousarray(clouds, dtype=np.float64)
+        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        T = offsets.shape[0] - 1
+        x = np.zeros((T, self.nx))
+        stats = (_lib.Stats * T)()
+        check(lib.avb_track_sequence(self.handle, T, ptr(clouds), ptr(labels), ptr(offsets), ptr(x0), C.byref(opt),
+                                     ptr(x), stats))
+        self.batch = 1
+        self.total_points = int(offsets[-1] - offsets[-2])
+        return x, list(stats)
+
     # parity taps
     def debug_correspond(self, x, opt):
         x = np.ascontiguousarray(x, dtype=np.float64)

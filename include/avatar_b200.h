@@ -150,6 +150,15 @@ int avb_fit_batch(avb_fitter* fitter, int32_t batch, const double* data_clouds,
                   const int32_t* data_part_labels, const int64_t* offsets, double* x,
                   const avb_options* opt, avb_stats* stats, double* cloud_out);
 
+/* Tracking mode (BASELINE.json configs[3]): ONE sequence of T frames fitted in order, frame t warm-started from the
+ * fit of frame t-1 -- what the reference's callers do by keeping `ava` between frames (demo.cpp:252-268,
+ * live-demo.cpp:405-432).  All clouds are passed at once (concatenated, offsets[T+1]); their H2D copies run ahead on
+ * a copy stream (one event per frame) while earlier frames are being fitted, and the parameter vector never leaves
+ * the device between frames.  x0: start of frame 0 [nx]; x_out: [T][nx]; stats: [T] (nullable). */
+int avb_track_sequence(avb_fitter* fitter, int32_t T, const double* data_clouds, const int32_t* data_part_labels,
+                       const int64_t* offsets, const double* x0, const avb_options* opt, double* x_out,
+                       avb_stats* stats);
+
 /* Split form of avb_fit_batch for callers that keep inputs resident on the device
  * (bench.py `value`): upload once, fit many times from different warm starts, download. */
 int avb_upload_batch(avb_fitter* fitter, int32_t batch, const double* data_clouds,

@@ -231,3 +231,63 @@ def ava_params_from(x, oracle_mod):
     for j in range(24):
         x[3 + 4 * j:7 + 4 * j] = oracle_mod.rotmat_to_quat(oracle_mod.quat_to_rotmat(x[3 + 4 * j:7 + 4 * j]))
     return x
+
+
+def test_tracking_sequence_matches_oracle(model, oracle_mod, oopt, omodel, prior_arrays):
+    """BASELINE.json configs[3]: frames fitted in order, each warm-started from the previous fit (demo.cpp:252-268)"""
+    from avatar_b200 import Fitter, synth
+    rng = np.random.default_rng(77)
+    xa, xb = synth.random_params(model, rng), synth.random_params(model, rng)
+    T = 5
+    pts, labs, xs_gt = [], [], []
+    for t in range(T):
+        a = t / (T - 1) * 0.25                       # a slow motion from pose a toward pose b
+        x = (1 - a) * xa + a * xb
+        q = x[3:99].reshape(24, 4)
+        q /= np.linalg.norm(q, axis=1, keepdims=True)
+        x[:3] = xa[:3]
+        cloud, _, _ = omodel.update_x(x)
+        p, l, _, _ = synth.render_cloud(model, cloud, prior_arrays["part_map"], interval=2)
+        pts.append(p)
+        labs.append(l)
+        xs_gt.append(x)
+    off = np.cumsum([0] + [len(p) for p in pts])
+    x0 = synth.perturbed_start(model, xs_gt[0], rng, rot_sigma=0.05)
+    ft = Fitter(model, int(prior_arrays["num_parts"]), prior_arrays["part_map"], 1, int(off[-1]) + 64)
+    o = _opts(icp_iters=2)
+    x, stats = ft.track_sequence(np.concatenate(pts), np.concatenate(labs), off, x0, o)
+    oo = oracle_mod.default_options(oracle_mod.SOLVER_GN_LM)
+    oo.icp_iters = 2
+    xo = x0
+    for t in range(T):
+        xo, st, _, _ = oopt.optimize(pts[t], labs[t], xo, oo)
+        assert np.abs(x[t] - xo).max() < PARAM_TOL, (t, np.abs(x[t] - xo).max())
+        assert stats[t].num_correspondences == st.num_correspondences and stats[t].num_points == len(pts[t])
+    # the same fitter still serves ordinary calls afterwards
+    x1, _, _ = ft.fit_batch(pts[0], labs[0], np.array([0, len(pts[0])]), x0[None], o)
+    assert np.abs(x1[0] - x[0]).max() == 0.0
+    ft.close()
+
+
+def test_stress_dense_cloud_many_iterations(model, oracle_mod, oopt, omodel, prior_arrays):
+    """BASELINE.json configs[4] shape: a dense (>150k points) cloud and up to 50 LM iterations; fp64 J^T J path
+    (the bf16 tensor-core variant named there is not implemented in round 1)"""
+    from avatar_b200 import Fitter, synth
+    rng = np.random.default_rng(5)
+    x_gt = synth.random_params(model, rng)
+    x_gt[2] = 2.3
+    x0 = synth.perturbed_start(model, x_gt, rng)
+    cloud, _, _ = omodel.update_x(x_gt)
+    pts, lab, _, _ = synth.render_cloud(model, cloud, prior_arrays["part_map"], width=2560, height=2304,
+                                        fx=2016.0, fy=2016.0, cx=1280.0, cy=1152.0)
+    assert len(pts) > 150000
+    ft = Fitter(model, int(prior_arrays["num_parts"]), prior_arrays["part_map"], 1, len(pts) + 64)
+    o = _opts(max_iters_per_icp=50, function_tolerance=1e-7)
+    x, stats, _ = ft.fit_batch(pts, lab, np.array([0, len(pts)]), x0[None], o)
+    oo = oracle_mod.default_options(oracle_mod.SOLVER_GN_LM)
+    oo.max_iters_per_icp, oo.function_tolerance = 50, 1e-7
+    xo, st, _, nn = oopt.optimize(pts, lab, x0, oo)
+    assert stats[0].iterations == st.iterations
+    assert np.abs(x[0] - xo).max() < PARAM_TOL
+    assert stats[0].num_correspondences == st.num_correspondences == (nn >= 0).sum()
+    ft.close()
