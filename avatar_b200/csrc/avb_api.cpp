@@ -115,6 +115,10 @@ struct avb_fitter {
     std::vector<int64_t> offsets;
     int launches = 0;
     int n_events = 0;
+    // per-kernel profiling (avb_set_profiling): events around every launch of the next avb_fit_resident
+    bool profile = false;
+    std::vector<cudaEvent_t> pev;   // pairs (begin, end)
+    std::vector<int> pcls;          // kernel class of each pair
     // tracking mode (avb_track_sequence)
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> copied;
@@ -464,6 +468,7 @@ void avb_fitter_destroy(avb_fitter* ft) {
     for (auto& e : ft->ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : ft->copied) cudaEventDestroy(e);
+    for (auto& e : ft->pev) cudaEventDestroy(e);
     if (ft->copy_stream) cudaStreamDestroy(ft->copy_stream);
     if (ft->stream) cudaStreamDestroy(ft->stream);
     delete ft;
@@ -689,6 +694,28 @@ int check_options(const avb_fitter* ft, const avb_options* o) {
     return AVB_OK;
 }
 
+// kernel classes for avb_last_kernel_ms
+enum { KC_POSE = 0, KC_NN = 1, KC_PREP = 2, KC_ROWS = 3, KC_SYRK = 4, KC_SOLVE = 5, KC_FINAL = 6, KC_COUNT = 7 };
+struct ProfScope {   // records an event pair around one launch when profiling is on
+    avb_fitter* ft;
+    size_t idx;
+    bool on;
+    ProfScope(avb_fitter* f, int cls) : ft(f), idx(0), on(f->profile) {
+        if (!on) return;
+        idx = ft->pcls.size();
+        ft->pcls.push_back(cls);
+        while (ft->pev.size() < 2 * (idx + 1)) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ft->pev.push_back(e);
+        }
+        cudaEventRecord(ft->pev[2 * idx], ft->stream);
+    }
+    ~ProfScope() {
+        if (on) cudaEventRecord(ft->pev[2 * idx + 1], ft->stream);
+    }
+};
+
 PoseArgs pose_args(avb_fitter* ft, const double* dx, bool vis, const avb_options* o) {
     PoseArgs a{};
     a.x = dx;
@@ -709,7 +736,10 @@ int enqueue_correspond(avb_fitter* ft, const double* dx, const avb_options* o, c
     cudaStream_t st = ft->stream;
     const int B = ft->batch, V = ft->model->V;
     PoseArgs pa = pose_args(ft, dx, true, o);
-    CUDA_TRY(launch_pose_visibility(ft->dm, ft->dp, pa, B, st));
+    {
+        ProfScope ps(ft, KC_POSE);
+        CUDA_TRY(launch_pose_visibility(ft->dm, ft->dp, pa, B, st));
+    }
     ++ft->launches;
     if (after_pose) CUDA_TRY(cudaEventRecord(after_pose, st));
     CUDA_TRY(cudaMemsetAsync(ft->d_cnt, 0, (size_t)B * V * 4, st));
@@ -732,7 +762,10 @@ int enqueue_correspond(avb_fitter* ft, const double* dx, const avb_options* o, c
     na.sum = ft->d_sum;
     na.qpart = ft->d_qpart;
     na.range_flag = ft->d_range;
-    CUDA_TRY(launch_nn(ft->dp, na, ft->num_chunks, st));
+    {
+        ProfScope ps(ft, KC_NN);
+        CUDA_TRY(launch_nn(ft->dp, na, ft->num_chunks, st));
+    }
     if (ft->num_chunks > 0) ++ft->launches;
     return AVB_OK;
 }
@@ -773,10 +806,17 @@ LmBuf lm_buf(avb_fitter* ft, double* dx, const avb_options* o) {
 // the inner solve of one ICP iteration: prep + (1 + max_iters) evaluations, all asynchronous
 int enqueue_solve(avb_fitter* ft, const LmBuf& la, const avb_options* o, int rounds) {
     cudaStream_t st = ft->stream;
-    CUDA_TRY(launch_lm_prep(ft->dm, ft->dp, la, ft->batch, st));
+    {
+        ProfScope ps(ft, KC_PREP);
+        CUDA_TRY(launch_lm_prep(ft->dm, ft->dp, la, ft->batch, st));
+    }
     ++ft->launches;
+    const bool acc64 = o->jtj_precision == AVB_JTJ_FP64;
     for (int r = 0; r < rounds; ++r) {
-        CUDA_TRY(launch_lm_eval(ft->dm, ft->dp, la, ft->batch, ft->max_nj, o->jtj_precision == AVB_JTJ_FP64, st));
+        for (int part = 0; part < 3; ++part) {
+            ProfScope ps(ft, KC_ROWS + part);
+            CUDA_TRY(launch_lm_eval_part(ft->dm, ft->dp, la, ft->batch, ft->max_nj, acc64, part, st));
+        }
         ft->launches += 3;
     }
     return AVB_OK;
@@ -797,6 +837,7 @@ int avb_fit_resident(avb_fitter* ft, const double* x_in, const avb_options* o) {
     CUDA_TRY(cudaMemcpyAsync(ft->d_x, ft->h_x, (size_t)B * nx * 8, cudaMemcpyHostToDevice, st));
     ft->launches = 0;
     ft->last_icp = o->icp_iters;
+    ft->pcls.clear();
     CUDA_TRY(cudaEventRecord(ft->ev[0], st));
     for (int icp = 0; icp < o->icp_iters; ++icp) {
         const bool timed = (icp == o->icp_iters - 1);
@@ -811,7 +852,10 @@ int avb_fit_resident(avb_fitter* ft, const double* x_in, const avb_options* o) {
     }
     // trailing ava.update() (AvatarOptimizer.cpp:1497)
     PoseArgs pa = pose_args(ft, ft->d_x, false, o);
-    CUDA_TRY(launch_pose_visibility(ft->dm, ft->dp, pa, B, st));
+    {
+        ProfScope ps(ft, KC_FINAL);
+        CUDA_TRY(launch_pose_visibility(ft->dm, ft->dp, pa, B, st));
+    }
     ++ft->launches;
     CUDA_TRY(cudaEventRecord(ft->ev[5], st));
     return AVB_OK;
@@ -857,6 +901,26 @@ int avb_timer_stop(avb_fitter* ft, float* ms) {
 }
 
 int avb_last_launch_count(avb_fitter* ft) { return ft ? ft->launches : 0; }
+
+int avb_set_profiling(avb_fitter* ft, int enabled) {
+    if (!ft) return fail(AVB_ERR_INVALID, "null fitter");
+    ft->profile = enabled != 0;
+    return AVB_OK;
+}
+
+int avb_last_kernel_ms(avb_fitter* ft, float* total_ms7, int32_t* launches7) {
+    if (!ft || !total_ms7 || !launches7) return fail(AVB_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    CUDA_TRY(cudaStreamSynchronize(ft->stream));
+    for (int k = 0; k < KC_COUNT; ++k) { total_ms7[k] = 0.f; launches7[k] = 0; }
+    for (size_t i = 0; i < ft->pcls.size(); ++i) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ft->pev[2 * i], ft->pev[2 * i + 1]));
+        total_ms7[ft->pcls[i]] += ms;
+        ++launches7[ft->pcls[i]];
+    }
+    return AVB_OK;
+}
 
 int avb_download_results(avb_fitter* ft, double* x_out, avb_stats* stats, double* cloud_out) {
     if (!ft) return fail(AVB_ERR_INVALID, "null fitter");

@@ -80,9 +80,9 @@ size_t pose_smem_bytes(int V, int J, int K);
 cudaError_t launch_pose_visibility(const DevModel& M, const DevParts& Pt, const PoseArgs& a, int batch, cudaStream_t st);
 cudaError_t launch_nn(const DevParts& Pt, const NNArgs& a, int num_chunks, cudaStream_t st);
 cudaError_t launch_lm_prep(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, cudaStream_t st);
-// one evaluation: lm_jac_kernel (chunks x frames) + lm_solve_kernel (frames)
-cudaError_t launch_lm_eval(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, int max_nj, bool acc64,
-                           cudaStream_t st);
+// one evaluation = parts 0 (lm_rows_kernel), 1 (lm_syrk_kernel), 2 (lm_solve_kernel) in order
+cudaError_t launch_lm_eval_part(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, int max_nj, bool acc64,
+                                int part, cudaStream_t st);
 long long lm_part_stride(int max_nj, int K);
 int lm_tab_doubles(int J, int K);
 int lm_rec_floats(int max_nj, int K);

@@ -163,21 +163,8 @@ lm_rows_kernel(DevModel M, DevParts Pt, LmBuf a) {
     for (int q = tid; q < a.tabD; q += 256) tab[q] = gtab[q];
     for (int q = tid; q < K; q += 256) w[q] = a.xt[(size_t)f * M.nx + 3 + 4 * J + q];
     for (int q = tid; q <= Pt.numGroups; q += 256) gstart[q] = a.gstart[(size_t)f * (kMaxGroups + 1) + q];
-    // shapedirs rows of this block's vertices: one coalesced 3K-float row per warp pass, 8 rows in flight
-    float* s_sd = reinterpret_cast<float*>(gstart + kMaxGroups + 2);
-    int* s_v = reinterpret_cast<int*>(s_sd + 256 * 3 * K);
+    int* s_v = reinterpret_cast<int*>(gstart + kMaxGroups + 2);
     s_v[tid] = (i < st.nmatched) ? (int)a.mlist[(size_t)f * M.V + i] : -1;
-    __syncthreads();
-    {
-        const int lane = tid & 31, wid = tid >> 5, per = 3 * K;
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) {
-            const int t = wid * 32 + k;
-            const int vv = s_v[t];
-            if (vv >= 0)
-                for (int q = lane; q < per; q += 32) s_sd[t * per + q] = __ldg(M.sd + (size_t)vv * per + q);
-        }
-    }
     __syncthreads();
     const double* G = tab;
     const double* pos = tab + 9 * J;
@@ -192,7 +179,7 @@ lm_rows_kernel(DevModel M, DevParts Pt, LmBuf a) {
         const int v = s_v[tid];
         float* rec = a.rec + (size_t)f * a.rec_stride * M.V + i;   // SoA: field q of vertex slot i at rec[q * V]
         const size_t RS = (size_t)M.V;
-        const float* sd = s_sd + tid * 3 * K;
+        const float* sd = M.sd + (size_t)v * 3 * K;
         double v0[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -285,23 +272,29 @@ lm_rows_kernel(DevModel M, DevParts Pt, LmBuf a) {
 // ---------------------------------------------------------------------------------------------
 // lm_syrk_kernel: A^T A of one chunk of Jacobian records (register-tiled, deterministic)
 // ---------------------------------------------------------------------------------------------
-// (block row of 8, block column of 4) pairs covering the upper triangle of an Lp x Lp matrix, Lp = 8 n
-__host__ __device__ inline int num_pairs(int n) { return n * n + n; }
+// 8x8 block pairs (bi <= bj) covering the upper triangle of an Lp x Lp matrix, Lp = 8 n
+__host__ __device__ inline int num_pairs(int n) { return n * (n + 1) / 2; }
 __device__ __forceinline__ void pair_to_blocks(int pair, int n, int& bi, int& bj) {
     bi = 0;
-    int rowlen = 2 * n;
+    int rowlen = n;
     while (pair >= rowlen) {
         pair -= rowlen;
         ++bi;
-        rowlen -= 2;
+        --rowlen;
     }
-    bj = 2 * bi + pair;
+    bj = bi + pair;
 }
 
+// Inner-loop shape chosen with tools/ubench/syrk_ubench.cu on B200: an 8x8 fp64 register block per thread fed from
+// an fp32 shared-memory tile (conversion in the loop) reaches ~12 TDFMA/s (65% of the fp64 pipe) with 128-thread
+// CTAs, 2 per SM; fp64 tiles in shared memory or 8x4 blocks stay below 7.4 TDFMA/s (shared-memory bandwidth bound).
+constexpr int kSyrkThreads = 128;
+
 template <typename AccT>
-__global__ void __launch_bounds__(kJacThreads, 2)
+__global__ void __launch_bounds__(kSyrkThreads, 2)
 lm_syrk_kernel(DevModel M, DevParts Pt, LmBuf a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int4 fmap[3 * kMaxJ + 3 * kMaxK + 8];   // where record field q lands inside a vertex's 3 Jacobian rows
     const int c = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
     const LmState& st = a.state[f];
     if (st.done || c >= st.nchunks) return;
@@ -315,23 +308,45 @@ lm_syrk_kernel(DevModel M, DevParts Pt, LmBuf a) {
     // syrk role: (block pair, row group); the row groups of a pair are adjacent lanes (shuffle reduction)
     const int n = Lp >> 3, npairs = num_pairs(n);
     int nrg = 1;
-    while (nrg < 32 && 2 * nrg * npairs <= kJacThreads) nrg <<= 1;
+    while (nrg < 32 && 2 * nrg * npairs <= kSyrkThreads) nrg <<= 1;
     const int pair = tid / nrg, rg = tid % nrg;
     const bool active = pair < npairs;
     int bi = 0, bj = 0;
     if (active) pair_to_blocks(pair, n, bi, bj);
-    AccT acc[8][4];
+    AccT acc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = AccT(0);
+        for (int j = 0; j < 8; ++j) acc[i][j] = AccT(0);
     const float* recs = a.rec + (size_t)f * a.rec_stride * M.V + start;
     const size_t RS = (size_t)M.V;
     const int cs = 3 + 3 * nj;
     const int nf = rec_floats(nj, K);
     // structural zeros of the tile (diagonal of every cross-product block, pad columns, off-diagonal of the
     // translation block) are written once: the scatter below never touches them
-    for (int e = tid; e < 3 * kTile * lda; e += kJacThreads) A[e] = 0.f;
+    for (int e = tid; e < 3 * kTile * lda; e += kSyrkThreads) A[e] = 0.f;
+    for (int q = tid; q < nf; q += kSyrkThreads) {   // offsets r * lda + col of up to three targets; .w = negate the 2nd
+        int t0x = -1, t1x = -1, t2x = -1, neg1 = 0;
+        if (q < 3 * nj) {
+            // f_c of joint gi sits at (row (c+1)%3, col (c+2)%3) with + and at (row (c+2)%3, col (c+1)%3) with -
+            const int gi = q / 3, cc = q - 3 * gi, c0 = 3 + 3 * gi;
+            const int r1 = (cc + 1) % 3, r2 = (cc + 2) % 3;
+            t0x = r1 * lda + c0 + r2;
+            t1x = r2 * lda + c0 + r1;
+            neg1 = 1;
+        } else if (q < 3 * nj + 3 * K) {
+            const int rm = q - 3 * nj, r = rm / K, m = rm - r * K;
+            t0x = r * lda + cs + m;
+        } else if (q < 3 * nj + 3 * K + 6) {
+            const int e2 = q - 3 * nj - 3 * K, hl = e2 / 3, r = e2 - 3 * hl;
+            t0x = r * lda + cs + K + hl;
+        } else {  // sc: root translation block sc * I (AvatarOptimizer.cpp:477-481)
+            t0x = 0;
+            t1x = lda + 1;
+            t2x = 2 * lda + 2;
+        }
+        fmap[q] = make_int4(t0x, t1x, t2x, neg1);
+    }
     __syncthreads();
 
     for (int t0 = 0; t0 < count; t0 += kTile) {
@@ -339,57 +354,46 @@ lm_syrk_kernel(DevModel M, DevParts Pt, LmBuf a) {
         // coalesced load of the tile's SoA records (field q, vertex t), kLd loads in flight per thread, then
         // scatter into Jacobian rows
         constexpr int kLd = 10;
-        for (int e0 = tid; e0 < nf * kTile; e0 += kJacThreads * kLd) {
+        for (int e0 = tid; e0 < nf * kTile; e0 += kSyrkThreads * kLd) {
             float vals[kLd];
 #pragma unroll
             for (int k = 0; k < kLd; ++k) {
-                const int e = e0 + k * kJacThreads;
+                const int e = e0 + k * kSyrkThreads;
                 const int q = e / kTile, t = e - q * kTile;
                 vals[k] = (e < nf * kTile && t < nv) ? __ldg(recs + (size_t)q * RS + t0 + t) : 0.f;
             }
 #pragma unroll
             for (int k = 0; k < kLd; ++k) {
-                const int e = e0 + k * kJacThreads;
+                const int e = e0 + k * kSyrkThreads;
                 const int q = e / kTile, t = e - q * kTile;
                 if (e >= nf * kTile || t >= nv) continue;
                 const float val = vals[k];
+                const int4 fm = fmap[q];
                 float* A3 = A + (size_t)(3 * t) * lda;
-                if (q < 3 * nj) {
-                    // f_c of joint gi sits at (row (c+1)%3, col (c+2)%3) with + and at (row (c+2)%3, col (c+1)%3) with -
-                    const int gi = q / 3, cc = q - 3 * gi, c0 = 3 + 3 * gi;
-                    const int r1 = (cc + 1) % 3, r2 = (cc + 2) % 3;
-                    A3[(size_t)r1 * lda + c0 + r2] = val;
-                    A3[(size_t)r2 * lda + c0 + r1] = -val;
-                } else if (q < 3 * nj + 3 * K) {
-                    const int rm = q - 3 * nj, r = rm / K, m = rm - r * K;
-                    A3[(size_t)r * lda + cs + m] = val;
-                } else if (q < 3 * nj + 3 * K + 6) {
-                    const int e2 = q - 3 * nj - 3 * K, hl = e2 / 3, r = e2 - 3 * hl;
-                    A3[(size_t)r * lda + cs + K + hl] = val;
-                } else {  // sc: root translation block sc * I (AvatarOptimizer.cpp:477-481)
-                    A3[0] = val;
-                    A3[(size_t)lda + 1] = val;
-                    A3[(size_t)2 * lda + 2] = val;
-                }
+                A3[fm.x] = val;
+                if (fm.y >= 0) A3[fm.y] = fm.w ? -val : val;
+                if (fm.z >= 0) A3[fm.z] = val;
             }
         }
         __syncthreads();
         if (active) {
             const int nrows = 3 * nv;
             const float* Ab = A + 8 * bi;
-            const float* Bb = A + 4 * bj;
+            const float* Bb = A + 8 * bj;
 #pragma unroll 2
             for (int r = rg; r < nrows; r += nrg) {
                 const float4 a0 = *reinterpret_cast<const float4*>(Ab + (size_t)r * lda);
                 const float4 a1 = *reinterpret_cast<const float4*>(Ab + (size_t)r * lda + 4);
                 const float4 b0 = *reinterpret_cast<const float4*>(Bb + (size_t)r * lda);
+                const float4 b1 = *reinterpret_cast<const float4*>(Bb + (size_t)r * lda + 4);
                 const AccT av[8] = {AccT(a0.x), AccT(a0.y), AccT(a0.z), AccT(a0.w),
                                     AccT(a1.x), AccT(a1.y), AccT(a1.z), AccT(a1.w)};
-                const AccT bv[4] = {AccT(b0.x), AccT(b0.y), AccT(b0.z), AccT(b0.w)};
+                const AccT bv[8] = {AccT(b0.x), AccT(b0.y), AccT(b0.z), AccT(b0.w),
+                                    AccT(b1.x), AccT(b1.y), AccT(b1.z), AccT(b1.w)};
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
             }
         }
         __syncthreads();
@@ -399,15 +403,15 @@ lm_syrk_kernel(DevModel M, DevParts Pt, LmBuf a) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], o);
+            for (int j = 0; j < 8; ++j) acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], o);
     }
     double* part = a.part + ((size_t)f * a.maxc + c) * a.pstride;
     if (active && rg == 0) {
-        double* p = part + (size_t)pair * 32;
+        double* p = part + (size_t)pair * 64;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) p[i * 4 + j] = (double)acc[i][j];
+            for (int j = 0; j < 8; ++j) p[i * 8 + j] = (double)acc[i][j];
     }
 }
 
@@ -443,50 +447,73 @@ __device__ inline SolveSmem carve_solve(unsigned char* raw, const DevModel& M) {
     return S;
 }
 
-// CTA-wide Cholesky W = L L^T in place (lower triangle; 2-D thread map, one barrier per column).
-// Right-looking without scaling inside the loop: after step j the entries below the diagonal of column j hold
-// l_ij * sqrt(d_j); a final pass scales them.  Returns false when a pivot is not positive.
-__device__ bool block_cholesky(double* W, int P, int* flag) {
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+// CTA-wide blocked right-looking Cholesky W = L L^T in place (lower triangle), panels of 4 columns: warp 0 factors
+// the panel, then all threads apply the rank-4 update to the trailing matrix (2 barriers per panel).  dinv receives
+// 1 / L_jj.  Returns false when a pivot is not positive.
+__device__ bool block_cholesky(double* W, int P, int* flag, double* dinv) {
+    constexpr int NB = 4;
+    const int tid = threadIdx.x, lane = tid & 31, ty = tid >> 4, tx = tid & 15;
     if (tid == 0) *flag = 1;
     __syncthreads();
-    for (int j = 0; j < P; ++j) {
-        const double d = W[(size_t)j * P + j];
-        if (!(d > 0.0) || !isfinite(d)) {  // uniform: every thread reads the same value
-            if (tid == 0) *flag = 0;
-            break;
+    for (int j0 = 0; j0 < P; j0 += NB) {
+        const int nb = min(NB, P - j0);
+        if (tid < 32) {
+            for (int c = 0; c < nb; ++c) {
+                const int j = j0 + c;
+                const double d = W[(size_t)j * P + j];
+                if (!(d > 0.0) || !isfinite(d)) {   // uniform inside the warp
+                    if (lane == 0) *flag = 0;
+                    break;
+                }
+                const double sd = sqrt(d), inv = 1.0 / sd;
+                __syncwarp();
+                if (lane == 0) {
+                    W[(size_t)j * P + j] = sd;
+                    dinv[j] = inv;
+                }
+                for (int i = j + 1 + lane; i < P; i += 32) W[(size_t)i * P + j] *= inv;
+                __syncwarp();
+                for (int c2 = c + 1; c2 < nb; ++c2) {
+                    const int k = j0 + c2;
+                    const double lkj = W[(size_t)k * P + j];
+                    for (int i = k + lane; i < P; i += 32) W[(size_t)i * P + k] -= W[(size_t)i * P + j] * lkj;
+                }
+                __syncwarp();
+            }
         }
-        const double inv = 1.0 / d;
-        for (int i = j + 1 + ty; i < P; i += 16) {
-            const double lij = W[(size_t)i * P + j] * inv;
-            for (int k = j + 1 + tx; k <= i; k += 16) W[(size_t)i * P + k] -= lij * W[(size_t)k * P + j];
+        __syncthreads();
+        if (*flag == 0) break;
+        const int t0 = j0 + nb;
+        for (int i = t0 + ty; i < P; i += 16) {
+            double li[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) li[c] = (c < nb) ? W[(size_t)i * P + j0 + c] : 0.0;
+            for (int k = t0 + tx; k <= i; k += 16) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    if (c < nb) sacc += li[c] * W[(size_t)k * P + j0 + c];
+                W[(size_t)i * P + k] -= sacc;
+            }
         }
         __syncthreads();
     }
     __syncthreads();
-    if (*flag == 0) return false;
-    for (int e = tid; e < P * P; e += blockDim.x) {
-        const int i = e / P, j = e - i * P;
-        if (j < i) W[e] *= 1.0 / sqrt(W[(size_t)j * P + j]);
-    }
-    __syncthreads();
-    for (int j = tid; j < P; j += blockDim.x) W[(size_t)j * P + j] = sqrt(W[(size_t)j * P + j]);
-    __syncthreads();
-    return true;
+    return *flag != 0;
 }
 
 // solve L L^T x = b in place with one warp (column-oriented forward, row-oriented backward substitution)
-__device__ void warp_chol_solve(const double* L, int P, double* b) {
+__device__ void warp_chol_solve(const double* L, const double* dinv, int P, double* b) {
     const int lane = threadIdx.x & 31;
     for (int i = 0; i < P; ++i) {
-        const double yi = b[i] / L[(size_t)i * P + i];
+        const double yi = b[i] * dinv[i];
         __syncwarp();
         if (lane == 0) b[i] = yi;
         for (int e = i + 1 + lane; e < P; e += 32) b[e] -= L[(size_t)e * P + i] * yi;
         __syncwarp();
     }
     for (int i = P - 1; i >= 0; --i) {
-        const double xi = b[i] / L[(size_t)i * P + i];
+        const double xi = b[i] * dinv[i];
         __syncwarp();
         if (lane == 0) b[i] = xi;
         for (int e = lane; e < i; e += 32) b[e] -= L[(size_t)i * P + e] * xi;
@@ -519,9 +546,11 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
     __syncthreads();
     // ---- reduce the chunk partials in chunk order ----
     double csum = 0.0;
-    for (int c = 0; c < st.nchunks; ++c) {
+    for (int c = 0; c < st.nchunks;) {
         const int4 ch = a.chunks[(size_t)f * a.maxc + c];
         const int g = ch.x, nj = Pt.gnj[g];
+        int c1 = c + 1;   // chunks [c, c1) belong to the same column group: identical partial layout
+        while (c1 < st.nchunks && a.chunks[(size_t)f * a.maxc + c1].x == g) ++c1;
         const int* gj = Pt.gjoints + g * kMaxJ;
         const int L = group_L(nj, K), Lp = (L + 7) & ~7, n = Lp >> 3;
         const int npairs = num_pairs(n);
@@ -532,19 +561,21 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
             if (q < L - 2) return 3 + 3 * J + (q - 3 - 3 * nj);
             return -1;
         };
-        for (int idx = tid; idx < npairs * 32; idx += kSolveThreads) {
-            const int pair = idx >> 5, e = idx & 31;
+        for (int idx = tid; idx < npairs * 64; idx += kSolveThreads) {
+            const int pair = idx >> 6, e = idx & 63;
             int bi, bj;
             pair_to_blocks(pair, n, bi, bj);
-            const int qa = 8 * bi + (e >> 2), qb = 4 * bj + (e & 3);
+            const int qa = 8 * bi + (e >> 3), qb = 8 * bj + (e & 7);
             if (qa > qb || qa >= L - 2 || qb >= L) continue;
+            double val = 0.0;   // chunk order is fixed => deterministic
+            for (int cc = 0; cc < c1 - c; ++cc) val += part[(size_t)cc * a.pstride + idx];
             const int ca = colmap(qa);
-            const double val = part[idx];
             if (qb == L - 2) S.gs[ca] += val;
             else if (qb == L - 1) S.glo[ca] += val;
             else S.Hs[(size_t)ca * P + colmap(qb)] += val;
         }
         __syncthreads();
+        c = c1;
     }
     for (int b = 0; b * 256 < st.nmatched; ++b) csum += a.cpart[(size_t)f * a.maxrb + b];
     double cost_t = 0.5 * (csum + st.Qsum);
@@ -734,11 +765,11 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
             S.Hs[(size_t)j * P + j] = h + d / (s * s * radius);
         }
         __syncthreads();
-        bool ok = block_cholesky(S.Hs, P, &S.iscr[50]);
+        bool ok = block_cholesky(S.Hs, P, &S.iscr[50], S.glo);
         if (ok) {
             for (int i = tid; i < P; i += kSolveThreads) S.delta[i] = -S.gcur[i];
             __syncthreads();
-            if (tid < 32) warp_chol_solve(S.Hs, P, S.delta);
+            if (tid < 32) warp_chol_solve(S.Hs, S.glo, P, S.delta);
             __syncthreads();
             // model_cost_change = -delta^T (g + 1/2 H delta), H without damping
             double part = 0;
@@ -821,7 +852,7 @@ size_t lm_prep_smem(const DevModel& M) {
     return (size_t)(((M.nx + 1) & ~1) + tables_doubles(M.J, M.K, true) + 64) * 8 + 64 * 4 + 64;
 }
 size_t lm_rows_smem(const DevModel& M) {
-    return (size_t)(tab_doubles(M.J, M.K) + ((M.K + 1) & ~1) + 32) * 8 + (kMaxGroups + 2) * 4 + (size_t)256 * 3 * M.K * 4 + 256 * 4 + 64;
+    return (size_t)(tab_doubles(M.J, M.K) + ((M.K + 1) & ~1) + 32) * 8 + (kMaxGroups + 2) * 4 + 256 * 4 + 64;
 }
 size_t lm_syrk_smem(const DevModel& M, int max_nj, bool acc64) {
     const int L = group_L(max_nj, M.K), Lp = (L + 7) & ~7, lda = Lp + 4;
@@ -834,24 +865,27 @@ cudaError_t launch_lm_prep(const DevModel& M, const DevParts& Pt, const LmBuf& a
     return cudaGetLastError();
 }
 
-cudaError_t launch_lm_eval(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, int max_nj, bool acc64,
-                           cudaStream_t st) {
-    const size_t jsm = lm_syrk_smem(M, max_nj, acc64);
+// part: 0 = lm_rows_kernel, 1 = lm_syrk_kernel, 2 = lm_solve_kernel (one evaluation = the three in order)
+cudaError_t launch_lm_eval_part(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, int max_nj, bool acc64,
+                                int part, cudaStream_t st) {
+    if (part == 0) {
+        lm_rows_kernel<<<dim3(a.maxrb, batch), 256, lm_rows_smem(M), st>>>(M, Pt, a);
+        return cudaGetLastError();
+    }
+    if (part == 1) {
+        const size_t jsm = lm_syrk_smem(M, max_nj, acc64);
+        cudaError_t e = acc64 ? cudaFuncSetAttribute(lm_syrk_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm)
+                              : cudaFuncSetAttribute(lm_syrk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm);
+        if (e != cudaSuccess) return e;
+        const dim3 grid(a.maxc, batch);
+        if (acc64)
+            lm_syrk_kernel<double><<<grid, kSyrkThreads, jsm, st>>>(M, Pt, a);
+        else
+            lm_syrk_kernel<float><<<grid, kSyrkThreads, jsm, st>>>(M, Pt, a);
+        return cudaGetLastError();
+    }
     const size_t ssm = solve_smem_bytes(M.J, M.K, M.gmmC);
-    cudaError_t e = acc64 ? cudaFuncSetAttribute(lm_syrk_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm)
-                          : cudaFuncSetAttribute(lm_syrk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(lm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
-    if (e != cudaSuccess) return e;
-    lm_rows_kernel<<<dim3(a.maxrb, batch), 256, lm_rows_smem(M), st>>>(M, Pt, a);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    const dim3 grid(a.maxc, batch);
-    if (acc64)
-        lm_syrk_kernel<double><<<grid, kJacThreads, jsm, st>>>(M, Pt, a);
-    else
-        lm_syrk_kernel<float><<<grid, kJacThreads, jsm, st>>>(M, Pt, a);
-    e = cudaGetLastError();
+    cudaError_t e = cudaFuncSetAttribute(lm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
     if (e != cudaSuccess) return e;
     lm_solve_kernel<<<batch, kSolveThreads, ssm, st>>>(M, Pt, a);
     return cudaGetLastError();
@@ -859,7 +893,7 @@ cudaError_t launch_lm_eval(const DevModel& M, const DevParts& Pt, const LmBuf& a
 
 long long lm_part_stride(int max_nj, int K) {
     const int L = group_L(max_nj, K), Lp = (L + 7) & ~7;
-    return (long long)num_pairs(Lp >> 3) * 32;
+    return (long long)num_pairs(Lp >> 3) * 64;
 }
 int lm_tab_doubles(int J, int K) { return tab_doubles(J, K); }
 int lm_rec_floats(int max_nj, int K) { return (rec_floats(max_nj, K) + 3) & ~3; }

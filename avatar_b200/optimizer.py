@@ -130,6 +130,19 @@ class Fitter:
         check(lib.avb_last_device_ms(self.handle, C.byref(tot), per))
         return tot.value, list(per)
 
+    KERNEL_CLASSES = ("pose_visibility_kernel", "nn_kernel", "lm_prep_kernel", "lm_rows_kernel", "lm_syrk_kernel",
+                      "lm_solve_kernel", "pose_visibility_kernel(final)")
+
+    def set_profiling(self, on):
+        check(lib.avb_set_profiling(self.handle, int(bool(on))))
+
+    def kernel_ms(self):
+        """{kernel class: (total ms, launches)} of the last profiled fit_resident"""
+        ms = (C.c_float * 7)()
+        n = (C.c_int32 * 7)()
+        check(lib.avb_last_kernel_ms(self.handle, ms, n))
+        return {k: (ms[i], n[i]) for i, k in enumerate(self.KERNEL_CLASSES)}
+
     def timer_start(self):
         check(lib.avb_timer_start(self.handle))
 

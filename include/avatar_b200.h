@@ -174,6 +174,12 @@ int avb_last_device_ms(avb_fitter* fitter, float* total_ms, float* per_kernel_ms
  * synchronises and returns the elapsed device time between them. */
 int avb_timer_start(avb_fitter* fitter);
 int avb_timer_stop(avb_fitter* fitter, float* ms);
+/* Per-kernel timing for bench.py's roofline: when enabled, the next avb_fit_resident records a CUDA-event pair
+ * around every kernel launch; avb_last_kernel_ms then returns, per kernel class
+ * [pose_visibility, nn, lm_prep, lm_rows, lm_syrk, lm_solve, final_pose], the summed device time (ms) and the
+ * number of launches.  Costs ~2 events per launch, so leave it off inside throughput-timed regions. */
+int avb_set_profiling(avb_fitter* fitter, int enabled);
+int avb_last_kernel_ms(avb_fitter* fitter, float* total_ms7, int32_t* launches7);
 /* number of kernel launches enqueued by the last avb_fit_resident / avb_fit_batch */
 int avb_last_launch_count(avb_fitter* fitter);
 
