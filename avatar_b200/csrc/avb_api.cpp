@@ -603,7 +603,7 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     TRY(dev_alloc(ft, &ft->d_mlist, B * V));
     TRY(dev_alloc(ft, &ft->d_chunks, B * (size_t)ft->maxc));
     TRY(dev_alloc(ft, &ft->d_state, B));
-    ft->max_chunks = (int)std::min<size_t>(NT / 512 + B + 8, (size_t)8 * ft->num_sms + 2 * B + 8);
+    ft->max_chunks = (int)std::max<size_t>(NT / 512 + 2 * B + 8, (size_t)8 * ft->num_sms + 2 * B + 8);
     ft->max_qblocks = (int64_t)(NT / kQBlock + B + 8);
     TRY(dev_alloc(ft, &ft->d_qpart, (size_t)ft->max_qblocks));
     TRY(dev_alloc(ft, &ft->d_chunk_frame, (size_t)ft->max_chunks));

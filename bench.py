@@ -188,12 +188,13 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=512, help="frames per GPU per step")
     ap.add_argument("--jtj", default="fp64", choices=["fp64", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("AVB_LANES", "2")),
                     help="split the rank's batch over this many fitters (streams) that run concurrently")
     args = ap.parse_args()
@@ -367,6 +368,30 @@ def main():
                     "ms_per_step": 1e3 * e2e_s / args.steps, "timer": "wall clock around synchronised steps"},
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks, "roofline": roofline, "wall_ms_per_step_resident": 1e3 * (t1 - t0) / args.steps}
+    # ---- secondary configs (BASELINE.json configs[1] and configs[3]), N=1 only: single-frame latency through
+    #      avb_fit and a warm-started tracking sequence through avb_track_sequence ----
+    if world == 1 and not args.no_extras:
+        f1 = Fitter(model, num_parts, part_map, 1, int(npts.max()) * 64 + 64, local_rank)
+        o1 = default_options()
+        o1.function_tolerance = 0.0
+        lat = []
+        for i in range(12):
+            tA = time.perf_counter()
+            f1.fit_batch(pts[i % 8], labs[i % 8], np.array([0, len(pts[i % 8])]), x0[i % 8][None], o1)
+            lat.append(time.perf_counter() - tA)
+        T = 60
+        seq_off = np.cumsum([0] + [len(pts[0])] * T)
+        seq_pts = np.concatenate([pts[0]] * T)
+        seq_lab = np.concatenate([labs[0]] * T)
+        f1.track_sequence(seq_pts[:seq_off[3]], seq_lab[:seq_off[3]], seq_off[:4], x0[0], o1)
+        tA = time.perf_counter()
+        f1.track_sequence(seq_pts, seq_lab, seq_off, x0[0], o1)
+        trk = time.perf_counter() - tA
+        line["secondary"] = {"single_frame_fit_ms_median": 1e3 * float(np.median(lat[2:])),
+                             "single_frame_points": int(len(pts[0])),
+                             "tracking_frames_per_s": T / trk, "tracking_frames": T,
+                             "note": "host buffers in, parameters out, icp_iters=1, 10 LM iterations; wall clock"}
+        f1.close()
     # ---- CPU baseline: the oracle port on a bounded sample, N=1 only ----
     if world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
