@@ -687,8 +687,10 @@ int check_options(const avb_fitter* ft, const avb_options* o) {
     if (!o) return fail(AVB_ERR_INVALID, "null options");
     if (o->icp_iters < 0 || o->max_iters_per_icp < 0) return fail(AVB_ERR_INVALID, "negative iteration count");
     if (o->solver != AVB_SOLVER_GN_LM) return fail(AVB_ERR_INVALID, "unknown solver");
-    if (o->jtj_precision != AVB_JTJ_FP64 && o->jtj_precision != AVB_JTJ_FP32)
-        return fail(AVB_ERR_INVALID, "jtj_precision: AVB_JTJ_FP64 and AVB_JTJ_FP32 are implemented");
+    if (o->jtj_precision != AVB_JTJ_FP64 && o->jtj_precision != AVB_JTJ_FP32 && o->jtj_precision != AVB_JTJ_BF16_TENSOR)
+        return fail(AVB_ERR_INVALID, "jtj_precision must be AVB_JTJ_FP64, AVB_JTJ_FP32 or AVB_JTJ_BF16_TENSOR");
+    if (o->jtj_precision == AVB_JTJ_BF16_TENSOR && 3 + 3 * ft->max_nj + ft->model->K + 3 > 128)
+        return fail(AVB_ERR_INVALID, "AVB_JTJ_BF16_TENSOR needs at most 128 Jacobian columns per group");
     if (o->beta_pose > 0.0 && ft->model->gmmC <= 0)
         return fail(AVB_ERR_PRIOR, "betaPose > 0 but the model has no pose prior");
     return AVB_OK;
@@ -783,6 +785,7 @@ LmBuf lm_buf(avb_fitter* ft, double* dx, const avb_options* o) {
     a.gstart = ft->d_gstart;
     a.maxrb = ft->maxrb;
     a.rec_stride = ft->rec_stride;
+    a.rho_cols = (o->jtj_precision == AVB_JTJ_BF16_TENSOR) ? 3 : 2;
     a.gcur = ft->d_gcur;
     a.Hcur = ft->d_Hcur;
     a.state = ft->d_state;

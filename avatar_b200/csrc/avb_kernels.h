@@ -56,6 +56,7 @@ struct LmBuf {
     float* rec;                  // [batch][V][rec_stride] fp32 Jacobian records of the matched vertices
     int* gstart;                 // [batch][kMaxGroups+1] group boundaries inside mlist
     int maxrb, rec_stride;
+    int rho_cols;                // residual columns in the A^T A partial: 2 (hi, lo) or 3 (bf16 x 3, tensor-core path)
     double* gcur;                // [batch][P]
     double* Hcur;                // [batch][P*P]
     LmState* state;              // [batch]

@@ -22,6 +22,7 @@
 #include "avb_kernels.h"
 #include "avb_tables.cuh"
 
+#include <cuda_bf16.h>
 #include <math.h>
 
 namespace avb {
@@ -416,10 +417,177 @@ lm_syrk_kernel(DevModel M, DevParts Pt, LmBuf a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// lm_syrk_tc_kernel: A^T A on the 5th-generation tensor cores (AVB_JTJ_BF16_TENSOR, BASELINE.json configs[4])
+// ---------------------------------------------------------------------------------------------
+// One CTA per chunk.  The Jacobian tile is written to shared memory TRANSPOSED (T[m][k]: m = Jacobian column,
+// k = tile row) as bf16 in the canonical K-major no-swizzle UMMA layout (8 x 16-byte core matrices), so that
+// D[128 x N] += T[0:128, k-slice] * T[0:N, k-slice]^T is a plain tcgen05.mma.cta_group::1.kind::f16 (M = 128, K = 16 per
+// instruction) issued by one thread with both operands described by the same shared-memory tile.  The fp32
+// accumulator lives in TMEM for the whole chunk and is read back once with tcgen05.ld.  The residual columns are
+// split into three bf16 terms (24 bits), so J^T r keeps fp32-level accuracy; bf16 only perturbs J^T J and the
+// Jacobian factor of J^T r, both of which multiply small quantities at the optimum.
+constexpr int kTcThreads = 128;
+constexpr int kTcM = 128;              // UMMA M (Jacobian columns padded)
+constexpr int kTcK = 3 * kTile;        // 192 tile rows = 12 MMA k-steps
+
+__device__ __forceinline__ uint32_t smem_u32_lm(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(kTcThreads, 4)
+lm_syrk_tc_kernel(DevModel M, DevParts Pt, LmBuf a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int4 fmap[3 * kMaxJ + 3 * kMaxK + 8];
+    const int c = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const LmState& st = a.state[f];
+    if (st.done || c >= st.nchunks) return;
+    const int K = M.K;
+    const int4 ch = a.chunks[(size_t)f * a.maxc + c];
+    const int g = ch.x, start = ch.y, count = ch.z;
+    const int nj = Pt.gnj[g];
+    const int L = group_L(nj, K) + 1;                 // three residual columns
+    const int Lp = (L + 7) & ~7, N = (L + 15) & ~15;  // N: UMMA N (multiple of 16 for M = 128)
+    const int cs = 3 + 3 * nj, nf = rec_floats(nj, K);
+    unsigned short* T = reinterpret_cast<unsigned short*>(smem_raw);   // bf16 bits, [kTcM/8][kTcK/8][8][8]
+    auto t_off = [](int m, int k) { return (((m >> 3) * (kTcK >> 3) + (k >> 3)) << 6) + ((m & 7) << 3) + (k & 7); };
+
+    if (wid == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32_lm(&tmem_base_s)), "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32_lm(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int e = tid; e < kTcM * kTcK / 2; e += kTcThreads) reinterpret_cast<uint32_t*>(T)[e] = 0u;
+    for (int q = tid; q < nf; q += kTcThreads) {   // targets (column m << 2 | row-in-vertex r); .w: negate the 2nd
+        int t0x = -1, t1x = -1, t2x = -1, neg1 = 0;
+        if (q < 3 * nj) {
+            const int gi = q / 3, cc = q - 3 * gi, c0 = 3 + 3 * gi;
+            const int r1 = (cc + 1) % 3, r2 = (cc + 2) % 3;
+            t0x = ((c0 + r2) << 2) | r1;
+            t1x = ((c0 + r1) << 2) | r2;
+            neg1 = 1;
+        } else if (q < 3 * nj + 3 * K) {
+            const int rm = q - 3 * nj, r = rm / K, m = rm - r * K;
+            t0x = ((cs + m) << 2) | r;
+        } else if (q < 3 * nj + 3 * K + 3) {   // rho_hi: split into three bf16 columns below
+            const int r = q - 3 * nj - 3 * K;
+            t0x = ((cs + K) << 2) | r;
+            neg1 = 2;
+        } else if (q < 3 * nj + 3 * K + 6) {   // rho_lo (fp32 residue): below bf16x3 resolution, dropped
+            t0x = -1;
+        } else {
+            t0x = (0 << 2) | 0;
+            t1x = (1 << 2) | 1;
+            t2x = (2 << 2) | 2;
+        }
+        fmap[q] = make_int4(t0x, t1x, t2x, neg1);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem_d = tmem_base_s;
+    // instruction descriptor: D = F32, A = B = BF16, K-major both, N >> 3 at [17,23), M >> 4 at [24,29)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+    // shared-memory descriptor: start >> 4 | LBO (K-direction core-matrix stride, 128 B) | SBO (8-row group stride) | version 1
+    const uint64_t desc0 = (uint64_t)((smem_u32_lm(T) >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) |
+                           ((uint64_t)(((kTcK >> 3) * 128) >> 4) << 32) | (1ull << 46);
+    const float* recs = a.rec + (size_t)f * a.rec_stride * M.V + start;
+    const size_t RS = (size_t)M.V;
+    int ntile = 0;
+    for (int t0 = 0; t0 < count; t0 += kTile, ++ntile) {
+        const int nv = min(kTile, count - t0);
+        constexpr int kLd = 10;
+        for (int e0 = tid; e0 < nf * kTile; e0 += kTcThreads * kLd) {
+            float vals[kLd];
+#pragma unroll
+            for (int k = 0; k < kLd; ++k) {
+                const int e = e0 + k * kTcThreads;
+                const int q = e / kTile, t = e - q * kTile;
+                vals[k] = (e < nf * kTile && t < nv) ? __ldg(recs + (size_t)q * RS + t0 + t) : 0.f;   // stale rows -> 0
+            }
+#pragma unroll
+            for (int k = 0; k < kLd; ++k) {
+                const int e = e0 + k * kTcThreads;
+                const int q = e / kTile, t = e - q * kTile;
+                if (e >= nf * kTile) continue;
+                const int4 fm = fmap[q];
+                if (fm.x < 0) continue;
+                const float val = vals[k];
+                auto put = [&](int tgt, float v) {
+                    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+                    T[t_off(tgt >> 2, 3 * t + (tgt & 3))] = *reinterpret_cast<const unsigned short*>(&b);
+                };
+                if (fm.w == 2) {   // residual: three bf16 terms in consecutive columns
+                    const __nv_bfloat16 b0 = __float2bfloat16_rn(val);
+                    const float r1 = val - __bfloat162float(b0);
+                    const __nv_bfloat16 b1 = __float2bfloat16_rn(r1);
+                    const float r2 = r1 - __bfloat162float(b1);
+                    const int m0 = fm.x >> 2, kk = 3 * t + (fm.x & 3);
+                    T[t_off(m0, kk)] = *reinterpret_cast<const unsigned short*>(&b0);
+                    T[t_off(m0 + 1, kk)] = *reinterpret_cast<const unsigned short*>(&b1);
+                    put(((m0 + 2) << 2) | (fm.x & 3), r2);
+                } else {
+                    put(fm.x, val);
+                    if (fm.y >= 0) put(fm.y, fm.w == 1 ? -val : val);
+                    if (fm.z >= 0) put(fm.z, val);
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll 1
+            for (int s2 = 0; s2 < kTcK / 16; ++s2) {
+                const uint64_t desc = desc0 + (uint64_t)((s2 * 256) >> 4);   // two core matrices per k-step
+                const uint32_t accum = (ntile > 0 || s2 > 0) ? 1u : 0u;
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                    ::"r"(tmem_d), "l"(desc), "l"(desc), "r"(idesc), "r"(accum) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32_lm(&mbar)) : "memory");
+        }
+        {   // the tile may be overwritten (and TMEM read) only after the MMAs retire
+            const uint32_t parity = (uint32_t)(ntile & 1);
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(smem_u32_lm(&mbar)), "r"(parity) : "memory");
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;");
+    }
+    // epilogue: TMEM lane = Jacobian column m (row of A^T A); warp w owns lanes [32w, 32w+32)
+    double* part = a.part + ((size_t)f * a.maxc + c) * a.pstride;
+    const int m = 32 * wid + lane, n8 = Lp >> 3;
+    for (int cb = 0; cb < (N >> 3); ++cb) {
+        uint32_t v[8];
+        const uint32_t taddr = tmem_d + ((uint32_t)(32 * wid) << 16) + (uint32_t)(8 * cb);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int bi = m >> 3;
+        if (m < Lp && cb >= bi && cb < n8) {
+            const int pair = bi * n8 - (bi * (bi - 1)) / 2 + (cb - bi);
+            double* p = part + (size_t)pair * 64 + (m & 7) * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) p[j] = (double)__uint_as_float(v[j]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(128));
+}
+
+// ---------------------------------------------------------------------------------------------
 // lm_solve_kernel
 // ---------------------------------------------------------------------------------------------
 struct SolveSmem {
-    double *xs, *xt, *tb, *Hs, *gs, *glo, *gcur, *delta, *aa, *ycomp, *scr;
+    double *xs, *xt, *tb, *Hs, *gs, *glo, *gl2, *gcur, *delta, *aa, *ycomp, *scr;
     int* iscr;
 };
 __host__ __device__ inline size_t solve_smem_bytes(int J, int K, int C) {
@@ -440,6 +608,7 @@ __device__ inline SolveSmem carve_solve(unsigned char* raw, const DevModel& M) {
     S.glo = d; d += (P + 1) & ~1;
     S.gcur = d; d += (P + 1) & ~1;
     S.delta = d; d += (P + 1) & ~1;
+    S.gl2 = S.delta;   // third gradient term of the tensor-core layout; delta is only written after the reduction
     S.aa = d; d += (D + 1) & ~1;
     S.ycomp = d; d += (size_t)C * ((D + 1) & ~1);
     S.scr = d; d += 64;
@@ -541,6 +710,7 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
     for (int i = tid; i < P; i += kSolveThreads) {
         S.gs[i] = 0.0;
         S.glo[i] = 0.0;
+        S.gl2[i] = 0.0;
         S.gcur[i] = gcur_g[i];
     }
     __syncthreads();
@@ -552,13 +722,14 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
         int c1 = c + 1;   // chunks [c, c1) belong to the same column group: identical partial layout
         while (c1 < st.nchunks && a.chunks[(size_t)f * a.maxc + c1].x == g) ++c1;
         const int* gj = Pt.gjoints + g * kMaxJ;
-        const int L = group_L(nj, K), Lp = (L + 7) & ~7, n = Lp >> 3;
+        const int L = group_L(nj, K) + (a.rho_cols - 2), Lp = (L + 7) & ~7, n = Lp >> 3;
+        const int rc = a.rho_cols;
         const int npairs = num_pairs(n);
         const double* part = a.part + ((size_t)f * a.maxc + c) * a.pstride;
         auto colmap = [&](int q) -> int {
             if (q < 3) return q;
             if (q < 3 + 3 * nj) return 3 + 3 * gj[(q - 3) / 3] + (q - 3) % 3;
-            if (q < L - 2) return 3 + 3 * J + (q - 3 - 3 * nj);
+            if (q < L - rc) return 3 + 3 * J + (q - 3 - 3 * nj);
             return -1;
         };
         for (int idx = tid; idx < npairs * 64; idx += kSolveThreads) {
@@ -566,12 +737,13 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
             int bi, bj;
             pair_to_blocks(pair, n, bi, bj);
             const int qa = 8 * bi + (e >> 3), qb = 8 * bj + (e & 7);
-            if (qa > qb || qa >= L - 2 || qb >= L) continue;
+            if (qa > qb || qa >= L - rc || qb >= L) continue;
             double val = 0.0;   // chunk order is fixed => deterministic
             for (int cc = 0; cc < c1 - c; ++cc) val += part[(size_t)cc * a.pstride + idx];
             const int ca = colmap(qa);
-            if (qb == L - 2) S.gs[ca] += val;
-            else if (qb == L - 1) S.glo[ca] += val;
+            if (qb == L - rc) S.gs[ca] += val;                 // residual columns: hi | lo (| third bf16 term)
+            else if (qb == L - rc + 1) S.glo[ca] += val;
+            else if (qb == L - rc + 2) S.gl2[ca] += val;
             else S.Hs[(size_t)ca * P + colmap(qb)] += val;
         }
         __syncthreads();
@@ -579,7 +751,7 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
     }
     for (int b = 0; b * 256 < st.nmatched; ++b) csum += a.cpart[(size_t)f * a.maxrb + b];
     double cost_t = 0.5 * (csum + st.Qsum);
-    for (int i = tid; i < P; i += kSolveThreads) S.gs[i] += S.glo[i];
+    for (int i = tid; i < P; i += kSolveThreads) S.gs[i] += S.glo[i] + S.gl2[i];
     for (int i = tid; i < P * P; i += kSolveThreads) {
         const int r = i / P, c = i - r * P;
         if (r > c) S.Hs[i] = S.Hs[(size_t)c * P + r];
@@ -872,6 +1044,13 @@ cudaError_t launch_lm_eval_part(const DevModel& M, const DevParts& Pt, const LmB
         lm_rows_kernel<<<dim3(a.maxrb, batch), 256, lm_rows_smem(M), st>>>(M, Pt, a);
         return cudaGetLastError();
     }
+    if (part == 1 && a.rho_cols == 3) {
+        const size_t tsm = (size_t)kTcM * kTcK * 2 + 1024;
+        cudaError_t e = cudaFuncSetAttribute(lm_syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+        if (e != cudaSuccess) return e;
+        lm_syrk_tc_kernel<<<dim3(a.maxc, batch), kTcThreads, tsm, st>>>(M, Pt, a);
+        return cudaGetLastError();
+    }
     if (part == 1) {
         const size_t jsm = lm_syrk_smem(M, max_nj, acc64);
         cudaError_t e = acc64 ? cudaFuncSetAttribute(lm_syrk_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm)
@@ -892,7 +1071,7 @@ cudaError_t launch_lm_eval_part(const DevModel& M, const DevParts& Pt, const LmB
 }
 
 long long lm_part_stride(int max_nj, int K) {
-    const int L = group_L(max_nj, K), Lp = (L + 7) & ~7;
+    const int L = group_L(max_nj, K) + 1, Lp = (L + 7) & ~7;   // + 1: the tensor-core layout has a third residual column
     return (long long)num_pairs(Lp >> 3) * 64;
 }
 int lm_tab_doubles(int J, int K) { return tab_doubles(J, K); }

@@ -291,3 +291,28 @@ def test_stress_dense_cloud_many_iterations(model, oracle_mod, oopt, omodel, pri
     assert np.abs(x[0] - xo).max() < PARAM_TOL
     assert stats[0].num_correspondences == st.num_correspondences == (nn >= 0).sum()
     ft.close()
+
+
+def test_bf16_tensor_core_jtj_path(fitter, oopt, frames):
+    """AVB_JTJ_BF16_TENSOR (BASELINE.json configs[4]): J^T J / J^T r through tcgen05.mma with bf16 operands and fp32
+    TMEM accumulation.  Not a parity path: bf16 rounds the Jacobian (8-bit mantissa), so the tolerances are those of
+    bf16, and the fit is checked against the fp64 path by its objective value."""
+    from avatar_b200 import _lib
+    pts, lab, off, x0 = _batch(frames, [0, 1])
+    fitter.upload(pts, lab, off)
+    o = _opts(jtj_precision=_lib.JTJ_BF16_TENSOR)
+    fitter.debug_correspond(x0, o)
+    nn = fitter.debug_read(_lib.TAP_NN)
+    cost, grad, H = fitter.debug_evaluate(x0, o)
+    for b in range(2):
+        p = pts[off[b]:off[b + 1]]
+        oc, og, oH = oopt.evaluate(x0[b], p, nn[off[b]:off[b + 1]], o.beta_pose, o.beta_shape)
+        assert abs(cost[b] - oc) <= COST_RTOL * oc                    # the cost never touches the tensor path
+        assert np.abs(grad[b] - og).max() <= 1e-2 * np.abs(og).max()
+        scale = np.sqrt(np.outer(np.diag(oH), np.diag(oH)))
+        assert (np.abs(H[b] - oH) / scale).max() <= 2e-2
+    x64, st64, _ = fitter.fit_batch(pts, lab, off, x0, _opts(icp_iters=2))
+    x16, st16, _ = fitter.fit_batch(pts, lab, off, x0, _opts(icp_iters=2, jtj_precision=_lib.JTJ_BF16_TENSOR))
+    for b in range(2):
+        assert st16[b].final_cost < st16[b].initial_cost
+        assert st16[b].final_cost <= 1.05 * st64[b].final_cost
