@@ -148,7 +148,7 @@ lm_prep_kernel(DevModel M, DevParts Pt, LmBuf a) {
 //   [ 2 sc y_j (3 per group joint) | sc S (3 x K, row-major) | rho_hi(3) | rho_lo(3) | sc ],  rho = (c x - sum d)/sc
 __host__ __device__ inline int rec_floats(int nj, int K) { return 3 * nj + 3 * K + 7; }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 lm_rows_kernel(DevModel M, DevParts Pt, LmBuf a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int f = blockIdx.y, tid = threadIdx.x;
