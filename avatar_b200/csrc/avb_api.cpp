@@ -97,7 +97,7 @@ struct avb_fitter {
     int* d_range = nullptr; double* d_Hcur = nullptr; FrameStats* d_stats = nullptr;
     double *d_xt = nullptr, *d_tab = nullptr, *d_part = nullptr, *d_cpart = nullptr, *d_gcur = nullptr;
     unsigned short* d_mlist = nullptr; int4* d_chunks = nullptr; LmState* d_state = nullptr;
-    float* d_rec = nullptr; int* d_gstart = nullptr; int maxrb = 0, rec_stride = 0;
+    float* d_rec = nullptr; int* d_gstart = nullptr; int maxrb = 0, rec_stride = 0, rec_rs = 0;
     int maxc = 0, tabD = 0, max_nj = 0, chunk_verts = 256;
     long long pstride = 0;
     int *d_chunk_frame = nullptr, *d_chunk_count = nullptr, *d_chunk_qblock = nullptr, *d_frame_qblock = nullptr;
@@ -178,8 +178,8 @@ void build_groups(const avb_model& m, int max_groups, std::vector<int>& gorder, 
             for (auto& g : groups)
                 if (g.mask == sig[v]) { ++g.n; break; }
     }
-    auto lp = [&](uint32_t mask) {
-        const int L = 3 + 3 * __builtin_popcount(mask) + K;
+    auto lp = [&](uint32_t mask) {   // padded record length of a group (the Gram matrix is lp x lp)
+        const int L = 3 * __builtin_popcount(mask) + 3 * K + 7;
         return (L + 7) & ~7;
     };
     auto cost = [&](uint32_t mask, long long n) { return (double)n * lp(mask) * lp(mask); };
@@ -587,20 +587,22 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     TRY(dev_alloc(ft, &ft->d_Hcur, B * P * P));
     TRY(dev_alloc(ft, &ft->d_stats, B));
     for (int g : gnj) ft->max_nj = std::max(ft->max_nj, g);
-    if (const char* e = std::getenv("AVB_CHUNK")) ft->chunk_verts = std::max(64, std::min(1024, std::atoi(e) / 64 * 64));
+    if (const char* e = std::getenv("AVB_CHUNK")) ft->chunk_verts = std::max(128, std::min(256, std::atoi(e) / 64 * 64));
+    while (ft->chunk_verts > 128 && lm_gram_smem_bytes(ft->max_nj, m->K, ft->chunk_verts, false) > 112 * 1024) ft->chunk_verts -= 64;
     ft->maxc = (V + ft->chunk_verts - 1) / ft->chunk_verts + dp.numGroups + 1;
     ft->tabD = lm_tab_doubles(m->J, m->K);
     ft->pstride = lm_part_stride(ft->max_nj, m->K);
     TRY(dev_alloc(ft, &ft->d_xt, B * nx));
     TRY(dev_alloc(ft, &ft->d_tab, B * (size_t)ft->tabD));
     TRY(dev_alloc(ft, &ft->d_part, B * (size_t)ft->maxc * (size_t)ft->pstride));
-    ft->maxrb = (V + 255) / 256;
+    ft->rec_rs = lm_rec_slots(V);
+    ft->maxrb = (ft->rec_rs + 255) / 256;
     ft->rec_stride = lm_rec_floats(ft->max_nj, m->K);
     TRY(dev_alloc(ft, &ft->d_cpart, B * (size_t)ft->maxrb));
-    TRY(dev_alloc(ft, &ft->d_rec, B * (size_t)V * (size_t)ft->rec_stride));
+    TRY(dev_alloc(ft, &ft->d_rec, B * (size_t)ft->rec_rs * (size_t)ft->rec_stride));
     TRY(dev_alloc(ft, &ft->d_gstart, B * (size_t)(kMaxGroups + 1)));
     TRY(dev_alloc(ft, &ft->d_gcur, B * P));
-    TRY(dev_alloc(ft, &ft->d_mlist, B * V));
+    TRY(dev_alloc(ft, &ft->d_mlist, B * (size_t)ft->rec_rs));
     TRY(dev_alloc(ft, &ft->d_chunks, B * (size_t)ft->maxc));
     TRY(dev_alloc(ft, &ft->d_state, B));
     ft->max_chunks = (int)std::max<size_t>(NT / 512 + 2 * B + 8, (size_t)8 * ft->num_sms + 2 * B + 8);
@@ -689,8 +691,8 @@ int check_options(const avb_fitter* ft, const avb_options* o) {
     if (o->solver != AVB_SOLVER_GN_LM) return fail(AVB_ERR_INVALID, "unknown solver");
     if (o->jtj_precision != AVB_JTJ_FP64 && o->jtj_precision != AVB_JTJ_FP32 && o->jtj_precision != AVB_JTJ_BF16_TENSOR)
         return fail(AVB_ERR_INVALID, "jtj_precision must be AVB_JTJ_FP64, AVB_JTJ_FP32 or AVB_JTJ_BF16_TENSOR");
-    if (o->jtj_precision == AVB_JTJ_BF16_TENSOR && 3 + 3 * ft->max_nj + ft->model->K + 3 > 128)
-        return fail(AVB_ERR_INVALID, "AVB_JTJ_BF16_TENSOR needs at most 128 Jacobian columns per group");
+    if (o->jtj_precision == AVB_JTJ_BF16_TENSOR && 3 * ft->max_nj + 3 * ft->model->K + 7 > 128)
+        return fail(AVB_ERR_INVALID, "AVB_JTJ_BF16_TENSOR needs at most 128 record fields per group");
     if (o->beta_pose > 0.0 && ft->model->gmmC <= 0)
         return fail(AVB_ERR_PRIOR, "betaPose > 0 but the model has no pose prior");
     return AVB_OK;
@@ -785,7 +787,7 @@ LmBuf lm_buf(avb_fitter* ft, double* dx, const avb_options* o) {
     a.gstart = ft->d_gstart;
     a.maxrb = ft->maxrb;
     a.rec_stride = ft->rec_stride;
-    a.rho_cols = (o->jtj_precision == AVB_JTJ_BF16_TENSOR) ? 3 : 2;
+    a.rec_rs = ft->rec_rs;
     a.gcur = ft->d_gcur;
     a.Hcur = ft->d_Hcur;
     a.state = ft->d_state;
@@ -814,11 +816,11 @@ int enqueue_solve(avb_fitter* ft, const LmBuf& la, const avb_options* o, int rou
         CUDA_TRY(launch_lm_prep(ft->dm, ft->dp, la, ft->batch, st));
     }
     ++ft->launches;
-    const bool acc64 = o->jtj_precision == AVB_JTJ_FP64;
+    const bool tensor = o->jtj_precision == AVB_JTJ_BF16_TENSOR;   // AVB_JTJ_FP32 permits, but no longer uses, fp32 sums
     for (int r = 0; r < rounds; ++r) {
         for (int part = 0; part < 3; ++part) {
             ProfScope ps(ft, KC_ROWS + part);
-            CUDA_TRY(launch_lm_eval_part(ft->dm, ft->dp, la, ft->batch, ft->max_nj, acc64, part, st));
+            CUDA_TRY(launch_lm_eval_part(ft->dm, ft->dp, la, ft->batch, ft->max_nj, tensor, part, st));
         }
         ft->launches += 3;
     }

@@ -42,21 +42,21 @@ struct NNArgs {
 
 struct LmState {  // per-frame Levenberg-Marquardt state, lives in HBM between the kernels of one ICP iteration
     double cost, radius, decrease, Qsum, sbp, sbs, initial_cost, model_change;
-    int done, iters, accepted, ncorr, nmatched, nchunks, evals, pad;
+    int done, iters, accepted, ncorr, nmatched, nchunks, evals, nslots;   // nslots: record slots incl. alignment gaps
 };
 
 struct LmBuf {
     double* x;                   // [batch][nx] current point (in/out)
     double* xt;                  // [batch][nx] trial point
     double* tab;                 // [batch][tabD] joint tables of the trial point: G | pos | tau | C
-    unsigned short* mlist;       // [batch][V] matched vertices grouped by Jacobian column group
+    unsigned short* mlist;       // [batch][rec_rs] matched vertices grouped by Jacobian column group (0xFFFF = gap)
     int4* chunks;                // [batch][maxc] (group, start in mlist, count, -)
-    double* part;                // [batch][maxc][pstride] A^T A partial per chunk (8x4 blocks of the upper triangle)
-    double* cpart;               // [batch][maxrb] cost partial per 256 matched vertices
-    float* rec;                  // [batch][V][rec_stride] fp32 Jacobian records of the matched vertices
+    double* part;                // [batch][maxc][pstride] chunk partial: upper triangle of J^T J | J^T r, group columns
+    double* cpart;               // [batch][maxrb] cost partial per 256 record slots
+    float* rec;                  // [batch][rec_stride][rec_rs] fp32 Jacobian records (SoA) of the matched vertices
     int* gstart;                 // [batch][kMaxGroups+1] group boundaries inside mlist
-    int maxrb, rec_stride;
-    int rho_cols;                // residual columns in the A^T A partial: 2 (hi, lo) or 3 (bf16 x 3, tensor-core path)
+    int maxrb, rec_stride;       // rec_stride: fields per record (max over groups)
+    int rec_rs;                  // record slots per frame (multiple of 4)
     double* gcur;                // [batch][P]
     double* Hcur;                // [batch][P*P]
     LmState* state;              // [batch]
@@ -81,11 +81,13 @@ size_t pose_smem_bytes(int V, int J, int K);
 cudaError_t launch_pose_visibility(const DevModel& M, const DevParts& Pt, const PoseArgs& a, int batch, cudaStream_t st);
 cudaError_t launch_nn(const DevParts& Pt, const NNArgs& a, int num_chunks, cudaStream_t st);
 cudaError_t launch_lm_prep(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, cudaStream_t st);
-// one evaluation = parts 0 (lm_rows_kernel), 1 (lm_syrk_kernel), 2 (lm_solve_kernel) in order
-cudaError_t launch_lm_eval_part(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, int max_nj, bool acc64,
+// one evaluation = parts 0 (lm_rows_kernel), 1 (lm_gram_kernel or lm_gram_tc_kernel), 2 (lm_solve_kernel) in order
+cudaError_t launch_lm_eval_part(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, int max_nj, bool tensor,
                                 int part, cudaStream_t st);
 long long lm_part_stride(int max_nj, int K);
 int lm_tab_doubles(int J, int K);
 int lm_rec_floats(int max_nj, int K);
+int lm_rec_slots(int V);
+size_t lm_gram_smem_bytes(int max_nj, int K, int chunk_verts, bool tensor);
 
 }  // namespace avb

@@ -5,19 +5,19 @@
 //   lm_rows_kernel   grid = 256-vertex blocks x frames   one thread per matched vertex: position, residual
 //                                             statistics and the analytic Jacobian (AvatarOptimizer.cpp:505-582 in
 //                                             closed form) as a compact fp32 record (SoA) in HBM; cost partial.
-//   lm_syrk_kernel   grid = chunks x frames   expands the records of up to 256 matched vertices into Jacobian rows in
-//                                             shared memory and accumulates their J^T J / J^T r contribution as a
-//                                             register-tiled A^T A; one deterministic partial per chunk.
+//   lm_gram_kernel   grid = chunks x frames   Gram matrix of the records of up to 256 matched vertices (fp64 DMMA from
+//                                             an fp32 tile; lm_gram_tc_kernel: bf16 tcgen05), turned into the chunk's
+//                                             deterministic partial of J^T J / J^T r.
 //   lm_solve_kernel  grid = frames            partial reduction in chunk order, priors (:661-692, :708-723),
 //                                             Levenberg-Marquardt step control, damped Cholesky solve, retraction
 //                                             (:123-143), joint tables of the next trial point.
 //
-// One evaluation = rows + syrk + solve; 1 + maxItersPerICP evaluations per ICP iteration, enqueued back to back on
+// One evaluation = rows + gram + solve; 1 + maxItersPerICP evaluations per ICP iteration, enqueued back to back on
 // one stream with no host round trip (frames that converged early skip their CTAs).
 //
-// Numerics: geometry, residuals, cost, gradient and the linear algebra are fp64.  Jacobian rows are staged in
-// shared memory as fp32 (they only scale the residual in J^T r, so their 6e-8 rounding moves the fixed point by
-// ~1e-11) and J^T J is accumulated in fp64 (AccT = double) or fp32 (AccT = float, AVB_JTJ_FP32).
+// Numerics: geometry, residuals, cost, gradient and the linear algebra are fp64.  Jacobian records are stored as
+// fp32 (they only scale the residual in J^T r, so their 6e-8 rounding moves the fixed point by ~1e-11; the residual
+// itself is carried as an fp32 hi/lo pair) and every product and sum of J^T J / J^T r is fp64.
 #include "avb_device.cuh"
 #include "avb_kernels.h"
 #include "avb_tables.cuh"
@@ -29,12 +29,12 @@ namespace avb {
 
 constexpr int kJacThreads = 256;
 constexpr int kSolveThreads = 256;
-constexpr int kTile = 64;     // vertices per Jacobian tile (3 row-threads per vertex => 192 busy threads)
+constexpr unsigned short kNoVertex = 0xFFFFu;   // gap slot in mlist
 
 __host__ __device__ inline int tab_doubles(int J, int K) { return J * (15 + 3 * K); }
 
-// column layout of a group's compact Jacobian: [ p(3) | 3 per group joint | K shape | rho_hi | rho_lo | pad ]
-__host__ __device__ inline int group_L(int nj, int K) { return 3 + 3 * nj + K + 2; }
+// columns of a group's compact Jacobian: [ p(3) | 3 per group joint | K shape ]
+__host__ __device__ inline int group_L(int nj, int K) { return 3 + 3 * nj + K; }
 
 // ---------------------------------------------------------------------------------------------
 // lm_prep_kernel
@@ -56,12 +56,15 @@ lm_prep_kernel(DevModel M, DevParts Pt, LmBuf a) {
         a.xt[(size_t)f * nx + i] = v;
     }
     const int* cnt = a.cnt + (size_t)f * V;
-    unsigned short* mlist = a.mlist + (size_t)f * V;
+    unsigned short* mlist = a.mlist + (size_t)f * a.rec_rs;
     int4* chunks = a.chunks + (size_t)f * a.maxc;
     const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-    int base = 0, ncorr = 0, nchunks = 0;
+    int base = 0, nmatched = 0, ncorr = 0, nchunks = 0;
     for (int g = 0; g < Pt.numGroups; ++g) {
         const int b0 = Pt.gvstart[g], b1 = Pt.gvstart[g + 1];
+        // a group's slots start on a 16-byte boundary of the fp32 record arrays (cp.async / float4 tile loads)
+        if (tid < ((4 - (base & 3)) & 3)) mlist[base + tid] = kNoVertex;
+        base = (base + 3) & ~3;
         const int gbase = base;
         if (tid == 0) a.gstart[(size_t)f * (kMaxGroups + 1) + g] = base;
         for (int i0 = b0; i0 < b1; i0 += nt) {
@@ -83,6 +86,7 @@ lm_prep_kernel(DevModel M, DevParts Pt, LmBuf a) {
             }
             if (cv > 0) mlist[base + woff + wpre] = (unsigned short)v;
             base += tot;
+            nmatched += tot;
             __syncthreads();
         }
         // chunk list of this group (every thread computes the same numbers; thread 0 writes)
@@ -125,12 +129,13 @@ lm_prep_kernel(DevModel M, DevParts Pt, LmBuf a) {
         st.iters = 0;
         st.accepted = 0;
         st.ncorr = ncorr;
-        st.nmatched = base;
+        st.nmatched = nmatched;
+        st.nslots = base;
         st.nchunks = min(nchunks, a.maxc);
         st.evals = 0;
         FrameStats& fs = a.stats[f];
         fs.num_correspondences = ncorr;
-        fs.num_matched_vertices = base;
+        fs.num_matched_vertices = nmatched;
         fs.iterations = 0;
         fs.accepted_steps = 0;
         fs.initial_cost = 0;
@@ -145,7 +150,9 @@ lm_prep_kernel(DevModel M, DevParts Pt, LmBuf a) {
 // Tangent Jacobian in "global-frame rotation" coordinates eta_j = G_parent(j) delta_j:
 // block_j = R(-1,parent j) dRot Lq_j = -2 [y_j]x G_parent(j) (AvatarOptimizer.cpp:529-565 in closed form); the
 // change of coordinates is undone in lm_solve_kernel.  Record of a vertex with count c (sc = sqrt(c)):
-//   [ 2 sc y_j (3 per group joint) | sc S (3 x K, row-major) | rho_hi(3) | rho_lo(3) | sc ],  rho = (c x - sum d)/sc
+//   [ 2 sc y_j (3 per group joint) | sc | rho_hi(3) | rho_lo(3) | sc S (3 x K, row-major) ],  rho = (c x - sum d)/sc
+// stored SoA: field q of slot i at rec[q * rec_rs + i]; slots = matched vertices in group order, every group
+// starting on a multiple of four (gap slots hold kNoVertex in mlist and are never read by the Gram kernels).
 __host__ __device__ inline int rec_floats(int nj, int K) { return 3 * nj + 3 * K + 7; }
 
 __global__ void __launch_bounds__(256, 3)
@@ -154,7 +161,7 @@ lm_rows_kernel(DevModel M, DevParts Pt, LmBuf a) {
     const int f = blockIdx.y, tid = threadIdx.x;
     const LmState& st = a.state[f];
     const int i = blockIdx.x * 256 + tid;
-    if (st.done || blockIdx.x * 256 >= st.nmatched) return;
+    if (st.done || blockIdx.x * 256 >= st.nslots) return;
     const int J = M.J, K = M.K;
     double* tab = reinterpret_cast<double*>(smem_raw);
     double* w = tab + a.tabD;
@@ -165,21 +172,21 @@ lm_rows_kernel(DevModel M, DevParts Pt, LmBuf a) {
     for (int q = tid; q < K; q += 256) w[q] = a.xt[(size_t)f * M.nx + 3 + 4 * J + q];
     for (int q = tid; q <= Pt.numGroups; q += 256) gstart[q] = a.gstart[(size_t)f * (kMaxGroups + 1) + q];
     int* s_v = reinterpret_cast<int*>(gstart + kMaxGroups + 2);
-    s_v[tid] = (i < st.nmatched) ? (int)a.mlist[(size_t)f * M.V + i] : -1;
+    s_v[tid] = (i < st.nslots) ? (int)a.mlist[(size_t)f * a.rec_rs + i] : (int)kNoVertex;
     __syncthreads();
     const double* G = tab;
     const double* pos = tab + 9 * J;
     const double* tau = tab + 12 * J;
     const double* C = tab + 15 * J;
     double costv = 0.0;
-    if (i < st.nmatched) {
+    if (s_v[tid] != (int)kNoVertex) {
         int g = 0;
         while (g + 1 < Pt.numGroups && i >= gstart[g + 1]) ++g;
         const int nj = Pt.gnj[g];
         const int* gj = Pt.gjoints + g * kMaxJ;
         const int v = s_v[tid];
-        float* rec = a.rec + (size_t)f * a.rec_stride * M.V + i;   // SoA: field q of vertex slot i at rec[q * V]
-        const size_t RS = (size_t)M.V;
+        float* rec = a.rec + (size_t)f * a.rec_stride * a.rec_rs + i;   // SoA: field q of slot i at rec[q * rec_rs]
+        const size_t RS = (size_t)a.rec_rs;
         const float* sd = M.sd + (size_t)v * 3 * K;
         double v0[3];
 #pragma unroll
@@ -233,7 +240,8 @@ lm_rows_kernel(DevModel M, DevParts Pt, LmBuf a) {
             rec[(3 * gi + 2) * RS] = (float)((y2 - W * pos[3 * j + 2]) * s2);
         }
         // shape: sum_k w_k (G_k (Delta_v - S_k) + H_k) = B Delta_v + sum_k w_k C_k  (AvatarOptimizer.cpp:568-580)
-        float* rs = rec + (size_t)(3 * nj) * RS;
+        float* rr = rec + (size_t)(3 * nj) * RS;   // sc | rho_hi | rho_lo
+        float* rs = rr + 7 * RS;
         for (int m = 0; m < K; ++m) {
             const double d0 = sd[m], d1 = sd[K + m], d2 = sd[2 * K + m];
             double e0 = B[0] * d0 + B[1] * d1 + B[2] * d2;
@@ -254,26 +262,36 @@ lm_rows_kernel(DevModel M, DevParts Pt, LmBuf a) {
         }
         // residual sum of the vertex's correspondences, c x - sum d (AvatarOptimizer.cpp:632-639), split hi/lo
         const unsigned long long* sumv = a.sum + 3 * ((size_t)f * M.V + v);
-        float* rr = rs + (size_t)(3 * K) * RS;
+        rr[0] = (float)sc;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const double sr = (double)(long long)sumv[c] * kFixInv;
             const double rho = (cn * x[c] - sr) / sc;
             const float hi = (float)rho;
-            rr[c * RS] = hi;
-            rr[(3 + c) * RS] = (float)(rho - (double)hi);
+            rr[(1 + c) * RS] = hi;
+            rr[(4 + c) * RS] = (float)(rho - (double)hi);
             costv += x[c] * (cn * x[c] - 2.0 * sr);  // sum_i |x - d_i|^2 - sum_i |d_i|^2 = x . (c x - 2 s)
         }
-        rr[6 * RS] = (float)sc;
     }
     const double cs = block_sum(costv, scr);
     if (tid == 0) a.cpart[(size_t)f * a.maxrb + blockIdx.x] = cs;
 }
 
 // ---------------------------------------------------------------------------------------------
-// lm_syrk_kernel: A^T A of one chunk of Jacobian records (register-tiled, deterministic)
+// lm_gram_kernel: J^T J / J^T r of one chunk of Jacobian records through their Gram matrix (fp64 DMMA)
 // ---------------------------------------------------------------------------------------------
-// 8x8 block pairs (bi <= bj) covering the upper triangle of an Lp x Lp matrix, Lp = 8 n
+// A matched vertex contributes three Jacobian rows  sc [ I | -2 [y_j]x ... | S ]  whose products are all bilinear
+// in the ONE record row  rec = [ u_j = 2 sc y_j | sc | rho_hi | rho_lo | sc S ]:
+//   rot j x rot k   (u_j . u_k) I - u_k u_j^T        rot j x shape m   u_j x (sc S_m)      rot j x rho   u_j x rho
+// so J^T J and J^T r follow from the Gram matrix  Gm = sum_v rec_v rec_v^T  (nf x nf, nf = 3 nj + 7 + 3 K) with a
+// third of the multiply-adds of the expanded 3-row form and no expansion step.  The Gram matrix is accumulated in
+// fp64 on the tensor cores' DMMA path (mma.sync.m8n8k4.f64; tools/ubench/dmma_ubench.cu measures 93-97% of the fp64
+// pipe from an fp32 tile, against 65% for an 8x8 SIMT register block) from an fp32 field-major tile T[q][t] that is
+// a straight asynchronous copy (cp.async, 16 B) of the chunk's SoA records.  The epilogue turns the Gram matrix into
+// the chunk's partial of (J^T J, J^T r) in group-local column order; lm_solve_kernel adds the partials in chunk order.
+constexpr int kGramThreads = 256;
+constexpr int kGramSlots = 4;     // 2x2-block warp tiles per warp: 28 tiles (14 blocks) over 8 warps
+
 __host__ __device__ inline int num_pairs(int n) { return n * (n + 1) / 2; }
 __device__ __forceinline__ void pair_to_blocks(int pair, int n, int& bi, int& bj) {
     bi = 0;
@@ -285,17 +303,97 @@ __device__ __forceinline__ void pair_to_blocks(int pair, int n, int& bi, int& bj
     }
     bj = bi + pair;
 }
+__device__ __forceinline__ int pair_index(int bi, int bj, int n) { return bi * n - ((bi * (bi - 1)) >> 1) + (bj - bi); }
 
-// Inner-loop shape chosen with tools/ubench/syrk_ubench.cu on B200: an 8x8 fp64 register block per thread fed from
-// an fp32 shared-memory tile (conversion in the loop) reaches ~12 TDFMA/s (65% of the fp64 pipe) with 128-thread
-// CTAs, 2 per SM; fp64 tiles in shared memory or 8x4 blocks stay below 7.4 TDFMA/s (shared-memory bandwidth bound).
-constexpr int kSyrkThreads = 128;
+// upper triangle (ra <= rb) of an Lg x Lg matrix enumerated densely: rows r and Lg-1-r share one line of Lg+1 entries
+__host__ __device__ inline int tri_count(int Lg) { return ((Lg + 1) >> 1) * (Lg + 1); }
+__device__ __forceinline__ bool tri_decode(int idx, int Lg, int& ra, int& rb) {
+    const int r = idx / (Lg + 1), c = idx - r * (Lg + 1);
+    if (c < Lg - r) {
+        ra = r;
+        rb = r + c;
+        return true;
+    }
+    ra = Lg - 1 - r;
+    rb = ra + (c - (Lg - r));
+    return ra != r;   // the middle row of an odd Lg pairs with itself: its second half is empty
+}
 
-template <typename AccT>
-__global__ void __launch_bounds__(kSyrkThreads, 2)
-lm_syrk_kernel(DevModel M, DevParts Pt, LmBuf a) {
+// Gram matrix in shared memory: 8x8 blocks of the upper block triangle, row-major inside a block
+__device__ __forceinline__ double gm(const double* Gs, int n, int p, int q) {
+    if (p > q) {
+        const int t = p;
+        p = q;
+        q = t;
+    }
+    return Gs[pair_index(p >> 3, q >> 3, n) * 64 + ((p & 7) << 3) + (q & 7)];
+}
+
+// chunk partial [ upper triangle of J^T J (tri_decode order) | J^T r ] in the group's column order
+// [ p(3) | 3 per group joint | K shape ], from the Gram matrix of the records
+__device__ void emit_partial(const double* Gs, int n, int nj, int K, double* part, int tid, int nt) {
+    const int Lg = 3 + 3 * nj + K, nH = tri_count(Lg);
+    const int SC = 3 * nj, RH = SC + 1, RL = SC + 4, S0 = SC + 7;
+    for (int idx = tid; idx < nH + Lg; idx += nt) {
+        double val = 0.0;
+        if (idx < nH) {
+            int ra, rb;
+            if (!tri_decode(idx, Lg, ra, rb)) continue;
+            if (ra < 3) {
+                const int a = ra;
+                if (rb < 3) {
+                    val = (a == rb) ? gm(Gs, n, SC, SC) : 0.0;
+                } else if (rb < 3 + 3 * nj) {   // (sc I)^T (-[u_k]x): eps_abc sum sc u_k,c
+                    const int k = (rb - 3) / 3, b = (rb - 3) - 3 * k;
+                    if (a != b) {
+                        const double w = gm(Gs, n, SC, 3 * k + (3 - a - b));
+                        val = (b == (a + 1) % 3) ? w : -w;
+                    }
+                } else {
+                    val = gm(Gs, n, SC, S0 + a * K + (rb - 3 - 3 * nj));
+                }
+            } else if (ra < 3 + 3 * nj) {
+                const int j = (ra - 3) / 3, a = (ra - 3) - 3 * j;
+                if (rb < 3 + 3 * nj) {          // [u_j]x^T [u_k]x = (u_j . u_k) I - u_k u_j^T
+                    const int k = (rb - 3) / 3, b = (rb - 3) - 3 * k;
+                    val = -gm(Gs, n, 3 * k + a, 3 * j + b);
+                    if (a == b)
+                        val += gm(Gs, n, 3 * j, 3 * k) + gm(Gs, n, 3 * j + 1, 3 * k + 1) + gm(Gs, n, 3 * j + 2, 3 * k + 2);
+                } else {                        // u_j x (sc S_m)
+                    const int m = rb - 3 - 3 * nj, a1 = (a + 1) % 3, a2 = (a + 2) % 3;
+                    val = gm(Gs, n, 3 * j + a1, S0 + a2 * K + m) - gm(Gs, n, 3 * j + a2, S0 + a1 * K + m);
+                }
+            } else {
+                const int m = ra - 3 - 3 * nj, m2 = rb - 3 - 3 * nj;
+                val = gm(Gs, n, S0 + m, S0 + m2) + gm(Gs, n, S0 + K + m, S0 + K + m2) +
+                      gm(Gs, n, S0 + 2 * K + m, S0 + 2 * K + m2);
+            }
+        } else {
+            const int ra = idx - nH;
+            if (ra < 3) {
+                val = gm(Gs, n, SC, RH + ra) + gm(Gs, n, SC, RL + ra);
+            } else if (ra < 3 + 3 * nj) {       // u_j x rho
+                const int j = (ra - 3) / 3, a = (ra - 3) - 3 * j, a1 = (a + 1) % 3, a2 = (a + 2) % 3;
+                val = (gm(Gs, n, 3 * j + a1, RH + a2) + gm(Gs, n, 3 * j + a1, RL + a2)) -
+                      (gm(Gs, n, 3 * j + a2, RH + a1) + gm(Gs, n, 3 * j + a2, RL + a1));
+            } else {
+                const int m = ra - 3 - 3 * nj;
+                for (int c = 0; c < 3; ++c) val += gm(Gs, n, S0 + c * K + m, RH + c) + gm(Gs, n, S0 + c * K + m, RL + c);
+            }
+        }
+        part[idx] = val;
+    }
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ uint32_t smem_u32_lm(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(kGramThreads, 2)
+lm_gram_kernel(DevModel M, DevParts Pt, LmBuf a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ int4 fmap[3 * kMaxJ + 3 * kMaxK + 8];   // where record field q lands inside a vertex's 3 Jacobian rows
     const int c = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
     const LmState& st = a.state[f];
     if (st.done || c >= st.nchunks) return;
@@ -303,141 +401,95 @@ lm_syrk_kernel(DevModel M, DevParts Pt, LmBuf a) {
     const int4 ch = a.chunks[(size_t)f * a.maxc + c];
     const int g = ch.x, start = ch.y, count = ch.z;
     const int nj = Pt.gnj[g];
-    const int L = group_L(nj, K), Lp = (L + 7) & ~7, lda = Lp + 4;
-    float* A = reinterpret_cast<float*>(smem_raw);   // [3 * kTile][lda] Jacobian rows of the current tile
-
-    // syrk role: (block pair, row group); the row groups of a pair are adjacent lanes (shuffle reduction)
-    const int n = Lp >> 3, npairs = num_pairs(n);
-    int nrg = 1;
-    while (nrg < 32 && 2 * nrg * npairs <= kSyrkThreads) nrg <<= 1;
-    const int pair = tid / nrg, rg = tid % nrg;
-    const bool active = pair < npairs;
-    int bi = 0, bj = 0;
-    if (active) pair_to_blocks(pair, n, bi, bj);
-    AccT acc[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = AccT(0);
-    const float* recs = a.rec + (size_t)f * a.rec_stride * M.V + start;
-    const size_t RS = (size_t)M.V;
-    const int cs = 3 + 3 * nj;
-    const int nf = rec_floats(nj, K);
-    // structural zeros of the tile (diagonal of every cross-product block, pad columns, off-diagonal of the
-    // translation block) are written once: the scatter below never touches them
-    for (int e = tid; e < 3 * kTile * lda; e += kSyrkThreads) A[e] = 0.f;
-    for (int q = tid; q < nf; q += kSyrkThreads) {   // offsets r * lda + col of up to three targets; .w = negate the 2nd
-        int t0x = -1, t1x = -1, t2x = -1, neg1 = 0;
-        if (q < 3 * nj) {
-            // f_c of joint gi sits at (row (c+1)%3, col (c+2)%3) with + and at (row (c+2)%3, col (c+1)%3) with -
-            const int gi = q / 3, cc = q - 3 * gi, c0 = 3 + 3 * gi;
-            const int r1 = (cc + 1) % 3, r2 = (cc + 2) % 3;
-            t0x = r1 * lda + c0 + r2;
-            t1x = r2 * lda + c0 + r1;
-            neg1 = 1;
-        } else if (q < 3 * nj + 3 * K) {
-            const int rm = q - 3 * nj, r = rm / K, m = rm - r * K;
-            t0x = r * lda + cs + m;
-        } else if (q < 3 * nj + 3 * K + 6) {
-            const int e2 = q - 3 * nj - 3 * K, hl = e2 / 3, r = e2 - 3 * hl;
-            t0x = r * lda + cs + K + hl;
-        } else {  // sc: root translation block sc * I (AvatarOptimizer.cpp:477-481)
-            t0x = 0;
-            t1x = lda + 1;
-            t2x = 2 * lda + 2;
-        }
-        fmap[q] = make_int4(t0x, t1x, t2x, neg1);
+    const int nf = rec_floats(nj, K), nfp = (nf + 7) & ~7, n = nfp >> 3;
+    const int ldt = a.chunk_verts + 4;              // ldt % 32 == 4: conflict-free fragment loads
+    const int cnt4 = (count + 3) & ~3, ng = cnt4 >> 2;
+    float* T = reinterpret_cast<float*>(smem_raw);  // [nfp][ldt] field-major tile
+    const float* recs = a.rec + (size_t)f * a.rec_stride * a.rec_rs + start;
+    for (int e = tid; e < nf * ng; e += kGramThreads) {   // 16-byte granules; bytes past `count` are zero-filled
+        const int q = e / ng, i = e - q * ng;
+        const int valid = min(4, count - 4 * i) * 4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32_lm(T + (size_t)q * ldt + 4 * i)),
+                     "l"(recs + (size_t)q * a.rec_rs + 4 * i), "r"(valid) : "memory");
     }
+    for (int e = tid; e < (nfp - nf) * cnt4; e += kGramThreads) T[(size_t)(nf + e / cnt4) * ldt + e % cnt4] = 0.f;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    // warp roles: 2x2-block tiles of the upper block triangle, round robin over the warps
+    const int wid = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+    const int n2 = (n + 1) >> 1, nwt = num_pairs(n2);
+    int offa[kGramSlots][2], offb[kGramSlots][2], mask[kGramSlots], bis[kGramSlots], bjs[kGramSlots];
+    double acc[kGramSlots][4][2];
+#pragma unroll
+    for (int s = 0; s < kGramSlots; ++s) {
+        const int wt = wid + (kGramThreads / 32) * s;
+        int ti = 0, tj = 0;
+        mask[s] = 0;
+        if (wt < nwt) {
+            pair_to_blocks(wt, n2, ti, tj);
+            const bool i1 = 2 * ti + 1 < n, j1 = 2 * tj + 1 < n;
+            mask[s] = 1 | (j1 ? 2 : 0) | ((i1 && ti != tj) ? 4 : 0) | ((i1 && j1) ? 8 : 0);
+        }
+        bis[s] = 2 * ti;
+        bjs[s] = 2 * tj;
+        offa[s][0] = (8 * (2 * ti) + gid) * ldt + tig;
+        offa[s][1] = (8 * min(2 * ti + 1, n - 1) + gid) * ldt + tig;
+        offb[s][0] = (8 * (2 * tj) + gid) * ldt + tig;
+        offb[s][1] = (8 * min(2 * tj + 1, n - 1) + gid) * ldt + tig;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[s][q][0] = acc[s][q][1] = 0.0;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
-    for (int t0 = 0; t0 < count; t0 += kTile) {
-        const int nv = min(kTile, count - t0);
-        // coalesced load of the tile's SoA records (field q, vertex t), kLd loads in flight per thread, then
-        // scatter into Jacobian rows
-        constexpr int kLd = 10;
-        for (int e0 = tid; e0 < nf * kTile; e0 += kSyrkThreads * kLd) {
-            float vals[kLd];
-#pragma unroll
-            for (int k = 0; k < kLd; ++k) {
-                const int e = e0 + k * kSyrkThreads;
-                const int q = e / kTile, t = e - q * kTile;
-                vals[k] = (e < nf * kTile && t < nv) ? __ldg(recs + (size_t)q * RS + t0 + t) : 0.f;
-            }
-#pragma unroll
-            for (int k = 0; k < kLd; ++k) {
-                const int e = e0 + k * kSyrkThreads;
-                const int q = e / kTile, t = e - q * kTile;
-                if (e >= nf * kTile || t >= nv) continue;
-                const float val = vals[k];
-                const int4 fm = fmap[q];
-                float* A3 = A + (size_t)(3 * t) * lda;
-                A3[fm.x] = val;
-                if (fm.y >= 0) A3[fm.y] = fm.w ? -val : val;
-                if (fm.z >= 0) A3[fm.z] = val;
-            }
-        }
-        __syncthreads();
-        if (active) {
-            const int nrows = 3 * nv;
-            const float* Ab = A + 8 * bi;
-            const float* Bb = A + 8 * bj;
 #pragma unroll 2
-            for (int r = rg; r < nrows; r += nrg) {
-                const float4 a0 = *reinterpret_cast<const float4*>(Ab + (size_t)r * lda);
-                const float4 a1 = *reinterpret_cast<const float4*>(Ab + (size_t)r * lda + 4);
-                const float4 b0 = *reinterpret_cast<const float4*>(Bb + (size_t)r * lda);
-                const float4 b1 = *reinterpret_cast<const float4*>(Bb + (size_t)r * lda + 4);
-                const AccT av[8] = {AccT(a0.x), AccT(a0.y), AccT(a0.z), AccT(a0.w),
-                                    AccT(a1.x), AccT(a1.y), AccT(a1.z), AccT(a1.w)};
-                const AccT bv[8] = {AccT(b0.x), AccT(b0.y), AccT(b0.z), AccT(b0.w),
-                                    AccT(b1.x), AccT(b1.y), AccT(b1.z), AccT(b1.w)};
+    for (int k0 = 0; k0 < cnt4; k0 += 4) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+        for (int s = 0; s < kGramSlots; ++s) {
+            if (mask[s]) {   // warp-uniform
+                const double a0 = (double)T[offa[s][0] + k0], a1 = (double)T[offa[s][1] + k0];
+                const double b0 = (double)T[offb[s][0] + k0], b1 = (double)T[offb[s][1] + k0];
+                dmma884(acc[s][0][0], acc[s][0][1], a0, b0);
+                if (mask[s] & 2) dmma884(acc[s][1][0], acc[s][1][1], a0, b1);
+                if (mask[s] & 4) dmma884(acc[s][2][0], acc[s][2][1], a1, b0);
+                if (mask[s] & 8) dmma884(acc[s][3][0], acc[s][3][1], a1, b1);
             }
         }
-        __syncthreads();
     }
-    // deterministic reduction over the row groups of each pair (fixed xor tree inside the warp)
-    for (int o = nrg >> 1; o > 0; o >>= 1) {
+    __syncthreads();   // every warp is done with the tile: reuse it for the Gram matrix
+    double* Gs = reinterpret_cast<double*>(smem_raw);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+    for (int s = 0; s < kGramSlots; ++s) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], o);
+        for (int q = 0; q < 4; ++q) {
+            if (mask[s] & (1 << q)) {
+                const int bi = bis[s] + (q >> 1), bj = bjs[s] + (q & 1);
+                *reinterpret_cast<double2*>(Gs + pair_index(bi, bj, n) * 64 + gid * 8 + 2 * tig) =
+                    make_double2(acc[s][q][0], acc[s][q][1]);
+            }
+        }
     }
-    double* part = a.part + ((size_t)f * a.maxc + c) * a.pstride;
-    if (active && rg == 0) {
-        double* p = part + (size_t)pair * 64;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) p[i * 8 + j] = (double)acc[i][j];
-    }
+    __syncthreads();
+    emit_partial(Gs, n, nj, K, a.part + ((size_t)f * a.maxc + c) * a.pstride, tid, kGramThreads);
 }
 
 // ---------------------------------------------------------------------------------------------
-// lm_syrk_tc_kernel: A^T A on the 5th-generation tensor cores (AVB_JTJ_BF16_TENSOR, BASELINE.json configs[4])
+// lm_gram_tc_kernel: the same Gram matrix on the 5th-generation tensor cores (AVB_JTJ_BF16_TENSOR)
 // ---------------------------------------------------------------------------------------------
-// One CTA per chunk.  The Jacobian tile is written to shared memory TRANSPOSED (T[m][k]: m = Jacobian column,
-// k = tile row) as bf16 in the canonical K-major no-swizzle UMMA layout (8 x 16-byte core matrices), so that
+// One CTA per chunk.  The field-major record tile IS the K-major operand: T[m][k] (m = record field, k = vertex) is
+// written as bf16 in the canonical no-swizzle UMMA layout (8 x 16-byte core matrices) and
 // D[128 x N] += T[0:128, k-slice] * T[0:N, k-slice]^T is a plain tcgen05.mma.cta_group::1.kind::f16 (M = 128, K = 16 per
-// instruction) issued by one thread with both operands described by the same shared-memory tile.  The fp32
-// accumulator lives in TMEM for the whole chunk and is read back once with tcgen05.ld.  The residual columns are
-// split into three bf16 terms (24 bits), so J^T r keeps fp32-level accuracy; bf16 only perturbs J^T J and the
-// Jacobian factor of J^T r, both of which multiply small quantities at the optimum.
+// instruction) issued by one thread with both operands described by the same shared-memory tile.  The fp32 accumulator
+// lives in TMEM and is read back once with tcgen05.ld.  The residual is carried as two bf16 terms (rho_hi's bf16 head
+// and remainder in the rho_hi / rho_lo fields): 16 bits, well below the 8-bit rounding of the Jacobian factor.
 constexpr int kTcThreads = 128;
-constexpr int kTcM = 128;              // UMMA M (Jacobian columns padded)
-constexpr int kTcK = 3 * kTile;        // 192 tile rows = 12 MMA k-steps
+constexpr int kTcM = 128;              // UMMA M (record fields padded)
 
-__device__ __forceinline__ uint32_t smem_u32_lm(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__global__ void __launch_bounds__(kTcThreads, 4)
-lm_syrk_tc_kernel(DevModel M, DevParts Pt, LmBuf a) {
+__global__ void __launch_bounds__(kTcThreads, 2)
+lm_gram_tc_kernel(DevModel M, DevParts Pt, LmBuf a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
-    __shared__ int4 fmap[3 * kMaxJ + 3 * kMaxK + 8];
     const int c = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const LmState& st = a.state[f];
     if (st.done || c >= st.nchunks) return;
@@ -445,11 +497,11 @@ lm_syrk_tc_kernel(DevModel M, DevParts Pt, LmBuf a) {
     const int4 ch = a.chunks[(size_t)f * a.maxc + c];
     const int g = ch.x, start = ch.y, count = ch.z;
     const int nj = Pt.gnj[g];
-    const int L = group_L(nj, K) + 1;                 // three residual columns
-    const int Lp = (L + 7) & ~7, N = (L + 15) & ~15;  // N: UMMA N (multiple of 16 for M = 128)
-    const int cs = 3 + 3 * nj, nf = rec_floats(nj, K);
-    unsigned short* T = reinterpret_cast<unsigned short*>(smem_raw);   // bf16 bits, [kTcM/8][kTcK/8][8][8]
-    auto t_off = [](int m, int k) { return (((m >> 3) * (kTcK >> 3) + (k >> 3)) << 6) + ((m & 7) << 3) + (k & 7); };
+    const int nf = rec_floats(nj, K), nfp = (nf + 7) & ~7, n = nfp >> 3;
+    const int N = (nf + 15) & ~15;                   // UMMA N (multiple of 16 for M = 128)
+    const int Kx = a.chunk_verts;                    // K extent of the tile (multiple of 64)
+    const int cnt16 = (count + 15) & ~15;
+    uint4* T = reinterpret_cast<uint4*>(smem_raw);   // bf16 [kTcM/8][Kx/8] core matrices of 8 rows x 16 bytes
 
     if (wid == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32_lm(&tmem_base_s)), "r"(128));
@@ -459,111 +511,70 @@ lm_syrk_tc_kernel(DevModel M, DevParts Pt, LmBuf a) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32_lm(&mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int e = tid; e < kTcM * kTcK / 2; e += kTcThreads) reinterpret_cast<uint32_t*>(T)[e] = 0u;
-    for (int q = tid; q < nf; q += kTcThreads) {   // targets (column m << 2 | row-in-vertex r); .w: negate the 2nd
-        int t0x = -1, t1x = -1, t2x = -1, neg1 = 0;
-        if (q < 3 * nj) {
-            const int gi = q / 3, cc = q - 3 * gi, c0 = 3 + 3 * gi;
-            const int r1 = (cc + 1) % 3, r2 = (cc + 2) % 3;
-            t0x = ((c0 + r2) << 2) | r1;
-            t1x = ((c0 + r1) << 2) | r2;
-            neg1 = 1;
-        } else if (q < 3 * nj + 3 * K) {
-            const int rm = q - 3 * nj, r = rm / K, m = rm - r * K;
-            t0x = ((cs + m) << 2) | r;
-        } else if (q < 3 * nj + 3 * K + 3) {   // rho_hi: split into three bf16 columns below
-            const int r = q - 3 * nj - 3 * K;
-            t0x = ((cs + K) << 2) | r;
-            neg1 = 2;
-        } else if (q < 3 * nj + 3 * K + 6) {   // rho_lo (fp32 residue): below bf16x3 resolution, dropped
-            t0x = -1;
-        } else {
-            t0x = (0 << 2) | 0;
-            t1x = (1 << 2) | 1;
-            t2x = (2 << 2) | 2;
+    // fp32 records -> bf16 tile, eight vertices (one 16-byte core-matrix row) per step; everything the MMAs read
+    // (fields < 128, vertices < cnt16) is written, zeros outside the chunk
+    const float* recs = a.rec + (size_t)f * a.rec_stride * a.rec_rs + start;
+    const int RLo = 3 * nj + 4, n8 = cnt16 >> 3;
+    for (int e = tid; e < kTcM * n8; e += kTcThreads) {
+        const int m = e / n8, i = e - m * n8;
+        uint4 out = make_uint4(0u, 0u, 0u, 0u);
+        if (m < nf && 8 * i < count) {
+            const bool second = (m >= RLo && m < RLo + 3);       // rho_lo slot carries rho_hi - bf16(rho_hi)
+            const float* src = recs + (size_t)(second ? m - 3 : m) * a.rec_rs + 8 * i;
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
+            const float4 v1 = (8 * i + 4 < count) ? __ldg(reinterpret_cast<const float4*>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            uint32_t w[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                unsigned short b2[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    float x = (8 * i + 2 * h + u < count) ? v[2 * h + u] : 0.f;
+                    if (second) x -= __bfloat162float(__float2bfloat16_rn(x));
+                    const __nv_bfloat16 b = __float2bfloat16_rn(x);
+                    b2[u] = *reinterpret_cast<const unsigned short*>(&b);
+                }
+                w[h] = (uint32_t)b2[0] | ((uint32_t)b2[1] << 16);
+            }
+            out = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        fmap[q] = make_int4(t0x, t1x, t2x, neg1);
+        T[((m >> 3) * (Kx >> 3) + i) * 8 + (m & 7)] = out;
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_d = tmem_base_s;
-    // instruction descriptor: D = F32, A = B = BF16, K-major both, N >> 3 at [17,23), M >> 4 at [24,29)
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
-    // shared-memory descriptor: start >> 4 | LBO (K-direction core-matrix stride, 128 B) | SBO (8-row group stride) | version 1
-    const uint64_t desc0 = (uint64_t)((smem_u32_lm(T) >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) |
-                           ((uint64_t)(((kTcK >> 3) * 128) >> 4) << 32) | (1ull << 46);
-    const float* recs = a.rec + (size_t)f * a.rec_stride * M.V + start;
-    const size_t RS = (size_t)M.V;
-    int ntile = 0;
-    for (int t0 = 0; t0 < count; t0 += kTile, ++ntile) {
-        const int nv = min(kTile, count - t0);
-        constexpr int kLd = 10;
-        for (int e0 = tid; e0 < nf * kTile; e0 += kTcThreads * kLd) {
-            float vals[kLd];
-#pragma unroll
-            for (int k = 0; k < kLd; ++k) {
-                const int e = e0 + k * kTcThreads;
-                const int q = e / kTile, t = e - q * kTile;
-                vals[k] = (e < nf * kTile && t < nv) ? __ldg(recs + (size_t)q * RS + t0 + t) : 0.f;   // stale rows -> 0
-            }
-#pragma unroll
-            for (int k = 0; k < kLd; ++k) {
-                const int e = e0 + k * kTcThreads;
-                const int q = e / kTile, t = e - q * kTile;
-                if (e >= nf * kTile) continue;
-                const int4 fm = fmap[q];
-                if (fm.x < 0) continue;
-                const float val = vals[k];
-                auto put = [&](int tgt, float v) {
-                    const __nv_bfloat16 b = __float2bfloat16_rn(v);
-                    T[t_off(tgt >> 2, 3 * t + (tgt & 3))] = *reinterpret_cast<const unsigned short*>(&b);
-                };
-                if (fm.w == 2) {   // residual: three bf16 terms in consecutive columns
-                    const __nv_bfloat16 b0 = __float2bfloat16_rn(val);
-                    const float r1 = val - __bfloat162float(b0);
-                    const __nv_bfloat16 b1 = __float2bfloat16_rn(r1);
-                    const float r2 = r1 - __bfloat162float(b1);
-                    const int m0 = fm.x >> 2, kk = 3 * t + (fm.x & 3);
-                    T[t_off(m0, kk)] = *reinterpret_cast<const unsigned short*>(&b0);
-                    T[t_off(m0 + 1, kk)] = *reinterpret_cast<const unsigned short*>(&b1);
-                    put(((m0 + 2) << 2) | (fm.x & 3), r2);
-                } else {
-                    put(fm.x, val);
-                    if (fm.y >= 0) put(fm.y, fm.w == 1 ? -val : val);
-                    if (fm.z >= 0) put(fm.z, val);
-                }
-            }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
-        asm volatile("tcgen05.fence::before_thread_sync;");
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;");
+    if (tid == 0) {
+        // instruction descriptor: D = F32, A = B = BF16, K-major both, N >> 3 at [17,23), M >> 4 at [24,29)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+        // shared-memory descriptor: start >> 4 | LBO (K-direction core-matrix stride, 128 B) | SBO (8-row group stride) | version 1
+        const uint64_t desc0 = (uint64_t)((smem_u32_lm(T) >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) |
+                               ((uint64_t)(((Kx >> 3) * 128) >> 4) << 32) | (1ull << 46);
 #pragma unroll 1
-            for (int s2 = 0; s2 < kTcK / 16; ++s2) {
-                const uint64_t desc = desc0 + (uint64_t)((s2 * 256) >> 4);   // two core matrices per k-step
-                const uint32_t accum = (ntile > 0 || s2 > 0) ? 1u : 0u;
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                    ::"r"(tmem_d), "l"(desc), "l"(desc), "r"(idesc), "r"(accum) : "memory");
-            }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32_lm(&mbar)) : "memory");
+        for (int s2 = 0; s2 < (cnt16 >> 4); ++s2) {
+            const uint64_t desc = desc0 + (uint64_t)((s2 * 256) >> 4);   // two core matrices per k-step
+            const uint32_t accum = s2 > 0 ? 1u : 0u;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                ::"r"(tmem_d), "l"(desc), "l"(desc), "r"(idesc), "r"(accum) : "memory");
         }
-        {   // the tile may be overwritten (and TMEM read) only after the MMAs retire
-            const uint32_t parity = (uint32_t)(ntile & 1);
-            uint32_t done = 0;
-            while (!done)
-                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                             : "=r"(done) : "r"(smem_u32_lm(&mbar)), "r"(parity) : "memory");
-        }
-        asm volatile("tcgen05.fence::after_thread_sync;");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32_lm(&mbar)) : "memory");
     }
-    // epilogue: TMEM lane = Jacobian column m (row of A^T A); warp w owns lanes [32w, 32w+32)
-    double* part = a.part + ((size_t)f * a.maxc + c) * a.pstride;
-    const int m = 32 * wid + lane, n8 = Lp >> 3;
-    for (int cb = 0; cb < (N >> 3); ++cb) {
+    {   // the tile may be overwritten (and TMEM read) only after the MMAs retire
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32_lm(&mbar)), "r"(0u) : "memory");
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    __syncthreads();
+    // epilogue: TMEM lane = record field m (row of the Gram matrix); warp w owns lanes [32w, 32w+32)
+    double* Gs = reinterpret_cast<double*>(smem_raw);
+    const int m = 32 * wid + lane;
+    for (int cb = 0; cb < n; ++cb) {
         uint32_t v[8];
         const uint32_t taddr = tmem_d + ((uint32_t)(32 * wid) << 16) + (uint32_t)(8 * cb);
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -571,9 +582,8 @@ lm_syrk_tc_kernel(DevModel M, DevParts Pt, LmBuf a) {
                      : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const int bi = m >> 3;
-        if (m < Lp && cb >= bi && cb < n8) {
-            const int pair = bi * n8 - (bi * (bi - 1)) / 2 + (cb - bi);
-            double* p = part + (size_t)pair * 64 + (m & 7) * 8;
+        if (m < nfp && cb >= bi) {
+            double* p = Gs + pair_index(bi, cb, n) * 64 + (m & 7) * 8;
 #pragma unroll
             for (int j = 0; j < 8; ++j) p[j] = (double)__uint_as_float(v[j]);
         }
@@ -581,13 +591,14 @@ lm_syrk_tc_kernel(DevModel M, DevParts Pt, LmBuf a) {
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(128));
+    emit_partial(Gs, n, nj, K, a.part + ((size_t)f * a.maxc + c) * a.pstride, tid, kTcThreads);
 }
 
 // ---------------------------------------------------------------------------------------------
 // lm_solve_kernel
 // ---------------------------------------------------------------------------------------------
 struct SolveSmem {
-    double *xs, *xt, *tb, *Hs, *gs, *glo, *gl2, *gcur, *delta, *aa, *ycomp, *scr;
+    double *xs, *xt, *tb, *Hs, *gs, *glo, *gcur, *delta, *aa, *ycomp, *scr;
     int* iscr;
 };
 __host__ __device__ inline size_t solve_smem_bytes(int J, int K, int C) {
@@ -608,7 +619,6 @@ __device__ inline SolveSmem carve_solve(unsigned char* raw, const DevModel& M) {
     S.glo = d; d += (P + 1) & ~1;
     S.gcur = d; d += (P + 1) & ~1;
     S.delta = d; d += (P + 1) & ~1;
-    S.gl2 = S.delta;   // third gradient term of the tensor-core layout; delta is only written after the reduction
     S.aa = d; d += (D + 1) & ~1;
     S.ycomp = d; d += (size_t)C * ((D + 1) & ~1);
     S.scr = d; d += 64;
@@ -709,8 +719,6 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
     for (int i = tid; i < P * P; i += kSolveThreads) S.Hs[i] = 0.0;
     for (int i = tid; i < P; i += kSolveThreads) {
         S.gs[i] = 0.0;
-        S.glo[i] = 0.0;
-        S.gl2[i] = 0.0;
         S.gcur[i] = gcur_g[i];
     }
     __syncthreads();
@@ -722,36 +730,41 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
         int c1 = c + 1;   // chunks [c, c1) belong to the same column group: identical partial layout
         while (c1 < st.nchunks && a.chunks[(size_t)f * a.maxc + c1].x == g) ++c1;
         const int* gj = Pt.gjoints + g * kMaxJ;
-        const int L = group_L(nj, K) + (a.rho_cols - 2), Lp = (L + 7) & ~7, n = Lp >> 3;
-        const int rc = a.rho_cols;
-        const int npairs = num_pairs(n);
+        const int Lg = group_L(nj, K), nH = tri_count(Lg), nrun = c1 - c;
         const double* part = a.part + ((size_t)f * a.maxc + c) * a.pstride;
         auto colmap = [&](int q) -> int {
             if (q < 3) return q;
             if (q < 3 + 3 * nj) return 3 + 3 * gj[(q - 3) / 3] + (q - 3) % 3;
-            if (q < L - rc) return 3 + 3 * J + (q - 3 - 3 * nj);
-            return -1;
+            return 3 + 3 * J + (q - 3 - 3 * nj);
         };
-        for (int idx = tid; idx < npairs * 64; idx += kSolveThreads) {
-            const int pair = idx >> 6, e = idx & 63;
-            int bi, bj;
-            pair_to_blocks(pair, n, bi, bj);
-            const int qa = 8 * bi + (e >> 3), qb = 8 * bj + (e & 7);
-            if (qa > qb || qa >= L - rc || qb >= L) continue;
-            double val = 0.0;   // chunk order is fixed => deterministic
-            for (int cc = 0; cc < c1 - c; ++cc) val += part[(size_t)cc * a.pstride + idx];
-            const int ca = colmap(qa);
-            if (qb == L - rc) S.gs[ca] += val;                 // residual columns: hi | lo (| third bf16 term)
-            else if (qb == L - rc + 1) S.glo[ca] += val;
-            else if (qb == L - rc + 2) S.gl2[ca] += val;
-            else S.Hs[(size_t)ca * P + colmap(qb)] += val;
+        constexpr int kB = 4;   // independent loads in flight per thread
+        for (int i0 = tid; i0 < nH + Lg; i0 += kSolveThreads * kB) {
+            double val[kB];
+#pragma unroll
+            for (int u = 0; u < kB; ++u) {
+                const int idx = i0 + u * kSolveThreads;
+                double v = 0.0;   // chunk order is fixed => deterministic
+                if (idx < nH + Lg)
+                    for (int cc = 0; cc < nrun; ++cc) v += __ldg(part + (size_t)cc * a.pstride + idx);
+                val[u] = v;
+            }
+#pragma unroll
+            for (int u = 0; u < kB; ++u) {
+                const int idx = i0 + u * kSolveThreads;
+                if (idx >= nH + Lg) continue;
+                if (idx >= nH) {
+                    S.gs[colmap(idx - nH)] += val[u];
+                } else {
+                    int ra, rb;
+                    if (tri_decode(idx, Lg, ra, rb)) S.Hs[(size_t)colmap(ra) * P + colmap(rb)] += val[u];
+                }
+            }
         }
         __syncthreads();
         c = c1;
     }
-    for (int b = 0; b * 256 < st.nmatched; ++b) csum += a.cpart[(size_t)f * a.maxrb + b];
+    for (int b = 0; b * 256 < st.nslots; ++b) csum += a.cpart[(size_t)f * a.maxrb + b];
     double cost_t = 0.5 * (csum + st.Qsum);
-    for (int i = tid; i < P; i += kSolveThreads) S.gs[i] += S.glo[i] + S.gl2[i];
     for (int i = tid; i < P * P; i += kSolveThreads) {
         const int r = i / P, c = i - r * P;
         if (r > c) S.Hs[i] = S.Hs[(size_t)c * P + r];
@@ -1026,10 +1039,11 @@ size_t lm_prep_smem(const DevModel& M) {
 size_t lm_rows_smem(const DevModel& M) {
     return (size_t)(tab_doubles(M.J, M.K) + ((M.K + 1) & ~1) + 32) * 8 + (kMaxGroups + 2) * 4 + 256 * 4 + 64;
 }
-size_t lm_syrk_smem(const DevModel& M, int max_nj, bool acc64) {
-    const int L = group_L(max_nj, M.K), Lp = (L + 7) & ~7, lda = Lp + 4;
-    (void)acc64;
-    return (size_t)3 * kTile * lda * 4 + 64;
+size_t lm_gram_smem(const DevModel& M, int max_nj, int chunk_verts, bool tensor) {
+    const int nf = rec_floats(max_nj, M.K), nfp = (nf + 7) & ~7, n = nfp >> 3;
+    const size_t tile = tensor ? (size_t)kTcM * chunk_verts * 2 : (size_t)nfp * (chunk_verts + 4) * 4;
+    const size_t gram = (size_t)num_pairs(n) * 64 * 8;
+    return (tile > gram ? tile : gram) + (tensor ? 1024 : 128);
 }
 
 cudaError_t launch_lm_prep(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, cudaStream_t st) {
@@ -1037,30 +1051,23 @@ cudaError_t launch_lm_prep(const DevModel& M, const DevParts& Pt, const LmBuf& a
     return cudaGetLastError();
 }
 
-// part: 0 = lm_rows_kernel, 1 = lm_syrk_kernel, 2 = lm_solve_kernel (one evaluation = the three in order)
-cudaError_t launch_lm_eval_part(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, int max_nj, bool acc64,
+// part: 0 = lm_rows_kernel, 1 = lm_gram_kernel / lm_gram_tc_kernel, 2 = lm_solve_kernel (one evaluation = the three in order)
+cudaError_t launch_lm_eval_part(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, int max_nj, bool tensor,
                                 int part, cudaStream_t st) {
     if (part == 0) {
         lm_rows_kernel<<<dim3(a.maxrb, batch), 256, lm_rows_smem(M), st>>>(M, Pt, a);
         return cudaGetLastError();
     }
-    if (part == 1 && a.rho_cols == 3) {
-        const size_t tsm = (size_t)kTcM * kTcK * 2 + 1024;
-        cudaError_t e = cudaFuncSetAttribute(lm_syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
-        if (e != cudaSuccess) return e;
-        lm_syrk_tc_kernel<<<dim3(a.maxc, batch), kTcThreads, tsm, st>>>(M, Pt, a);
-        return cudaGetLastError();
-    }
     if (part == 1) {
-        const size_t jsm = lm_syrk_smem(M, max_nj, acc64);
-        cudaError_t e = acc64 ? cudaFuncSetAttribute(lm_syrk_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm)
-                              : cudaFuncSetAttribute(lm_syrk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm);
+        const size_t gsm = lm_gram_smem(M, max_nj, a.chunk_verts, tensor);
+        cudaError_t e = tensor ? cudaFuncSetAttribute(lm_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm)
+                               : cudaFuncSetAttribute(lm_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
         if (e != cudaSuccess) return e;
         const dim3 grid(a.maxc, batch);
-        if (acc64)
-            lm_syrk_kernel<double><<<grid, kSyrkThreads, jsm, st>>>(M, Pt, a);
+        if (tensor)
+            lm_gram_tc_kernel<<<grid, kTcThreads, gsm, st>>>(M, Pt, a);
         else
-            lm_syrk_kernel<float><<<grid, kSyrkThreads, jsm, st>>>(M, Pt, a);
+            lm_gram_kernel<<<grid, kGramThreads, gsm, st>>>(M, Pt, a);
         return cudaGetLastError();
     }
     const size_t ssm = solve_smem_bytes(M.J, M.K, M.gmmC);
@@ -1071,10 +1078,16 @@ cudaError_t launch_lm_eval_part(const DevModel& M, const DevParts& Pt, const LmB
 }
 
 long long lm_part_stride(int max_nj, int K) {
-    const int L = group_L(max_nj, K) + 1, Lp = (L + 7) & ~7;   // + 1: the tensor-core layout has a third residual column
-    return (long long)num_pairs(Lp >> 3) * 64;
+    const int Lg = group_L(max_nj, K);
+    return (long long)((tri_count(Lg) + Lg + 1) & ~1);
 }
 int lm_tab_doubles(int J, int K) { return tab_doubles(J, K); }
-int lm_rec_floats(int max_nj, int K) { return (rec_floats(max_nj, K) + 3) & ~3; }
+int lm_rec_floats(int max_nj, int K) { return rec_floats(max_nj, K); }
+int lm_rec_slots(int V) { return (V + 3 * kMaxGroups + 3) & ~3; }
+size_t lm_gram_smem_bytes(int max_nj, int K, int chunk_verts, bool tensor) {
+    DevModel M{};
+    M.K = K;
+    return lm_gram_smem(M, max_nj, chunk_verts, tensor);
+}
 
 }  // namespace avb
