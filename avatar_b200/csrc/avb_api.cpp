@@ -100,6 +100,11 @@ struct avb_fitter {
     float* d_rec = nullptr; int* d_gstart = nullptr; int maxrb = 0, rec_stride = 0, rec_rs = 0;
     int maxc = 0, tabD = 0, max_nj = 0, chunk_verts = 256;
     long long pstride = 0;
+    // lm_flow_kernel work queue
+    unsigned long long* d_qslots = nullptr; unsigned int* d_qctrl = nullptr; int *d_rows_left = nullptr, *d_gram_left = nullptr;
+    unsigned long long* d_qprof = nullptr; unsigned int qcap = 0; bool use_flow = true;
+    unsigned int* h_qctrl = nullptr;
+    std::vector<int> group_nj, group_nv;   // Jacobian column groups: joints and model vertices per group
     int *d_chunk_frame = nullptr, *d_chunk_count = nullptr, *d_chunk_qblock = nullptr, *d_frame_qblock = nullptr;
     long long* d_chunk_begin = nullptr;
     double *d_dump_cost = nullptr, *d_dump_grad = nullptr, *d_dump_H = nullptr;
@@ -560,6 +565,8 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     std::vector<int> gorder, gvstart, gjoints, gnj;
     build_groups(*m, max_groups, gorder, gvstart, gjoints, gnj);
     dp.numGroups = (int)gnj.size();
+    ft->group_nj = gnj;
+    for (size_t g = 0; g + 1 < gvstart.size(); ++g) ft->group_nv.push_back(gvstart[g + 1] - gvstart[g]);
     TRY(dev_put(ft, &dp.gorder, gorder));
     TRY(dev_put(ft, &dp.gvstart, gvstart));
     TRY(dev_put(ft, &dp.gjoints, gjoints));
@@ -605,6 +612,20 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     TRY(dev_alloc(ft, &ft->d_mlist, B * (size_t)ft->rec_rs));
     TRY(dev_alloc(ft, &ft->d_chunks, B * (size_t)ft->maxc));
     TRY(dev_alloc(ft, &ft->d_state, B));
+    {   // work queue: ring of 4x the tasks that can be outstanding at once
+        size_t need = 4 * B * (size_t)std::max(ft->maxrb, ft->maxc);
+        ft->qcap = 1024;
+        while (ft->qcap < need) ft->qcap <<= 1;
+        TRY(dev_alloc(ft, &ft->d_qslots, (size_t)ft->qcap));
+        TRY(dev_alloc(ft, &ft->d_qctrl, 8));
+        TRY(dev_alloc(ft, &ft->d_rows_left, B));
+        TRY(dev_alloc(ft, &ft->d_gram_left, B));
+        TRY(dev_alloc(ft, &ft->d_qprof, 4));
+        CUDA_TRY_FT(cudaMemset(ft->d_qslots, 0xFF, (size_t)ft->qcap * 8));
+        CUDA_TRY_FT(cudaMemset(ft->d_qctrl, 0, 32));
+        CUDA_TRY_FT(cudaMemset(ft->d_qprof, 0, 32));
+        if (const char* e = std::getenv("AVB_FLOW")) ft->use_flow = std::atoi(e) != 0;
+    }
     ft->max_chunks = (int)std::max<size_t>(NT / 512 + 2 * B + 8, (size_t)8 * ft->num_sms + 2 * B + 8);
     ft->max_qblocks = (int64_t)(NT / kQBlock + B + 8);
     TRY(dev_alloc(ft, &ft->d_qpart, (size_t)ft->max_qblocks));
@@ -615,6 +636,7 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     TRY(dev_alloc(ft, &ft->d_frame_qblock, B + 1));
     TRY(pin_alloc(ft, &ft->h_x, B * nx));
     TRY(pin_alloc(ft, &ft->h_stats, B));
+    TRY(pin_alloc(ft, &ft->h_qctrl, 4));
     TRY(pin_alloc(ft, &ft->h_chunk_frame, (size_t)ft->max_chunks));
     TRY(pin_alloc(ft, &ft->h_chunk_count, (size_t)ft->max_chunks));
     TRY(pin_alloc(ft, &ft->h_chunk_qblock, (size_t)ft->max_chunks));
@@ -699,7 +721,7 @@ int check_options(const avb_fitter* ft, const avb_options* o) {
 }
 
 // kernel classes for avb_last_kernel_ms
-enum { KC_POSE = 0, KC_NN = 1, KC_PREP = 2, KC_ROWS = 3, KC_SYRK = 4, KC_SOLVE = 5, KC_FINAL = 6, KC_COUNT = 7 };
+enum { KC_POSE = 0, KC_NN = 1, KC_PREP = 2, KC_ROWS = 3, KC_GRAM = 4, KC_SOLVE = 5, KC_FINAL = 6, KC_FLOW = 7, KC_COUNT = 8 };
 struct ProfScope {   // records an event pair around one launch when profiling is on
     avb_fitter* ft;
     size_t idx;
@@ -805,6 +827,16 @@ LmBuf lm_buf(avb_fitter* ft, double* dx, const avb_options* o) {
     a.function_tolerance = o->function_tolerance;
     a.max_iters = o->max_iters_per_icp;
     a.stats = ft->d_stats;
+    // one persistent data-flow kernel for the whole inner solve; the tensor-core Gram variant and the debug
+    // evaluation (one evaluation, dump) use the staged kernels
+    if (ft->use_flow && o->jtj_precision != AVB_JTJ_BF16_TENSOR) {
+        a.q.slots = ft->d_qslots;
+        a.q.ctrl = ft->d_qctrl;
+        a.q.rows_left = ft->d_rows_left;
+        a.q.gram_left = ft->d_gram_left;
+        a.q.prof = ft->profile ? ft->d_qprof : nullptr;
+        a.q.cap_mask = ft->qcap - 1;
+    }
     return a;
 }
 
@@ -816,6 +848,15 @@ int enqueue_solve(avb_fitter* ft, const LmBuf& la, const avb_options* o, int rou
         CUDA_TRY(launch_lm_prep(ft->dm, ft->dp, la, ft->batch, st));
     }
     ++ft->launches;
+    if (la.q.slots) {
+        if (la.q.prof) CUDA_TRY(cudaMemsetAsync(ft->d_qprof, 0, 32, st));
+        const int ctas = std::min(2 * ft->num_sms, std::max(1, ft->batch * 16));
+        ProfScope ps(ft, KC_FLOW);
+        CUDA_TRY(launch_lm_flow(ft->dm, ft->dp, la, ft->max_nj, ctas, st));
+        ++ft->launches;
+        (void)rounds;
+        return AVB_OK;
+    }
     const bool tensor = o->jtj_precision == AVB_JTJ_BF16_TENSOR;   // AVB_JTJ_FP32 permits, but no longer uses, fp32 sums
     for (int r = 0; r < rounds; ++r) {
         for (int part = 0; part < 3; ++part) {
@@ -913,16 +954,36 @@ int avb_set_profiling(avb_fitter* ft, int enabled) {
     return AVB_OK;
 }
 
-int avb_last_kernel_ms(avb_fitter* ft, float* total_ms7, int32_t* launches7) {
-    if (!ft || !total_ms7 || !launches7) return fail(AVB_ERR_INVALID, "null argument");
+int avb_fitter_groups(avb_fitter* ft, int32_t* num_groups, int32_t* joints16, int32_t* vertices16) {
+    if (!ft || !num_groups) return fail(AVB_ERR_INVALID, "null argument");
+    *num_groups = (int32_t)ft->group_nj.size();
+    for (size_t g = 0; g < ft->group_nj.size() && g < 16; ++g) {
+        if (joints16) joints16[g] = ft->group_nj[g];
+        if (vertices16) vertices16[g] = ft->group_nv[g];
+    }
+    return AVB_OK;
+}
+
+int avb_last_flow_task_ms(avb_fitter* ft, float* ms4) {
+    if (!ft || !ms4) return fail(AVB_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(ft->device));
     CUDA_TRY(cudaStreamSynchronize(ft->stream));
-    for (int k = 0; k < KC_COUNT; ++k) { total_ms7[k] = 0.f; launches7[k] = 0; }
+    unsigned long long ns[4];
+    CUDA_TRY(cudaMemcpy(ns, ft->d_qprof, 32, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 4; ++k) ms4[k] = (float)((double)ns[k] * 1e-6);
+    return AVB_OK;
+}
+
+int avb_last_kernel_ms(avb_fitter* ft, float* total_ms8, int32_t* launches8) {
+    if (!ft || !total_ms8 || !launches8) return fail(AVB_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    CUDA_TRY(cudaStreamSynchronize(ft->stream));
+    for (int k = 0; k < KC_COUNT; ++k) { total_ms8[k] = 0.f; launches8[k] = 0; }
     for (size_t i = 0; i < ft->pcls.size(); ++i) {
         float ms = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&ms, ft->pev[2 * i], ft->pev[2 * i + 1]));
-        total_ms7[ft->pcls[i]] += ms;
-        ++launches7[ft->pcls[i]];
+        total_ms8[ft->pcls[i]] += ms;
+        ++launches8[ft->pcls[i]];
     }
     return AVB_OK;
 }
@@ -936,7 +997,13 @@ int avb_download_results(avb_fitter* ft, double* x_out, avb_stats* stats, double
     if (x_out) CUDA_TRY(cudaMemcpyAsync(ft->h_x, ft->d_x, (size_t)B * nx * 8, cudaMemcpyDeviceToHost, st));
     if (stats) CUDA_TRY(cudaMemcpyAsync(ft->h_stats, ft->d_stats, (size_t)B * sizeof(FrameStats), cudaMemcpyDeviceToHost, st));
     if (cloud_out) CUDA_TRY(cudaMemcpyAsync(cloud_out, ft->d_cloud, (size_t)B * 3 * V * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ft->h_qctrl, ft->d_qctrl, 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (ft->h_qctrl[3] != 0u) {   // leave the queue usable for the next call
+        cudaMemset(ft->d_qctrl, 0, 32);
+        cudaMemset(ft->d_qslots, 0xFF, (size_t)ft->qcap * 8);
+        return fail(AVB_ERR_CUDA, "lm_flow_kernel watchdog fired: the work queue starved (internal error)");
+    }
     if (x_out) std::memcpy(x_out, ft->h_x, (size_t)B * nx * 8);
     int worst = AVB_OK;
     if (stats) {

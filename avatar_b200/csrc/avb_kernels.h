@@ -45,6 +45,15 @@ struct LmState {  // per-frame Levenberg-Marquardt state, lives in HBM between t
     int done, iters, accepted, ncorr, nmatched, nchunks, evals, nslots;   // nslots: record slots incl. alignment gaps
 };
 
+struct FlowQueue {  // device work queue of lm_flow_kernel
+    unsigned long long* slots;   // [cap_mask + 1] ring of (ticket << 32 | task); nullptr: staged kernels
+    unsigned int* ctrl;          // [0] head, [1] tail, [2] frames still running, [3] watchdog flag, [4] CTAs that left
+    int* rows_left;              // [batch] record blocks of the current evaluation still running
+    int* gram_left;              // [batch] chunks of the current evaluation still running
+    unsigned long long* prof;    // nullable [4]: CTA nanoseconds in rows / gram / solve tasks / waiting
+    unsigned int cap_mask;
+};
+
 struct LmBuf {
     double* x;                   // [batch][nx] current point (in/out)
     double* xt;                  // [batch][nx] trial point
@@ -75,6 +84,7 @@ struct LmBuf {
     double* trace;               // nullable [batch][trace_cap][nx]
     int trace_cap;
     FrameStats* stats;           // [batch]
+    FlowQueue q;
 };
 
 size_t pose_smem_bytes(int V, int J, int K);
@@ -84,6 +94,8 @@ cudaError_t launch_lm_prep(const DevModel& M, const DevParts& Pt, const LmBuf& a
 // one evaluation = parts 0 (lm_rows_kernel), 1 (lm_gram_kernel or lm_gram_tc_kernel), 2 (lm_solve_kernel) in order
 cudaError_t launch_lm_eval_part(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, int max_nj, bool tensor,
                                 int part, cudaStream_t st);
+// the same evaluations as one persistent data-flow kernel (launch_lm_prep with a.q set seeds the queue)
+cudaError_t launch_lm_flow(const DevModel& M, const DevParts& Pt, const LmBuf& a, int max_nj, int ctas, cudaStream_t st);
 long long lm_part_stride(int max_nj, int K);
 int lm_tab_doubles(int J, int K);
 int lm_rec_floats(int max_nj, int K);

@@ -31,6 +31,67 @@ constexpr int kJacThreads = 256;
 constexpr int kSolveThreads = 256;
 constexpr unsigned short kNoVertex = 0xFFFFu;   // gap slot in mlist
 
+// Buffers that one task writes and a later task (possibly on another SM) reads inside the same lm_flow_kernel launch
+// are read through L2 (ld.global.cg): L1 is not coherent across SMs.
+__device__ __forceinline__ double ldg2(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ int ldg2(const int* p) { return __ldcg(p); }
+__device__ __forceinline__ LmState load_state(const LmState* p) {
+    static_assert(sizeof(LmState) % 16 == 0, "LmState is copied as 16-byte words");
+    LmState st;
+    const longlong2* src = reinterpret_cast<const longlong2*>(p);
+    longlong2* dst = reinterpret_cast<longlong2*>(&st);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(LmState) / 16); ++i) dst[i] = __ldcg(src + i);
+    return st;
+}
+
+// ---------------------------------------------------------------------------------------------
+// work queue of lm_flow_kernel (tasks are pushed only when their inputs are complete, so no task ever waits)
+// ---------------------------------------------------------------------------------------------
+enum { kTaskRows = 0, kTaskGram = 1 };
+__device__ __forceinline__ unsigned make_task(int type, int f, int idx) {
+    return ((unsigned)type << 30) | ((unsigned)f << 12) | (unsigned)idx;
+}
+// one thread: append tasks (type, f, 0..n-1); the caller has fenced the data the tasks will read
+__device__ void flow_push(const FlowQueue& q, int type, int f, int n) {
+    const unsigned t0 = atomicAdd(&q.ctrl[1], (unsigned)n);
+    for (int i = 0; i < n; ++i) {
+        const unsigned t = t0 + (unsigned)i;
+        const unsigned long long v = ((unsigned long long)t << 32) | make_task(type, f, i);
+        *reinterpret_cast<volatile unsigned long long*>(q.slots + (t & q.cap_mask)) = v;
+    }
+}
+// one thread: next task, or -1 when every frame of the launch has finished (or the watchdog fired).  A ticket is
+// taken unconditionally (one atomicAdd: a compare-and-swap loop collapses under ~300 contending CTAs) and the CTA
+// waits for the ticket's slot; tickets taken past the last push are reconciled by the last CTA to leave the kernel.
+__device__ int flow_pop(const FlowQueue& q) {
+    volatile unsigned* ctrl = q.ctrl;
+    const unsigned ticket = atomicAdd(&q.ctrl[0], 1u);
+    volatile unsigned long long* slot = q.slots + (ticket & q.cap_mask);
+    const long long t_begin = clock64();
+    unsigned long long v = *slot;
+    while ((unsigned)(v >> 32) != ticket) {
+        if (ctrl[2] == 0u || ctrl[3] != 0u) return -1;
+        __nanosleep(128);
+        if (clock64() - t_begin > (8ll << 30)) {   // ~4 s without work: report instead of hanging the device
+            atomicExch(&q.ctrl[3], 1u);
+            return -1;
+        }
+        v = *slot;
+    }
+    __threadfence();
+    return (int)(unsigned)(v & 0xFFFFFFFFull);
+}
+// one thread, on leaving the kernel: the last CTA out sets head = tail for the next launch
+__device__ void flow_leave(const FlowQueue& q) {
+    __threadfence();
+    if (atomicAdd(&q.ctrl[4], 1u) == gridDim.x - 1) {
+        q.ctrl[4] = 0u;
+        q.ctrl[0] = *reinterpret_cast<volatile unsigned*>(&q.ctrl[1]);
+        __threadfence();
+    }
+}
+
 __host__ __device__ inline int tab_doubles(int J, int K) { return J * (15 + 3 * K); }
 
 // columns of a group's compact Jacobian: [ p(3) | 3 per group joint | K shape ]
@@ -113,6 +174,8 @@ lm_prep_kernel(DevModel M, DevParts Pt, LmBuf a) {
         tab[12 * J + i] = T.tau[i];
     }
     for (int i = tid; i < 3 * J * K; i += nt) tab[15 * J + i] = T.C[i];
+    __threadfence();
+    __syncthreads();
 
     if (tid == 0) {
         LmState& st = a.state[f];
@@ -141,6 +204,13 @@ lm_prep_kernel(DevModel M, DevParts Pt, LmBuf a) {
         fs.initial_cost = 0;
         fs.final_cost = 0;
         fs.status = a.range_flag[f] ? 4 : 0;
+        if (a.q.slots && !st.done) {   // lm_flow_kernel: the frame's first tasks
+            const int nrb = (base + 255) >> 8;
+            a.q.rows_left[f] = nrb;
+            __threadfence();
+            atomicAdd(&a.q.ctrl[2], 1u);
+            flow_push(a.q, kTaskRows, f, nrb);
+        }
     }
 }
 
@@ -155,24 +225,21 @@ lm_prep_kernel(DevModel M, DevParts Pt, LmBuf a) {
 // starting on a multiple of four (gap slots hold kNoVertex in mlist and are never read by the Gram kernels).
 __host__ __device__ inline int rec_floats(int nj, int K) { return 3 * nj + 3 * K + 7; }
 
-__global__ void __launch_bounds__(256, 3)
-lm_rows_kernel(DevModel M, DevParts Pt, LmBuf a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int f = blockIdx.y, tid = threadIdx.x;
-    const LmState& st = a.state[f];
-    const int i = blockIdx.x * 256 + tid;
-    if (st.done || blockIdx.x * 256 >= st.nslots) return;
+__device__ void rows_body(const DevModel& M, const DevParts& Pt, const LmBuf& a, int f, int blk, int nslots,
+                          unsigned char* smem_raw) {
+    const int tid = threadIdx.x;
+    const int i = blk * 256 + tid;
     const int J = M.J, K = M.K;
     double* tab = reinterpret_cast<double*>(smem_raw);
     double* w = tab + a.tabD;
     double* scr = w + ((K + 1) & ~1);
     int* gstart = reinterpret_cast<int*>(scr + 32);
     const double* gtab = a.tab + (size_t)f * a.tabD;
-    for (int q = tid; q < a.tabD; q += 256) tab[q] = gtab[q];
-    for (int q = tid; q < K; q += 256) w[q] = a.xt[(size_t)f * M.nx + 3 + 4 * J + q];
+    for (int q = tid; q < a.tabD; q += 256) tab[q] = ldg2(gtab + q);
+    for (int q = tid; q < K; q += 256) w[q] = ldg2(a.xt + (size_t)f * M.nx + 3 + 4 * J + q);
     for (int q = tid; q <= Pt.numGroups; q += 256) gstart[q] = a.gstart[(size_t)f * (kMaxGroups + 1) + q];
     int* s_v = reinterpret_cast<int*>(gstart + kMaxGroups + 2);
-    s_v[tid] = (i < st.nslots) ? (int)a.mlist[(size_t)f * a.rec_rs + i] : (int)kNoVertex;
+    s_v[tid] = (i < nslots) ? (int)a.mlist[(size_t)f * a.rec_rs + i] : (int)kNoVertex;
     __syncthreads();
     const double* G = tab;
     const double* pos = tab + 9 * J;
@@ -274,7 +341,16 @@ lm_rows_kernel(DevModel M, DevParts Pt, LmBuf a) {
         }
     }
     const double cs = block_sum(costv, scr);
-    if (tid == 0) a.cpart[(size_t)f * a.maxrb + blockIdx.x] = cs;
+    if (tid == 0) a.cpart[(size_t)f * a.maxrb + blk] = cs;
+}
+
+__global__ void __launch_bounds__(256, 3)
+lm_rows_kernel(DevModel M, DevParts Pt, LmBuf a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int f = blockIdx.y;
+    const int nslots = a.state[f].nslots;
+    if (a.state[f].done || blockIdx.x * 256 >= nslots) return;
+    rows_body(M, Pt, a, f, blockIdx.x, nslots, smem_raw);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -391,12 +467,8 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 __device__ __forceinline__ uint32_t smem_u32_lm(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(kGramThreads, 2)
-lm_gram_kernel(DevModel M, DevParts Pt, LmBuf a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int c = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
-    const LmState& st = a.state[f];
-    if (st.done || c >= st.nchunks) return;
+__device__ void gram_body(const DevModel& M, const DevParts& Pt, const LmBuf& a, int f, int c, unsigned char* smem_raw) {
+    const int tid = threadIdx.x;
     const int K = M.K;
     const int4 ch = a.chunks[(size_t)f * a.maxc + c];
     const int g = ch.x, start = ch.y, count = ch.z;
@@ -473,6 +545,14 @@ lm_gram_kernel(DevModel M, DevParts Pt, LmBuf a) {
     emit_partial(Gs, n, nj, K, a.part + ((size_t)f * a.maxc + c) * a.pstride, tid, kGramThreads);
 }
 
+__global__ void __launch_bounds__(kGramThreads, 2)
+lm_gram_kernel(DevModel M, DevParts Pt, LmBuf a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int c = blockIdx.x, f = blockIdx.y;
+    if (a.state[f].done || c >= a.state[f].nchunks) return;
+    gram_body(M, Pt, a, f, c, smem_raw);
+}
+
 // ---------------------------------------------------------------------------------------------
 // lm_gram_tc_kernel: the same Gram matrix on the 5th-generation tensor cores (AVB_JTJ_BF16_TENSOR)
 // ---------------------------------------------------------------------------------------------
@@ -487,7 +567,7 @@ constexpr int kTcM = 128;              // UMMA M (record fields padded)
 
 __global__ void __launch_bounds__(kTcThreads, 2)
 lm_gram_tc_kernel(DevModel M, DevParts Pt, LmBuf a) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
     const int c = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -597,13 +677,14 @@ lm_gram_tc_kernel(DevModel M, DevParts Pt, LmBuf a) {
 // ---------------------------------------------------------------------------------------------
 // lm_solve_kernel
 // ---------------------------------------------------------------------------------------------
+constexpr int kNBsq = 64;   // 8 x 8 diagonal block of the Cholesky panels
 struct SolveSmem {
-    double *xs, *xt, *tb, *Hs, *gs, *glo, *gcur, *delta, *aa, *ycomp, *scr;
+    double *xs, *xt, *tb, *Hs, *gs, *glo, *gcur, *delta, *dd, *wscr, *aa, *ycomp, *scr;
     int* iscr;
 };
 __host__ __device__ inline size_t solve_smem_bytes(int J, int K, int C) {
     const int P = 3 + 3 * J + K, nx = 3 + 4 * J + K, D = 3 * (J - 1);
-    size_t d = 2 * ((nx + 1) & ~1) + tables_doubles(J, K, true) + (size_t)P * P + 4 * ((P + 1) & ~1) + ((D + 1) & ~1) +
+    size_t d = 2 * ((nx + 1) & ~1) + tables_doubles(J, K, true) + (size_t)(P + 2) * P + 5 * ((P + 1) & ~1) + 8 * kNBsq + ((D + 1) & ~1) +
                (size_t)(C > 0 ? C : 1) * ((D + 1) & ~1) + 64;
     return d * 8 + 64 * 4 + 128;
 }
@@ -614,11 +695,13 @@ __device__ inline SolveSmem carve_solve(unsigned char* raw, const DevModel& M) {
     S.xs = d; d += (nx + 1) & ~1;
     S.xt = d; d += (nx + 1) & ~1;
     S.tb = d; d += tables_doubles(M.J, M.K, true);
-    S.Hs = d; d += (size_t)P * P;
+    S.Hs = d; d += (size_t)(P + 2) * P;   // + the augmented right-hand-side row (and one row of padding)
     S.gs = d; d += (P + 1) & ~1;
     S.glo = d; d += (P + 1) & ~1;
     S.gcur = d; d += (P + 1) & ~1;
     S.delta = d; d += (P + 1) & ~1;
+    S.dd = d; d += (P + 1) & ~1;
+    S.wscr = d; d += 8 * kNBsq;
     S.aa = d; d += (D + 1) & ~1;
     S.ycomp = d; d += (size_t)C * ((D + 1) & ~1);
     S.scr = d; d += 64;
@@ -626,100 +709,173 @@ __device__ inline SolveSmem carve_solve(unsigned char* raw, const DevModel& M) {
     return S;
 }
 
-// CTA-wide blocked right-looking Cholesky W = L L^T in place (lower triangle), panels of 4 columns: warp 0 factors
-// the panel, then all threads apply the rank-4 update to the trailing matrix (2 barriers per panel).  dinv receives
-// 1 / L_jj.  Returns false when a pivot is not positive.
-__device__ bool block_cholesky(double* W, int P, int* flag, double* dinv) {
-    constexpr int NB = 4;
-    const int tid = threadIdx.x, lane = tid & 31, ty = tid >> 4, tx = tid & 15;
-    if (tid == 0) *flag = 1;
-    __syncthreads();
-    for (int j0 = 0; j0 < P; j0 += NB) {
-        const int nb = min(NB, P - j0);
-        if (tid < 32) {
-            for (int c = 0; c < nb; ++c) {
-                const int j = j0 + c;
-                const double d = W[(size_t)j * P + j];
-                if (!(d > 0.0) || !isfinite(d)) {   // uniform inside the warp
-                    if (lane == 0) *flag = 0;
-                    break;
-                }
-                const double sd = sqrt(d), inv = 1.0 / sd;
-                __syncwarp();
-                if (lane == 0) {
-                    W[(size_t)j * P + j] = sd;
-                    dinv[j] = inv;
-                }
-                for (int i = j + 1 + lane; i < P; i += 32) W[(size_t)i * P + j] *= inv;
-                __syncwarp();
-                for (int c2 = c + 1; c2 < nb; ++c2) {
-                    const int k = j0 + c2;
-                    const double lkj = W[(size_t)k * P + j];
-                    for (int i = k + lane; i < P; i += 32) W[(size_t)i * P + k] -= W[(size_t)i * P + j] * lkj;
-                }
-                __syncwarp();
+// CTA-wide blocked right-looking Cholesky of the leading P x P lower triangle of W (row-major, leading dimension P),
+// carried through R >= P rows: rows P..R-1 enter as right-hand sides b^T and leave as (L^-1 b)^T, i.e. the forward
+// substitution comes for free.  Panels of 8 columns: every warp factors the 8x8 diagonal block redundantly in
+// registers (one row per lane, shuffles), solves its share of the rows below against it, and all threads apply the
+// rank-8 update to the trailing matrix as 4x4 register tiles: two CTA barriers per panel.  dinv receives 1 / L_jj.
+// Returns false (uniformly) when a pivot is not positive.
+constexpr int kNB = 8;
+__device__ bool aug_cholesky(double* W, int P, int R, double* dinv, double* wscr) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nthr = blockDim.x;
+    double* Lw = wscr + wid * (kNB * kNB);   // this warp's copy of L11 (diagonal: 1 / L_cc)
+    const int r = lane & 7;
+    for (int j0 = 0; j0 < P; j0 += kNB) {
+        const int nb = min(kNB, P - j0);
+        // ---- A: diagonal block (rows beyond nb are identity rows) ----
+        double a[kNB];
+#pragma unroll
+        for (int c = 0; c < kNB; ++c)
+            a[c] = (r < nb && c <= r) ? W[(size_t)(j0 + r) * P + j0 + c] : ((c == r) ? 1.0 : 0.0);
+        bool ok = true;
+        double myinv = 1.0;
+#pragma unroll
+        for (int k = 0; k < kNB; ++k) {
+            const double d = __shfl_sync(0xffffffffu, a[k], k);
+            if (!(d > 0.0) || !isfinite(d)) ok = false;
+            const double inv = rsqrt(d);
+            const double lk = (r == k) ? d * inv : a[k] * inv;
+            a[k] = lk;
+            if (r == k) myinv = inv;
+#pragma unroll
+            for (int c = k + 1; c < kNB; ++c) {
+                const double lc = __shfl_sync(0xffffffffu, lk, c);
+                a[c] -= lk * lc;
             }
         }
-        __syncthreads();
-        if (*flag == 0) break;
+        if (!ok) return false;   // every warp factors the same block: uniform over the CTA
+        if (lane < kNB) {
+#pragma unroll
+            for (int c = 0; c < kNB; ++c) Lw[lane * kNB + c] = (c < lane) ? a[c] : ((c == lane) ? myinv : 0.0);
+            if (wid == 0 && lane < nb) dinv[j0 + lane] = myinv;
+        }
+        __syncwarp();
+        // ---- B: rows below the block, x L11^T = W[i][j0 .. j0+nb) ----
         const int t0 = j0 + nb;
-        for (int i = t0 + ty; i < P; i += 16) {
-            double li[NB];
+        for (int i = t0 + tid; i < R; i += nthr) {
+            double* wi = W + (size_t)i * P + j0;
+            double x[kNB];
 #pragma unroll
-            for (int c = 0; c < NB; ++c) li[c] = (c < nb) ? W[(size_t)i * P + j0 + c] : 0.0;
-            for (int k = t0 + tx; k <= i; k += 16) {
-                double sacc = 0.0;
+            for (int c = 0; c < kNB; ++c) {
+                if (c < nb) {
+                    double sacc = wi[c];
 #pragma unroll
-                for (int c = 0; c < NB; ++c)
-                    if (c < nb) sacc += li[c] * W[(size_t)k * P + j0 + c];
-                W[(size_t)i * P + k] -= sacc;
+                    for (int k = 0; k < c; ++k) sacc -= x[k] * Lw[c * kNB + k];
+                    x[c] = sacc * Lw[c * kNB + c];
+                    wi[c] = x[c];
+                } else {
+                    x[c] = 0.0;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- C: trailing update W[i][k] -= sum_c L[i][c] L[k][c] on 4x4 tiles of the lower triangle ----
+        if (wid == 0 && lane < nb) {   // L11 itself (nobody reads the diagonal block any more)
+#pragma unroll
+            for (int c = 0; c < kNB; ++c)
+                if (c <= lane) W[(size_t)(j0 + lane) * P + j0 + c] = a[c];
+        }
+        const int mrow = R - t0, mcol = P - t0;
+        if (mcol > 0) {
+            const int Tc = (mcol + 3) >> 2, Tr = (mrow + 3) >> 2;
+            const int ntri = Tc * (Tc + 1) / 2, ntile = ntri + (Tr - Tc) * Tc;
+            for (int t = tid; t < ntile; t += nthr) {
+                int ti, tk;
+                if (t < ntri) {
+                    ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+                    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+                    while (ti * (ti + 1) / 2 > t) --ti;
+                    tk = t - ti * (ti + 1) / 2;
+                } else {
+                    ti = Tc + (t - ntri) / Tc;
+                    tk = (t - ntri) % Tc;
+                }
+                const int i0 = t0 + 4 * ti, k0 = t0 + 4 * tk;
+                const double* li[4];
+                const double* lk[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    li[q] = W + (size_t)min(i0 + q, R - 1) * P + j0;
+                    lk[q] = W + (size_t)min(k0 + q, P - 1) * P + j0;
+                }
+                double acc[4][4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) acc[q][u] = 0.0;
+#pragma unroll
+                for (int c = 0; c < kNB; ++c) {
+                    if (c < nb) {
+                        double av[4], bv[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            av[q] = li[q][c];
+                            bv[q] = lk[q][c];
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) acc[q][u] = fma(av[q], bv[u], acc[q][u]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + q, k = k0 + u;
+                        if (i < R && k < P && k <= i) W[(size_t)i * P + k] -= acc[q][u];
+                    }
             }
         }
         __syncthreads();
     }
-    __syncthreads();
-    return *flag != 0;
+    return true;
 }
 
-// solve L L^T x = b in place with one warp (column-oriented forward, row-oriented backward substitution)
-__device__ void warp_chol_solve(const double* L, const double* dinv, int P, double* b) {
+// x = L^-T y with one warp: the solution lives in registers (entry e in lane e % 32), one shuffle per step
+__device__ void warp_back_solve(const double* L, const double* dinv, int P, const double* y, double* x) {
     const int lane = threadIdx.x & 31;
-    for (int i = 0; i < P; ++i) {
-        const double yi = b[i] * dinv[i];
-        __syncwarp();
-        if (lane == 0) b[i] = yi;
-        for (int e = i + 1 + lane; e < P; e += 32) b[e] -= L[(size_t)e * P + i] * yi;
-        __syncwarp();
+    double b[4];
+#pragma unroll
+    for (int sg = 0; sg < 4; ++sg) b[sg] = (lane + 32 * sg < P) ? y[lane + 32 * sg] : 0.0;
+#pragma unroll
+    for (int sg = 3; sg >= 0; --sg) {
+        for (int ii = 31; ii >= 0; --ii) {
+            const int i = 32 * sg + ii;
+            if (i >= P) continue;
+            const double xi = __shfl_sync(0xffffffffu, b[sg], ii) * dinv[i];
+            if (lane == ii) b[sg] = xi;
+            const double* Li = L + (size_t)i * P;
+#pragma unroll
+            for (int s2 = 0; s2 <= sg; ++s2) {
+                const int e = lane + 32 * s2;
+                if (e < i) b[s2] -= Li[e] * xi;
+            }
+        }
     }
-    for (int i = P - 1; i >= 0; --i) {
-        const double xi = b[i] * dinv[i];
-        __syncwarp();
-        if (lane == 0) b[i] = xi;
-        for (int e = lane; e < i; e += 32) b[e] -= L[(size_t)i * P + e] * xi;
-        __syncwarp();
-    }
+#pragma unroll
+    for (int sg = 0; sg < 4; ++sg)
+        if (lane + 32 * sg < P) x[lane + 32 * sg] = b[sg];
 }
 
-__global__ void __launch_bounds__(kSolveThreads, 2)
-lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int f = blockIdx.x, tid = threadIdx.x;
+// returns true when the frame has finished (uniform over the CTA)
+__device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a, int f, unsigned char* smem_raw) {
+    const int tid = threadIdx.x;
     LmState& gst = a.state[f];
-    if (gst.done) return;
     const int P = M.P, nx = M.nx, J = M.J, K = M.K;
     SolveSmem S = carve_solve(smem_raw, M);
     double* Hcur = a.Hcur + (size_t)f * P * P;
     double* gcur_g = a.gcur + (size_t)f * P;
-    const LmState st = gst;  // snapshot (only thread 0 writes it back at the end)
+    const LmState st = load_state(&gst);  // snapshot (only thread 0 writes it back at the end)
 
     for (int i = tid; i < nx; i += kSolveThreads) {
-        S.xs[i] = a.x[(size_t)f * nx + i];
-        S.xt[i] = a.xt[(size_t)f * nx + i];
+        S.xs[i] = ldg2(a.x + (size_t)f * nx + i);
+        S.xt[i] = ldg2(a.xt + (size_t)f * nx + i);
     }
     for (int i = tid; i < P * P; i += kSolveThreads) S.Hs[i] = 0.0;
     for (int i = tid; i < P; i += kSolveThreads) {
         S.gs[i] = 0.0;
-        S.gcur[i] = gcur_g[i];
+        S.gcur[i] = ldg2(gcur_g + i);
     }
     __syncthreads();
     // ---- reduce the chunk partials in chunk order ----
@@ -745,7 +901,7 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
                 const int idx = i0 + u * kSolveThreads;
                 double v = 0.0;   // chunk order is fixed => deterministic
                 if (idx < nH + Lg)
-                    for (int cc = 0; cc < nrun; ++cc) v += __ldg(part + (size_t)cc * a.pstride + idx);
+                    for (int cc = 0; cc < nrun; ++cc) v += ldg2(part + (size_t)cc * a.pstride + idx);
                 val[u] = v;
             }
 #pragma unroll
@@ -763,7 +919,7 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
         __syncthreads();
         c = c1;
     }
-    for (int b = 0; b * 256 < st.nslots; ++b) csum += a.cpart[(size_t)f * a.maxrb + b];
+    for (int b = 0; b * 256 < st.nslots; ++b) csum += ldg2(a.cpart + (size_t)f * a.maxrb + b);
     double cost_t = 0.5 * (csum + st.Qsum);
     for (int i = tid; i < P * P; i += kSolveThreads) {
         const int r = i / P, c = i - r * P;
@@ -771,10 +927,12 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
     }
     __syncthreads();
     // ---- eta -> delta coordinates: H = T^T Ht T, g = T^T gt, T_j = G_parent(j) at the trial point ----
-    const double* Gt = a.tab + (size_t)f * a.tabD;
+    double* Gs9 = S.tb;   // global joint rotations of the trial point (the table scratch is free until the retraction)
+    for (int i = tid; i < 9 * J; i += kSolveThreads) Gs9[i] = ldg2(a.tab + (size_t)f * a.tabD + i);
+    __syncthreads();
     for (int i = tid; i < P * (J - 1); i += kSolveThreads) {
         const int j = 1 + i / P, c = i % P;
-        const double* Gp = Gt + 9 * M.parent[j];
+        const double* Gp = Gs9 + 9 * M.parent[j];
         double* h = S.Hs + (size_t)(3 + 3 * j) * P + c;
         const double h0 = h[0], h1 = h[P], h2 = h[2 * P];
         h[0] = Gp[0] * h0 + Gp[3] * h1 + Gp[6] * h2;
@@ -784,7 +942,7 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
     __syncthreads();
     for (int i = tid; i < P * (J - 1); i += kSolveThreads) {
         const int j = 1 + i / P, r = i % P;
-        const double* Gp = Gt + 9 * M.parent[j];
+        const double* Gp = Gs9 + 9 * M.parent[j];
         double* h = S.Hs + (size_t)r * P + 3 + 3 * j;
         const double h0 = h[0], h1 = h[1], h2 = h[2];
         h[0] = h0 * Gp[0] + h1 * Gp[3] + h2 * Gp[6];
@@ -792,7 +950,7 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
         h[2] = h0 * Gp[2] + h1 * Gp[5] + h2 * Gp[8];
     }
     for (int j = 1 + tid; j < J; j += kSolveThreads) {
-        const double* Gp = Gt + 9 * M.parent[j];
+        const double* Gp = Gs9 + 9 * M.parent[j];
         double* gg = S.gs + 3 + 3 * j;
         const double g0 = gg[0], g1 = gg[1], g2 = gg[2];
         gg[0] = Gp[0] * g0 + Gp[3] * g1 + Gp[6] * g2;
@@ -820,12 +978,21 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
         }
         __syncthreads();
         for (int i = tid; i < C * D; i += kSolveThreads) {  // y_c = Sigma_c^-1 (x - mu_c)
+            // the precision matrices are symmetric (symmetrised at load): walk column r so that consecutive
+            // threads read consecutive addresses
             const int cc = i / D, r = i % D;
-            const double* Pm = M.gmm_prec + ((size_t)cc * D + r) * D;
+            const double* Pm = M.gmm_prec + (size_t)cc * D * D + r;
             const double* mu = M.gmm_mean + (size_t)cc * D;
-            double s = 0;
-            for (int k = 0; k < D; ++k) s += Pm[k] * (S.aa[k] - mu[k]);
-            S.ycomp[cc * Dp + r] = s;
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            int k = 0;
+            for (; k + 4 <= D; k += 4) {
+                s0 += Pm[(size_t)k * D] * (S.aa[k] - mu[k]);
+                s1 += Pm[(size_t)(k + 1) * D] * (S.aa[k + 1] - mu[k + 1]);
+                s2 += Pm[(size_t)(k + 2) * D] * (S.aa[k + 2] - mu[k + 2]);
+                s3 += Pm[(size_t)(k + 3) * D] * (S.aa[k + 3] - mu[k + 3]);
+            }
+            for (; k < D; ++k) s0 += Pm[(size_t)k * D] * (S.aa[k] - mu[k]);
+            S.ycomp[cc * Dp + r] = (s0 + s1) + (s2 + s3);
         }
         __syncthreads();
         if (tid < 32) {  // p_c = 1/2 (x-mu)^T Sigma^-1 (x-mu) - consts_log[c]; first minimum wins (strict <)
@@ -875,7 +1042,7 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
         }
         for (int i = tid; i < P; i += kSolveThreads) a.dump_grad[(size_t)f * P + i] = S.gs[i];
         for (int i = tid; i < P * P; i += kSolveThreads) a.dump_H[(size_t)f * P * P + i] = S.Hs[i];
-        return;
+        return true;
     }
 
     // ---- Levenberg-Marquardt step control (Ceres-1.14-style trust region; DESIGN.md "solver") ----
@@ -938,31 +1105,27 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
     while (!done && iters < a.max_iters && !have_step) {
         ++iters;
         if (!have_cur_in_smem) {
-            for (int i = tid; i < P * P; i += kSolveThreads) S.Hs[i] = Hcur[i];
+            for (int i = tid; i < P * P; i += kSolveThreads) S.Hs[i] = ldg2(Hcur + i);
             __syncthreads();
         }
         have_cur_in_smem = false;  // the factorisation below overwrites S.Hs
-        // W = Hcur + D,  D_jj = clamp(s^2 h_jj, 1e-6, 1e32) / (s^2 radius),  s = 1 / (1 + sqrt(h_jj))
+        // W = Hcur + D,  D_jj = clamp(s^2 h_jj, 1e-6, 1e32) / (s^2 radius),  s = 1 / (1 + sqrt(h_jj)); row P = -g^T
         for (int j = tid; j < P; j += kSolveThreads) {
             const double h = S.Hs[(size_t)j * P + j];
-            const double s = 1.0 / (1.0 + sqrt(h));
-            const double d = fmin(fmax(s * s * h, 1e-6), 1e32);
-            S.Hs[(size_t)j * P + j] = h + d / (s * s * radius);
+            const double sj = 1.0 / (1.0 + sqrt(h));
+            const double dj = fmin(fmax(sj * sj * h, 1e-6), 1e32) / (sj * sj * radius);
+            S.dd[j] = dj;
+            S.Hs[(size_t)j * P + j] = h + dj;
+            S.Hs[(size_t)P * P + j] = -S.gcur[j];
         }
         __syncthreads();
-        bool ok = block_cholesky(S.Hs, P, &S.iscr[50], S.glo);
+        bool ok = aug_cholesky(S.Hs, P, P + 1, S.glo, S.wscr);
         if (ok) {
-            for (int i = tid; i < P; i += kSolveThreads) S.delta[i] = -S.gcur[i];
+            if (tid < 32) warp_back_solve(S.Hs, S.glo, P, S.Hs + (size_t)P * P, S.delta);
             __syncthreads();
-            if (tid < 32) warp_chol_solve(S.Hs, S.glo, P, S.delta);
-            __syncthreads();
-            // model_cost_change = -delta^T (g + 1/2 H delta), H without damping
+            // model_cost_change = -delta^T (g + 1/2 H delta) with (H + D) delta = -g  =>  1/2 delta^T (D delta - g)
             double part = 0;
-            for (int r = tid; r < P; r += kSolveThreads) {
-                double s = 0;
-                for (int c = 0; c < P; ++c) s += Hcur[(size_t)r * P + c] * S.delta[c];
-                part -= S.delta[r] * (S.gcur[r] + 0.5 * s);
-            }
+            for (int r = tid; r < P; r += kSolveThreads) part += 0.5 * S.delta[r] * (S.dd[r] * S.delta[r] - S.gcur[r]);
             model_change = block_sum(part, S.scr);
             ok = model_change > 0.0 && isfinite(model_change);
         }
@@ -1028,6 +1191,94 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
         fs.final_cost = cost;
         if (!isfinite(cost)) fs.status = 4;
     }
+    return done;
+}
+
+__global__ void __launch_bounds__(kSolveThreads, 2)
+lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (a.state[blockIdx.x].done) return;
+    solve_body(M, Pt, a, blockIdx.x, smem_raw);
+}
+
+// ---------------------------------------------------------------------------------------------
+// lm_flow_kernel: the whole inner solve (every evaluation of every frame) as one persistent data-flow kernel
+// ---------------------------------------------------------------------------------------------
+// CTAs take tasks from a global queue: rows(f, block) -> gram(f, chunk) -> solve(f) -> rows(f, ...) of the next
+// evaluation.  A task is pushed only when its inputs are complete (per-frame countdowns), so no CTA ever waits on
+// another one; the CTA that finishes a frame's last chunk runs the frame's solve itself.  The latency-bound solves
+// of some frames overlap the throughput-bound record and Gram tasks of others, and the 3 x (1 + maxItersPerICP)
+// kernel boundaries of the staged schedule disappear.  Results are identical to the staged kernels: the same
+// bodies run on the same data in the same per-frame order.
+__global__ void __launch_bounds__(256, 2)
+lm_flow_kernel(DevModel M, DevParts Pt, LmBuf a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int s_task, s_last;
+    const int tid = threadIdx.x;
+    unsigned long long t_prev = 0;
+    if (a.q.prof && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_prev));
+    auto lap = [&](int cls) {   // thread 0: CTA time per task class (avb_set_profiling)
+        if (a.q.prof) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            atomicAdd(a.q.prof + cls, t - t_prev);
+            t_prev = t;
+        }
+    };
+    for (;;) {
+        if (tid == 0) {
+            s_task = flow_pop(a.q);
+            lap(3);
+            if (s_task == -1) flow_leave(a.q);
+        }
+        __syncthreads();
+        const int task = s_task;
+        if (task == -1) return;
+        const int type = (int)((unsigned)task >> 30), f = (task >> 12) & 0x3FFFF, idx = task & 0xFFF;
+        if (type == kTaskRows) {
+            const int nslots = ldg2(&a.state[f].nslots);
+            rows_body(M, Pt, a, f, idx, nslots, smem_raw);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                if (atomicSub(&a.q.rows_left[f], 1) == 1) {
+                    __threadfence();
+                    const int nch = ldg2(&a.state[f].nchunks);
+                    atomicExch(&a.q.gram_left[f], nch);
+                    __threadfence();
+                    flow_push(a.q, kTaskGram, f, nch);
+                }
+                lap(0);
+            }
+        } else {
+            gram_body(M, Pt, a, f, idx, smem_raw);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                s_last = atomicSub(&a.q.gram_left[f], 1) == 1;
+                lap(1);
+            }
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                const bool done = solve_body(M, Pt, a, f, smem_raw);
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) {
+                    if (done) {
+                        atomicSub(&a.q.ctrl[2], 1u);
+                    } else {
+                        const int nrb = (ldg2(&a.state[f].nslots) + 255) >> 8;
+                        atomicExch(&a.q.rows_left[f], nrb);
+                        __threadfence();
+                        flow_push(a.q, kTaskRows, f, nrb);
+                    }
+                    lap(2);
+                }
+            }
+        }
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1074,6 +1325,20 @@ cudaError_t launch_lm_eval_part(const DevModel& M, const DevParts& Pt, const LmB
     cudaError_t e = cudaFuncSetAttribute(lm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
     if (e != cudaSuccess) return e;
     lm_solve_kernel<<<batch, kSolveThreads, ssm, st>>>(M, Pt, a);
+    return cudaGetLastError();
+}
+
+size_t lm_flow_smem(const DevModel& M, int max_nj, int chunk_verts) {
+    size_t b = lm_gram_smem(M, max_nj, chunk_verts, false);
+    b = b > lm_rows_smem(M) ? b : lm_rows_smem(M);
+    const size_t ssm = solve_smem_bytes(M.J, M.K, M.gmmC);
+    return b > ssm ? b : ssm;
+}
+cudaError_t launch_lm_flow(const DevModel& M, const DevParts& Pt, const LmBuf& a, int max_nj, int ctas, cudaStream_t st) {
+    const size_t sm = lm_flow_smem(M, max_nj, a.chunk_verts);
+    cudaError_t e = cudaFuncSetAttribute(lm_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+    lm_flow_kernel<<<ctas, 256, sm, st>>>(M, Pt, a);
     return cudaGetLastError();
 }
 

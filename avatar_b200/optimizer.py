@@ -130,18 +130,32 @@ class Fitter:
         check(lib.avb_last_device_ms(self.handle, C.byref(tot), per))
         return tot.value, list(per)
 
-    KERNEL_CLASSES = ("pose_visibility_kernel", "nn_kernel", "lm_prep_kernel", "lm_rows_kernel", "lm_syrk_kernel",
-                      "lm_solve_kernel", "pose_visibility_kernel(final)")
+    KERNEL_CLASSES = ("pose_visibility_kernel", "nn_kernel", "lm_prep_kernel", "lm_rows_kernel", "lm_gram_kernel",
+                      "lm_solve_kernel", "pose_visibility_kernel(final)", "lm_flow_kernel")
 
     def set_profiling(self, on):
         check(lib.avb_set_profiling(self.handle, int(bool(on))))
 
     def kernel_ms(self):
         """{kernel class: (total ms, launches)} of the last profiled fit_resident"""
-        ms = (C.c_float * 7)()
-        n = (C.c_int32 * 7)()
+        ms = (C.c_float * 8)()
+        n = (C.c_int32 * 8)()
         check(lib.avb_last_kernel_ms(self.handle, ms, n))
-        return {k: (ms[i], n[i]) for i, k in enumerate(self.KERNEL_CLASSES)}
+        return {k: (ms[i], n[i]) for i, k in enumerate(self.KERNEL_CLASSES) if n[i] > 0}
+
+    def groups(self):
+        """[(joints, model vertices)] of the static Jacobian column groups"""
+        n = C.c_int32()
+        nj = (C.c_int32 * 16)()
+        nv = (C.c_int32 * 16)()
+        check(lib.avb_fitter_groups(self.handle, C.byref(n), nj, nv))
+        return [(nj[g], nv[g]) for g in range(n.value)]
+
+    def flow_task_ms(self):
+        """CTA milliseconds the last profiled lm_flow_kernel spent in (record tasks, Gram tasks, solves, waiting)"""
+        ms = (C.c_float * 4)()
+        check(lib.avb_last_flow_task_ms(self.handle, ms))
+        return dict(zip(("rows", "gram", "solve", "wait"), list(ms)))
 
     def timer_start(self):
         check(lib.avb_timer_start(self.handle))

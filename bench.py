@@ -311,26 +311,39 @@ def main():
     npts = np.diff(off)
     # ---- roofline of the dominant kernel: one extra profiled step per lane (CUDA-event pair around every launch
     #      on the launching stream), lanes profiled one after the other ----
-    kms, klaunch = {}, {}
+    kms, klaunch, flow_ms = {}, {}, {}
     for ln in lanes:
         ln["ft"].set_profiling(True)
         ln["ft"].fit_resident(ln["x0"], opt)
         for k, (ms, n) in ln["ft"].kernel_ms().items():
             kms[k] = kms.get(k, 0.0) + ms
             klaunch[k] = klaunch.get(k, 0) + n
+        if "lm_flow_kernel" in kms:
+            for k, ms in ln["ft"].flow_task_ms().items():
+                flow_ms[k] = flow_ms.get(k, 0.0) + ms
         ln["ft"].set_profiling(False)
     dom = max(kms, key=kms.get)
     V, K = model.numPoints(), model.numShapeKeys()
     evals = float(np.mean(iters)) + 1.0
     nm, nvis = float(np.sum(nmatch)), 0.5 * V * F
-    rec_b = 4.0 * (3 * 10 + 3 * K + 7)                  # mean fp32 Jacobian record (about 10 group joints)
+    groups = lanes[0]["ft"].groups()
+    gv = float(sum(v for _, v in groups))
+    nj_mean = sum(j * v for j, v in groups) / gv        # joints per record, weighted by the groups' vertex counts
+    rec_b = 4.0 * (3 * nj_mean + 3 * K + 7)             # mean fp32 Jacobian record
+    Lg = 3 + 3 * nj_mean + K
+    part_b = 8.0 * (Lg * (Lg + 1) / 2 + Lg)             # chunk partial: upper triangle of J^T J + J^T r
+    chunks = nm / 256.0 + 0.5 * len(groups) * F         # chunks per evaluation (256 slots, one ragged chunk per group)
+    rows_b = evals * nm * (4 + 24 + 24 + 12 * K + 37 + 2 + rec_b)
+    gram_b = evals * (nm * rec_b + chunks * part_b)
+    solve_b = evals * (chunks * part_b + F * 3 * 8.0 * 85 * 85)
     alg_step = {                                         # algorithmic bytes per STEP of each kernel class
         "pose_visibility_kernel": F * (24.0 * V + V + 4 * V) + 24.0 * nvis,
         "nn_kernel": 32.0 * total + 24.0 * nvis,
         "lm_prep_kernel": F * (4.0 * V + 2.0 * V + 8 * 1080),
-        "lm_rows_kernel": evals * nm * (4 + 24 + 24 + 12 * K + 37 + 2 + rec_b),
-        "lm_syrk_kernel": evals * (nm * rec_b + (nm / 256.0 + 8 * F) * 36 * 512.0),
-        "lm_solve_kernel": evals * F * ((nm / F / 256.0 + 8) * 36 * 512.0 + 3 * 8.0 * 85 * 85),
+        "lm_rows_kernel": rows_b,
+        "lm_gram_kernel": gram_b,
+        "lm_solve_kernel": solve_b,
+        "lm_flow_kernel": rows_b + gram_b + solve_b,
         "pose_visibility_kernel(final)": F * 24.0 * V,
     }
     peak, how = load_peaks()
@@ -352,8 +365,12 @@ def main():
                 "avg_launch_ms": avg_launch_ms, "launches_per_step": dom_launches,
                 "kernel_ms_per_step": {k: round(v, 4) for k, v in kms.items()},
                 "kernel_share": {k: round(v / tot_ms, 4) for k, v in kms.items()},
-                "note": "the dominant kernel is fp64-FMA / latency bound (ncu: fp64 pipe ~25% active, DRAM < 2%), "
-                        "not HBM bound: the HBM fraction is reported as required and is not the limiter (DESIGN.md section 5)"}
+                "note": "the dominant kernel is fp64-pipe / latency bound (DMMA Gram tasks, fp64 record generation and "
+                        "85x85 solves; ncu: DRAM < 2% of peak), not HBM bound: the HBM fraction is reported as required "
+                        "and is not the limiter (DESIGN.md section 5)"}
+    if flow_ms:
+        tot_cta = sum(flow_ms.values()) or 1.0
+        roofline["flow_task_share"] = {k: round(v / tot_cta, 4) for k, v in flow_ms.items()}
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"fp64": "f64", "fp32": "f64 (J^T J accumulated in f32)",

@@ -176,10 +176,19 @@ int avb_timer_start(avb_fitter* fitter);
 int avb_timer_stop(avb_fitter* fitter, float* ms);
 /* Per-kernel timing for bench.py's roofline: when enabled, the next avb_fit_resident records a CUDA-event pair
  * around every kernel launch; avb_last_kernel_ms then returns, per kernel class
- * [pose_visibility, nn, lm_prep, lm_rows, lm_syrk, lm_solve, final_pose], the summed device time (ms) and the
- * number of launches.  Costs ~2 events per launch, so leave it off inside throughput-timed regions. */
+ * [pose_visibility, nn, lm_prep, lm_rows, lm_gram, lm_solve, final_pose, lm_flow], the summed device time (ms) and
+ * the number of launches.  Costs ~2 events per launch, so leave it off inside throughput-timed regions.
+ * The inner solve normally runs as ONE persistent kernel (lm_flow_kernel: record, Gram and solve tasks of all frames
+ * from a device work queue), so lm_rows / lm_gram / lm_solve are zero unless the staged kernels are selected
+ * (AVB_JTJ_BF16_TENSOR, or AVB_FLOW=0 in the environment); avb_last_flow_task_ms returns the CTA time (ms, summed
+ * over CTAs) the profiled lm_flow_kernel spent in [record tasks, Gram tasks, solves, waiting for work]. */
 int avb_set_profiling(avb_fitter* fitter, int enabled);
-int avb_last_kernel_ms(avb_fitter* fitter, float* total_ms7, int32_t* launches7);
+int avb_last_kernel_ms(avb_fitter* fitter, float* total_ms8, int32_t* launches8);
+int avb_last_flow_task_ms(avb_fitter* fitter, float* ms4);
+/* The fitter's static Jacobian column groups (vertices whose skinning joints share an ancestor set): number of
+ * groups, joints per group and model vertices per group (arrays of 16).  bench.py derives the algorithmic bytes
+ * of the record / Gram kernels from them. */
+int avb_fitter_groups(avb_fitter* fitter, int32_t* num_groups, int32_t* joints16, int32_t* vertices16);
 /* number of kernel launches enqueued by the last avb_fit_resident / avb_fit_batch */
 int avb_last_launch_count(avb_fitter* fitter);
 
