@@ -75,6 +75,7 @@ SYMBOLS = [
     ("avb_set_profiling", C.c_int, [_P, C.c_int]),
     ("avb_last_kernel_ms", C.c_int, [_P, _P, _P]),
     ("avb_last_flow_task_ms", C.c_int, [_P, _P]),
+    ("avb_last_flow_phase_ms", C.c_int, [_P, _P]),
     ("avb_fitter_groups", C.c_int, [_P, _P, _P, _P]),
     ("avb_last_launch_count", C.c_int, [_P]),
     ("avb_host_alloc", _P, [C.c_uint64]),

@@ -96,7 +96,7 @@ struct avb_fitter {
     int* d_nn = nullptr; int* d_cnt = nullptr; unsigned long long* d_sum = nullptr; double* d_qpart = nullptr;
     int* d_range = nullptr; double* d_Hcur = nullptr; FrameStats* d_stats = nullptr;
     double *d_xt = nullptr, *d_tab = nullptr, *d_part = nullptr, *d_cpart = nullptr, *d_gcur = nullptr;
-    unsigned short* d_mlist = nullptr; int4* d_chunks = nullptr; LmState* d_state = nullptr;
+    unsigned short* d_mlist = nullptr; int4* d_chunks = nullptr; int2* d_gruns = nullptr; LmState* d_state = nullptr;
     float* d_rec = nullptr; int* d_gstart = nullptr; int maxrb = 0, rec_stride = 0, rec_rs = 0;
     int maxc = 0, tabD = 0, max_nj = 0, chunk_verts = 256;
     long long pstride = 0;
@@ -544,6 +544,15 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     TRY(dev_put(ft, &dm.gmm_mean, m->gmm_mean));
     TRY(dev_put(ft, &dm.gmm_prec, m->gmm_prec));
     TRY(dev_put(ft, &dm.gmm_clog, m->gmm_clog));
+    {
+        const size_t PP = (size_t)m->P * m->P;
+        const int D = m->gmmD;
+        std::vector<double> pfull((size_t)std::max(m->gmmC, 1) * PP, 0.0);
+        for (int c = 0; c < m->gmmC; ++c)
+            for (int r = 0; r < D; ++r)
+                for (int q = 0; q < D; ++q) pfull[c * PP + (size_t)(6 + r) * m->P + 6 + q] = m->gmm_prec[((size_t)c * D + r) * D + q];
+        TRY(dev_put(ft, &dm.gmm_pfull, pfull));
+    }
 
     // ---- part tables (AvatarOptimizer.cpp:1223-1243) ----
     const int V = m->V, NP = cfg->num_parts;
@@ -611,6 +620,7 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     TRY(dev_alloc(ft, &ft->d_gcur, B * P));
     TRY(dev_alloc(ft, &ft->d_mlist, B * (size_t)ft->rec_rs));
     TRY(dev_alloc(ft, &ft->d_chunks, B * (size_t)ft->maxc));
+    TRY(dev_alloc(ft, &ft->d_gruns, B * (size_t)kMaxGroups));
     TRY(dev_alloc(ft, &ft->d_state, B));
     {   // work queue: ring of 4x the tasks that can be outstanding at once
         size_t need = 4 * B * (size_t)std::max(ft->maxrb, ft->maxc);
@@ -620,10 +630,10 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
         TRY(dev_alloc(ft, &ft->d_qctrl, 8));
         TRY(dev_alloc(ft, &ft->d_rows_left, B));
         TRY(dev_alloc(ft, &ft->d_gram_left, B));
-        TRY(dev_alloc(ft, &ft->d_qprof, 4));
+        TRY(dev_alloc(ft, &ft->d_qprof, 16));
         CUDA_TRY_FT(cudaMemset(ft->d_qslots, 0xFF, (size_t)ft->qcap * 8));
         CUDA_TRY_FT(cudaMemset(ft->d_qctrl, 0, 32));
-        CUDA_TRY_FT(cudaMemset(ft->d_qprof, 0, 32));
+        CUDA_TRY_FT(cudaMemset(ft->d_qprof, 0, 128));
         if (const char* e = std::getenv("AVB_FLOW")) ft->use_flow = std::atoi(e) != 0;
     }
     ft->max_chunks = (int)std::max<size_t>(NT / 512 + 2 * B + 8, (size_t)8 * ft->num_sms + 2 * B + 8);
@@ -803,6 +813,7 @@ LmBuf lm_buf(avb_fitter* ft, double* dx, const avb_options* o) {
     a.tab = ft->d_tab;
     a.mlist = ft->d_mlist;
     a.chunks = ft->d_chunks;
+    a.gruns = ft->d_gruns;
     a.part = ft->d_part;
     a.cpart = ft->d_cpart;
     a.rec = ft->d_rec;
@@ -834,9 +845,9 @@ LmBuf lm_buf(avb_fitter* ft, double* dx, const avb_options* o) {
         a.q.ctrl = ft->d_qctrl;
         a.q.rows_left = ft->d_rows_left;
         a.q.gram_left = ft->d_gram_left;
-        a.q.prof = ft->profile ? ft->d_qprof : nullptr;
         a.q.cap_mask = ft->qcap - 1;
     }
+    a.q.prof = ft->profile ? ft->d_qprof : nullptr;   // per-phase CTA time (also with the staged kernels)
     return a;
 }
 
@@ -848,9 +859,10 @@ int enqueue_solve(avb_fitter* ft, const LmBuf& la, const avb_options* o, int rou
         CUDA_TRY(launch_lm_prep(ft->dm, ft->dp, la, ft->batch, st));
     }
     ++ft->launches;
+    if (la.q.prof) CUDA_TRY(cudaMemsetAsync(ft->d_qprof, 0, 128, st));
     if (la.q.slots) {
-        if (la.q.prof) CUDA_TRY(cudaMemsetAsync(ft->d_qprof, 0, 32, st));
-        const int ctas = std::min(2 * ft->num_sms, std::max(1, ft->batch * 16));
+        int ctas = std::min(2 * ft->num_sms, std::max(1, ft->batch * 16));
+        if (const char* e = std::getenv("AVB_FLOW_CTAS")) ctas = std::max(1, std::min(ctas, std::atoi(e)));
         ProfScope ps(ft, KC_FLOW);
         CUDA_TRY(launch_lm_flow(ft->dm, ft->dp, la, ft->max_nj, ctas, st));
         ++ft->launches;
@@ -971,6 +983,16 @@ int avb_last_flow_task_ms(avb_fitter* ft, float* ms4) {
     unsigned long long ns[4];
     CUDA_TRY(cudaMemcpy(ns, ft->d_qprof, 32, cudaMemcpyDeviceToHost));
     for (int k = 0; k < 4; ++k) ms4[k] = (float)((double)ns[k] * 1e-6);
+    return AVB_OK;
+}
+
+int avb_last_flow_phase_ms(avb_fitter* ft, float* ms12) {
+    if (!ft || !ms12) return fail(AVB_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    CUDA_TRY(cudaStreamSynchronize(ft->stream));
+    unsigned long long ns[16];
+    CUDA_TRY(cudaMemcpy(ns, ft->d_qprof, 128, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 12; ++k) ms12[k] = (float)((double)ns[4 + k] * 1e-6);
     return AVB_OK;
 }
 

@@ -34,6 +34,7 @@ struct DevModel {
     const double* gmm_mean;    // [C][D]
     const double* gmm_prec;    // [C][D][D]   Sigma^-1 = prec_cho prec_cho^T (full symmetric)
     const double* gmm_clog;    // [C]         consts_log
+    const double* gmm_pfull;   // [C][P][P]   Sigma^-1 zero padded to the tangent layout (rows/cols 6..6+D)
 };
 
 // Per-optimizer part tables (AvatarOptimizer.cpp:1213-1244) and the static column-group schedule
@@ -86,6 +87,7 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
     if (lane == 0) scratch[wid] = v;
     __syncthreads();
     double s = 0;
+#pragma unroll 1
     for (int i = 0; i < nw; ++i) s += scratch[i];
     return s;
 }

@@ -50,7 +50,7 @@ struct FlowQueue {  // device work queue of lm_flow_kernel
     unsigned int* ctrl;          // [0] head, [1] tail, [2] frames still running, [3] watchdog flag, [4] CTAs that left
     int* rows_left;              // [batch] record blocks of the current evaluation still running
     int* gram_left;              // [batch] chunks of the current evaluation still running
-    unsigned long long* prof;    // nullable [4]: CTA nanoseconds in rows / gram / solve tasks / waiting
+    unsigned long long* prof;    // nullable [16]: CTA nanoseconds in rows / gram / solve tasks / waiting, then sub-phases
     unsigned int cap_mask;
 };
 
@@ -60,6 +60,7 @@ struct LmBuf {
     double* tab;                 // [batch][tabD] joint tables of the trial point: G | pos | tau | C
     unsigned short* mlist;       // [batch][rec_rs] matched vertices grouped by Jacobian column group (0xFFFF = gap)
     int4* chunks;                // [batch][maxc] (group, start in mlist, count, -)
+    int2* gruns;                 // [batch][kMaxGroups] (first chunk, chunks) of every column group
     double* part;                // [batch][maxc][pstride] chunk partial: upper triangle of J^T J | J^T r, group columns
     double* cpart;               // [batch][maxrb] cost partial per 256 record slots
     float* rec;                  // [batch][rec_stride][rec_rs] fp32 Jacobian records (SoA) of the matched vertices

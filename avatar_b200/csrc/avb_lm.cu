@@ -92,6 +92,22 @@ __device__ void flow_leave(const FlowQueue& q) {
     }
 }
 
+// avb_set_profiling: thread 0 adds the nanoseconds since *t_prev to phase counter `cls` (prof[4..15]: sub-phases)
+__device__ __forceinline__ void phase_lap(const FlowQueue& q, int cls, unsigned long long& t_prev) {
+    if (q.prof && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicAdd(q.prof + cls, t - t_prev);
+        t_prev = t;
+    }
+    if (q.prof) __syncwarp();   // thread 0 rejoins its warp here: a warp left diverged runs its shuffle / __syncwarp code on the slow path
+}
+__device__ __forceinline__ unsigned long long phase_begin(const FlowQueue& q) {
+    unsigned long long t = 0;
+    if (q.prof && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __host__ __device__ inline int tab_doubles(int J, int K) { return J * (15 + 3 * K); }
 
 // columns of a group's compact Jacobian: [ p(3) | 3 per group joint | K shape ]
@@ -151,10 +167,12 @@ lm_prep_kernel(DevModel M, DevParts Pt, LmBuf a) {
             __syncthreads();
         }
         // chunk list of this group (every thread computes the same numbers; thread 0 writes)
+        const int c0 = min(nchunks, a.maxc);
         for (int s = gbase; s < base; s += a.chunk_verts) {
             if (tid == 0 && nchunks < a.maxc) chunks[nchunks] = make_int4(g, s, min(a.chunk_verts, base - s), 0);
             ++nchunks;
         }
+        if (tid == 0) a.gruns[(size_t)f * kMaxGroups + g] = make_int2(c0, min(nchunks, a.maxc) - c0);
     }
     if (tid == 0) a.gstart[(size_t)f * (kMaxGroups + 1) + Pt.numGroups] = base;
     ncorr = warp_sum_i(ncorr);
@@ -230,6 +248,7 @@ __device__ void rows_body(const DevModel& M, const DevParts& Pt, const LmBuf& a,
     const int tid = threadIdx.x;
     const int i = blk * 256 + tid;
     const int J = M.J, K = M.K;
+    unsigned long long tp = phase_begin(a.q);
     double* tab = reinterpret_cast<double*>(smem_raw);
     double* w = tab + a.tabD;
     double* scr = w + ((K + 1) & ~1);
@@ -241,6 +260,7 @@ __device__ void rows_body(const DevModel& M, const DevParts& Pt, const LmBuf& a,
     int* s_v = reinterpret_cast<int*>(gstart + kMaxGroups + 2);
     s_v[tid] = (i < nslots) ? (int)a.mlist[(size_t)f * a.rec_rs + i] : (int)kNoVertex;
     __syncthreads();
+    phase_lap(a.q, 12, tp);
     const double* G = tab;
     const double* pos = tab + 9 * J;
     const double* tau = tab + 12 * J;
@@ -342,6 +362,7 @@ __device__ void rows_body(const DevModel& M, const DevParts& Pt, const LmBuf& a,
     }
     const double cs = block_sum(costv, scr);
     if (tid == 0) a.cpart[(size_t)f * a.maxrb + blk] = cs;
+    phase_lap(a.q, 13, tp);
 }
 
 __global__ void __launch_bounds__(256, 3)
@@ -470,6 +491,7 @@ __device__ __forceinline__ uint32_t smem_u32_lm(const void* p) { return (uint32_
 __device__ void gram_body(const DevModel& M, const DevParts& Pt, const LmBuf& a, int f, int c, unsigned char* smem_raw) {
     const int tid = threadIdx.x;
     const int K = M.K;
+    unsigned long long tp = phase_begin(a.q);
     const int4 ch = a.chunks[(size_t)f * a.maxc + c];
     const int g = ch.x, start = ch.y, count = ch.z;
     const int nj = Pt.gnj[g];
@@ -513,6 +535,7 @@ __device__ void gram_body(const DevModel& M, const DevParts& Pt, const LmBuf& a,
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    phase_lap(a.q, 14, tp);
 
 #pragma unroll 2
     for (int k0 = 0; k0 < cnt4; k0 += 4) {
@@ -529,6 +552,7 @@ __device__ void gram_body(const DevModel& M, const DevParts& Pt, const LmBuf& a,
         }
     }
     __syncthreads();   // every warp is done with the tile: reuse it for the Gram matrix
+    phase_lap(a.q, 15, tp);
     double* Gs = reinterpret_cast<double*>(smem_raw);
 #pragma unroll
     for (int s = 0; s < kGramSlots; ++s) {
@@ -679,13 +703,13 @@ lm_gram_tc_kernel(DevModel M, DevParts Pt, LmBuf a) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kNBsq = 64;   // 8 x 8 diagonal block of the Cholesky panels
 struct SolveSmem {
-    double *xs, *xt, *tb, *Hs, *gs, *glo, *gcur, *delta, *dd, *wscr, *aa, *ycomp, *scr;
+    double *xs, *xt, *tb, *Hs, *gs, *glo, *gcur, *delta, *dd, *wscr, *aa, *ycomp, *dcomp, *scr;
     int* iscr;
 };
 __host__ __device__ inline size_t solve_smem_bytes(int J, int K, int C) {
     const int P = 3 + 3 * J + K, nx = 3 + 4 * J + K, D = 3 * (J - 1);
     size_t d = 2 * ((nx + 1) & ~1) + tables_doubles(J, K, true) + (size_t)(P + 2) * P + 5 * ((P + 1) & ~1) + 8 * kNBsq + ((D + 1) & ~1) +
-               (size_t)(C > 0 ? C : 1) * ((D + 1) & ~1) + 64;
+               2 * (size_t)(C > 0 ? C : 1) * ((D + 8) & ~7) + 64;
     return d * 8 + 64 * 4 + 128;
 }
 __device__ inline SolveSmem carve_solve(unsigned char* raw, const DevModel& M) {
@@ -703,7 +727,8 @@ __device__ inline SolveSmem carve_solve(unsigned char* raw, const DevModel& M) {
     S.dd = d; d += (P + 1) & ~1;
     S.wscr = d; d += 8 * kNBsq;
     S.aa = d; d += (D + 1) & ~1;
-    S.ycomp = d; d += (size_t)C * ((D + 1) & ~1);
+    S.ycomp = d; d += (size_t)C * ((D + 8) & ~7);
+    S.dcomp = d; d += (size_t)C * ((D + 8) & ~7);
     S.scr = d; d += 64;
     S.iscr = reinterpret_cast<int*>(d);
     return S;
@@ -716,8 +741,27 @@ __device__ inline SolveSmem carve_solve(unsigned char* raw, const DevModel& M) {
 // rank-8 update to the trailing matrix as 4x4 register tiles: two CTA barriers per panel.  dinv receives 1 / L_jj.
 // Returns false (uniformly) when a pivot is not positive.
 constexpr int kNB = 8;
+// 1 / sqrt(d) for a pivot: single-precision seed and two Newton steps in fp64 (full double accuracy up to rounding),
+// without the special-case handling of rsqrt(double); pivots outside the float range take the library path
+__device__ __forceinline__ double pivot_rsqrt(double d) {
+    if (!(d > 1e-30 && d < 1e30)) return rsqrt(d);
+    double y = (double)rsqrtf((float)d);
+    const double h = 0.5 * d;
+    y = fma(y, fma(-h * y, y, 0.5), y);
+    y = fma(y, fma(-h * y, y, 0.5), y);
+    return y;
+}
+#ifdef AVB_UBENCH_PHASES
+__device__ long long g_chol_cyc[4];
+#define CHOL_T(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) { long long t_ = clock64(); g_chol_cyc[k] += t_ - tph; tph = t_; } } while (0)
+#else
+#define CHOL_T(k) do { } while (0)
+#endif
 __device__ bool aug_cholesky(double* W, int P, int R, double* dinv, double* wscr) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nthr = blockDim.x;
+#ifdef AVB_UBENCH_PHASES
+    long long tph = clock64();
+#endif
     double* Lw = wscr + wid * (kNB * kNB);   // this warp's copy of L11 (diagonal: 1 / L_cc)
     const int r = lane & 7;
     for (int j0 = 0; j0 < P; j0 += kNB) {
@@ -733,7 +777,7 @@ __device__ bool aug_cholesky(double* W, int P, int R, double* dinv, double* wscr
         for (int k = 0; k < kNB; ++k) {
             const double d = __shfl_sync(0xffffffffu, a[k], k);
             if (!(d > 0.0) || !isfinite(d)) ok = false;
-            const double inv = rsqrt(d);
+            const double inv = pivot_rsqrt(d);
             const double lk = (r == k) ? d * inv : a[k] * inv;
             a[k] = lk;
             if (r == k) myinv = inv;
@@ -744,6 +788,7 @@ __device__ bool aug_cholesky(double* W, int P, int R, double* dinv, double* wscr
             }
         }
         if (!ok) return false;   // every warp factors the same block: uniform over the CTA
+        CHOL_T(0);
         if (lane < kNB) {
 #pragma unroll
             for (int c = 0; c < kNB; ++c) Lw[lane * kNB + c] = (c < lane) ? a[c] : ((c == lane) ? myinv : 0.0);
@@ -769,6 +814,7 @@ __device__ bool aug_cholesky(double* W, int P, int R, double* dinv, double* wscr
             }
         }
         __syncthreads();
+        CHOL_T(1);
         // ---- C: trailing update W[i][k] -= sum_c L[i][c] L[k][c] on 4x4 tiles of the lower triangle ----
         if (wid == 0 && lane < nb) {   // L11 itself (nobody reads the diagonal block any more)
 #pragma unroll
@@ -828,34 +874,32 @@ __device__ bool aug_cholesky(double* W, int P, int R, double* dinv, double* wscr
             }
         }
         __syncthreads();
+        CHOL_T(2);
     }
     return true;
 }
 
-// x = L^-T y with one warp: the solution lives in registers (entry e in lane e % 32), one shuffle per step
+// x = L^-T y with one warp, in place in shared memory (x and y may alias).  Column-oriented: step i fixes x_i and
+// subtracts L[i][e] x_i from the entries e < i.  Deliberately a tight rolled loop: the solve is executed once per
+// task from a cold instruction cache, where every 128 B of straight-line code costs an L2 round trip.
 __device__ void warp_back_solve(const double* L, const double* dinv, int P, const double* y, double* x) {
     const int lane = threadIdx.x & 31;
-    double b[4];
-#pragma unroll
-    for (int sg = 0; sg < 4; ++sg) b[sg] = (lane + 32 * sg < P) ? y[lane + 32 * sg] : 0.0;
-#pragma unroll
-    for (int sg = 3; sg >= 0; --sg) {
-        for (int ii = 31; ii >= 0; --ii) {
-            const int i = 32 * sg + ii;
-            if (i >= P) continue;
-            const double xi = __shfl_sync(0xffffffffu, b[sg], ii) * dinv[i];
-            if (lane == ii) b[sg] = xi;
-            const double* Li = L + (size_t)i * P;
-#pragma unroll
-            for (int s2 = 0; s2 <= sg; ++s2) {
-                const int e = lane + 32 * s2;
-                if (e < i) b[s2] -= Li[e] * xi;
-            }
-        }
+#pragma unroll 1
+    for (int e = lane; e < P; e += 32) x[e] = y[e];
+    __syncwarp();
+#pragma unroll 1
+    for (int i = P - 1; i >= 0; --i) {
+        const double* Li = L + (size_t)i * P;
+        const double l0 = (lane < i) ? Li[lane] : 0.0, l1 = (lane + 32 < i) ? Li[lane + 32] : 0.0;
+        const double xi = x[i] * dinv[i];
+        __syncwarp();
+        if (lane < i) x[lane] = fma(-l0, xi, x[lane]);
+        if (lane + 32 < i) x[lane + 32] = fma(-l1, xi, x[lane + 32]);
+#pragma unroll 1
+        for (int e = lane + 64; e < i; e += 32) x[e] = fma(-Li[e], xi, x[e]);
+        if (lane == 0) x[i] = xi;
+        __syncwarp();
     }
-#pragma unroll
-    for (int sg = 0; sg < 4; ++sg)
-        if (lane + 32 * sg < P) x[lane + 32 * sg] = b[sg];
 }
 
 // returns true when the frame has finished (uniform over the CTA)
@@ -867,69 +911,89 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
     double* Hcur = a.Hcur + (size_t)f * P * P;
     double* gcur_g = a.gcur + (size_t)f * P;
     const LmState st = load_state(&gst);  // snapshot (only thread 0 writes it back at the end)
+    unsigned long long tp = phase_begin(a.q);
 
+#pragma unroll 1
     for (int i = tid; i < nx; i += kSolveThreads) {
         S.xs[i] = ldg2(a.x + (size_t)f * nx + i);
         S.xt[i] = ldg2(a.xt + (size_t)f * nx + i);
     }
-    for (int i = tid; i < P * P; i += kSolveThreads) S.Hs[i] = 0.0;
+#pragma unroll 1
     for (int i = tid; i < P; i += kSolveThreads) {
-        S.gs[i] = 0.0;
         S.gcur[i] = ldg2(gcur_g + i);
+        S.gs[i] = 0.0;
     }
+#pragma unroll 4
+    for (int i = tid; i < P * P; i += kSolveThreads) S.Hs[i] = 0.0;
+    double* Gs9 = S.tb;   // global joint rotations of the trial point (the table scratch is free until the retraction)
+#pragma unroll 1
+    for (int i = tid; i < 9 * J; i += kSolveThreads) Gs9[i] = ldg2(a.tab + (size_t)f * a.tabD + i);
     __syncthreads();
-    // ---- reduce the chunk partials in chunk order ----
-    double csum = 0.0;
-    for (int c = 0; c < st.nchunks;) {
-        const int4 ch = a.chunks[(size_t)f * a.maxc + c];
-        const int g = ch.x, nj = Pt.gnj[g];
-        int c1 = c + 1;   // chunks [c, c1) belong to the same column group: identical partial layout
-        while (c1 < st.nchunks && a.chunks[(size_t)f * a.maxc + c1].x == g) ++c1;
+    phase_lap(a.q, 4, tp);
+    // ---- reduce the chunk partials, group by group (chunks of a group share one layout), chunks in order ----
+#pragma unroll 1
+    for (int g = 0; g < Pt.numGroups; ++g) {
+        const int2 run = a.gruns[(size_t)f * kMaxGroups + g];
+        if (run.y <= 0) continue;   // uniform
+        const int nj = Pt.gnj[g], Lg = group_L(nj, K), nH = tri_count(Lg);
         const int* gj = Pt.gjoints + g * kMaxJ;
-        const int Lg = group_L(nj, K), nH = tri_count(Lg), nrun = c1 - c;
-        const double* part = a.part + ((size_t)f * a.maxc + c) * a.pstride;
-        auto colmap = [&](int q) -> int {
-            if (q < 3) return q;
-            if (q < 3 + 3 * nj) return 3 + 3 * gj[(q - 3) / 3] + (q - 3) % 3;
-            return 3 + 3 * J + (q - 3 - 3 * nj);
-        };
-        constexpr int kB = 4;   // independent loads in flight per thread
+        const double* part = a.part + ((size_t)f * a.maxc + run.x) * a.pstride;
+        constexpr int kB = 8;   // independent loads in flight per thread
+#pragma unroll 1
         for (int i0 = tid; i0 < nH + Lg; i0 += kSolveThreads * kB) {
             double val[kB];
 #pragma unroll
             for (int u = 0; u < kB; ++u) {
                 const int idx = i0 + u * kSolveThreads;
-                double v = 0.0;   // chunk order is fixed => deterministic
-                if (idx < nH + Lg)
-                    for (int cc = 0; cc < nrun; ++cc) v += ldg2(part + (size_t)cc * a.pstride + idx);
-                val[u] = v;
+                val[u] = (idx < nH + Lg) ? ldg2(part + idx) : 0.0;
+            }
+#pragma unroll 1
+            for (int cc = 1; cc < run.y; ++cc) {   // further chunks of the group, in chunk order
+#pragma unroll
+                for (int u = 0; u < kB; ++u) {
+                    const int idx = i0 + u * kSolveThreads;
+                    if (idx < nH + Lg) val[u] += ldg2(part + (size_t)cc * a.pstride + idx);
+                }
             }
 #pragma unroll
             for (int u = 0; u < kB; ++u) {
                 const int idx = i0 + u * kSolveThreads;
-                if (idx >= nH + Lg) continue;
-                if (idx >= nH) {
-                    S.gs[colmap(idx - nH)] += val[u];
-                } else {
-                    int ra, rb;
-                    if (tri_decode(idx, Lg, ra, rb)) S.Hs[(size_t)colmap(ra) * P + colmap(rb)] += val[u];
+                int ra = idx - nH, rb = -1;
+                bool ok = idx < nH + Lg;
+                if (idx < nH) ok = tri_decode(idx, Lg, ra, rb);
+                if (ok) {
+                    // group column -> tangent column: [ p | 3 per group joint | shape ]
+                    const int ca = ra < 3 ? ra : (ra < 3 + 3 * nj ? 3 + 3 * gj[(ra - 3) / 3] + (ra - 3) % 3 : ra + 3 * (J - nj));
+                    if (rb < 0) {
+                        S.gs[ca] += val[u];
+                    } else {
+                        const int cb = rb < 3 ? rb : (rb < 3 + 3 * nj ? 3 + 3 * gj[(rb - 3) / 3] + (rb - 3) % 3 : rb + 3 * (J - nj));
+                        S.Hs[(size_t)ca * P + cb] += val[u];
+                        if (ca != cb) S.Hs[(size_t)cb * P + ca] += val[u];
+                    }
                 }
             }
         }
         __syncthreads();
-        c = c1;
     }
-    for (int b = 0; b * 256 < st.nslots; ++b) csum += ldg2(a.cpart + (size_t)f * a.maxrb + b);
+    double csum = 0.0;   // cost partials in record-block order, eight loads in flight
+    {
+        const int nb = (st.nslots + 255) >> 8;
+#pragma unroll 1
+        for (int b = 0; b < nb; b += 8) {
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = (b + u < nb) ? ldg2(a.cpart + (size_t)f * a.maxrb + b + u) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (b + u < nb) csum += t[u];
+        }
+    }
     double cost_t = 0.5 * (csum + st.Qsum);
-    for (int i = tid; i < P * P; i += kSolveThreads) {
-        const int r = i / P, c = i - r * P;
-        if (r > c) S.Hs[i] = S.Hs[(size_t)c * P + r];
-    }
     __syncthreads();
+    phase_lap(a.q, 5, tp);
     // ---- eta -> delta coordinates: H = T^T Ht T, g = T^T gt, T_j = G_parent(j) at the trial point ----
-    double* Gs9 = S.tb;   // global joint rotations of the trial point (the table scratch is free until the retraction)
-    for (int i = tid; i < 9 * J; i += kSolveThreads) Gs9[i] = ldg2(a.tab + (size_t)f * a.tabD + i);
-    __syncthreads();
+#pragma unroll 1
     for (int i = tid; i < P * (J - 1); i += kSolveThreads) {
         const int j = 1 + i / P, c = i % P;
         const double* Gp = Gs9 + 9 * M.parent[j];
@@ -940,6 +1004,7 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         h[2 * P] = Gp[2] * h0 + Gp[5] * h1 + Gp[8] * h2;
     }
     __syncthreads();
+#pragma unroll 1
     for (int i = tid; i < P * (J - 1); i += kSolveThreads) {
         const int j = 1 + i / P, r = i % P;
         const double* Gp = Gs9 + 9 * M.parent[j];
@@ -949,6 +1014,7 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         h[1] = h0 * Gp[1] + h1 * Gp[4] + h2 * Gp[7];
         h[2] = h0 * Gp[2] + h1 * Gp[5] + h2 * Gp[8];
     }
+#pragma unroll 1
     for (int j = 1 + tid; j < J; j += kSolveThreads) {
         const double* Gp = Gs9 + 9 * M.parent[j];
         double* gg = S.gs + 3 + 3 * j;
@@ -958,11 +1024,13 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         gg[2] = Gp[2] * g0 + Gp[5] * g1 + Gp[8] * g2;
     }
     __syncthreads();
+    phase_lap(a.q, 6, tp);
     // ---- pose prior (AvatarOptimizer.cpp:661-692, GaussianMixture.cpp:95-114) ----
     const double sbp = st.sbp, sbs = st.sbs;
     const double* w = S.xt + 3 + 4 * J;
     if (sbp > 0.0 && M.gmmC > 0) {
-        const int D = M.gmmD, C = M.gmmC, Dp = (D + 1) & ~1;
+        const int D = M.gmmD, C = M.gmmC, Dp = (D + 8) & ~7;   // row stride: zero padded to 8, slot D of ycomp holds p_c
+#pragma unroll 1
         for (int j = 1 + tid; j < J; j += kSolveThreads) {  // Eigen AngleAxisd(Quaterniond)
             const double* q = S.xt + 3 + 4 * j;
             double nn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
@@ -977,70 +1045,102 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
             S.aa[3 * (j - 1) + 2] = q[2] * s;
         }
         __syncthreads();
-        for (int i = tid; i < C * D; i += kSolveThreads) {  // y_c = Sigma_c^-1 (x - mu_c)
-            // the precision matrices are symmetric (symmetrised at load): walk column r so that consecutive
-            // threads read consecutive addresses
-            const int cc = i / D, r = i % D;
-            const double* Pm = M.gmm_prec + (size_t)cc * D * D + r;
-            const double* mu = M.gmm_mean + (size_t)cc * D;
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            int k = 0;
-            for (; k + 4 <= D; k += 4) {
-                s0 += Pm[(size_t)k * D] * (S.aa[k] - mu[k]);
-                s1 += Pm[(size_t)(k + 1) * D] * (S.aa[k + 1] - mu[k + 1]);
-                s2 += Pm[(size_t)(k + 2) * D] * (S.aa[k + 2] - mu[k + 2]);
-                s3 += Pm[(size_t)(k + 3) * D] * (S.aa[k + 3] - mu[k + 3]);
-            }
-            for (; k < D; ++k) s0 += Pm[(size_t)k * D] * (S.aa[k] - mu[k]);
-            S.ycomp[cc * Dp + r] = (s0 + s1) + (s2 + s3);
+#pragma unroll 1
+        for (int i = tid; i < C * Dp; i += kSolveThreads) {
+            const int cc = i / Dp, k = i - cc * Dp;
+            S.dcomp[i] = (k < D) ? S.aa[k] - M.gmm_mean[cc * D + k] : 0.0;
         }
         __syncthreads();
-        if (tid < 32) {  // p_c = 1/2 (x-mu)^T Sigma^-1 (x-mu) - consts_log[c]; first minimum wins (strict <)
+#pragma unroll 1
+        for (int i = tid; i < C * D; i += kSolveThreads) {  // y_c = Sigma_c^-1 (x - mu_c)
+            // the precision matrices are symmetric (symmetrised at load): walk column r so that consecutive
+            // threads read consecutive addresses; eight loads in flight per thread (the walk is L2-latency bound)
+            const int cc = i / D, r = i - cc * D;
+            const double* Pm = M.gmm_prec + (size_t)cc * D * D + r;
+            const double* dc = S.dcomp + cc * Dp;
+            double s0 = 0, s1 = 0;
+#pragma unroll 1
+            for (int k = 0; k < D; k += 8) {
+                double t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = (k + u < D) ? __ldg(Pm + (size_t)(k + u) * D) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) {
+                    s0 = fma(t[u], dc[k + u], s0);          // dcomp rows are zero padded to a multiple of 8
+                    s1 = fma(t[u + 1], dc[k + u + 1], s1);
+                }
+            }
+            S.ycomp[cc * Dp + r] = s0 + s1;
+        }
+        __syncthreads();
+        // p_c = 1/2 (x-mu)^T Sigma^-1 (x-mu) - consts_log[c], one warp per component; first minimum wins (strict <)
+#pragma unroll 1
+        for (int cc = tid >> 5; cc < C; cc += kSolveThreads >> 5) {
+            double sp = 0;
+#pragma unroll 1
+            for (int k = tid & 31; k < D; k += 32) sp += S.dcomp[cc * Dp + k] * S.ycomp[cc * Dp + k];
+            sp = 0.5 * warp_sum(sp);
+            if ((tid & 31) == 0) S.ycomp[cc * Dp + D] = sp;
+        }
+        __syncthreads();
+        if (tid == 0) {
             double bestp = 1.79769313486231570e308, bestsq = 0;
             int best = 0;
+#pragma unroll 1
             for (int cc = 0; cc < C; ++cc) {
-                double s = 0;
-                for (int k = tid; k < D; k += 32) s += (S.aa[k] - M.gmm_mean[(size_t)cc * D + k]) * S.ycomp[cc * Dp + k];
-                s = 0.5 * warp_sum(s);
-                const double p = s - M.gmm_clog[cc];
-                if (p < bestp) {
-                    bestp = p;
-                    bestsq = s;
+                const double sq = S.ycomp[cc * Dp + D];
+                const double pc = sq - M.gmm_clog[cc];
+                if (pc < bestp) {
+                    bestp = pc;
+                    bestsq = sq;
                     best = cc;
                 }
             }
-            if (tid == 0) {
-                S.iscr[0] = best;
-                S.scr[40] = 0.5 * sbp * sbp * (bestsq - M.gmm_clog[best]);
-            }
+            S.iscr[0] = best;
+            S.scr[40] = 0.5 * sbp * sbp * (bestsq - M.gmm_clog[best]);
         }
         __syncthreads();
         const int best = S.iscr[0];
         const double hb = 0.5 * sbp * sbp;
-        for (int i = tid; i < D * D; i += kSolveThreads) {
-            const int r = i / D, c = i % D;
-            S.Hs[(size_t)(6 + r) * P + 6 + c] += hb * M.gmm_prec[((size_t)best * D + r) * D + c];
+        {   // H += hb Sigma_best^-1, stored zero-padded to the P x P tangent layout: one flat pass, no index maths
+            const double* Pf = M.gmm_pfull + (size_t)best * P * P;
+#pragma unroll 1
+            for (int i0 = tid; i0 < P * P; i0 += 8 * kSolveThreads) {
+                double t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = (i0 + u * kSolveThreads < P * P) ? __ldg(Pf + i0 + u * kSolveThreads) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (i0 + u * kSolveThreads < P * P) S.Hs[i0 + u * kSolveThreads] = fma(hb, t[u], S.Hs[i0 + u * kSolveThreads]);
+            }
         }
+#pragma unroll 1
         for (int r = tid; r < D; r += kSolveThreads) S.gs[6 + r] += hb * S.ycomp[best * Dp + r];
+        __syncthreads();   // the flat pass above touched every entry of H, the shape prior below owns some of them
         cost_t += S.scr[40];
     }
     // ---- shape prior (AvatarOptimizer.cpp:708-723) ----
     if (sbs > 0.0) {
         double sq = 0;
+#pragma unroll 1
         for (int k = 0; k < K; ++k) sq += w[k] * w[k];
         cost_t += 0.5 * sbs * sbs * sq;
+#pragma unroll 1
         for (int k = tid; k < K; k += kSolveThreads) {
             S.Hs[(size_t)(3 + 3 * J + k) * P + 3 + 3 * J + k] += sbs * sbs;
             S.gs[3 + 3 * J + k] += sbs * sbs * w[k];
         }
     }
     __syncthreads();
+    phase_lap(a.q, 7, tp);
     if (a.dump_cost) {  // avb_debug_evaluate: report the objective at the evaluation point and stop
         if (tid == 0) {
             a.dump_cost[f] = cost_t;
             gst.done = 1;
         }
+#pragma unroll 1
         for (int i = tid; i < P; i += kSolveThreads) a.dump_grad[(size_t)f * P + i] = S.gs[i];
+#pragma unroll 1
         for (int i = tid; i < P * P; i += kSolveThreads) a.dump_H[(size_t)f * P * P + i] = S.Hs[i];
         return true;
     }
@@ -1048,68 +1148,75 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
     // ---- Levenberg-Marquardt step control (Ceres-1.14-style trust region; DESIGN.md "solver") ----
     double cost = st.cost, radius = st.radius, decrease = st.decrease, initial_cost = st.initial_cost;
     int iters = st.iters, accepted = st.accepted;
-    bool done = false, have_cur_in_smem = false;
-    auto gmax = [&](const double* g) {
-        double m = 0;
-        for (int i = 0; i < P; ++i) m = fmax(m, fabs(g[i]));
-        return m;
-    };
-    auto trace_now = [&]() {
-        if (a.trace && iters >= 1) {
-            const int slot = min(iters - 1, a.trace_cap - 1);
-            for (int i = tid; i < nx; i += kSolveThreads) a.trace[((size_t)f * a.trace_cap + slot) * nx + i] = S.xs[i];
-        }
-    };
+    bool done = false, have_cur_in_smem = false, take_point = false;
+    double gm = 0;   // max |g| at the evaluation point (every thread: a short rolled loop beats a reduction here)
+#pragma unroll 1
+    for (int i = 0; i < P; ++i) gm = fmax(gm, fabs(S.gs[i]));
     if (st.evals == 0) {
         // first evaluation: the trial point is the start point
         cost = initial_cost = cost_t;
-        for (int i = tid; i < P * P; i += kSolveThreads) Hcur[i] = S.Hs[i];
-        for (int i = tid; i < P; i += kSolveThreads) S.gcur[i] = S.gs[i];
-        __syncthreads();
-        have_cur_in_smem = true;
-        done = !(gmax(S.gcur) > 1e-10) || !isfinite(cost);
+        take_point = true;
+        done = !(gm > 1e-10) || !isfinite(cost);
     } else {
         // finish iteration `iters`: accept or reject the trial point
         const double rho = (cost - cost_t) / st.model_change;
         if (isfinite(cost_t) && rho > 1e-3) {
             ++accepted;
             double dn = 0, xn = 0;
+#pragma unroll 1
             for (int i = 0; i < nx; ++i) {
                 const double dd = S.xt[i] - S.xs[i];
                 dn += dd * dd;
                 xn += S.xs[i] * S.xs[i];
             }
             const double cost_change = cost - cost_t, cost_old = cost;
-            __syncthreads();
-            for (int i = tid; i < nx; i += kSolveThreads) S.xs[i] = S.xt[i];
-            for (int i = tid; i < P * P; i += kSolveThreads) Hcur[i] = S.Hs[i];
-            for (int i = tid; i < P; i += kSolveThreads) S.gcur[i] = S.gs[i];
-            __syncthreads();
-            have_cur_in_smem = true;
+            take_point = true;
             cost = cost_t;
-            radius = fmin(1e16, radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rho - 1.0, 3.0)));
+            const double t3 = 2.0 * rho - 1.0;
+            radius = fmin(1e16, radius / fmax(1.0 / 3.0, 1.0 - t3 * t3 * t3));
             decrease = 2.0;
             if (sqrt(dn) <= 1e-8 * (sqrt(xn) + 1e-8)) done = true;
             if (fabs(cost_change) <= a.function_tolerance * cost_old) done = true;
-            if (!(gmax(S.gcur) > 1e-10)) done = true;
+            if (!(gm > 1e-10)) done = true;
         } else {
             radius /= decrease;
             decrease *= 2.0;
             if (radius < 1e-32) done = true;
         }
-        trace_now();
     }
+    if (take_point) {   // the evaluation point becomes the current point (uniform over the CTA)
+        __syncthreads();
+#pragma unroll 1
+        for (int i = tid; i < nx; i += kSolveThreads) S.xs[i] = S.xt[i];
+#pragma unroll 4
+        for (int i = tid; i < P * P; i += kSolveThreads) Hcur[i] = S.Hs[i];
+#pragma unroll 1
+        for (int i = tid; i < P; i += kSolveThreads) S.gcur[i] = S.gs[i];
+        __syncthreads();
+        have_cur_in_smem = true;
+    }
+    auto trace_now = [&]() {
+        if (a.trace && iters >= 1) {
+            const int slot = min(iters - 1, a.trace_cap - 1);
+#pragma unroll 1
+            for (int i = tid; i < nx; i += kSolveThreads) a.trace[((size_t)f * a.trace_cap + slot) * nx + i] = S.xs[i];
+        }
+    };
+    if (st.evals > 0) trace_now();
     // ---- next iteration(s): damped solve until a usable step exists ----
     double model_change = 0.0;
     bool have_step = false;
+    phase_lap(a.q, 8, tp);
     while (!done && iters < a.max_iters && !have_step) {
         ++iters;
         if (!have_cur_in_smem) {
+#pragma unroll 1
             for (int i = tid; i < P * P; i += kSolveThreads) S.Hs[i] = ldg2(Hcur + i);
             __syncthreads();
         }
         have_cur_in_smem = false;  // the factorisation below overwrites S.Hs
         // W = Hcur + D,  D_jj = clamp(s^2 h_jj, 1e-6, 1e32) / (s^2 radius),  s = 1 / (1 + sqrt(h_jj)); row P = -g^T
+#pragma unroll 1
         for (int j = tid; j < P; j += kSolveThreads) {
             const double h = S.Hs[(size_t)j * P + j];
             const double sj = 1.0 / (1.0 + sqrt(h));
@@ -1120,11 +1227,13 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         }
         __syncthreads();
         bool ok = aug_cholesky(S.Hs, P, P + 1, S.glo, S.wscr);
+        phase_lap(a.q, 9, tp);
         if (ok) {
             if (tid < 32) warp_back_solve(S.Hs, S.glo, P, S.Hs + (size_t)P * P, S.delta);
             __syncthreads();
             // model_cost_change = -delta^T (g + 1/2 H delta) with (H + D) delta = -g  =>  1/2 delta^T (D delta - g)
             double part = 0;
+#pragma unroll 1
             for (int r = tid; r < P; r += kSolveThreads) part += 0.5 * S.delta[r] * (S.dd[r] * S.delta[r] - S.gcur[r]);
             model_change = block_sum(part, S.scr);
             ok = model_change > 0.0 && isfinite(model_change);
@@ -1139,18 +1248,24 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         }
     }
     if (!have_step) done = true;
+    phase_lap(a.q, 10, tp);
     if (!done) {
         // retraction: p, w additive; q <- dq (x) q, |delta| is the half angle (AvatarOptimizer.cpp:123-143)
+#pragma unroll 1
         for (int i = tid; i < 3; i += kSolveThreads) S.xt[i] = S.xs[i] + S.delta[i];
+#pragma unroll 1
         for (int k = tid; k < K; k += kSolveThreads) S.xt[3 + 4 * J + k] = S.xs[3 + 4 * J + k] + S.delta[3 + 3 * J + k];
+#pragma unroll 1
         for (int j = tid; j < J; j += kSolveThreads) {
             const double* d = S.delta + 3 + 3 * j;
             const double* q = S.xs + 3 + 4 * j;
             double* o = S.xt + 3 + 4 * j;
             const double nd = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
             if (nd > 0.0) {
-                const double sdd = sin(nd) / nd;
-                const double ax = sdd * d[0], ay = sdd * d[1], az = sdd * d[2], aw = cos(nd);
+                double sn, aw;
+                sincos(nd, &sn, &aw);
+                const double sdd = sn / nd;
+                const double ax = sdd * d[0], ay = sdd * d[1], az = sdd * d[2];
                 o[0] = aw * q[0] + ax * q[3] + ay * q[2] - az * q[1];
                 o[1] = aw * q[1] + ay * q[3] + az * q[0] - ax * q[2];
                 o[2] = aw * q[2] + az * q[3] + ax * q[1] - ay * q[0];
@@ -1163,15 +1278,21 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         Tables T = carve_tables(S.tb, J, K, true);
         build_tables(M, S.xt, T, true);
         double* tab = a.tab + (size_t)f * a.tabD;
+#pragma unroll 1
         for (int i = tid; i < 9 * J; i += kSolveThreads) tab[i] = T.G[i];
+#pragma unroll 1
         for (int i = tid; i < 3 * J; i += kSolveThreads) {
             tab[9 * J + i] = T.pos[i];
             tab[12 * J + i] = T.tau[i];
         }
+#pragma unroll 1
         for (int i = tid; i < 3 * J * K; i += kSolveThreads) tab[15 * J + i] = T.C[i];
+#pragma unroll 1
         for (int i = tid; i < nx; i += kSolveThreads) a.xt[(size_t)f * nx + i] = S.xt[i];
     }
+#pragma unroll 1
     for (int i = tid; i < nx; i += kSolveThreads) a.x[(size_t)f * nx + i] = S.xs[i];
+#pragma unroll 1
     for (int i = tid; i < P; i += kSolveThreads) gcur_g[i] = S.gcur[i];
     if (tid == 0) {
         gst.cost = cost;
@@ -1191,6 +1312,7 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         fs.final_cost = cost;
         if (!isfinite(cost)) fs.status = 4;
     }
+    phase_lap(a.q, 11, tp);
     return done;
 }
 

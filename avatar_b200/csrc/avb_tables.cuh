@@ -35,47 +35,62 @@ __device__ inline Tables carve_tables(double* base, int J, int K, bool with_shap
 __device__ inline void build_tables(const DevModel& M, const double* xs, Tables T, bool with_shape) {
     const int J = M.J, K = M.K, tid = threadIdx.x, nt = blockDim.x;
     const double* w = xs + 3 + 4 * J;
+#pragma unroll 1
     for (int i = tid; i < 3 * J; i += nt) {
         double s = 0;
+#pragma unroll 1
         for (int k = 0; k < K; ++k) s += M.jreg[i * K + k] * w[k];
         T.Jr[i] = M.jbase[i] + s;
     }
+#pragma unroll 1
     for (int j = tid; j < J; j += nt) quat_to_rot(xs + 3 + 4 * j, T.Rq + 9 * j);
     __syncthreads();
+#pragma unroll 1
     for (int d = 0; d <= M.max_depth; ++d) {
+#pragma unroll 1
         for (int j = tid; j < J; j += nt) {
             if (M.depth[j] != d) continue;
             const int pa = M.parent[j];
             double* Gj = T.G + 9 * j;
             const double* R = T.Rq + 9 * j;
             if (pa < 0) {
+#pragma unroll 1
                 for (int e = 0; e < 9; ++e) Gj[e] = R[e];
+#pragma unroll 1
                 for (int c = 0; c < 3; ++c) T.pos[3 * j + c] = xs[c];
             } else {
                 const double* Gp = T.G + 9 * pa;
+#pragma unroll 1
                 for (int r = 0; r < 3; ++r)
+#pragma unroll 1
                     for (int c = 0; c < 3; ++c)
                         Gj[3 * r + c] = Gp[3 * r] * R[c] + Gp[3 * r + 1] * R[3 + c] + Gp[3 * r + 2] * R[6 + c];
                 const double v0 = T.Jr[3 * j] - T.Jr[3 * pa], v1 = T.Jr[3 * j + 1] - T.Jr[3 * pa + 1],
                              v2 = T.Jr[3 * j + 2] - T.Jr[3 * pa + 2];
+#pragma unroll 1
                 for (int r = 0; r < 3; ++r)
                     T.pos[3 * j + r] = Gp[3 * r] * v0 + Gp[3 * r + 1] * v1 + Gp[3 * r + 2] * v2 + T.pos[3 * pa + r];
             }
         }
         __syncthreads();
     }
+#pragma unroll 1
     for (int j = tid; j < J; j += nt) {
         const double* Gj = T.G + 9 * j;
+#pragma unroll 1
         for (int r = 0; r < 3; ++r)
             T.tau[3 * j + r] = T.pos[3 * j + r] -
                                (Gj[3 * r] * T.Jr[3 * j] + Gj[3 * r + 1] * T.Jr[3 * j + 1] + Gj[3 * r + 2] * T.Jr[3 * j + 2]);
     }
     if (with_shape) {
         const int per = 3 * K;
+#pragma unroll 1
         for (int i = tid; i < J * per; i += nt)
             if (M.depth[i / per] == 0) T.Hj[i] = 0.0;
         __syncthreads();
+#pragma unroll 1
         for (int d = 1; d <= M.max_depth; ++d) {
+#pragma unroll 1
             for (int i = tid; i < J * per; i += nt) {
                 const int j = i / per;
                 if (M.depth[j] != d) continue;
@@ -87,6 +102,7 @@ __device__ inline void build_tables(const DevModel& M, const double* xs, Tables 
             }
             __syncthreads();
         }
+#pragma unroll 1
         for (int i = tid; i < J * per; i += nt) {
             const int j = i / per, r = (i % per) / K, m = i % K;
             const double* Gj = T.G + 9 * j;

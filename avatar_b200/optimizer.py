@@ -157,6 +157,14 @@ class Fitter:
         check(lib.avb_last_flow_task_ms(self.handle, ms))
         return dict(zip(("rows", "gram", "solve", "wait"), list(ms)))
 
+    def flow_phase_ms(self):
+        """finer split of flow_task_ms (CTA ms per sub-phase of the solve / record / Gram tasks)"""
+        ms = (C.c_float * 12)()
+        check(lib.avb_last_flow_phase_ms(self.handle, ms))
+        names = ("solve.load", "solve.reduce", "solve.basis", "solve.prior", "solve.control", "solve.cholesky",
+                 "solve.backsub", "solve.retract", "rows.prologue", "rows.body", "gram.load", "gram.dmma")
+        return dict(zip(names, list(ms)))
+
     def timer_start(self):
         check(lib.avb_timer_start(self.handle))
 

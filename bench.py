@@ -311,16 +311,18 @@ def main():
     npts = np.diff(off)
     # ---- roofline of the dominant kernel: one extra profiled step per lane (CUDA-event pair around every launch
     #      on the launching stream), lanes profiled one after the other ----
-    kms, klaunch, flow_ms = {}, {}, {}
+    kms, klaunch, flow_ms, phase_ms = {}, {}, {}, {}
     for ln in lanes:
         ln["ft"].set_profiling(True)
         ln["ft"].fit_resident(ln["x0"], opt)
         for k, (ms, n) in ln["ft"].kernel_ms().items():
             kms[k] = kms.get(k, 0.0) + ms
             klaunch[k] = klaunch.get(k, 0) + n
-        if "lm_flow_kernel" in kms:
+        if True:   # per-phase CTA time (flow kernel or staged kernels)
             for k, ms in ln["ft"].flow_task_ms().items():
                 flow_ms[k] = flow_ms.get(k, 0.0) + ms
+            for k, ms in ln["ft"].flow_phase_ms().items():
+                phase_ms[k] = phase_ms.get(k, 0.0) + ms
         ln["ft"].set_profiling(False)
     dom = max(kms, key=kms.get)
     V, K = model.numPoints(), model.numShapeKeys()
@@ -371,6 +373,7 @@ def main():
     if flow_ms:
         tot_cta = sum(flow_ms.values()) or 1.0
         roofline["flow_task_share"] = {k: round(v / tot_cta, 4) for k, v in flow_ms.items()}
+        roofline["flow_phase_share"] = {k: round(v / tot_cta, 4) for k, v in phase_ms.items()}
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"fp64": "f64", "fp32": "f64 (J^T J accumulated in f32)",

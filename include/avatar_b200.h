@@ -185,6 +185,10 @@ int avb_timer_stop(avb_fitter* fitter, float* ms);
 int avb_set_profiling(avb_fitter* fitter, int enabled);
 int avb_last_kernel_ms(avb_fitter* fitter, float* total_ms8, int32_t* launches8);
 int avb_last_flow_task_ms(avb_fitter* fitter, float* ms4);
+/* Finer split of the same profiled launch (CTA ms): solve [load, partial reduction, basis change, pose prior,
+ * step control, Cholesky, back substitution, retraction + tables], record task [prologue, body], Gram task
+ * [tile load, DMMA loop] (the Gram epilogue is the rest of the Gram task time). */
+int avb_last_flow_phase_ms(avb_fitter* fitter, float* ms12);
 /* The fitter's static Jacobian column groups (vertices whose skinning joints share an ancestor set): number of
  * groups, joints per group and model vertices per group (arrays of 16).  bench.py derives the algorithmic bytes
  * of the record / Gram kernels from them. */

@@ -1,6 +1,7 @@
-timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-for fl in 1 0; do AVB_FLOW=$fl timeout 120 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extras 2>&1 | tail -1 | python -c "
-import sys,json
-d=json.loads(sys.stdin.read()); r=d['roofline']
-print(round(d['value']), round(d['e2e']['value']), round(d['ms_per_step'],3), r['kernel_ms_per_step'], r.get('flow_task_share'))
-"; done
+#!/bin/bash
+# scratch sweep: staged vs flow, lanes
+for cfg in "0 2" "0 3" "0 4" "0 8" "1 2"; do
+  set -- $cfg
+  echo "flow=$1 lanes=$2"
+  AVB_FLOW=$1 python bench.py --lanes $2 --steps 10 --no-extras --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('  value', round(d['value']), 'e2e', round(d['e2e']['value']))"
+done
