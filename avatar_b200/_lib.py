@@ -47,6 +47,11 @@ class Stats(C.Structure):
 
 # every symbol include/avatar_b200.h declares: (name, restype, argtypes)
 _P = C.c_void_p
+class ImageDesc(C.Structure):   # avb_image_desc
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_float), ("cx", C.c_float), ("fy", C.c_float),
+                ("cy", C.c_float), ("interval", C.c_int32), ("num_parts", C.c_int32)]
+
+
 SYMBOLS = [
     ("avb_default_options", None, [C.POINTER(Options)]),
     ("avb_last_error", C.c_char_p, []),
@@ -67,6 +72,8 @@ SYMBOLS = [
     ("avb_track_sequence", C.c_int, [_P, C.c_int32, _P, _P, _P, _P, C.POINTER(Options), _P, _P]),
     ("avb_upload_batch", C.c_int, [_P, C.c_int32, _P, _P, _P]),
     ("avb_fit_resident", C.c_int, [_P, _P, C.POINTER(Options)]),
+    ("avb_upload_depth_batch", C.c_int, [_P, C.c_int32, _P, _P, _P, C.POINTER(ImageDesc), _P]),
+    ("avb_download_batch", C.c_int, [_P, _P, _P, _P]),
     ("avb_download_results", C.c_int, [_P, _P, _P, _P]),
     ("avb_synchronize", C.c_int, [_P]),
     ("avb_last_device_ms", C.c_int, [_P, C.POINTER(C.c_float), _P]),

@@ -114,6 +114,11 @@ struct avb_fitter {
     long long* h_chunk_begin = nullptr;
     int max_chunks = 0;
     int64_t max_qblocks = 0;
+    // cloud construction from images (avb_upload_depth_batch): staging grown on demand
+    float* d_depth = nullptr; uint8_t* d_parts = nullptr; int* d_roi = nullptr; int* d_strip_count = nullptr;
+    long long* d_strip_offset = nullptr; int* d_bad_label = nullptr;
+    size_t img_cap = 0, strip_cap = 0;
+    std::vector<int> h_strip_count; std::vector<long long> h_strip_offset;
     // state of the uploaded batch
     int batch = 0, num_chunks = 0;
     int64_t total_points = 0;
@@ -474,6 +479,8 @@ void avb_fitter_destroy(avb_fitter* ft) {
         if (e) cudaEventDestroy(e);
     for (auto& e : ft->copied) cudaEventDestroy(e);
     for (auto& e : ft->pev) cudaEventDestroy(e);
+    cudaFree(ft->d_depth); cudaFree(ft->d_parts); cudaFree(ft->d_roi); cudaFree(ft->d_strip_count);
+    cudaFree(ft->d_strip_offset); cudaFree(ft->d_bad_label);
     if (ft->copy_stream) cudaStreamDestroy(ft->copy_stream);
     if (ft->stream) cudaStreamDestroy(ft->stream);
     delete ft;
@@ -661,20 +668,17 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
 }
 
 /* -------- batch upload: data + the NN chunk schedule -------- */
-int avb_upload_batch(avb_fitter* ft, int32_t batch, const double* clouds, const int32_t* labels, const int64_t* offsets) {
-    if (!ft || !offsets || batch <= 0) return fail(AVB_ERR_INVALID, "null argument or empty batch");
-    if (batch > ft->max_batch) return fail(AVB_ERR_CAPACITY, "batch exceeds fitter capacity");
+namespace {
+// NN chunk schedule of a batch whose data are (or are about to be) resident: every frame is cut into equal chunks
+// (multiples of 512 points) so that the grid has about 4 CTAs per SM; |d|^2 partials are always per 256 points,
+// independent of the cut.  Enqueues the schedule tables on the fitter's stream.
+int schedule_batch(avb_fitter* ft, int32_t batch, const int64_t* offsets) {
     const int64_t total = offsets[batch] - offsets[0];
-    if (total < 0 || total > ft->max_points) return fail(AVB_ERR_CAPACITY, "point count exceeds fitter capacity");
-    if (total > 0 && (!clouds || !labels)) return fail(AVB_ERR_INVALID, "null cloud or labels");
-    CUDA_TRY(cudaSetDevice(ft->device));
     ft->offsets.assign(offsets, offsets + batch + 1);
     for (int f = 0; f < batch; ++f)
         if (offsets[f + 1] < offsets[f] || offsets[f + 1] - offsets[f] > (int64_t)1 << 21)
             return fail(AVB_ERR_INVALID, "offsets must be non-decreasing and a frame may hold at most 2^21 points");
     const int64_t o0 = offsets[0];
-    // NN chunk schedule: every frame is cut into equal chunks (multiples of 512 points) so that the
-    // grid has about 4 CTAs per SM; |d|^2 partials are always per 256 points, independent of the cut.
     int64_t target = std::max<int64_t>(512, (total / (4 * (int64_t)ft->num_sms) + 511) / 512 * 512);
     int nc = 0;
     int qb = 0;
@@ -701,10 +705,6 @@ int avb_upload_batch(avb_fitter* ft, int32_t batch, const double* clouds, const 
     ft->num_chunks = nc;
     ft->total_points = total;
     cudaStream_t st = ft->stream;
-    if (total > 0) {
-        CUDA_TRY(cudaMemcpyAsync(ft->d_data, clouds + 3 * o0, (size_t)total * 24, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(ft->d_labels, labels + o0, (size_t)total * 4, cudaMemcpyHostToDevice, st));
-    }
     if (nc > 0) {
         CUDA_TRY(cudaMemcpyAsync(ft->d_chunk_frame, ft->h_chunk_frame, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(ft->d_chunk_begin, ft->h_chunk_begin, (size_t)nc * 8, cudaMemcpyHostToDevice, st));
@@ -712,6 +712,112 @@ int avb_upload_batch(avb_fitter* ft, int32_t batch, const double* clouds, const 
         CUDA_TRY(cudaMemcpyAsync(ft->d_chunk_qblock, ft->h_chunk_qblock, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
     }
     CUDA_TRY(cudaMemcpyAsync(ft->d_frame_qblock, ft->h_frame_qblock, (size_t)(batch + 1) * 4, cudaMemcpyHostToDevice, st));
+    return AVB_OK;
+}
+}  // namespace
+
+int avb_upload_batch(avb_fitter* ft, int32_t batch, const double* clouds, const int32_t* labels, const int64_t* offsets) {
+    if (!ft || !offsets || batch <= 0) return fail(AVB_ERR_INVALID, "null argument or empty batch");
+    if (batch > ft->max_batch) return fail(AVB_ERR_CAPACITY, "batch exceeds fitter capacity");
+    const int64_t total = offsets[batch] - offsets[0];
+    if (total < 0 || total > ft->max_points) return fail(AVB_ERR_CAPACITY, "point count exceeds fitter capacity");
+    if (total > 0 && (!clouds || !labels)) return fail(AVB_ERR_INVALID, "null cloud or labels");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    int rc = schedule_batch(ft, batch, offsets);
+    if (rc != AVB_OK) return rc;
+    if (total > 0) {
+        const int64_t o0 = offsets[0];
+        CUDA_TRY(cudaMemcpyAsync(ft->d_data, clouds + 3 * o0, (size_t)total * 24, cudaMemcpyHostToDevice, ft->stream));
+        CUDA_TRY(cudaMemcpyAsync(ft->d_labels, labels + o0, (size_t)total * 4, cudaMemcpyHostToDevice, ft->stream));
+    }
+    return AVB_OK;
+}
+
+/* -------- cloud construction on the device (demo.cpp:215-250, Calibration.cpp:83-95) -------- */
+int avb_upload_depth_batch(avb_fitter* ft, int32_t batch, const float* depth, const uint8_t* parts, const int32_t* roi,
+                           const avb_image_desc* img, int64_t* offsets_out) {
+    if (!ft || !depth || !parts || !img || batch <= 0) return fail(AVB_ERR_INVALID, "null argument or empty batch");
+    if (batch > ft->max_batch) return fail(AVB_ERR_CAPACITY, "batch exceeds fitter capacity");
+    if (img->width <= 0 || img->height <= 0 || img->interval <= 0) return fail(AVB_ERR_INVALID, "bad image description");
+    if (img->num_parts <= 0 || img->num_parts > 255) return fail(AVB_ERR_INVALID, "num_parts must be in 1..255");
+    if (!(img->fx != 0.f) || !(img->fy != 0.f)) return fail(AVB_ERR_INVALID, "focal lengths must be non-zero");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    cudaStream_t st = ft->stream;
+    const size_t px = (size_t)img->width * img->height, npx = px * batch;
+    const int rows_per_strip = cloud_strip_rows();
+    const int strips = ((img->height + img->interval - 1) / img->interval + rows_per_strip - 1) / rows_per_strip;
+    if (npx > ft->img_cap || (size_t)batch * strips > ft->strip_cap) {   // (re)allocate the image staging
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(ft->d_depth); cudaFree(ft->d_parts); cudaFree(ft->d_roi); cudaFree(ft->d_strip_count);
+        cudaFree(ft->d_strip_offset); cudaFree(ft->d_bad_label);
+        ft->d_depth = nullptr; ft->d_parts = nullptr; ft->d_roi = nullptr; ft->d_strip_count = nullptr;
+        ft->d_strip_offset = nullptr; ft->d_bad_label = nullptr;
+        ft->img_cap = ft->strip_cap = 0;
+        const size_t sc = (size_t)ft->max_batch * strips;
+        if (cudaMalloc(&ft->d_depth, npx * 4) != cudaSuccess || cudaMalloc(&ft->d_parts, npx) != cudaSuccess ||
+            cudaMalloc(&ft->d_roi, (size_t)ft->max_batch * 16) != cudaSuccess || cudaMalloc(&ft->d_strip_count, sc * 4) != cudaSuccess ||
+            cudaMalloc(&ft->d_strip_offset, sc * 8) != cudaSuccess || cudaMalloc(&ft->d_bad_label, (size_t)ft->max_batch * 4) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(AVB_ERR_CUDA, "cudaMalloc of the image staging buffers failed");
+        }
+        ft->img_cap = npx;
+        ft->strip_cap = sc;
+    }
+    CUDA_TRY(cudaMemcpyAsync(ft->d_depth, depth, npx * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ft->d_parts, parts, npx, cudaMemcpyHostToDevice, st));
+    if (roi) CUDA_TRY(cudaMemcpyAsync(ft->d_roi, roi, (size_t)batch * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(ft->d_bad_label, 0, (size_t)batch * 4, st));
+    CloudArgs a{};
+    a.depth = ft->d_depth;
+    a.parts = ft->d_parts;
+    a.roi = roi ? ft->d_roi : nullptr;
+    a.width = img->width; a.height = img->height; a.interval = img->interval; a.num_parts = img->num_parts;
+    a.fx = img->fx; a.cx = img->cx; a.fy = img->fy; a.cy = img->cy;
+    a.max_strips = strips;
+    a.strip_count = ft->d_strip_count;
+    a.strip_offset = ft->d_strip_offset;
+    a.bad_label = ft->d_bad_label;
+    a.cloud = ft->d_data;
+    a.labels = ft->d_labels;
+    CUDA_TRY(launch_cloud_count(a, strips, batch, st));
+    // strip counts -> host: frame offsets, strip offsets and the NN schedule (one small round trip per batch)
+    ft->h_strip_count.resize((size_t)batch * strips + batch);
+    ft->h_strip_offset.resize((size_t)batch * strips);
+    CUDA_TRY(cudaMemcpyAsync(ft->h_strip_count.data(), ft->d_strip_count, (size_t)batch * strips * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ft->h_strip_count.data() + (size_t)batch * strips, ft->d_bad_label, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int f = 0; f < batch; ++f)
+        if (ft->h_strip_count[(size_t)batch * strips + f])
+            return fail(AVB_ERR_INVALID, "body-part label >= num_parts in frame " + std::to_string(f) +
+                                             " (the reference exits here, demo.cpp:232-239)");
+    std::vector<int64_t> off((size_t)batch + 1, 0);
+    for (int f = 0; f < batch; ++f) {
+        int64_t run = off[f];
+        for (int s2 = 0; s2 < strips; ++s2) {
+            ft->h_strip_offset[(size_t)f * strips + s2] = run;
+            run += ft->h_strip_count[(size_t)f * strips + s2];
+        }
+        off[f + 1] = run;
+    }
+    if (off[batch] > ft->max_points) return fail(AVB_ERR_CAPACITY, "point count exceeds fitter capacity");
+    int rc = schedule_batch(ft, batch, off.data());
+    if (rc != AVB_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(ft->d_strip_offset, ft->h_strip_offset.data(), (size_t)batch * strips * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(launch_cloud_compact(a, strips, batch, st));
+    if (offsets_out) std::copy(off.begin(), off.end(), offsets_out);
+    return AVB_OK;
+}
+
+int avb_download_batch(avb_fitter* ft, double* clouds, int32_t* labels, int64_t* offsets) {
+    if (!ft) return fail(AVB_ERR_INVALID, "null fitter");
+    if (ft->batch <= 0) return fail(AVB_ERR_INVALID, "no batch uploaded");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    if (clouds && ft->total_points > 0)
+        CUDA_TRY(cudaMemcpyAsync(clouds, ft->d_data, (size_t)ft->total_points * 24, cudaMemcpyDeviceToHost, ft->stream));
+    if (labels && ft->total_points > 0)
+        CUDA_TRY(cudaMemcpyAsync(labels, ft->d_labels, (size_t)ft->total_points * 4, cudaMemcpyDeviceToHost, ft->stream));
+    CUDA_TRY(cudaStreamSynchronize(ft->stream));
+    if (offsets) std::copy(ft->offsets.begin(), ft->offsets.end(), offsets);
     return AVB_OK;
 }
 

@@ -40,6 +40,20 @@ struct NNArgs {
     int* range_flag;             // [batch]
 };
 
+struct CloudArgs {  // data-cloud construction from depth + part-label images (avb_cloud.cu)
+    const float* depth;          // [batch][height][width] metres
+    const uint8_t* parts;        // [batch][height][width] body-part label, 255 = background
+    const int* roi;              // nullable [batch][4] x0, y0, x1, y1 inclusive (demo.cpp: bgsub.topLeft / botRight)
+    int width, height, interval, num_parts;
+    float fx, cx, fy, cy;        // CameraIntrin (Calibration.cpp:68-74)
+    int max_strips;              // row stride of strip_count / strip_offset
+    int* strip_count;            // [batch][max_strips] foreground pixels per strip of 8 sampled rows
+    const long long* strip_offset;  // [batch][max_strips] first point of the strip in the batch cloud
+    int* bad_label;              // [batch] set when a label >= num_parts (and != 255) was seen
+    double* cloud;               // [3 * total points] out
+    int* labels;                 // [total points] out
+};
+
 struct LmState {  // per-frame Levenberg-Marquardt state, lives in HBM between the kernels of one ICP iteration
     double cost, radius, decrease, Qsum, sbp, sbs, initial_cost, model_change;
     int done, iters, accepted, ncorr, nmatched, nchunks, evals, nslots;   // nslots: record slots incl. alignment gaps
@@ -88,6 +102,9 @@ struct LmBuf {
     FlowQueue q;
 };
 
+int cloud_strip_rows();
+cudaError_t launch_cloud_count(const CloudArgs& a, int strips, int batch, cudaStream_t st);
+cudaError_t launch_cloud_compact(const CloudArgs& a, int strips, int batch, cudaStream_t st);
 size_t pose_smem_bytes(int V, int J, int K);
 cudaError_t launch_pose_visibility(const DevModel& M, const DevParts& Pt, const PoseArgs& a, int batch, cudaStream_t st);
 cudaError_t launch_nn(const DevParts& Pt, const NNArgs& a, int num_chunks, cudaStream_t st);

@@ -63,6 +63,34 @@ class Fitter:
         self.total_points = int(offsets[-1] - offsets[0])
         check(lib.avb_upload_batch(self.handle, self.batch, ptr(clouds), ptr(labels), ptr(offsets)))
 
+    def upload_depth(self, depth, parts, intrin, num_parts, roi=None, interval=1):
+        """Build the batch's data clouds on the device from depth [B,H,W] float32 (metres) and body-part label images
+        [B,H,W] uint8 (255 = background), as demo.cpp:215-250 + CameraIntrin::depthToXYZ do on the host.
+        intrin = (fx, cx, fy, cy); roi: optional [B,4] int32 (x0, y0, x1, y1 inclusive).  Returns the offsets."""
+        depth = np.ascontiguousarray(depth, dtype=np.float32)
+        parts = np.ascontiguousarray(parts, dtype=np.uint8)
+        if depth.ndim == 2:
+            depth, parts = depth[None], parts[None]
+        assert depth.shape == parts.shape
+        B, H, W = depth.shape
+        roi_a = None if roi is None else np.ascontiguousarray(roi, dtype=np.int32).reshape(B, 4)
+        img = _lib.ImageDesc(W, H, float(intrin[0]), float(intrin[1]), float(intrin[2]), float(intrin[3]), int(interval),
+                             int(num_parts))
+        off = np.zeros(B + 1, dtype=np.int64)
+        self._keep = (depth, parts, roi_a)
+        check(lib.avb_upload_depth_batch(self.handle, B, ptr(depth), ptr(parts), ptr(roi_a), C.byref(img), ptr(off)))
+        self.batch = B
+        self.total_points = int(off[-1])
+        return off
+
+    def download_batch(self):
+        """the resident batch: (clouds [N,3] float64, labels [N] int32, offsets [B+1])"""
+        pts = np.zeros((self.total_points, 3))
+        lab = np.zeros(self.total_points, dtype=np.int32)
+        off = np.zeros(self.batch + 1, dtype=np.int64)
+        check(lib.avb_download_batch(self.handle, ptr(pts), ptr(lab), ptr(off)))
+        return pts, lab, off
+
     def fit_resident(self, x, opt):
         x = np.ascontiguousarray(x, dtype=np.float64)
         check(lib.avb_fit_resident(self.handle, ptr(x), C.byref(opt)))

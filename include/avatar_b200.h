@@ -164,6 +164,26 @@ int avb_track_sequence(avb_fitter* fitter, int32_t T, const double* data_clouds,
 int avb_upload_batch(avb_fitter* fitter, int32_t batch, const double* data_clouds,
                      const int32_t* data_part_labels, const int64_t* offsets);
 int avb_fit_resident(avb_fitter* fitter, const double* x_in, const avb_options* opt);  /* async enqueue */
+
+/* Data-cloud construction on the device.  Replaces the caller-side loops of
+ * demo.cpp:215-250 / live-demo.cpp:364-400 (count and fill dataCloud / dataPartLabels from the xyz map and the
+ * RTree label image inside the background-subtractor bounding box, stride `interval`, y negated) together with
+ * CameraIntrin::depthToXYZ (Calibration.cpp:83-95, float arithmetic).  depth: [batch][height][width] float metres;
+ * parts: [batch][height][width] uint8, 255 = background; roi: nullable [batch][4] = x0, y0, x1, y1 inclusive
+ * (bgsub.topLeft / botRight; NULL = whole image).  Points are produced in the reference's raster order and are
+ * bit-identical to the host loop.  A label >= num_parts other than 255 is an error (the reference prints FATAL and
+ * exits, demo.cpp:232-239).  Afterwards the batch is resident exactly as after avb_upload_batch: call
+ * avb_fit_resident / avb_download_results; offsets_out (nullable, batch + 1 entries) receives the per-frame point
+ * offsets; avb_download_batch reads the constructed clouds back (tests). */
+typedef struct avb_image_desc {
+    int32_t width, height;
+    float fx, cx, fy, cy;   /* CameraIntrin, in the order of its intrin[] file format (Calibration.cpp:68-74) */
+    int32_t interval;       /* pixel stride in both directions (demo.cpp `interval`) */
+    int32_t num_parts;      /* rtree.numParts */
+} avb_image_desc;
+int avb_upload_depth_batch(avb_fitter* fitter, int32_t batch, const float* depth, const uint8_t* parts,
+                           const int32_t* roi, const avb_image_desc* img, int64_t* offsets_out);
+int avb_download_batch(avb_fitter* fitter, double* data_clouds, int32_t* data_part_labels, int64_t* offsets);
 int avb_download_results(avb_fitter* fitter, double* x_out, avb_stats* stats, double* cloud_out);
 int avb_synchronize(avb_fitter* fitter);
 /* device time of the kernels enqueued by the last avb_fit_resident, measured with CUDA events on the

@@ -1474,4 +1474,46 @@ int orc_optimize(const orc_optimizer* o, const double* data, const int32_t* labe
     return 0;
 }
 
+
+/* demo.cpp:215-250 + Calibration.cpp:83-95 (see header) */
+int64_t orc_build_cloud(const float* depth, const uint8_t* parts, int width, int height, const float* intrin,
+                        const int32_t* roi, int interval, int num_parts, double* cloud, int32_t* labels,
+                        int64_t capacity) {
+    const float fx = intrin[0], cx = intrin[1], fy = intrin[2], cy = intrin[3];
+    int x0 = 0, y0 = 0, x1 = width - 1, y1 = height - 1;
+    if (roi) { x0 = roi[0]; y0 = roi[1]; x1 = roi[2]; y1 = roi[3]; }
+    if (x0 < 0) x0 = 0;
+    if (y0 < 0) y0 = 0;
+    if (x1 > width - 1) x1 = width - 1;
+    if (y1 > height - 1) y1 = height - 1;
+    // first pass: count (demo.cpp:216-225)
+    int64_t cnz = 0;
+    for (int r = y0; r <= y1; r += interval) {
+        const uint8_t* partptr = parts + (size_t)r * width;
+        for (int c = x0; c <= x1; c += interval) {
+            if (partptr[c] == 255) continue;
+            ++cnz;
+        }
+    }
+    if (cnz > capacity) return -2;
+    // second pass: fill (demo.cpp:229-250); xyz as depthToXYZ computes it (Calibration.cpp:91)
+    int64_t i = 0;
+    for (int r = y0; r <= y1; r += interval) {
+        const float* inPtr = depth + (size_t)r * width;
+        const uint8_t* partptr = parts + (size_t)r * width;
+        for (int c = x0; c <= x1; c += interval) {
+            if (partptr[c] == 255) continue;
+            if (partptr[c] >= num_parts) return -1;
+            const float z = inPtr[c];
+            const float X = (c - cx) * z / fx;
+            const float Y = (r - cy) * z / fy;
+            cloud[3 * i] = X;
+            cloud[3 * i + 1] = -Y;
+            cloud[3 * i + 2] = z;
+            labels[i] = partptr[c];
+            ++i;
+        }
+    }
+    return cnz;
+}
 }  // extern "C"

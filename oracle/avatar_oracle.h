@@ -104,6 +104,14 @@ void orc_retract(const orc_optimizer*, const double* x, const double* delta, dou
 int orc_optimize(const orc_optimizer*, const double* data, const int32_t* labels, int N,
                  double* x, const orc_options*, orc_stats*, double* trace, int trace_cap,
                  int* trace_len, int32_t* nn_out);
+/* Data-cloud construction as the reference's callers do it: CameraIntrin::depthToXYZ
+ * (Calibration.cpp:83-95, float arithmetic) followed by the count-and-fill loops of demo.cpp:215-250 over the
+ * bounding box roi = {x0, y0, x1, y1} (inclusive; NULL = whole image) at stride `interval`: background = 255,
+ * y negated, raster order.  intrin = {fx, cx, fy, cy}.  Returns the number of points, -1 when a label >= num_parts
+ * is met (the reference exits, demo.cpp:232-239), -2 when `capacity` points do not suffice. */
+int64_t orc_build_cloud(const float* depth, const uint8_t* parts, int width, int height, const float* intrin,
+                        const int32_t* roi, int interval, int num_parts, double* cloud, int32_t* labels,
+                        int64_t capacity);
 /* functional stand-in for AvatarRenderer::renderDepth / renderPartMask used only by tests */
 int orc_param_dim(const orc_optimizer*);   /* 3 + 4J + K */
 int orc_tangent_dim(const orc_optimizer*); /* 3 + 3J + K */

@@ -61,6 +61,7 @@ _sig = {
     "orc_retract": (None, [_P, _P, _P, _P]),
     "orc_optimize": (C.c_int, [_P, _P, _P, C.c_int, _P, C.POINTER(Options), C.POINTER(Stats), _P, C.c_int,
                                C.POINTER(C.c_int), _P]),
+    "orc_build_cloud": (C.c_int64, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, C.c_int64]),
     "orc_param_dim": (C.c_int, [_P]),
     "orc_tangent_dim": (C.c_int, [_P]),
 }
@@ -200,6 +201,24 @@ class OracleOptimizer:
         _lib.orc_optimize(self.h, _p(data), _p(labels), data.shape[0], _p(x), C.byref(opt), C.byref(st),
                           _p(trace) if trace_cap else None, trace_cap, C.byref(tl), _p(nn))
         return x, st, trace[:tl.value], nn
+
+
+def build_cloud(depth, parts, intrin, num_parts, roi=None, interval=1):
+    """demo.cpp:215-250 + Calibration.cpp:83-95 restated (orc_build_cloud): (points [N,3], labels [N]); raises
+    ValueError on a label >= num_parts (where the reference exits)"""
+    depth = np.ascontiguousarray(depth, dtype=np.float32)
+    parts = np.ascontiguousarray(parts, dtype=np.uint8)
+    h, w = depth.shape
+    k = np.ascontiguousarray(intrin, dtype=np.float32)
+    r = None if roi is None else np.ascontiguousarray(roi, dtype=np.int32)
+    cap = int((parts != 255).sum()) + 1
+    pts = np.zeros((cap, 3))
+    lab = np.zeros(cap, dtype=np.int32)
+    n = _lib.orc_build_cloud(_p(depth), _p(parts), w, h, _p(k), _p(r), int(interval), int(num_parts), _p(pts), _p(lab), cap)
+    if n == -1:
+        raise ValueError("body-part label >= num_parts")
+    assert n >= 0
+    return pts[:n].copy(), lab[:n].copy()
 
 
 def ref_nanoflann_nn(points, queries):

@@ -316,3 +316,101 @@ def test_bf16_tensor_core_jtj_path(fitter, oopt, frames):
     for b in range(2):
         assert st16[b].final_cost < st16[b].initial_cost
         assert st16[b].final_cost <= 1.05 * st64[b].final_cost
+
+
+# ---------------------------------------------------------------------------------------------
+# data-cloud construction on the device (avb_upload_depth_batch)
+# ---------------------------------------------------------------------------------------------
+def _rendered(model, omodel, prior_arrays, seeds, width=None, height=None):
+    from avatar_b200 import synth
+    W, H = width or synth.WIDTH, height or synth.HEIGHT
+    depth, parts, x0s = [], [], []
+    for s in seeds:
+        rng = np.random.default_rng(1000 + s)
+        x_gt = synth.random_params(model, rng)
+        x0s.append(synth.perturbed_start(model, x_gt, rng))
+        cloud_gt, _, _ = omodel.update_x(x_gt)
+        _, _, d, p = synth.render_cloud(model, cloud_gt, prior_arrays["part_map"], width=W, height=H)
+        depth.append(d)
+        parts.append(p)
+    return np.stack(depth), np.stack(parts), np.stack(x0s)
+
+
+def _bbox(part):
+    ys, xs = np.nonzero(part != 255)
+    return [int(xs.min()), int(ys.min()), int(xs.max()), int(ys.max())]
+
+
+@pytest.mark.gpu
+def test_depth_cloud_construction_bit_exact(model, oracle_mod, omodel, prior_arrays):
+    """device cloud construction == the oracle restatement of demo.cpp:215-250 + Calibration.cpp:83-95: same points
+    (every coordinate bit for bit), same labels, same raster order, for whole images, bounding boxes, strides and
+    the degenerate cases (empty box, all-background frame)"""
+    from avatar_b200 import Fitter, synth, AvbError
+    nparts = int(prior_arrays["num_parts"])
+    intrin = (synth.FX, synth.CX, synth.FY, synth.CY)
+    depth, parts, _ = _rendered(model, omodel, prior_arrays, [0, 1, 2, 3])
+    parts[3][:] = 255                                     # an all-background frame inside the batch
+    ft = Fitter(model, nparts, prior_arrays["part_map"], 4, 4 * 40000)
+    boxes = [_bbox(parts[0]), _bbox(parts[1]), [300, 200, 420, 330], [0, 0, 639, 575]]
+    cases = [(None, 1), (None, 2), (None, 3), (boxes, 1), (boxes, 2), (boxes, 5),
+             ([[10, 10, 5, 300], [5, 5, 5, 5], boxes[0], boxes[1]], 1)]
+    for roi, interval in cases:
+        off = ft.upload_depth(depth, parts, intrin, nparts, roi, interval)
+        pts, lab, off2 = ft.download_batch()
+        assert np.array_equal(off, off2)
+        for b in range(4):
+            po, lo = oracle_mod.build_cloud(depth[b], parts[b], intrin, nparts, None if roi is None else roi[b], interval)
+            assert off[b + 1] - off[b] == len(po)
+            assert np.array_equal(pts[off[b]:off[b + 1]], po)
+            assert np.array_equal(lab[off[b]:off[b + 1]], lo)
+        assert off[4] == off[3]                           # the background frame contributes nothing
+    bad = parts.copy()
+    bad[1, 100, 100] = nparts + 3                         # the reference prints FATAL and exits (demo.cpp:232-239)
+    with pytest.raises(AvbError):
+        ft.upload_depth(depth, bad, intrin, nparts)
+    ft.close()
+
+
+@pytest.mark.gpu
+def test_fit_from_depth_equals_fit_from_host_cloud(model, oracle_mod, omodel, prior_arrays):
+    """a fit whose data clouds were built on the device is bit-identical to the fit of the host-built clouds"""
+    from avatar_b200 import Fitter, synth
+    nparts = int(prior_arrays["num_parts"])
+    intrin = (synth.FX, synth.CX, synth.FY, synth.CY)
+    depth, parts, x0 = _rendered(model, omodel, prior_arrays, [0, 1])
+    ft = Fitter(model, nparts, prior_arrays["part_map"], 2, 2 * 40000)
+    o = _opts()
+    ft.upload_depth(depth, parts, intrin, nparts)
+    ft.fit_resident(x0, o)
+    xd, std, _ = ft.download()
+    host = [oracle_mod.build_cloud(depth[b], parts[b], intrin, nparts) for b in range(2)]
+    pts = np.concatenate([h[0] for h in host])
+    lab = np.concatenate([h[1] for h in host])
+    off = np.cumsum([0] + [len(h[0]) for h in host])
+    xh, sth, _ = ft.fit_batch(pts, lab, off, x0, o)
+    assert np.array_equal(xd, xh)
+    assert [s.num_correspondences for s in std] == [s.num_correspondences for s in sth]
+    ft.close()
+
+
+@pytest.mark.gpu
+def test_depth_cloud_construction_large_image(model, oracle_mod, omodel, prior_arrays):
+    """2560x2304 render (configs[4] density, > 150k points), odd bounding box and stride"""
+    from avatar_b200 import Fitter, synth
+    nparts = int(prior_arrays["num_parts"])
+    rng = np.random.default_rng(5)
+    x_gt = synth.random_params(model, rng)
+    x_gt[2] = 2.3
+    cloud, _, _ = omodel.update_x(x_gt)
+    intrin = (2016.0, 1280.0, 2016.0, 1152.0)
+    _, _, depth, part = synth.render_cloud(model, cloud, prior_arrays["part_map"], width=2560, height=2304,
+                                           fx=2016.0, fy=2016.0, cx=1280.0, cy=1152.0)
+    ft = Fitter(model, nparts, prior_arrays["part_map"], 1, 400000)
+    for roi, interval in [(None, 1), ([_bbox(part)], 1), ([[101, 77, 2203, 2001]], 3)]:
+        off = ft.upload_depth(depth, part, intrin, nparts, roi, interval)
+        pts, lab, _ = ft.download_batch()
+        po, lo = oracle_mod.build_cloud(depth, part, intrin, nparts, None if roi is None else roi[0], interval)
+        assert len(po) == off[1] and (interval > 1 or len(po) > 150000)
+        assert np.array_equal(pts, po) and np.array_equal(lab, lo)
+    ft.close()

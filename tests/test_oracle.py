@@ -237,3 +237,60 @@ def test_solvers_reduce_cost_and_agree_on_the_optimum(oracle_mod, oopt, frames):
     o.max_iters_per_icp = 60
     x_lm2, st_lm2, _, _ = oopt.optimize(pts, lab, x0, o)
     assert abs(st_b2.final_cost - st_lm2.final_cost) < 1e-3 * st_lm2.final_cost
+
+
+# ---------------------------------------------------------------------------------------------
+# data-cloud construction (demo.cpp:215-250 + Calibration.cpp:83-95)
+# ---------------------------------------------------------------------------------------------
+def _numpy_build_cloud(depth, parts, intrin, roi=None, interval=1):
+    """independent float32 restatement with numpy scalars (pure-Python loops: small images only)"""
+    fx, cx, fy, cy = [np.float32(v) for v in intrin]
+    h, w = depth.shape
+    x0, y0, x1, y1 = (0, 0, w - 1, h - 1) if roi is None else roi
+    pts, lab = [], []
+    for r in range(y0, y1 + 1, interval):
+        for c in range(x0, x1 + 1, interval):
+            if parts[r, c] == 255:
+                continue
+            z = np.float32(depth[r, c])
+            X = (np.float32(c) - cx) * z / fx
+            Y = (np.float32(r) - cy) * z / fy
+            pts.append([np.float64(X), -np.float64(Y), np.float64(z)])
+            lab.append(int(parts[r, c]))
+    return np.array(pts).reshape(-1, 3), np.array(lab, dtype=np.int32)
+
+
+def test_build_cloud_oracle_small_cases(oracle_mod):
+    rng = np.random.default_rng(3)
+    h, w = 13, 17
+    depth = rng.uniform(0.5, 4.0, (h, w)).astype(np.float32)
+    parts = rng.integers(0, 16, (h, w)).astype(np.uint8)
+    parts[rng.random((h, w)) < 0.6] = 255
+    intrin = (504.25, 8.3, 503.5, 6.1)
+    for roi, interval in [(None, 1), (None, 2), ((2, 1, 14, 11), 1), ((3, 2, 16, 12), 3), ((5, 5, 5, 5), 1), ((9, 3, 4, 8), 1)]:
+        p, l = oracle_mod.build_cloud(depth, parts, intrin, 16, roi, interval)
+        pn, ln = _numpy_build_cloud(depth, parts, intrin, roi, interval)
+        assert p.shape == pn.shape
+        assert np.array_equal(p, pn) and np.array_equal(l, ln)
+    # a label >= num_parts is fatal in the reference (demo.cpp:232-239)
+    parts[4, 4] = 40
+    with pytest.raises(ValueError):
+        oracle_mod.build_cloud(depth, parts, intrin, 16)
+    # all background -> empty cloud
+    p, l = oracle_mod.build_cloud(depth, np.full((h, w), 255, np.uint8), intrin, 16)
+    assert p.shape == (0, 3) and l.shape == (0,)
+
+
+def test_build_cloud_oracle_matches_harness_backprojection(oracle_mod, model, omodel, prior_arrays):
+    """the oracle restatement of demo.cpp's loops and the synthetic harness' own back-projection (avb_synth.cpp,
+    written from optim.cpp:104-120) agree bit for bit on a rendered 640x576 frame"""
+    from avatar_b200 import synth
+    rng = np.random.default_rng(1000)
+    x_gt = synth.random_params(model, rng)
+    cloud_gt, _, _ = omodel.update_x(x_gt)
+    for interval in (1, 3):
+        pts, lab, depth, part = synth.render_cloud(model, cloud_gt, prior_arrays["part_map"], interval=interval)
+        p, l = oracle_mod.build_cloud(depth, part, (synth.FX, synth.CX, synth.FY, synth.CY), int(prior_arrays["num_parts"]),
+                                      None, interval)
+        assert len(p) == len(pts) > 100
+        assert np.array_equal(p, pts) and np.array_equal(l, lab)
