@@ -74,6 +74,7 @@ SYMBOLS = [
     ("avb_fit_resident", C.c_int, [_P, _P, C.POINTER(Options)]),
     ("avb_upload_depth_batch", C.c_int, [_P, C.c_int32, _P, _P, _P, C.POINTER(ImageDesc), _P]),
     ("avb_download_batch", C.c_int, [_P, _P, _P, _P]),
+    ("avb_last_cloud_ms", C.c_int, [_P, _P]),
     ("avb_download_results", C.c_int, [_P, _P, _P, _P]),
     ("avb_synchronize", C.c_int, [_P]),
     ("avb_last_device_ms", C.c_int, [_P, C.POINTER(C.c_float), _P]),

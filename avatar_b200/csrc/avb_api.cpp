@@ -118,6 +118,7 @@ struct avb_fitter {
     float* d_depth = nullptr; uint8_t* d_parts = nullptr; int* d_roi = nullptr; int* d_strip_count = nullptr;
     long long* d_strip_offset = nullptr; int* d_bad_label = nullptr;
     size_t img_cap = 0, strip_cap = 0;
+    cudaEvent_t cev[4] = {};   // around cloud_count_kernel and cloud_compact_kernel of the last avb_upload_depth_batch
     std::vector<int> h_strip_count; std::vector<long long> h_strip_offset;
     // state of the uploaded batch
     int batch = 0, num_chunks = 0;
@@ -481,6 +482,7 @@ void avb_fitter_destroy(avb_fitter* ft) {
     for (auto& e : ft->pev) cudaEventDestroy(e);
     cudaFree(ft->d_depth); cudaFree(ft->d_parts); cudaFree(ft->d_roi); cudaFree(ft->d_strip_count);
     cudaFree(ft->d_strip_offset); cudaFree(ft->d_bad_label);
+    for (auto& e : ft->cev) if (e) cudaEventDestroy(e);
     if (ft->copy_stream) cudaStreamDestroy(ft->copy_stream);
     if (ft->stream) cudaStreamDestroy(ft->stream);
     delete ft;
@@ -779,7 +781,11 @@ int avb_upload_depth_batch(avb_fitter* ft, int32_t batch, const float* depth, co
     a.bad_label = ft->d_bad_label;
     a.cloud = ft->d_data;
     a.labels = ft->d_labels;
+    if (!ft->cev[0])
+        for (auto& e : ft->cev) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaEventRecord(ft->cev[0], st));
     CUDA_TRY(launch_cloud_count(a, strips, batch, st));
+    CUDA_TRY(cudaEventRecord(ft->cev[1], st));
     // strip counts -> host: frame offsets, strip offsets and the NN schedule (one small round trip per batch)
     ft->h_strip_count.resize((size_t)batch * strips + batch);
     ft->h_strip_offset.resize((size_t)batch * strips);
@@ -803,8 +809,20 @@ int avb_upload_depth_batch(avb_fitter* ft, int32_t batch, const float* depth, co
     int rc = schedule_batch(ft, batch, off.data());
     if (rc != AVB_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(ft->d_strip_offset, ft->h_strip_offset.data(), (size_t)batch * strips * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaEventRecord(ft->cev[2], st));
     CUDA_TRY(launch_cloud_compact(a, strips, batch, st));
+    CUDA_TRY(cudaEventRecord(ft->cev[3], st));
     if (offsets_out) std::copy(off.begin(), off.end(), offsets_out);
+    return AVB_OK;
+}
+
+int avb_last_cloud_ms(avb_fitter* ft, float* ms2) {
+    if (!ft || !ms2) return fail(AVB_ERR_INVALID, "null argument");
+    if (!ft->cev[0]) return fail(AVB_ERR_INVALID, "no avb_upload_depth_batch yet");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    CUDA_TRY(cudaEventSynchronize(ft->cev[3]));
+    CUDA_TRY(cudaEventElapsedTime(&ms2[0], ft->cev[0], ft->cev[1]));
+    CUDA_TRY(cudaEventElapsedTime(&ms2[1], ft->cev[2], ft->cev[3]));
     return AVB_OK;
 }
 

@@ -57,6 +57,7 @@ struct CloudArgs {  // data-cloud construction from depth + part-label images (a
 struct LmState {  // per-frame Levenberg-Marquardt state, lives in HBM between the kernels of one ICP iteration
     double cost, radius, decrease, Qsum, sbp, sbs, initial_cost, model_change;
     int done, iters, accepted, ncorr, nmatched, nchunks, evals, nslots;   // nslots: record slots incl. alignment gaps
+    int last, pad0, pad1, pad2;   // last: the pending evaluation only decides the final accept / reject (cost only)
 };
 
 struct FlowQueue {  // device work queue of lm_flow_kernel

@@ -214,6 +214,8 @@ lm_prep_kernel(DevModel M, DevParts Pt, LmBuf a) {
         st.nslots = base;
         st.nchunks = min(nchunks, a.maxc);
         st.evals = 0;
+        st.last = 0;
+        st.pad0 = st.pad1 = st.pad2 = 0;
         FrameStats& fs = a.stats[f];
         fs.num_correspondences = ncorr;
         fs.num_matched_vertices = nmatched;
@@ -244,7 +246,7 @@ lm_prep_kernel(DevModel M, DevParts Pt, LmBuf a) {
 __host__ __device__ inline int rec_floats(int nj, int K) { return 3 * nj + 3 * K + 7; }
 
 __device__ void rows_body(const DevModel& M, const DevParts& Pt, const LmBuf& a, int f, int blk, int nslots,
-                          unsigned char* smem_raw) {
+                          bool cost_only, unsigned char* smem_raw) {
     const int tid = threadIdx.x;
     const int i = blk * 256 + tid;
     const int J = M.J, K = M.K;
@@ -310,7 +312,8 @@ __device__ void rows_body(const DevModel& M, const DevParts& Pt, const LmBuf& a,
         }
         const double cn = (double)a.cnt[(size_t)f * M.V + v];
         const double sc = sqrt(cn), s2 = 2.0 * sc;
-        for (int gi = 0; gi < nj; ++gi) {
+        // the evaluation that only decides the last accept / reject needs the cost, not the Jacobian records
+        for (int gi = 0; gi < (cost_only ? 0 : nj); ++gi) {
             const int j = gj[gi];
             double y0 = 0, y1 = 0, y2 = 0, W = 0;
 #pragma unroll
@@ -329,7 +332,7 @@ __device__ void rows_body(const DevModel& M, const DevParts& Pt, const LmBuf& a,
         // shape: sum_k w_k (G_k (Delta_v - S_k) + H_k) = B Delta_v + sum_k w_k C_k  (AvatarOptimizer.cpp:568-580)
         float* rr = rec + (size_t)(3 * nj) * RS;   // sc | rho_hi | rho_lo
         float* rs = rr + 7 * RS;
-        for (int m = 0; m < K; ++m) {
+        for (int m = 0; m < (cost_only ? 0 : K); ++m) {
             const double d0 = sd[m], d1 = sd[K + m], d2 = sd[2 * K + m];
             double e0 = B[0] * d0 + B[1] * d1 + B[2] * d2;
             double e1 = B[3] * d0 + B[4] * d1 + B[5] * d2;
@@ -349,14 +352,16 @@ __device__ void rows_body(const DevModel& M, const DevParts& Pt, const LmBuf& a,
         }
         // residual sum of the vertex's correspondences, c x - sum d (AvatarOptimizer.cpp:632-639), split hi/lo
         const unsigned long long* sumv = a.sum + 3 * ((size_t)f * M.V + v);
-        rr[0] = (float)sc;
+        if (!cost_only) rr[0] = (float)sc;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const double sr = (double)(long long)sumv[c] * kFixInv;
-            const double rho = (cn * x[c] - sr) / sc;
-            const float hi = (float)rho;
-            rr[(1 + c) * RS] = hi;
-            rr[(4 + c) * RS] = (float)(rho - (double)hi);
+            if (!cost_only) {
+                const double rho = (cn * x[c] - sr) / sc;
+                const float hi = (float)rho;
+                rr[(1 + c) * RS] = hi;
+                rr[(4 + c) * RS] = (float)(rho - (double)hi);
+            }
             costv += x[c] * (cn * x[c] - 2.0 * sr);  // sum_i |x - d_i|^2 - sum_i |d_i|^2 = x . (c x - 2 s)
         }
     }
@@ -371,7 +376,7 @@ lm_rows_kernel(DevModel M, DevParts Pt, LmBuf a) {
     const int f = blockIdx.y;
     const int nslots = a.state[f].nslots;
     if (a.state[f].done || blockIdx.x * 256 >= nslots) return;
-    rows_body(M, Pt, a, f, blockIdx.x, nslots, smem_raw);
+    rows_body(M, Pt, a, f, blockIdx.x, nslots, a.state[f].last != 0, smem_raw);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -573,7 +578,7 @@ __global__ void __launch_bounds__(kGramThreads, 2)
 lm_gram_kernel(DevModel M, DevParts Pt, LmBuf a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int c = blockIdx.x, f = blockIdx.y;
-    if (a.state[f].done || c >= a.state[f].nchunks) return;
+    if (a.state[f].done || a.state[f].last || c >= a.state[f].nchunks) return;
     gram_body(M, Pt, a, f, c, smem_raw);
 }
 
@@ -596,7 +601,7 @@ lm_gram_tc_kernel(DevModel M, DevParts Pt, LmBuf a) {
     __shared__ uint32_t tmem_base_s;
     const int c = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const LmState& st = a.state[f];
-    if (st.done || c >= st.nchunks) return;
+    if (st.done || st.last || c >= st.nchunks) return;
     const int K = M.K;
     const int4 ch = a.chunks[(size_t)f * a.maxc + c];
     const int g = ch.x, start = ch.y, count = ch.z;
@@ -931,8 +936,9 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
     __syncthreads();
     phase_lap(a.q, 4, tp);
     // ---- reduce the chunk partials, group by group (chunks of a group share one layout), chunks in order ----
+    const bool last = st.last != 0;   // cost-only evaluation: it decides the final accept / reject, no step follows
 #pragma unroll 1
-    for (int g = 0; g < Pt.numGroups; ++g) {
+    for (int g = 0; g < (last ? 0 : Pt.numGroups); ++g) {
         const int2 run = a.gruns[(size_t)f * kMaxGroups + g];
         if (run.y <= 0) continue;   // uniform
         const int nj = Pt.gnj[g], Lg = group_L(nj, K), nH = tri_count(Lg);
@@ -993,6 +999,7 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
     __syncthreads();
     phase_lap(a.q, 5, tp);
     // ---- eta -> delta coordinates: H = T^T Ht T, g = T^T gt, T_j = G_parent(j) at the trial point ----
+    if (!last) {
 #pragma unroll 1
     for (int i = tid; i < P * (J - 1); i += kSolveThreads) {
         const int j = 1 + i / P, c = i % P;
@@ -1022,6 +1029,7 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         gg[0] = Gp[0] * g0 + Gp[3] * g1 + Gp[6] * g2;
         gg[1] = Gp[1] * g0 + Gp[4] * g1 + Gp[7] * g2;
         gg[2] = Gp[2] * g0 + Gp[5] * g1 + Gp[8] * g2;
+    }
     }
     __syncthreads();
     phase_lap(a.q, 6, tp);
@@ -1102,7 +1110,7 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         __syncthreads();
         const int best = S.iscr[0];
         const double hb = 0.5 * sbp * sbp;
-        {   // H += hb Sigma_best^-1, stored zero-padded to the P x P tangent layout: one flat pass, no index maths
+        if (!last) {   // H += hb Sigma_best^-1, stored zero-padded to the P x P tangent layout: one flat pass, no index maths
             const double* Pf = M.gmm_pfull + (size_t)best * P * P;
 #pragma unroll 1
             for (int i0 = tid; i0 < P * P; i0 += 8 * kSolveThreads) {
@@ -1115,7 +1123,7 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
             }
         }
 #pragma unroll 1
-        for (int r = tid; r < D; r += kSolveThreads) S.gs[6 + r] += hb * S.ycomp[best * Dp + r];
+        for (int r = tid; r < (last ? 0 : D); r += kSolveThreads) S.gs[6 + r] += hb * S.ycomp[best * Dp + r];
         __syncthreads();   // the flat pass above touched every entry of H, the shape prior below owns some of them
         cost_t += S.scr[40];
     }
@@ -1151,7 +1159,8 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
     bool done = false, have_cur_in_smem = false, take_point = false;
     double gm = 0;   // max |g| at the evaluation point (every thread: a short rolled loop beats a reduction here)
 #pragma unroll 1
-    for (int i = 0; i < P; ++i) gm = fmax(gm, fabs(S.gs[i]));
+    for (int i = 0; i < (last ? 0 : P); ++i) gm = fmax(gm, fabs(S.gs[i]));
+    if (last) gm = 1.0;   // no gradient in a cost-only evaluation; the frame ends after it in any case
     if (st.evals == 0) {
         // first evaluation: the trial point is the start point
         cost = initial_cost = cost_t;
@@ -1189,11 +1198,11 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
 #pragma unroll 1
         for (int i = tid; i < nx; i += kSolveThreads) S.xs[i] = S.xt[i];
 #pragma unroll 4
-        for (int i = tid; i < P * P; i += kSolveThreads) Hcur[i] = S.Hs[i];
+        for (int i = tid; i < (last ? 0 : P * P); i += kSolveThreads) Hcur[i] = S.Hs[i];
 #pragma unroll 1
-        for (int i = tid; i < P; i += kSolveThreads) S.gcur[i] = S.gs[i];
+        for (int i = tid; i < (last ? 0 : P); i += kSolveThreads) S.gcur[i] = S.gs[i];
         __syncthreads();
-        have_cur_in_smem = true;
+        have_cur_in_smem = !last;
     }
     auto trace_now = [&]() {
         if (a.trace && iters >= 1) {
@@ -1303,6 +1312,7 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         gst.iters = iters;
         gst.accepted = accepted;
         gst.evals = st.evals + 1;
+        gst.last = (!done && iters >= a.max_iters) ? 1 : 0;   // the pending trial is the last one: cost only
         gst.done = done ? 1 : 0;
         FrameStats& fs = a.stats[f];
         // an iteration whose trial point is still to be evaluated is counted once that evaluation is reduced
@@ -1359,16 +1369,22 @@ lm_flow_kernel(DevModel M, DevParts Pt, LmBuf a) {
         const int type = (int)((unsigned)task >> 30), f = (task >> 12) & 0x3FFFF, idx = task & 0xFFF;
         if (type == kTaskRows) {
             const int nslots = ldg2(&a.state[f].nslots);
-            rows_body(M, Pt, a, f, idx, nslots, smem_raw);
+            const bool cost_only = ldg2(&a.state[f].last) != 0;
+            rows_body(M, Pt, a, f, idx, nslots, cost_only, smem_raw);
             __threadfence();
             __syncthreads();
             if (tid == 0) {
+                s_last = 0;
                 if (atomicSub(&a.q.rows_left[f], 1) == 1) {
                     __threadfence();
-                    const int nch = ldg2(&a.state[f].nchunks);
-                    atomicExch(&a.q.gram_left[f], nch);
-                    __threadfence();
-                    flow_push(a.q, kTaskGram, f, nch);
+                    if (cost_only) {
+                        s_last = 1;   // no Gram tasks: this CTA finishes the frame
+                    } else {
+                        const int nch = ldg2(&a.state[f].nchunks);
+                        atomicExch(&a.q.gram_left[f], nch);
+                        __threadfence();
+                        flow_push(a.q, kTaskGram, f, nch);
+                    }
                 }
                 lap(0);
             }
@@ -1380,23 +1396,23 @@ lm_flow_kernel(DevModel M, DevParts Pt, LmBuf a) {
                 s_last = atomicSub(&a.q.gram_left[f], 1) == 1;
                 lap(1);
             }
+        }
+        __syncthreads();
+        if (s_last) {   // the frame's evaluation is complete: this CTA runs its solve
+            __threadfence();
+            const bool done = solve_body(M, Pt, a, f, smem_raw);
+            __threadfence();
             __syncthreads();
-            if (s_last) {
-                __threadfence();
-                const bool done = solve_body(M, Pt, a, f, smem_raw);
-                __threadfence();
-                __syncthreads();
-                if (tid == 0) {
-                    if (done) {
-                        atomicSub(&a.q.ctrl[2], 1u);
-                    } else {
-                        const int nrb = (ldg2(&a.state[f].nslots) + 255) >> 8;
-                        atomicExch(&a.q.rows_left[f], nrb);
-                        __threadfence();
-                        flow_push(a.q, kTaskRows, f, nrb);
-                    }
-                    lap(2);
+            if (tid == 0) {
+                if (done) {
+                    atomicSub(&a.q.ctrl[2], 1u);
+                } else {
+                    const int nrb = (ldg2(&a.state[f].nslots) + 255) >> 8;
+                    atomicExch(&a.q.rows_left[f], nrb);
+                    __threadfence();
+                    flow_push(a.q, kTaskRows, f, nrb);
                 }
+                lap(2);
             }
         }
         __syncthreads();

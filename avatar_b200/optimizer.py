@@ -83,6 +83,12 @@ class Fitter:
         self.total_points = int(off[-1])
         return off
 
+    def cloud_ms(self):
+        """device ms of (cloud_count_kernel, cloud_compact_kernel) of the last upload_depth"""
+        ms = (C.c_float * 2)()
+        check(lib.avb_last_cloud_ms(self.handle, ms))
+        return float(ms[0]), float(ms[1])
+
     def download_batch(self):
         """the resident batch: (clouds [N,3] float64, labels [N] int32, offsets [B+1])"""
         pts = np.zeros((self.total_points, 3))

@@ -423,6 +423,43 @@ def main():
                              "tracking_frames_per_s": T / trk, "tracking_frames": T,
                              "note": "host buffers in, parameters out, icp_iters=1, 10 LM iterations; wall clock"}
         f1.close()
+        # ---- data-cloud construction on the device from depth + part-label images ----
+        from avatar_b200 import synth
+        NI = min(256, F)
+        dimg = pinned_array(_lib.lib, (NI, synth.HEIGHT, synth.WIDTH), np.float32)   # pinned, like the cloud batches
+        pimg = pinned_array(_lib.lib, (NI, synth.HEIGHT, synth.WIDTH), np.uint8)
+        for i in range(NI):
+            _, _, dimg[i], pimg[i] = synth.render_cloud(model, clouds_gt[i], part_map)
+        intrin = (synth.FX, synth.CX, synth.FY, synth.CY)
+        fc = Fitter(model, num_parts, part_map, NI, int(off[NI]) + 64, local_rank)
+        fc.upload_depth(dimg, pimg, intrin, num_parts)
+        kms, wall = [], []
+        for _ in range(5):
+            tA = time.perf_counter()
+            offc = fc.upload_depth(dimg, pimg, intrin, num_parts)
+            fc.synchronize()
+            wall.append(time.perf_counter() - tA)
+            kms.append(sum(fc.cloud_ms()))
+        npt = int(offc[-1])
+        alg = NI * synth.HEIGHT * synth.WIDTH * 5.0 + 28.0 * npt    # label (1 B) + depth (4 B) per pixel read, 28 B per point written
+        k_ms = float(np.median(kms))
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as orc_c
+        tA = time.perf_counter()
+        for i in range(16):
+            orc_c.build_cloud(dimg[i], pimg[i], intrin, num_parts)
+        cpu_s = (time.perf_counter() - tA) / 16
+        fc.close()
+        line["cloud_construction"] = {
+            "what": "avb_upload_depth_batch: depth + part-label images -> data clouds on the device (demo.cpp:215-250, "
+                    "Calibration.cpp:83-95), %d frames of 640x576, %d points" % (NI, npt),
+            "kernel_ms": k_ms, "frames_per_s_kernels": NI / (k_ms * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (k_ms * 1e-3) / 1e9 / peak,
+                         "note": "algorithmic bytes = 5 B per pixel read + 28 B per point written, over both kernels"},
+            "e2e_ms": 1e3 * float(np.median(wall)), "frames_per_s_e2e": NI / float(np.median(wall)),
+            "h2d_bytes": int(NI * synth.HEIGHT * synth.WIDTH * 5),
+            "cpu_oracle_ms_per_frame_1thread": 1e3 * cpu_s}
     # ---- CPU baseline: the oracle port on a bounded sample, N=1 only ----
     if world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))

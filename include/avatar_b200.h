@@ -184,6 +184,8 @@ typedef struct avb_image_desc {
 int avb_upload_depth_batch(avb_fitter* fitter, int32_t batch, const float* depth, const uint8_t* parts,
                            const int32_t* roi, const avb_image_desc* img, int64_t* offsets_out);
 int avb_download_batch(avb_fitter* fitter, double* data_clouds, int32_t* data_part_labels, int64_t* offsets);
+/* device time (ms) of [cloud_count_kernel, cloud_compact_kernel] of the last avb_upload_depth_batch (CUDA events) */
+int avb_last_cloud_ms(avb_fitter* fitter, float* ms2);
 int avb_download_results(avb_fitter* fitter, double* x_out, avb_stats* stats, double* cloud_out);
 int avb_synchronize(avb_fitter* fitter);
 /* device time of the kernels enqueued by the last avb_fit_resident, measured with CUDA events on the
