@@ -711,9 +711,15 @@ struct SolveSmem {
     double *xs, *xt, *tb, *Hs, *gs, *glo, *gcur, *delta, *dd, *wscr, *aa, *ycomp, *dcomp, *scr;
     int* iscr;
 };
+// table scratch of the solve: the joint tables of the retraction, earlier the joint rotations of the basis change and
+// the column-major panel of the factorisation (8 x ((P + 4) & ~3) + 8 doubles)
+__host__ __device__ inline int solve_tb_doubles(int J, int K) {
+    const int P = 3 + 3 * J + K, t = tables_doubles(J, K, true), pnl = 8 * ((P + 4) & ~3) + 8;
+    return t > pnl ? t : pnl;
+}
 __host__ __device__ inline size_t solve_smem_bytes(int J, int K, int C) {
     const int P = 3 + 3 * J + K, nx = 3 + 4 * J + K, D = 3 * (J - 1);
-    size_t d = 2 * ((nx + 1) & ~1) + tables_doubles(J, K, true) + (size_t)(P + 2) * P + 5 * ((P + 1) & ~1) + 8 * kNBsq + ((D + 1) & ~1) +
+    size_t d = 2 * ((nx + 1) & ~1) + solve_tb_doubles(J, K) + (size_t)(P + 2) * P + 5 * ((P + 1) & ~1) + 8 * kNBsq + ((D + 1) & ~1) +
                2 * (size_t)(C > 0 ? C : 1) * ((D + 8) & ~7) + 64;
     return d * 8 + 64 * 4 + 128;
 }
@@ -723,7 +729,7 @@ __device__ inline SolveSmem carve_solve(unsigned char* raw, const DevModel& M) {
     double* d = reinterpret_cast<double*>(raw);
     S.xs = d; d += (nx + 1) & ~1;
     S.xt = d; d += (nx + 1) & ~1;
-    S.tb = d; d += tables_doubles(M.J, M.K, true);
+    S.tb = d; d += solve_tb_doubles(M.J, M.K);
     S.Hs = d; d += (size_t)(P + 2) * P;   // + the augmented right-hand-side row (and one row of padding)
     S.gs = d; d += (P + 1) & ~1;
     S.glo = d; d += (P + 1) & ~1;
@@ -762,12 +768,19 @@ __device__ long long g_chol_cyc[4];
 #else
 #define CHOL_T(k) do { } while (0)
 #endif
-__device__ bool aug_cholesky(double* W, int P, int R, double* dinv, double* wscr) {
+__device__ bool aug_cholesky(double* W, int P, int R, double* dinv, double* wscr, double* panel) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nthr = blockDim.x;
 #ifdef AVB_UBENCH_PHASES
     long long tph = clock64();
 #endif
-    double* Lw = wscr + wid * (kNB * kNB);   // this warp's copy of L11 (diagonal: 1 / L_cc)
+    double* Lw = wscr + wid * (kNB * kNB);   // this warp's copy of L11 scaled by rows: L[c][k] / L[c][c], diagonal 1 / L[c][c]
+    // the current panel, column-major Lp[c][row - t0] (leading dimension ldp, 32-byte aligned): the trailing update
+    // reads four consecutive rows of a column with two 16-byte loads, conflict-free across a warp (the row-major
+    // matrix gives eight-way bank conflicts here: a 4-row tile step is a multiple of eight banks)
+    double* Lp = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(panel) + 31) & ~(uintptr_t)31);   // needs 8 * ldp + 4 doubles
+    const int ldp = (R + 3) & ~3;
+    for (int e = tid; e < kNB * ldp; e += nthr) Lp[e] = 0.0;
+    __syncthreads();
     const int r = lane & 7;
     for (int j0 = 0; j0 < P; j0 += kNB) {
         const int nb = min(kNB, P - j0);
@@ -796,26 +809,26 @@ __device__ bool aug_cholesky(double* W, int P, int R, double* dinv, double* wscr
         CHOL_T(0);
         if (lane < kNB) {
 #pragma unroll
-            for (int c = 0; c < kNB; ++c) Lw[lane * kNB + c] = (c < lane) ? a[c] : ((c == lane) ? myinv : 0.0);
+            for (int c = 0; c < kNB; ++c) Lw[lane * kNB + c] = (c < lane) ? a[c] * myinv : ((c == lane) ? myinv : 0.0);
             if (wid == 0 && lane < nb) dinv[j0 + lane] = myinv;
         }
         __syncwarp();
-        // ---- B: rows below the block, x L11^T = W[i][j0 .. j0+nb) ----
+        // ---- B: rows below the block, x L11^T = W[i][j0 .. j0+nb), column-oriented: one fma on the critical path
+        //      per column (x_c = w_c / L_cc - sum_k x_k L_ck / L_cc) ----
         const int t0 = j0 + nb;
         for (int i = t0 + tid; i < R; i += nthr) {
             double* wi = W + (size_t)i * P + j0;
             double x[kNB];
 #pragma unroll
-            for (int c = 0; c < kNB; ++c) {
-                if (c < nb) {
-                    double sacc = wi[c];
+            for (int c = 0; c < kNB; ++c) x[c] = (c < nb) ? wi[c] * Lw[c * kNB + c] : 0.0;
 #pragma unroll
-                    for (int k = 0; k < c; ++k) sacc -= x[k] * Lw[c * kNB + k];
-                    x[c] = sacc * Lw[c * kNB + c];
-                    wi[c] = x[c];
-                } else {
-                    x[c] = 0.0;
-                }
+            for (int k = 0; k < kNB - 1; ++k)
+#pragma unroll
+                for (int c = k + 1; c < kNB; ++c) x[c] = fma(-x[k], Lw[c * kNB + k], x[c]);
+#pragma unroll
+            for (int c = 0; c < kNB; ++c) {
+                if (c < nb) wi[c] = x[c];
+                Lp[c * ldp + (i - t0)] = x[c];
             }
         }
         __syncthreads();
@@ -842,32 +855,21 @@ __device__ bool aug_cholesky(double* W, int P, int R, double* dinv, double* wscr
                     tk = (t - ntri) % Tc;
                 }
                 const int i0 = t0 + 4 * ti, k0 = t0 + 4 * tk;
-                const double* li[4];
-                const double* lk[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    li[q] = W + (size_t)min(i0 + q, R - 1) * P + j0;
-                    lk[q] = W + (size_t)min(k0 + q, P - 1) * P + j0;
-                }
                 double acc[4][4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
 #pragma unroll
                     for (int u = 0; u < 4; ++u) acc[q][u] = 0.0;
 #pragma unroll
-                for (int c = 0; c < kNB; ++c) {
-                    if (c < nb) {
-                        double av[4], bv[4];
+                for (int c = 0; c < kNB; ++c) {   // columns beyond nb hold zeros
+                    const double2* pa = reinterpret_cast<const double2*>(Lp + c * ldp + 4 * ti);
+                    const double2* pb = reinterpret_cast<const double2*>(Lp + c * ldp + 4 * tk);
+                    const double2 a01 = pa[0], a23 = pa[1], b01 = pb[0], b23 = pb[1];
+                    const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            av[q] = li[q][c];
-                            bv[q] = lk[q][c];
-                        }
+                    for (int q = 0; q < 4; ++q)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) acc[q][u] = fma(av[q], bv[u], acc[q][u]);
-                    }
+                        for (int u = 0; u < 4; ++u) acc[q][u] = fma(av[q], bv[u], acc[q][u]);
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
@@ -1235,7 +1237,7 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
             S.Hs[(size_t)P * P + j] = -S.gcur[j];
         }
         __syncthreads();
-        bool ok = aug_cholesky(S.Hs, P, P + 1, S.glo, S.wscr);
+        bool ok = aug_cholesky(S.Hs, P, P + 1, S.glo, S.wscr, S.tb);
         phase_lap(a.q, 9, tp);
         if (ok) {
             if (tid < 32) warp_back_solve(S.Hs, S.glo, P, S.Hs + (size_t)P * P, S.delta);

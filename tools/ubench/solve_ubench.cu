@@ -15,18 +15,18 @@ __global__ void __launch_bounds__(256, 2) k_roles(const double* A, int P, long l
     double* W = reinterpret_cast<double*>(raw);
     double* dinv = W + (size_t)(P + 2) * P;
     double* wscr = dinv + 128;
-    double* x = wscr + 8 * 64;
+    double* x = wscr + 8 * 64 + 8 * 96 + 8;
     for (int i = threadIdx.x; i < (P + 1) * P; i += 256) W[i] = A[i];
     __syncthreads();
     if (blockIdx.x >= 148) {
         for (int r = 0; r < reps; ++r) {
             for (int i = threadIdx.x; i < (P + 1) * P; i += 256) W[i] = A[i];
             __syncthreads();
-            aug_cholesky(W, P, P + 1, dinv, wscr);
+            aug_cholesky(W, P, P + 1, dinv, wscr, wscr + 8 * 64);
         }
         return;
     }
-    aug_cholesky(W, P, P + 1, dinv, wscr);
+    aug_cholesky(W, P, P + 1, dinv, wscr, wscr + 8 * 64);
     long long tb = 0;
     for (int r = 0; r < reps * 3; ++r) {
         long long t1 = clock64();
@@ -43,13 +43,13 @@ __global__ void __launch_bounds__(256, 2) k_solve(const double* A, int P, long l
     double* W = reinterpret_cast<double*>(raw);   // (P+1) x P
     double* dinv = W + (size_t)(P + 2) * P;
     double* wscr = dinv + 128;
-    double* x = wscr + 8 * 64;
+    double* x = wscr + 8 * 64 + 8 * 96 + 8;
     long long tc = 0, tb = 0, tc0 = 0, tb0 = 0;
     for (int r = 0; r < reps; ++r) {
         for (int i = threadIdx.x; i < (P + 1) * P; i += 256) W[i] = A[i];
         __syncthreads();
         long long t0 = clock64();
-        bool ok = aug_cholesky(W, P, P + 1, dinv, wscr);
+        bool ok = aug_cholesky(W, P, P + 1, dinv, wscr, wscr + 8 * 64);
         long long t1 = clock64();
         if (threadIdx.x < 32) warp_back_solve(W, dinv, P, W + (size_t)P * P, x);
         __syncthreads();
@@ -131,7 +131,7 @@ int main() {
     cudaMalloc(&dh, 148 * 2 * 256 * 8);
     cudaMalloc(&dc, 148 * 2 * 4 * 8);
     cudaMemcpy(dA, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
-    const size_t smem = ((size_t)(P + 2) * P + 128 + 512 + 128) * 8;
+    const size_t smem = ((size_t)(P + 2) * P + 128 + 512 + 8 * 96 + 8 + 128) * 8;
     cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaStream_t s1, s2;
     cudaStreamCreate(&s1);
