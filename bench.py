@@ -344,9 +344,10 @@ def main():
     Lg = 3 + 3 * nj_mean + K
     part_b = 8.0 * (Lg * (Lg + 1) / 2 + Lg)             # chunk partial: upper triangle of J^T J + J^T r
     chunks = nm / 256.0 + 0.5 * len(groups) * F         # chunks per evaluation (256 slots, one ragged chunk per group)
-    rows_b = evals * nm * (4 + 24 + 24 + 12 * K + 37 + 2 + rec_b)
-    gram_b = evals * (nm * rec_b + chunks * part_b)
-    solve_b = evals * (chunks * part_b + F * 3 * 8.0 * 85 * 85)
+    full = evals - 1.0                                   # the last evaluation is cost-only: no records, no Gram, no H
+    rows_b = nm * (evals * (4 + 24 + 24 + 12 * K + 37 + 2) + full * rec_b)
+    gram_b = full * (nm * rec_b + chunks * part_b)
+    solve_b = full * (chunks * part_b + F * 3 * 8.0 * 85 * 85)
     alg_step = {                                         # algorithmic bytes per STEP of each kernel class
         "pose_visibility_kernel": F * (24.0 * V + V + 4 * V) + 24.0 * nvis,
         "nn_kernel": 32.0 * total + 24.0 * nvis,
