@@ -539,6 +539,13 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     dm.V = m->V; dm.J = m->J; dm.K = m->K; dm.F = m->F; dm.P = m->P; dm.nx = m->nx; dm.max_depth = m->max_depth;
     TRY(dev_put(ft, &dm.vt, m->vt));
     TRY(dev_put(ft, &dm.sd, m->sd));
+    {   // component-major copy for the thread-per-vertex sweep of pose_visibility_kernel (coalesced)
+        std::vector<float> sdt(m->sd.size());
+        const size_t V_ = (size_t)m->V, CK = (size_t)3 * m->K;
+        for (size_t v = 0; v < V_; ++v)
+            for (size_t q = 0; q < CK; ++q) sdt[q * V_ + v] = m->sd[v * CK + q];
+        TRY(dev_put(ft, &dm.sdT, sdt));
+    }
     TRY(dev_put(ft, &dm.sk_w, m->sk_w));
     TRY(dev_put(ft, &dm.sk_j, m->sk_j));
     TRY(dev_put(ft, &dm.sk_n, m->sk_n));

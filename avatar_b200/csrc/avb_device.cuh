@@ -20,6 +20,7 @@ struct DevModel {
     int V, J, K, F, P, nx, max_depth;
     const double* vt;          // [3V]        baseCloud
     const float* sd;           // [V][3][K]   keyClouds rows of vertex v (fp32 storage, fp64 maths)
+    const float* sdT;          // [3][K][V]   the same, component-major (coalesced when one thread owns one vertex)
     const double* sk_w;        // [V][4]      assignedJoints weights (desc), 0 padded
     const uint8_t* sk_j;       // [V][4]      assignedJoints joints
     const uint8_t* sk_n;       // [V]

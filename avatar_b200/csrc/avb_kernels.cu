@@ -24,9 +24,9 @@
 namespace avb {
 
 // ---------------------------------------------------------------------------------------------
-// K1: forward SMPL + visibility + per-part compaction.  grid = batch, block = 256
+// K1: forward SMPL + visibility + per-part compaction.  grid = batch, block = 512 (two CTAs per SM: a lane of <= 296 frames is one wave)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 pose_visibility_kernel(DevModel M, DevParts Pt, PoseArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int f = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
@@ -43,13 +43,14 @@ pose_visibility_kernel(DevModel M, DevParts Pt, PoseArgs a) {
 
     double* cloud = a.cloud + (size_t)f * 3 * V;
     const double* w = xs + 3 + 4 * J;
+#pragma unroll 2
     for (int v = tid; v < V; v += nt) {
         // shape blend (Avatar.cpp:26) then LBS with the assignedJoints weights (AvatarOptimizer.cpp:507-514)
-        const float* sd = M.sd + (size_t)v * 3 * K;
+        const float* sd = M.sdT + v;   // component-major: consecutive threads read consecutive addresses
         double v0[3];
         for (int c = 0; c < 3; ++c) {
             double s = 0;
-            for (int k = 0; k < K; ++k) s += (double)sd[c * K + k] * w[k];
+            for (int k = 0; k < K; ++k) s += (double)sd[(size_t)(c * K + k) * V] * w[k];
             v0[c] = M.vt[3 * (size_t)v + c] + s;
         }
         double x0 = 0, x1 = 0, x2 = 0;
@@ -80,7 +81,8 @@ pose_visibility_kernel(DevModel M, DevParts Pt, PoseArgs a) {
     __threadfence_block();
     __syncthreads();
     if (a.enable_occlusion) {
-        for (int t = tid; t < M.F; t += nt) {
+#pragma unroll 4
+        for (int t = tid; t < M.F; t += nt) {   // unrolled: the index -> position gathers of four faces in flight
             const int i1 = M.faces[3 * t], i2 = M.faces[3 * t + 1], i3 = M.faces[3 * t + 2];
             const double p1x = cloud[3 * (size_t)i1], p1y = cloud[3 * (size_t)i1 + 1];
             const double p2x = cloud[3 * (size_t)i2], p2y = cloud[3 * (size_t)i2 + 1];
@@ -269,7 +271,7 @@ size_t pose_smem_bytes(int V, int J, int K) {
 
 cudaError_t launch_pose_visibility(const DevModel& M, const DevParts& Pt, const PoseArgs& a, int batch, cudaStream_t st) {
     const size_t smem = pose_smem_bytes(M.V, M.J, M.K);
-    pose_visibility_kernel<<<batch, 256, smem, st>>>(M, Pt, a);
+    pose_visibility_kernel<<<batch, 512, smem, st>>>(M, Pt, a);
     return cudaGetLastError();
 }
 

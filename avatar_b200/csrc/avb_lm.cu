@@ -116,7 +116,7 @@ __host__ __device__ inline int group_L(int nj, int K) { return 3 + 3 * nj + K; }
 // ---------------------------------------------------------------------------------------------
 // lm_prep_kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 lm_prep_kernel(DevModel M, DevParts Pt, LmBuf a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int f = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
@@ -1438,7 +1438,7 @@ size_t lm_gram_smem(const DevModel& M, int max_nj, int chunk_verts, bool tensor)
 }
 
 cudaError_t launch_lm_prep(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, cudaStream_t st) {
-    lm_prep_kernel<<<batch, 256, lm_prep_smem(M), st>>>(M, Pt, a);
+    lm_prep_kernel<<<batch, 512, lm_prep_smem(M), st>>>(M, Pt, a);
     return cudaGetLastError();
 }
 
