@@ -118,6 +118,8 @@ struct avb_fitter {
     float* d_depth = nullptr; uint8_t* d_parts = nullptr; int* d_roi = nullptr; int* d_strip_count = nullptr;
     long long* d_strip_offset = nullptr; int* d_bad_label = nullptr;
     size_t img_cap = 0, strip_cap = 0;
+    RTreeNode* d_rt_nodes = nullptr; uint8_t* d_rt_leaf = nullptr; int rt_nodes = 0, rt_leaves = 0, rt_parts = 0;
+    cudaEvent_t rev[2] = {};   // around the RTree kernels of the last prediction
     cudaEvent_t cev[4] = {};   // around cloud_count_kernel and cloud_compact_kernel of the last avb_upload_depth_batch
     std::vector<int> h_strip_count; std::vector<long long> h_strip_offset;
     // state of the uploaded batch
@@ -483,6 +485,8 @@ void avb_fitter_destroy(avb_fitter* ft) {
     cudaFree(ft->d_depth); cudaFree(ft->d_parts); cudaFree(ft->d_roi); cudaFree(ft->d_strip_count);
     cudaFree(ft->d_strip_offset); cudaFree(ft->d_bad_label);
     for (auto& e : ft->cev) if (e) cudaEventDestroy(e);
+    for (auto& e : ft->rev) if (e) cudaEventDestroy(e);
+    cudaFree(ft->d_rt_nodes); cudaFree(ft->d_rt_leaf);
     if (ft->copy_stream) cudaStreamDestroy(ft->copy_stream);
     if (ft->stream) cudaStreamDestroy(ft->stream);
     delete ft;
@@ -742,10 +746,75 @@ int avb_upload_batch(avb_fitter* ft, int32_t batch, const double* clouds, const 
     return AVB_OK;
 }
 
+namespace {
+// image staging of avb_upload_depth_batch / avb_rtree_predict_batch, grown on demand
+int ensure_image_staging(avb_fitter* ft, size_t npx, size_t strip_slots) {
+    if (npx <= ft->img_cap && strip_slots <= ft->strip_cap) return AVB_OK;
+    npx = std::max(npx, ft->img_cap);
+    strip_slots = std::max(strip_slots, ft->strip_cap);
+    CUDA_TRY(cudaStreamSynchronize(ft->stream));
+    cudaFree(ft->d_depth); cudaFree(ft->d_parts); cudaFree(ft->d_roi); cudaFree(ft->d_strip_count);
+    cudaFree(ft->d_strip_offset); cudaFree(ft->d_bad_label);
+    ft->d_depth = nullptr; ft->d_parts = nullptr; ft->d_roi = nullptr; ft->d_strip_count = nullptr;
+    ft->d_strip_offset = nullptr; ft->d_bad_label = nullptr;
+    ft->img_cap = ft->strip_cap = 0;
+    if (cudaMalloc(&ft->d_depth, npx * 4) != cudaSuccess || cudaMalloc(&ft->d_parts, npx) != cudaSuccess ||
+        cudaMalloc(&ft->d_roi, (size_t)ft->max_batch * 16) != cudaSuccess ||
+        cudaMalloc(&ft->d_strip_count, std::max<size_t>(strip_slots, 1) * 4) != cudaSuccess ||
+        cudaMalloc(&ft->d_strip_offset, std::max<size_t>(strip_slots, 1) * 8) != cudaSuccess ||
+        cudaMalloc(&ft->d_bad_label, (size_t)ft->max_batch * 4) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(AVB_ERR_CUDA, "cudaMalloc of the image staging buffers failed");
+    }
+    ft->img_cap = npx;
+    ft->strip_cap = strip_slots;
+    return AVB_OK;
+}
+
+// RTree::predictBest + upscaleGrid on the depth images resident in d_depth -> d_parts (roi already in d_roi if given)
+int enqueue_rtree(avb_fitter* ft, int batch, int width, int height, const int32_t* roi_host, bool roi_on_device, int interval,
+                  bool fill) {
+    if (!ft->d_rt_nodes) return fail(AVB_ERR_INVALID, "no decision tree: call avb_fitter_set_rtree first");
+    if (interval <= 0) return fail(AVB_ERR_INVALID, "RTree interval must be positive");
+    cudaStream_t st = ft->stream;
+    int max_w = width, max_h = height;
+    if (roi_host) {
+        max_w = max_h = 0;
+        for (int f = 0; f < batch; ++f) {
+            max_w = std::max(max_w, roi_host[4 * f + 2] - roi_host[4 * f] + 1);
+            max_h = std::max(max_h, roi_host[4 * f + 3] - roi_host[4 * f + 1] + 1);
+        }
+        max_w = std::min(std::max(max_w, 0), width + interval);
+        max_h = std::min(std::max(max_h, 0), height + interval);
+    }
+    RTreeArgs a{};
+    a.nodes = ft->d_rt_nodes;
+    a.leaf_best = ft->d_rt_leaf;
+    a.depth = ft->d_depth;
+    a.parts = ft->d_parts;
+    a.roi = roi_on_device ? ft->d_roi : nullptr;
+    a.width = width; a.height = height; a.interval = interval;
+    if (!ft->rev[0])
+        for (auto& e : ft->rev) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaMemsetAsync(ft->d_parts, 0xFF, (size_t)batch * width * height, st));   // result.setTo(255)
+    CUDA_TRY(cudaEventRecord(ft->rev[0], st));
+    const long long cells = (long long)((max_w + interval - 1) / interval) * (max_h / interval + 1);
+    CUDA_TRY(launch_rtree_predict(a, batch, (int)std::min<long long>(cells, 1 << 30), st));
+    if (fill && interval > 1) {
+        const long long px = (long long)(max_w + interval) * (max_h + 1);
+        CUDA_TRY(launch_rtree_upscale(a, batch, (int)std::min<long long>(px, 1 << 30), st));
+    }
+    CUDA_TRY(cudaEventRecord(ft->rev[1], st));
+    return AVB_OK;
+}
+}  // namespace
+
 /* -------- cloud construction on the device (demo.cpp:215-250, Calibration.cpp:83-95) -------- */
 int avb_upload_depth_batch(avb_fitter* ft, int32_t batch, const float* depth, const uint8_t* parts, const int32_t* roi,
                            const avb_image_desc* img, int64_t* offsets_out) {
-    if (!ft || !depth || !parts || !img || batch <= 0) return fail(AVB_ERR_INVALID, "null argument or empty batch");
+    if (!ft || !depth || !img || batch <= 0) return fail(AVB_ERR_INVALID, "null argument or empty batch");
+    if (!parts && !ft->d_rt_nodes) return fail(AVB_ERR_INVALID, "parts == NULL needs a decision tree (avb_fitter_set_rtree)");
+    if (!parts && img->rtree_interval <= 0) return fail(AVB_ERR_INVALID, "rtree_interval must be positive when parts == NULL");
     if (batch > ft->max_batch) return fail(AVB_ERR_CAPACITY, "batch exceeds fitter capacity");
     if (img->width <= 0 || img->height <= 0 || img->interval <= 0) return fail(AVB_ERR_INVALID, "bad image description");
     if (img->num_parts <= 0 || img->num_parts > 255) return fail(AVB_ERR_INVALID, "num_parts must be in 1..255");
@@ -755,26 +824,18 @@ int avb_upload_depth_batch(avb_fitter* ft, int32_t batch, const float* depth, co
     const size_t px = (size_t)img->width * img->height, npx = px * batch;
     const int rows_per_strip = cloud_strip_rows();
     const int strips = ((img->height + img->interval - 1) / img->interval + rows_per_strip - 1) / rows_per_strip;
-    if (npx > ft->img_cap || (size_t)batch * strips > ft->strip_cap) {   // (re)allocate the image staging
-        CUDA_TRY(cudaStreamSynchronize(st));
-        cudaFree(ft->d_depth); cudaFree(ft->d_parts); cudaFree(ft->d_roi); cudaFree(ft->d_strip_count);
-        cudaFree(ft->d_strip_offset); cudaFree(ft->d_bad_label);
-        ft->d_depth = nullptr; ft->d_parts = nullptr; ft->d_roi = nullptr; ft->d_strip_count = nullptr;
-        ft->d_strip_offset = nullptr; ft->d_bad_label = nullptr;
-        ft->img_cap = ft->strip_cap = 0;
-        const size_t sc = (size_t)ft->max_batch * strips;
-        if (cudaMalloc(&ft->d_depth, npx * 4) != cudaSuccess || cudaMalloc(&ft->d_parts, npx) != cudaSuccess ||
-            cudaMalloc(&ft->d_roi, (size_t)ft->max_batch * 16) != cudaSuccess || cudaMalloc(&ft->d_strip_count, sc * 4) != cudaSuccess ||
-            cudaMalloc(&ft->d_strip_offset, sc * 8) != cudaSuccess || cudaMalloc(&ft->d_bad_label, (size_t)ft->max_batch * 4) != cudaSuccess) {
-            cudaGetLastError();
-            return fail(AVB_ERR_CUDA, "cudaMalloc of the image staging buffers failed");
-        }
-        ft->img_cap = npx;
-        ft->strip_cap = sc;
+    {
+        int rc0 = ensure_image_staging(ft, npx, (size_t)ft->max_batch * strips);
+        if (rc0 != AVB_OK) return rc0;
     }
     CUDA_TRY(cudaMemcpyAsync(ft->d_depth, depth, npx * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(ft->d_parts, parts, npx, cudaMemcpyHostToDevice, st));
     if (roi) CUDA_TRY(cudaMemcpyAsync(ft->d_roi, roi, (size_t)batch * 16, cudaMemcpyHostToDevice, st));
+    if (parts) {
+        CUDA_TRY(cudaMemcpyAsync(ft->d_parts, parts, npx, cudaMemcpyHostToDevice, st));
+    } else {   // demo.cpp:198-200: labels from the decision tree, on the device
+        int rcr = enqueue_rtree(ft, batch, img->width, img->height, roi, roi != nullptr, img->rtree_interval, true);
+        if (rcr != AVB_OK) return rcr;
+    }
     CUDA_TRY(cudaMemsetAsync(ft->d_bad_label, 0, (size_t)batch * 4, st));
     CloudArgs a{};
     a.depth = ft->d_depth;
@@ -820,6 +881,59 @@ int avb_upload_depth_batch(avb_fitter* ft, int32_t batch, const float* depth, co
     CUDA_TRY(launch_cloud_compact(a, strips, batch, st));
     CUDA_TRY(cudaEventRecord(ft->cev[3], st));
     if (offsets_out) std::copy(off.begin(), off.end(), offsets_out);
+    return AVB_OK;
+}
+
+int avb_fitter_set_rtree(avb_fitter* ft, const avb_rtree_desc* t) {
+    if (!ft || !t) return fail(AVB_ERR_INVALID, "null argument");
+    if (t->num_nodes <= 0 || t->num_leaves <= 0 || !t->u || !t->v || !t->thresh || !t->lnode || !t->rnode || !t->leafid || !t->leaf_best)
+        return fail(AVB_ERR_INVALID, "incomplete decision tree");
+    std::vector<RTreeNode> nodes((size_t)t->num_nodes);
+    for (int i = 0; i < t->num_nodes; ++i) {
+        RTreeNode& n = nodes[i];
+        n.ux = t->u[2 * i]; n.uy = t->u[2 * i + 1]; n.vx = t->v[2 * i]; n.vy = t->v[2 * i + 1];
+        n.thresh = t->thresh[i];
+        n.lnode = t->lnode[i]; n.rnode = t->rnode[i]; n.leafid = t->leafid[i];
+        if (n.leafid < -1 || n.leafid >= t->num_leaves) return fail(AVB_ERR_INVALID, "leaf id out of range");
+        if (n.leafid == -1 && (n.lnode <= i || n.lnode >= t->num_nodes || n.rnode <= i || n.rnode >= t->num_nodes))
+            return fail(AVB_ERR_INVALID, "child index out of range (children must follow their parent)");
+    }
+    CUDA_TRY(cudaSetDevice(ft->device));
+    CUDA_TRY(cudaStreamSynchronize(ft->stream));
+    cudaFree(ft->d_rt_nodes); cudaFree(ft->d_rt_leaf);
+    ft->d_rt_nodes = nullptr; ft->d_rt_leaf = nullptr;
+    CUDA_TRY(cudaMalloc(&ft->d_rt_nodes, nodes.size() * sizeof(RTreeNode)));
+    CUDA_TRY(cudaMalloc(&ft->d_rt_leaf, (size_t)t->num_leaves));
+    CUDA_TRY(cudaMemcpy(ft->d_rt_nodes, nodes.data(), nodes.size() * sizeof(RTreeNode), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(ft->d_rt_leaf, t->leaf_best, (size_t)t->num_leaves, cudaMemcpyHostToDevice));
+    ft->rt_nodes = t->num_nodes; ft->rt_leaves = t->num_leaves; ft->rt_parts = t->num_parts;
+    return AVB_OK;
+}
+
+int avb_rtree_predict_batch(avb_fitter* ft, int32_t batch, const float* depth, int32_t width, int32_t height, const int32_t* roi,
+                            int32_t interval, int32_t fill_in_gaps, uint8_t* parts_out) {
+    if (!ft || !depth || !parts_out || batch <= 0 || width <= 0 || height <= 0) return fail(AVB_ERR_INVALID, "null argument or empty batch");
+    if (batch > ft->max_batch) return fail(AVB_ERR_CAPACITY, "batch exceeds fitter capacity");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    const size_t npx = (size_t)width * height * batch;
+    int rc = ensure_image_staging(ft, npx, 0);
+    if (rc != AVB_OK) return rc;
+    cudaStream_t st = ft->stream;
+    CUDA_TRY(cudaMemcpyAsync(ft->d_depth, depth, npx * 4, cudaMemcpyHostToDevice, st));
+    if (roi) CUDA_TRY(cudaMemcpyAsync(ft->d_roi, roi, (size_t)batch * 16, cudaMemcpyHostToDevice, st));
+    rc = enqueue_rtree(ft, batch, width, height, roi, roi != nullptr, interval, fill_in_gaps != 0);
+    if (rc != AVB_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(parts_out, ft->d_parts, npx, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return AVB_OK;
+}
+
+int avb_last_rtree_ms(avb_fitter* ft, float* ms) {
+    if (!ft || !ms) return fail(AVB_ERR_INVALID, "null argument");
+    if (!ft->rev[0]) return fail(AVB_ERR_INVALID, "no RTree prediction yet");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    CUDA_TRY(cudaEventSynchronize(ft->rev[1]));
+    CUDA_TRY(cudaEventElapsedTime(ms, ft->rev[0], ft->rev[1]));
     return AVB_OK;
 }
 

@@ -54,6 +54,19 @@ struct CloudArgs {  // data-cloud construction from depth + part-label images (a
     int* labels;                 // [total points] out
 };
 
+struct RTreeNode {   // RTree::RNode (include/RTree.h:28-41) packed into one 32-byte sector
+    float ux, uy, vx, vy, thresh;
+    int lnode, rnode, leafid;   // leafid == -1: internal node
+};
+struct RTreeArgs {   // RTree::predictBest on images (avb_rtree.cu)
+    const RTreeNode* nodes;
+    const uint8_t* leaf_best;    // [leaves] leafBestMatch
+    const float* depth;          // [batch][height][width]
+    uint8_t* parts;              // [batch][height][width] out (255 = not predicted)
+    const int* roi;              // nullable [batch][4] top_left.x, top_left.y, bot_right.x, bot_right.y
+    int width, height, interval;
+};
+
 struct LmState {  // per-frame Levenberg-Marquardt state, lives in HBM between the kernels of one ICP iteration
     double cost, radius, decrease, Qsum, sbp, sbs, initial_cost, model_change;
     int done, iters, accepted, ncorr, nmatched, nchunks, evals, nslots;   // nslots: record slots incl. alignment gaps
@@ -103,6 +116,8 @@ struct LmBuf {
     FlowQueue q;
 };
 
+cudaError_t launch_rtree_predict(const RTreeArgs& a, int batch, int max_box_pixels, cudaStream_t st);
+cudaError_t launch_rtree_upscale(const RTreeArgs& a, int batch, int max_box_pixels, cudaStream_t st);
 int cloud_strip_rows();
 cudaError_t launch_cloud_count(const CloudArgs& a, int strips, int batch, cudaStream_t st);
 cudaError_t launch_cloud_compact(const CloudArgs& a, int strips, int batch, cudaStream_t st);

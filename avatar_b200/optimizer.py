@@ -63,19 +63,45 @@ class Fitter:
         self.total_points = int(offsets[-1] - offsets[0])
         check(lib.avb_upload_batch(self.handle, self.batch, ptr(clouds), ptr(labels), ptr(offsets)))
 
-    def upload_depth(self, depth, parts, intrin, num_parts, roi=None, interval=1):
+    def set_rtree(self, tree, num_parts):
+        """give the fitter a decision tree (RTree::nodes + leafBestMatch as arrays, see avb_rtree_desc)"""
+        t = {k: np.ascontiguousarray(tree[k], dtype=d) for k, d in (("u", np.float32), ("v", np.float32), ("thresh", np.float32),
+                                                                  ("lnode", np.int32), ("rnode", np.int32), ("leafid", np.int32),
+                                                                  ("leaf_best", np.uint8))}
+        d = _lib.RTreeDesc(len(t["thresh"]), len(t["leaf_best"]), int(num_parts), *(t[k].ctypes.data for k in
+                           ("u", "v", "thresh", "lnode", "rnode", "leafid", "leaf_best")))
+        check(lib.avb_fitter_set_rtree(self.handle, C.byref(d)))
+
+    def rtree_predict(self, depth, roi=None, interval=1, fill_in_gaps=True):
+        """RTree::predictBest on a batch of depth images [B,H,W] -> labels [B,H,W] uint8 (255 = not predicted)"""
+        depth = np.ascontiguousarray(depth, dtype=np.float32)
+        if depth.ndim == 2:
+            depth = depth[None]
+        B, H, W = depth.shape
+        roi_a = None if roi is None else np.ascontiguousarray(roi, dtype=np.int32).reshape(B, 4)
+        out = np.zeros((B, H, W), dtype=np.uint8)
+        check(lib.avb_rtree_predict_batch(self.handle, B, ptr(depth), W, H, ptr(roi_a), int(interval), int(bool(fill_in_gaps)),
+                                          ptr(out)))
+        return out
+
+    def rtree_ms(self):
+        ms = C.c_float()
+        check(lib.avb_last_rtree_ms(self.handle, C.byref(ms)))
+        return ms.value
+
+    def upload_depth(self, depth, parts, intrin, num_parts, roi=None, interval=1, rtree_interval=2):
         """Build the batch's data clouds on the device from depth [B,H,W] float32 (metres) and body-part label images
         [B,H,W] uint8 (255 = background), as demo.cpp:215-250 + CameraIntrin::depthToXYZ do on the host.
         intrin = (fx, cx, fy, cy); roi: optional [B,4] int32 (x0, y0, x1, y1 inclusive).  Returns the offsets."""
         depth = np.ascontiguousarray(depth, dtype=np.float32)
-        parts = np.ascontiguousarray(parts, dtype=np.uint8)
         if depth.ndim == 2:
-            depth, parts = depth[None], parts[None]
-        assert depth.shape == parts.shape
+            depth = depth[None]
+        if parts is not None:   # parts=None: labels from the fitter's decision tree (set_rtree), on the device
+            parts = np.ascontiguousarray(parts, dtype=np.uint8).reshape(depth.shape)
         B, H, W = depth.shape
         roi_a = None if roi is None else np.ascontiguousarray(roi, dtype=np.int32).reshape(B, 4)
         img = _lib.ImageDesc(W, H, float(intrin[0]), float(intrin[1]), float(intrin[2]), float(intrin[3]), int(interval),
-                             int(num_parts))
+                             int(num_parts), int(rtree_interval))
         off = np.zeros(B + 1, dtype=np.int64)
         self._keep = (depth, parts, roi_a)
         check(lib.avb_upload_depth_batch(self.handle, B, ptr(depth), ptr(parts), ptr(roi_a), C.byref(img), ptr(off)))

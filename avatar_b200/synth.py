@@ -88,3 +88,31 @@ def backproject(depth, part, fx=FX, fy=FY, cx=CX, cy=CY, interval=1):
     n = lib.avb_synth_backproject(ptr(depth), ptr(part), w, h, fx, fy, cx, cy, interval, ptr(pts), ptr(lab), cap)
     assert n >= 0
     return pts[:n].copy(), lab[:n].copy()
+
+
+def random_rtree(rng, num_parts, depth_levels=12, leaf_prob=0.12):
+    """a random decision tree in the layout of RTree::nodes / leafBestMatch (include/RTree.h:28-41): probe offsets in
+    pixel-metres (a few to ~150 px at 1 m), thresholds around zero, children after their parent.  Harness data: the
+    reference ships no trained tree."""
+    u, v, thresh, lnode, rnode, leafid, leaf_best = [], [], [], [], [], [], []
+
+    def new_node():
+        u.append([0.0, 0.0]); v.append([0.0, 0.0]); thresh.append(0.0); lnode.append(-1); rnode.append(-1); leafid.append(-1)
+        return len(thresh) - 1
+    frontier = [(new_node(), 0)]
+    while frontier:
+        nxt = []
+        for n, d in frontier:
+            if d >= depth_levels or (d >= 3 and rng.random() < leaf_prob):
+                leafid[n] = len(leaf_best)
+                leaf_best.append(int(rng.integers(0, num_parts)))
+                continue
+            u[n] = list(rng.normal(0.0, 60.0, 2))
+            v[n] = list(rng.normal(0.0, 60.0, 2)) if rng.random() < 0.8 else [0.0, 0.0]
+            thresh[n] = float(rng.normal(0.0, 0.4)) if rng.random() < 0.7 else float(rng.normal(0.0, 8.0))
+            lnode[n], rnode[n] = new_node(), new_node()
+            nxt += [(lnode[n], d + 1), (rnode[n], d + 1)]
+        frontier = nxt
+    return dict(u=np.array(u, np.float32), v=np.array(v, np.float32), thresh=np.array(thresh, np.float32),
+                lnode=np.array(lnode, np.int32), rnode=np.array(rnode, np.int32), leafid=np.array(leafid, np.int32),
+                leaf_best=np.array(leaf_best, np.uint8))

@@ -174,16 +174,43 @@ int avb_fit_resident(avb_fitter* fitter, const double* x_in, const avb_options* 
  * bit-identical to the host loop.  A label >= num_parts other than 255 is an error (the reference prints FATAL and
  * exits, demo.cpp:232-239).  Afterwards the batch is resident exactly as after avb_upload_batch: call
  * avb_fit_resident / avb_download_results; offsets_out (nullable, batch + 1 entries) receives the per-frame point
- * offsets; avb_download_batch reads the constructed clouds back (tests). */
+ * offsets; avb_download_batch reads the constructed clouds back (tests).
+ * parts == NULL: the labels are predicted on the device with the decision tree given to avb_fitter_set_rtree, as
+ * demo.cpp:198-200 does on the host (RTree::predictBest(depth, threads, rtree_interval, topLeft, botRight) with gap
+ * filling), so only the depth image crosses PCIe. */
 typedef struct avb_image_desc {
     int32_t width, height;
     float fx, cx, fy, cy;   /* CameraIntrin, in the order of its intrin[] file format (Calibration.cpp:68-74) */
     int32_t interval;       /* pixel stride in both directions (demo.cpp `interval`) */
     int32_t num_parts;      /* rtree.numParts */
+    int32_t rtree_interval; /* parts == NULL only: stride of RTree::predictBest (demo.cpp:198 uses 2); gaps are filled */
 } avb_image_desc;
 int avb_upload_depth_batch(avb_fitter* fitter, int32_t batch, const float* depth, const uint8_t* parts,
                            const int32_t* roi, const avb_image_desc* img, int64_t* offsets_out);
 int avb_download_batch(avb_fitter* fitter, double* data_clouds, int32_t* data_part_labels, int64_t* offsets);
+/* Body-part label prediction on the device: the image form of RTree::predictBest
+ * (RTree.cpp:3184-3262) with its gap filling (upscaleGrid, RTree.cpp:70-100).  The tree is given as the arrays of
+ * RTree::nodes (include/RTree.h:28-41: u, v [nodes][2], thresh, lnode, rnode, leafid with -1 = internal) and
+ * leafBestMatch ([leaves], RTree.cpp:3455-3463); file parsing (RTree::loadFile) stays with the caller.
+ * avb_rtree_predict_batch: depth [batch][height][width] float (0 = no data) in, labels [batch][height][width] uint8
+ * out (255 = not predicted), roi = top_left / bot_right per frame (NULL = whole image), labels bit-exact.  The
+ * reference never predicts the first row of the box (its row loop pre-increments, RTree.cpp:3196-3199); neither does
+ * this.  postProcess (connected components, RTree.cpp:3422-3450) is not part of it. */
+typedef struct avb_rtree_desc {
+    int32_t num_nodes, num_leaves, num_parts;
+    const float* u;            /* [num_nodes][2] */
+    const float* v;            /* [num_nodes][2] */
+    const float* thresh;       /* [num_nodes] */
+    const int32_t* lnode;      /* [num_nodes] */
+    const int32_t* rnode;      /* [num_nodes] */
+    const int32_t* leafid;     /* [num_nodes], -1 = internal node */
+    const uint8_t* leaf_best;  /* [num_leaves] */
+} avb_rtree_desc;
+int avb_fitter_set_rtree(avb_fitter* fitter, const avb_rtree_desc* tree);
+int avb_rtree_predict_batch(avb_fitter* fitter, int32_t batch, const float* depth, int32_t width, int32_t height,
+                            const int32_t* roi, int32_t interval, int32_t fill_in_gaps, uint8_t* parts_out);
+/* device time (ms) of the last RTree prediction (predict + gap filling kernels) */
+int avb_last_rtree_ms(avb_fitter* fitter, float* ms);
 /* device time (ms) of [cloud_count_kernel, cloud_compact_kernel] of the last avb_upload_depth_batch (CUDA events) */
 int avb_last_cloud_ms(avb_fitter* fitter, float* ms2);
 int avb_download_results(avb_fitter* fitter, double* x_out, avb_stats* stats, double* cloud_out);

@@ -1516,4 +1516,64 @@ int64_t orc_build_cloud(const float* depth, const uint8_t* parts, int width, int
     }
     return cnz;
 }
+
+/* RTree::predictBest on an image + upscaleGrid (see header) */
+void orc_rtree_predict(const float* depth, int width, int height, int num_nodes, const float* u, const float* v,
+                       const float* thresh, const int32_t* lnode, const int32_t* rnode, const int32_t* leafid,
+                       const uint8_t* leaf_best, const int32_t* roi, int interval, int fill_in_gaps, uint8_t* out) {
+    (void)num_nodes;
+    const float BACKGROUND_DEPTH = 20.f;   // RTree.cpp:325
+    std::fill(out, out + (size_t)width * height, (uint8_t)255);   // result.setTo(255), RTree.cpp:3189
+    int tlx = 0, tly = 0, brx = width - 1, bry = height - 1;      // bot_right == -1: whole image (:3190-3193)
+    if (roi) { tlx = roi[0]; tly = roi[1]; brx = roi[2]; bry = roi[3]; }
+    // RTree.cpp:3196-3199: r = (row += interval) with row starting at top_left.y
+    for (int r = tly + interval; r <= bry; r += interval) {
+        if (r < 0 || r >= height) continue;
+        const float* inPtr = depth + (size_t)r * width;
+        for (int c = tlx; c <= brx; c += interval) {
+            if (c < 0 || c >= width) continue;
+            if (inPtr[c] == 0.f) continue;
+            int nodeid = 0;
+            const float sampleDepth = inPtr[c];
+            while (leafid[nodeid] == -1) {
+                // Eigen Vector2f / float: component-wise division; std::round: half away from zero (:3209-3217)
+                const float utx = u[2 * nodeid] / sampleDepth, uty = u[2 * nodeid + 1] / sampleDepth;
+                const float vtx = v[2 * nodeid] / sampleDepth, vty = v[2 * nodeid + 1] / sampleDepth;
+                const int32_t ux = static_cast<int32_t>(std::round(utx)) + c, uy = static_cast<int32_t>(std::round(uty)) + r;
+                const int32_t vx = static_cast<int32_t>(std::round(vtx)) + c, vy = static_cast<int32_t>(std::round(vty)) + r;
+                float zu, zv;
+                if (ux < tlx || uy < tly || ux > brx || uy > bry) {
+                    zu = BACKGROUND_DEPTH;
+                } else {
+                    zu = depth[(size_t)uy * width + ux];
+                    if (zu == 0.0) zu = BACKGROUND_DEPTH;
+                }
+                if (vx < tlx || vy < tly || vx > brx || vy > bry) {
+                    zv = BACKGROUND_DEPTH;
+                } else {
+                    zv = depth[(size_t)vy * width + vx];
+                    if (zv == 0.0) zv = BACKGROUND_DEPTH;
+                }
+                nodeid = (zu - zv < thresh[nodeid]) ? lnode[nodeid] : rnode[nodeid];
+            }
+            out[(size_t)r * width + c] = leaf_best[leafid[nodeid]];
+        }
+    }
+    if (fill_in_gaps && interval > 1) {   // upscaleGrid, RTree.cpp:70-100
+        for (int rr = tly + interval; rr <= bry; rr += interval) {
+            if (rr < 0 || rr >= height) continue;
+            const uint8_t* ptrRef = out + (size_t)rr * width;
+            for (int r = rr; r < rr + interval; ++r) {
+                if (r > bry) break;
+                if (r >= height) break;
+                uint8_t* ptr = out + (size_t)r * width;
+                for (int cc = tlx; cc <= brx; cc += interval) {
+                    if (cc < 0 || cc >= width) continue;
+                    const uint8_t val = ptrRef[cc];
+                    for (int x = cc; x < cc + interval && x < width; ++x) ptr[x] = val;   // memset(ptr + cc, val, interval)
+                }
+            }
+        }
+    }
+}
 }  // extern "C"

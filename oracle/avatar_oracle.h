@@ -112,6 +112,15 @@ int orc_optimize(const orc_optimizer*, const double* data, const int32_t* labels
 int64_t orc_build_cloud(const float* depth, const uint8_t* parts, int width, int height, const float* intrin,
                         const int32_t* roi, int interval, int num_parts, double* cloud, int32_t* labels,
                         int64_t capacity);
+/* Image form of RTree::predictBest (RTree.cpp:3184-3262) with upscaleGrid (RTree.cpp:70-100) when fill_in_gaps and
+ * interval > 1.  Tree = the arrays of RTree::nodes (u, v [nodes][2], thresh, lnode, rnode, leafid
+ * with -1 = internal) and leafBestMatch.  roi = {top_left.x, top_left.y, bot_right.x, bot_right.y} or NULL (whole
+ * image).  out: [height][width] uint8, 255 where nothing is predicted.  The reference's row loop pre-increments, so
+ * the first row of the box is never predicted; its memset in upscaleGrid may run past bot_right.x (kept) and past the
+ * end of the row (clamped to the image here). */
+void orc_rtree_predict(const float* depth, int width, int height, int num_nodes, const float* u, const float* v,
+                       const float* thresh, const int32_t* lnode, const int32_t* rnode, const int32_t* leafid,
+                       const uint8_t* leaf_best, const int32_t* roi, int interval, int fill_in_gaps, uint8_t* out);
 /* functional stand-in for AvatarRenderer::renderDepth / renderPartMask used only by tests */
 int orc_param_dim(const orc_optimizer*);   /* 3 + 4J + K */
 int orc_tangent_dim(const orc_optimizer*); /* 3 + 3J + K */

@@ -62,6 +62,7 @@ _sig = {
     "orc_optimize": (C.c_int, [_P, _P, _P, C.c_int, _P, C.POINTER(Options), C.POINTER(Stats), _P, C.c_int,
                                C.POINTER(C.c_int), _P]),
     "orc_build_cloud": (C.c_int64, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, C.c_int64]),
+    "orc_rtree_predict": (None, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "orc_param_dim": (C.c_int, [_P]),
     "orc_tangent_dim": (C.c_int, [_P]),
 }
@@ -219,6 +220,21 @@ def build_cloud(depth, parts, intrin, num_parts, roi=None, interval=1):
         raise ValueError("body-part label >= num_parts")
     assert n >= 0
     return pts[:n].copy(), lab[:n].copy()
+
+
+def rtree_predict(depth, tree, roi=None, interval=1, fill_in_gaps=True):
+    """RTree::predictBest on one image (RTree.cpp:3184-3262) + upscaleGrid; tree: dict of u, v, thresh, lnode, rnode,
+    leafid, leaf_best arrays (avatar_b200.synth.random_rtree layout)"""
+    depth = np.ascontiguousarray(depth, dtype=np.float32)
+    h, w = depth.shape
+    t = {k: np.ascontiguousarray(tree[k], dtype=d) for k, d in (("u", np.float32), ("v", np.float32), ("thresh", np.float32),
+                                                              ("lnode", np.int32), ("rnode", np.int32), ("leafid", np.int32),
+                                                              ("leaf_best", np.uint8))}
+    r = None if roi is None else np.ascontiguousarray(roi, dtype=np.int32)
+    out = np.zeros((h, w), dtype=np.uint8)
+    _lib.orc_rtree_predict(_p(depth), w, h, len(t["thresh"]), _p(t["u"]), _p(t["v"]), _p(t["thresh"]), _p(t["lnode"]),
+                           _p(t["rnode"]), _p(t["leafid"]), _p(t["leaf_best"]), _p(r), int(interval), int(bool(fill_in_gaps)), _p(out))
+    return out
 
 
 def ref_nanoflann_nn(points, queries):

@@ -414,3 +414,58 @@ def test_depth_cloud_construction_large_image(model, oracle_mod, omodel, prior_a
         assert len(po) == off[1] and (interval > 1 or len(po) > 150000)
         assert np.array_equal(pts, po) and np.array_equal(lab, lo)
     ft.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# RTree::predictBest on the device (avb_rtree_predict_batch)
+# ---------------------------------------------------------------------------------------------
+def test_rtree_predict_bit_exact(model, oracle_mod, omodel, prior_arrays):
+    """device labels == oracle restatement of RTree.cpp:3184-3262 + upscaleGrid, bit for bit: whole images, boxes,
+    strides, with and without gap filling, an empty frame, a degenerate box"""
+    from avatar_b200 import Fitter, synth
+    nparts = int(prior_arrays["num_parts"])
+    depth, parts, _ = _rendered(model, omodel, prior_arrays, [0, 1, 2])
+    depth[2][:] = 0.0
+    tree = synth.random_rtree(np.random.default_rng(21), nparts)
+    ft = Fitter(model, nparts, prior_arrays["part_map"], 3, 3 * 40000)
+    ft.set_rtree(tree, nparts)
+    boxes = [_bbox(parts[0]), _bbox(parts[1]), [100, 100, 300, 300]]
+    for roi, interval, fill in [(None, 1, True), (None, 2, True), (boxes, 1, False), (boxes, 2, True), (boxes, 3, True),
+                                ([[50, 60, 40, 300], boxes[1], boxes[0]], 2, True)]:
+        got = ft.rtree_predict(depth, roi, interval, fill)
+        for b in range(3):
+            want = oracle_mod.rtree_predict(depth[b], tree, None if roi is None else roi[b], interval, fill)
+            assert np.array_equal(got[b], want), (roi is not None, interval, fill, b, int((got[b] != want).sum()))
+        assert (got[2] == 255).all()
+        assert (got[0] != 255).sum() > 1000 or roi is not None and roi[0][2] < roi[0][0]
+    ft.close()
+
+
+def test_depth_to_fit_pipeline_on_device(model, oracle_mod, omodel, prior_arrays):
+    """depth image -> RTree labels -> data cloud -> fit, all on the device (parts=None), equals the host pipeline
+    (oracle RTree + oracle cloud construction) followed by the same fit: same clouds, same labels, same parameters"""
+    from avatar_b200 import Fitter, synth
+    nparts = int(prior_arrays["num_parts"])
+    intrin = (synth.FX, synth.CX, synth.FY, synth.CY)
+    depth, parts, x0 = _rendered(model, omodel, prior_arrays, [0, 1])
+    tree = synth.random_rtree(np.random.default_rng(22), nparts)
+    boxes = [_bbox(parts[0]), _bbox(parts[1])]
+    ft = Fitter(model, nparts, prior_arrays["part_map"], 2, 2 * 40000)
+    ft.set_rtree(tree, nparts)
+    off = ft.upload_depth(depth, None, intrin, nparts, roi=boxes, interval=1, rtree_interval=2)
+    pts, lab, _ = ft.download_batch()
+    host = []
+    for b in range(2):
+        labels_img = oracle_mod.rtree_predict(depth[b], tree, boxes[b], 2, True)
+        host.append(oracle_mod.build_cloud(depth[b], labels_img, intrin, nparts, boxes[b], 1))
+        assert np.array_equal(pts[off[b]:off[b + 1]], host[b][0])
+        assert np.array_equal(lab[off[b]:off[b + 1]], host[b][1])
+    assert off[2] > 10000
+    o = _opts()
+    ft.fit_resident(x0, o)
+    xd, _, _ = ft.download()
+    hp = np.concatenate([h[0] for h in host])
+    hl = np.concatenate([h[1] for h in host])
+    xh, _, _ = ft.fit_batch(hp, hl, off, x0, o)
+    assert np.array_equal(xd, xh)
+    ft.close()

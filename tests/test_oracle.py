@@ -294,3 +294,66 @@ def test_build_cloud_oracle_matches_harness_backprojection(oracle_mod, model, om
                                       None, interval)
         assert len(p) == len(pts) > 100
         assert np.array_equal(p, pts) and np.array_equal(l, lab)
+
+
+# ---------------------------------------------------------------------------------------------
+# RTree::predictBest on images (RTree.cpp:3184-3262) + upscaleGrid (RTree.cpp:70-100)
+# ---------------------------------------------------------------------------------------------
+def _py_round(x):
+    """std::round on a float32: half away from zero"""
+    x = float(x)
+    return int(np.floor(x + 0.5)) if x >= 0 else -int(np.floor(-x + 0.5))
+
+
+def _python_rtree_predict(depth, t, roi, interval, fill):
+    """independent pure-Python restatement with numpy float32 scalars (small images only)"""
+    h, w = depth.shape
+    out = np.full((h, w), 255, np.uint8)
+    tlx, tly, brx, bry = (0, 0, w - 1, h - 1) if roi is None else roi
+    bg = np.float32(20.0)
+    r = tly + interval
+    while r <= bry:
+        for c in range(tlx, brx + 1, interval):
+            z = np.float32(depth[r, c])
+            if z == 0:
+                continue
+            n = 0
+            while t["leafid"][n] == -1:
+                ux = _py_round(np.float32(t["u"][n, 0]) / z) + c
+                uy = _py_round(np.float32(t["u"][n, 1]) / z) + r
+                vx = _py_round(np.float32(t["v"][n, 0]) / z) + c
+                vy = _py_round(np.float32(t["v"][n, 1]) / z) + r
+                zu = bg if (ux < tlx or uy < tly or ux > brx or uy > bry) else np.float32(depth[uy, ux])
+                zv = bg if (vx < tlx or vy < tly or vx > brx or vy > bry) else np.float32(depth[vy, vx])
+                zu = bg if zu == 0 else zu
+                zv = bg if zv == 0 else zv
+                n = int(t["lnode"][n]) if np.float32(zu - zv) < np.float32(t["thresh"][n]) else int(t["rnode"][n])
+            out[r, c] = t["leaf_best"][t["leafid"][n]]
+        r += interval
+    if fill and interval > 1:
+        rr = tly + interval
+        while rr <= bry:
+            for r2 in range(rr, min(rr + interval, bry + 1)):
+                for cc in range(tlx, brx + 1, interval):
+                    val = out[rr, cc]
+                    out[r2, cc:min(cc + interval, w)] = val
+            rr += interval
+    return out
+
+
+def test_rtree_predict_oracle_small_cases(oracle_mod):
+    from avatar_b200 import synth
+    rng = np.random.default_rng(11)
+    tree = synth.random_rtree(rng, 16, depth_levels=9)
+    h, w = 37, 45
+    depth = np.zeros((h, w), np.float32)
+    depth[4:33, 6:40] = rng.uniform(0.8, 3.5, (29, 34)).astype(np.float32)
+    depth[rng.random((h, w)) < 0.15] = 0.0
+    for roi, interval, fill in [(None, 1, True), (None, 2, True), (None, 3, False), ((5, 3, 41, 34), 1, True),
+                                ((5, 3, 41, 34), 2, True), ((6, 4, 40, 33), 3, True), ((10, 10, 9, 30), 1, True)]:
+        o = oracle_mod.rtree_predict(depth, tree, roi, interval, fill)
+        p = _python_rtree_predict(depth, tree, roi, interval, fill)
+        assert np.array_equal(o, p), (roi, interval, fill, int((o != p).sum()))
+    # the first row of the box is never predicted (reference quirk, RTree.cpp:3196-3199)
+    o = oracle_mod.rtree_predict(depth, tree, (6, 4, 39, 32), 1, True)
+    assert (o[4] == 255).all() and (o[5, 6:40][depth[5, 6:40] > 0] != 255).all()
