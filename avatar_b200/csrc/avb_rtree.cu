@@ -28,7 +28,7 @@ __device__ __forceinline__ void rtree_roi(const RTreeArgs& a, int f, int& x0, in
     }
 }
 
-// grid = (ceil(sampled pixels of the largest box / 256), frames)
+// grid = (ceil(sampled pixels of the largest box / 2048), frames), grid-stride over the box
 __global__ void __launch_bounds__(256)
 rtree_predict_kernel(RTreeArgs a) {
     const int f = blockIdx.y;
@@ -36,36 +36,40 @@ rtree_predict_kernel(RTreeArgs a) {
     rtree_roi(a, f, x0, y0, x1, y1);
     const int ncols = (x1 >= x0) ? (x1 - x0) / a.interval + 1 : 0;
     const int nrows = (y1 - y0) / a.interval;             // rows y0 + interval, y0 + 2 interval, ... <= y1
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (ncols <= 0 || nrows <= 0 || i >= (long long)ncols * nrows) return;
-    const int r = y0 + (int)(i / ncols + 1) * a.interval, c = x0 + (int)(i % ncols) * a.interval;
-    if (r < 0 || r >= a.height || c < 0 || c >= a.width) return;   // a box outside the image is undefined in the reference
+    if (ncols <= 0 || nrows <= 0) return;
     const float* depth = a.depth + (size_t)f * a.height * a.width;
-    const float sampleDepth = depth[(size_t)r * a.width + c];
-    if (sampleDepth == 0.f) return;
-    int nodeid = 0;
-    RTreeNode nd = a.nodes[0];
-    while (nd.leafid == -1) {
-        // Eigen: Vector2f / float is a component-wise IEEE division; std::round is half away from zero
-        const int ux = (int)roundf(__fdiv_rn(nd.ux, sampleDepth)) + c, uy = (int)roundf(__fdiv_rn(nd.uy, sampleDepth)) + r;
-        const int vx = (int)roundf(__fdiv_rn(nd.vx, sampleDepth)) + c, vy = (int)roundf(__fdiv_rn(nd.vy, sampleDepth)) + r;
-        float zu = kBackgroundDepth, zv = kBackgroundDepth;
-        if (!(ux < x0 || uy < y0 || ux > x1 || uy > y1)) {
-            zu = depth[(size_t)uy * a.width + ux];
-            if (zu == 0.f) zu = kBackgroundDepth;
+    const unsigned total = (unsigned)ncols * (unsigned)nrows;   // < 2^31 pixels per image: 32-bit index maths
+    // grid-stride: most pixels are background (one depth load, no walk); eight per thread keep the launch small
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
+        const unsigned q = i / (unsigned)ncols;
+        const int r = y0 + (int)(q + 1) * a.interval, c = x0 + (int)(i - q * (unsigned)ncols) * a.interval;
+        if (r < 0 || r >= a.height || c < 0 || c >= a.width) continue;   // a box outside the image is undefined in the reference
+        const float sampleDepth = depth[(size_t)r * a.width + c];
+        if (sampleDepth == 0.f) continue;
+        int nodeid = 0;
+        RTreeNode nd = a.nodes[0];
+        while (nd.leafid == -1) {
+            // Eigen: Vector2f / float is a component-wise IEEE division; std::round is half away from zero
+            const int ux = (int)roundf(__fdiv_rn(nd.ux, sampleDepth)) + c, uy = (int)roundf(__fdiv_rn(nd.uy, sampleDepth)) + r;
+            const int vx = (int)roundf(__fdiv_rn(nd.vx, sampleDepth)) + c, vy = (int)roundf(__fdiv_rn(nd.vy, sampleDepth)) + r;
+            float zu = kBackgroundDepth, zv = kBackgroundDepth;
+            if (!(ux < x0 || uy < y0 || ux > x1 || uy > y1)) {
+                zu = depth[(size_t)uy * a.width + ux];
+                if (zu == 0.f) zu = kBackgroundDepth;
+            }
+            if (!(vx < x0 || vy < y0 || vx > x1 || vy > y1)) {
+                zv = depth[(size_t)vy * a.width + vx];
+                if (zv == 0.f) zv = kBackgroundDepth;
+            }
+            nodeid = (__fsub_rn(zu, zv) < nd.thresh) ? nd.lnode : nd.rnode;
+            nd = a.nodes[nodeid];
         }
-        if (!(vx < x0 || vy < y0 || vx > x1 || vy > y1)) {
-            zv = depth[(size_t)vy * a.width + vx];
-            if (zv == 0.f) zv = kBackgroundDepth;
-        }
-        nodeid = (__fsub_rn(zu, zv) < nd.thresh) ? nd.lnode : nd.rnode;
-        nd = a.nodes[nodeid];
+        a.parts[((size_t)f * a.height + r) * a.width + c] = a.leaf_best[nd.leafid];
     }
-    a.parts[((size_t)f * a.height + r) * a.width + c] = a.leaf_best[nd.leafid];
 }
 
 // upscaleGrid (RTree.cpp:70-100): every interval x interval cell below / right of a predicted pixel takes its label.
-// grid = (ceil(box pixels / 256), frames); the predicted pixels themselves are left alone (no read/write overlap).
+// grid = (ceil(box pixels / 2048), frames), grid-stride; the predicted pixels themselves are left alone (no read/write overlap).
 __global__ void __launch_bounds__(256)
 rtree_upscale_kernel(RTreeArgs a) {
     const int f = blockIdx.y;
@@ -74,25 +78,27 @@ rtree_upscale_kernel(RTreeArgs a) {
     const int ncols = (x1 >= x0) ? (x1 - x0) / a.interval + 1 : 0;   // cells per row
     const int wcols = ncols * a.interval;                             // memset(ptr + cc, val, interval) may pass x1
     const int hrows = y1 - (y0 + a.interval) + 1;                     // rows y0 + interval .. y1
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (wcols <= 0 || hrows <= 0 || i >= (long long)wcols * hrows) return;
-    const int dr = (int)(i / wcols), dc = (int)(i % wcols);
-    const int r = y0 + a.interval + dr, x = x0 + dc;
-    const int rr = y0 + a.interval + (dr / a.interval) * a.interval, cc = x0 + (dc / a.interval) * a.interval;
-    if (r < 0 || r >= a.height || x < 0 || x >= a.width || (r == rr && x == cc)) return;   // clamped to the image
+    if (wcols <= 0 || hrows <= 0) return;
     uint8_t* img = a.parts + (size_t)f * a.height * a.width;
-    img[(size_t)r * a.width + x] = img[(size_t)rr * a.width + cc];
+    const unsigned total = (unsigned)wcols * (unsigned)hrows;
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
+        const int dr = (int)(i / (unsigned)wcols), dc = (int)(i - (unsigned)dr * (unsigned)wcols);
+        const int r = y0 + a.interval + dr, x = x0 + dc;
+        const int rr = y0 + a.interval + (dr / a.interval) * a.interval, cc = x0 + (dc / a.interval) * a.interval;
+        if (r < 0 || r >= a.height || x < 0 || x >= a.width || (r == rr && x == cc)) continue;   // clamped to the image
+        img[(size_t)r * a.width + x] = img[(size_t)rr * a.width + cc];
+    }
 }
 
 cudaError_t launch_rtree_predict(const RTreeArgs& a, int batch, int max_box_pixels, cudaStream_t st) {
     if (batch <= 0 || max_box_pixels <= 0) return cudaSuccess;
-    const int blocks = (max_box_pixels + 255) / 256;
+    const int blocks = (max_box_pixels + 2047) / 2048;   // eight pixels per thread
     rtree_predict_kernel<<<dim3(blocks, batch), 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_rtree_upscale(const RTreeArgs& a, int batch, int max_box_pixels, cudaStream_t st) {
     if (batch <= 0 || max_box_pixels <= 0) return cudaSuccess;
-    const int blocks = (max_box_pixels + 255) / 256;
+    const int blocks = (max_box_pixels + 2047) / 2048;
     rtree_upscale_kernel<<<dim3(blocks, batch), 256, 0, st>>>(a);
     return cudaGetLastError();
 }

@@ -450,6 +450,41 @@ def main():
         for i in range(16):
             orc_c.build_cloud(dimg[i], pimg[i], intrin, num_parts)
         cpu_s = (time.perf_counter() - tA) / 16
+        # ---- RTree::predictBest on the device (random tree: the reference ships no trained one) ----
+        tree = synth.random_rtree(np.random.default_rng(7), num_parts)
+        fc.set_rtree(tree, num_parts)
+        rt = {}
+        for iv in (1, 2):
+            fc.rtree_predict(dimg[:NI], None, iv, True)
+            ms_l = []
+            for _ in range(3):
+                fc.rtree_predict(dimg[:NI], None, iv, True)
+                ms_l.append(fc.rtree_ms())
+            rt[iv] = float(np.median(ms_l))
+        fg = int((dimg[:NI] > 0).sum())
+        tA = time.perf_counter()
+        for i in range(8):
+            orc_c.rtree_predict(dimg[i], tree, None, 2, True)
+        rt_cpu = (time.perf_counter() - tA) / 8
+        # depth -> labels -> cloud, everything on the device, only the depth image crosses PCIe
+        wall2 = []
+        for _ in range(3):
+            tA = time.perf_counter()
+            fc.upload_depth(dimg, None, intrin, num_parts, rtree_interval=2)
+            fc.synchronize()
+            wall2.append(time.perf_counter() - tA)
+        line["rtree_prediction"] = {
+            "what": "avb_rtree_predict_batch: RTree::predictBest (RTree.cpp:3184-3262) + gap filling on %d depth images of 640x576, "
+                    "%d foreground pixels, random tree of %d nodes" % (NI, fg, len(tree["thresh"])),
+            "kernel_ms_interval1": rt[1], "kernel_ms_interval2": rt[2],
+            "foreground_pixels_per_s_interval1": fg / (rt[1] * 1e-3),
+            "frames_per_s_interval2": NI / (rt[2] * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": NI * synth.HEIGHT * synth.WIDTH * 5.0 / (rt[1] * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": NI * synth.HEIGHT * synth.WIDTH * 5.0 / (rt[1] * 1e-3) / 1e9 / peak,
+                         "note": "compulsory bytes only (4 B depth read + 1 B label written per pixel, interval 1); the walk itself is "
+                                 "a chain of dependent L2 gathers (32 B node + two 4 B probes per level), not an HBM stream"},
+            "cpu_oracle_ms_per_frame_1thread_interval2": 1e3 * rt_cpu,
+            "depth_to_cloud_e2e_ms": 1e3 * float(np.median(wall2)), "depth_to_cloud_frames_per_s_e2e": NI / float(np.median(wall2))}
         fc.close()
         line["cloud_construction"] = {
             "what": "avb_upload_depth_batch: depth + part-label images -> data clouds on the device (demo.cpp:215-250, "
