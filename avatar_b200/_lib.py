@@ -52,6 +52,11 @@ class ImageDesc(C.Structure):   # avb_image_desc
                 ("cy", C.c_float), ("interval", C.c_int32), ("num_parts", C.c_int32), ("rtree_interval", C.c_int32)]
 
 
+class RenderDesc(C.Structure):   # avb_render_desc
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_float), ("cx", C.c_float), ("fy", C.c_float),
+                ("cy", C.c_float)]
+
+
 class RTreeDesc(C.Structure):   # avb_rtree_desc
     _fields_ = [("num_nodes", C.c_int32), ("num_leaves", C.c_int32), ("num_parts", C.c_int32), ("u", C.c_void_p),
                 ("v", C.c_void_p), ("thresh", C.c_void_p), ("lnode", C.c_void_p), ("rnode", C.c_void_p),
@@ -84,6 +89,8 @@ SYMBOLS = [
     ("avb_fitter_set_rtree", C.c_int, [_P, C.POINTER(RTreeDesc)]),
     ("avb_rtree_predict_batch", C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, _P]),
     ("avb_last_rtree_ms", C.c_int, [_P, _P]),
+    ("avb_render_batch", C.c_int, [_P, C.c_int32, _P, C.POINTER(RenderDesc), _P, _P, _P]),
+    ("avb_last_render_ms", C.c_int, [_P, _P]),
     ("avb_download_results", C.c_int, [_P, _P, _P, _P]),
     ("avb_synchronize", C.c_int, [_P]),
     ("avb_last_device_ms", C.c_int, [_P, C.POINTER(C.c_float), _P]),

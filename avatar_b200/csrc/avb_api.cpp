@@ -119,6 +119,9 @@ struct avb_fitter {
     long long* d_strip_offset = nullptr; int* d_bad_label = nullptr;
     size_t img_cap = 0, strip_cap = 0;
     RTreeNode* d_rt_nodes = nullptr; uint8_t* d_rt_leaf = nullptr; int rt_nodes = 0, rt_leaves = 0, rt_parts = 0;
+    const uint8_t* d_vpart = nullptr; float* d_proj = nullptr; int* d_order = nullptr; unsigned* d_win = nullptr;
+    float* d_rdepth = nullptr; uint8_t* d_rparts = nullptr; int* d_rfaces = nullptr; size_t render_cap = 0;
+    cudaEvent_t nev[4] = {};   // around the three renderer kernels
     cudaEvent_t rev[2] = {};   // around the RTree kernels of the last prediction
     cudaEvent_t cev[4] = {};   // around cloud_count_kernel and cloud_compact_kernel of the last avb_upload_depth_batch
     std::vector<int> h_strip_count; std::vector<long long> h_strip_offset;
@@ -487,6 +490,8 @@ void avb_fitter_destroy(avb_fitter* ft) {
     for (auto& e : ft->cev) if (e) cudaEventDestroy(e);
     for (auto& e : ft->rev) if (e) cudaEventDestroy(e);
     cudaFree(ft->d_rt_nodes); cudaFree(ft->d_rt_leaf);
+    cudaFree(ft->d_win); cudaFree(ft->d_rdepth); cudaFree(ft->d_rparts); cudaFree(ft->d_rfaces); cudaFree(ft->d_proj); cudaFree(ft->d_order);
+    for (auto& e : ft->nev) if (e) cudaEventDestroy(e);
     if (ft->copy_stream) cudaStreamDestroy(ft->copy_stream);
     if (ft->stream) cudaStreamDestroy(ft->stream);
     delete ft;
@@ -586,6 +591,11 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     for (int p = NP - 1; p >= 0; --p) first_part_at[part_start[p]] = p;
     DevParts& dp = ft->dp;
     dp.numParts = NP;
+    {   // part of every vertex: part_map[assignedJoints[v][0]] (the renderer's part mask, AvatarHelpers.cpp:162-169)
+        std::vector<uint8_t> vpart((size_t)V);
+        for (int v = 0; v < V; ++v) vpart[v] = (uint8_t)cfg->part_map[m->main_joint[v]];
+        TRY(dev_put(ft, &ft->d_vpart, vpart));
+    }
     TRY(dev_put(ft, &dp.part_start, part_start));
     TRY(dev_put(ft, &dp.part_verts, part_verts));
     TRY(dev_put(ft, &dp.first_part_at, first_part_at));
@@ -901,6 +911,8 @@ int avb_fitter_set_rtree(avb_fitter* ft, const avb_rtree_desc* t) {
     CUDA_TRY(cudaSetDevice(ft->device));
     CUDA_TRY(cudaStreamSynchronize(ft->stream));
     cudaFree(ft->d_rt_nodes); cudaFree(ft->d_rt_leaf);
+    cudaFree(ft->d_win); cudaFree(ft->d_rdepth); cudaFree(ft->d_rparts); cudaFree(ft->d_rfaces); cudaFree(ft->d_proj); cudaFree(ft->d_order);
+    for (auto& e : ft->nev) if (e) cudaEventDestroy(e);
     ft->d_rt_nodes = nullptr; ft->d_rt_leaf = nullptr;
     CUDA_TRY(cudaMalloc(&ft->d_rt_nodes, nodes.size() * sizeof(RTreeNode)));
     CUDA_TRY(cudaMalloc(&ft->d_rt_leaf, (size_t)t->num_leaves));
@@ -1321,6 +1333,71 @@ int avb_avatar_update(avb_fitter* ft, int batch, const double* x, double* cloud,
     if (joint_pos) CUDA_TRY(cudaMemcpyAsync(joint_pos, ft->d_jpos, (size_t)batch * 3 * J * 8, cudaMemcpyDeviceToHost, st));
     if (joint_trans) CUDA_TRY(cudaMemcpyAsync(joint_trans, ft->d_jtrans, (size_t)batch * 12 * J * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return AVB_OK;
+}
+
+/* -------- AvatarRenderer on the device -------- */
+int avb_render_batch(avb_fitter* ft, int32_t batch, const double* x, const avb_render_desc* d, float* depth_out,
+                     uint8_t* parts_out, int32_t* faces_out) {
+    if (!ft || !x || !d || batch <= 0) return fail(AVB_ERR_INVALID, "null argument or empty batch");
+    if (batch > ft->max_batch) return fail(AVB_ERR_CAPACITY, "batch exceeds fitter capacity");
+    if (d->width <= 0 || d->height <= 0 || (size_t)d->width * d->height >= ((size_t)1 << 31)) return fail(AVB_ERR_INVALID, "bad image size");
+    if (ft->model->F > render_max_faces()) return fail(AVB_ERR_CAPACITY, "the renderer sorts at most 16384 faces per frame");
+    if (!depth_out && !parts_out && !faces_out) return AVB_OK;
+    CUDA_TRY(cudaSetDevice(ft->device));
+    cudaStream_t st = ft->stream;
+    const size_t nx = ft->model->nx, V = ft->model->V, F = ft->model->F;
+    const size_t px = (size_t)d->width * d->height, npx = px * batch;
+    if (npx > ft->render_cap) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(ft->d_win); cudaFree(ft->d_rdepth); cudaFree(ft->d_rparts); cudaFree(ft->d_rfaces);
+        ft->d_win = nullptr; ft->d_rdepth = nullptr; ft->d_rparts = nullptr; ft->d_rfaces = nullptr;
+        ft->render_cap = 0;
+        if (cudaMalloc(&ft->d_win, npx * 3 * 4) != cudaSuccess || cudaMalloc(&ft->d_rdepth, npx * 4) != cudaSuccess ||
+            cudaMalloc(&ft->d_rparts, npx) != cudaSuccess || cudaMalloc(&ft->d_rfaces, npx * 4) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(AVB_ERR_CUDA, "cudaMalloc of the render buffers failed");
+        }
+        ft->render_cap = npx;
+    }
+    if (!ft->d_proj) {
+        CUDA_TRY(cudaMalloc(&ft->d_proj, (size_t)ft->max_batch * V * 8));
+        CUDA_TRY(cudaMalloc(&ft->d_order, (size_t)ft->max_batch * F * 4));
+        for (auto& e : ft->nev) CUDA_TRY(cudaEventCreate(&e));
+    }
+    // the posed models: Avatar::update at x (the renderer reads ava.cloud)
+    CUDA_TRY(cudaMemcpyAsync(ft->d_xdbg, x, (size_t)batch * nx * 8, cudaMemcpyHostToDevice, st));
+    PoseArgs pa = pose_args(ft, ft->d_xdbg, false, nullptr);
+    CUDA_TRY(launch_pose_visibility(ft->dm, ft->dp, pa, batch, st));
+    CUDA_TRY(cudaMemsetAsync(ft->d_win, 0, npx * 3 * 4, st));
+    RenderArgs a{};
+    a.cloud = ft->d_cloud;
+    a.faces = ft->dm.faces;
+    a.vpart = ft->d_vpart;
+    a.proj = ft->d_proj;
+    a.order = ft->d_order;
+    a.win_depth = depth_out ? ft->d_win : nullptr;
+    a.win_parts = parts_out ? ft->d_win + npx : nullptr;
+    a.win_faces = faces_out ? ft->d_win + 2 * npx : nullptr;
+    a.depth_out = depth_out ? ft->d_rdepth : nullptr;
+    a.parts_out = parts_out ? ft->d_rparts : nullptr;
+    a.faces_out = faces_out ? ft->d_rfaces : nullptr;
+    a.V = (int)V; a.F = (int)F; a.width = d->width; a.height = d->height;
+    a.fx = d->fx; a.cx = d->cx; a.fy = d->fy; a.cy = d->cy;
+    CUDA_TRY(launch_render(a, batch, st, ft->nev));
+    if (depth_out) CUDA_TRY(cudaMemcpyAsync(depth_out, ft->d_rdepth, npx * 4, cudaMemcpyDeviceToHost, st));
+    if (parts_out) CUDA_TRY(cudaMemcpyAsync(parts_out, ft->d_rparts, npx, cudaMemcpyDeviceToHost, st));
+    if (faces_out) CUDA_TRY(cudaMemcpyAsync(faces_out, ft->d_rfaces, npx * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return AVB_OK;
+}
+
+int avb_last_render_ms(avb_fitter* ft, float* ms3) {
+    if (!ft || !ms3) return fail(AVB_ERR_INVALID, "null argument");
+    if (!ft->nev[0]) return fail(AVB_ERR_INVALID, "no avb_render_batch yet");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    CUDA_TRY(cudaEventSynchronize(ft->nev[3]));
+    for (int k = 0; k < 3; ++k) CUDA_TRY(cudaEventElapsedTime(&ms3[k], ft->nev[k], ft->nev[k + 1]));
     return AVB_OK;
 }
 

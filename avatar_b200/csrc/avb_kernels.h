@@ -67,6 +67,22 @@ struct RTreeArgs {   // RTree::predictBest on images (avb_rtree.cu)
     int width, height, interval;
 };
 
+struct RenderArgs {   // AvatarRenderer on the device (avb_render.cu)
+    const double* cloud;         // [batch][3V] posed models
+    const int* faces;            // [3F]
+    const uint8_t* vpart;        // [V] part of the vertex's main joint
+    float* proj;                 // [batch][V][2] scratch: projected vertices
+    int* order;                  // [batch][F] scratch: faces in paint order
+    unsigned* win_depth;         // nullable [batch][H][W] scratch: winning rank per pixel, zeroed by the caller
+    unsigned* win_parts;
+    unsigned* win_faces;
+    float* depth_out;            // nullable [batch][H][W]
+    uint8_t* parts_out;
+    int* faces_out;
+    int V, F, width, height;
+    float fx, cx, fy, cy;
+};
+
 struct LmState {  // per-frame Levenberg-Marquardt state, lives in HBM between the kernels of one ICP iteration
     double cost, radius, decrease, Qsum, sbp, sbs, initial_cost, model_change;
     int done, iters, accepted, ncorr, nmatched, nchunks, evals, nslots;   // nslots: record slots incl. alignment gaps
@@ -118,6 +134,8 @@ struct LmBuf {
 
 cudaError_t launch_rtree_predict(const RTreeArgs& a, int batch, int max_box_pixels, cudaStream_t st);
 cudaError_t launch_rtree_upscale(const RTreeArgs& a, int batch, int max_box_pixels, cudaStream_t st);
+int render_max_faces();
+cudaError_t launch_render(const RenderArgs& a, int batch, cudaStream_t st, cudaEvent_t* ev4);
 int cloud_strip_rows();
 cudaError_t launch_cloud_count(const CloudArgs& a, int strips, int batch, cudaStream_t st);
 cudaError_t launch_cloud_compact(const CloudArgs& a, int strips, int batch, cudaStream_t st);

@@ -63,6 +63,23 @@ class Fitter:
         self.total_points = int(offsets[-1] - offsets[0])
         check(lib.avb_upload_batch(self.handle, self.batch, ptr(clouds), ptr(labels), ptr(offsets)))
 
+    def render(self, x, width, height, intrin, want=("depth", "parts", "faces")):
+        """AvatarRenderer::renderDepth / renderPartMask / renderFaces of the model posed at x [B, nx]; intrin = (fx, cx, fy,
+        cy).  Returns a dict of [B, H, W] images (float32 depth, uint8 parts, int32 faces = position in paint order)."""
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        B = x.shape[0]
+        d = _lib.RenderDesc(int(width), int(height), float(intrin[0]), float(intrin[1]), float(intrin[2]), float(intrin[3]))
+        depth = np.zeros((B, height, width), np.float32) if "depth" in want else None
+        parts = np.zeros((B, height, width), np.uint8) if "parts" in want else None
+        faces = np.zeros((B, height, width), np.int32) if "faces" in want else None
+        check(lib.avb_render_batch(self.handle, B, ptr(x), C.byref(d), ptr(depth), ptr(parts), ptr(faces)))
+        return dict(depth=depth, parts=parts, faces=faces)
+
+    def render_ms(self):
+        ms = (C.c_float * 3)()
+        check(lib.avb_last_render_ms(self.handle, ms))
+        return dict(zip(("prepare", "cover", "resolve"), list(ms)))
+
     def set_rtree(self, tree, num_parts):
         """give the fitter a decision tree (RTree::nodes + leafBestMatch as arrays, see avb_rtree_desc)"""
         t = {k: np.ascontiguousarray(tree[k], dtype=d) for k, d in (("u", np.float32), ("v", np.float32), ("thresh", np.float32),

@@ -5,7 +5,7 @@
  * The reference has no FFI; its boundary is the C++ class API of include/Avatar.h and
  * include/AvatarOptimizer.h.  Each entry point below names the reference interface it replaces
  * (paths relative to the reference tree).  The header-compatible C++ facade
- * (include/ark_b200/, avatar_b200/cpp/ark_b200.cpp) and the Python mirror (avatar_b200/*.py) are thin callers of this ABI.
+ * (include/ark_b200/, avatar_b200/cpp/ark_b200.cpp) and the Python mirror (the avatar_b200 package) are thin callers of this ABI.
  *
  * Conventions: int return codes (AVB_OK = 0), no exceptions cross the ABI, caller owns host
  * buffers, the library owns device buffers, plain pointers and sizes only.  All host arrays are
@@ -188,6 +188,21 @@ typedef struct avb_image_desc {
 int avb_upload_depth_batch(avb_fitter* fitter, int32_t batch, const float* depth, const uint8_t* parts,
                            const int32_t* roi, const avb_image_desc* img, int64_t* offsets_out);
 int avb_download_batch(avb_fitter* fitter, double* data_clouds, int32_t* data_part_labels, int64_t* offsets);
+/* The reference's renderer on the device: AvatarRenderer::renderDepth,
+ * renderPartMask and renderFaces (AvatarRenderer.cpp:72-98, 170-216; painters in AvatarHelpers.cpp:61-302) for a batch
+ * of parameter vectors x [batch][nx] (the fitter poses the model, then paints).  Outputs are host arrays
+ * [batch][height][width], each nullable: depth float (0 = nothing), parts uint8 (255 = nothing, part of the nearest
+ * projected vertex otherwise, with the fitter's part_map), faces int32 (-1 = nothing, else the face's position in paint
+ * order, as the reference writes it).  Bit-identical to the sequential painter; faces with equal depth keys are painted
+ * in ascending face index (the reference's std::sort leaves that order unspecified).  renderLambert is not built. */
+typedef struct avb_render_desc {
+    int32_t width, height;
+    float fx, cx, fy, cy;
+} avb_render_desc;
+int avb_render_batch(avb_fitter* fitter, int32_t batch, const double* x, const avb_render_desc* view, float* depth_out,
+                     uint8_t* parts_out, int32_t* faces_out);
+/* device time (ms) of [prepare (project + sort), cover, resolve] of the last avb_render_batch */
+int avb_last_render_ms(avb_fitter* fitter, float* ms3);
 /* Body-part label prediction on the device: the image form of RTree::predictBest
  * (RTree.cpp:3184-3262) with its gap filling (upscaleGrid, RTree.cpp:70-100).  The tree is given as the arrays of
  * RTree::nodes (include/RTree.h:28-41: u, v [nodes][2], thresh, lnode, rnode, leafid with -1 = internal) and

@@ -63,6 +63,7 @@ _sig = {
                                C.POINTER(C.c_int), _P]),
     "orc_build_cloud": (C.c_int64, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, C.c_int64]),
     "orc_rtree_predict": (None, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "orc_render": (None, [_P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "orc_param_dim": (C.c_int, [_P]),
     "orc_tangent_dim": (C.c_int, [_P]),
 }
@@ -235,6 +236,38 @@ def rtree_predict(depth, tree, roi=None, interval=1, fill_in_gaps=True):
     _lib.orc_rtree_predict(_p(depth), w, h, len(t["thresh"]), _p(t["u"]), _p(t["v"]), _p(t["thresh"]), _p(t["lnode"]),
                            _p(t["rnode"]), _p(t["leafid"]), _p(t["leaf_best"]), _p(r), int(interval), int(bool(fill_in_gaps)), _p(out))
     return out
+
+
+def render(cloud, faces, vertex_part, width, height, intrin, want=("depth", "parts", "faces")):
+    """AvatarRenderer::renderDepth / renderPartMask / renderFaces restated (orc_render): dict of images + 'order'"""
+    cloud = _f64(cloud)
+    faces = np.ascontiguousarray(faces, dtype=np.int32)
+    vp = np.ascontiguousarray(vertex_part, dtype=np.int32)
+    k = np.ascontiguousarray(intrin, dtype=np.float32)
+    depth = np.zeros((height, width), np.float32) if "depth" in want else None
+    parts = np.zeros((height, width), np.uint8) if "parts" in want else None
+    fids = np.zeros((height, width), np.int32) if "faces" in want else None
+    order = np.zeros(faces.shape[0], np.int32)
+    _lib.orc_render(_p(cloud), cloud.shape[0], _p(faces), faces.shape[0], _p(vp), width, height, _p(k), _p(depth), _p(parts),
+                    _p(fids), _p(order))
+    return dict(depth=depth, parts=parts, faces=fids, order=order)
+
+
+def paint_check_render(cloud, faces, vertex_part, width, height, intrin):
+    """the product's rank-form renderer (avatar_b200/csrc/avb_paint.h) run on the CPU by tests/cpp/libpaint_check.so"""
+    lib = C.CDLL(os.path.join(os.path.dirname(_HERE), "tests", "cpp", "libpaint_check.so"))
+    cloud = _f64(cloud)
+    faces = np.ascontiguousarray(faces, dtype=np.int32)
+    vp = np.ascontiguousarray(vertex_part, dtype=np.uint8)
+    k = np.ascontiguousarray(intrin, dtype=np.float32)
+    depth = np.zeros((height, width), np.float32)
+    parts = np.zeros((height, width), np.uint8)
+    fids = np.zeros((height, width), np.int32)
+    order = np.zeros(faces.shape[0], np.int32)
+    lib.paint_check_render.argtypes = [_P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P]
+    lib.paint_check_render(_p(cloud), cloud.shape[0], _p(faces), faces.shape[0], _p(vp), width, height, _p(k), _p(depth),
+                           _p(parts), _p(fids), _p(order))
+    return dict(depth=depth, parts=parts, faces=fids, order=order)
 
 
 def ref_nanoflann_nn(points, queries):

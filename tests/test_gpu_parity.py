@@ -469,3 +469,29 @@ def test_depth_to_fit_pipeline_on_device(model, oracle_mod, omodel, prior_arrays
     xh, _, _ = ft.fit_batch(hp, hl, off, x0, o)
     assert np.array_equal(xd, xh)
     ft.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# AvatarRenderer on the device (avb_render_batch)
+# ---------------------------------------------------------------------------------------------
+def test_renderer_bit_exact(model, oracle_mod, omodel, prior_arrays):
+    """device renderDepth / renderPartMask / renderFaces == the sequential painter of oracle/render_oracle.cpp on the
+    same posed cloud, bit for bit, at 640x576 and at an odd size with off-centre intrinsics; single outputs too"""
+    from avatar_b200 import Fitter, synth
+    nparts = int(prior_arrays["num_parts"])
+    vp = synth.vertex_parts(model, prior_arrays["part_map"])
+    faces = np.ascontiguousarray(model.mesh, dtype=np.int32)
+    xs = np.stack([synth.random_params(model, np.random.default_rng(1000 + s)) for s in range(3)])
+    ft = Fitter(model, nparts, prior_arrays["part_map"], 3, 1000)
+    clouds, _, _ = ft.avatar_update(xs)                      # the renderer paints exactly this cloud
+    for (w, h, k) in [(synth.WIDTH, synth.HEIGHT, (synth.FX, synth.CX, synth.FY, synth.CY)), (321, 203, (250.5, 160.25, 251.0, 101.5))]:
+        got = ft.render(xs, w, h, k)
+        for b in range(3):
+            want = oracle_mod.render(clouds[b], faces, vp, w, h, k)
+            for name in ("depth", "parts", "faces"):
+                assert np.array_equal(got[name][b], want[name]), (name, b, w, int((got[name][b] != want[name]).sum()))
+            assert (want["depth"] > 0).sum() > 1000
+    only = ft.render(xs[:1], 160, 144, (126.0, 80.0, 126.0, 72.0), want=("parts",))
+    want = oracle_mod.render(clouds[0], faces, vp, 160, 144, (126.0, 80.0, 126.0, 72.0))
+    assert only["depth"] is None and np.array_equal(only["parts"][0], want["parts"])
+    ft.close()

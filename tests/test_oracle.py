@@ -357,3 +357,45 @@ def test_rtree_predict_oracle_small_cases(oracle_mod):
     # the first row of the box is never predicted (reference quirk, RTree.cpp:3196-3199)
     o = oracle_mod.rtree_predict(depth, tree, (6, 4, 39, 32), 1, True)
     assert (o[4] == 255).all() and (o[5, 6:40][depth[5, 6:40] > 0] != 255).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# AvatarRenderer (painter's algorithm) -- sequential oracle vs the product's rank-form renderer
+# (avatar_b200/csrc/avb_paint.h, the code the CUDA kernels call) executed on the CPU
+# ---------------------------------------------------------------------------------------------
+def _same_images(a, b):
+    for k in ("order", "depth", "parts", "faces"):
+        assert np.array_equal(a[k], b[k]), (k, int((a[k] != b[k]).sum()))
+
+
+def test_rank_form_renderer_equals_sequential_painter_on_the_model(oracle_mod, model, omodel, prior_arrays):
+    from avatar_b200 import synth
+    vp = synth.vertex_parts(model, prior_arrays["part_map"])
+    faces = np.ascontiguousarray(model.mesh, dtype=np.int32)
+    intrin = (synth.FX, synth.CX, synth.FY, synth.CY)
+    for seed, (w, h, k) in zip((1000, 1001), ((synth.WIDTH, synth.HEIGHT, intrin), (321, 203, (250.5, 160.25, 251.0, 101.5)))):
+        rng = np.random.default_rng(seed)
+        cloud, _, _ = omodel.update_x(synth.random_params(model, rng))
+        a = oracle_mod.render(cloud, faces, vp, w, h, k)
+        b = oracle_mod.paint_check_render(cloud, faces, vp, w, h, k)
+        _same_images(a, b)
+        assert (a["depth"] > 0).sum() > 1000 and (a["parts"] != 255).sum() > 1000 and (a["faces"] >= 0).sum() > 1000
+        # a person-shaped silhouette: depth and part mask cover nearly the same pixels
+        both = (a["depth"] > 0) & (a["parts"] != 255)
+        assert both.sum() > 0.9 * (a["depth"] > 0).sum()
+
+
+def test_rank_form_renderer_equals_sequential_painter_on_triangle_soup(oracle_mod):
+    """random triangles incl. degenerate, grazing, off-screen and sub-pixel ones, equal keys and shared vertices"""
+    rng = np.random.default_rng(77)
+    for trial in range(6):
+        V, F, w, h = 60, 90, 64, 48
+        cloud = np.stack([rng.uniform(-1.2, 1.2, V), rng.uniform(-0.9, 0.9, V), rng.uniform(1.5, 4.0, V)], 1)
+        if trial % 2:
+            cloud[:, 2] = np.round(cloud[:, 2] * 4) / 4            # many equal depth keys and grazing faces
+            cloud[::3, :2] = np.round(cloud[::3, :2] * 8) / 8     # vertices on integer-ish pixel positions
+        faces = rng.integers(0, V, (F, 3)).astype(np.int32)
+        faces[::10, 2] = faces[::10, 1]                           # degenerate faces
+        vp = rng.integers(0, 16, V)
+        k = (40.0 + trial, w / 2 + 0.3 * trial, 39.0, h / 2 - 0.2 * trial)
+        _same_images(oracle_mod.render(cloud, faces, vp, w, h, k), oracle_mod.paint_check_render(cloud, faces, vp, w, h, k))
