@@ -485,6 +485,28 @@ def main():
                                  "a chain of dependent L2 gathers (32 B node + two 4 B probes per level), not an HBM stream"},
             "cpu_oracle_ms_per_frame_1thread_interval2": 1e3 * rt_cpu,
             "depth_to_cloud_e2e_ms": 1e3 * float(np.median(wall2)), "depth_to_cloud_frames_per_s_e2e": NI / float(np.median(wall2))}
+        # ---- AvatarRenderer (depth + part mask) on the device ----
+        NR = min(64, NI)
+        fc.render(xg[:NR], synth.WIDTH, synth.HEIGHT, intrin, want=("depth", "parts"))
+        rms = []
+        for _ in range(3):
+            fc.render(xg[:NR], synth.WIDTH, synth.HEIGHT, intrin, want=("depth", "parts"))
+            rms.append(fc.render_ms())
+        rmed = {k2: float(np.median([r[k2] for r in rms])) for k2 in rms[0]}
+        vparts = synth.vertex_parts(model, part_map)
+        mesh = np.ascontiguousarray(model.mesh, dtype=np.int32)
+        tA = time.perf_counter()
+        for i in range(4):
+            orc_c.render(clouds_gt[i], mesh, vparts, synth.WIDTH, synth.HEIGHT, intrin, want=("depth", "parts"))
+        rcpu = (time.perf_counter() - tA) / 4
+        rtot = sum(rmed.values())
+        line["renderer"] = {
+            "what": "avb_render_batch: AvatarRenderer::renderDepth + renderPartMask (painter's algorithm as rank painting) of %d "
+                    "posed models at 640x576, 13776 faces each" % NR,
+            "kernel_ms": rmed, "frames_per_s_kernels": NR / (rtot * 1e-3),
+            "cpu_oracle_ms_per_frame_1thread": 1e3 * rcpu,
+            "note": "prepare = projection + 16384-key bitonic sort per frame in shared memory (latency bound), cover = per-face "
+                    "atomicMax of the paint rank, resolve = per-pixel value of the winning face"}
         fc.close()
         line["cloud_construction"] = {
             "what": "avb_upload_depth_batch: depth + part-label images -> data clouds on the device (demo.cpp:215-250, "

@@ -383,6 +383,12 @@ def test_rank_form_renderer_equals_sequential_painter_on_the_model(oracle_mod, m
         # a person-shaped silhouette: depth and part mask cover nearly the same pixels
         both = (a["depth"] > 0) & (a["parts"] != 255)
         assert both.sum() > 0.9 * (a["depth"] > 0).sum()
+        # independent sanity check of the painter itself: the harness' z-buffer rasteriser (different algorithm, exact
+        # nearest surface) sees about the same silhouette and nearly the same depths
+        _, _, zb, _ = synth.render_cloud(model, cloud, prior_arrays["part_map"], width=w, height=h, fx=k[0], fy=k[2], cx=k[1], cy=k[3])
+        pa, pz = a["depth"] > 0, zb > 0
+        assert (pa & pz).sum() > 0.7 * (pa | pz).sum()   # the painter's floor/ceil runs dilate every triangle by up to a pixel
+        assert np.median(np.abs(a["depth"][pa & pz] - zb[pa & pz])) < 5e-3
 
 
 def test_rank_form_renderer_equals_sequential_painter_on_triangle_soup(oracle_mod):
