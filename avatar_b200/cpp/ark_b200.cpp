@@ -2,13 +2,18 @@
 // Host-side only: file parsing and marshalling; every computation happens in libavatar_b200.so.
 #include "../../include/ark_b200/AvatarOptimizer.h"
 #include "../../include/ark_b200/npz.h"
+#include "../../include/ark_b200/RTree.h"
 #include "../../include/avatar_b200.h"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
 #include <functional>
+#include <limits>
+#include <map>
+#include <sstream>
 #include <stdexcept>
 
 namespace ark {
@@ -261,3 +266,159 @@ void AvatarOptimizer::optimize(const Eigen::Matrix<double, 3, Eigen::Dynamic>& d
     lastFinalCost = st.final_cost;
 }
 }  // namespace ark
+
+// ---- ark::RTree data side (RTree.cpp:2967-3061, 3452-3510) ----------------------------------------------------------
+namespace ark {
+namespace {
+template <class T> bool read_bin(std::istream& is, T& v) { return (bool)is.read(reinterpret_cast<char*>(&v), sizeof(T)); }
+}
+
+bool RTree::loadFile(const std::string& path) {
+    std::ifstream bifs(path, std::ios::in | std::ios::binary);
+    if (!bifs) return false;
+    char marker = 0;
+    bifs.get(marker);
+    if (marker == 'R') {   // binary format
+        uint32_t nNodes = 0, nLeafs = 0;
+        int32_t np = 0;
+        if (!read_bin(bifs, nNodes) || !read_bin(bifs, nLeafs) || !read_bin(bifs, np)) throw std::runtime_error("RTree file is truncated: " + path);
+        numParts = np;
+        nodes.assign(nNodes, RNode());
+        leafData.assign(nLeafs, std::vector<float>());
+        uint32_t last = 0;
+        for (size_t i = 0; i < nodes.size(); ++i) {
+            uint8_t isLeaf = 0;
+            if (!read_bin(bifs, isLeaf)) throw std::runtime_error("RTree file is truncated: " + path);
+            if (isLeaf) {
+                if (last >= nLeafs) throw std::runtime_error("RTree file has more leaves than announced: " + path);
+                leafData[last].assign(numParts, 0.f);
+                uint8_t cnt = 0;
+                read_bin(bifs, cnt);
+                if (cnt > numParts) throw std::runtime_error("RTree leaf has more parts than numParts: " + path);
+                for (uint8_t j = 0; j < cnt; ++j) {
+                    uint8_t k = 0;
+                    float val = 0;
+                    read_bin(bifs, k);
+                    if (k >= numParts || !read_bin(bifs, val)) throw std::runtime_error("RTree leaf entry out of bounds: " + path);
+                    leafData[last][k] = val;
+                }
+                nodes[i].leafid = (int)last++;
+            } else {
+                int32_t l = 0, r = 0;
+                read_bin(bifs, l);
+                read_bin(bifs, r);
+                nodes[i].lnode = l;
+                nodes[i].rnode = r;
+                read_bin(bifs, nodes[i].thresh);
+                bifs.read(reinterpret_cast<char*>(nodes[i].u), sizeof(float) * 2);
+                if (!bifs.read(reinterpret_cast<char*>(nodes[i].v), sizeof(float) * 2)) throw std::runtime_error("RTree file is truncated: " + path);
+            }
+        }
+        bifs.get(marker);
+        if (marker != 'T') throw std::runtime_error("incorrect RTree format, T end marker missing: " + path);
+    } else {               // legacy text format
+        bifs.close();
+        std::ifstream ifs(path);
+        if (!ifs) return false;
+        size_t nNodes = 0, nLeafs = 0;
+        ifs >> nNodes >> nLeafs >> numParts;
+        if (!ifs) throw std::runtime_error("RTree text file has no header: " + path);
+        nodes.assign(nNodes, RNode());
+        leafData.assign(nLeafs, std::vector<float>());
+        for (size_t i = 0; i < nNodes; ++i) {
+            ifs >> nodes[i].leafid;
+            if (nodes[i].leafid < 0)
+                ifs >> nodes[i].lnode >> nodes[i].rnode >> nodes[i].thresh >> nodes[i].u[0] >> nodes[i].u[1] >> nodes[i].v[0] >> nodes[i].v[1];
+        }
+        for (size_t i = 0; i < nLeafs; ++i) {
+            leafData[i].assign(numParts, 0.f);
+            for (int j = 0; j < numParts; ++j) ifs >> leafData[i][j];
+        }
+        if (!ifs) throw std::runtime_error("RTree text file is truncated: " + path);
+    }
+    updateBestMatchTable();
+    int numNew = 0;
+    if (!readPartMap(path + ".partmap", partMap, numNew, partMapType))
+        std::fprintf(stderr, "Warning: partmap not found or invalid beside %s; using default map\n", path.c_str());
+    return true;
+}
+
+void RTree::updateBestMatchTable() {
+    leafBestMatch.assign(leafData.size(), 0);
+    for (size_t i = 0; i < leafData.size(); ++i) {
+        float best = std::numeric_limits<float>::lowest();
+        for (int j = 0; j < numParts && j < (int)leafData[i].size(); ++j)
+            if (leafData[i][j] > best) {
+                best = leafData[i][j];
+                leafBestMatch[i] = (uint8_t)j;
+            }
+    }
+}
+
+bool RTree::readPartMap(const std::string& path, std::vector<int>& result, int& num_new_parts, int& partmap_type) {
+    std::ifstream is(path);
+    if (!is) return false;
+    std::string marker;
+    is >> marker;
+    if (marker != "partmap") return false;
+    is >> marker;
+    if (marker == "disjoint") partmap_type = 1;
+    else if (marker == "contiguous") partmap_type = 0;
+    else return false;
+    int nOld = 0, nNew = 0;
+    is >> marker;
+    if (marker != "src") return false;
+    is >> nOld;
+    std::map<std::string, int> oldEnum, newEnum;
+    for (int i = 0; i < nOld; ++i) { std::string name; is >> name; oldEnum[name] = i; }
+    is >> marker;
+    if (marker != "dest") return false;
+    is >> nNew;
+    for (int i = 0; i < nNew; ++i) { std::string name; is >> name; newEnum[name] = i; }
+    result.assign(nOld, 0);
+    for (int i = 0; i < nOld; ++i) {
+        std::string a, b;
+        if (!(is >> a >> b)) break;
+        result[oldEnum[a]] = newEnum[b];
+    }
+    num_new_parts = nNew;
+    return true;
+}
+
+void RTree::attach(avb_fitter* fitter) const {
+    std::vector<float> u(2 * nodes.size()), v(2 * nodes.size()), th(nodes.size());
+    std::vector<int32_t> l(nodes.size()), r(nodes.size()), id(nodes.size());
+    for (size_t i = 0; i < nodes.size(); ++i) {
+        u[2 * i] = nodes[i].u[0]; u[2 * i + 1] = nodes[i].u[1]; v[2 * i] = nodes[i].v[0]; v[2 * i + 1] = nodes[i].v[1];
+        th[i] = nodes[i].thresh; l[i] = nodes[i].lnode; r[i] = nodes[i].rnode; id[i] = nodes[i].leafid;
+    }
+    avb_rtree_desc d{(int32_t)nodes.size(), (int32_t)leafBestMatch.size(), numParts, u.data(), v.data(), th.data(), l.data(), r.data(),
+                     id.data(), leafBestMatch.data()};
+    if (avb_fitter_set_rtree(fitter, &d) != AVB_OK) die("avb_fitter_set_rtree");
+}
+
+}  // namespace ark
+
+// test hook (tests/test_cpp_facade.py): load a tree file with the facade and copy its arrays out
+extern "C" int ark_b200_rtree_probe(const char* path, int32_t* counts3, float* uvt /*[nodes][5]*/, int32_t* lri /*[nodes][3]*/,
+                                    uint8_t* leaf_best, int32_t cap_nodes, int32_t cap_leaves, int32_t* partmap_info /*[2 + 64]*/) {
+    try {
+        ark::RTree t(0);
+        if (!t.loadFile(path)) return 1;
+        counts3[0] = (int32_t)t.nodes.size(); counts3[1] = (int32_t)t.leafBestMatch.size(); counts3[2] = t.numParts;
+        if ((int)t.nodes.size() > cap_nodes || (int)t.leafBestMatch.size() > cap_leaves) return 2;
+        for (size_t i = 0; i < t.nodes.size(); ++i) {
+            uvt[5 * i] = t.nodes[i].u[0]; uvt[5 * i + 1] = t.nodes[i].u[1]; uvt[5 * i + 2] = t.nodes[i].v[0]; uvt[5 * i + 3] = t.nodes[i].v[1];
+            uvt[5 * i + 4] = t.nodes[i].thresh;
+            lri[3 * i] = t.nodes[i].lnode; lri[3 * i + 1] = t.nodes[i].rnode; lri[3 * i + 2] = t.nodes[i].leafid;
+        }
+        for (size_t i = 0; i < t.leafBestMatch.size(); ++i) leaf_best[i] = t.leafBestMatch[i];
+        partmap_info[0] = t.partMapType;
+        partmap_info[1] = (int32_t)t.partMap.size();
+        for (size_t i = 0; i < t.partMap.size() && i < 64; ++i) partmap_info[2 + i] = t.partMap[i];
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "ark_b200_rtree_probe: %s\n", e.what());
+        return 3;
+    }
+}

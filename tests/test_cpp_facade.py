@@ -57,3 +57,38 @@ def test_facade_optimize_matches_oracle(model_dir, oracle_mod, oopt, frames, pri
     assert int(lines["STATS"][1]) == st.num_correspondences
     cloud, _, _ = oopt.model.update_x(x)
     np.testing.assert_allclose([float(v) for v in lines["CLOUD0"]], cloud[0], atol=1e-9)
+
+
+def test_facade_rtree_loader_matches_the_python_mirror(build_all, tmp_path):
+    """ark::RTree::loadFile of the facade (binary 'R' format, legacy text, .partmap) against avatar_b200.rtree"""
+    import ctypes as C
+    from avatar_b200 import synth, rtree
+    lib = C.CDLL(os.path.join(ROOT, "avatar_b200", "libark_b200.so"))
+    rng = np.random.default_rng(9)
+    tree = synth.random_rtree(rng, 16, depth_levels=8)
+    n_leafs = len(tree["leaf_best"])
+    leaf_data = np.zeros((n_leafs, 16), np.float32)
+    leaf_data[np.arange(n_leafs), tree["leaf_best"]] = 0.75
+    leaf_data[np.arange(n_leafs), (tree["leaf_best"] + 3) % 16] = 0.25
+    for legacy in (False, True):
+        p = str(tmp_path / ("t.txt" if legacy else "t.srtr"))
+        rtree.save_rtree(p, tree, leaf_data, legacy_text=legacy)
+        with open(p + ".partmap", "w") as fh:
+            fh.write("partmap contiguous\nsrc 3 head torso leg\ndest 2 up down\nhead up\ntorso up\nleg down\n")
+        n = len(tree["thresh"])
+        counts = (C.c_int32 * 3)()
+        uvt = np.zeros((n, 5), np.float32)
+        lri = np.zeros((n, 3), np.int32)
+        best = np.zeros(n_leafs, np.uint8)
+        pm = (C.c_int32 * 66)()
+        rc = lib.ark_b200_rtree_probe(p.encode(), counts, uvt.ctypes.data_as(C.c_void_p), lri.ctypes.data_as(C.c_void_p),
+                                      best.ctypes.data_as(C.c_void_p), n, n_leafs, pm)
+        assert rc == 0 and list(counts) == [n, n_leafs, 16]
+        py = rtree.load_rtree(p)
+        assert np.array_equal(uvt[:, :2], py["u"]) and np.array_equal(uvt[:, 2:4], py["v"]) and np.array_equal(uvt[:, 4], py["thresh"])
+        internal = py["leafid"] < 0
+        assert np.array_equal(lri[internal, 0], py["lnode"][internal]) and np.array_equal(lri[internal, 1], py["rnode"][internal])
+        assert np.array_equal(lri[:, 2], py["leafid"]) and np.array_equal(best, py["leaf_best"])
+        assert pm[0] == 0 and pm[1] == 3 and list(pm[2:5]) == [0, 0, 1]
+        assert rtree.read_partmap(p + ".partmap") == ([0, 0, 1], 2, 0)
+    assert lib.ark_b200_rtree_probe(str(tmp_path / "missing.srtr").encode(), counts, None, None, None, 0, 0, pm) == 1

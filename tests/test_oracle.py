@@ -405,3 +405,38 @@ def test_rank_form_renderer_equals_sequential_painter_on_triangle_soup(oracle_mo
         vp = rng.integers(0, 16, V)
         k = (40.0 + trial, w / 2 + 0.3 * trial, 39.0, h / 2 - 0.2 * trial)
         _same_images(oracle_mod.render(cloud, faces, vp, w, h, k), oracle_mod.paint_check_render(cloud, faces, vp, w, h, k))
+
+
+# ---------------------------------------------------------------------------------------------
+# RTree model files (RTree.cpp:2967-3094, 3452-3510): host-side readers of the Python mirror
+# ---------------------------------------------------------------------------------------------
+def test_rtree_file_formats_roundtrip(tmp_path, oracle_mod):
+    from avatar_b200 import synth, rtree
+    rng = np.random.default_rng(5)
+    tree = synth.random_rtree(rng, 16, depth_levels=8)
+    n_leafs = len(tree["leaf_best"])
+    leaf_data = np.zeros((n_leafs, 16), np.float32)
+    for i in range(n_leafs):                                 # sparse distributions whose arg-max is the tree's label
+        ks = rng.choice(16, 3, replace=False)
+        leaf_data[i, ks] = rng.uniform(0.05, 0.3, 3).astype(np.float32)
+        leaf_data[i, tree["leaf_best"][i]] = np.float32(0.5)
+    for legacy in (False, True):
+        p = str(tmp_path / ("tree.txt" if legacy else "tree.srtr"))
+        rtree.save_rtree(p, tree, leaf_data, legacy_text=legacy)
+        got = rtree.load_rtree(p)
+        assert got["num_parts"] == 16
+        for k in ("u", "v", "thresh", "lnode", "rnode", "leafid", "leaf_best"):
+            assert np.array_equal(got[k], tree[k]), (k, legacy)
+        assert np.array_equal(got["leaf_data"], leaf_data)
+        # and the loaded tree predicts what the original predicts
+        depth = np.zeros((30, 40), np.float32)
+        depth[3:27, 5:35] = rng.uniform(1, 3, (24, 30)).astype(np.float32)
+        assert np.array_equal(oracle_mod.rtree_predict(depth, got, None, 1, True), oracle_mod.rtree_predict(depth, tree, None, 1, True))
+    # ties in a leaf distribution: the first maximum wins (RTree.cpp:3456-3461)
+    ld = np.zeros((1, 4), np.float32); ld[0, 1] = ld[0, 3] = 0.5
+    assert rtree._best_match(ld)[0] == 1
+    pm = tmp_path / "tree.srtr.partmap"
+    pm.write_text("partmap disjoint\nsrc 3 a b c\ndest 2 x y\na x\nb y\nc y\n")
+    assert rtree.read_partmap(str(pm)) == ([0, 1, 1], 2, 1)
+    pm.write_text("nonsense")
+    assert rtree.read_partmap(str(pm)) is None
