@@ -10,6 +10,9 @@
  *   - everything upstream of the solver (forward model, visibility, NN, residuals, Jacobians,
  *     priors) is specified by the reference source and restated line by line; the NN step is
  *     additionally pinned against the reference's own vendored nanoflann.hpp (oracle/_ref);
+ *   - the widened rows: the renderer's painters and CameraIntrin::depthToXYZ are pinned against the reference's own
+ *     AvatarHelpers.cpp / Calibration.cpp compiled into oracle/_ref with container-only stand-ins (oracle/shim);
+ *     RTree::predictBest is restated from source (RTree.cpp needs the full Eigen/OpenCV stack);
  *   - the solver trajectory (Ceres 1.14, external, un-vendored) is PARITY UNPINNED.
  * Every function cites the reference file:line it follows (paths relative to /root/reference).
  */

@@ -64,6 +64,7 @@ _sig = {
     "orc_build_cloud": (C.c_int64, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, C.c_int64]),
     "orc_rtree_predict": (None, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "orc_render": (None, [_P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "orc_render_prelude": (None, [_P, C.c_int, _P, C.c_int, _P, _P, _P, _P]),
     "orc_param_dim": (C.c_int, [_P]),
     "orc_tangent_dim": (C.c_int, [_P]),
 }
@@ -251,6 +252,48 @@ def render(cloud, faces, vertex_part, width, height, intrin, want=("depth", "par
     _lib.orc_render(_p(cloud), cloud.shape[0], _p(faces), faces.shape[0], _p(vp), width, height, _p(k), _p(depth), _p(parts),
                     _p(fids), _p(order))
     return dict(depth=depth, parts=parts, faces=fids, order=order)
+
+
+REF_PAINTERS_PATH = os.path.join(_HERE, "_ref", "libref_painters.so")
+
+
+def ref_painters_render(cloud, faces, vertex_part, width, height, intrin):
+    """the images painted by the REFERENCE'S OWN painters (AvatarHelpers.cpp compiled into oracle/_ref against the
+    container stand-ins of oracle/shim), driven face by face in the renderer's order; None if oracle/_ref is not built"""
+    if not os.path.exists(REF_PAINTERS_PATH):
+        return None
+    lib = C.CDLL(REF_PAINTERS_PATH)
+    cloud = _f64(cloud)
+    faces = np.ascontiguousarray(faces, dtype=np.int32)
+    vp = np.ascontiguousarray(vertex_part, dtype=np.int32)
+    k = np.ascontiguousarray(intrin, dtype=np.float32)
+    V, F = cloud.shape[0], faces.shape[0]
+    proj = np.zeros((V, 2), np.float32)
+    order = np.zeros(F, np.int32)
+    grazing = np.zeros(F, np.uint8)
+    _lib.orc_render_prelude(_p(cloud), V, _p(faces), F, _p(k), _p(proj), _p(order), _p(grazing))
+    of = np.ascontiguousarray(faces[order])
+    zv = np.ascontiguousarray(cloud[of, 2].astype(np.float32))
+    depth = np.zeros((height, width), np.float32)
+    parts = np.full((height, width), 255, np.uint8)
+    fids = np.full((height, width), -1, np.int32)
+    lib.ref_paint_faces.argtypes = [_P, C.c_int, _P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P]
+    lib.ref_paint_faces(_p(proj), V, _p(of), F, _p(grazing), _p(zv), _p(vp), width, height, _p(depth), _p(parts), _p(fids))
+    return dict(depth=depth, parts=parts, faces=fids, order=order)
+
+
+def ref_depth_to_xyz(depth, intrin):
+    """CameraIntrin::depthToXYZ of the reference itself (Calibration.cpp compiled into oracle/_ref); intrin = (fx, cx, fy, cy);
+    None if oracle/_ref is not built"""
+    if not os.path.exists(REF_PAINTERS_PATH):
+        return None
+    lib = C.CDLL(REF_PAINTERS_PATH)
+    depth = np.ascontiguousarray(depth, dtype=np.float32)
+    h, w = depth.shape
+    out = np.zeros((h, w, 3), np.float32)
+    lib.ref_depth_to_xyz.argtypes = [_P, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _P]
+    lib.ref_depth_to_xyz(_p(depth), w, h, float(intrin[0]), float(intrin[1]), float(intrin[2]), float(intrin[3]), _p(out))
+    return out
 
 
 def paint_check_render(cloud, faces, vertex_part, width, height, intrin):

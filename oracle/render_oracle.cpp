@@ -9,8 +9,12 @@
  *
  * Deviation that cannot be avoided: the reference orders faces with std::sort, whose order among equal keys is
  * unspecified; here (and in the device renderer) equal keys keep ascending face index.
- * PARITY STATUS: the reference has no test or golden image for the renderer and needs OpenCV/Eigen to build:
- * unpinned by reference vectors, restated from source. */
+ * PARITY STATUS: the three painters are PINNED against the reference's own AvatarHelpers.cpp, compiled from
+ * /root/reference into oracle/_ref/libref_painters.so with container-only OpenCV/Eigen stand-ins (oracle/shim,
+ * oracle/ref_painters.cpp): tests/test_oracle.py::test_oracle_painter_equals_the_references_own_painters drives the
+ * reference code face by face and gets the same images.  Projection, face order and the grazing test
+ * (AvatarRenderer.cpp, which needs the full Eigen/OpenCV stack) are restated from source; the reference has no golden
+ * image. */
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -184,4 +188,27 @@ void orc_render(const double* cloud, int V, const int32_t* faces, int F, const i
     }
 }
 
+
+/* the renderer's per-frame prelude, for tests that drive the reference's own painters (oracle/_ref/libref_painters.so):
+ * projected vertices [V][2], faces in paint order [F], and per ordered face the grazing flag (|n_z| < 0.1) */
+void orc_render_prelude(const double* cloud, int V, const int32_t* faces, int F, const float* intrin, float* proj_xy,
+                        int32_t* order, uint8_t* grazing) {
+    const float fx = intrin[0], cx = intrin[1], fy = intrin[2], cy = intrin[3];
+    for (int i = 0; i < V; ++i) {
+        const double* pt = cloud + 3 * (size_t)i;
+        proj_xy[2 * i] = static_cast<double>(pt[0]) * fx / pt[2] + cx;
+        proj_xy[2 * i + 1] = -static_cast<double>(pt[1]) * fy / pt[2] + cy;
+    }
+    std::vector<std::pair<float, int>> ord(F);
+    for (int i = 0; i < F; ++i) {
+        const int32_t* f = faces + 3 * (size_t)i;
+        ord[i].first = (cloud[3 * (size_t)f[0] + 2] + cloud[3 * (size_t)f[1] + 2] + cloud[3 * (size_t)f[2] + 2]) / 3.f;
+        ord[i].second = i;
+    }
+    std::stable_sort(ord.begin(), ord.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first > b.first; });
+    for (int i = 0; i < F; ++i) {
+        order[i] = ord[i].second;
+        grazing[i] = zcross_of(cloud, faces + 3 * (size_t)ord[i].second) < 0.1 ? 1 : 0;
+    }
+}
 }  // extern "C"

@@ -440,3 +440,49 @@ def test_rtree_file_formats_roundtrip(tmp_path, oracle_mod):
     assert rtree.read_partmap(str(pm)) == ([0, 1, 1], 2, 1)
     pm.write_text("nonsense")
     assert rtree.read_partmap(str(pm)) is None
+
+
+def test_oracle_painter_equals_the_references_own_painters(oracle_mod, model, omodel, prior_arrays):
+    """PIN: oracle/render_oracle.cpp against the reference's own AvatarHelpers.cpp (compiled from /root/reference into
+    oracle/_ref with container-only OpenCV/Eigen stand-ins): the same faces in the same order give the same images"""
+    from avatar_b200 import synth
+    vp = synth.vertex_parts(model, prior_arrays["part_map"])
+    faces = np.ascontiguousarray(model.mesh, dtype=np.int32)
+    rng = np.random.default_rng(1002)
+    cloud, _, _ = omodel.update_x(synth.random_params(model, rng))
+    cases = [(cloud, faces, vp, synth.WIDTH, synth.HEIGHT, (synth.FX, synth.CX, synth.FY, synth.CY)),
+             (cloud, faces, vp, 211, 173, (160.5, 100.25, 161.0, 90.5))]
+    for trial in range(4):                                       # triangle soups with degenerate / grazing / off-screen faces
+        V, F, w, h = 60, 90, 64, 48
+        c = np.stack([rng.uniform(-1.2, 1.2, V), rng.uniform(-0.9, 0.9, V), rng.uniform(1.5, 4.0, V)], 1)
+        if trial % 2:
+            c[:, 2] = np.round(c[:, 2] * 4) / 4
+            c[::3, :2] = np.round(c[::3, :2] * 8) / 8
+        f = rng.integers(0, V, (F, 3)).astype(np.int32)
+        f[::10, 2] = f[::10, 1]
+        cases.append((c, f, rng.integers(0, 16, V), w, h, (40.0 + trial, w / 2 + 0.3 * trial, 39.0, h / 2 - 0.2 * trial)))
+    for c, f, p, w, h, k in cases:
+        ref = oracle_mod.ref_painters_render(c, f, p, w, h, k)
+        if ref is None:
+            pytest.skip("oracle/_ref/libref_painters.so not built (reference tree absent)")
+        _same_images(oracle_mod.render(c, f, p, w, h, k), ref)
+
+
+def test_build_cloud_oracle_equals_the_references_own_depth_to_xyz(oracle_mod, model, omodel, prior_arrays):
+    """PIN: the xyz arithmetic of orc_build_cloud against the reference's own CameraIntrin::depthToXYZ (Calibration.cpp
+    compiled from /root/reference into oracle/_ref): every foreground pixel's point equals the xyz map entry, y negated
+    as demo.cpp:244-246 does"""
+    from avatar_b200 import synth
+    rng = np.random.default_rng(1003)
+    cloud, _, _ = omodel.update_x(synth.random_params(model, rng))
+    _, _, depth, part = synth.render_cloud(model, cloud, prior_arrays["part_map"])
+    for intrin in [(synth.FX, synth.CX, synth.FY, synth.CY), (606.438, 637.294, 606.351, 366.992)]:
+        xyz = oracle_mod.ref_depth_to_xyz(depth, intrin)
+        if xyz is None:
+            pytest.skip("oracle/_ref/libref_painters.so not built (reference tree absent)")
+        pts, lab = oracle_mod.build_cloud(depth, part, intrin, int(prior_arrays["num_parts"]))
+        rr, cc = np.nonzero(part != 255)                         # raster order
+        want = xyz[rr, cc].astype(np.float64)
+        want[:, 1] = -want[:, 1]
+        assert len(pts) == len(rr) > 5000
+        assert np.array_equal(pts, want) and np.array_equal(lab, part[rr, cc].astype(np.int32))
