@@ -194,7 +194,8 @@ int avb_download_batch(avb_fitter* fitter, double* data_clouds, int32_t* data_pa
  * [batch][height][width], each nullable: depth float (0 = nothing), parts uint8 (255 = nothing, part of the nearest
  * projected vertex otherwise, with the fitter's part_map), faces int32 (-1 = nothing, else the face's position in paint
  * order, as the reference writes it).  Bit-identical to the sequential painter; faces with equal depth keys are painted
- * in ascending face index (the reference's std::sort leaves that order unspecified).  renderLambert is not built. */
+ * in ascending face index (the reference's std::sort leaves that order unspecified).  renderLambert is not built.
+ * The call poses the models into the fitter's model-cloud buffer: download the results of a pending fit first. */
 typedef struct avb_render_desc {
     int32_t width, height;
     float fx, cx, fy, cy;
