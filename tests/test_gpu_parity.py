@@ -495,3 +495,22 @@ def test_renderer_bit_exact(model, oracle_mod, omodel, prior_arrays):
     want = oracle_mod.render(clouds[0], faces, vp, 160, 144, (126.0, 80.0, 126.0, 72.0))
     assert only["depth"] is None and np.array_equal(only["parts"][0], want["parts"])
     ft.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# frozen golden outputs (tests/golden/expected_r1.npz)
+# ---------------------------------------------------------------------------------------------
+def test_fit_matches_the_frozen_golden_vectors(fitter, frames):
+    """the device fit against the FROZEN outputs of the oracle (not the live oracle): parameters within the stated
+    tolerance, iteration / correspondence counts exact, costs to 1e-6"""
+    import os
+    from conftest import GOLDEN
+    gold = np.load(os.path.join(GOLDEN, "expected_r1.npz"))
+    pts, lab, off, x0 = _batch(frames, [0, 1, 2])
+    x, stats, _ = fitter.fit_batch(pts, lab, off, x0, _opts(function_tolerance=0.0))
+    for b in range(3):
+        assert np.abs(x[b] - gold[f"fit_x_{b}"]).max() < PARAM_TOL
+        it, acc, ncorr = [int(v) for v in gold[f"fit_iters_{b}"]]
+        assert (stats[b].iterations, stats[b].accepted_steps, stats[b].num_correspondences) == (it, acc, ncorr)
+        assert abs(stats[b].final_cost - gold[f"fit_cost_{b}"][1]) <= 1e-6 * gold[f"fit_cost_{b}"][1]
+        assert int(gold[f"num_points_{b}"]) == off[b + 1] - off[b]

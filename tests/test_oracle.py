@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, ROOT
 
 
 def rand_x(model_J, model_K, rng, scale=0.4):
@@ -486,3 +486,24 @@ def test_build_cloud_oracle_equals_the_references_own_depth_to_xyz(oracle_mod, m
         want[:, 1] = -want[:, 1]
         assert len(pts) == len(rr) > 5000
         assert np.array_equal(pts, want) and np.array_equal(lab, part[rr, cc].astype(np.int32))
+
+
+# ---------------------------------------------------------------------------------------------
+# golden OUTPUT vectors (tests/golden/expected_r1.npz, frozen by tools/make_golden_outputs.py)
+# ---------------------------------------------------------------------------------------------
+def test_oracle_reproduces_the_frozen_golden_outputs(build_all):
+    """the reference ships no golden vectors, so the oracle's outputs on the seeded fixtures are frozen and
+    versioned here: fitted parameters, costs, NN index checksums, cloud / RTree / renderer image checksums.  Guards
+    the oracle (and through the parity tests the device path) against silent drift."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_outputs", os.path.join(ROOT, "tools", "make_golden_outputs.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    got = mod.compute()
+    want = np.load(os.path.join(GOLDEN, "expected_r1.npz"))
+    assert sorted(got) == sorted(want.files)
+    for k in want.files:
+        if k.startswith("fit_x") or k.startswith("fit_cost"):
+            np.testing.assert_allclose(got[k], want[k], rtol=1e-9, atol=1e-9, err_msg=k)   # libm / numpy versions may move last bits
+        else:
+            assert np.array_equal(np.asarray(got[k]), want[k]), k
