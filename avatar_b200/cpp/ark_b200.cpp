@@ -422,3 +422,69 @@ extern "C" int ark_b200_rtree_probe(const char* path, int32_t* counts3, float* u
         return 3;
     }
 }
+
+// ---- ark::CameraIntrin (Calibration.cpp:13-51, 68-80, 97-111); only without OpenCV, like its declaration --------------
+#if !__has_include(<opencv2/core.hpp>)
+namespace ark {
+void CameraIntrin::clear() {
+    fx = fy = cx = cy = 0.f;
+    std::fill(k, k + 6, 0.f);
+    std::fill(p, p + 2, 0.f);
+}
+bool CameraIntrin::readFile(const std::string& path) {
+    clear();
+    std::ifstream ifs(path);
+    int good = 0;
+    while (ifs) {
+        std::string tag;
+        ifs >> tag;
+        if (tag.size() != 2) continue;
+        if (tag == "cx") { ifs >> cx; ++good; }
+        else if (tag == "cy") { ifs >> cy; ++good; }
+        else if (tag == "fx") { ifs >> fx; ++good; }
+        else if (tag == "fy") { ifs >> fy; ++good; }
+        else if (tag[0] == 'k') {
+            const int idx = tag[1] - '1';
+            if (idx < 0 || idx >= 6) continue;
+            ifs >> k[idx];
+        } else if (tag[0] == 'p') {
+            const int idx = tag[1] - '1';
+            if (idx < 0 || idx >= 6) continue;   // the reference checks against 6 here too (p has 2 entries)
+            if (idx < 2) ifs >> p[idx];
+            else { float skip; ifs >> skip; }
+        }
+    }
+    return good == 4;
+}
+bool CameraIntrin::writeFile(const std::string& path) const {
+    std::ofstream ofs(path);
+    if (!ofs) return false;
+    ofs << "fx " << fx << "\ncx " << cx << "\nfy " << fy << "\ncy " << cy << "\n";
+    for (int i = 0; i < 6; ++i)
+        if (k[i] != 0.f) ofs << "k" << i << " " << k[i] << "\n";   // 0-based tags, as the reference writes them
+    for (int i = 0; i < 2; ++i)
+        if (p[i] != 0.f) ofs << "p" << i << " " << p[i] << "\n";
+    return true;
+}
+void CameraIntrin::to3D(float px, float py, float depth, float out[3]) const {
+    out[0] = (px - cx) * depth / fx;
+    out[1] = (py - cy) * depth / fy;
+    out[2] = depth;
+}
+void CameraIntrin::to2D(const float xyz[3], float out[2]) const {
+    out[0] = xyz[0] * fx / xyz[2] + cx;
+    out[1] = xyz[1] * fy / xyz[2] + cy;
+}
+}  // namespace ark
+
+// test hook: read an intrinsics file with the facade, write it back, return the twelve numbers
+extern "C" int ark_b200_intrin_probe(const char* path_in, const char* path_out, float* out12) {
+    ark::CameraIntrin c;
+    const bool ok = c.readFile(path_in);
+    out12[0] = c.fx; out12[1] = c.fy; out12[2] = c.cx; out12[3] = c.cy;
+    for (int i = 0; i < 6; ++i) out12[4 + i] = c.k[i];
+    out12[10] = c.p[0]; out12[11] = c.p[1];
+    if (path_out && !c.writeFile(path_out)) return 2;
+    return ok ? 0 : 1;
+}
+#endif

@@ -7,9 +7,20 @@
 
 namespace ark {
 #if !__has_include(<opencv2/core.hpp>)
-/** include/Calibration.h: pinhole intrinsics; stored by the optimizer and otherwise unused on this path */
+/** include/Calibration.h:11-76: pinhole intrinsics with the reference's text file format (Calibration.cpp:19-51,
+ *  97-111; tags fx/fy/cx/cy, k1..k6, p1..p2 on reading -- the writer emits 0-based k/p tags, a reference quirk kept) */
 struct CameraIntrin {
     float fx = 0, fy = 0, cx = 0, cy = 0;
+    float k[6] = {0, 0, 0, 0, 0, 0};
+    float p[2] = {0, 0};
+    CameraIntrin() {}
+    explicit CameraIntrin(const std::string& path) { readFile(path); }
+    void clear();
+    bool readFile(const std::string& path);          // true iff fx, fy, cx, cy were all present
+    bool writeFile(const std::string& path) const;
+    /** Calibration.cpp:68-74 / :76-80, float arithmetic */
+    void to3D(float px, float py, float depth, float out_xyz[3]) const;
+    void to2D(const float xyz[3], float out_xy[2]) const;
 };
 #endif
 

@@ -53,4 +53,16 @@ void ref_depth_to_xyz(const float* depth, int W, int H, float fx, float cx, floa
     const cv::Mat out = k.depthToXYZ(d);
     std::memcpy(xyz, out.data, (size_t)W * H * 12);
 }
+
+/* CameraIntrin::readFile / writeFile of the reference (Calibration.cpp:19-51, 97-111): read path_in, optionally write
+ * path_out, return fx, fy, cx, cy, k[6], p[2]; result 0 iff readFile returned true */
+int ref_intrin_probe(const char* path_in, const char* path_out, float* out12) {
+    ark::CameraIntrin c;
+    const bool ok = c.readFile(path_in);
+    out12[0] = c.fx; out12[1] = c.fy; out12[2] = c.cx; out12[3] = c.cy;
+    for (int i = 0; i < 6; ++i) out12[4 + i] = c.k[i];
+    out12[10] = c.p[0]; out12[11] = c.p[1];
+    if (path_out && !c.writeFile(path_out)) return 2;
+    return ok ? 0 : 1;
+}
 }  // extern "C"

@@ -92,3 +92,30 @@ def test_facade_rtree_loader_matches_the_python_mirror(build_all, tmp_path):
         assert pm[0] == 0 and pm[1] == 3 and list(pm[2:5]) == [0, 0, 1]
         assert rtree.read_partmap(p + ".partmap") == ([0, 0, 1], 2, 0)
     assert lib.ark_b200_rtree_probe(str(tmp_path / "missing.srtr").encode(), counts, None, None, None, 0, 0, pm) == 1
+
+
+def test_facade_camera_intrin_matches_the_reference(build_all, tmp_path):
+    """ark::CameraIntrin of the facade against the reference's own Calibration.cpp (compiled into oracle/_ref): same
+    numbers read, same file written back (incl. the reference's 0-based k/p tags on writing)"""
+    import ctypes as C
+    fac = C.CDLL(os.path.join(ROOT, "avatar_b200", "libark_b200.so"))
+    ref_path = os.path.join(ROOT, "oracle", "_ref", "libref_painters.so")
+    src = tmp_path / "intrin.txt"
+    src.write_text("fx 606.438\ncx 637.294\nfy 606.351\ncy 366.992\nk1 0.51\nk2 -2.7\nk6 1e-3\np1 0.0004\np2 -7e-5\nzz 9\nk9 4\n")
+    a, b = (C.c_float * 12)(), (C.c_float * 12)()
+    out_a, out_b = str(tmp_path / "a.txt"), str(tmp_path / "b.txt")
+    assert fac.ark_b200_intrin_probe(str(src).encode(), out_a.encode(), a) == 0
+    assert list(a)[:4] == [np.float32(606.438), np.float32(606.351), np.float32(637.294), np.float32(366.992)]
+    assert a[4] == np.float32(0.51) and a[5] == np.float32(-2.7) and a[9] == np.float32(1e-3) and a[10] == np.float32(0.0004)
+    incomplete = tmp_path / "bad.txt"
+    incomplete.write_text("fx 1\nfy 2\ncx 3\n")
+    assert fac.ark_b200_intrin_probe(str(incomplete).encode(), None, a) == 1
+    if not os.path.exists(ref_path):
+        pytest.skip("oracle/_ref/libref_painters.so not built (reference tree absent)")
+    ref = C.CDLL(ref_path)
+    a2 = (C.c_float * 12)()
+    assert fac.ark_b200_intrin_probe(str(src).encode(), out_a.encode(), a2) == 0
+    assert ref.ref_intrin_probe(str(src).encode(), out_b.encode(), b) == 0
+    assert list(a2) == list(b)
+    assert open(out_a).read() == open(out_b).read()
+    assert ref.ref_intrin_probe(str(incomplete).encode(), None, b) == 1
