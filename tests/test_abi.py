@@ -93,3 +93,27 @@ def test_shard_and_gather_world2_gloo(tmp_path):
     out = np.load(str(tmp_path / "out.npy"))
     assert out.shape == (10, 109)
     np.testing.assert_array_equal(out[:, 0], np.arange(10))
+
+
+def test_widened_entry_points_validate_without_a_gpu(build_all):
+    """the entry points of the widened rows (cloud construction, RTree, renderer) reject null handles / arguments with
+    AVB_ERR_INVALID before touching CUDA"""
+    from avatar_b200 import _lib
+    lib = _lib.lib
+    img = _lib.ImageDesc(640, 576, 504.0, 320.0, 504.0, 288.0, 1, 16, 2)
+    view = _lib.RenderDesc(640, 576, 504.0, 320.0, 504.0, 288.0)
+    tree = _lib.RTreeDesc()
+    ms = (C.c_float * 4)()
+    calls = [
+        lambda: lib.avb_upload_depth_batch(None, 1, None, None, None, C.byref(img), None),
+        lambda: lib.avb_download_batch(None, None, None, None),
+        lambda: lib.avb_last_cloud_ms(None, ms),
+        lambda: lib.avb_fitter_set_rtree(None, C.byref(tree)),
+        lambda: lib.avb_rtree_predict_batch(None, 1, None, 640, 576, None, 1, 1, None),
+        lambda: lib.avb_last_rtree_ms(None, ms),
+        lambda: lib.avb_render_batch(None, 1, None, C.byref(view), None, None, None),
+        lambda: lib.avb_last_render_ms(None, ms),
+    ]
+    for call in calls:
+        assert call() == 1                                  # AVB_ERR_INVALID
+        assert len(lib.avb_last_error()) > 0
