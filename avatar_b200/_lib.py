@@ -107,10 +107,6 @@ SYMBOLS = [
     ("avb_debug_correspond", C.c_int, [_P, _P, C.POINTER(Options)]),
     ("avb_debug_read", C.c_int, [_P, C.c_int, _P, C.c_uint64]),
     ("avb_debug_evaluate", C.c_int, [_P, _P, C.POINTER(Options), _P, _P, _P]),
-    ("avb_synth_render", C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_float, C.c_float,
-                                   C.c_float, C.c_float, _P, _P]),
-    ("avb_synth_backproject", C.c_int64, [_P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float,
-                                          C.c_int32, _P, _P, C.c_int64]),
 ]
 
 JTJ_FP64, JTJ_FP32, JTJ_BF16_TENSOR = 0, 1, 2

@@ -83,6 +83,7 @@ struct avb_fitter {
     int num_parts = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
+    cudaEvent_t hx_ev = nullptr; bool hx_busy = false;   // recorded after the H2D copy that reads the h_x staging buffer
     DevModel dm{};
     DevParts dp{};
     std::vector<void*> allocs;  // everything cudaMalloc'ed, freed in destroy
@@ -159,6 +160,45 @@ int pin_alloc(avb_fitter* ft, T** p, size_t count) {
     cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T), cudaHostAllocDefault);
     if (e != cudaSuccess) return fail(AVB_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
     ft->pinned.push_back(*p);
+    return AVB_OK;
+}
+template <class T>
+void dev_release(avb_fitter* ft, T** p) {   // frees one dev_alloc'ed buffer now (not at destroy)
+    if (!*p) return;
+    auto it = std::find(ft->allocs.begin(), ft->allocs.end(), static_cast<void*>(*p));
+    if (it != ft->allocs.end()) ft->allocs.erase(it);
+    cudaFree(*p);
+    *p = nullptr;
+}
+template <class T>
+void pin_release(avb_fitter* ft, T** p) {
+    if (!*p) return;
+    auto it = std::find(ft->pinned.begin(), ft->pinned.end(), static_cast<void*>(*p));
+    if (it != ft->pinned.end()) ft->pinned.erase(it);
+    cudaFreeHost(*p);
+    *p = nullptr;
+}
+// NN chunk tables (device + pinned mirrors) for at least `need` chunks; the stream must be idle when they grow
+int ensure_chunk_tables(avb_fitter* ft, size_t need) {
+    if (need <= (size_t)ft->max_chunks) return AVB_OK;
+    cudaError_t e = cudaStreamSynchronize(ft->stream);
+    if (e != cudaSuccess) return fail(AVB_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+    dev_release(ft, &ft->d_chunk_frame); dev_release(ft, &ft->d_chunk_count); dev_release(ft, &ft->d_chunk_qblock);
+    dev_release(ft, &ft->d_chunk_begin);
+    pin_release(ft, &ft->h_chunk_frame); pin_release(ft, &ft->h_chunk_count); pin_release(ft, &ft->h_chunk_qblock);
+    pin_release(ft, &ft->h_chunk_begin);
+    ft->max_chunks = 0;
+    need += need / 4 + 64;
+    int rc = dev_alloc(ft, &ft->d_chunk_frame, need);
+    if (rc == AVB_OK) rc = dev_alloc(ft, &ft->d_chunk_count, need);
+    if (rc == AVB_OK) rc = dev_alloc(ft, &ft->d_chunk_qblock, need);
+    if (rc == AVB_OK) rc = dev_alloc(ft, &ft->d_chunk_begin, need);
+    if (rc == AVB_OK) rc = pin_alloc(ft, &ft->h_chunk_frame, need);
+    if (rc == AVB_OK) rc = pin_alloc(ft, &ft->h_chunk_count, need);
+    if (rc == AVB_OK) rc = pin_alloc(ft, &ft->h_chunk_qblock, need);
+    if (rc == AVB_OK) rc = pin_alloc(ft, &ft->h_chunk_begin, need);
+    if (rc != AVB_OK) return rc;
+    ft->max_chunks = (int)need;
     return AVB_OK;
 }
 template <class T>
@@ -483,6 +523,7 @@ void avb_fitter_destroy(avb_fitter* ft) {
     for (void* p : ft->pinned) cudaFreeHost(p);
     for (auto& e : ft->ev)
         if (e) cudaEventDestroy(e);
+    if (ft->hx_ev) cudaEventDestroy(ft->hx_ev);
     for (auto& e : ft->copied) cudaEventDestroy(e);
     for (auto& e : ft->pev) cudaEventDestroy(e);
     cudaFree(ft->d_depth); cudaFree(ft->d_parts); cudaFree(ft->d_roi); cudaFree(ft->d_strip_count);
@@ -515,6 +556,15 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major < 10) return fail(AVB_ERR_CUDA, "avatar_b200 kernels are built for sm_100a only");
+    {   // the kernels' shared-memory budgets, checked here instead of failing as an opaque launch error at fit time
+        const size_t optin = (size_t)prop.sharedMemPerBlockOptin;
+        if (nn_smem_bytes(m->V) > optin)
+            return fail(AVB_ERR_INVALID, "model too large for nn_kernel: the visible model cloud of a frame (24 B per vertex) must fit the " +
+                                             std::to_string(optin / 1024) + " KB of shared memory of one CTA (V <= " +
+                                             std::to_string((optin - 256) / 24) + ")");
+        if (pose_smem_bytes(m->V, m->J, m->K) > optin)
+            return fail(AVB_ERR_INVALID, "model too large for pose_visibility_kernel (one visibility byte per vertex in shared memory)");
+    }
 
     auto ft = new avb_fitter;
     ft->model = m;
@@ -542,6 +592,7 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     } while (0)
     CUDA_TRY_FT(cudaStreamCreateWithFlags(&ft->stream, cudaStreamNonBlocking));
     for (auto& e : ft->ev) CUDA_TRY_FT(cudaEventCreate(&e));
+    CUDA_TRY_FT(cudaEventCreateWithFlags(&ft->hx_ev, cudaEventDisableTiming));
 
     // ---- model -> device ----
     DevModel& dm = ft->dm;
@@ -781,6 +832,20 @@ int ensure_image_staging(avb_fitter* ft, size_t npx, size_t strip_slots) {
     return AVB_OK;
 }
 
+// A bounding box handed to the RTree kernels must lie inside the image: the probes are looked up "inside the box"
+// (RTree.cpp:52-67), so a box that leaves the image would read a neighbouring row or frame.  Empty boxes are fine.
+int validate_rtree_roi(const int32_t* roi, int batch, int width, int height) {
+    if (!roi) return AVB_OK;
+    for (int f = 0; f < batch; ++f) {
+        const int x0 = roi[4 * f], y0 = roi[4 * f + 1], x1 = roi[4 * f + 2], y1 = roi[4 * f + 3];
+        if (x1 < x0 || y1 < y0) continue;   // empty box: nothing is predicted
+        if (x0 < 0 || y0 < 0 || x1 >= width || y1 >= height)
+            return fail(AVB_ERR_INVALID, "RTree bounding box of frame " + std::to_string(f) +
+                                             " leaves the image (need 0 <= x0 <= x1 < width, 0 <= y0 <= y1 < height; inclusive corners)");
+    }
+    return AVB_OK;
+}
+
 // RTree::predictBest + upscaleGrid on the depth images resident in d_depth -> d_parts (roi already in d_roi if given)
 int enqueue_rtree(avb_fitter* ft, int batch, int width, int height, const int32_t* roi_host, bool roi_on_device, int interval,
                   bool fill) {
@@ -829,6 +894,10 @@ int avb_upload_depth_batch(avb_fitter* ft, int32_t batch, const float* depth, co
     if (img->width <= 0 || img->height <= 0 || img->interval <= 0) return fail(AVB_ERR_INVALID, "bad image description");
     if (img->num_parts <= 0 || img->num_parts > 255) return fail(AVB_ERR_INVALID, "num_parts must be in 1..255");
     if (!(img->fx != 0.f) || !(img->fy != 0.f)) return fail(AVB_ERR_INVALID, "focal lengths must be non-zero");
+    if (!parts) {
+        const int rcv = validate_rtree_roi(roi, batch, img->width, img->height);
+        if (rcv != AVB_OK) return rcv;
+    }
     CUDA_TRY(cudaSetDevice(ft->device));
     cudaStream_t st = ft->stream;
     const size_t px = (size_t)img->width * img->height, npx = px * batch;
@@ -910,10 +979,9 @@ int avb_fitter_set_rtree(avb_fitter* ft, const avb_rtree_desc* t) {
     }
     CUDA_TRY(cudaSetDevice(ft->device));
     CUDA_TRY(cudaStreamSynchronize(ft->stream));
-    cudaFree(ft->d_rt_nodes); cudaFree(ft->d_rt_leaf);
-    cudaFree(ft->d_win); cudaFree(ft->d_rdepth); cudaFree(ft->d_rparts); cudaFree(ft->d_rfaces); cudaFree(ft->d_proj); cudaFree(ft->d_order);
-    for (auto& e : ft->nev) if (e) cudaEventDestroy(e);
+    cudaFree(ft->d_rt_nodes); cudaFree(ft->d_rt_leaf);   // only the previous tree: the renderer buffers are not this call's
     ft->d_rt_nodes = nullptr; ft->d_rt_leaf = nullptr;
+    ft->rt_nodes = ft->rt_leaves = 0;
     CUDA_TRY(cudaMalloc(&ft->d_rt_nodes, nodes.size() * sizeof(RTreeNode)));
     CUDA_TRY(cudaMalloc(&ft->d_rt_leaf, (size_t)t->num_leaves));
     CUDA_TRY(cudaMemcpy(ft->d_rt_nodes, nodes.data(), nodes.size() * sizeof(RTreeNode), cudaMemcpyHostToDevice));
@@ -926,6 +994,12 @@ int avb_rtree_predict_batch(avb_fitter* ft, int32_t batch, const float* depth, i
                             int32_t interval, int32_t fill_in_gaps, uint8_t* parts_out) {
     if (!ft || !depth || !parts_out || batch <= 0 || width <= 0 || height <= 0) return fail(AVB_ERR_INVALID, "null argument or empty batch");
     if (batch > ft->max_batch) return fail(AVB_ERR_CAPACITY, "batch exceeds fitter capacity");
+    if (!ft->d_rt_nodes) return fail(AVB_ERR_INVALID, "no decision tree: call avb_fitter_set_rtree first");
+    if (interval <= 0) return fail(AVB_ERR_INVALID, "RTree interval must be positive");
+    {
+        const int rcv = validate_rtree_roi(roi, batch, width, height);
+        if (rcv != AVB_OK) return rcv;
+    }
     CUDA_TRY(cudaSetDevice(ft->device));
     const size_t npx = (size_t)width * height * batch;
     int rc = ensure_image_staging(ft, npx, 0);
@@ -1148,8 +1222,13 @@ int avb_fit_resident(avb_fitter* ft, const double* x_in, const avb_options* o) {
     cudaStream_t st = ft->stream;
     const int B = ft->batch;
     const size_t nx = ft->model->nx;
+    // h_x is the one pinned staging buffer of the start points: the copy of the previous (still queued) call must have
+    // read it before it is rewritten, or back-to-back fits from different warm starts would see each other's x
+    if (ft->hx_busy) CUDA_TRY(cudaEventSynchronize(ft->hx_ev));
     std::memcpy(ft->h_x, x_in, (size_t)B * nx * 8);
     CUDA_TRY(cudaMemcpyAsync(ft->d_x, ft->h_x, (size_t)B * nx * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaEventRecord(ft->hx_ev, st));
+    ft->hx_busy = true;
     ft->launches = 0;
     ft->last_icp = o->icp_iters;
     ft->pcls.clear();
@@ -1343,6 +1422,7 @@ int avb_render_batch(avb_fitter* ft, int32_t batch, const double* x, const avb_r
     if (batch > ft->max_batch) return fail(AVB_ERR_CAPACITY, "batch exceeds fitter capacity");
     if (d->width <= 0 || d->height <= 0 || (size_t)d->width * d->height >= ((size_t)1 << 31)) return fail(AVB_ERR_INVALID, "bad image size");
     if (ft->model->F > render_max_faces()) return fail(AVB_ERR_CAPACITY, "the renderer sorts at most 16384 faces per frame");
+    if (ft->model->F <= 0) return fail(AVB_ERR_INVALID, "the model has no mesh (hasMesh == false): nothing to render");
     if (!depth_out && !parts_out && !faces_out) return AVB_OK;
     CUDA_TRY(cudaSetDevice(ft->device));
     cudaStream_t st = ft->stream;
@@ -1421,6 +1501,9 @@ int avb_track_sequence(avb_fitter* ft, int32_t T, const double* clouds, const in
     }
     const size_t nx = ft->model->nx, V = ft->model->V;
     if (ft->seq_cap < T) {
+        dev_release(ft, &ft->d_xseq); dev_release(ft, &ft->d_stats_seq);
+        pin_release(ft, &ft->h_xseq); pin_release(ft, &ft->h_stats_seq);
+        ft->seq_cap = 0;
         rc = dev_alloc(ft, &ft->d_xseq, (size_t)T * nx);
         if (rc == AVB_OK) rc = dev_alloc(ft, &ft->d_stats_seq, (size_t)T);
         if (rc == AVB_OK) rc = pin_alloc(ft, &ft->h_xseq, (size_t)T * nx);
@@ -1431,9 +1514,19 @@ int avb_track_sequence(avb_fitter* ft, int32_t T, const double* clouds, const in
     // per-frame NN chunk schedule; every frame is "frame 0" of a batch of one
     std::vector<int> c0(T + 1, 0), q0(T + 1, 0);
     int nc = 0, qb = 0;
+    {   // a long sequence of small frames needs more chunk slots than total points / 512: size the tables from the frames
+        size_t need = 0;
+        for (int t = 0; t < T; ++t) {
+            const int64_t n = offsets[t + 1] - offsets[t];
+            if (n < 0 || n > ((int64_t)1 << 21)) return fail(AVB_ERR_INVALID, "bad offsets");
+            const int64_t target = std::max<int64_t>(512, (n / (4 * (int64_t)ft->num_sms) + 511) / 512 * 512);
+            need += (size_t)((n + target - 1) / target);
+        }
+        rc = ensure_chunk_tables(ft, need);
+        if (rc != AVB_OK) return rc;
+    }
     for (int t = 0; t < T; ++t) {
         const int64_t n = offsets[t + 1] - offsets[t];
-        if (n < 0 || n > ((int64_t)1 << 21)) return fail(AVB_ERR_INVALID, "bad offsets");
         c0[t] = nc;
         q0[t] = qb;
         if (n > 0) {
@@ -1506,7 +1599,13 @@ int avb_track_sequence(avb_fitter* ft, int32_t T, const double* clouds, const in
     CUDA_TRY(launch_pose_visibility(ft->dm, ft->dp, pa, 1, st));
     CUDA_TRY(cudaMemcpyAsync(ft->h_xseq, ft->d_xseq, (size_t)T * nx * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(ft->h_stats_seq, ft->d_stats_seq, (size_t)T * sizeof(FrameStats), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ft->h_qctrl, ft->d_qctrl, 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (ft->h_qctrl[3] != 0u) {   // a starved work queue must not return stale parameters as AVB_OK
+        cudaMemset(ft->d_qctrl, 0, 32);
+        cudaMemset(ft->d_qslots, 0xFF, (size_t)ft->qcap * 8);
+        return fail(AVB_ERR_CUDA, "lm_flow_kernel watchdog fired: the work queue starved (internal error)");
+    }
     std::memcpy(x_out, ft->h_xseq, (size_t)T * nx * 8);
     ft->offsets.assign(2, 0);
     ft->offsets[1] = offsets[T] - offsets[T - 1];

@@ -218,7 +218,9 @@ nn_kernel(DevParts Pt, NNArgs a) {
             for (int k = s; k < e; ++k) {
                 // nanoflann L2_Simple: sum_c (a_c - b_c)^2, c = 0,1,2 (nanoflann.hpp:423-445); strict '<'
                 const double d0 = q0 - mxyz[3 * k], d1 = q1 - mxyz[3 * k + 1], d2 = qz - mxyz[3 * k + 2];
-                const double dist = __fma_rn(d2, d2, __fma_rn(d1, d1, __dmul_rn(d0, d0)));
+                // ((d0^2 + d1^2) + d2^2) with every product and sum rounded: the reference is built without -march
+                // (CMakeLists.txt:37), so `result += diff * diff` is never contracted into an FMA
+                const double dist = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
                 if (dist < best) {
                     best = dist;
                     bi = k;
@@ -269,14 +271,20 @@ size_t pose_smem_bytes(int V, int J, int K) {
     return (size_t)(((nx + 1) & ~1) + tables_doubles(J, K, false)) * 8 + 64 * 4 + (size_t)V + 64;
 }
 
+size_t nn_smem_bytes(int V) { return (((size_t)V * 24 + 15) & ~(size_t)15) + 128; }
+
 cudaError_t launch_pose_visibility(const DevModel& M, const DevParts& Pt, const PoseArgs& a, int batch, cudaStream_t st) {
     const size_t smem = pose_smem_bytes(M.V, M.J, M.K);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(pose_visibility_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     pose_visibility_kernel<<<batch, 512, smem, st>>>(M, Pt, a);
     return cudaGetLastError();
 }
 
 cudaError_t launch_nn(const DevParts& Pt, const NNArgs& a, int num_chunks, cudaStream_t st) {
-    const size_t smem = (((size_t)a.V * 24 + 15) & ~(size_t)15) + 128;
+    const size_t smem = nn_smem_bytes(a.V);
     {   // per device/context attribute: set on every launch (cheap host call)
         cudaError_t e = cudaFuncSetAttribute(nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -140,6 +140,7 @@ int cloud_strip_rows();
 cudaError_t launch_cloud_count(const CloudArgs& a, int strips, int batch, cudaStream_t st);
 cudaError_t launch_cloud_compact(const CloudArgs& a, int strips, int batch, cudaStream_t st);
 size_t pose_smem_bytes(int V, int J, int K);
+size_t nn_smem_bytes(int V);
 cudaError_t launch_pose_visibility(const DevModel& M, const DevParts& Pt, const PoseArgs& a, int batch, cudaStream_t st);
 cudaError_t launch_nn(const DevParts& Pt, const NNArgs& a, int num_chunks, cudaStream_t st);
 cudaError_t launch_lm_prep(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, cudaStream_t st);

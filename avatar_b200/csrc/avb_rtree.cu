@@ -53,11 +53,13 @@ rtree_predict_kernel(RTreeArgs a) {
             const int ux = (int)roundf(__fdiv_rn(nd.ux, sampleDepth)) + c, uy = (int)roundf(__fdiv_rn(nd.uy, sampleDepth)) + r;
             const int vx = (int)roundf(__fdiv_rn(nd.vx, sampleDepth)) + c, vy = (int)roundf(__fdiv_rn(nd.vy, sampleDepth)) + r;
             float zu = kBackgroundDepth, zv = kBackgroundDepth;
-            if (!(ux < x0 || uy < y0 || ux > x1 || uy > y1)) {
+            // inside the box AND inside the image (the entry points reject boxes that leave the image; this keeps the
+            // gather in bounds even so)
+            if (!(ux < x0 || uy < y0 || ux > x1 || uy > y1) && (unsigned)ux < (unsigned)a.width && (unsigned)uy < (unsigned)a.height) {
                 zu = depth[(size_t)uy * a.width + ux];
                 if (zu == 0.f) zu = kBackgroundDepth;
             }
-            if (!(vx < x0 || vy < y0 || vx > x1 || vy > y1)) {
+            if (!(vx < x0 || vy < y0 || vx > x1 || vy > y1) && (unsigned)vx < (unsigned)a.width && (unsigned)vy < (unsigned)a.height) {
                 zv = depth[(size_t)vy * a.width + vx];
                 if (zv == 0.f) zv = kBackgroundDepth;
             }

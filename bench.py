@@ -46,7 +46,7 @@ def make_model():
 
 
 def gen_params(model, seeds):
-    from avatar_b200 import synth
+    from harness import synth
     xg, x0 = [], []
     for s in seeds:
         rng = np.random.default_rng(100000 + int(s))
@@ -57,7 +57,7 @@ def gen_params(model, seeds):
 
 
 def render_frames(model, part_map, clouds_gt):
-    from avatar_b200 import synth
+    from harness import synth
     pts, labs = [], []
     for c in clouds_gt:
         p, l, _, _ = synth.render_cloud(model, c, part_map)
@@ -445,7 +445,7 @@ def main():
             line["secondary"]["icp10_x_1iter_error"] = str(exc)
         try:
             # ---- data-cloud construction on the device from depth + part-label images ----
-            from avatar_b200 import synth
+            from harness import synth
             NI = min(256, F)
             dimg = pinned_array(_lib.lib, (NI, synth.HEIGHT, synth.WIDTH), np.float32)   # pinned, like the cloud batches
             pimg = pinned_array(_lib.lib, (NI, synth.HEIGHT, synth.WIDTH), np.uint8)

@@ -1,9 +1,11 @@
-// avb_synth.cpp -- synthetic-data harness (host CPU code; NOT on the fit path).
+// avb_synth.cpp -- synthetic-data harness (host CPU code; NOT on the fit path, NOT part of libavatar_b200.so).
 // Functional stand-in for AvatarRenderer::renderDepth / renderPartMask (AvatarRenderer.cpp:72-216,
 // AvatarHelpers.cpp:61-313) and for the depth -> cloud back-projection the reference's callers do
 // (optim.cpp:104-120, demo.cpp:226-250, Calibration.cpp:68-74).  Own z-buffer rasteriser; exactness
 // against the reference's painter's algorithm is not required.
-#include "../../include/avatar_b200.h"
+#include <cstdint>
+#define AVB_ERR_INVALID 1
+#define AVB_OK 0
 
 #include <algorithm>
 #include <cmath>

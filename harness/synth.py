@@ -1,9 +1,68 @@
 """Synthetic smplsynth-style frames: the recipe of Avatar::randomize
 (Avatar.cpp:77-126), the optim.cpp:74-145 scenario (render -> back-project -> perturbed start) and
-the fixed 640x576 intrinsics.  Harness code: the rasteriser is host C++ (avb_synth_*), the fit is not."""
+the fixed 640x576 intrinsics.
+
+TEST / BENCH HARNESS, not product: the rasteriser is host C++ in harness/libavb_harness.so (its own shared object, so
+that a process that only generates fixtures -- bench.py --impl reference -- never maps the product library), and
+nothing here imports avatar_b200.  Functions take any model object with the reference's member names
+(numJoints(), numShapeKeys(), posePrior, assignedJoints, mesh): avatar_b200.AvatarModel or the plain-numpy HostModel
+below."""
+import ctypes as C
+import os
+import subprocess
+
 import numpy as np
 
-from ._lib import lib, ptr, check
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libavb_harness.so")
+if not os.path.exists(LIB_PATH):
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+lib = C.CDLL(LIB_PATH)
+_P = C.c_void_p
+lib.avb_synth_render.restype = C.c_int
+lib.avb_synth_render.argtypes = [_P, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float,
+                                 C.c_float, _P, _P]
+lib.avb_synth_backproject.restype = C.c_int64
+lib.avb_synth_backproject.argtypes = [_P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
+                                      _P, _P, C.c_int64]
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError(f"harness call failed with code {rc}")
+
+
+class _Prior:
+    pass
+
+
+class HostModel:
+    """the members of ark::AvatarModel the generators read, loaded with numpy only (model.npz schema of
+    AvatarModel.cpp:26-102); used where the product library must not be loaded"""
+
+    def __init__(self, npz_path, prior_arrays):
+        npz = np.load(npz_path)
+        weights = np.asarray(npz["weights"], dtype=np.float64)
+        self.parent = np.asarray(npz["kintree_table"])[0].astype(np.uint32).astype(np.int32)
+        self.mesh = np.ascontiguousarray(np.asarray(npz["f"]).astype(np.int64).astype(np.int32))
+        self._K = int(np.asarray(npz["shapedirs"]).shape[2])
+        self.assignedJoints = []
+        for v in range(weights.shape[0]):   # (weight, joint), weight > 1e-12, descending by the pair (AvatarModel.cpp:74-94)
+            nz = np.nonzero(weights[v] > 1e-12)[0]
+            self.assignedJoints.append(sorted(((float(weights[v, j]), int(j)) for j in nz), reverse=True))
+        g = _Prior()
+        g.weight = np.ascontiguousarray(prior_arrays["weights"], dtype=np.float64)
+        g.mean = np.ascontiguousarray(prior_arrays["means"], dtype=np.float64)
+        g.cov = np.ascontiguousarray(prior_arrays["covs"], dtype=np.float64)
+        g.nComps, g.nDims = g.mean.shape
+        self.posePrior = g
+
+    def numJoints(self): return int(self.parent.shape[0])
+    def numShapeKeys(self): return self._K
 
 WIDTH, HEIGHT = 640, 576
 FX = FY = 504.0

@@ -281,16 +281,6 @@ int avb_debug_read(avb_fitter* fitter, int what, void* out, uint64_t bytes);
 int avb_debug_evaluate(avb_fitter* fitter, const double* x_in, const avb_options* opt, double* cost,
                        double* grad, double* H);
 
-/* Synthetic-data harness (host CPU code, not on the fit path): functional stand-in for
- * AvatarRenderer::renderDepth / renderPartMask (AvatarRenderer.cpp:72-216) and the depth ->
- * cloud back-projection of optim.cpp:104-120 / demo.cpp:226-250 (float arithmetic, y negated). */
-int avb_synth_render(const double* cloud, int32_t V, const int32_t* faces, int32_t F,
-                     const int32_t* vertex_part, int32_t width, int32_t height, float fx, float fy,
-                     float cx, float cy, float* depth_out, uint8_t* part_out);
-int64_t avb_synth_backproject(const float* depth, const uint8_t* part, int32_t width, int32_t height,
-                              float fx, float fy, float cx, float cy, int32_t interval,
-                              double* cloud_out, int32_t* labels_out, int64_t max_points);
-
 #ifdef __cplusplus
 }
 #endif

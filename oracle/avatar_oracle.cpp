@@ -1331,6 +1331,29 @@ void orc_find_nn(const orc_optimizer* o, const double* cloud, const uint8_t* vis
     find_nn(*o, cloud, vis, data, labels, N, method, 1, idx);
 }
 
+/* plain exact 1-NN of every query among pts[0..n) with the distance arithmetic of nanoflann.hpp:423-445 (strict <,
+ * lowest index wins exact ties); parallel over queries */
+void orc_brute_nn(const double* pts, int n, const double* queries, int nq, int32_t* out) {
+    const int nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+        th.emplace_back([=]() {
+            for (int i = t; i < nq; i += nt) {
+                double best = std::numeric_limits<double>::max();
+                int bi = -1;
+                for (int k = 0; k < n; ++k) {
+                    const double d = dist2(queries + 3 * (size_t)i, pts + 3 * (size_t)k);
+                    if (d < best) {
+                        best = d;
+                        bi = k;
+                    }
+                }
+                out[i] = bi;
+            }
+        });
+    for (auto& x : th) x.join();
+}
+
 static void build_problem(Common& cm, Problem& pb, const int32_t* idx, int N) {
     const int V = cm.V;
     std::vector<std::vector<int>> correspondences(V);

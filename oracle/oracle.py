@@ -313,11 +313,28 @@ def paint_check_render(cloud, faces, vertex_part, width, height, intrin):
     return dict(depth=depth, parts=parts, faces=fids, order=order)
 
 
-def ref_nanoflann_nn(points, queries):
-    """exact 1-NN through the reference's own vendored nanoflann (oracle/_ref); None if not built"""
-    if not os.path.exists(REF_NANOFLANN_PATH):
+def brute_nn(points, queries):
+    """exact brute-force 1-NN (nanoflann distance arithmetic, lowest index on exact ties)"""
+    points, queries = _f64(points), _f64(queries)
+    out = np.zeros(queries.shape[0], dtype=np.int32)
+    _lib.orc_brute_nn.argtypes = [_P, C.c_int, _P, C.c_int, _P]
+    _lib.orc_brute_nn.restype = None
+    _lib.orc_brute_nn(_p(points), points.shape[0], _p(queries), queries.shape[0], _p(out))
+    return out
+
+
+REF_NANOFLANN_FMA_PATH = os.path.join(_HERE, "_ref", "libref_nanoflann_fma.so")
+
+
+def ref_nanoflann_nn(points, queries, fma=False):
+    """exact 1-NN through the reference's own vendored nanoflann (oracle/_ref); None if not built.
+    fma=False: built with the reference's flags (CMakeLists.txt:37: -O3 -funroll-loops, no -march => no FMA);
+    fma=True: the same source built with -march=x86-64-v3 (GCC contracts `result += diff*diff`), kept to measure how
+    many answers depend on the contraction."""
+    path = REF_NANOFLANN_FMA_PATH if fma else REF_NANOFLANN_PATH
+    if not os.path.exists(path):
         return None
-    lib = C.CDLL(REF_NANOFLANN_PATH)
+    lib = C.CDLL(path)
     lib.ref_nanoflann_nn.argtypes = [_P, C.c_int, _P, C.c_int, _P]
     points, queries = _f64(points), _f64(queries)
     out = np.zeros(queries.shape[0], dtype=np.int32)

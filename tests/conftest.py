@@ -50,7 +50,7 @@ def model(build_all, prior_arrays):
 @pytest.fixture(scope="session")
 def frames(model, oracle_mod, omodel, prior_arrays):
     """a few deterministic synthetic frames: (x_gt, x_init, cloud Nx3, labels N)"""
-    from avatar_b200 import synth
+    from harness import synth
     out = []
     for seed in range(3):
         rng = np.random.default_rng(1000 + seed)

@@ -63,7 +63,7 @@ def test_no_cpu_fallback(model, prior_arrays):
 
 
 def test_synth_render_and_backproject(model, omodel, prior_arrays):
-    from avatar_b200 import synth
+    from harness import synth
     rng = np.random.default_rng(0)
     x = synth.random_params(model, rng)
     cloud, _, _ = omodel.update_x(x)

@@ -62,7 +62,8 @@ def test_facade_optimize_matches_oracle(model_dir, oracle_mod, oopt, frames, pri
 def test_facade_rtree_loader_matches_the_python_mirror(build_all, tmp_path):
     """ark::RTree::loadFile of the facade (binary 'R' format, legacy text, .partmap) against avatar_b200.rtree"""
     import ctypes as C
-    from avatar_b200 import synth, rtree
+    from avatar_b200 import rtree
+    from harness import synth
     lib = C.CDLL(os.path.join(ROOT, "avatar_b200", "libark_b200.so"))
     rng = np.random.default_rng(9)
     tree = synth.random_rtree(rng, 16, depth_levels=8)

@@ -235,7 +235,8 @@ def ava_params_from(x, oracle_mod):
 
 def test_tracking_sequence_matches_oracle(model, oracle_mod, oopt, omodel, prior_arrays):
     """BASELINE.json configs[3]: frames fitted in order, each warm-started from the previous fit (demo.cpp:252-268)"""
-    from avatar_b200 import Fitter, synth
+    from avatar_b200 import Fitter
+    from harness import synth
     rng = np.random.default_rng(77)
     xa, xb = synth.random_params(model, rng), synth.random_params(model, rng)
     T = 5
@@ -272,7 +273,8 @@ def test_tracking_sequence_matches_oracle(model, oracle_mod, oopt, omodel, prior
 def test_stress_dense_cloud_many_iterations(model, oracle_mod, oopt, omodel, prior_arrays):
     """BASELINE.json configs[4] shape: a dense (>150k points) cloud and up to 50 LM iterations; fp64 J^T J path
     (the bf16 tensor-core variant named there is not implemented in round 1)"""
-    from avatar_b200 import Fitter, synth
+    from avatar_b200 import Fitter
+    from harness import synth
     rng = np.random.default_rng(5)
     x_gt = synth.random_params(model, rng)
     x_gt[2] = 2.3
@@ -322,7 +324,7 @@ def test_bf16_tensor_core_jtj_path(fitter, oopt, frames):
 # data-cloud construction on the device (avb_upload_depth_batch)
 # ---------------------------------------------------------------------------------------------
 def _rendered(model, omodel, prior_arrays, seeds, width=None, height=None):
-    from avatar_b200 import synth
+    from harness import synth
     W, H = width or synth.WIDTH, height or synth.HEIGHT
     depth, parts, x0s = [], [], []
     for s in seeds:
@@ -346,7 +348,8 @@ def test_depth_cloud_construction_bit_exact(model, oracle_mod, omodel, prior_arr
     """device cloud construction == the oracle restatement of demo.cpp:215-250 + Calibration.cpp:83-95: same points
     (every coordinate bit for bit), same labels, same raster order, for whole images, bounding boxes, strides and
     the degenerate cases (empty box, all-background frame)"""
-    from avatar_b200 import Fitter, synth, AvbError
+    from avatar_b200 import Fitter, AvbError
+    from harness import synth
     nparts = int(prior_arrays["num_parts"])
     intrin = (synth.FX, synth.CX, synth.FY, synth.CY)
     depth, parts, _ = _rendered(model, omodel, prior_arrays, [0, 1, 2, 3])
@@ -375,7 +378,8 @@ def test_depth_cloud_construction_bit_exact(model, oracle_mod, omodel, prior_arr
 @pytest.mark.gpu
 def test_fit_from_depth_equals_fit_from_host_cloud(model, oracle_mod, omodel, prior_arrays):
     """a fit whose data clouds were built on the device is bit-identical to the fit of the host-built clouds"""
-    from avatar_b200 import Fitter, synth
+    from avatar_b200 import Fitter
+    from harness import synth
     nparts = int(prior_arrays["num_parts"])
     intrin = (synth.FX, synth.CX, synth.FY, synth.CY)
     depth, parts, x0 = _rendered(model, omodel, prior_arrays, [0, 1])
@@ -397,7 +401,8 @@ def test_fit_from_depth_equals_fit_from_host_cloud(model, oracle_mod, omodel, pr
 @pytest.mark.gpu
 def test_depth_cloud_construction_large_image(model, oracle_mod, omodel, prior_arrays):
     """2560x2304 render (configs[4] density, > 150k points), odd bounding box and stride"""
-    from avatar_b200 import Fitter, synth
+    from avatar_b200 import Fitter
+    from harness import synth
     nparts = int(prior_arrays["num_parts"])
     rng = np.random.default_rng(5)
     x_gt = synth.random_params(model, rng)
@@ -422,7 +427,8 @@ def test_depth_cloud_construction_large_image(model, oracle_mod, omodel, prior_a
 def test_rtree_predict_bit_exact(model, oracle_mod, omodel, prior_arrays):
     """device labels == oracle restatement of RTree.cpp:3184-3262 + upscaleGrid, bit for bit: whole images, boxes,
     strides, with and without gap filling, an empty frame, a degenerate box"""
-    from avatar_b200 import Fitter, synth
+    from avatar_b200 import Fitter
+    from harness import synth
     nparts = int(prior_arrays["num_parts"])
     depth, parts, _ = _rendered(model, omodel, prior_arrays, [0, 1, 2])
     depth[2][:] = 0.0
@@ -444,7 +450,8 @@ def test_rtree_predict_bit_exact(model, oracle_mod, omodel, prior_arrays):
 def test_depth_to_fit_pipeline_on_device(model, oracle_mod, omodel, prior_arrays):
     """depth image -> RTree labels -> data cloud -> fit, all on the device (parts=None), equals the host pipeline
     (oracle RTree + oracle cloud construction) followed by the same fit: same clouds, same labels, same parameters"""
-    from avatar_b200 import Fitter, synth
+    from avatar_b200 import Fitter
+    from harness import synth
     nparts = int(prior_arrays["num_parts"])
     intrin = (synth.FX, synth.CX, synth.FY, synth.CY)
     depth, parts, x0 = _rendered(model, omodel, prior_arrays, [0, 1])
@@ -477,7 +484,8 @@ def test_depth_to_fit_pipeline_on_device(model, oracle_mod, omodel, prior_arrays
 def test_renderer_bit_exact(model, oracle_mod, omodel, prior_arrays):
     """device renderDepth / renderPartMask / renderFaces == the sequential painter of oracle/render_oracle.cpp on the
     same posed cloud, bit for bit, at 640x576 and at an odd size with off-centre intrinsics; single outputs too"""
-    from avatar_b200 import Fitter, synth
+    from avatar_b200 import Fitter
+    from harness import synth
     nparts = int(prior_arrays["num_parts"])
     vp = synth.vertex_parts(model, prior_arrays["part_map"])
     faces = np.ascontiguousarray(model.mesh, dtype=np.int32)

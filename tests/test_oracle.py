@@ -143,6 +143,59 @@ def test_nn_bruteforce_kdtree_and_reference_nanoflann_agree(oracle_mod, oopt, om
     assert checked > 0.9 * len(pts)
 
 
+def near_tie_queries(cloud, rng, n):
+    """queries on (or within a few ulps of) the bisector plane of two model vertices: the two candidate distances agree
+    to the last bits, so whether `result += diff*diff` is contracted into an FMA can decide the answer"""
+    from scipy.spatial import cKDTree
+    V = cloud.shape[0]
+    a = rng.integers(0, V, n)
+    # partner: the vertex's own nearest neighbour, so that both are the two closest vertices of the midpoint
+    b = cKDTree(cloud).query(cloud[a], k=2)[1][:, 1]
+    mid = 0.5 * (cloud[a] + cloud[b])
+    d = cloud[b] - cloud[a]
+    r = rng.standard_normal((n, 3))
+    r -= (np.sum(r * d, axis=1) / np.maximum(np.sum(d * d, axis=1), 1e-300))[:, None] * d   # inside the bisector plane
+    q = mid + 1e-4 * r
+    q += rng.standard_normal((n, 3)) * (np.abs(q) * 2.0 ** -52)                               # a few ulps off it
+    return np.ascontiguousarray(q)
+
+
+def test_nn_fma_contraction_sensitivity(oracle_mod, oopt, omodel, frames):
+    """the reference is built WITHOUT -march (CMakeLists.txt:37), so nanoflann's `result += diff*diff`
+    is not contracted.  Both builds of the reference's own nanoflann.hpp are compiled into oracle/_ref; the oracle (and
+    the device kernel, tests/test_gpu_parity.py) must agree with the non-FMA build on every query, and the number of
+    queries on which the two builds differ is the honest size of the issue (printed, and non-zero only on near ties)."""
+    x_gt, x0, pts, lab = frames[0]
+    cloud, _, _ = omodel.update_x(x0)
+    rng = np.random.default_rng(77)
+    sub = np.ascontiguousarray(cloud[rng.permutation(cloud.shape[0])[:2500]])
+    q_rand = np.ascontiguousarray(pts[rng.integers(0, len(pts), 400000)] + rng.standard_normal((400000, 3)) * 0.02)
+    q_tie = near_tie_queries(sub, rng, 200000)
+    ref = oracle_mod.ref_nanoflann_nn(sub, q_rand)
+    if ref is None or oracle_mod.ref_nanoflann_nn(sub, q_rand[:4], fma=True) is None:
+        pytest.skip("oracle/_ref not built (reference tree absent and no prebuilt library)")
+    fma = oracle_mod.ref_nanoflann_nn(sub, q_rand, fma=True)
+    ref_t = oracle_mod.ref_nanoflann_nn(sub, q_tie)
+    fma_t = oracle_mod.ref_nanoflann_nn(sub, q_tie, fma=True)
+    # the oracle's own exact search (one part holding every vertex) against the reference-flag build
+    own = oracle_mod.brute_nn(sub, q_rand)
+    own_t = oracle_mod.brute_nn(sub, q_tie)
+    d_rand, d_tie = int((ref != fma).sum()), int((ref_t != fma_t).sum())
+    print(f"nanoflann no-FMA vs FMA build: {d_rand} of {len(q_rand)} random queries differ, {d_tie} of {len(q_tie)} near-tie queries differ")
+
+    def d2(q, i):   # the reference's arithmetic: ((d0^2 + d1^2) + d2^2), every operation rounded
+        d = q - sub[i]
+        return (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    # wherever the oracle and the reference-flag build name different vertices, the two are at EXACTLY the same
+    # distance (tie rule: oracle lowest index, nanoflann first visited); never a closer / farther vertex
+    for q, a, b in ((q_rand, own, ref), (q_tie, own_t, ref_t)):
+        bad = np.nonzero(a != b)[0]
+        assert np.array_equal(d2(q[bad], a[bad]), d2(q[bad], b[bad])), "oracle NN differs from the reference-flag nanoflann beyond exact ties"
+        assert (d2(q, a) <= d2(q, b)).all()
+    assert d_rand <= 5          # random data: contraction practically never matters
+    assert d_tie < len(q_tie) // 2
+
+
 _main_cache = {}
 
 
@@ -284,7 +337,7 @@ def test_build_cloud_oracle_small_cases(oracle_mod):
 def test_build_cloud_oracle_matches_harness_backprojection(oracle_mod, model, omodel, prior_arrays):
     """the oracle restatement of demo.cpp's loops and the synthetic harness' own back-projection (avb_synth.cpp,
     written from optim.cpp:104-120) agree bit for bit on a rendered 640x576 frame"""
-    from avatar_b200 import synth
+    from harness import synth
     rng = np.random.default_rng(1000)
     x_gt = synth.random_params(model, rng)
     cloud_gt, _, _ = omodel.update_x(x_gt)
@@ -342,7 +395,7 @@ def _python_rtree_predict(depth, t, roi, interval, fill):
 
 
 def test_rtree_predict_oracle_small_cases(oracle_mod):
-    from avatar_b200 import synth
+    from harness import synth
     rng = np.random.default_rng(11)
     tree = synth.random_rtree(rng, 16, depth_levels=9)
     h, w = 37, 45
@@ -369,7 +422,7 @@ def _same_images(a, b):
 
 
 def test_rank_form_renderer_equals_sequential_painter_on_the_model(oracle_mod, model, omodel, prior_arrays):
-    from avatar_b200 import synth
+    from harness import synth
     vp = synth.vertex_parts(model, prior_arrays["part_map"])
     faces = np.ascontiguousarray(model.mesh, dtype=np.int32)
     intrin = (synth.FX, synth.CX, synth.FY, synth.CY)
@@ -411,7 +464,8 @@ def test_rank_form_renderer_equals_sequential_painter_on_triangle_soup(oracle_mo
 # RTree model files (RTree.cpp:2967-3094, 3452-3510): host-side readers of the Python mirror
 # ---------------------------------------------------------------------------------------------
 def test_rtree_file_formats_roundtrip(tmp_path, oracle_mod):
-    from avatar_b200 import synth, rtree
+    from avatar_b200 import rtree
+    from harness import synth
     rng = np.random.default_rng(5)
     tree = synth.random_rtree(rng, 16, depth_levels=8)
     n_leafs = len(tree["leaf_best"])
@@ -445,7 +499,7 @@ def test_rtree_file_formats_roundtrip(tmp_path, oracle_mod):
 def test_oracle_painter_equals_the_references_own_painters(oracle_mod, model, omodel, prior_arrays):
     """PIN: oracle/render_oracle.cpp against the reference's own AvatarHelpers.cpp (compiled from /root/reference into
     oracle/_ref with container-only OpenCV/Eigen stand-ins): the same faces in the same order give the same images"""
-    from avatar_b200 import synth
+    from harness import synth
     vp = synth.vertex_parts(model, prior_arrays["part_map"])
     faces = np.ascontiguousarray(model.mesh, dtype=np.int32)
     rng = np.random.default_rng(1002)
@@ -472,7 +526,7 @@ def test_build_cloud_oracle_equals_the_references_own_depth_to_xyz(oracle_mod, m
     """PIN: the xyz arithmetic of orc_build_cloud against the reference's own CameraIntrin::depthToXYZ (Calibration.cpp
     compiled from /root/reference into oracle/_ref): every foreground pixel's point equals the xyz map entry, y negated
     as demo.cpp:244-246 does"""
-    from avatar_b200 import synth
+    from harness import synth
     rng = np.random.default_rng(1003)
     cloud, _, _ = omodel.update_x(synth.random_params(model, rng))
     _, _, depth, part = synth.render_cloud(model, cloud, prior_arrays["part_map"])

@@ -24,7 +24,8 @@ def crc(a):
 def golden_cases():
     """the seeded inputs every golden entry is computed from (shared with the tests)"""
     import oracle as orc
-    from avatar_b200 import AvatarModel, GaussianMixture, synth
+    from avatar_b200 import AvatarModel, GaussianMixture
+    from harness import synth
     pr = np.load(os.path.join(GOLD, "prior_synth.npz"))
     g = GaussianMixture.from_arrays(pr["weights"], pr["means"], pr["covs"])
     model = AvatarModel(npz_path=os.path.join(GOLD, "model_synth.npz"), pose_prior=g)
@@ -42,7 +43,7 @@ def golden_cases():
 
 
 def compute():
-    from avatar_b200 import synth
+    from harness import synth
     orc, model, pr, om, oo, frames = golden_cases()
     nparts = int(pr["num_parts"])
     out = {}

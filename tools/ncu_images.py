@@ -8,7 +8,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from avatar_b200 import AvatarModel, GaussianMixture, Fitter, synth  # noqa: E402
+from avatar_b200 import AvatarModel, GaussianMixture, Fitter  # noqa: E402
+from harness import synth
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 pr = np.load(os.path.join(GOLD, "prior_synth.npz"))
