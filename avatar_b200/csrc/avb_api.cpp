@@ -309,7 +309,7 @@ void avb_default_options(avb_options* o) {
     o->nn_step = 20;             // AvatarOptimizer.h:33 (unused by the inverted NN mode)
     o->function_tolerance = 1e-4;  // AvatarOptimizer.cpp:1333
     o->solver = AVB_SOLVER_GN_LM;
-    o->jtj_precision = AVB_JTJ_FP64;
+    o->jtj_precision = AVB_JTJ_BF16_TENSOR;   // J^T J on the tensor cores (split bf16, fp32 TMEM accumulation); J^T r, cost in fp64
 }
 
 int avb_device_count(void) {
@@ -693,7 +693,7 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     TRY(dev_alloc(ft, &ft->d_tab, B * (size_t)ft->tabD));
     TRY(dev_alloc(ft, &ft->d_part, B * (size_t)ft->maxc * (size_t)ft->pstride));
     ft->rec_rs = lm_rec_slots(V);
-    ft->maxrb = (ft->rec_rs + 255) / 256;
+    ft->maxrb = std::max((ft->rec_rs + 255) / 256, ft->maxc);   // cost partials: one per record block (fp64 path) or per chunk (tensor path)
     ft->rec_stride = lm_rec_floats(ft->max_nj, m->K);
     TRY(dev_alloc(ft, &ft->d_cpart, B * (size_t)ft->maxrb));
     TRY(dev_alloc(ft, &ft->d_rec, B * (size_t)ft->rec_rs * (size_t)ft->rec_stride));
@@ -1054,8 +1054,9 @@ int check_options(const avb_fitter* ft, const avb_options* o) {
     if (o->solver != AVB_SOLVER_GN_LM) return fail(AVB_ERR_INVALID, "unknown solver");
     if (o->jtj_precision != AVB_JTJ_FP64 && o->jtj_precision != AVB_JTJ_FP32 && o->jtj_precision != AVB_JTJ_BF16_TENSOR)
         return fail(AVB_ERR_INVALID, "jtj_precision must be AVB_JTJ_FP64, AVB_JTJ_FP32 or AVB_JTJ_BF16_TENSOR");
-    if (o->jtj_precision == AVB_JTJ_BF16_TENSOR && 3 * ft->max_nj + 3 * ft->model->K + 7 > 128)
-        return fail(AVB_ERR_INVALID, "AVB_JTJ_BF16_TENSOR needs at most 128 record fields per group");
+    if (o->jtj_precision == AVB_JTJ_BF16_TENSOR && !lm_tensor_supported(ft->max_nj, ft->model->K))
+        return fail(AVB_ERR_INVALID, "AVB_JTJ_BF16_TENSOR needs at most 80 record fields (3 joints + 1 + 3 shape keys) and 64 Jacobian "
+                                     "columns per column group: use AVB_JTJ_FP64 for this model (or more groups, AVB_GROUPS)");
     if (o->beta_pose > 0.0 && ft->model->gmmC <= 0)
         return fail(AVB_ERR_PRIOR, "betaPose > 0 but the model has no pose prior");
     return AVB_OK;
@@ -1169,9 +1170,9 @@ LmBuf lm_buf(avb_fitter* ft, double* dx, const avb_options* o) {
     a.function_tolerance = o->function_tolerance;
     a.max_iters = o->max_iters_per_icp;
     a.stats = ft->d_stats;
-    // one persistent data-flow kernel for the whole inner solve; the tensor-core Gram variant and the debug
-    // evaluation (one evaluation, dump) use the staged kernels
-    if (ft->use_flow && o->jtj_precision != AVB_JTJ_BF16_TENSOR) {
+    // one persistent data-flow kernel for the whole inner solve (the staged kernels, AVB_FLOW=0, exist for the fp64 path only)
+    a.tensor = o->jtj_precision == AVB_JTJ_BF16_TENSOR ? 1 : 0;
+    if (ft->use_flow || a.tensor) {
         a.q.slots = ft->d_qslots;
         a.q.ctrl = ft->d_qctrl;
         a.q.rows_left = ft->d_rows_left;
@@ -1192,7 +1193,7 @@ int enqueue_solve(avb_fitter* ft, const LmBuf& la, const avb_options* o, int rou
     ++ft->launches;
     if (la.q.prof) CUDA_TRY(cudaMemsetAsync(ft->d_qprof, 0, 128, st));
     if (la.q.slots) {
-        int ctas = std::min(2 * ft->num_sms, std::max(1, ft->batch * 16));
+        int ctas = std::min(lm_flow_ctas_per_sm(la.tensor != 0) * ft->num_sms, std::max(1, ft->batch * 16));
         if (const char* e = std::getenv("AVB_FLOW_CTAS")) ctas = std::max(1, std::min(ctas, std::atoi(e)));
         ProfScope ps(ft, KC_FLOW);
         CUDA_TRY(launch_lm_flow(ft->dm, ft->dp, la, ft->max_nj, ctas, st));

@@ -129,6 +129,7 @@ struct LmBuf {
     double* trace;               // nullable [batch][trace_cap][nx]
     int trace_cap;
     FrameStats* stats;           // [batch]
+    int tensor;                  // 1: fused record + Gram tasks on tcgen05 (lm_flow_kernel<true>); 0: fp64 DMMA path
     FlowQueue q;
 };
 
@@ -154,5 +155,7 @@ int lm_tab_doubles(int J, int K);
 int lm_rec_floats(int max_nj, int K);
 int lm_rec_slots(int V);
 size_t lm_gram_smem_bytes(int max_nj, int K, int chunk_verts, bool tensor);
+bool lm_tensor_supported(int max_nj, int K);
+int lm_flow_ctas_per_sm(bool tensor);
 
 }  // namespace avb

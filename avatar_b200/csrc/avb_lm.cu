@@ -6,8 +6,12 @@
 //                                             statistics and the analytic Jacobian (AvatarOptimizer.cpp:505-582 in
 //                                             closed form) as a compact fp32 record (SoA) in HBM; cost partial.
 //   lm_gram_kernel   grid = chunks x frames   Gram matrix of the records of up to 256 matched vertices (fp64 DMMA from
-//                                             an fp32 tile; lm_gram_tc_kernel: bf16 tcgen05), turned into the chunk's
-//                                             deterministic partial of J^T J / J^T r.
+//                                             an fp32 tile), turned into the chunk's deterministic partial of
+//                                             J^T J / J^T r.
+//   lm_flow_kernel<true> (default)            persistent data-flow kernel: fused record + Gram tasks (fused_body: the
+//                                             records go straight into a swizzled bf16 operand tile, J^T J on tcgen05
+//                                             with a TMEM accumulator, J^T r and cost in fp64) and the solves.
+//   lm_flow_kernel<false>                     the same data flow over rows / gram (fp64 DMMA) / solve tasks.
 //   lm_solve_kernel  grid = frames            partial reduction in chunk order, priors (:661-692, :708-723),
 //                                             Levenberg-Marquardt step control, damped Cholesky solve, retraction
 //                                             (:123-143), joint tables of the next trial point.
@@ -48,7 +52,7 @@ __device__ __forceinline__ LmState load_state(const LmState* p) {
 // ---------------------------------------------------------------------------------------------
 // work queue of lm_flow_kernel (tasks are pushed only when their inputs are complete, so no task ever waits)
 // ---------------------------------------------------------------------------------------------
-enum { kTaskRows = 0, kTaskGram = 1 };
+enum { kTaskRows = 0, kTaskGram = 1, kTaskFused = 2 };
 __device__ __forceinline__ unsigned make_task(int type, int f, int idx) {
     return ((unsigned)type << 30) | ((unsigned)f << 12) | (unsigned)idx;
 }
@@ -225,11 +229,18 @@ lm_prep_kernel(DevModel M, DevParts Pt, LmBuf a) {
         fs.final_cost = 0;
         fs.status = a.range_flag[f] ? 4 : 0;
         if (a.q.slots && !st.done) {   // lm_flow_kernel: the frame's first tasks
-            const int nrb = (base + 255) >> 8;
-            a.q.rows_left[f] = nrb;
-            __threadfence();
-            atomicAdd(&a.q.ctrl[2], 1u);
-            flow_push(a.q, kTaskRows, f, nrb);
+            if (a.tensor) {             // fused record + Gram tasks, one per chunk
+                a.q.gram_left[f] = st.nchunks;
+                __threadfence();
+                atomicAdd(&a.q.ctrl[2], 1u);
+                flow_push(a.q, kTaskFused, f, st.nchunks);
+            } else {
+                const int nrb = (base + 255) >> 8;
+                a.q.rows_left[f] = nrb;
+                __threadfence();
+                atomicAdd(&a.q.ctrl[2], 1u);
+                flow_push(a.q, kTaskRows, f, nrb);
+            }
         }
     }
 }
@@ -583,124 +594,356 @@ lm_gram_kernel(DevModel M, DevParts Pt, LmBuf a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// lm_gram_tc_kernel: the same Gram matrix on the 5th-generation tensor cores (AVB_JTJ_BF16_TENSOR)
+// fused record + Gram task of lm_flow_kernel<true> (the default path): J^T J on the 5th-generation tensor cores
 // ---------------------------------------------------------------------------------------------
-// One CTA per chunk.  The field-major record tile IS the K-major operand: T[m][k] (m = record field, k = vertex) is
-// written as bf16 in the canonical no-swizzle UMMA layout (8 x 16-byte core matrices) and
-// D[128 x N] += T[0:128, k-slice] * T[0:N, k-slice]^T is a plain tcgen05.mma.cta_group::1.kind::f16 (M = 128, K = 16 per
-// instruction) issued by one thread with both operands described by the same shared-memory tile.  The fp32 accumulator
-// lives in TMEM and is read back once with tcgen05.ld.  The residual is carried as two bf16 terms (rho_hi's bf16 head
-// and remainder in the rho_hi / rho_lo fields): 16 bits, well below the 8-bit rounding of the Jacobian factor.
-constexpr int kTcThreads = 128;
-constexpr int kTcM = 128;              // UMMA M (record fields padded)
+// One task = one chunk (<= 256 matched vertices of one column group), processed as sub-tiles of 128 vertices.  Two
+// threads per vertex compute the vertex's position, residual and the record fields [ u_j = 2 sc y_j | sc | sc S ] in fp64
+// (AvatarOptimizer.cpp:505-582 in closed form, see rows_body) and write them STRAIGHT into shared memory as the
+// K-major SWIZZLE_128B operand tile of tcgen05.mma -- no Jacobian record ever goes to HBM.  Every fp32 field is split
+// into kTcTerms bf16 terms (x = t0 + t1 + t2, 8 bits each); the Gram matrix  sum_v rec_v rec_v^T  is the sum of the term
+// products of weight >= 2^-8(kTcTerms-1), all accumulated by tcgen05.mma.kind::f16 (M = 128, N = nf rounded to 16,
+// K = 16) into ONE fp32 TMEM accumulator per CTA (allocated once per CTA, 128 columns).  The operands never leave
+// shared memory, the accumulator never touches registers until the epilogue (tcgen05.ld) turns the Gram matrix into the
+// chunk's partial of J^T J exactly as the fp64 path does (emit_partial).
+// J^T r and the cost do NOT go through the tensor cores: every thread forms its vertex's contributions in fp64 from
+// unrounded fields and the fp64 residual, and they are summed with warp shuffles (fixed tree) and a fixed warp order,
+// so the gradient -- and with it the fixed point of the iteration -- has full fp64 accuracy; the tensor-core J^T J
+// (two bf16 terms: measured 4e-6 of the diagonal scale, which is already the floor of fp32 accumulation over a sub-tile --
+// a third term costs twice the MMAs and buys nothing, tools/ubench/umma_gram_test.cu) only steers the step.
+#ifndef AVB_TC_TERMS
+#define AVB_TC_TERMS 2
+#endif
+constexpr int kTcTerms = AVB_TC_TERMS;
+constexpr int kTcSub = 128;                         // vertices per sub-tile: two 64-element swizzle atoms along K
+constexpr int kTcRows = 80;                         // record fields of the tile (3 nj + 1 + 3 K <= 80)
+constexpr int kTcAtomBytes = kTcRows * 128;         // one K atom: kTcRows rows of 128 B (64 bf16)
+constexpr int kTcTermBytes = 2 * kTcAtomBytes;
+constexpr int kTcTileBytes = kTcTerms * kTcTermBytes;
+constexpr int kTcCols = 128;                        // TMEM columns per CTA (power of two >= kTcRows)
+constexpr int kTcGcols = 64;                        // >= columns of a group's compact Jacobian (3 + 3 nj + K)
 
-__global__ void __launch_bounds__(kTcThreads, 2)
-lm_gram_tc_kernel(DevModel M, DevParts Pt, LmBuf a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t mbar;
-    __shared__ uint32_t tmem_base_s;
-    const int c = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-    const LmState& st = a.state[f];
-    if (st.done || st.last || c >= st.nchunks) return;
-    const int K = M.K;
+__host__ __device__ inline int tc_fields(int nj, int K) { return 3 * nj + 1 + 3 * K; }
+
+// byte offset of (field m, vertex k of the sub-tile) inside one term tile: 8-row groups of 1024 B, rows of 128 B whose
+// 16-byte chunks are XOR-swizzled with (row & 7) -- the layout SWIZZLE_128B shared-memory descriptors address
+__device__ __forceinline__ uint32_t tc_off(int m, int k) {
+    return (uint32_t)((k >> 6) * kTcAtomBytes + (m >> 3) * 1024 + (m & 7) * 128 + (((((k & 63) >> 3) ^ m) & 7) << 4) + ((k & 7) << 1));
+}
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
+    // start >> 4 | LBO (unused for swizzled K-major: 1) | SBO = 1024 B between 8-row groups | version 1 | SWIZZLE_128B
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tc_store_terms(unsigned char* tile, uint32_t off, double value) {
+    float x = (float)value;
+#pragma unroll
+    for (int t = 0; t < kTcTerms; ++t) {
+        const __nv_bfloat16 b = __float2bfloat16_rn(x);
+        x -= __bfloat162float(b);
+        *reinterpret_cast<__nv_bfloat16*>(tile + t * kTcTermBytes + off) = b;
+    }
+}
+// sum over the 16 lanes of a half warp (the 16 vertices this half of the warp owns); every lane gets the sum
+__device__ __forceinline__ double half_sum(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+__device__ __forceinline__ void tc_wait(uint64_t* mbar, uint32_t& phase) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32_lm(mbar)), "r"(phase) : "memory");
+    phase ^= 1u;
+}
+
+struct TcSmem {
+    unsigned char* tile;   // kTcTileBytes, 1024-byte aligned; later the fp64 Gram matrix
+    double *tab, *w, *gsm, *gvec, *scr;
+    int* gstart;
+};
+__host__ __device__ inline size_t tc_smem_bytes(int J, int K) {
+    // tile | tab | w | gsm [8 warps][kTcGcols] | gvec [kTcGcols] | scr [32]; the tile must be followed by >= 6 KB of
+    // addressable shared memory: M = 128 makes the last K atom read 48 rows past its 80 (their accumulator rows are ignored)
+    return 1024 + (size_t)kTcTileBytes + (size_t)(tab_doubles(J, K) + ((K + 1) & ~1) + 9 * kTcGcols + 32) * 8 + 64;
+}
+__device__ inline TcSmem carve_tc(unsigned char* raw, int tabD, int K) {
+    TcSmem S;
+    S.tile = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+    double* d = reinterpret_cast<double*>(S.tile + kTcTileBytes);
+    S.tab = d; d += tabD;
+    S.w = d; d += (K + 1) & ~1;
+    S.gsm = d; d += 8 * kTcGcols;
+    S.gvec = d; d += kTcGcols;
+    S.scr = d; d += 32;
+    S.gstart = reinterpret_cast<int*>(d);
+    return S;
+}
+
+// chunk partial from the Gram matrix of [ u_j | sc | sc S ] (no residual fields) and the fp64 gradient gvec
+__device__ void emit_partial_tc(const double* Gs, int n, int nj, int K, const double* gvec, double* part, int tid, int nt) {
+    const int Lg = 3 + 3 * nj + K, nH = tri_count(Lg);
+    const int SC = 3 * nj, S0 = SC + 1;
+    for (int idx = tid; idx < nH + Lg; idx += nt) {
+        double val = 0.0;
+        if (idx < nH) {
+            int ra, rb;
+            if (!tri_decode(idx, Lg, ra, rb)) continue;
+            if (ra < 3) {
+                const int a = ra;
+                if (rb < 3) {
+                    val = (a == rb) ? gm(Gs, n, SC, SC) : 0.0;
+                } else if (rb < 3 + 3 * nj) {
+                    const int k = (rb - 3) / 3, b = (rb - 3) - 3 * k;
+                    if (a != b) {
+                        const double w = gm(Gs, n, SC, 3 * k + (3 - a - b));
+                        val = (b == (a + 1) % 3) ? w : -w;
+                    }
+                } else {
+                    val = gm(Gs, n, SC, S0 + a * K + (rb - 3 - 3 * nj));
+                }
+            } else if (ra < 3 + 3 * nj) {
+                const int j = (ra - 3) / 3, a = (ra - 3) - 3 * j;
+                if (rb < 3 + 3 * nj) {
+                    const int k = (rb - 3) / 3, b = (rb - 3) - 3 * k;
+                    val = -gm(Gs, n, 3 * k + a, 3 * j + b);
+                    if (a == b)
+                        val += gm(Gs, n, 3 * j, 3 * k) + gm(Gs, n, 3 * j + 1, 3 * k + 1) + gm(Gs, n, 3 * j + 2, 3 * k + 2);
+                } else {
+                    const int m = rb - 3 - 3 * nj, a1 = (a + 1) % 3, a2 = (a + 2) % 3;
+                    val = gm(Gs, n, 3 * j + a1, S0 + a2 * K + m) - gm(Gs, n, 3 * j + a2, S0 + a1 * K + m);
+                }
+            } else {
+                const int m = ra - 3 - 3 * nj, m2 = rb - 3 - 3 * nj;
+                val = gm(Gs, n, S0 + m, S0 + m2) + gm(Gs, n, S0 + K + m, S0 + K + m2) +
+                      gm(Gs, n, S0 + 2 * K + m, S0 + 2 * K + m2);
+            }
+        } else {
+            val = gvec[idx - nH];
+        }
+        part[idx] = val;
+    }
+}
+
+// tmem_d: the CTA's accumulator; mbar: its commit barrier; phase: parity the next commit completes (per thread copy)
+__device__ void fused_body(const DevModel& M, const DevParts& Pt, const LmBuf& a, int f, int c, bool cost_only,
+                           unsigned char* smem_raw, uint32_t tmem_d, uint64_t* mbar, uint32_t& phase) {
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int J = M.J, K = M.K;
+    unsigned long long tp = phase_begin(a.q);
+    const TcSmem S = carve_tc(smem_raw, a.tabD, K);
     const int4 ch = a.chunks[(size_t)f * a.maxc + c];
     const int g = ch.x, start = ch.y, count = ch.z;
     const int nj = Pt.gnj[g];
-    const int nf = rec_floats(nj, K), nfp = (nf + 7) & ~7, n = nfp >> 3;
-    const int N = (nf + 15) & ~15;                   // UMMA N (multiple of 16 for M = 128)
-    const int Kx = a.chunk_verts;                    // K extent of the tile (multiple of 64)
-    const int cnt16 = (count + 15) & ~15;
-    uint4* T = reinterpret_cast<uint4*>(smem_raw);   // bf16 [kTcM/8][Kx/8] core matrices of 8 rows x 16 bytes
-
-    if (wid == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32_lm(&tmem_base_s)), "r"(128));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    const int* gj = Pt.gjoints + g * kMaxJ;
+    const int nf = tc_fields(nj, K), Lg = group_L(nj, K);
+    {
+        const double* gtab = a.tab + (size_t)f * a.tabD;
+        for (int q = tid; q < a.tabD; q += 256) S.tab[q] = ldg2(gtab + q);
+        for (int q = tid; q < K; q += 256) S.w[q] = ldg2(a.xt + (size_t)f * M.nx + 3 + 4 * J + q);
+        for (int q = tid; q < 8 * kTcGcols; q += 256) S.gsm[q] = 0.0;
     }
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32_lm(&mbar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    // fp32 records -> bf16 tile, eight vertices (one 16-byte core-matrix row) per step; everything the MMAs read
-    // (fields < 128, vertices < cnt16) is written, zeros outside the chunk
-    const float* recs = a.rec + (size_t)f * a.rec_stride * a.rec_rs + start;
-    const int RLo = 3 * nj + 4, n8 = cnt16 >> 3;
-    for (int e = tid; e < kTcM * n8; e += kTcThreads) {
-        const int m = e / n8, i = e - m * n8;
-        uint4 out = make_uint4(0u, 0u, 0u, 0u);
-        if (m < nf && 8 * i < count) {
-            const bool second = (m >= RLo && m < RLo + 3);       // rho_lo slot carries rho_hi - bf16(rho_hi)
-            const float* src = recs + (size_t)(second ? m - 3 : m) * a.rec_rs + 8 * i;
-            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
-            const float4 v1 = (8 * i + 4 < count) ? __ldg(reinterpret_cast<const float4*>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            uint32_t w[4];
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                unsigned short b2[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    float x = (8 * i + 2 * h + u < count) ? v[2 * h + u] : 0.f;
-                    if (second) x -= __bfloat162float(__float2bfloat16_rn(x));
-                    const __nv_bfloat16 b = __float2bfloat16_rn(x);
-                    b2[u] = *reinterpret_cast<const unsigned short*>(&b);
-                }
-                w[h] = (uint32_t)b2[0] | ((uint32_t)b2[1] << 16);
-            }
-            out = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-        T[((m >> 3) * (Kx >> 3) + i) * 8 + (m & 7)] = out;
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
-    asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    const uint32_t tmem_d = tmem_base_s;
-    if (tid == 0) {
-        // instruction descriptor: D = F32, A = B = BF16, K-major both, N >> 3 at [17,23), M >> 4 at [24,29)
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
-        // shared-memory descriptor: start >> 4 | LBO (K-direction core-matrix stride, 128 B) | SBO (8-row group stride) | version 1
-        const uint64_t desc0 = (uint64_t)((smem_u32_lm(T) >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) |
-                               ((uint64_t)(((Kx >> 3) * 128) >> 4) << 32) | (1ull << 46);
+    phase_lap(a.q, 12, tp);
+    const double* G = S.tab;
+    const double* pos = S.tab + 9 * J;
+    const double* tau = S.tab + 12 * J;
+    const double* C = S.tab + 15 * J;
+    const int kk = (tid & 15) + 16 * wid;      // vertex slot inside the sub-tile; the two half warps split its fields
+    const int h = (tid >> 4) & 1;
+    const bool lead = (lane & 15) == 0;
+    double* gw = S.gsm + wid * kTcGcols;       // this warp's gradient sums (one writer per column)
+    double costv = 0.0;
+    const int nsub = (count + kTcSub - 1) / kTcSub;
+    const int SC = 3 * nj, S0 = SC + 1;
 #pragma unroll 1
-        for (int s2 = 0; s2 < (cnt16 >> 4); ++s2) {
-            const uint64_t desc = desc0 + (uint64_t)((s2 * 256) >> 4);   // two core matrices per k-step
-            const uint32_t accum = s2 > 0 ? 1u : 0u;
-            asm volatile(
-                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                ::"r"(tmem_d), "l"(desc), "l"(desc), "r"(idesc), "r"(accum) : "memory");
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32_lm(&mbar)) : "memory");
-    }
-    {   // the tile may be overwritten (and TMEM read) only after the MMAs retire
-        uint32_t done = 0;
-        while (!done)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(smem_u32_lm(&mbar)), "r"(0u) : "memory");
-    }
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    __syncthreads();
-    // epilogue: TMEM lane = record field m (row of the Gram matrix); warp w owns lanes [32w, 32w+32)
-    double* Gs = reinterpret_cast<double*>(smem_raw);
-    const int m = 32 * wid + lane;
-    for (int cb = 0; cb < n; ++cb) {
-        uint32_t v[8];
-        const uint32_t taddr = tmem_d + ((uint32_t)(32 * wid) << 16) + (uint32_t)(8 * cb);
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                     : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const int bi = m >> 3;
-        if (m < nfp && cb >= bi) {
-            double* p = Gs + pair_index(bi, cb, n) * 64 + (m & 7) * 8;
+    for (int sub = 0; sub < nsub; ++sub) {
+        const int li = sub * kTcSub + kk;
+        int v = (li < count) ? (int)a.mlist[(size_t)f * a.rec_rs + start + li] : (int)kNoVertex;
+        const bool valid = v != (int)kNoVertex;
+        if (!valid) v = 0;
+        // ---- position, residual (AvatarOptimizer.cpp:507-514, 632-639) ----
+        const float* sd = M.sd + (size_t)v * 3 * K;
+        double v0[3];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) p[j] = (double)__uint_as_float(v[j]);
+        for (int cc = 0; cc < 3; ++cc) {
+            double s = 0;
+            for (int k = 0; k < K; ++k) s += (double)sd[cc * K + k] * S.w[k];
+            v0[cc] = M.vt[3 * (size_t)v + cc] + s;
+        }
+        const int n = M.sk_n[v];
+        double xk[AVB_MAX_ASSIGN_][3], wk[AVB_MAX_ASSIGN_];
+        int jk[AVB_MAX_ASSIGN_];
+        uint32_t mk[AVB_MAX_ASSIGN_];
+        double x[3] = {0, 0, 0}, B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
+            if (q < n) {
+                const int k = M.sk_j[4 * (size_t)v + q];
+                const double wt = M.sk_w[4 * (size_t)v + q];
+                const double* Gk = G + 9 * k;
+                jk[q] = k;
+                wk[q] = wt;
+                mk[q] = M.anc_mask[k];
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) {
+                    xk[q][cc] = Gk[3 * cc] * v0[0] + Gk[3 * cc + 1] * v0[1] + Gk[3 * cc + 2] * v0[2] + tau[3 * k + cc];
+                    x[cc] += wt * xk[q][cc];
+                }
+#pragma unroll
+                for (int e = 0; e < 9; ++e) B[e] += wt * Gk[e];
+            } else {
+                jk[q] = 0; wk[q] = 0; mk[q] = 0;
+                xk[q][0] = xk[q][1] = xk[q][2] = 0;
+            }
+        }
+        const double cn = valid ? (double)a.cnt[(size_t)f * M.V + v] : 0.0;
+        const double sc = sqrt(cn), s2 = 2.0 * sc;
+        double rho[3] = {0, 0, 0};
+        if (valid) {
+            const unsigned long long* sumv = a.sum + 3 * ((size_t)f * M.V + v);
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+                const double sr = (double)(long long)sumv[cc] * kFixInv;
+                rho[cc] = (cn * x[cc] - sr) / sc;
+                if (h == 0) costv += x[cc] * (cn * x[cc] - 2.0 * sr);   // sum_i |x - d_i|^2 - sum_i |d_i|^2 = x . (c x - 2 s)
+            }
+        }
+        if (cost_only) continue;
+        if (sub > 0) tc_wait(mbar, phase);   // the previous sub-tile's MMAs have read the tile: it may be rewritten
+        const uint32_t kb = (uint32_t)kk;
+        // ---- translation columns and the sc field (half 0); J^T r contributions are summed in fp64 ----
+        {
+            const double g0 = half_sum(sc * rho[0]), g1 = half_sum(sc * rho[1]), g2 = half_sum(sc * rho[2]);
+            if (h == 0) {
+                tc_store_terms(S.tile, tc_off(SC, kb), sc);
+                if (lead) { gw[0] += g0; gw[1] += g1; gw[2] += g2; }
+            }
+        }
+        // ---- rotation fields: u_j = 2 sc y_j, block_j = -[u_j]x (rows_body); J^T r: u_j x rho ----
+#pragma unroll 1
+        for (int i = 0; 2 * i < nj; ++i) {
+            const int gi = 2 * i + h;
+            const bool act = gi < nj;
+            const int j = gj[act ? gi : 0];
+            double y0 = 0, y1 = 0, y2 = 0, W = 0;
+#pragma unroll
+            for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
+                if ((mk[q] >> j) & 1u) {
+                    W += wk[q];
+                    y0 += wk[q] * xk[q][0];
+                    y1 += wk[q] * xk[q][1];
+                    y2 += wk[q] * xk[q][2];
+                }
+            }
+            const double u0 = (y0 - W * pos[3 * j]) * s2, u1 = (y1 - W * pos[3 * j + 1]) * s2, u2 = (y2 - W * pos[3 * j + 2]) * s2;
+            if (act) {
+                tc_store_terms(S.tile, tc_off(3 * gi, kb), u0);
+                tc_store_terms(S.tile, tc_off(3 * gi + 1, kb), u1);
+                tc_store_terms(S.tile, tc_off(3 * gi + 2, kb), u2);
+            }
+            const double g0 = half_sum(u1 * rho[2] - u2 * rho[1]), g1 = half_sum(u2 * rho[0] - u0 * rho[2]),
+                         g2 = half_sum(u0 * rho[1] - u1 * rho[0]);
+            if (lead && act) {
+                gw[3 + 3 * gi] += g0;
+                gw[3 + 3 * gi + 1] += g1;
+                gw[3 + 3 * gi + 2] += g2;
+            }
+        }
+        // ---- shape fields: sc (B Delta_v + sum_k w_k C_k) (AvatarOptimizer.cpp:568-580); J^T r: (sc S_m) . rho ----
+#pragma unroll 1
+        for (int i = 0; 2 * i < K; ++i) {
+            const int m = 2 * i + h;
+            const bool act = m < K;
+            const int mm = act ? m : 0;
+            const double d0 = sd[mm], d1 = sd[K + mm], d2 = sd[2 * K + mm];
+            double e0 = B[0] * d0 + B[1] * d1 + B[2] * d2;
+            double e1 = B[3] * d0 + B[4] * d1 + B[5] * d2;
+            double e2 = B[6] * d0 + B[7] * d1 + B[8] * d2;
+#pragma unroll
+            for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
+                if (q < n) {
+                    const double* Cq = C + (size_t)jk[q] * 3 * K;
+                    e0 += wk[q] * Cq[mm];
+                    e1 += wk[q] * Cq[K + mm];
+                    e2 += wk[q] * Cq[2 * K + mm];
+                }
+            }
+            e0 *= sc; e1 *= sc; e2 *= sc;   // sc == 0 for an unused slot: zero fields, zero gradient
+            if (act) {
+                tc_store_terms(S.tile, tc_off(S0 + m, kb), e0);
+                tc_store_terms(S.tile, tc_off(S0 + K + m, kb), e1);
+                tc_store_terms(S.tile, tc_off(S0 + 2 * K + m, kb), e2);
+            }
+            const double gs = half_sum(e0 * rho[0] + e1 * rho[1] + e2 * rho[2]);
+            if (lead && act) gw[3 + 3 * nj + m] += gs;
+        }
+        // ---- tensor cores: D += sum over term pairs of T_ta T_tb^T over this sub-tile's vertices ----
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy tile writes -> tensor-core reads
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const int N = (nf + 15) & ~15;
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const int ksteps = (min(kTcSub, count - sub * kTcSub) + 15) >> 4;   // vertices past the chunk hold zeros up to a multiple of 16
+            const uint32_t base = smem_u32_lm(S.tile);
+            uint32_t accum = sub > 0 ? 1u : 0u;
+#pragma unroll 1
+            for (int ta = 0; ta < kTcTerms; ++ta)
+#pragma unroll 1
+                for (int tb = 0; ta + tb < kTcTerms; ++tb)
+#pragma unroll 1
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint32_t koff = (uint32_t)((ks >> 2) * kTcAtomBytes + (ks & 3) * 32);
+                        const uint64_t da = tc_desc(base + ta * kTcTermBytes + koff), db = tc_desc(base + tb * kTcTermBytes + koff);
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                            ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+                        accum = 1u;
+                    }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32_lm(mbar)) : "memory");
+        }
+    }
+    phase_lap(a.q, 13, tp);
+    const double cs = block_sum(costv, S.scr);
+    if (tid == 0) a.cpart[(size_t)f * a.maxrb + c] = cs;
+    if (cost_only) return;
+    tc_wait(mbar, phase);                                  // every MMA of the chunk has retired
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    phase_lap(a.q, 14, tp);
+    // ---- epilogue: TMEM (lane = field m, column = field) -> fp64 Gram matrix (upper block triangle) over the tile ----
+    const int n = (nf + 7) >> 3;
+    double* Gs = reinterpret_cast<double*>(S.tile);
+    if ((wid & 3) < 3) {
+        const int m = 32 * (wid & 3) + lane, bi = m >> 3;
+        const int cb0 = (wid >> 2) ? (n >> 1) : 0, cb1 = (wid >> 2) ? n : (n >> 1);
+#pragma unroll 1
+        for (int cb = cb0; cb < cb1; ++cb) {
+            uint32_t r[8];
+            const uint32_t taddr = tmem_d + ((uint32_t)(32 * (wid & 3)) << 16) + (uint32_t)(8 * cb);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (bi < n && cb >= bi) {
+                double* p = Gs + pair_index(bi, cb, n) * 64 + (m & 7) * 8;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) p[q] = (double)__uint_as_float(r[q]);
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
+    if (tid < Lg) {   // gradient: warp partials in warp order
+        double s = 0;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) s += S.gsm[w8 * kTcGcols + tid];
+        S.gvec[tid] = s;
+    }
     __syncthreads();
-    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(128));
-    emit_partial(Gs, n, nj, K, a.part + ((size_t)f * a.maxc + c) * a.pstride, tid, kTcThreads);
+    emit_partial_tc(Gs, n, nj, K, S.gvec, a.part + ((size_t)f * a.maxc + c) * a.pstride, tid, 256);
+    phase_lap(a.q, 15, tp);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -986,7 +1229,7 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
     }
     double csum = 0.0;   // cost partials in record-block order, eight loads in flight
     {
-        const int nb = (st.nslots + 255) >> 8;
+        const int nb = a.tensor ? st.nchunks : (st.nslots + 255) >> 8;   // one cost partial per fused task / per record block
 #pragma unroll 1
         for (int b = 0; b < nb; b += 8) {
             double t[8];
@@ -1344,11 +1587,32 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
 // of some frames overlap the throughput-bound record and Gram tasks of others, and the 3 x (1 + maxItersPerICP)
 // kernel boundaries of the staged schedule disappear.  Results are identical to the staged kernels: the same
 // bodies run on the same data in the same per-frame order.
-__global__ void __launch_bounds__(256, 2)
+// TC = true: the default path, fused record + Gram tasks on tcgen05 (fused_body); TC = false: fp64 DMMA Gram from fp32
+// records in HBM (rows_body + gram_body).
+constexpr int kFlowMinCtasTc = 2;
+template <bool TC>
+__global__ void __launch_bounds__(256, TC ? kFlowMinCtasTc : 2)
 lm_flow_kernel(DevModel M, DevParts Pt, LmBuf a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ int s_task, s_last;
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x;
+    uint32_t tmem_d = 0, mma_phase = 0;
+    if (TC) {   // the CTA's fp32 accumulator in tensor memory, held for the lifetime of the persistent CTA
+        if (tid < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32_lm(&s_tmem)), "r"(kTcCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32_lm(&s_mbar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        tmem_d = s_tmem;
+    }
     unsigned long long t_prev = 0;
     if (a.q.prof && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_prev));
     auto lap = [&](int cls) {   // thread 0: CTA time per task class (avb_set_profiling)
@@ -1367,9 +1631,18 @@ lm_flow_kernel(DevModel M, DevParts Pt, LmBuf a) {
         }
         __syncthreads();
         const int task = s_task;
-        if (task == -1) return;
+        if (task == -1) break;
         const int type = (int)((unsigned)task >> 30), f = (task >> 12) & 0x3FFFF, idx = task & 0xFFF;
-        if (type == kTaskRows) {
+        if (TC) {
+            const bool cost_only = ldg2(&a.state[f].last) != 0;
+            fused_body(M, Pt, a, f, idx, cost_only, smem_raw, tmem_d, &s_mbar, mma_phase);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                s_last = atomicSub(&a.q.gram_left[f], 1) == 1;
+                lap(1);
+            }
+        } else if (type == kTaskRows) {
             const int nslots = ldg2(&a.state[f].nslots);
             const bool cost_only = ldg2(&a.state[f].last) != 0;
             rows_body(M, Pt, a, f, idx, nslots, cost_only, smem_raw);
@@ -1408,6 +1681,11 @@ lm_flow_kernel(DevModel M, DevParts Pt, LmBuf a) {
             if (tid == 0) {
                 if (done) {
                     atomicSub(&a.q.ctrl[2], 1u);
+                } else if (TC) {
+                    const int nch = ldg2(&a.state[f].nchunks);
+                    atomicExch(&a.q.gram_left[f], nch);
+                    __threadfence();
+                    flow_push(a.q, kTaskFused, f, nch);
                 } else {
                     const int nrb = (ldg2(&a.state[f].nslots) + 255) >> 8;
                     atomicExch(&a.q.rows_left[f], nrb);
@@ -1418,6 +1696,11 @@ lm_flow_kernel(DevModel M, DevParts Pt, LmBuf a) {
             }
         }
         __syncthreads();
+    }
+    if (TC) {
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTcCols));
     }
 }
 
@@ -1432,9 +1715,10 @@ size_t lm_rows_smem(const DevModel& M) {
 }
 size_t lm_gram_smem(const DevModel& M, int max_nj, int chunk_verts, bool tensor) {
     const int nf = rec_floats(max_nj, M.K), nfp = (nf + 7) & ~7, n = nfp >> 3;
-    const size_t tile = tensor ? (size_t)kTcM * chunk_verts * 2 : (size_t)nfp * (chunk_verts + 4) * 4;
+    (void)tensor;
+    const size_t tile = (size_t)nfp * (chunk_verts + 4) * 4;
     const size_t gram = (size_t)num_pairs(n) * 64 * 8;
-    return (tile > gram ? tile : gram) + (tensor ? 1024 : 128);
+    return (tile > gram ? tile : gram) + 128;
 }
 
 cudaError_t launch_lm_prep(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, cudaStream_t st) {
@@ -1442,7 +1726,7 @@ cudaError_t launch_lm_prep(const DevModel& M, const DevParts& Pt, const LmBuf& a
     return cudaGetLastError();
 }
 
-// part: 0 = lm_rows_kernel, 1 = lm_gram_kernel / lm_gram_tc_kernel, 2 = lm_solve_kernel (one evaluation = the three in order)
+// part: 0 = lm_rows_kernel, 1 = lm_gram_kernel, 2 = lm_solve_kernel (one evaluation = the three in order; fp64 path only)
 cudaError_t launch_lm_eval_part(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, int max_nj, bool tensor,
                                 int part, cudaStream_t st) {
     if (part == 0) {
@@ -1450,15 +1734,11 @@ cudaError_t launch_lm_eval_part(const DevModel& M, const DevParts& Pt, const LmB
         return cudaGetLastError();
     }
     if (part == 1) {
-        const size_t gsm = lm_gram_smem(M, max_nj, a.chunk_verts, tensor);
-        cudaError_t e = tensor ? cudaFuncSetAttribute(lm_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm)
-                               : cudaFuncSetAttribute(lm_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
+        (void)tensor;   // the tensor-core Gram only exists fused into lm_flow_kernel<true>
+        const size_t gsm = lm_gram_smem(M, max_nj, a.chunk_verts, false);
+        cudaError_t e = cudaFuncSetAttribute(lm_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
         if (e != cudaSuccess) return e;
-        const dim3 grid(a.maxc, batch);
-        if (tensor)
-            lm_gram_tc_kernel<<<grid, kTcThreads, gsm, st>>>(M, Pt, a);
-        else
-            lm_gram_kernel<<<grid, kGramThreads, gsm, st>>>(M, Pt, a);
+        lm_gram_kernel<<<dim3(a.maxc, batch), kGramThreads, gsm, st>>>(M, Pt, a);
         return cudaGetLastError();
     }
     const size_t ssm = solve_smem_bytes(M.J, M.K, M.gmmC);
@@ -1468,19 +1748,28 @@ cudaError_t launch_lm_eval_part(const DevModel& M, const DevParts& Pt, const LmB
     return cudaGetLastError();
 }
 
-size_t lm_flow_smem(const DevModel& M, int max_nj, int chunk_verts) {
-    size_t b = lm_gram_smem(M, max_nj, chunk_verts, false);
-    b = b > lm_rows_smem(M) ? b : lm_rows_smem(M);
-    const size_t ssm = solve_smem_bytes(M.J, M.K, M.gmmC);
+size_t lm_flow_smem(const DevModel& M, int max_nj, int chunk_verts, bool tensor) {
+    size_t b = tensor ? tc_smem_bytes(M.J, M.K) : lm_gram_smem(M, max_nj, chunk_verts, false);
+    if (!tensor) b = b > lm_rows_smem(M) ? b : lm_rows_smem(M);
+    const size_t ssm = solve_smem_bytes(M.J, M.K, M.gmmC) + (tensor ? 1024 : 0);
     return b > ssm ? b : ssm;
 }
 cudaError_t launch_lm_flow(const DevModel& M, const DevParts& Pt, const LmBuf& a, int max_nj, int ctas, cudaStream_t st) {
-    const size_t sm = lm_flow_smem(M, max_nj, a.chunk_verts);
-    cudaError_t e = cudaFuncSetAttribute(lm_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    if (e != cudaSuccess) return e;
-    lm_flow_kernel<<<ctas, 256, sm, st>>>(M, Pt, a);
+    const size_t sm = lm_flow_smem(M, max_nj, a.chunk_verts, a.tensor != 0);
+    if (a.tensor) {
+        cudaError_t e = cudaFuncSetAttribute(lm_flow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+        lm_flow_kernel<true><<<ctas, 256, sm, st>>>(M, Pt, a);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(lm_flow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+        lm_flow_kernel<false><<<ctas, 256, sm, st>>>(M, Pt, a);
+    }
     return cudaGetLastError();
 }
+// the tensor path needs every column group to fit the tile (record fields) and the gradient scratch (columns)
+bool lm_tensor_supported(int max_nj, int K) { return tc_fields(max_nj, K) <= kTcRows && group_L(max_nj, K) <= kTcGcols; }
+int lm_flow_ctas_per_sm(bool tensor) { return tensor ? kFlowMinCtasTc : 2; }
 
 long long lm_part_stride(int max_nj, int K) {
     const int Lg = group_L(max_nj, K);

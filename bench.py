@@ -192,8 +192,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=512, help="frames per GPU per step")
-    ap.add_argument("--jtj", default="fp64", choices=["fp64", "fp32", "bf16"],
-                    help="J^T J path: fp64 (parity path, default), fp32, or bf16 = tcgen05 tensor cores (not a parity path)")
+    ap.add_argument("--jtj", default="tensor", choices=["tensor", "fp64"],
+                    help="J^T J path: tensor (default: split-bf16 tcgen05 with fp32 TMEM accumulation; J^T r and cost in fp64) "
+                         "or fp64 (DMMA Gram of fp32 records)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("AVB_LANES", "3")),
@@ -241,7 +242,7 @@ def main():
     ft = lanes[0]["ft"]
     opt = default_options()
     opt.function_tolerance = 0.0      # run all 10 LM iterations: no early exit inside the timed region
-    opt.jtj_precision = {"fp64": _lib.JTJ_FP64, "fp32": _lib.JTJ_FP32, "bf16": _lib.JTJ_BF16_TENSOR}[args.jtj]
+    opt.jtj_precision = {"fp64": _lib.JTJ_FP64, "tensor": _lib.JTJ_BF16_TENSOR}[args.jtj]
 
     def barrier():
         if world > 1:
@@ -386,8 +387,7 @@ def main():
         roofline["flow_phase_share"] = {k: round(v / tot_cta, 4) for k, v in phase_ms.items()}
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"fp64": "f64", "fp32": "f64 (J^T J accumulated in f32)",
-                      "bf16": "f64 (J^T J via bf16 tcgen05, f32 accumulate)"}[args.jtj],
+            "vs_baseline": None, "dtype": {"fp64": "f64", "tensor": "f64 (J^T J: split-bf16 tcgen05, f32 TMEM accumulate)"}[args.jtj],
             "data": "synthetic",
             "config": {"workload": "512-frame synthetic batch per GPU (BASELINE.json configs[2]), 640x576 "
                                    "smplsynth-style clouds, icp_iters=1, 10 LM iterations (function_tolerance=0)",

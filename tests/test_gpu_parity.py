@@ -12,7 +12,9 @@ PARAM_TOL = 1e-4
 CLOUD_TOL = 1e-12      # fp64 forward model, different summation order only
 COST_RTOL = 1e-9
 GRAD_RTOL = 2e-6       # Jacobian rows are stored in fp32 (relative to |grad|_inf)
-HESS_RTOL = 2e-5       # fp32 Gauss-Newton accumulation (relative to the diagonal scale)
+HESS_RTOL = 2e-5       # fp64 path: fp32 Jacobian records, fp64 accumulation (relative to the diagonal scale)
+HESS_RTOL_TENSOR = 1e-4   # default path: split-bf16 operands, fp32 accumulation in TMEM (the tensor cores' fp32 adds truncate:
+                          # J^T J comes out ~1e-6 low; up to 5e-5 of the diagonal scale in near-degenerate twist directions)
 
 
 @pytest.fixture(scope="module")
@@ -100,7 +102,7 @@ def test_objective_gradient_hessian_match_oracle(fitter, oopt, frames):
         assert abs(cost[b] - oc) <= COST_RTOL * oc
         assert np.abs(grad[b] - og).max() <= GRAD_RTOL * np.abs(og).max()
         scale = np.sqrt(np.outer(np.diag(oH), np.diag(oH)))
-        assert (np.abs(H[b] - oH) / scale).max() <= HESS_RTOL
+        assert (np.abs(H[b] - oH) / scale).max() <= HESS_RTOL_TENSOR    # default options = tensor path
         np.testing.assert_allclose(H[b], H[b].T, rtol=0, atol=1e-9 * np.abs(oH).max())
     # priors off
     o2 = _opts(beta_pose=0.0, beta_shape=0.0)
@@ -295,29 +297,35 @@ def test_stress_dense_cloud_many_iterations(model, oracle_mod, oopt, omodel, pri
     ft.close()
 
 
-def test_bf16_tensor_core_jtj_path(fitter, oopt, frames):
-    """AVB_JTJ_BF16_TENSOR (BASELINE.json configs[4]): J^T J / J^T r through tcgen05.mma with bf16 operands and fp32
-    TMEM accumulation.  Not a parity path: bf16 rounds the Jacobian (8-bit mantissa), so the tolerances are those of
-    bf16, and the fit is checked against the fp64 path by its objective value."""
-    from avatar_b200 import _lib
+def test_tensor_and_fp64_jtj_paths(fitter, oopt, frames):
+    """the default path (AVB_JTJ_BF16_TENSOR: J^T J through tcgen05.mma from split-bf16 operands with fp32 TMEM accumulation,
+    J^T r and cost in fp64) and the fp64 DMMA path (AVB_JTJ_FP64) against the oracle and against each other"""
+    from avatar_b200 import _lib, default_options
+    assert default_options().jtj_precision == _lib.JTJ_BF16_TENSOR
     pts, lab, off, x0 = _batch(frames, [0, 1])
     fitter.upload(pts, lab, off)
-    o = _opts(jtj_precision=_lib.JTJ_BF16_TENSOR)
-    fitter.debug_correspond(x0, o)
-    nn = fitter.debug_read(_lib.TAP_NN)
-    cost, grad, H = fitter.debug_evaluate(x0, o)
+    res = {}
+    for name, prec in (("tensor", _lib.JTJ_BF16_TENSOR), ("fp64", _lib.JTJ_FP64)):
+        o = _opts(jtj_precision=prec)
+        fitter.debug_correspond(x0, o)
+        nn = fitter.debug_read(_lib.TAP_NN)
+        cost, grad, H = fitter.debug_evaluate(x0, o)
+        for b in range(2):
+            p = pts[off[b]:off[b + 1]]
+            oc, og, oH = oopt.evaluate(x0[b], p, nn[off[b]:off[b + 1]], o.beta_pose, o.beta_shape)
+            assert abs(cost[b] - oc) <= COST_RTOL * oc                    # the cost never touches the tensor path
+            gerr = np.abs(grad[b] - og).max() / np.abs(og).max()
+            scale = np.sqrt(np.outer(np.diag(oH), np.diag(oH)))
+            herr = (np.abs(H[b] - oH) / scale).max()
+            print(f"{name}: frame {b}: gradient rel err {gerr:.2e}, J^T J err / diagonal scale {herr:.2e}")
+            assert gerr <= (1e-10 if name == "tensor" else GRAD_RTOL)     # tensor path: J^T r is summed in fp64 from fp64 fields
+            assert herr <= (HESS_RTOL_TENSOR if name == "tensor" else HESS_RTOL)
+        res[name] = fitter.fit_batch(pts, lab, off, x0, _opts(icp_iters=2, jtj_precision=prec))
+    (xt, stt, _), (x6, st6, _) = res["tensor"], res["fp64"]
     for b in range(2):
-        p = pts[off[b]:off[b + 1]]
-        oc, og, oH = oopt.evaluate(x0[b], p, nn[off[b]:off[b + 1]], o.beta_pose, o.beta_shape)
-        assert abs(cost[b] - oc) <= COST_RTOL * oc                    # the cost never touches the tensor path
-        assert np.abs(grad[b] - og).max() <= 1e-2 * np.abs(og).max()
-        scale = np.sqrt(np.outer(np.diag(oH), np.diag(oH)))
-        assert (np.abs(H[b] - oH) / scale).max() <= 2e-2
-    x64, st64, _ = fitter.fit_batch(pts, lab, off, x0, _opts(icp_iters=2))
-    x16, st16, _ = fitter.fit_batch(pts, lab, off, x0, _opts(icp_iters=2, jtj_precision=_lib.JTJ_BF16_TENSOR))
-    for b in range(2):
-        assert st16[b].final_cost < st16[b].initial_cost
-        assert st16[b].final_cost <= 1.05 * st64[b].final_cost
+        assert stt[b].iterations == st6[b].iterations and stt[b].accepted_steps == st6[b].accepted_steps
+        assert np.abs(xt[b] - x6[b]).max() < 1e-5
+        assert abs(stt[b].final_cost - st6[b].final_cost) <= 1e-7 * st6[b].final_cost
 
 
 # ---------------------------------------------------------------------------------------------
