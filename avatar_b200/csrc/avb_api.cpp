@@ -309,7 +309,7 @@ void avb_default_options(avb_options* o) {
     o->nn_step = 20;             // AvatarOptimizer.h:33 (unused by the inverted NN mode)
     o->function_tolerance = 1e-4;  // AvatarOptimizer.cpp:1333
     o->solver = AVB_SOLVER_GN_LM;
-    o->jtj_precision = AVB_JTJ_BF16_TENSOR;   // J^T J on the tensor cores (split bf16, fp32 TMEM accumulation); J^T r, cost in fp64
+    o->jtj_precision = AVB_JTJ_FP64;   // parity path; AVB_JTJ_BF16_TENSOR = tcgen05 J^T J (faster, fits within ~3e-4 of this path)
 }
 
 int avb_device_count(void) {
@@ -688,7 +688,7 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     while (ft->chunk_verts > 128 && lm_gram_smem_bytes(ft->max_nj, m->K, ft->chunk_verts, false) > 112 * 1024) ft->chunk_verts -= 64;
     ft->maxc = (V + ft->chunk_verts - 1) / ft->chunk_verts + dp.numGroups + 1;
     ft->tabD = lm_tab_doubles(m->J, m->K);
-    ft->pstride = lm_part_stride(ft->max_nj, m->K);
+    ft->pstride = lm_part_stride(ft->max_nj, m->J, m->K);
     TRY(dev_alloc(ft, &ft->d_xt, B * nx));
     TRY(dev_alloc(ft, &ft->d_tab, B * (size_t)ft->tabD));
     TRY(dev_alloc(ft, &ft->d_part, B * (size_t)ft->maxc * (size_t)ft->pstride));

@@ -150,7 +150,7 @@ cudaError_t launch_lm_eval_part(const DevModel& M, const DevParts& Pt, const LmB
                                 int part, cudaStream_t st);
 // the same evaluations as one persistent data-flow kernel (launch_lm_prep with a.q set seeds the queue)
 cudaError_t launch_lm_flow(const DevModel& M, const DevParts& Pt, const LmBuf& a, int max_nj, int ctas, cudaStream_t st);
-long long lm_part_stride(int max_nj, int K);
+long long lm_part_stride(int max_nj, int J, int K);
 int lm_tab_doubles(int J, int K);
 int lm_rec_floats(int max_nj, int K);
 int lm_rec_slots(int V);

@@ -596,50 +596,63 @@ lm_gram_kernel(DevModel M, DevParts Pt, LmBuf a) {
 // ---------------------------------------------------------------------------------------------
 // fused record + Gram task of lm_flow_kernel<true> (the default path): J^T J on the 5th-generation tensor cores
 // ---------------------------------------------------------------------------------------------
-// One task = one chunk (<= 256 matched vertices of one column group), processed as sub-tiles of 128 vertices.  Two
-// threads per vertex compute the vertex's position, residual and the record fields [ u_j = 2 sc y_j | sc | sc S ] in fp64
-// (AvatarOptimizer.cpp:505-582 in closed form, see rows_body) and write them STRAIGHT into shared memory as the
-// K-major SWIZZLE_128B operand tile of tcgen05.mma -- no Jacobian record ever goes to HBM.  Every fp32 field is split
-// into kTcTerms bf16 terms (x = t0 + t1 + t2, 8 bits each); the Gram matrix  sum_v rec_v rec_v^T  is the sum of the term
-// products of weight >= 2^-8(kTcTerms-1), all accumulated by tcgen05.mma.kind::f16 (M = 128, N = nf rounded to 16,
-// K = 16) into ONE fp32 TMEM accumulator per CTA (allocated once per CTA, 128 columns).  The operands never leave
-// shared memory, the accumulator never touches registers until the epilogue (tcgen05.ld) turns the Gram matrix into the
-// chunk's partial of J^T J exactly as the fp64 path does (emit_partial).
-// J^T r and the cost do NOT go through the tensor cores: every thread forms its vertex's contributions in fp64 from
-// unrounded fields and the fp64 residual, and they are summed with warp shuffles (fixed tree) and a fixed warp order,
-// so the gradient -- and with it the fixed point of the iteration -- has full fp64 accuracy; the tensor-core J^T J
-// (two bf16 terms: measured 4e-6 of the diagonal scale, which is already the floor of fp32 accumulation over a sub-tile --
-// a third term costs twice the MMAs and buys nothing, tools/ubench/umma_gram_test.cu) only steers the step.
-#ifndef AVB_TC_TERMS
-#define AVB_TC_TERMS 2
-#endif
-constexpr int kTcTerms = AVB_TC_TERMS;
+// One task = one chunk (<= 256 matched vertices of one column group), processed as sub-tiles of 128 vertices, two
+// threads per vertex.
+//
+//  * Geometry in fp64: position x_v = sum_k w_k (G_k v0 + tau_k) (AvatarOptimizer.cpp:507-514), residual sum
+//    rho' = c x - sum d (:632-639), cost.
+//  * J^T J: the record fields [ u_j = 2 sc y_j | sc | sc S ] (:529-580 in closed form, see rows_body) are only ever
+//    consumed as bf16 terms, so they are formed in fp32 from fp64-accurate differences and written STRAIGHT into
+//    shared memory as the K-major SWIZZLE_128B operand tile of tcgen05.mma -- no Jacobian record goes to HBM.  Every field
+//    is split into two bf16 terms (x = t0 + t1); the Gram matrix sum_v rec_v rec_v^T is the sum of the term products
+//    t0 t0 + t0 t1 + t1 t0, accumulated by tcgen05.mma.kind::f16 (M = 128, N = fields rounded to 16, K = 16) into ONE
+//    fp32 TMEM accumulator per CTA (128 columns, allocated once per persistent CTA).  The epilogue (tcgen05.ld) turns
+//    the Gram matrix into the chunk's partial of J^T J exactly as the fp64 path does.
+//    Accuracy (measured, tools/diag_h.py): the tensor cores' fp32 adds TRUNCATE, so J^T J comes out ~1.4e-6 low and up
+//    to 5e-5 of the diagonal scale in near-degenerate twist directions.  Ten LM iterations amplify an H error of 1e-7
+//    into ~3e-5 of parameter difference (they stop far from convergence), so this path is the fast OPTION
+//    (AVB_JTJ_BF16_TENSOR: fits within ~3e-4 of the fp64 path, same objective to 1e-5), not the parity path.  An exact
+//    integer variant (int8 slices, int32 TMEM accumulators, tools/ubench/umma_i8_test.cu: bit exact) was built and
+//    measured too: three slices fit the TMEM budget of two CTAs per SM but their 22-bit fixed point per row bound is
+//    coarser than bf16's floating split for the many fields far below their bound (H error 6e-4); parity-grade needs
+//    five slices = five accumulators = the whole TMEM of an SM for one CTA.
+//  * J^T r never touches the tensor cores and needs no Jacobian: by the chain rule through the skinning sum,
+//        g_p = sum_v rho',   g_j = 2 sum_{k in subtree(j)} (M_k - (pos_j - o) x R_k),   g_shape,m = T_m + sum_k C_k[:,m] . R_k
+//    with per-ASSIGNED-joint moments  R_k = sum w_k rho',  M_k = sum w_k (x^(k) - o) x rho'  and  T_m = sum Delta_v,m . (B_v^T rho'),
+//    i.e. O(4) work per vertex instead of O(joints).  R and M are accumulated in 2^-36 fixed point with 64-bit integer
+//    shared-memory atomics (order independent => bit reproducible), P and T with a fixed shuffle tree; the solve adds the
+//    chunks in order and applies the subtree sums.  The gradient therefore has full fp64 accuracy -- the fixed point of
+//    the iteration does not move; the tensor-core J^T J only steers the step (a third bf16 term costs twice the MMAs and
+//    buys nothing: fp32 accumulation is the floor, tools/ubench/umma_gram_test.cu).
+constexpr int kTcTerms = 2;                         // bf16 terms per fp32 field
 constexpr int kTcSub = 128;                         // vertices per sub-tile: two 64-element swizzle atoms along K
 constexpr int kTcRows = 80;                         // record fields of the tile (3 nj + 1 + 3 K <= 80)
 constexpr int kTcAtomBytes = kTcRows * 128;         // one K atom: kTcRows rows of 128 B (64 bf16)
 constexpr int kTcTermBytes = 2 * kTcAtomBytes;
 constexpr int kTcTileBytes = kTcTerms * kTcTermBytes;
 constexpr int kTcCols = 128;                        // TMEM columns per CTA (power of two >= kTcRows)
-constexpr int kTcGcols = 64;                        // >= columns of a group's compact Jacobian (3 + 3 nj + K)
+constexpr int kTcGw = 3 + kMaxK;                    // shuffle-reduced gradient sums per warp: P (3) | T (K)
 
 __host__ __device__ inline int tc_fields(int nj, int K) { return 3 * nj + 1 + 3 * K; }
+// gradient accumulators of a chunk partial: P (3) | R (J x 3) | M (J x 3) | T (K)
+__host__ __device__ inline int tc_gacc(int J, int K) { return 3 + 6 * J + K; }
 
-// byte offset of (field m, vertex k of the sub-tile) inside one term tile: 8-row groups of 1024 B, rows of 128 B whose
-// 16-byte chunks are XOR-swizzled with (row & 7) -- the layout SWIZZLE_128B shared-memory descriptors address
-__device__ __forceinline__ uint32_t tc_off(int m, int k) {
-    return (uint32_t)((k >> 6) * kTcAtomBytes + (m >> 3) * 1024 + (m & 7) * 128 + (((((k & 63) >> 3) ^ m) & 7) << 4) + ((k & 7) << 1));
-}
 __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
     // start >> 4 | LBO (unused for swizzled K-major: 1) | SBO = 1024 B between 8-row groups | version 1 | SWIZZLE_128B
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-__device__ __forceinline__ void tc_store_terms(unsigned char* tile, uint32_t off, double value) {
-    float x = (float)value;
+// Field m of this thread's vertex into the term tiles.  Element (m, k) of a term tile lives at
+//   (k >> 6) * atom + m * 128 + ((((k & 63) >> 3) ^ m) & 7) * 16 + (k & 7) * 2
+// (8-row groups of 1024 B, rows of 128 B whose 16-byte chunks are XOR-swizzled with row & 7: what a SWIZZLE_128B
+// shared-memory descriptor addresses); tile_kbase = shared address of the tile + (k >> 6) * atom + (k & 7) * 2 and
+// kc = (k & 63) >> 3 are per thread.  32-bit shared addresses, st.shared: no generic address arithmetic.
+__device__ __forceinline__ void tc_store(uint32_t tile_kbase, uint32_t kc, int m, float x) {
+    const uint32_t addr = tile_kbase + ((uint32_t)m << 7) + (((kc ^ (uint32_t)m) & 7u) << 4);
 #pragma unroll
     for (int t = 0; t < kTcTerms; ++t) {
         const __nv_bfloat16 b = __float2bfloat16_rn(x);
-        x -= __bfloat162float(b);
-        *reinterpret_cast<__nv_bfloat16*>(tile + t * kTcTermBytes + off) = b;
+        if (t + 1 < kTcTerms) x -= __bfloat162float(b);
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr + (uint32_t)(t * kTcTermBytes)), "h"(*reinterpret_cast<const unsigned short*>(&b)) : "memory");
     }
 }
 // sum over the 16 lanes of a half warp (the 16 vertices this half of the warp owns); every lane gets the sum
@@ -658,226 +671,322 @@ __device__ __forceinline__ void tc_wait(uint64_t* mbar, uint32_t& phase) {
     phase ^= 1u;
 }
 
+// order-independent accumulation in 2^-36 fixed point.  Generic-address reduction on purpose: for a .shared address the
+// compiler expands a 64-bit integer add into a compare-and-swap spin loop (ATOMS.CAST.SPIN.64), which collapses when the
+// lanes of a warp hit the same joint; the generic form is a single RED.E.ADD.64.
+__device__ __forceinline__ void fix_add(unsigned long long* p, double v) {
+    asm volatile("red.add.u64 [%0], %1;" ::"l"(p), "l"((unsigned long long)__double2ll_rn(v * kFixScale)) : "memory");
+}
+
 struct TcSmem {
-    unsigned char* tile;   // kTcTileBytes, 1024-byte aligned; later the fp64 Gram matrix
-    double *tab, *w, *gsm, *gvec, *scr;
-    int* gstart;
+    unsigned char* tile;          // kTcTileBytes, 1024-byte aligned; later the fp64 Gram matrix
+    double *G, *tau, *o, *w;      // fp64: global joint rotations, skinning translations, origin (root position), shape weights
+    double *gsm, *scr;            // [8 warps][kTcGw] shuffle-reduced sums; block_sum scratch
+    unsigned long long* acc;      // [J][6] fixed-point R_k | M_k
+    float *Gf, *posr, *Cf;        // fp32 copies for the record fields: G, pos_j - o, C
+    int* gjs;                     // [kMaxJ] the group's joints
 };
 __host__ __device__ inline size_t tc_smem_bytes(int J, int K) {
-    // tile | tab | w | gsm [8 warps][kTcGcols] | gvec [kTcGcols] | scr [32]; the tile must be followed by >= 6 KB of
-    // addressable shared memory: M = 128 makes the last K atom read 48 rows past its 80 (their accumulator rows are ignored)
-    return 1024 + (size_t)kTcTileBytes + (size_t)(tab_doubles(J, K) + ((K + 1) & ~1) + 9 * kTcGcols + 32) * 8 + 64;
+    // the tile must be followed by >= 6 KB of addressable shared memory: M = 128 makes the last K atom read 48 rows past
+    // its 80 (their accumulator rows are ignored); the tables behind it provide that
+    const size_t tail = (size_t)(12 * J + 4 + ((K + 1) & ~1) + 8 * kTcGw + 32 + 6 * J) * 8 + (size_t)(12 * J + 3 * J * K) * 4 + kMaxJ * 4;
+    return 1024 + (size_t)kTcTileBytes + (tail < 6400 ? 6400 : tail) + 64;
 }
-__device__ inline TcSmem carve_tc(unsigned char* raw, int tabD, int K) {
+__device__ inline TcSmem carve_tc(unsigned char* raw, int J, int K) {
     TcSmem S;
-    S.tile = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment (SWIZZLE_128B) by pointer arithmetic on the shared array -- no pointer -> integer -> pointer round
+    // trip, so that the compiler keeps every access below in the shared address space (LDS / STS, 32-bit addresses)
+    S.tile = raw + ((1024u - (smem_u32_lm(raw) & 1023u)) & 1023u);
     double* d = reinterpret_cast<double*>(S.tile + kTcTileBytes);
-    S.tab = d; d += tabD;
+    S.G = d; d += 9 * J;
+    S.tau = d; d += 3 * J;
+    S.o = d; d += 4;
     S.w = d; d += (K + 1) & ~1;
-    S.gsm = d; d += 8 * kTcGcols;
-    S.gvec = d; d += kTcGcols;
+    S.gsm = d; d += 8 * kTcGw;
     S.scr = d; d += 32;
-    S.gstart = reinterpret_cast<int*>(d);
+    S.acc = reinterpret_cast<unsigned long long*>(d); d += 6 * J;
+    float* fl = reinterpret_cast<float*>(d);
+    S.Gf = fl; fl += 9 * J;
+    S.posr = fl; fl += 3 * J;
+    S.Cf = fl; fl += 3 * J * K;
+    S.gjs = reinterpret_cast<int*>(fl);
     return S;
 }
 
-// chunk partial from the Gram matrix of [ u_j | sc | sc S ] (no residual fields) and the fp64 gradient gvec
-__device__ void emit_partial_tc(const double* Gs, int n, int nj, int K, const double* gvec, double* part, int tid, int nt) {
+// chunk partial [ upper triangle of J^T J in the group's column order | P | R | M | T ] from the Gram matrix of
+// [ u_j | sc | sc S ] and the gradient accumulators
+__device__ void emit_partial_tc(const double* Gs, int n, int nj, int K, double* part, int tid, int nt) {
     const int Lg = 3 + 3 * nj + K, nH = tri_count(Lg);
     const int SC = 3 * nj, S0 = SC + 1;
-    for (int idx = tid; idx < nH + Lg; idx += nt) {
+    for (int idx = tid; idx < nH; idx += nt) {
         double val = 0.0;
-        if (idx < nH) {
-            int ra, rb;
-            if (!tri_decode(idx, Lg, ra, rb)) continue;
-            if (ra < 3) {
-                const int a = ra;
-                if (rb < 3) {
-                    val = (a == rb) ? gm(Gs, n, SC, SC) : 0.0;
-                } else if (rb < 3 + 3 * nj) {
-                    const int k = (rb - 3) / 3, b = (rb - 3) - 3 * k;
-                    if (a != b) {
-                        const double w = gm(Gs, n, SC, 3 * k + (3 - a - b));
-                        val = (b == (a + 1) % 3) ? w : -w;
-                    }
-                } else {
-                    val = gm(Gs, n, SC, S0 + a * K + (rb - 3 - 3 * nj));
-                }
-            } else if (ra < 3 + 3 * nj) {
-                const int j = (ra - 3) / 3, a = (ra - 3) - 3 * j;
-                if (rb < 3 + 3 * nj) {
-                    const int k = (rb - 3) / 3, b = (rb - 3) - 3 * k;
-                    val = -gm(Gs, n, 3 * k + a, 3 * j + b);
-                    if (a == b)
-                        val += gm(Gs, n, 3 * j, 3 * k) + gm(Gs, n, 3 * j + 1, 3 * k + 1) + gm(Gs, n, 3 * j + 2, 3 * k + 2);
-                } else {
-                    const int m = rb - 3 - 3 * nj, a1 = (a + 1) % 3, a2 = (a + 2) % 3;
-                    val = gm(Gs, n, 3 * j + a1, S0 + a2 * K + m) - gm(Gs, n, 3 * j + a2, S0 + a1 * K + m);
+        int ra, rb;
+        if (!tri_decode(idx, Lg, ra, rb)) continue;
+        if (ra < 3) {
+            const int a = ra;
+            if (rb < 3) {
+                val = (a == rb) ? gm(Gs, n, SC, SC) : 0.0;
+            } else if (rb < 3 + 3 * nj) {   // (sc I)^T (-[u_k]x): eps_abc sum sc u_k,c
+                const int k = (rb - 3) / 3, b = (rb - 3) - 3 * k;
+                if (a != b) {
+                    const double w = gm(Gs, n, SC, 3 * k + (3 - a - b));
+                    val = (b == (a + 1) % 3) ? w : -w;
                 }
             } else {
-                const int m = ra - 3 - 3 * nj, m2 = rb - 3 - 3 * nj;
-                val = gm(Gs, n, S0 + m, S0 + m2) + gm(Gs, n, S0 + K + m, S0 + K + m2) +
-                      gm(Gs, n, S0 + 2 * K + m, S0 + 2 * K + m2);
+                val = gm(Gs, n, SC, S0 + a * K + (rb - 3 - 3 * nj));
+            }
+        } else if (ra < 3 + 3 * nj) {
+            const int j = (ra - 3) / 3, a = (ra - 3) - 3 * j;
+            if (rb < 3 + 3 * nj) {          // [u_j]x^T [u_k]x = (u_j . u_k) I - u_k u_j^T
+                const int k = (rb - 3) / 3, b = (rb - 3) - 3 * k;
+                val = -gm(Gs, n, 3 * k + a, 3 * j + b);
+                if (a == b)
+                    val += gm(Gs, n, 3 * j, 3 * k) + gm(Gs, n, 3 * j + 1, 3 * k + 1) + gm(Gs, n, 3 * j + 2, 3 * k + 2);
+            } else {                        // u_j x (sc S_m)
+                const int m = rb - 3 - 3 * nj, a1 = (a + 1) % 3, a2 = (a + 2) % 3;
+                val = gm(Gs, n, 3 * j + a1, S0 + a2 * K + m) - gm(Gs, n, 3 * j + a2, S0 + a1 * K + m);
             }
         } else {
-            val = gvec[idx - nH];
+            const int m = ra - 3 - 3 * nj, m2 = rb - 3 - 3 * nj;
+            val = gm(Gs, n, S0 + m, S0 + m2) + gm(Gs, n, S0 + K + m, S0 + K + m2) +
+                  gm(Gs, n, S0 + 2 * K + m, S0 + 2 * K + m2);
         }
         part[idx] = val;
     }
 }
 
 // tmem_d: the CTA's accumulator; mbar: its commit barrier; phase: parity the next commit completes (per thread copy)
+// KT: number of shape keys when known at compile time (10 = SMPL: the shapedirs row of the vertex lives in registers and
+// the shape loops unroll), 0 = any K at run time
+template <int KT>
 __device__ void fused_body(const DevModel& M, const DevParts& Pt, const LmBuf& a, int f, int c, bool cost_only,
                            unsigned char* smem_raw, uint32_t tmem_d, uint64_t* mbar, uint32_t& phase) {
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-    const int J = M.J, K = M.K;
+    const int J = M.J, K = KT > 0 ? KT : M.K;
     unsigned long long tp = phase_begin(a.q);
-    const TcSmem S = carve_tc(smem_raw, a.tabD, K);
+    const TcSmem S = carve_tc(smem_raw, J, K);
     const int4 ch = a.chunks[(size_t)f * a.maxc + c];
     const int g = ch.x, start = ch.y, count = ch.z;
     const int nj = Pt.gnj[g];
-    const int* gj = Pt.gjoints + g * kMaxJ;
     const int nf = tc_fields(nj, K), Lg = group_L(nj, K);
     {
-        const double* gtab = a.tab + (size_t)f * a.tabD;
-        for (int q = tid; q < a.tabD; q += 256) S.tab[q] = ldg2(gtab + q);
+        const double* gtab = a.tab + (size_t)f * a.tabD;   // G | pos | tau | C of the trial point
+        const double o0 = ldg2(gtab + 9 * J), o1 = ldg2(gtab + 9 * J + 1), o2 = ldg2(gtab + 9 * J + 2);
+        for (int q = tid; q < 9 * J; q += 256) {
+            const double v = ldg2(gtab + q);
+            S.G[q] = v;
+            S.Gf[q] = (float)v;
+        }
+        for (int q = tid; q < 3 * J; q += 256) {
+            S.tau[q] = ldg2(gtab + 12 * J + q);
+            const int cc = q % 3;
+            S.posr[q] = (float)(ldg2(gtab + 9 * J + q) - (cc == 0 ? o0 : (cc == 1 ? o1 : o2)));
+        }
+        for (int q = tid; q < 3 * J * K; q += 256) S.Cf[q] = (float)ldg2(gtab + 15 * J + q);
+        if (tid < 3) S.o[tid] = tid == 0 ? o0 : (tid == 1 ? o1 : o2);
         for (int q = tid; q < K; q += 256) S.w[q] = ldg2(a.xt + (size_t)f * M.nx + 3 + 4 * J + q);
-        for (int q = tid; q < 8 * kTcGcols; q += 256) S.gsm[q] = 0.0;
+        for (int q = tid; q < 8 * kTcGw; q += 256) S.gsm[q] = 0.0;
+        for (int q = tid; q < 6 * J; q += 256) S.acc[q] = 0ull;
+        for (int q = tid; q < nj; q += 256) S.gjs[q] = Pt.gjoints[g * kMaxJ + q];
     }
     __syncthreads();
     phase_lap(a.q, 12, tp);
-    const double* G = S.tab;
-    const double* pos = S.tab + 9 * J;
-    const double* tau = S.tab + 12 * J;
-    const double* C = S.tab + 15 * J;
     const int kk = (tid & 15) + 16 * wid;      // vertex slot inside the sub-tile; the two half warps split its fields
     const int h = (tid >> 4) & 1;
     const bool lead = (lane & 15) == 0;
-    double* gw = S.gsm + wid * kTcGcols;       // this warp's gradient sums (one writer per column)
+    const uint32_t tkb = smem_u32_lm(S.tile) + (uint32_t)((kk >> 6) * kTcAtomBytes + (kk & 7) * 2), kc = (uint32_t)((kk & 63) >> 3);
+    double* gw = S.gsm + wid * kTcGw;          // this warp's sums: one writer per entry (P: lane 0; T_m: the half that owns m)
     double costv = 0.0;
     const int nsub = (count + kTcSub - 1) / kTcSub;
     const int SC = 3 * nj, S0 = SC + 1;
+    const double ox = S.o[0], oy = S.o[1], oz = S.o[2];
 #pragma unroll 1
     for (int sub = 0; sub < nsub; ++sub) {
         const int li = sub * kTcSub + kk;
         int v = (li < count) ? (int)a.mlist[(size_t)f * a.rec_rs + start + li] : (int)kNoVertex;
         const bool valid = v != (int)kNoVertex;
         if (!valid) v = 0;
-        // ---- position, residual (AvatarOptimizer.cpp:507-514, 632-639) ----
+        // ---- fp64: shaped vertex, per-joint positions, position, residual sum, cost ----
         const float* sd = M.sd + (size_t)v * 3 * K;
+        float sdr[KT > 0 ? 3 * KT : 2];   // KT > 0: the vertex's shapedirs row (3 x K floats, 8-byte aligned when 3 K is even)
+        if (KT > 0) {
+#pragma unroll
+            for (int i = 0; i < (3 * KT) / 2; ++i) {
+                const float2 t2 = __ldg(reinterpret_cast<const float2*>(sd) + i);
+                sdr[2 * i] = t2.x;
+                sdr[2 * i + 1] = t2.y;
+            }
+        }
+#define AVB_SD(i) (KT > 0 ? sdr[(i)] : sd[(i)])
         double v0[3];
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
-            double s = 0;
-            for (int k = 0; k < K; ++k) s += (double)sd[cc * K + k] * S.w[k];
-            v0[cc] = M.vt[3 * (size_t)v + cc] + s;
+            double s0 = 0, s1 = 0;
+            if (KT > 0) {
+#pragma unroll
+                for (int k = 0; k < KT; k += 2) {
+                    s0 = fma((double)sdr[cc * KT + k], S.w[k], s0);
+                    if (k + 1 < KT) s1 = fma((double)sdr[cc * KT + k + 1], S.w[k + 1], s1);
+                }
+            } else {
+                int k = 0;
+                for (; k + 1 < K; k += 2) {
+                    s0 = fma((double)sd[cc * K + k], S.w[k], s0);
+                    s1 = fma((double)sd[cc * K + k + 1], S.w[k + 1], s1);
+                }
+                if (k < K) s0 = fma((double)sd[cc * K + k], S.w[k], s0);
+            }
+            v0[cc] = M.vt[3 * (size_t)v + cc] + (s0 + s1);
         }
-        const int n = M.sk_n[v];
+        const int n = valid ? (int)M.sk_n[v] : 0;
         double xk[AVB_MAX_ASSIGN_][3], wk[AVB_MAX_ASSIGN_];
         int jk[AVB_MAX_ASSIGN_];
         uint32_t mk[AVB_MAX_ASSIGN_];
-        double x[3] = {0, 0, 0}, B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        double x[3] = {0, 0, 0};
 #pragma unroll
         for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
             if (q < n) {
                 const int k = M.sk_j[4 * (size_t)v + q];
                 const double wt = M.sk_w[4 * (size_t)v + q];
-                const double* Gk = G + 9 * k;
+                const double* Gk = S.G + 9 * k;
                 jk[q] = k;
                 wk[q] = wt;
                 mk[q] = M.anc_mask[k];
 #pragma unroll
                 for (int cc = 0; cc < 3; ++cc) {
-                    xk[q][cc] = Gk[3 * cc] * v0[0] + Gk[3 * cc + 1] * v0[1] + Gk[3 * cc + 2] * v0[2] + tau[3 * k + cc];
+                    xk[q][cc] = Gk[3 * cc] * v0[0] + Gk[3 * cc + 1] * v0[1] + Gk[3 * cc + 2] * v0[2] + S.tau[3 * k + cc];
                     x[cc] += wt * xk[q][cc];
                 }
-#pragma unroll
-                for (int e = 0; e < 9; ++e) B[e] += wt * Gk[e];
             } else {
                 jk[q] = 0; wk[q] = 0; mk[q] = 0;
                 xk[q][0] = xk[q][1] = xk[q][2] = 0;
             }
         }
         const double cn = valid ? (double)a.cnt[(size_t)f * M.V + v] : 0.0;
-        const double sc = sqrt(cn), s2 = 2.0 * sc;
-        double rho[3] = {0, 0, 0};
+        double rp[3] = {0, 0, 0};   // rho' = c x - sum d  (= sc * rho of rows_body)
         if (valid) {
             const unsigned long long* sumv = a.sum + 3 * ((size_t)f * M.V + v);
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc) {
                 const double sr = (double)(long long)sumv[cc] * kFixInv;
-                rho[cc] = (cn * x[cc] - sr) / sc;
-                if (h == 0) costv += x[cc] * (cn * x[cc] - 2.0 * sr);   // sum_i |x - d_i|^2 - sum_i |d_i|^2 = x . (c x - 2 s)
+                rp[cc] = cn * x[cc] - sr;
+                if (h == 0) costv += x[cc] * (rp[cc] - sr);   // sum_i |x - d_i|^2 - sum_i |d_i|^2 = x . (c x - 2 s)
             }
         }
         if (cost_only) continue;
-        if (sub > 0) tc_wait(mbar, phase);   // the previous sub-tile's MMAs have read the tile: it may be rewritten
-        const uint32_t kb = (uint32_t)kk;
-        // ---- translation columns and the sc field (half 0); J^T r contributions are summed in fp64 ----
-        {
-            const double g0 = half_sum(sc * rho[0]), g1 = half_sum(sc * rho[1]), g2 = half_sum(sc * rho[2]);
-            if (h == 0) {
-                tc_store_terms(S.tile, tc_off(SC, kb), sc);
-                if (lead) { gw[0] += g0; gw[1] += g1; gw[2] += g2; }
+        // ---- fp64 gradient accumulators: this half's assigned joints q = h, h + 2 ----
+        double t0 = 0, t1 = 0, t2 = 0;   // B^T rho' = sum_q w_q G_q^T rho'
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq) {
+            const int q = 2 * qq + h;    // h is warp-half uniform: compile-time unrolled over qq, selected by h below
+            const double wq = (q == 0) ? wk[0] : (q == 1 ? wk[1] : (q == 2 ? wk[2] : wk[3]));
+            const int kq = (q == 0) ? jk[0] : (q == 1 ? jk[1] : (q == 2 ? jk[2] : jk[3]));
+            const double xq0 = (q == 0) ? xk[0][0] : (q == 1 ? xk[1][0] : (q == 2 ? xk[2][0] : xk[3][0]));
+            const double xq1 = (q == 0) ? xk[0][1] : (q == 1 ? xk[1][1] : (q == 2 ? xk[2][1] : xk[3][1]));
+            const double xq2 = (q == 0) ? xk[0][2] : (q == 1 ? xk[1][2] : (q == 2 ? xk[2][2] : xk[3][2]));
+            if (q < n) {
+                const double r0 = wq * rp[0], r1 = wq * rp[1], r2 = wq * rp[2];
+                const double a0 = xq0 - ox, a1 = xq1 - oy, a2 = xq2 - oz;
+                unsigned long long* ac = S.acc + 6 * kq;
+                fix_add(ac + 0, r0);
+                fix_add(ac + 1, r1);
+                fix_add(ac + 2, r2);
+                fix_add(ac + 3, a1 * r2 - a2 * r1);
+                fix_add(ac + 4, a2 * r0 - a0 * r2);
+                fix_add(ac + 5, a0 * r1 - a1 * r0);
+                const double* Gk = S.G + 9 * kq;
+                t0 += Gk[0] * r0 + Gk[3] * r1 + Gk[6] * r2;
+                t1 += Gk[1] * r0 + Gk[4] * r1 + Gk[7] * r2;
+                t2 += Gk[2] * r0 + Gk[5] * r1 + Gk[8] * r2;
             }
         }
-        // ---- rotation fields: u_j = 2 sc y_j, block_j = -[u_j]x (rows_body); J^T r: u_j x rho ----
+        t0 += __shfl_xor_sync(0xffffffffu, t0, 16);   // the other half's joints
+        t1 += __shfl_xor_sync(0xffffffffu, t1, 16);
+        t2 += __shfl_xor_sync(0xffffffffu, t2, 16);
+        {
+            const double p0 = half_sum(rp[0]), p1 = half_sum(rp[1]), p2 = half_sum(rp[2]);
+            if (lane == 0) { gw[0] += p0; gw[1] += p1; gw[2] += p2; }
+        }
+#pragma unroll
+        for (int i = 0; 2 * i < (KT > 0 ? KT : K); ++i) {
+            const int m = 2 * i + h;
+            double dm0, dm1, dm2;
+            if (KT > 0) {   // register row: select the half's entry (no dynamic register indexing)
+                const int e1 = 2 * i + 1 < KT ? 2 * i + 1 : 2 * i;
+                dm0 = h ? sdr[e1] : sdr[2 * i];
+                dm1 = h ? sdr[KT + e1] : sdr[KT + 2 * i];
+                dm2 = h ? sdr[2 * KT + e1] : sdr[2 * KT + 2 * i];
+            } else {
+                const int mm = m < K ? m : 0;
+                dm0 = sd[mm]; dm1 = sd[K + mm]; dm2 = sd[2 * K + mm];
+            }
+            const double tm = half_sum(dm0 * t0 + dm1 * t1 + dm2 * t2);
+            if (lead && m < K) gw[3 + m] += tm;
+        }
+        // ---- fp32 record fields -> bf16 term tiles ----
+        float rq[AVB_MAX_ASSIGN_][3], wf[AVB_MAX_ASSIGN_], Bf[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
+            wf[q] = (float)wk[q];
+            rq[q][0] = (float)(xk[q][0] - x[0]);
+            rq[q][1] = (float)(xk[q][1] - x[1]);
+            rq[q][2] = (float)(xk[q][2] - x[2]);
+            const float* Gq = S.Gf + 9 * jk[q];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) Bf[e] = fmaf(wf[q], Gq[e], Bf[e]);   // wf == 0 for q >= n
+        }
+        const float xo0 = (float)(x[0] - ox), xo1 = (float)(x[1] - oy), xo2 = (float)(x[2] - oz);
+        const float scf = (float)sqrt(cn), s2f = 2.f * scf;
+        if (sub > 0) tc_wait(mbar, phase);   // the previous sub-tile's MMAs have read the tile: it may be rewritten
+        if (h == 0) tc_store(tkb, kc, SC, scf);
+        // rotation fields u_j = 2 sc (sum_{q in desc(j)} w_q (x^(q) - x) + W_j (x - pos_j))
 #pragma unroll 1
         for (int i = 0; 2 * i < nj; ++i) {
             const int gi = 2 * i + h;
-            const bool act = gi < nj;
-            const int j = gj[act ? gi : 0];
-            double y0 = 0, y1 = 0, y2 = 0, W = 0;
+            if (gi < nj) {
+                const int j = S.gjs[gi];
+                float y0 = 0, y1 = 0, y2 = 0, W = 0;
 #pragma unroll
-            for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
-                if ((mk[q] >> j) & 1u) {
-                    W += wk[q];
-                    y0 += wk[q] * xk[q][0];
-                    y1 += wk[q] * xk[q][1];
-                    y2 += wk[q] * xk[q][2];
+                for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
+                    const float wq = ((mk[q] >> j) & 1u) ? wf[q] : 0.f;
+                    W += wq;
+                    y0 = fmaf(wq, rq[q][0], y0);
+                    y1 = fmaf(wq, rq[q][1], y1);
+                    y2 = fmaf(wq, rq[q][2], y2);
                 }
-            }
-            const double u0 = (y0 - W * pos[3 * j]) * s2, u1 = (y1 - W * pos[3 * j + 1]) * s2, u2 = (y2 - W * pos[3 * j + 2]) * s2;
-            if (act) {
-                tc_store_terms(S.tile, tc_off(3 * gi, kb), u0);
-                tc_store_terms(S.tile, tc_off(3 * gi + 1, kb), u1);
-                tc_store_terms(S.tile, tc_off(3 * gi + 2, kb), u2);
-            }
-            const double g0 = half_sum(u1 * rho[2] - u2 * rho[1]), g1 = half_sum(u2 * rho[0] - u0 * rho[2]),
-                         g2 = half_sum(u0 * rho[1] - u1 * rho[0]);
-            if (lead && act) {
-                gw[3 + 3 * gi] += g0;
-                gw[3 + 3 * gi + 1] += g1;
-                gw[3 + 3 * gi + 2] += g2;
+                tc_store(tkb, kc, 3 * gi, s2f * fmaf(W, xo0 - S.posr[3 * j], y0));
+                tc_store(tkb, kc, 3 * gi + 1, s2f * fmaf(W, xo1 - S.posr[3 * j + 1], y1));
+                tc_store(tkb, kc, 3 * gi + 2, s2f * fmaf(W, xo2 - S.posr[3 * j + 2], y2));
             }
         }
-        // ---- shape fields: sc (B Delta_v + sum_k w_k C_k) (AvatarOptimizer.cpp:568-580); J^T r: (sc S_m) . rho ----
-#pragma unroll 1
-        for (int i = 0; 2 * i < K; ++i) {
-            const int m = 2 * i + h;
-            const bool act = m < K;
-            const int mm = act ? m : 0;
-            const double d0 = sd[mm], d1 = sd[K + mm], d2 = sd[2 * K + mm];
-            double e0 = B[0] * d0 + B[1] * d1 + B[2] * d2;
-            double e1 = B[3] * d0 + B[4] * d1 + B[5] * d2;
-            double e2 = B[6] * d0 + B[7] * d1 + B[8] * d2;
+        // shape fields sc (B Delta_v + sum_q w_q C_q) (AvatarOptimizer.cpp:568-580)
 #pragma unroll
-            for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
-                if (q < n) {
-                    const double* Cq = C + (size_t)jk[q] * 3 * K;
-                    e0 += wk[q] * Cq[mm];
-                    e1 += wk[q] * Cq[K + mm];
-                    e2 += wk[q] * Cq[2 * K + mm];
+        for (int i = 0; 2 * i < (KT > 0 ? KT : K); ++i) {
+            const int m = 2 * i + h;
+            if (m < K) {
+                float d0, d1, d2;
+                if (KT > 0) {
+                    const int e1 = 2 * i + 1 < KT ? 2 * i + 1 : 2 * i;
+                    d0 = h ? sdr[e1] : sdr[2 * i];
+                    d1 = h ? sdr[KT + e1] : sdr[KT + 2 * i];
+                    d2 = h ? sdr[2 * KT + e1] : sdr[2 * KT + 2 * i];
+                } else {
+                    d0 = sd[m]; d1 = sd[K + m]; d2 = sd[2 * K + m];
                 }
+                float e0 = Bf[0] * d0 + Bf[1] * d1 + Bf[2] * d2;
+                float e1 = Bf[3] * d0 + Bf[4] * d1 + Bf[5] * d2;
+                float e2 = Bf[6] * d0 + Bf[7] * d1 + Bf[8] * d2;
+#pragma unroll
+                for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
+                    const float* Cq = S.Cf + jk[q] * 3 * K;   // wf == 0 for q >= n (jk == 0: a valid table row)
+                    e0 = fmaf(wf[q], Cq[m], e0);
+                    e1 = fmaf(wf[q], Cq[K + m], e1);
+                    e2 = fmaf(wf[q], Cq[2 * K + m], e2);
+                }
+                tc_store(tkb, kc, S0 + m, scf * e0);
+                tc_store(tkb, kc, S0 + K + m, scf * e1);
+                tc_store(tkb, kc, S0 + 2 * K + m, scf * e2);
             }
-            e0 *= sc; e1 *= sc; e2 *= sc;   // sc == 0 for an unused slot: zero fields, zero gradient
-            if (act) {
-                tc_store_terms(S.tile, tc_off(S0 + m, kb), e0);
-                tc_store_terms(S.tile, tc_off(S0 + K + m, kb), e1);
-                tc_store_terms(S.tile, tc_off(S0 + 2 * K + m, kb), e2);
-            }
-            const double gs = half_sum(e0 * rho[0] + e1 * rho[1] + e2 * rho[2]);
-            if (lead && act) gw[3 + 3 * nj + m] += gs;
         }
         // ---- tensor cores: D += sum over term pairs of T_ta T_tb^T over this sub-tile's vertices ----
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy tile writes -> tensor-core reads
@@ -886,8 +995,9 @@ __device__ void fused_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;");
             const int N = (nf + 15) & ~15;
+            // instruction descriptor: D = F32, A = B = BF16, K-major both, N >> 3 at [17,23), M >> 4 at [24,29)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const int ksteps = (min(kTcSub, count - sub * kTcSub) + 15) >> 4;   // vertices past the chunk hold zeros up to a multiple of 16
+            const int ksteps = (min(kTcSub, count - sub * kTcSub) + 15) >> 4;   // unused slots hold zeros (sc = 0) up to a multiple of 16
             const uint32_t base = smem_u32_lm(S.tile);
             uint32_t accum = sub > 0 ? 1u : 0u;
 #pragma unroll 1
@@ -935,14 +1045,26 @@ __device__ void fused_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
-    if (tid < Lg) {   // gradient: warp partials in warp order
-        double s = 0;
+    double* part = a.part + ((size_t)f * a.maxc + c) * a.pstride;
+    {   // gradient accumulators behind the J^T J triangle: P | R | M | T
+        double* ga = part + tri_count(Lg);
+        const int GA = tc_gacc(J, K);
+        for (int i = tid; i < GA; i += 256) {
+            double val;
+            if (i < 3 || i >= 3 + 6 * J) {
+                const int e = i < 3 ? i : 3 + (i - 3 - 6 * J);
+                val = 0;
 #pragma unroll
-        for (int w8 = 0; w8 < 8; ++w8) s += S.gsm[w8 * kTcGcols + tid];
-        S.gvec[tid] = s;
+                for (int w8 = 0; w8 < 8; ++w8) val += S.gsm[w8 * kTcGw + e];   // warp partials in warp order
+            } else {
+                const int e = i - 3, k = e < 3 * J ? e / 3 : (e - 3 * J) / 3, cc = e % 3;
+                val = (double)(long long)S.acc[6 * k + (e < 3 * J ? cc : 3 + cc)] * kFixInv;
+            }
+            ga[i] = val;
+        }
     }
     __syncthreads();
-    emit_partial_tc(Gs, n, nj, K, S.gvec, a.part + ((size_t)f * a.maxc + c) * a.pstride, tid, 256);
+    emit_partial_tc(Gs, n, nj, K, part, tid, 256);
     phase_lap(a.q, 15, tp);
 }
 
@@ -1187,30 +1309,31 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         const int2 run = a.gruns[(size_t)f * kMaxGroups + g];
         if (run.y <= 0) continue;   // uniform
         const int nj = Pt.gnj[g], Lg = group_L(nj, K), nH = tri_count(Lg);
+        const int nE = nH + (a.tensor ? 0 : Lg);   // tensor path: the gradient is assembled from the moment accumulators below
         const int* gj = Pt.gjoints + g * kMaxJ;
         const double* part = a.part + ((size_t)f * a.maxc + run.x) * a.pstride;
         constexpr int kB = 8;   // independent loads in flight per thread
 #pragma unroll 1
-        for (int i0 = tid; i0 < nH + Lg; i0 += kSolveThreads * kB) {
+        for (int i0 = tid; i0 < nE; i0 += kSolveThreads * kB) {
             double val[kB];
 #pragma unroll
             for (int u = 0; u < kB; ++u) {
                 const int idx = i0 + u * kSolveThreads;
-                val[u] = (idx < nH + Lg) ? ldg2(part + idx) : 0.0;
+                val[u] = (idx < nE) ? ldg2(part + idx) : 0.0;
             }
 #pragma unroll 1
             for (int cc = 1; cc < run.y; ++cc) {   // further chunks of the group, in chunk order
 #pragma unroll
                 for (int u = 0; u < kB; ++u) {
                     const int idx = i0 + u * kSolveThreads;
-                    if (idx < nH + Lg) val[u] += ldg2(part + (size_t)cc * a.pstride + idx);
+                    if (idx < nE) val[u] += ldg2(part + (size_t)cc * a.pstride + idx);
                 }
             }
 #pragma unroll
             for (int u = 0; u < kB; ++u) {
                 const int idx = i0 + u * kSolveThreads;
                 int ra = idx - nH, rb = -1;
-                bool ok = idx < nH + Lg;
+                bool ok = idx < nE;
                 if (idx < nH) ok = tri_decode(idx, Lg, ra, rb);
                 if (ok) {
                     // group column -> tangent column: [ p | 3 per group joint | shape ]
@@ -1242,6 +1365,52 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
     }
     double cost_t = 0.5 * (csum + st.Qsum);
     __syncthreads();
+    if (a.tensor && !last) {
+        // ---- J^T r from the moment accumulators of the fused tasks (see fused_body), chunks added in chunk order:
+        //      g_p = P,  g_j = 2 sum_{k in subtree(j)} (M_k - (pos_j - o) x R_k),  g_shape,m = T_m + sum_k C_k[:,m] . R_k ----
+        const int GA = tc_gacc(J, K);
+        double* ga = S.tb + 9 * J;          // behind the joint rotations G (table scratch)
+        double* posj = ga + ((GA + 1) & ~1);
+        double* Ctab = posj + 3 * J;
+#pragma unroll 1
+        for (int i = tid; i < GA; i += kSolveThreads) {
+            double sacc = 0.0;
+#pragma unroll 1
+            for (int cc = 0; cc < st.nchunks; ++cc) {
+                const int gc = a.chunks[(size_t)f * a.maxc + cc].x;
+                sacc += ldg2(a.part + ((size_t)f * a.maxc + cc) * a.pstride + tri_count(group_L(Pt.gnj[gc], K)) + i);
+            }
+            ga[i] = sacc;
+        }
+#pragma unroll 1
+        for (int i = tid; i < 3 * J; i += kSolveThreads) posj[i] = ldg2(a.tab + (size_t)f * a.tabD + 9 * J + i);
+#pragma unroll 1
+        for (int i = tid; i < 3 * J * K; i += kSolveThreads) Ctab[i] = ldg2(a.tab + (size_t)f * a.tabD + 15 * J + i);
+        __syncthreads();
+        const double* Rk = ga + 3;
+        const double* Mk = ga + 3 + 3 * J;
+#pragma unroll 1
+        for (int i = tid; i < 3; i += kSolveThreads) S.gs[i] = ga[i];
+#pragma unroll 1
+        for (int i = tid; i < 3 * J; i += kSolveThreads) {
+            const int j = i / 3, cc = i - 3 * j, c1 = (cc + 1) % 3, c2 = (cc + 2) % 3;
+            const double pj1 = posj[3 * j + c1] - posj[c1], pj2 = posj[3 * j + c2] - posj[c2];   // o = root position
+            double sacc = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < J; ++k)
+                if ((M.anc_mask[k] >> j) & 1u) sacc += Mk[3 * k + cc] - (pj1 * Rk[3 * k + c2] - pj2 * Rk[3 * k + c1]);
+            S.gs[3 + i] = 2.0 * sacc;
+        }
+#pragma unroll 1
+        for (int m = tid; m < K; m += kSolveThreads) {
+            double sacc = ga[3 + 6 * J + m];
+#pragma unroll 1
+            for (int k = 0; k < J; ++k)
+                sacc += Ctab[(3 * k) * K + m] * Rk[3 * k] + Ctab[(3 * k + 1) * K + m] * Rk[3 * k + 1] + Ctab[(3 * k + 2) * K + m] * Rk[3 * k + 2];
+            S.gs[3 + 3 * J + m] = sacc;
+        }
+        __syncthreads();
+    }
     phase_lap(a.q, 5, tp);
     // ---- eta -> delta coordinates: H = T^T Ht T, g = T^T gt, T_j = G_parent(j) at the trial point ----
     if (!last) {
@@ -1635,7 +1804,10 @@ lm_flow_kernel(DevModel M, DevParts Pt, LmBuf a) {
         const int type = (int)((unsigned)task >> 30), f = (task >> 12) & 0x3FFFF, idx = task & 0xFFF;
         if (TC) {
             const bool cost_only = ldg2(&a.state[f].last) != 0;
-            fused_body(M, Pt, a, f, idx, cost_only, smem_raw, tmem_d, &s_mbar, mma_phase);
+            if (M.K == 10)
+                fused_body<10>(M, Pt, a, f, idx, cost_only, smem_raw, tmem_d, &s_mbar, mma_phase);
+            else
+                fused_body<0>(M, Pt, a, f, idx, cost_only, smem_raw, tmem_d, &s_mbar, mma_phase);
             __threadfence();
             __syncthreads();
             if (tid == 0) {
@@ -1768,12 +1940,12 @@ cudaError_t launch_lm_flow(const DevModel& M, const DevParts& Pt, const LmBuf& a
     return cudaGetLastError();
 }
 // the tensor path needs every column group to fit the tile (record fields) and the gradient scratch (columns)
-bool lm_tensor_supported(int max_nj, int K) { return tc_fields(max_nj, K) <= kTcRows && group_L(max_nj, K) <= kTcGcols; }
+bool lm_tensor_supported(int max_nj, int K) { return tc_fields(max_nj, K) <= kTcRows; }
 int lm_flow_ctas_per_sm(bool tensor) { return tensor ? kFlowMinCtasTc : 2; }
 
-long long lm_part_stride(int max_nj, int K) {
-    const int Lg = group_L(max_nj, K);
-    return (long long)((tri_count(Lg) + Lg + 1) & ~1);
+long long lm_part_stride(int max_nj, int J, int K) {   // [ J^T J triangle | J^T r (fp64 path) or P | R | M | T (tensor path) ]
+    const int Lg = group_L(max_nj, K), ga = tc_gacc(J, K);
+    return (long long)((tri_count(Lg) + (Lg > ga ? Lg : ga) + 1) & ~1);
 }
 int lm_tab_doubles(int J, int K) { return tab_doubles(J, K); }
 int lm_rec_floats(int max_nj, int K) { return rec_floats(max_nj, K); }

@@ -192,9 +192,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=512, help="frames per GPU per step")
-    ap.add_argument("--jtj", default="tensor", choices=["tensor", "fp64"],
-                    help="J^T J path: tensor (default: split-bf16 tcgen05 with fp32 TMEM accumulation; J^T r and cost in fp64) "
-                         "or fp64 (DMMA Gram of fp32 records)")
+    ap.add_argument("--jtj", default="fp64", choices=["fp64", "tensor"],
+                    help="J^T J path: fp64 (default, parity path: DMMA Gram of fp32 records) or tensor (split-bf16 tcgen05 with "
+                         "fp32 TMEM accumulation, J^T r and cost in fp64; not a parity path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("AVB_LANES", "3")),
