@@ -45,6 +45,23 @@ def make_model():
     return AvatarModel(npz_path=os.path.join(GOLD, "model_synth.npz"), pose_prior=g), pr
 
 
+def make_host_model():
+    """plain-numpy model view for the fixture generators: the reference arm must not map the product library"""
+    from harness import synth
+    pr = np.load(os.path.join(GOLD, "prior_synth.npz"))
+    return synth.HostModel(os.path.join(GOLD, "model_synth.npz"), pr), pr
+
+
+def load_fp64_peak():
+    """measured fp64 peaks of this pool's B200 (tools/ubench/fp64_peak.cu, committed as profiles/r2_fp64_peak.json)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_fp64_peak.json")) as fh:
+            p = json.load(fh)
+        return float(p["dmma_tflops"]), float(p["dfma_tflops"]), "measured (profiles/r2_fp64_peak.json)"
+    except Exception:
+        return 37.0, 34.0, "fallback"
+
+
 def gen_params(model, seeds):
     from harness import synth
     xg, x0 = [], []
@@ -156,7 +173,7 @@ def run_reference(args, rank, world):
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as orc
-    model, pr = make_model()
+    model, pr = make_host_model()      # no avatar_b200 import anywhere in this arm: only oracle/ and harness/ are mapped
     om = orc.OracleModel(os.path.join(GOLD, "model_synth.npz"), pr)
     oo = orc.OracleOptimizer(om, int(pr["num_parts"]), pr["part_map"])
     cores = os.cpu_count() or 1
@@ -175,7 +192,8 @@ def run_reference(args, rank, world):
               "(icp_iters=1, maxItersPerICP=10, function_tolerance=1e-4)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "same_config_note": "frames/s is per frame: the CPU arm times a bounded sample of the same synthetic frames",
             "config": {"workload": "512-frame synthetic batch per GPU, 640x576 smplsynth-style clouds, "
                                    "icp_iters=1, 10 solver iterations", "frames_per_step_sample": nsample,
                        "mean_points_per_frame": float(np.mean(np.diff(off)))},
@@ -195,6 +213,9 @@ def main():
     ap.add_argument("--jtj", default="fp64", choices=["fp64", "tensor"],
                     help="J^T J path: fp64 (default, parity path: DMMA Gram of fp32 records) or tensor (split-bf16 tcgen05 with "
                          "fp32 TMEM accumulation, J^T r and cost in fp64; not a parity path)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --frames per GPU (default); strong: --frames in total, sharded over the ranks (BASELINE.json configs[2])")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity sample printed on the line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("AVB_LANES", "3")),
@@ -215,11 +236,19 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     model, pr = make_model()
     part_map, num_parts = pr["part_map"], int(pr["num_parts"])
-    F = args.frames
     nx = 3 + 4 * model.numJoints() + model.numShapeKeys()
 
-    # ---- synthetic frames of this rank (weak scaling: distinct seeds per rank) ----
-    xg, x0 = gen_params(model, range(rank * F, (rank + 1) * F))
+    # ---- synthetic frames of this rank.  weak: every rank fits its own --frames frames (seeds rank*F ..);
+    #      strong: the SAME --frames frames (seeds 0 ..) are sharded as contiguous blocks over the ranks ----
+    if args.scaling == "strong":
+        f_lo, f_hi = shard.frame_range(args.frames, rank, world)
+        F_total = args.frames
+    else:
+        f_lo, f_hi = rank * args.frames, (rank + 1) * args.frames
+        F_total = args.frames * world
+    F = f_hi - f_lo
+    F_max = shard.frame_range(args.frames, 0, world)[1] if args.scaling == "strong" else args.frames   # largest shard
+    xg, x0 = gen_params(model, range(f_lo, f_hi))
     pose_ft = Fitter(model, num_parts, part_map, F, 16, local_rank)
     clouds_gt, _, _ = pose_ft.avatar_update(xg)
     pose_ft.close()
@@ -273,7 +302,7 @@ def main():
     for ln in lanes:
         stats += ln["ft"].download()[1]
     dev_ms = shard.max_over_ranks(dev_ms, dev)
-    value = F * world * args.steps / (dev_ms * 1e-3)
+    value = F_total * args.steps / (dev_ms * 1e-3)
 
     # ---- e2e: host buffers in, parameters out, through the public batch call ----
     # Every lane (fitter + stream) is driven by its own host thread that calls avb_fit_batch step after step, so one
@@ -295,10 +324,12 @@ def main():
         full = None
         for _ in range(nsteps):
             x = np.concatenate([q.get() for q in qs])
-            full = shard.gather_params(x, F * world, rank, world, dev) if world > 1 else x
+            full = gatherer.gather(x) if world > 1 else x
         for t in ths:
             t.join()
         return full
+    gatherer = shard.ParamGatherer(F_max, nx, rank, world, dev, [shard.frame_range(args.frames, r, world) if args.scaling == "strong"
+                                                                  else (r * args.frames, (r + 1) * args.frames) for r in range(world)])
     e2e_run(1)
     barrier()
     t2 = time.perf_counter()
@@ -306,7 +337,7 @@ def main():
     barrier()
     t3 = time.perf_counter()
     e2e_s = shard.max_over_ranks(t3 - t2, dev)
-    e2e_value = F * world * args.steps / e2e_s
+    e2e_value = F_total * args.steps / e2e_s
     clocks = sampler.stop(t0, t3) if sampler else None
     h2d = total * 24 + total * 4 + F * nx * 8 + (F + 1) * 8
     d2h = F * nx * 8 + F * 40
@@ -335,63 +366,91 @@ def main():
                 phase_ms[k] = phase_ms.get(k, 0.0) + ms
         ln["ft"].set_profiling(False)
     dom = max(kms, key=kms.get)
-    V, K = model.numPoints(), model.numShapeKeys()
+    V, K, J = model.numPoints(), model.numShapeKeys(), model.numJoints()
+    P = 3 + 3 * J + K
     evals = float(np.mean(iters)) + 1.0
-    nm, nvis = float(np.sum(nmatch)), 0.5 * V * F
-    groups = lanes[0]["ft"].groups()
-    gv = float(sum(v for _, v in groups))
-    nj_mean = sum(j * v for j, v in groups) / gv        # joints per record, weighted by the groups' vertex counts
-    rec_b = 4.0 * (3 * nj_mean + 3 * K + 7)             # mean fp32 Jacobian record
-    Lg = 3 + 3 * nj_mean + K
-    part_b = 8.0 * (Lg * (Lg + 1) / 2 + Lg)             # chunk partial: upper triangle of J^T J + J^T r
-    chunks = nm / 256.0 + 0.5 * len(groups) * F         # chunks per evaluation (256 slots, one ragged chunk per group)
-    full = evals - 1.0                                   # the last evaluation is cost-only: no records, no Gram, no H
-    rows_b = nm * (evals * (4 + 24 + 24 + 12 * K + 37 + 2) + full * rec_b)
-    gram_b = full * (nm * rec_b + chunks * part_b)
-    solve_b = full * (chunks * part_b + F * 3 * 8.0 * 85 * 85)
-    alg_step = {                                         # algorithmic bytes per STEP of each kernel class
-        "pose_visibility_kernel": F * (24.0 * V + V + 4 * V) + 24.0 * nvis,
-        "nn_kernel": 32.0 * total + 24.0 * nvis,
-        "lm_prep_kernel": F * (4.0 * V + 2.0 * V + 8 * 1080),
-        "lm_rows_kernel": rows_b,
-        "lm_gram_kernel": gram_b,
-        "lm_solve_kernel": solve_b,
-        "lm_flow_kernel": rows_b + gram_b + solve_b,
-        "pose_visibility_kernel(final)": F * 24.0 * V,
+    inner = float(np.mean(iters))                        # solver iterations actually run (10 with function_tolerance = 0)
+    nm = float(np.sum(nmatch))
+    # ---- ALGORITHMIC bytes, SURVEY.md section 8(d) (fp32 device storage, per frame):
+    #        per ICP iteration (pose + visibility + NN): write cloud 12 V, read data 12 N + labels 4 N, write index 4 N = 20 N + 12 V
+    #        per inner iteration (the solve):            read data 12 N + index 4 N, write J^T J + J^T r 4 P^2 + 4 P = 16 N + 29 240
+    #        final forward pass:                          write cloud 12 V
+    #      These are the contract's bytes, NOT this design's traffic (which is lower: the inner loop touches matched vertices,
+    #      not points); `traffic` is the measured DRAM traffic of the same kernel. ----
+    n_pts = float(total)
+    alg_inner_frame = 16.0 * n_pts / F + 4.0 * P * P + 4.0 * P            # per frame per inner iteration (mean N)
+    alg_step = {
+        "pose_visibility_kernel": F * 12.0 * V,
+        "nn_kernel": 20.0 * n_pts,
+        "lm_prep_kernel": 0.0,
+        "lm_rows_kernel": inner * F * alg_inner_frame * 0.5,
+        "lm_gram_kernel": inner * F * alg_inner_frame * 0.5,
+        "lm_solve_kernel": 0.0,
+        "lm_flow_kernel": inner * F * alg_inner_frame,
+        "pose_visibility_kernel(final)": F * 12.0 * V,
     }
+    alg_step_total = 20.0 * n_pts + inner * F * alg_inner_frame + 2 * F * 12.0 * V     # = 180 N + 0.91 MB per frame at 10 iterations
     peak, how = load_peaks()
     dom_launches = max(klaunch[dom], 1)
     avg_launch_ms = kms[dom] / dom_launches
     achieved = alg_step[dom] / dom_launches / (avg_launch_ms * 1e-3) / 1e9
     traffic = None
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-        tag = dom.split("_kernel")[0].replace("lm_", "")
-        with open(os.path.join(ROOT, "profiles", f"r1_ncu_{tag}_kernel_raw.csv")) as fh:
+    traffic_src = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this kernel
+        tag = {"fp64": "r2_ncu_flow_fp64_raw.csv", "tensor": "r2_ncu_flow_tensor_raw.csv"}[args.jtj] if dom == "lm_flow_kernel" else \
+            "r1_ncu_%s_kernel_raw.csv" % dom.split("_kernel")[0].replace("lm_", "")
+        with open(os.path.join(ROOT, "profiles", tag)) as fh:
             vals = {r.split(",")[0]: r.strip().split(",") for r in fh}
         mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         traffic = sum(float(vals[k][2]) * mult[vals[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        traffic_src = "profiles/" + tag
     except Exception:
         traffic = None
     tot_ms = sum(kms.values())
+    alg_per_launch = alg_step[dom] / dom_launches
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": how,
+                "algorithmic_bytes_per_launch": alg_per_launch,
+                "traffic_over_algorithmic": (traffic / alg_per_launch) if traffic else None, "traffic_source": traffic_src,
+                "algorithmic_bytes": "SURVEY 8(d): inner solve = iterations x frames x (16 N + 4 P^2 + 4 P) B; whole step = 180 N + 0.91 MB per frame",
+                "step": {"algorithmic_bytes": alg_step_total, "achieved": alg_step_total / (dev_ms / args.steps * 1e-3) / 1e9,
+                         "frac": alg_step_total / (dev_ms / args.steps * 1e-3) / 1e9 / peak},
                 "avg_launch_ms": avg_launch_ms, "launches_per_step": dom_launches,
                 "kernel_ms_per_step": {k: round(v, 4) for k, v in kms.items()},
                 "kernel_share": {k: round(v / tot_ms, 4) for k, v in kms.items()},
-                "note": "the dominant kernel is fp64-pipe / latency bound (DMMA Gram tasks, fp64 record generation and "
-                        "85x85 solves; ncu: DRAM < 2% of peak), not HBM bound: the HBM fraction is reported as required "
-                        "and is not the limiter (DESIGN.md section 5)"}
+                "note": "the inner solve is NOT HBM bound: it is an fp64 / latency problem on ~1.45 k matched vertices per frame that "
+                        "stay in L2 (DESIGN.md section 5); the HBM fraction is the contract's number, the fp64 roofline below is the "
+                        "one that bounds the kernel"}
+    # ---- fp64 roofline of the dominant kernel: useful fp64 flops / measured DMMA / DFMA peak ----
+    dmma_pk, dfma_pk, pk_src = load_fp64_peak()
+    groups = lanes[0]["ft"].groups()
+    gv = float(sum(v for _, v in groups)) or 1.0
+    full_evals = inner                                     # evaluations that build J^T J (the last one is cost only)
+    nfield = [(3 * j + 3 * K + (1 if args.jtj == "tensor" else 7), v / gv) for j, v in groups]
+    gram_flops = 2.0 * full_evals * nm * sum(share * nf * (nf + 1) / 2 for nf, share in nfield)      # Gram of the records (upper triangle)
+    rec_flops = 2.0 * evals * nm * sum(share * (60 + 96 + 19 * j + 21 * K) for (j, v), share in zip(groups, [v / gv for _, v in groups]))
+    solve_flops = 2.0 * full_evals * F * (P ** 3 / 6.0 + 2 * P * P + max(model.posePrior.nComps, 0) * 69 * 69)
+    useful = gram_flops + rec_flops + solve_flops
+    flow_ms_step = kms.get("lm_flow_kernel", kms[dom])
+    roofline_fp64 = {"kernel": dom, "useful_fp64_gflop_per_step": useful / 1e9,
+                     "gram_gflop": gram_flops / 1e9, "records_gflop": rec_flops / 1e9, "solve_gflop": solve_flops / 1e9,
+                     "achieved_tflops": useful / (flow_ms_step * 1e-3) / 1e12, "peak_dmma_tflops": dmma_pk, "peak_dfma_tflops": dfma_pk,
+                     "frac_of_dmma_peak": useful / (flow_ms_step * 1e-3) / 1e12 / dmma_pk, "peak_source": pk_src,
+                     "note": "tensor path: the Gram flops run on tcgen05 (bf16), not on the fp64 pipe" if args.jtj == "tensor" else
+                             "fp64 path: the Gram runs on the fp64 tensor path (DMMA), records and solves on DFMA"}
     if flow_ms:
         tot_cta = sum(flow_ms.values()) or 1.0
         roofline["flow_task_share"] = {k: round(v / tot_cta, 4) for k, v in flow_ms.items()}
         roofline["flow_phase_share"] = {k: round(v / tot_cta, 4) for k, v in phase_ms.items()}
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": {"fp64": "f64", "tensor": "f64 (J^T J: split-bf16 tcgen05, f32 TMEM accumulate)"}[args.jtj],
             "data": "synthetic",
-            "config": {"workload": "512-frame synthetic batch per GPU (BASELINE.json configs[2]), 640x576 "
-                                   "smplsynth-style clouds, icp_iters=1, 10 LM iterations (function_tolerance=0)",
-                       "frames_per_gpu": F, "mean_points_per_frame": float(npts.mean()),
+            "config": {"workload": ("%d-frame synthetic batch per GPU" % args.frames if args.scaling == "weak" else
+                                    "%d-frame synthetic batch in total, sharded over the GPUs" % args.frames) +
+                                   " (BASELINE.json configs[2]), 640x576 smplsynth-style clouds, icp_iters=1, 10 LM iterations "
+                                   "(function_tolerance=0)",
+                       "frames_per_gpu": F, "frames_total": F_total, "mean_points_per_frame": float(npts.mean()),
                        "mean_matched_vertices": float(nmatch.mean()), "mean_lm_iterations": float(iters.mean()),
                        "mean_correspondences": float(ncorr.mean()), "solver": "gn_lm", "jtj": args.jtj,
                        "lanes": NL,
@@ -399,7 +458,68 @@ def main():
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_s / args.steps, "timer": "wall clock around the K steps (barrier + synchronize on both sides); lanes free-running"},
             "gpu_launches": int(launches_per_step * args.steps),
-            "clocks": clocks, "roofline": roofline, "wall_ms_per_step_resident": 1e3 * (t1 - t0) / args.steps}
+            "clocks": clocks, "roofline": roofline, "roofline_fp64": roofline_fp64,
+            "wall_ms_per_step_resident": 1e3 * (t1 - t0) / args.steps}
+    # ---- parity on the timed batch itself (outside the timed region): a sample of this rank's frames refitted by the CPU
+    #      oracle (gn_lm = the same algorithm in fp64; itself unpinned against Ceres), NN indices of the
+    #      sample against the oracle's exact search, and -- multi-GPU -- frames of ANOTHER rank refitted here bit for bit ----
+    if not args.no_parity:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import oracle as orc_p
+            om_p = orc_p.OracleModel(os.path.join(GOLD, "model_synth.npz"), pr)
+            oo_p = orc_p.OracleOptimizer(om_p, num_parts, part_map)
+            ns = min(16, F)
+            sample = [int(round(i * (F - 1) / max(ns - 1, 1))) for i in range(ns)]
+            oopt_p = orc_p.default_options(orc_p.SOLVER_GN_LM)
+            oopt_p.function_tolerance, oopt_p.num_threads = 0.0, 1
+            res_p = [None] * ns
+
+            def work_p(k):
+                for i in range(k, ns, 8):
+                    b = sample[i]
+                    res_p[i] = oo_p.optimize(pts[b], labs[b], x0[b], oopt_p)
+            ths = [threading.Thread(target=work_p, args=(k,)) for k in range(8)]
+            [t.start() for t in ths]
+            [t.join() for t in ths]
+            row0 = sum(hi - lo for lo, hi in gatherer.ranges[:rank])
+            x_mine = full[row0:row0 + F]
+            errs = [float(np.abs(x_mine[b] - res_p[i][0]).max()) for i, b in enumerate(sample)]
+            it_eq = all(stats[b].iterations == res_p[i][1].iterations and stats[b].accepted_steps == res_p[i][1].accepted_steps
+                        for i, b in enumerate(sample))
+            # NN: device search at the start point against the oracle's exact search on the device's own posed cloud
+            fp = Fitter(model, num_parts, part_map, ns, int(sum(len(pts[b]) for b in sample)) + 64, local_rank)
+            offp = np.cumsum([0] + [len(pts[b]) for b in sample]).astype(np.int64)
+            fp.upload(np.concatenate([pts[b] for b in sample]), np.concatenate([labs[b] for b in sample]), offp)
+            fp.debug_correspond(np.stack([x0[b] for b in sample]), opt)
+            nn_g = fp.debug_read(_lib.TAP_NN)
+            cl_g = fp.debug_read(_lib.TAP_CLOUD)
+            nn_bad = 0
+            for i, b in enumerate(sample[:4]):
+                nn_o = oo_p.find_nn(cl_g[i], oo_p.visibility(cl_g[i]), pts[b], labs[b], 1)
+                nn_bad += int((nn_o != nn_g[offp[i]:offp[i + 1]]).sum())
+            fp.close()
+            line["parity"] = {"oracle": "oracle gn_lm (fp64 CPU restatement, same LM as the device; unpinned against Ceres)",
+                              "frames_checked": ns, "max_param_err": max(errs), "median_param_err": float(np.median(errs)),
+                              "tolerance": 1e-4, "iterations_and_accepts_equal": bool(it_eq),
+                              "nn_mismatches": nn_bad, "nn_points_checked": int(offp[min(4, ns)]), "jtj": args.jtj}
+            if world > 1:   # frames of rank 1 refitted on this GPU == the gathered result of rank 1, bit for bit
+                lo1, hi1 = gatherer.ranges[1]
+                nchk = min(8, hi1 - lo1)
+                seeds1 = range(lo1, lo1 + nchk)
+                xg1, x01 = gen_params(model, seeds1)
+                f1c = Fitter(model, num_parts, part_map, nchk, 16, local_rank)
+                cg1, _, _ = f1c.avatar_update(xg1)
+                f1c.close()
+                p1, l1, o1 = render_frames(model, part_map, cg1)
+                f1b = Fitter(model, num_parts, part_map, nchk, int(o1[-1]) + 64, local_rank)
+                xr1, _, _ = f1b.fit_batch(np.concatenate(p1), np.concatenate(l1), o1, x01, opt)
+                f1b.close()
+                row1 = sum(hi - lo for lo, hi in gatherer.ranges[:1])
+                line["parity"]["nrank_equals_1rank"] = {"frames_checked": nchk, "bitwise_equal": bool(np.array_equal(xr1, full[row1:row1 + nchk])),
+                                                        "what": "frames of rank 1 refitted on rank 0 vs the NCCL-gathered parameters of rank 1"}
+        except Exception as exc:   # never take the headline down
+            line["parity"] = {"error": repr(exc)}
     # ---- secondary configs (BASELINE.json configs[1] and configs[3]), N=1 only: single-frame latency through
     #      avb_fit and a warm-started tracking sequence through avb_track_sequence ----
     if world == 1 and not args.no_extras:
