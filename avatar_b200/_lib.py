@@ -91,6 +91,7 @@ SYMBOLS = [
     ("avb_last_rtree_ms", C.c_int, [_P, _P]),
     ("avb_render_batch", C.c_int, [_P, C.c_int32, _P, C.POINTER(RenderDesc), _P, _P, _P]),
     ("avb_last_render_ms", C.c_int, [_P, _P]),
+    ("avb_render_lambert_batch", C.c_int, [_P, C.c_int32, _P, C.POINTER(RenderDesc), _P]),
     ("avb_download_results", C.c_int, [_P, _P, _P, _P]),
     ("avb_synchronize", C.c_int, [_P]),
     ("avb_last_device_ms", C.c_int, [_P, C.POINTER(C.c_float), _P]),

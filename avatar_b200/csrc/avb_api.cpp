@@ -122,6 +122,8 @@ struct avb_fitter {
     RTreeNode* d_rt_nodes = nullptr; uint8_t* d_rt_leaf = nullptr; int rt_nodes = 0, rt_leaves = 0, rt_parts = 0;
     const uint8_t* d_vpart = nullptr; float* d_proj = nullptr; int* d_order = nullptr; unsigned* d_win = nullptr;
     float* d_rdepth = nullptr; uint8_t* d_rparts = nullptr; int* d_rfaces = nullptr; size_t render_cap = 0;
+    const int *d_vf_start = nullptr, *d_vf_list = nullptr; int max_valence = 0;   // faces incident to every vertex (renderLambert)
+    int* d_rank_of = nullptr; float* d_vlam = nullptr; unsigned* d_win_l = nullptr; uint8_t* d_rlam = nullptr; size_t lam_cap = 0;
     cudaEvent_t nev[4] = {};   // around the three renderer kernels
     cudaEvent_t rev[2] = {};   // around the RTree kernels of the last prediction
     cudaEvent_t cev[4] = {};   // around cloud_count_kernel and cloud_compact_kernel of the last avb_upload_depth_batch
@@ -532,6 +534,7 @@ void avb_fitter_destroy(avb_fitter* ft) {
     for (auto& e : ft->rev) if (e) cudaEventDestroy(e);
     cudaFree(ft->d_rt_nodes); cudaFree(ft->d_rt_leaf);
     cudaFree(ft->d_win); cudaFree(ft->d_rdepth); cudaFree(ft->d_rparts); cudaFree(ft->d_rfaces); cudaFree(ft->d_proj); cudaFree(ft->d_order);
+    cudaFree(ft->d_rank_of); cudaFree(ft->d_vlam); cudaFree(ft->d_win_l); cudaFree(ft->d_rlam);
     for (auto& e : ft->nev) if (e) cudaEventDestroy(e);
     if (ft->copy_stream) cudaStreamDestroy(ft->copy_stream);
     if (ft->stream) cudaStreamDestroy(ft->stream);
@@ -646,6 +649,23 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
         std::vector<uint8_t> vpart((size_t)V);
         for (int v = 0; v < V; ++v) vpart[v] = (uint8_t)cfg->part_map[m->main_joint[v]];
         TRY(dev_put(ft, &ft->d_vpart, vpart));
+    }
+    {   // faces incident to every vertex (CSR, each face once per vertex, ascending): renderLambert's vertex normals
+        std::vector<int> vs((size_t)V + 1, 0), vl;
+        std::vector<std::vector<int>> inc((size_t)V);
+        for (int t = 0; t < m->F; ++t)
+            for (int c = 0; c < 3; ++c) {
+                auto& l = inc[m->faces[3 * (size_t)t + c]];
+                if (l.empty() || l.back() != t) l.push_back(t);
+            }
+        for (int v = 0; v < V; ++v) {
+            vs[v] = (int)vl.size();
+            vl.insert(vl.end(), inc[v].begin(), inc[v].end());
+            ft->max_valence = std::max(ft->max_valence, (int)inc[v].size());
+        }
+        vs[V] = (int)vl.size();
+        TRY(dev_put(ft, &ft->d_vf_start, vs));
+        TRY(dev_put(ft, &ft->d_vf_list, vl));
     }
     TRY(dev_put(ft, &dp.part_start, part_start));
     TRY(dev_put(ft, &dp.part_verts, part_verts));
@@ -1469,6 +1489,61 @@ int avb_render_batch(avb_fitter* ft, int32_t batch, const double* x, const avb_r
     if (depth_out) CUDA_TRY(cudaMemcpyAsync(depth_out, ft->d_rdepth, npx * 4, cudaMemcpyDeviceToHost, st));
     if (parts_out) CUDA_TRY(cudaMemcpyAsync(parts_out, ft->d_rparts, npx, cudaMemcpyDeviceToHost, st));
     if (faces_out) CUDA_TRY(cudaMemcpyAsync(faces_out, ft->d_rfaces, npx * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return AVB_OK;
+}
+
+/* AvatarRenderer::renderLambert (AvatarRenderer.cpp:103-172) for a batch of parameter vectors */
+int avb_render_lambert_batch(avb_fitter* ft, int32_t batch, const double* x, const avb_render_desc* d, uint8_t* gray_out) {
+    if (!ft || !x || !d || !gray_out || batch <= 0) return fail(AVB_ERR_INVALID, "null argument or empty batch");
+    if (batch > ft->max_batch) return fail(AVB_ERR_CAPACITY, "batch exceeds fitter capacity");
+    if (d->width <= 0 || d->height <= 0 || (size_t)d->width * d->height >= ((size_t)1 << 31)) return fail(AVB_ERR_INVALID, "bad image size");
+    if (ft->model->F > render_max_faces()) return fail(AVB_ERR_CAPACITY, "the renderer sorts at most 16384 faces per frame");
+    if (ft->model->F <= 0) return fail(AVB_ERR_INVALID, "the model has no mesh (hasMesh == false): nothing to render");
+    if (ft->max_valence > render_max_valence()) return fail(AVB_ERR_CAPACITY, "renderLambert handles at most 32 faces per vertex");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    cudaStream_t st = ft->stream;
+    const size_t nx = ft->model->nx, V = ft->model->V, F = ft->model->F;
+    const size_t px = (size_t)d->width * d->height, npx = px * batch;
+    if (npx > ft->lam_cap) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(ft->d_win_l); cudaFree(ft->d_rlam);
+        ft->d_win_l = nullptr; ft->d_rlam = nullptr; ft->lam_cap = 0;
+        if (cudaMalloc(&ft->d_win_l, npx * 4) != cudaSuccess || cudaMalloc(&ft->d_rlam, npx) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(AVB_ERR_CUDA, "cudaMalloc of the render buffers failed");
+        }
+        ft->lam_cap = npx;
+    }
+    if (!ft->d_proj) {
+        CUDA_TRY(cudaMalloc(&ft->d_proj, (size_t)ft->max_batch * V * 8));
+        CUDA_TRY(cudaMalloc(&ft->d_order, (size_t)ft->max_batch * F * 4));
+        for (auto& e : ft->nev) CUDA_TRY(cudaEventCreate(&e));
+    }
+    if (!ft->d_rank_of) {
+        CUDA_TRY(cudaMalloc(&ft->d_rank_of, (size_t)ft->max_batch * F * 4));
+        CUDA_TRY(cudaMalloc(&ft->d_vlam, (size_t)ft->max_batch * V * 4));
+    }
+    CUDA_TRY(cudaMemcpyAsync(ft->d_xdbg, x, (size_t)batch * nx * 8, cudaMemcpyHostToDevice, st));
+    PoseArgs pa = pose_args(ft, ft->d_xdbg, false, nullptr);
+    CUDA_TRY(launch_pose_visibility(ft->dm, ft->dp, pa, batch, st));
+    CUDA_TRY(cudaMemsetAsync(ft->d_win_l, 0, npx * 4, st));
+    RenderArgs a{};
+    a.cloud = ft->d_cloud;
+    a.faces = ft->dm.faces;
+    a.vpart = ft->d_vpart;
+    a.proj = ft->d_proj;
+    a.order = ft->d_order;
+    a.V = (int)V; a.F = (int)F; a.width = d->width; a.height = d->height;
+    a.fx = d->fx; a.cx = d->cx; a.fy = d->fy; a.cy = d->cy;
+    a.vf_start = ft->d_vf_start;
+    a.vf_list = ft->d_vf_list;
+    a.rank_of = ft->d_rank_of;
+    a.vlam = ft->d_vlam;
+    a.win_lambert = ft->d_win_l;
+    a.lambert_out = ft->d_rlam;
+    CUDA_TRY(launch_render_lambert(a, batch, st));
+    CUDA_TRY(cudaMemcpyAsync(gray_out, ft->d_rlam, npx, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return AVB_OK;
 }

@@ -81,6 +81,13 @@ struct RenderArgs {   // AvatarRenderer on the device (avb_render.cu)
     int* faces_out;
     int V, F, width, height;
     float fx, cx, fy, cy;
+    // renderLambert (AvatarRenderer.cpp:103-172)
+    const int* vf_start;         // [V+1] CSR of the faces incident to every vertex
+    const int* vf_list;          // [3F]
+    int* rank_of;                // nullable [batch][F] scratch: paint position of every model face
+    float* vlam;                 // [batch][V] scratch: the value painted at every vertex
+    unsigned* win_lambert;       // [batch][H][W] scratch, zeroed by the caller
+    uint8_t* lambert_out;        // [batch][H][W]
 };
 
 struct LmState {  // per-frame Levenberg-Marquardt state, lives in HBM between the kernels of one ICP iteration
@@ -137,6 +144,8 @@ cudaError_t launch_rtree_predict(const RTreeArgs& a, int batch, int max_box_pixe
 cudaError_t launch_rtree_upscale(const RTreeArgs& a, int batch, int max_box_pixels, cudaStream_t st);
 int render_max_faces();
 cudaError_t launch_render(const RenderArgs& a, int batch, cudaStream_t st, cudaEvent_t* ev4);
+int render_max_valence();
+cudaError_t launch_render_lambert(const RenderArgs& a, int batch, cudaStream_t st);
 int cloud_strip_rows();
 cudaError_t launch_cloud_count(const CloudArgs& a, int strips, int batch, cudaStream_t st);
 cudaError_t launch_cloud_compact(const CloudArgs& a, int strips, int batch, cudaStream_t st);

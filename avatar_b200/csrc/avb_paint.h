@@ -248,6 +248,40 @@ AVB_HD double face_zcross(const double a[3], const double b[3], const double c[3
     return fabs(zn);
 }
 
+// unit face normal (b - a) x (c - a), Eigen normalized() (AvatarRenderer.cpp:127); every operation rounded once
+AVB_HD void face_unit_normal(const double a[3], const double b[3], const double c[3], double n[3]) {
+    const double ab[3] = {dsub(b[0], a[0]), dsub(b[1], a[1]), dsub(b[2], a[2])};
+    const double ac[3] = {dsub(c[0], a[0]), dsub(c[1], a[1]), dsub(c[2], a[2])};
+    n[0] = dsub(dmul(ab[1], ac[2]), dmul(ab[2], ac[1]));
+    n[1] = dsub(dmul(ab[2], ac[0]), dmul(ab[0], ac[2]));
+    n[2] = dsub(dmul(ab[0], ac[1]), dmul(ab[1], ac[0]));
+    const double n2 = dadd(dadd(dmul(n[0], n[0]), dmul(n[1], n[1])), dmul(n[2], n[2]));
+    if (n2 > 0.0) {
+        const double r = sqrt(n2);
+        n[0] = ddiv(n[0], r); n[1] = ddiv(n[1], r); n[2] = ddiv(n[2], r);
+    }
+}
+AVB_HD void normalize3(double v[3]) {
+    const double n2 = dadd(dadd(dmul(v[0], v[0]), dmul(v[1], v[1])), dmul(v[2], v[2]));
+    if (n2 > 0.0) {
+        const double r = sqrt(n2);
+        v[0] = ddiv(v[0], r); v[1] = ddiv(v[1], r); v[2] = ddiv(v[2], r);
+    }
+}
+// the value renderLambert paints at a vertex (AvatarRenderer.cpp:111-115, 137-163): nsum = the vertex's normal sum
+AVB_HD float vertex_lambert(const double pos[3], double nsum[3]) {
+    normalize3(nsum);
+    if (nsum[2] > 0) { nsum[0] = -nsum[0]; nsum[1] = -nsum[1]; nsum[2] = -nsum[2]; }
+    double ml[3] = {dsub(0.8, pos[0]), dsub(1.5, pos[1]), dsub(-1.2, pos[2])};
+    double bl[3] = {dsub(-0.2, pos[0]), dsub(-1.5, pos[1]), dsub(0.4, pos[2])};
+    normalize3(ml);
+    normalize3(bl);
+    const double dm = dadd(dadd(dmul(ml[0], nsum[0]), dmul(ml[1], nsum[1])), dmul(ml[2], nsum[2]));
+    const double db = dadd(dadd(dmul(bl[0], nsum[0]), dmul(bl[1], nsum[1])), dmul(bl[2], nsum[2]));
+    const float v = fmul((float)dadd(dmul(dm, 0.8), dmul(db, 0.2)), 255.f);
+    return v > 0.f ? v : 0.f;
+}
+
 // ---- the renderer in rank form ----------------------------------------------------------------------------------------
 struct RenderView {
     const double* cloud;       // [V][3] posed model
@@ -307,6 +341,28 @@ AVB_HD uint8_t resolve_parts(const RenderView& v, const int32_t* order, unsigned
     return v.vpart[f[nearest_parts(p, i, j)]];
 }
 AVB_HD int32_t resolve_faces(unsigned rank) { return rank == 0 ? -1 : (int32_t)rank - 1; }
+
+// renderLambert (AvatarRenderer.cpp:103-172): faces with |n_z| <= 1e-2 are not painted, the others with
+// paintTriangleBary<uint8_t> and the three vertex values
+template <class MaxOp>
+AVB_HD void face_cover_lambert(const RenderView& v, int face, unsigned rank, unsigned* win, MaxOp amax) {
+    P2 p[3];
+    double zc;
+    face_points(v, face, p, &zc);
+    if (!(zc > 1e-2)) return;
+    const int W = v.W, H = v.H;
+    spans_bary(p, W, H, [&](int i, int lo, int hi) { for (int j = lo; j <= hi; ++j) amax(win + (size_t)i * W + j, rank); });
+}
+AVB_HD uint8_t resolve_lambert(const RenderView& v, const int32_t* order, const float* vlam, unsigned rank, int i, int j) {
+    if (rank == 0) return 0;
+    P2 p[3];
+    double zc;
+    const int face = order[rank - 1];
+    face_points(v, face, p, &zc);
+    const int32_t* f = v.faces + 3 * (size_t)face;
+    const float lv[3] = {vlam[f[0]], vlam[f[1]], vlam[f[2]]};
+    return (uint8_t)value_bary(p, lv, i, j, 255.0f);
+}
 
 }  // namespace paint
 }  // namespace avb

@@ -53,7 +53,11 @@ render_prepare_kernel(RenderArgs a) {
             __syncthreads();
         }
     int* order = a.order + (size_t)f * a.F;
-    for (int i = tid; i < a.F; i += kPrepThreads) order[i] = (int)(keys[i] & 0xFFFFFFFFull);
+    for (int i = tid; i < a.F; i += kPrepThreads) {
+        const int face = (int)(keys[i] & 0xFFFFFFFFull);
+        order[i] = face;
+        if (a.rank_of) a.rank_of[(size_t)f * a.F + face] = i;
+    }
 }
 
 __device__ __forceinline__ RenderView view_of(const RenderArgs& a, int f) {
@@ -90,6 +94,78 @@ render_resolve_kernel(RenderArgs a) {
     if (a.depth_out) a.depth_out[f * px + p] = resolve_depth(v, order, a.win_depth[f * px + p], i, j);
     if (a.parts_out) a.parts_out[f * px + p] = resolve_parts(v, order, a.win_parts[f * px + p], i, j);
     if (a.faces_out) a.faces_out[f * px + p] = resolve_faces(a.win_faces[f * px + p]);
+}
+
+// ---- renderLambert (AvatarRenderer.cpp:103-172) ----
+// The reference adds the unit normal of every face to its three vertices while it walks the faces in PAINT order, so the
+// floating-point sum at a vertex depends on the frame's face order.  One thread per vertex: gather the incident faces
+// (static CSR), order them by the frame's paint position, add their normals in that order, normalise, flip towards the
+// camera, light (paint::vertex_lambert).
+constexpr int kMaxValence = 32;
+
+__global__ void __launch_bounds__(128)
+render_vertex_lambert_kernel(RenderArgs a) {
+    const int f = blockIdx.y, v = blockIdx.x * 128 + threadIdx.x;
+    if (v >= a.V) return;
+    const double* cloud = a.cloud + (size_t)f * 3 * a.V;
+    const int* rank_of = a.rank_of + (size_t)f * a.F;
+    const int s0 = a.vf_start[v], n = min(a.vf_start[v + 1] - s0, kMaxValence);
+    int fr[kMaxValence], fc[kMaxValence];
+    for (int i = 0; i < n; ++i) {   // insertion sort by paint position
+        const int face = a.vf_list[s0 + i], r = rank_of[face];
+        int k = i;
+        while (k > 0 && fr[k - 1] > r) {
+            fr[k] = fr[k - 1];
+            fc[k] = fc[k - 1];
+            --k;
+        }
+        fr[k] = r;
+        fc[k] = face;
+    }
+    double ns[3] = {0.0, 0.0, 0.0};
+    for (int i = 0; i < n; ++i) {
+        const int* t = a.faces + 3 * (size_t)fc[i];
+        double nn[3];
+        face_unit_normal(cloud + 3 * (size_t)t[0], cloud + 3 * (size_t)t[1], cloud + 3 * (size_t)t[2], nn);
+        // a degenerate face listing the vertex twice adds its normal twice, as the reference's loop over j does
+        for (int j = 0; j < 3; ++j)
+            if (t[j] == v) { ns[0] = dadd(ns[0], nn[0]); ns[1] = dadd(ns[1], nn[1]); ns[2] = dadd(ns[2], nn[2]); }
+    }
+    a.vlam[(size_t)f * a.V + v] = vertex_lambert(cloud + 3 * (size_t)v, ns);
+}
+
+__global__ void __launch_bounds__(128)
+render_cover_lambert_kernel(RenderArgs a) {
+    const int f = blockIdx.y, i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= a.F) return;
+    const RenderView v = view_of(a, f);
+    const size_t px = (size_t)a.width * a.height;
+    face_cover_lambert(v, a.order[(size_t)f * a.F + i], (unsigned)i + 1u, a.win_lambert + f * px, [](unsigned* p, unsigned r) { atomicMax(p, r); });
+}
+
+__global__ void __launch_bounds__(256)
+render_resolve_lambert_kernel(RenderArgs a) {
+    const int f = blockIdx.y;
+    const size_t px = (size_t)a.width * a.height;
+    const unsigned p = blockIdx.x * 256u + threadIdx.x;
+    if (p >= px) return;
+    const int i = (int)(p / (unsigned)a.width), j = (int)(p - (unsigned)i * (unsigned)a.width);
+    const RenderView v = view_of(a, f);
+    a.lambert_out[f * px + p] = resolve_lambert(v, a.order + (size_t)f * a.F, a.vlam + (size_t)f * a.V, a.win_lambert[f * px + p], i, j);
+}
+
+int render_max_valence() { return kMaxValence; }
+
+cudaError_t launch_render_lambert(const RenderArgs& a, int batch, cudaStream_t st) {
+    const size_t smem = (size_t)kSortN * 8;
+    cudaError_t e = cudaFuncSetAttribute(render_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    render_prepare_kernel<<<batch, kPrepThreads, smem, st>>>(a);
+    render_vertex_lambert_kernel<<<dim3((a.V + 127) / 128, batch), 128, 0, st>>>(a);
+    render_cover_lambert_kernel<<<dim3((a.F + 127) / 128, batch), 128, 0, st>>>(a);
+    const size_t px = (size_t)a.width * a.height;
+    render_resolve_lambert_kernel<<<dim3((unsigned)((px + 255) / 256), batch), 256, 0, st>>>(a);
+    return cudaGetLastError();
 }
 
 int render_max_faces() { return kSortN; }

@@ -75,6 +75,15 @@ class Fitter:
         check(lib.avb_render_batch(self.handle, B, ptr(x), C.byref(d), ptr(depth), ptr(parts), ptr(faces)))
         return dict(depth=depth, parts=parts, faces=faces)
 
+    def render_lambert(self, x, width, height, intrin):
+        """AvatarRenderer::renderLambert of the model posed at x [B, nx]; intrin = (fx, cx, fy, cy) -> uint8 [B, H, W]"""
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        B = x.shape[0]
+        d = _lib.RenderDesc(int(width), int(height), float(intrin[0]), float(intrin[1]), float(intrin[2]), float(intrin[3]))
+        gray = np.zeros((B, height, width), np.uint8)
+        check(lib.avb_render_lambert_batch(self.handle, B, ptr(x), C.byref(d), ptr(gray)))
+        return gray
+
     def render_ms(self):
         ms = (C.c_float * 3)()
         check(lib.avb_last_render_ms(self.handle, ms))

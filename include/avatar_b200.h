@@ -202,6 +202,12 @@ typedef struct avb_render_desc {
 } avb_render_desc;
 int avb_render_batch(avb_fitter* fitter, int32_t batch, const double* x, const avb_render_desc* view, float* depth_out,
                      uint8_t* parts_out, int32_t* faces_out);
+/* AvatarRenderer::renderLambert (AvatarRenderer.cpp:103-172), the call demo.cpp:275-277 and live-demo.cpp:428-434 make right
+ * after optimize(): per-vertex normals (unit face normals added in the frame's paint order, normalised, turned towards
+ * the camera), two point lights, faces with |n_z| <= 1e-2 skipped, painted far to near with paintTriangleBary<uint8_t>.
+ * gray_out: host [batch][height][width] uint8 (0 = nothing painted), bit for bit the reference's image. */
+int avb_render_lambert_batch(avb_fitter* fitter, int32_t batch, const double* x, const avb_render_desc* desc, uint8_t* gray_out);
+
 /* device time (ms) of [prepare (project + sort), cover, resolve] of the last avb_render_batch */
 int avb_last_render_ms(avb_fitter* fitter, float* ms3);
 /* Body-part label prediction on the device: the image form of RTree::predictBest

@@ -65,6 +65,7 @@ _sig = {
     "orc_rtree_predict": (None, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "orc_render": (None, [_P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "orc_render_prelude": (None, [_P, C.c_int, _P, C.c_int, _P, _P, _P, _P]),
+    "orc_render_lambert": (None, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "orc_param_dim": (C.c_int, [_P]),
     "orc_tangent_dim": (C.c_int, [_P]),
 }
@@ -254,7 +255,49 @@ def render(cloud, faces, vertex_part, width, height, intrin, want=("depth", "par
     return dict(depth=depth, parts=parts, faces=fids, order=order)
 
 
+def render_lambert(cloud, faces, width, height, intrin, taps=False):
+    """AvatarRenderer::renderLambert restated (orc_render_lambert): uint8 image [H, W]; taps=True also returns the per-vertex
+    lambert values [V] and the visibility of the ordered faces [F]"""
+    cloud = _f64(cloud)
+    faces = np.ascontiguousarray(faces, dtype=np.int32)
+    k = np.ascontiguousarray(intrin, dtype=np.float32)
+    gray = np.zeros((height, width), np.uint8)
+    lam = np.zeros(cloud.shape[0], np.float32)
+    vis = np.zeros(faces.shape[0], np.uint8)
+    _lib.orc_render_lambert(_p(cloud), cloud.shape[0], _p(faces), faces.shape[0], width, height, _p(k), _p(gray), _p(lam), _p(vis))
+    return (gray, lam, vis) if taps else gray
+
+
+def ref_paint_lambert(proj, faces_ordered, visible, lambert, width, height):
+    """renderLambert's painting loop through the REFERENCE'S OWN paintTriangleBary<uint8_t> (oracle/_ref); None if not built"""
+    if not os.path.exists(REF_PAINTERS_PATH):
+        return None
+    lib = C.CDLL(REF_PAINTERS_PATH)
+    proj = np.ascontiguousarray(proj, dtype=np.float32)
+    fo = np.ascontiguousarray(faces_ordered, dtype=np.int32)
+    vis = np.ascontiguousarray(visible, dtype=np.uint8)
+    lam = np.ascontiguousarray(lambert, dtype=np.float32)
+    gray = np.zeros((height, width), np.uint8)
+    lib.ref_paint_lambert.argtypes = [_P, C.c_int, _P, C.c_int, _P, _P, C.c_int, C.c_int, _P]
+    lib.ref_paint_lambert.restype = None
+    lib.ref_paint_lambert(_p(proj), proj.shape[0], _p(fo), fo.shape[0], _p(vis), _p(lam), width, height, _p(gray))
+    return gray
+
+
 REF_PAINTERS_PATH = os.path.join(_HERE, "_ref", "libref_painters.so")
+
+
+def render_prelude(cloud, faces, intrin):
+    """getProjectedPoints + getOrderedFaces + the grazing test restated: (proj [V,2] float32, order [F], grazing [F])"""
+    cloud = _f64(cloud)
+    faces = np.ascontiguousarray(faces, dtype=np.int32)
+    k = np.ascontiguousarray(intrin, dtype=np.float32)
+    V, F = cloud.shape[0], faces.shape[0]
+    proj = np.zeros((V, 2), np.float32)
+    order = np.zeros(F, np.int32)
+    grazing = np.zeros(F, np.uint8)
+    _lib.orc_render_prelude(_p(cloud), V, _p(faces), F, _p(k), _p(proj), _p(order), _p(grazing))
+    return proj, order, grazing
 
 
 def ref_painters_render(cloud, faces, vertex_part, width, height, intrin):
@@ -324,6 +367,20 @@ def brute_nn(points, queries):
 
 
 REF_NANOFLANN_FMA_PATH = os.path.join(_HERE, "_ref", "libref_nanoflann_fma.so")
+
+
+def paint_check_lambert(cloud, faces, width, height, intrin):
+    """the product's rank-form renderLambert (avatar_b200/csrc/avb_paint.h) run on the CPU by tests/cpp/libpaint_check.so"""
+    lib = C.CDLL(os.path.join(os.path.dirname(_HERE), "tests", "cpp", "libpaint_check.so"))
+    cloud = _f64(cloud)
+    faces = np.ascontiguousarray(faces, dtype=np.int32)
+    k = np.ascontiguousarray(intrin, dtype=np.float32)
+    gray = np.zeros((height, width), np.uint8)
+    vlam = np.zeros(cloud.shape[0], np.float32)
+    lib.paint_check_lambert.argtypes = [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]
+    lib.paint_check_lambert.restype = None
+    lib.paint_check_lambert(_p(cloud), cloud.shape[0], _p(faces), faces.shape[0], width, height, _p(k), _p(gray), _p(vlam))
+    return gray, vlam
 
 
 def ref_nanoflann_nn(points, queries, fma=False):

@@ -44,6 +44,20 @@ void ref_paint_faces(const float* proj_xy, int V, const int32_t* faces, int nf, 
 }
 
 
+/* renderLambert's painting loop with the reference's paintTriangleBary<uint8_t>: faces in the given (paint) order, only
+ * those with visible[i] != 0, lambert[i][3] = the three vertex values of face i */
+void ref_paint_lambert(const float* proj_xy, int V, const int32_t* faces, int nf, const uint8_t* visible, const float* lambert,
+                       int W, int H, uint8_t* gray) {
+    const std::vector<cv::Point2f> proj = points_of(proj_xy, V);
+    const cv::Size size(W, H);
+    cv::Mat mg(H, W, 1, gray);
+    for (int i = 0; i < nf; ++i) {
+        if (!visible[i]) continue;
+        const cv::Vec3i face(faces[3 * i], faces[3 * i + 1], faces[3 * i + 2]);
+        ark::paintTriangleBary<uint8_t>(mg, size, proj, face, lambert + 3 * i);
+    }
+}
+
 /* CameraIntrin::depthToXYZ of the reference (Calibration.cpp:83-95): depth [H][W] float -> xyz [H][W][3] float */
 void ref_depth_to_xyz(const float* depth, int W, int H, float fx, float cx, float fy, float cy, float* xyz) {
     ark::CameraIntrin k;

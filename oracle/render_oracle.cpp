@@ -25,8 +25,9 @@ namespace {
 
 struct Pt { float x, y; };
 
-// paintTriangleBary<float> (AvatarHelpers.cpp:61-131)
-void paint_bary(float* out, int W, int H, const Pt* proj, const int32_t* face, const float* zvec, float maxz = 255.0f) {
+// paintTriangleBary<T> (AvatarHelpers.cpp:61-131); T = float (renderDepth) or uint8_t (renderLambert)
+template <class T>
+void paint_bary(T* out, int W, int H, const Pt* proj, const int32_t* face, const float* zvec, float maxz = 255.0f) {
     std::pair<double, int> yf[3] = {{proj[face[0]].y, 0}, {proj[face[1]].y, 1}, {proj[face[2]].y, 2}};
     std::sort(yf, yf + 3);
     Pt a = proj[face[yf[0].second]], b = proj[face[yf[1].second]], c = proj[face[yf[2].second]];
@@ -40,11 +41,11 @@ void paint_bary(float* out, int W, int H, const Pt* proj, const int32_t* face, c
         const int minxi = std::max<int>(std::floor(mlo * i + blo), 0), maxxi = std::min<int>(std::ceil(mhi * i + bhi), W - 1);
         if (minxi > maxxi) return;
         const float w1v = (b.x - c.x) * (i - c.y), w2v = (c.x - a.x) * (i - c.y);
-        float* ptr = out + (size_t)i * W;
+        T* ptr = out + (size_t)i * W;
         for (int j = minxi; j <= maxxi; ++j) {
             const float w1 = (w1v + (c.y - b.y) * (j - c.x)) * denom;
             const float w2 = (w2v + (a.y - c.y) * (j - c.x)) * denom;
-            ptr[j] = std::min(std::max(w1 * az + w2 * bz + (1.f - w1 - w2) * cz, 0.0f), maxz);
+            ptr[j] = T(std::min(std::max(w1 * az + w2 * bz + (1.f - w1 - w2) * cz, 0.0f), maxz));
         }
     };
     if (a.y != b.y) {
@@ -177,7 +178,7 @@ void orc_render(const double* cloud, int V, const int32_t* faces, int F, const i
                 paint_single<float>(depth, W, H, proj.data(), f, 0.f);
             } else {
                 const float zv[3] = {(float)cloud[3 * (size_t)f[0] + 2], (float)cloud[3 * (size_t)f[1] + 2], (float)cloud[3 * (size_t)f[2] + 2]};
-                paint_bary(depth, W, H, proj.data(), f, zv);
+                paint_bary<float>(depth, W, H, proj.data(), f, zv);
             }
         }
         if (parts) {   // renderPartMask (AvatarRenderer.cpp:170-197)
@@ -188,6 +189,76 @@ void orc_render(const double* cloud, int V, const int32_t* faces, int F, const i
     }
 }
 
+
+/* AvatarRenderer::renderLambert (AvatarRenderer.cpp:103-172): per-vertex normals = sum of the unit normals of the incident
+ * faces, added IN PAINT ORDER (the loop runs over the ordered faces), normalised, flipped towards the camera (z <= 0);
+ * two point lights; faces with |n_z| <= 1e-2 are skipped; painted far to near with paintTriangleBary<uint8_t>.
+ * Eigen conventions restated: cross = (a1 b2 - a2 b1, a2 b0 - a0 b2, a0 b1 - a1 b0); normalized() / normalize() divide by
+ * sqrt(squaredNorm) when squaredNorm > 0 and leave the vector otherwise; dot and squaredNorm sum ((x + y) + z); abs() is
+ * the floating overload.  gray [H][W] uint8 (0 = nothing).  Optional taps: vertex_lambert [V] float (the value painted at
+ * every vertex), face_visible [F] (ordered faces). */
+void orc_render_lambert(const double* cloud, int V, const int32_t* faces, int F, int W, int H, const float* intrin, uint8_t* gray,
+                        float* vertex_lambert, uint8_t* face_visible) {
+    const float fx = intrin[0], cx = intrin[1], fy = intrin[2], cy = intrin[3];
+    std::vector<Pt> proj(V);
+    for (int i = 0; i < V; ++i) {
+        const double* pt = cloud + 3 * (size_t)i;
+        proj[i].x = static_cast<double>(pt[0]) * fx / pt[2] + cx;
+        proj[i].y = -static_cast<double>(pt[1]) * fy / pt[2] + cy;
+    }
+    std::vector<std::pair<float, int>> ord(F);
+    for (int i = 0; i < F; ++i) {
+        const int32_t* f = faces + 3 * (size_t)i;
+        ord[i].first = (cloud[3 * (size_t)f[0] + 2] + cloud[3 * (size_t)f[1] + 2] + cloud[3 * (size_t)f[2] + 2]) / 3.f;
+        ord[i].second = i;
+    }
+    std::stable_sort(ord.begin(), ord.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first > b.first; });
+    auto normalize3 = [](double* v) {
+        const double z = (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2];
+        if (z > 0.0) {
+            const double n = std::sqrt(z);
+            v[0] /= n; v[1] /= n; v[2] /= n;
+        }
+    };
+    std::vector<double> vn(3 * (size_t)V, 0.0);
+    std::vector<uint8_t> visible(F);
+    for (int i = 0; i < F; ++i) {
+        const int32_t* f = faces + 3 * (size_t)ord[i].second;
+        const double* a = cloud + 3 * (size_t)f[0];
+        const double* b = cloud + 3 * (size_t)f[1];
+        const double* c = cloud + 3 * (size_t)f[2];
+        const double ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ac[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+        double n[3] = {ab[1] * ac[2] - ab[2] * ac[1], ab[2] * ac[0] - ab[0] * ac[2], ab[0] * ac[1] - ab[1] * ac[0]};
+        normalize3(n);
+        for (int j = 0; j < 3; ++j)
+            for (int k = 0; k < 3; ++k) vn[3 * (size_t)f[j] + k] += n[k];
+        visible[i] = std::fabs(n[2]) > 1e-2;
+    }
+    const double mainLight[3] = {0.8, 1.5, -1.2}, backLight[3] = {-0.2, -1.5, 0.4};
+    const double mainI = 0.8, backI = 0.2;
+    std::vector<float> lam(V);
+    for (int v = 0; v < V; ++v) {
+        double* n = &vn[3 * (size_t)v];
+        normalize3(n);
+        if (n[2] > 0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
+        const double* a = cloud + 3 * (size_t)v;
+        double ml[3] = {mainLight[0] - a[0], mainLight[1] - a[1], mainLight[2] - a[2]};
+        double bl[3] = {backLight[0] - a[0], backLight[1] - a[1], backLight[2] - a[2]};
+        normalize3(ml);
+        normalize3(bl);
+        const double dm = (ml[0] * n[0] + ml[1] * n[1]) + ml[2] * n[2], db = (bl[0] * n[0] + bl[1] * n[1]) + bl[2] * n[2];
+        lam[v] = std::max(float(dm * mainI + db * backI) * 255, 0.f);
+    }
+    if (vertex_lambert) std::copy(lam.begin(), lam.end(), vertex_lambert);
+    if (face_visible) std::copy(visible.begin(), visible.end(), face_visible);
+    std::fill(gray, gray + (size_t)W * H, (uint8_t)0);
+    for (int i = 0; i < F; ++i) {
+        if (!visible[i]) continue;
+        const int32_t* f = faces + 3 * (size_t)ord[i].second;
+        const float lv[3] = {lam[f[0]], lam[f[1]], lam[f[2]]};
+        paint_bary<uint8_t>(gray, W, H, proj.data(), f, lv);
+    }
+}
 
 /* the renderer's per-frame prelude, for tests that drive the reference's own painters (oracle/_ref/libref_painters.so):
  * projected vertices [V][2], faces in paint order [F], and per ordered face the grazing flag (|n_z| < 0.1) */

@@ -222,3 +222,29 @@ def test_part_without_visible_vertices(model, oracle_mod, omodel, prior_arrays):
     assert st[0].num_correspondences == sto.num_correspondences < len(pts) * 6 // 7 + 1
     assert np.abs(x[0] - xo).max() < PARAM_TOL
     ft.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# SURVEY.md 8(f)-2 finished: AvatarRenderer::renderLambert on the device
+# ---------------------------------------------------------------------------------------------
+def test_render_lambert_bit_exact(model, oracle_mod, omodel, prior_arrays):
+    """device renderLambert (AvatarRenderer.cpp:103-172) == the sequential restatement of oracle/render_oracle.cpp on the
+    same posed cloud, bit for bit (the oracle is in turn pinned to the reference's own paintTriangleBary<uint8_t> by
+    tests/test_oracle.py), at 640x576 and at an odd size with off-centre intrinsics"""
+    from avatar_b200 import Fitter
+    from harness import synth
+    nparts = int(prior_arrays["num_parts"])
+    faces = np.ascontiguousarray(model.mesh, dtype=np.int32)
+    xs = np.stack([synth.random_params(model, np.random.default_rng(3000 + s)) for s in range(3)])
+    ft = Fitter(model, nparts, prior_arrays["part_map"], 3, 1000)
+    clouds, _, _ = ft.avatar_update(xs)
+    for (w, h, k) in [(synth.WIDTH, synth.HEIGHT, (synth.FX, synth.CX, synth.FY, synth.CY)), (321, 203, (250.5, 160.25, 251.0, 101.5))]:
+        got = ft.render_lambert(xs, w, h, k)
+        for b in range(3):
+            want = oracle_mod.render_lambert(clouds[b], faces, w, h, k)
+            assert np.array_equal(got[b], want), (b, w, int((got[b] != want).sum()))
+            assert (want > 0).sum() > 500
+    # the other renderer outputs still work on the same fitter afterwards
+    d = ft.render(xs[:1], 160, 144, (126.0, 80.0, 126.0, 72.0), want=("depth",))
+    assert (d["depth"] > 0).sum() > 100
+    ft.close()

@@ -561,3 +561,31 @@ def test_oracle_reproduces_the_frozen_golden_outputs(build_all):
             np.testing.assert_allclose(got[k], want[k], rtol=1e-9, atol=1e-9, err_msg=k)   # libm / numpy versions may move last bits
         else:
             assert np.array_equal(np.asarray(got[k]), want[k]), k
+
+
+# ---------------------------------------------------------------------------------------------
+# SURVEY.md 8(f)-2, finished in round 2: AvatarRenderer::renderLambert (AvatarRenderer.cpp:103-172)
+# ---------------------------------------------------------------------------------------------
+def test_render_lambert_rank_form_oracle_and_reference_painter(oracle_mod, model, omodel, prior_arrays):
+    """three implementations of renderLambert give the same uint8 image, bit for bit, without a GPU: the sequential
+    restatement (oracle/render_oracle.cpp), the product's rank-form code run on the CPU (avb_paint.h through
+    tests/cpp/paint_check.cpp), and the REFERENCE'S OWN paintTriangleBary<uint8_t> (AvatarHelpers.cpp compiled into
+    oracle/_ref) driven with the oracle's paint order, visibility flags and vertex values."""
+    from harness import synth
+    intrin = (synth.FX, synth.CX, synth.FY, synth.CY)
+    mesh = np.ascontiguousarray(model.mesh, dtype=np.int32)
+    for seed, (W, H) in ((0, (synth.WIDTH, synth.HEIGHT)), (1, (320, 288)), (2, (synth.WIDTH, synth.HEIGHT))):
+        rng = np.random.default_rng(2000 + seed)
+        x = synth.random_params(model, rng)
+        cloud, _, _ = omodel.update_x(x)
+        k = intrin if W == synth.WIDTH else (synth.FX / 2, synth.CX / 2, synth.FY / 2, synth.CY / 2)
+        gray, lam, vis = oracle_mod.render_lambert(cloud, mesh, W, H, k, taps=True)
+        assert (gray > 0).sum() > 500 and 0.3 < vis.mean() <= 1.0 and lam.max() <= 255.0
+        g2, lam2 = oracle_mod.paint_check_lambert(cloud, mesh, W, H, k)
+        assert np.array_equal(lam, lam2), np.abs(lam - lam2).max()
+        assert np.array_equal(gray, g2), int((gray != g2).sum())
+        proj, order, _ = oracle_mod.render_prelude(cloud, mesh, k)
+        g3 = oracle_mod.ref_paint_lambert(proj, mesh[order], vis, lam[mesh[order]], W, H)
+        if g3 is None:
+            pytest.skip("oracle/_ref/libref_painters.so not built (reference tree absent)")
+        assert np.array_equal(gray, g3), int((gray != g3).sum())
