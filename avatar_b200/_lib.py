@@ -49,7 +49,8 @@ class Stats(C.Structure):
 _P = C.c_void_p
 class ImageDesc(C.Structure):   # avb_image_desc
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_float), ("cx", C.c_float), ("fy", C.c_float),
-                ("cy", C.c_float), ("interval", C.c_int32), ("num_parts", C.c_int32), ("rtree_interval", C.c_int32)]
+                ("cy", C.c_float), ("interval", C.c_int32), ("num_parts", C.c_int32), ("rtree_interval", C.c_int32),
+                ("rtree_postprocess", C.c_int32), ("part_map_type", C.c_int32), ("dist_to_pre_weight", C.c_double)]
 
 
 class RenderDesc(C.Structure):   # avb_render_desc
@@ -89,6 +90,8 @@ SYMBOLS = [
     ("avb_fitter_set_rtree", C.c_int, [_P, C.POINTER(RTreeDesc)]),
     ("avb_rtree_predict_batch", C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, _P]),
     ("avb_last_rtree_ms", C.c_int, [_P, _P]),
+    ("avb_rtree_postprocess_batch", C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_double]),
+    ("avb_rtree_reset_tracking", C.c_int, [_P]),
     ("avb_render_batch", C.c_int, [_P, C.c_int32, _P, C.POINTER(RenderDesc), _P, _P, _P]),
     ("avb_last_render_ms", C.c_int, [_P, _P]),
     ("avb_render_lambert_batch", C.c_int, [_P, C.c_int32, _P, C.POINTER(RenderDesc), _P]),

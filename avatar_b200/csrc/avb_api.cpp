@@ -120,6 +120,8 @@ struct avb_fitter {
     long long* d_strip_offset = nullptr; int* d_bad_label = nullptr;
     size_t img_cap = 0, strip_cap = 0;
     RTreeNode* d_rt_nodes = nullptr; uint8_t* d_rt_leaf = nullptr; int rt_nodes = 0, rt_leaves = 0, rt_parts = 0;
+    // RTree::postProcess scratch (grown on demand) and the per-frame centre-of-mass state of the chained pipeline
+    int *d_pp_arena = nullptr, *d_pp_stack = nullptr, *d_pp_ovf = nullptr; double* d_pp_com = nullptr; size_t pp_cap = 0; int pp_parts = 0;
     const uint8_t* d_vpart = nullptr; float* d_proj = nullptr; int* d_order = nullptr; unsigned* d_win = nullptr;
     float* d_rdepth = nullptr; uint8_t* d_rparts = nullptr; int* d_rfaces = nullptr; size_t render_cap = 0;
     const int *d_vf_start = nullptr, *d_vf_list = nullptr; int max_valence = 0;   // faces incident to every vertex (renderLambert)
@@ -533,6 +535,7 @@ void avb_fitter_destroy(avb_fitter* ft) {
     for (auto& e : ft->cev) if (e) cudaEventDestroy(e);
     for (auto& e : ft->rev) if (e) cudaEventDestroy(e);
     cudaFree(ft->d_rt_nodes); cudaFree(ft->d_rt_leaf);
+    cudaFree(ft->d_pp_arena); cudaFree(ft->d_pp_stack); cudaFree(ft->d_pp_ovf); cudaFree(ft->d_pp_com);
     cudaFree(ft->d_win); cudaFree(ft->d_rdepth); cudaFree(ft->d_rparts); cudaFree(ft->d_rfaces); cudaFree(ft->d_proj); cudaFree(ft->d_order);
     cudaFree(ft->d_rank_of); cudaFree(ft->d_vlam); cudaFree(ft->d_win_l); cudaFree(ft->d_rlam);
     for (auto& e : ft->nev) if (e) cudaEventDestroy(e);
@@ -904,6 +907,12 @@ int enqueue_rtree(avb_fitter* ft, int batch, int width, int height, const int32_
 }
 }  // namespace
 
+namespace {
+int enqueue_postprocess(avb_fitter* ft, int batch, int width, int height, const int32_t* roi_host, int interval, int num_parts,
+                        int part_map_type, double dist_w);
+int ensure_com_state(avb_fitter* ft, int num_parts, bool reset);
+}  // namespace
+
 /* -------- cloud construction on the device (demo.cpp:215-250, Calibration.cpp:83-95) -------- */
 int avb_upload_depth_batch(avb_fitter* ft, int32_t batch, const float* depth, const uint8_t* parts, const int32_t* roi,
                            const avb_image_desc* img, int64_t* offsets_out) {
@@ -934,6 +943,13 @@ int avb_upload_depth_batch(avb_fitter* ft, int32_t batch, const float* depth, co
     } else {   // demo.cpp:198-200: labels from the decision tree, on the device
         int rcr = enqueue_rtree(ft, batch, img->width, img->height, roi, roi != nullptr, img->rtree_interval, true);
         if (rcr != AVB_OK) return rcr;
+        if (img->rtree_postprocess) {   // demo.cpp:201: rtree.postProcess(result, comPre, 2, threads, topLeft, botRight)
+            rcr = ensure_com_state(ft, img->num_parts, false);
+            if (rcr == AVB_OK)
+                rcr = enqueue_postprocess(ft, batch, img->width, img->height, roi, img->rtree_interval, img->num_parts,
+                                          img->part_map_type, img->dist_to_pre_weight > 0.0 ? img->dist_to_pre_weight : 0.001);
+            if (rcr != AVB_OK) return rcr;
+        }
     }
     CUDA_TRY(cudaMemsetAsync(ft->d_bad_label, 0, (size_t)batch * 4, st));
     CloudArgs a{};
@@ -1007,6 +1023,101 @@ int avb_fitter_set_rtree(avb_fitter* ft, const avb_rtree_desc* t) {
     CUDA_TRY(cudaMemcpy(ft->d_rt_nodes, nodes.data(), nodes.size() * sizeof(RTreeNode), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(ft->d_rt_leaf, t->leaf_best, (size_t)t->num_leaves, cudaMemcpyHostToDevice));
     ft->rt_nodes = t->num_nodes; ft->rt_leaves = t->num_leaves; ft->rt_parts = t->num_parts;
+    return AVB_OK;
+}
+
+namespace {
+// RTree::postProcess on the label images resident in d_parts; com_pre on the device (ft->d_pp_com), roi in d_roi if given
+int enqueue_postprocess(avb_fitter* ft, int batch, int width, int height, const int32_t* roi_host, int interval, int num_parts,
+                        int part_map_type, double dist_w) {
+    if (interval <= 0) return fail(AVB_ERR_INVALID, "interval must be positive");
+    if (num_parts <= 0 || num_parts > 64) return fail(AVB_ERR_INVALID, "postProcess handles 1..64 parts (labels < 128)");
+    if (width > 65535 || height > 32767) return fail(AVB_ERR_INVALID, "postProcess packs pixel ids into 16 + 15 bits");
+    long long grid = 0;
+    for (int f = 0; f < batch; ++f) {
+        const int x0 = roi_host ? roi_host[4 * f] : 0, y0 = roi_host ? roi_host[4 * f + 1] : 0;
+        const int x1 = roi_host ? roi_host[4 * f + 2] : width - 1, y1 = roi_host ? roi_host[4 * f + 3] : height - 1;
+        if (x1 < x0 || y1 < y0) continue;
+        if (x0 < 0 || y0 < 0 || x1 >= width || y1 >= height)
+            return fail(AVB_ERR_INVALID, "postProcess bounding box of frame " + std::to_string(f) + " leaves the image");
+        grid = std::max(grid, (long long)((x1 - x0) / interval + 1) * ((y1 - y0) / interval + 1));
+    }
+    const size_t cap = (size_t)(2 * grid + 64);
+    if (cap > ft->pp_cap) {
+        CUDA_TRY(cudaStreamSynchronize(ft->stream));
+        cudaFree(ft->d_pp_arena); cudaFree(ft->d_pp_stack);
+        ft->d_pp_arena = ft->d_pp_stack = nullptr;
+        ft->pp_cap = 0;
+        CUDA_TRY(cudaMalloc(&ft->d_pp_arena, (size_t)ft->max_batch * cap * 4));
+        CUDA_TRY(cudaMalloc(&ft->d_pp_stack, (size_t)ft->max_batch * cap * 4));
+        ft->pp_cap = cap;
+    }
+    if (!ft->d_pp_ovf) CUDA_TRY(cudaMalloc(&ft->d_pp_ovf, (size_t)ft->max_batch * 4));
+    CUDA_TRY(cudaMemsetAsync(ft->d_pp_ovf, 0, (size_t)batch * 4, ft->stream));
+    RTreePostArgs a{};
+    a.parts = ft->d_parts;
+    a.roi = roi_host ? ft->d_roi : nullptr;
+    a.width = width; a.height = height; a.interval = interval; a.num_parts = num_parts; a.part_map_type = part_map_type;
+    a.dist_w = dist_w;
+    a.com_pre = ft->d_pp_com;
+    a.arena = ft->d_pp_arena;
+    a.stack = ft->d_pp_stack;
+    a.cap = (long long)ft->pp_cap;
+    a.overflow = ft->d_pp_ovf;
+    CUDA_TRY(launch_rtree_postprocess(a, batch, ft->stream));
+    return AVB_OK;
+}
+int ensure_com_state(avb_fitter* ft, int num_parts, bool reset) {
+    if (!ft->d_pp_com || ft->pp_parts != num_parts) {
+        CUDA_TRY(cudaStreamSynchronize(ft->stream));
+        cudaFree(ft->d_pp_com);
+        ft->d_pp_com = nullptr;
+        CUDA_TRY(cudaMalloc(&ft->d_pp_com, (size_t)ft->max_batch * 2 * num_parts * 8));
+        ft->pp_parts = num_parts;
+        reset = true;
+    }
+    if (reset) {   // the reference's freshly resized com_pre: x = -1 (not seen), y = 0 (RTree.cpp:3432-3436)
+        std::vector<double> init((size_t)ft->max_batch * 2 * num_parts, 0.0);
+        for (size_t i = 0; i < init.size(); i += 2) init[i] = -1.0;
+        CUDA_TRY(cudaMemcpyAsync(ft->d_pp_com, init.data(), init.size() * 8, cudaMemcpyHostToDevice, ft->stream));
+        CUDA_TRY(cudaStreamSynchronize(ft->stream));
+    }
+    return AVB_OK;
+}
+}  // namespace
+
+/* RTree::postProcess (RTree.cpp:3422-3450) on a batch of label images */
+int avb_rtree_postprocess_batch(avb_fitter* ft, int32_t batch, uint8_t* parts, int32_t width, int32_t height, const int32_t* roi,
+                                int32_t interval, int32_t num_parts, int32_t part_map_type, double* com_pre, double dist_to_pre_weight) {
+    if (!ft || !parts || !com_pre || batch <= 0 || width <= 0 || height <= 0) return fail(AVB_ERR_INVALID, "null argument or empty batch");
+    if (batch > ft->max_batch) return fail(AVB_ERR_CAPACITY, "batch exceeds fitter capacity");
+    if (num_parts <= 0 || num_parts > 64) return fail(AVB_ERR_INVALID, "postProcess handles 1..64 parts (labels < 128)");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    const size_t npx = (size_t)width * height * batch;
+    int rc = ensure_image_staging(ft, npx, 0);
+    if (rc != AVB_OK) return rc;
+    rc = ensure_com_state(ft, num_parts, false);
+    if (rc != AVB_OK) return rc;
+    cudaStream_t st = ft->stream;
+    CUDA_TRY(cudaMemcpyAsync(ft->d_parts, parts, npx, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ft->d_pp_com, com_pre, (size_t)batch * 2 * num_parts * 8, cudaMemcpyHostToDevice, st));
+    if (roi) CUDA_TRY(cudaMemcpyAsync(ft->d_roi, roi, (size_t)batch * 16, cudaMemcpyHostToDevice, st));
+    rc = enqueue_postprocess(ft, batch, width, height, roi, interval, num_parts, part_map_type, dist_to_pre_weight);
+    if (rc != AVB_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(parts, ft->d_parts, npx, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(com_pre, ft->d_pp_com, (size_t)batch * 2 * num_parts * 8, cudaMemcpyDeviceToHost, st));
+    std::vector<int> ovf((size_t)batch);
+    CUDA_TRY(cudaMemcpyAsync(ovf.data(), ft->d_pp_ovf, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int f = 0; f < batch; ++f)
+        if (ovf[f]) return fail(AVB_ERR_CAPACITY, "postProcess scratch overflow in frame " + std::to_string(f) + " (internal error)");
+    return AVB_OK;
+}
+
+int avb_rtree_reset_tracking(avb_fitter* ft) {
+    if (!ft) return fail(AVB_ERR_INVALID, "null fitter");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    if (ft->pp_parts > 0) return ensure_com_state(ft, ft->pp_parts, true);
     return AVB_OK;
 }
 

@@ -67,6 +67,18 @@ struct RTreeArgs {   // RTree::predictBest on images (avb_rtree.cu)
     int width, height, interval;
 };
 
+struct RTreePostArgs {   // RTree::postProcess on the device (avb_rtree.cu)
+    uint8_t* parts;              // [batch][height][width] in/out
+    const int* roi;              // nullable [batch][4]
+    int width, height, interval, num_parts, part_map_type;
+    double dist_w;               // dist_to_pre_weight
+    double* com_pre;             // [batch][2 * num_parts] in/out, x of part i at [2 i] (-1: not seen), y at [2 i + 1]
+    int* arena;                  // [batch][cap] component pixel lists (append-only per frame)
+    int* stack;                  // [batch][cap] DFS stack
+    long long cap;               // ints per frame in arena and in stack (>= 2 * grid pixels + 64)
+    int* overflow;               // [batch] set when a frame ran out of scratch
+};
+
 struct RenderArgs {   // AvatarRenderer on the device (avb_render.cu)
     const double* cloud;         // [batch][3V] posed models
     const int* faces;            // [3F]
@@ -142,6 +154,7 @@ struct LmBuf {
 
 cudaError_t launch_rtree_predict(const RTreeArgs& a, int batch, int max_box_pixels, cudaStream_t st);
 cudaError_t launch_rtree_upscale(const RTreeArgs& a, int batch, int max_box_pixels, cudaStream_t st);
+cudaError_t launch_rtree_postprocess(const RTreePostArgs& a, int batch, cudaStream_t st);
 int render_max_faces();
 cudaError_t launch_render(const RenderArgs& a, int batch, cudaStream_t st, cudaEvent_t* ev4);
 int render_max_valence();

@@ -1762,7 +1762,8 @@ constexpr int kFlowMinCtasTc = 2;
 template <bool TC>
 __global__ void __launch_bounds__(256, TC ? kFlowMinCtasTc : 2)
 lm_flow_kernel(DevModel M, DevParts Pt, LmBuf a) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_flow[];
+    unsigned char* const smem_raw = smem_flow;
     __shared__ int s_task, s_last;
     __shared__ __align__(8) uint64_t s_mbar;
     __shared__ uint32_t s_tmem;

@@ -110,12 +110,26 @@ class Fitter:
                                           ptr(out)))
         return out
 
+    def rtree_postprocess(self, parts, roi=None, interval=1, num_parts=16, part_map_type=0, com_pre=None, dist_to_pre_weight=0.001):
+        """RTree::postProcess on a batch of label images [B,H,W] uint8 -> (images, com_pre [B, num_parts, 2])"""
+        img = np.array(parts, dtype=np.uint8, order="C", copy=True)
+        if img.ndim == 2:
+            img = img[None]
+        B, H, W = img.shape
+        cp = (np.tile(np.array([-1.0, 0.0]), (B, num_parts, 1)) if com_pre is None
+              else np.array(com_pre, dtype=np.float64, order="C", copy=True).reshape(B, num_parts, 2))
+        roi_a = None if roi is None else np.ascontiguousarray(roi, dtype=np.int32).reshape(B, 4)
+        check(lib.avb_rtree_postprocess_batch(self.handle, B, ptr(img), W, H, ptr(roi_a), int(interval), int(num_parts),
+                                              int(part_map_type), ptr(cp), float(dist_to_pre_weight)))
+        return img, cp
+
     def rtree_ms(self):
         ms = C.c_float()
         check(lib.avb_last_rtree_ms(self.handle, C.byref(ms)))
         return ms.value
 
-    def upload_depth(self, depth, parts, intrin, num_parts, roi=None, interval=1, rtree_interval=2):
+    def upload_depth(self, depth, parts, intrin, num_parts, roi=None, interval=1, rtree_interval=2, postprocess=False,
+                     part_map_type=0, dist_to_pre_weight=0.001):
         """Build the batch's data clouds on the device from depth [B,H,W] float32 (metres) and body-part label images
         [B,H,W] uint8 (255 = background), as demo.cpp:215-250 + CameraIntrin::depthToXYZ do on the host.
         intrin = (fx, cx, fy, cy); roi: optional [B,4] int32 (x0, y0, x1, y1 inclusive).  Returns the offsets."""
@@ -127,7 +141,7 @@ class Fitter:
         B, H, W = depth.shape
         roi_a = None if roi is None else np.ascontiguousarray(roi, dtype=np.int32).reshape(B, 4)
         img = _lib.ImageDesc(W, H, float(intrin[0]), float(intrin[1]), float(intrin[2]), float(intrin[3]), int(interval),
-                             int(num_parts), int(rtree_interval))
+                             int(num_parts), int(rtree_interval), int(bool(postprocess)), int(part_map_type), float(dist_to_pre_weight))
         off = np.zeros(B + 1, dtype=np.int64)
         self._keep = (depth, parts, roi_a)
         check(lib.avb_upload_depth_batch(self.handle, B, ptr(depth), ptr(parts), ptr(roi_a), C.byref(img), ptr(off)))

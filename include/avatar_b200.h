@@ -184,6 +184,11 @@ typedef struct avb_image_desc {
     int32_t interval;       /* pixel stride in both directions (demo.cpp `interval`) */
     int32_t num_parts;      /* rtree.numParts */
     int32_t rtree_interval; /* parts == NULL only: stride of RTree::predictBest (demo.cpp:198 uses 2); gaps are filled */
+    int32_t rtree_postprocess;  /* parts == NULL only: != 0 runs RTree::postProcess on the predicted labels (demo.cpp:201), with
+                                 * the fitter's per-frame centre-of-mass state (comPre), see avb_rtree_reset_tracking */
+    int32_t part_map_type;      /* RTree::partMapType of the .partmap file: 0 = contiguous parts (best blob per part), else
+                                 * small pieces are removed (RTree.cpp:3437-3446) */
+    double dist_to_pre_weight;  /* postProcess' dist_to_pre_weight; <= 0 selects the reference default 0.001 */
 } avb_image_desc;
 int avb_upload_depth_batch(avb_fitter* fitter, int32_t batch, const float* depth, const uint8_t* parts,
                            const int32_t* roi, const avb_image_desc* img, int64_t* offsets_out);
@@ -194,7 +199,7 @@ int avb_download_batch(avb_fitter* fitter, double* data_clouds, int32_t* data_pa
  * [batch][height][width], each nullable: depth float (0 = nothing), parts uint8 (255 = nothing, part of the nearest
  * projected vertex otherwise, with the fitter's part_map), faces int32 (-1 = nothing, else the face's position in paint
  * order, as the reference writes it).  Bit-identical to the sequential painter; faces with equal depth keys are painted
- * in ascending face index (the reference's std::sort leaves that order unspecified).  renderLambert is not built.
+ * in ascending face index (the reference's std::sort leaves that order unspecified).  renderLambert: avb_render_lambert_batch.
  * The call poses the models into the fitter's model-cloud buffer: download the results of a pending fit first. */
 typedef struct avb_render_desc {
     int32_t width, height;
@@ -231,6 +236,18 @@ typedef struct avb_rtree_desc {
 int avb_fitter_set_rtree(avb_fitter* fitter, const avb_rtree_desc* tree);
 int avb_rtree_predict_batch(avb_fitter* fitter, int32_t batch, const float* depth, int32_t width, int32_t height,
                             const int32_t* roi, int32_t interval, int32_t fill_in_gaps, uint8_t* parts_out);
+/* RTree::postProcess (RTree.cpp:3422-3450; suppressPartNonMax :125-232 or removeSmallPieces :234-320, then upscaleGrid
+ * :70-100) on a batch of label images: parts host [batch][height][width] uint8 in/out (255 = background), roi nullable
+ * [batch][4] inclusive corners inside the image, com_pre host [batch][2 * num_parts] in/out laid out like the
+ * reference's 2 x numParts matrix (x of part i at [2 i], -1 = not seen; y at [2 i + 1]); a fresh matrix is (-1, 0).
+ * Bit for bit the reference's sequential flood fill, including its behaviour for interval > 1 (the downward probe tests
+ * row r + 1 but continues at row r + interval): one warp per frame walks the image in the reference's order. */
+int avb_rtree_postprocess_batch(avb_fitter* fitter, int32_t batch, uint8_t* parts, int32_t width, int32_t height, const int32_t* roi,
+                                int32_t interval, int32_t num_parts, int32_t part_map_type, double* com_pre, double dist_to_pre_weight);
+/* forget the centres of mass the chained pipeline (avb_upload_depth_batch with parts == NULL and rtree_postprocess) keeps
+ * per batch slot between calls: the next call starts from the reference's fresh comPre */
+int avb_rtree_reset_tracking(avb_fitter* fitter);
+
 /* device time (ms) of the last RTree prediction (predict + gap filling kernels) */
 int avb_last_rtree_ms(avb_fitter* fitter, float* ms);
 /* device time (ms) of [cloud_count_kernel, cloud_compact_kernel] of the last avb_upload_depth_batch (CUDA events) */

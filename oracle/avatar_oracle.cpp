@@ -1540,6 +1540,130 @@ int64_t orc_build_cloud(const float* depth, const uint8_t* parts, int width, int
     return cnz;
 }
 
+/* RTree::postProcess (RTree.cpp:3422-3450) with suppressPartNonMax (:125-232) / removeSmallPieces (:234-320) and the
+ * trailing upscaleGrid (:70-100), restated literally -- INCLUDING the reference's quirk for interval > 1: the downward
+ * probe tests pixel (r + 1, c) but pushes the id of (r + interval, c), unmarked and whatever its label (:176), so a
+ * component "passes through" the grid pixel below; such pixels are counted, can be erased with the component and can
+ * still seed their own component later.  The scan is sequential and its result depends on the visiting order, which is
+ * therefore kept: raster order of the seeds, LIFO stack, probes in the order up, down, left, right.
+ * image [H][W] uint8 in/out (255 = background); roi = {x0, y0, x1, y1} inclusive or NULL; com_pre [2 * num_parts] in/out,
+ * column major like the reference's 2 x numParts matrix (x of part i at [2 i], y at [2 i + 1]; x = -1: part not seen);
+ * part_map_type 0 = contiguous (keep the best blob per part), otherwise remove pieces smaller than 0.0005 of the grid. */
+void orc_rtree_postprocess(uint8_t* image, int width, int height, const int32_t* roi, int interval, int num_parts, int part_map_type,
+                           double* com_pre, double dist_to_pre_weight) {
+    int tlx = 0, tly = 0, brx = width - 1, bry = height - 1;
+    if (roi) { tlx = roi[0]; tly = roi[1]; brx = roi[2]; bry = roi[3]; }
+    auto at = [&](int r, int c) -> uint8_t& { return image[(size_t)r * width + c]; };
+    const int VISITED_OFFSET = 128;
+    std::vector<int> stk, curCompVis;
+    int hi_bit = (1 << 16);
+    const int lo_mask = hi_bit - 1;
+    hi_bit *= interval;
+    uint8_t seed_val = 0;
+    auto maybe_visit = [&](int new_r, int new_c, int new_id) {
+        uint8_t& val = at(new_r, new_c);
+        if (seed_val == val) {
+            val += VISITED_OFFSET;
+            curCompVis.push_back(new_id);
+            stk.push_back(new_id);
+        }
+    };
+    if (part_map_type == 0) {
+        std::vector<std::vector<int>> bestComp(num_parts);
+        std::vector<double> bestScore(num_parts, 0.0), comBest(2 * (size_t)num_parts, 0.0);
+        for (int rr = tly; rr <= bry; rr += interval) {
+            for (int cc = tlx; cc <= brx; cc += interval) {
+                const uint8_t val = at(rr, cc);
+                if (val >= VISITED_OFFSET) continue;
+                seed_val = val;
+                at(rr, cc) += VISITED_OFFSET;
+                stk.push_back((rr << 16) + cc);
+                curCompVis.clear();
+                curCompVis.push_back(stk.back());
+                double com0 = 0, com1 = 0;
+                const bool hasPrevCom = com_pre[2 * val] >= 0.;
+                while (stk.size()) {
+                    const int id = stk.back();
+                    const int cur_c = (id & lo_mask), cur_r = (id >> 16);
+                    stk.pop_back();
+                    if (cur_r >= tly + interval) maybe_visit(cur_r - interval, cur_c, id - hi_bit);
+                    if (cur_r <= bry - interval) maybe_visit(cur_r + 1, cur_c, id + hi_bit);
+                    if (cur_c >= tlx + interval) maybe_visit(cur_r, cur_c - interval, id - interval);
+                    if (cur_c <= brx - interval) maybe_visit(cur_r, cur_c + interval, id + interval);
+                    com0 += cur_c;
+                    com1 += cur_r;
+                }
+                double score = (double)curCompVis.size();
+                com0 /= curCompVis.size();
+                com1 /= curCompVis.size();
+                if (hasPrevCom) {
+                    const double d0 = com0 - com_pre[2 * val], d1 = com1 - com_pre[2 * val + 1];
+                    score -= (d0 * d0 + d1 * d1) * dist_to_pre_weight;
+                }
+                if (score > bestScore[val]) {
+                    bestScore[val] = score;
+                    comBest[2 * val] = com0;
+                    comBest[2 * val + 1] = com1;
+                    for (int id : bestComp[val]) at(id >> 16, id & lo_mask) = 255;
+                    bestComp[val].swap(curCompVis);
+                } else {
+                    for (int id : curCompVis) at(id >> 16, id & lo_mask) = 255;
+                }
+            }
+        }
+        for (int i = 0; i < num_parts; ++i) {
+            if (bestComp[i].empty()) {
+                com_pre[2 * i] = -1.;
+            } else {
+                com_pre[2 * i] = comBest[2 * i];
+                com_pre[2 * i + 1] = comBest[2 * i + 1];
+            }
+        }
+    } else {
+        const size_t scaledThresh = (size_t)(height * width / (interval * interval) * 0.0005);
+        for (int rr = tly; rr <= bry; rr += interval) {
+            for (int cc = tlx; cc <= brx; cc += interval) {
+                const uint8_t val = at(rr, cc);
+                if (val >= VISITED_OFFSET) continue;
+                seed_val = val;
+                at(rr, cc) += VISITED_OFFSET;
+                stk.push_back((rr << 16) + cc);
+                curCompVis.clear();
+                curCompVis.push_back(stk.back());
+                while (stk.size()) {
+                    const int id = stk.back();
+                    const int cur_c = (id & lo_mask), cur_r = (id >> 16);
+                    stk.pop_back();
+                    if (cur_r >= tly + interval) maybe_visit(cur_r - interval, cur_c, id - hi_bit);
+                    if (cur_r <= bry - interval) maybe_visit(cur_r + 1, cur_c, id + hi_bit);
+                    if (cur_c >= tlx + interval) maybe_visit(cur_r, cur_c - interval, id - interval);
+                    if (cur_c <= brx - interval) maybe_visit(cur_r, cur_c + interval, id + interval);
+                }
+                if (curCompVis.size() < scaledThresh)
+                    for (int id : curCompVis) at(id >> 16, id & lo_mask) = 255;
+            }
+        }
+    }
+    for (int r = tly; r <= bry; ++r)
+        for (int cc = tlx; cc <= brx; ++cc) {
+            uint8_t& val = at(r, cc);
+            if (val >= VISITED_OFFSET && val != 255) val -= VISITED_OFFSET;
+        }
+    if (interval > 1) {   // upscaleGrid (RTree.cpp:70-100); memset(ptr + cc, val, interval) may pass bot_right.x: clamped to the image
+        for (int rr = tly + interval; rr <= bry; rr += interval) {
+            const uint8_t* ptrRef = image + (size_t)rr * width;
+            for (int r = rr; r < rr + interval; ++r) {
+                if (r > bry) break;
+                uint8_t* ptr = image + (size_t)r * width;
+                for (int cc = tlx; cc <= brx; cc += interval) {
+                    const uint8_t v = ptrRef[cc];
+                    for (int k = 0; k < interval && cc + k < width; ++k) ptr[cc + k] = v;
+                }
+            }
+        }
+    }
+}
+
 /* RTree::predictBest on an image + upscaleGrid (see header) */
 void orc_rtree_predict(const float* depth, int width, int height, int num_nodes, const float* u, const float* v,
                        const float* thresh, const int32_t* lnode, const int32_t* rnode, const int32_t* leafid,

@@ -86,6 +86,9 @@ void orc_visibility(const orc_optimizer*, const double* cloud, uint8_t* visible)
 /* findNN(..., invert=true) (AvatarOptimizer.cpp:841-920): out idx[N] = matched model vertex or -1 */
 void orc_find_nn(const orc_optimizer*, const double* cloud, const uint8_t* visible,
                  const double* data /*3N*/, const int32_t* labels, int N, int method, int32_t* idx);
+/* RTree::postProcess (RTree.cpp:3422-3450): suppressPartNonMax / removeSmallPieces + upscaleGrid on one label image */
+void orc_rtree_postprocess(uint8_t* image, int width, int height, const int32_t* roi, int interval, int num_parts, int part_map_type,
+                           double* com_pre, double dist_to_pre_weight);
 /* exact brute-force 1-NN with nanoflann's distance arithmetic (no part structure): out[nq] = index into pts */
 void orc_brute_nn(const double* pts, int n, const double* queries, int nq, int32_t* out);
 /* One evaluation of the Ceres problem (AvatarOptimizer.cpp:283-347, 505-582, 632-639, 661-692,

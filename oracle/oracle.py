@@ -356,6 +356,19 @@ def paint_check_render(cloud, faces, vertex_part, width, height, intrin):
     return dict(depth=depth, parts=parts, faces=fids, order=order)
 
 
+def rtree_postprocess(image, roi, interval, num_parts, part_map_type=0, com_pre=None, dist_to_pre_weight=0.001):
+    """RTree::postProcess restated (orc_rtree_postprocess): returns (image uint8 [H, W], com_pre [num_parts, 2]); com_pre=None
+    is the reference's freshly resized matrix (x = -1, y = 0)"""
+    img = np.array(image, dtype=np.uint8, order="C", copy=True)
+    h, w = img.shape
+    cp = np.tile(np.array([-1.0, 0.0]), (num_parts, 1)) if com_pre is None else np.array(com_pre, dtype=np.float64, order="C", copy=True)
+    roi_a = None if roi is None else np.ascontiguousarray(roi, dtype=np.int32)
+    _lib.orc_rtree_postprocess.argtypes = [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, C.c_double]
+    _lib.orc_rtree_postprocess.restype = None
+    _lib.orc_rtree_postprocess(_p(img), w, h, _p(roi_a), int(interval), int(num_parts), int(part_map_type), _p(cp), float(dist_to_pre_weight))
+    return img, cp
+
+
 def brute_nn(points, queries):
     """exact brute-force 1-NN (nanoflann distance arithmetic, lowest index on exact ties)"""
     points, queries = _f64(points), _f64(queries)

@@ -248,3 +248,89 @@ def test_render_lambert_bit_exact(model, oracle_mod, omodel, prior_arrays):
     d = ft.render(xs[:1], 160, 144, (126.0, 80.0, 126.0, 72.0), want=("depth",))
     assert (d["depth"] > 0).sum() > 100
     ft.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# SURVEY.md 8(f)-4 finished: RTree::postProcess on the device
+# ---------------------------------------------------------------------------------------------
+def _rendered2(model, omodel, prior_arrays, seeds):
+    from harness import synth
+    depth, parts, x0s = [], [], []
+    for s in seeds:
+        rng = np.random.default_rng(1000 + s)
+        x_gt = synth.random_params(model, rng)
+        x0s.append(synth.perturbed_start(model, x_gt, rng))
+        cloud_gt, _, _ = omodel.update_x(x_gt)
+        _, _, d, p = synth.render_cloud(model, cloud_gt, prior_arrays["part_map"])
+        depth.append(d)
+        parts.append(p)
+    return np.stack(depth), np.stack(parts), np.stack(x0s)
+
+
+def _bbox2(part):
+    ys, xs = np.nonzero(part != 255)
+    return [int(xs.min()), int(ys.min()), int(xs.max()), int(ys.max())]
+
+
+def test_rtree_postprocess_bit_exact(model, oracle_mod, omodel, prior_arrays):
+    """device RTree::postProcess == the literal restatement of RTree.cpp:3422-3450 (suppressPartNonMax / removeSmallPieces
+    + upscaleGrid), images and centres of mass, bit for bit: predicted label images of rendered frames, boxes, intervals
+    1 / 2 / 3, both part-map types, fresh and carried-over comPre (two consecutive calls = two tracked frames)"""
+    from avatar_b200 import Fitter
+    from harness import synth
+    nparts = int(prior_arrays["num_parts"])
+    depth, parts, _ = _rendered2(model, omodel, prior_arrays, [0, 1, 2])
+    tree = synth.random_rtree(np.random.default_rng(23), nparts)
+    ft = Fitter(model, nparts, prior_arrays["part_map"], 3, 3 * 40000)
+    ft.set_rtree(tree, nparts)
+    boxes = [_bbox2(parts[0]), _bbox2(parts[1]), _bbox2(parts[2])]
+    for roi, interval in [(None, 1), (boxes, 2), (boxes, 3), (None, 2), (boxes, 1)]:
+        labels = ft.rtree_predict(depth, roi, interval, True)
+        assert (labels != 255).sum() > 3000
+        for pmt in (0, 1):
+            got, gcp = ft.rtree_postprocess(labels, roi, interval, nparts, pmt, None, 0.001)
+            got2, gcp2 = ft.rtree_postprocess(labels[::-1], None if roi is None else roi[::-1], interval, nparts, pmt, gcp, 0.001)   # "next frame"
+            for b in range(3):
+                want, wcp = oracle_mod.rtree_postprocess(labels[b], None if roi is None else roi[b], interval, nparts, pmt, None, 0.001)
+                assert np.array_equal(got[b], want), (interval, pmt, b, int((got[b] != want).sum()))
+                if pmt == 0:
+                    assert np.array_equal(gcp[b], wcp)
+                    assert (wcp[:, 0] >= 0).sum() >= 3
+                want2, wcp2 = oracle_mod.rtree_postprocess(labels[2 - b], None if roi is None else roi[2 - b], interval, nparts, pmt, gcp[b], 0.001)
+                assert np.array_equal(got2[b], want2), ("carried comPre", interval, pmt, b)
+                if pmt == 0:
+                    assert np.array_equal(gcp2[b], wcp2)
+            if pmt == 0:
+                assert (got != 255).sum() < (labels != 255).sum()      # something was suppressed
+    # ground-truth part masks (contiguous parts by construction): interval 1
+    got, gcp = ft.rtree_postprocess(parts, boxes, 1, nparts, 0, None, 0.001)
+    for b in range(3):
+        want, wcp = oracle_mod.rtree_postprocess(parts[b], boxes[b], 1, nparts, 0, None, 0.001)
+        assert np.array_equal(got[b], want) and np.array_equal(gcp[b], wcp)
+    ft.close()
+
+
+def test_depth_to_fit_pipeline_with_postprocess(model, oracle_mod, omodel, prior_arrays):
+    """the full front end of demo.cpp:195-250 on the device: depth -> RTree::predictBest -> RTree::postProcess (comPre carried
+    from call to call) -> data cloud, equal to the host chain of the three oracle restatements, over two calls"""
+    from avatar_b200 import Fitter
+    from harness import synth
+    nparts = int(prior_arrays["num_parts"])
+    intrin = (synth.FX, synth.CX, synth.FY, synth.CY)
+    depth, parts, x0 = _rendered2(model, omodel, prior_arrays, [0, 1])
+    tree = synth.random_rtree(np.random.default_rng(22), nparts)
+    boxes = [_bbox2(parts[0]), _bbox2(parts[1])]
+    ft = Fitter(model, nparts, prior_arrays["part_map"], 2, 2 * 40000)
+    ft.set_rtree(tree, nparts)
+    cps = [None, None]
+    for call in range(2):
+        off = ft.upload_depth(depth, None, intrin, nparts, roi=boxes, interval=1, rtree_interval=2, postprocess=True)
+        pts, lab, _ = ft.download_batch()
+        for b in range(2):
+            img = oracle_mod.rtree_predict(depth[b], tree, boxes[b], 2, True)
+            img, cps[b] = oracle_mod.rtree_postprocess(img, boxes[b], 2, nparts, 0, cps[b], 0.001)
+            hp, hl = oracle_mod.build_cloud(depth[b], img, intrin, nparts, boxes[b], 1)
+            assert np.array_equal(pts[off[b]:off[b + 1]], hp), (call, b)
+            assert np.array_equal(lab[off[b]:off[b + 1]], hl), (call, b)
+        assert off[2] > 100
+    ft.close()

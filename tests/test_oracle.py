@@ -589,3 +589,108 @@ def test_render_lambert_rank_form_oracle_and_reference_painter(oracle_mod, model
         if g3 is None:
             pytest.skip("oracle/_ref/libref_painters.so not built (reference tree absent)")
         assert np.array_equal(gray, g3), int((gray != g3).sum())
+
+
+# ---------------------------------------------------------------------------------------------
+# SURVEY.md 8(f)-4 finished in round 2: RTree::postProcess (RTree.cpp:3422-3450)
+# ---------------------------------------------------------------------------------------------
+def _py_postprocess(image, roi, interval, num_parts, part_map_type, com_pre, w_dist):
+    """independent pure-Python restatement of suppressPartNonMax / removeSmallPieces + upscaleGrid (small cases only)"""
+    img = image.astype(np.int64).copy()
+    H, W = img.shape
+    x0, y0, x1, y1 = (0, 0, W - 1, H - 1) if roi is None else roi
+    com_pre = np.array(com_pre, dtype=np.float64)
+    best = [None] * num_parts
+    best_score = [0.0] * num_parts
+    com_best = np.zeros((num_parts, 2))
+    thresh = int(H * W // (interval * interval) * 0.0005)
+    for rr in range(y0, y1 + 1, interval):
+        for cc in range(x0, x1 + 1, interval):
+            val = img[rr, cc]
+            if val >= 128:
+                continue
+            img[rr, cc] += 128
+            stack, comp = [(rr, cc)], [(rr, cc)]
+            sx = sy = 0.0
+            has_prev = com_pre[val, 0] >= 0
+            while stack:
+                r, c = stack.pop()
+                for ok, pr, pc, nid in ((r >= y0 + interval, r - interval, c, (r - interval, c)),
+                                        (r <= y1 - interval, r + 1, c, (r + interval, c)),     # the reference's quirk
+                                        (c >= x0 + interval, r, c - interval, (r, c - interval)),
+                                        (c <= x1 - interval, r, c + interval, (r, c + interval))):
+                    if ok and img[pr, pc] == val:
+                        img[pr, pc] += 128
+                        comp.append(nid)
+                        stack.append(nid)
+                sx += c
+                sy += r
+            if part_map_type == 0:
+                score = float(len(comp))
+                cx, cy = sx / len(comp), sy / len(comp)
+                if has_prev:
+                    score -= ((cx - com_pre[val, 0]) ** 2 + (cy - com_pre[val, 1]) ** 2) * w_dist
+                if score > best_score[val]:
+                    best_score[val] = score
+                    com_best[val] = (cx, cy)
+                    for (r, c) in (best[val] or []):
+                        img[r, c] = 255
+                    best[val] = comp
+                else:
+                    for (r, c) in comp:
+                        img[r, c] = 255
+            elif len(comp) < thresh:
+                for (r, c) in comp:
+                    img[r, c] = 255
+    if part_map_type == 0:
+        for i in range(num_parts):
+            if not best[i]:
+                com_pre[i, 0] = -1.0
+            else:
+                com_pre[i] = com_best[i]
+    sub = img[y0:y1 + 1, x0:x1 + 1]
+    sub[(sub >= 128) & (sub != 255)] -= 128
+    if interval > 1:
+        for rr in range(y0 + interval, y1 + 1, interval):
+            for r in range(rr, min(rr + interval, y1 + 1)):
+                for cc in range(x0, x1 + 1, interval):
+                    img[r, cc:min(cc + interval, W)] = img[rr, cc]
+    return img.astype(np.uint8), com_pre
+
+
+def test_rtree_postprocess_oracle_small_cases(oracle_mod):
+    """orc_rtree_postprocess against an independent pure-Python restatement (random label images, boxes, intervals 1-3,
+    both part-map types, with and without a previous centre of mass) and, for interval 1, against scipy's connected
+    components (the best blob per label is the largest 4-connected one, first in raster order on ties)"""
+    from scipy import ndimage
+    rng = np.random.default_rng(9)
+    nparts = 5
+    for trial in range(24):
+        H, W = int(rng.integers(12, 40)), int(rng.integers(12, 48))
+        interval = int(rng.integers(1, 4))
+        img = np.full((H, W), 255, np.uint8)
+        lab = rng.integers(0, nparts, (H, W)).astype(np.uint8)
+        blobs = ndimage.uniform_filter(rng.random((H, W)), 5) > 0.48
+        img[blobs] = lab[blobs]
+        if interval > 1:   # as after predictBest with gap filling: labels constant over interval x interval cells
+            g = img[::interval, ::interval]
+            img = np.kron(g, np.ones((interval, interval), np.uint8))[:H, :W].copy()
+            img[:interval] = 255   # the first row of the box is never predicted
+        roi = None if trial % 3 == 0 else [int(rng.integers(0, 4)), int(rng.integers(0, 4)), W - 1 - int(rng.integers(0, 4)), H - 1 - int(rng.integers(0, 4))]
+        cp = None if trial % 2 == 0 else np.column_stack([rng.uniform(-1, W, nparts), rng.uniform(0, H, nparts)])
+        for pmt in (0, 1):
+            got, gcp = oracle_mod.rtree_postprocess(img, roi, interval, nparts, pmt, cp, 0.01)
+            want, wcp = _py_postprocess(img, roi, interval, nparts, pmt, np.tile([-1.0, 0.0], (nparts, 1)) if cp is None else cp, 0.01)
+            assert np.array_equal(got, want), (trial, interval, pmt, int((got != want).sum()))
+            if pmt == 0:
+                np.testing.assert_array_equal(gcp, wcp)
+        if interval == 1 and roi is None and cp is None:
+            got, gcp = oracle_mod.rtree_postprocess(img, None, 1, nparts, 0, None, 0.0)
+            for p in range(nparts):
+                lbl, n = ndimage.label(img == p)
+                if n == 0:
+                    assert not (got == p).any() and gcp[p, 0] == -1.0
+                    continue
+                sizes = ndimage.sum(img == p, lbl, range(1, n + 1))
+                keep = int(np.argmax(sizes)) + 1          # first maximum = first in raster order of its first pixel
+                assert np.array_equal(got == p, lbl == keep)
