@@ -3,7 +3,9 @@
 #include "../../include/ark_b200/AvatarOptimizer.h"
 #include "../../include/ark_b200/npz.h"
 #include "../../include/ark_b200/RTree.h"
+#include "../../include/ark_b200/AvatarRenderer.h"
 #include "../../include/avatar_b200.h"
+#include <random>
 
 #include <algorithm>
 #include <cmath>
@@ -267,6 +269,217 @@ void AvatarOptimizer::optimize(const Eigen::Matrix<double, 3, Eigen::Dynamic>& d
 }
 }  // namespace ark
 
+// ---- Avatar::randomize / alignToJoints, GaussianMixture::sample (host-side utilities of the reference's callers) ---------------
+namespace ark {
+namespace {
+// dense lower Cholesky of a small SPD matrix (Eigen::LLT in the reference, GaussianMixture.cpp:44-63)
+std::vector<double> chol_lower_dense(const Eigen::MatrixXd& A) {
+    const long n = A.rows();
+    std::vector<double> L((size_t)n * n, 0.0);
+    for (long j = 0; j < n; ++j) {
+        double d = A(j, j);
+        for (long k = 0; k < j; ++k) d -= L[j * n + k] * L[j * n + k];
+        if (!(d > 0.0)) throw std::runtime_error("Decomposition failed!");
+        d = std::sqrt(d);
+        L[j * n + j] = d;
+        for (long i = j + 1; i < n; ++i) {
+            double acc = A(i, j);
+            for (long k = 0; k < j; ++k) acc -= L[i * n + k] * L[j * n + k];
+            L[i * n + j] = acc / d;
+        }
+    }
+    return L;
+}
+void axis_angle_to_rot(const double* aa, Eigen::Matrix3d& R) {   // AngleAxisd(angle, axis).toRotationMatrix()
+    const double ang = std::sqrt(aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2]);
+    if (ang == 0.0) { R.setIdentity(); return; }
+    const double x = aa[0] / ang, y = aa[1] / ang, z = aa[2] / ang, c = std::cos(ang), sn = std::sin(ang), t = 1.0 - c;
+    R(0, 0) = t * x * x + c;      R(0, 1) = t * x * y - sn * z; R(0, 2) = t * x * z + sn * y;
+    R(1, 0) = t * x * y + sn * z; R(1, 1) = t * y * y + c;      R(1, 2) = t * y * z - sn * x;
+    R(2, 0) = t * x * z - sn * y; R(2, 1) = t * y * z + sn * x; R(2, 2) = t * z * z + c;
+}
+void mat3_mul(const Eigen::Matrix3d& A, const Eigen::Matrix3d& B, Eigen::Matrix3d& C) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) C(i, j) = A(i, 0) * B(0, j) + A(i, 1) * B(1, j) + A(i, 2) * B(2, j);
+}
+// Eigen::Quaterniond::FromTwoVectors(a, b).toRotationMatrix(): the shortest rotation taking a to b
+void rot_from_two_vectors(const double* a, const double* b, Eigen::Matrix3d& R) {
+    const double na = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]), nb = std::sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+    double v0[3] = {a[0] / na, a[1] / na, a[2] / na}, v1[3] = {b[0] / nb, b[1] / nb, b[2] / nb};
+    const double c = v0[0] * v1[0] + v0[1] * v1[1] + v0[2] * v1[2];
+    double q[4];   // x y z w
+    if (c < -1.0 + 1e-12) {   // opposite vectors: any axis orthogonal to v0 (Eigen takes it from an SVD; same rotation angle pi)
+        double ax[3] = {0, -v0[2], v0[1]};
+        if (std::fabs(v0[0]) > 0.9) { ax[0] = -v0[2]; ax[1] = 0; ax[2] = v0[0]; }
+        const double n = std::sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+        q[0] = ax[0] / n; q[1] = ax[1] / n; q[2] = ax[2] / n; q[3] = 0.0;
+    } else {
+        const double axis[3] = {v0[1] * v1[2] - v0[2] * v1[1], v0[2] * v1[0] - v0[0] * v1[2], v0[0] * v1[1] - v0[1] * v1[0]};
+        const double s = std::sqrt((1.0 + c) * 2.0), invs = 1.0 / s;
+        q[0] = axis[0] * invs; q[1] = axis[1] * invs; q[2] = axis[2] * invs; q[3] = s * 0.5;
+    }
+    double Rm[9];
+    avb_quat_to_rotmat(q, Rm);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R(i, j) = Rm[3 * i + j];
+}
+std::mt19937& facade_rng() {
+    thread_local static std::mt19937 rg(std::random_device{}());
+    return rg;
+}
+}  // namespace
+
+// GaussianMixture.cpp:116-132
+Eigen::VectorXd GaussianMixture::sample() const {
+    std::mt19937& rg = facade_rng();
+    float randf = std::uniform_real_distribution<float>(0.0f, 1.0f)(rg);
+    int component = 0;
+    for (int i = 0; i < nComps; ++i) {   // the reference keeps the LAST component whose running weight passes randf
+        randf -= (float)weight(i);
+        if (randf <= 0) component = i;
+    }
+    Eigen::VectorXd rv(nDims);
+    std::normal_distribution<float> nd(0.f, 1.f);
+    std::vector<double> z(nDims);
+    for (int i = 0; i < nDims; ++i) z[i] = nd(rg);
+    const std::vector<double> L = chol_lower_dense(cov[component]);
+    for (int i = 0; i < nDims; ++i) {     // r *= cov_cho is r^T L in the reference (row vector times lower factor)
+        double acc = 0;
+        for (int k = i; k < nDims; ++k) acc += z[k] * L[(size_t)k * nDims + i];
+        rv(i) = acc + mean(component, i);
+    }
+    return rv;
+}
+
+// Avatar.cpp:77-126
+void Avatar::randomize(bool randomize_pose, bool randomize_shape, bool randomize_root_pos_rot, uint32_t seed) {
+    thread_local static std::mt19937 rg(std::random_device{}());
+    if (~seed) rg.seed(seed);
+    auto randn = [&](float mean, float sd) { return std::normal_distribution<float>(mean, sd)(rg); };
+    auto uniform = [&](float lo, float hi) { return std::uniform_real_distribution<float>(lo, hi)(rg); };
+    if (randomize_shape)
+        for (int i = 0; i < model.numShapeKeys(); ++i) w(i) = randn(0.f, 1.f);
+    if (randomize_pose && model.hasPosePrior()) {
+        const Eigen::VectorXd samp = model.posePrior.sample();
+        for (int i = 0; i < model.numJoints() - 1; ++i) {
+            const double aa[3] = {samp(3 * i), samp(3 * i + 1), samp(3 * i + 2)};
+            axis_angle_to_rot(aa, r[i + 1]);
+        }
+    }
+    if (randomize_root_pos_rot) {
+        p(0) = uniform(-1.0f, 1.0f);
+        p(1) = uniform(-0.5f, 0.5f);
+        p(2) = uniform(2.2f, 4.5f);
+        const double angle_up = uniform((float)(-M_PI / 3.), (float)(M_PI / 3.)) + M_PI;
+        const double theta = uniform(0.f, (float)(2 * M_PI)), phi = uniform((float)(-M_PI / 2), (float)(M_PI / 2));
+        const double axis_perturb[3] = {std::sin(phi) * std::cos(theta), std::cos(phi), std::sin(phi) * std::sin(theta)};   // fromSpherical
+        const double angle_perturb = randn(0.0f, 0.2f);
+        const double up[3] = {0.0, angle_up, 0.0};
+        const double pert[3] = {axis_perturb[0] * angle_perturb, axis_perturb[1] * angle_perturb, axis_perturb[2] * angle_perturb};
+        Eigen::Matrix3d Rup, Rp;
+        axis_angle_to_rot(up, Rup);
+        axis_angle_to_rot(pert, Rp);
+        mat3_mul(Rp, Rup, r[0]);   // (aa_perturb * aa_up).toRotationMatrix()
+    }
+}
+
+// Avatar.cpp:141-193
+void Avatar::alignToJoints(const CloudType& pos) {
+    const int J = model.numJoints();
+    if (pos.cols() != J) throw std::runtime_error("alignToJoints: need one position per joint");
+    auto jp = [&](const CloudType& m, int j, double* out) { out[0] = m(0, j); out[1] = m(1, j); out[2] = m(2, j); };
+    auto sub = [](const double* a, const double* b, double* o) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; };
+    auto nrm = [](const double* a) { return std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); };
+    const int SPINE1 = 3, SPINE2 = 6, ROOT = 0;
+    double a0[3], a1[3], b0[3], b1[3], vr[3], vrt[3];
+    jp(model.initialJointPos, SPINE1, a1); jp(model.initialJointPos, ROOT, a0); sub(a1, a0, vr);
+    jp(pos, SPINE1, b1); jp(pos, ROOT, b0); sub(b1, b0, vrt);
+    if (!std::isnan(pos(0, 0))) for (int c = 0; c < 3; ++c) p(c) = pos(c, 0);
+    if (!std::isnan(vr[0]) && !std::isnan(vrt[0])) rot_from_two_vectors(vr, vrt, r[0]);
+    else r[0].setIdentity();
+    std::vector<Eigen::Matrix3d> rotTrans(J);
+    rotTrans[0] = r[0];
+    double scaleAvg = 0.0;
+    for (int i = 1; i < J; ++i) {
+        double u[3], v[3], x0[3], x1[3];
+        jp(pos, i, x1); jp(pos, model.parent(i), x0); sub(x1, x0, u);
+        jp(model.initialJointPos, i, x1); jp(model.initialJointPos, model.parent(i), x0); sub(x1, x0, v);
+        scaleAvg += nrm(u) / nrm(v);
+    }
+    scaleAvg /= (J - 1.0);
+    double s2[3], s0[3], sv[3];
+    jp(model.initialJointPos, SPINE2, s2); jp(model.initialJointPos, ROOT, s0); sub(s2, s0, sv);
+    const double baseScale = nrm(sv) * (scaleAvg - 1.0);
+    const double PC1_DIST_FACT = 32.0;
+    if (model.numShapeKeys() > 0) {
+        w(0) = baseScale * PC1_DIST_FACT;
+        if (std::isnan(w(0))) w(0) = 1.5;
+    }
+    for (int i = 1; i < J; ++i) {
+        rotTrans[i] = rotTrans[model.parent(i)];
+        if (!std::isnan(pos(0, i))) {
+            double vv[3], vvt[3], x0[3], x1[3];
+            jp(model.initialJointPos, i, x1); jp(model.initialJointPos, model.parent(i), x0); sub(x1, x0, vv);
+            jp(pos, i, x1); jp(pos, model.parent(i), x0); sub(x1, x0, vvt);
+            rot_from_two_vectors(vv, vvt, rotTrans[i]);
+            const Eigen::Matrix3d& Pm = rotTrans[model.parent(i)];
+            for (int a = 0; a < 3; ++a)      // r[i] = rotTrans[parent]^T * rotTrans[i]
+                for (int b = 0; b < 3; ++b) r[i](a, b) = Pm(0, a) * rotTrans[i](0, b) + Pm(1, a) * rotTrans[i](1, b) + Pm(2, a) * rotTrans[i](2, b);
+        } else {
+            r[i].setIdentity();
+        }
+    }
+}
+
+// ---- ark::AvatarRenderer (AvatarRenderer.cpp) over avb_render_batch / avb_render_lambert_batch ------------------------------------
+AvatarRenderer::AvatarRenderer(const Avatar& a, const CameraIntrin& in) : ava(a), intrin(in) {}
+AvatarRenderer::~AvatarRenderer() {
+    if (fitter_) avb_fitter_destroy(fitter_);
+}
+avb_fitter* AvatarRenderer::fitter(const std::vector<int>& part_map) const {
+    std::vector<int> pm = part_map;
+    if (pm.empty()) pm.assign(ava.model.numJoints(), 0);
+    if (fitter_ && pm == fitter_part_map_) return fitter_;
+    if (fitter_) avb_fitter_destroy(fitter_);
+    fitter_ = nullptr;
+    int nparts = 1;
+    for (int v : pm) nparts = std::max(nparts, v + 1);
+    std::vector<int32_t> pm32(pm.begin(), pm.end());
+    avb_fitter_config cfg{0, 1, 16, nparts, pm32.data()};
+    if (avb_fitter_create(ava.model.handle(), &cfg, &fitter_) != AVB_OK) die("avb_fitter_create");
+    fitter_part_map_ = pm;
+    return fitter_;
+}
+cv::Mat AvatarRenderer::renderDepth(const cv::Size& sz) const {
+    cv::Mat out(sz, CV_32F);
+    const std::vector<double> x = ava.packParams();
+    avb_render_desc d{sz.width, sz.height, intrin.fx, intrin.cx, intrin.fy, intrin.cy};
+    if (avb_render_batch(fitter({}), 1, x.data(), &d, out.ptr<float>(0), nullptr, nullptr) != AVB_OK) die("avb_render_batch");
+    return out;
+}
+cv::Mat AvatarRenderer::renderLambert(const cv::Size& sz) const {
+    cv::Mat out(sz, CV_8U);
+    const std::vector<double> x = ava.packParams();
+    avb_render_desc d{sz.width, sz.height, intrin.fx, intrin.cx, intrin.fy, intrin.cy};
+    if (avb_render_lambert_batch(fitter({}), 1, x.data(), &d, out.ptr<uint8_t>(0)) != AVB_OK) die("avb_render_lambert_batch");
+    return out;
+}
+cv::Mat AvatarRenderer::renderPartMask(const cv::Size& sz, const std::vector<int>& part_map) const {
+    cv::Mat out(sz, CV_8U);
+    const std::vector<double> x = ava.packParams();
+    avb_render_desc d{sz.width, sz.height, intrin.fx, intrin.cx, intrin.fy, intrin.cy};
+    if (avb_render_batch(fitter(part_map), 1, x.data(), &d, nullptr, out.ptr<uint8_t>(0), nullptr) != AVB_OK) die("avb_render_batch");
+    return out;
+}
+cv::Mat AvatarRenderer::renderFaces(const cv::Size& sz, int) const {
+    cv::Mat out(sz, CV_32S);
+    const std::vector<double> x = ava.packParams();
+    avb_render_desc d{sz.width, sz.height, intrin.fx, intrin.cx, intrin.fy, intrin.cy};
+    if (avb_render_batch(fitter({}), 1, x.data(), &d, nullptr, nullptr, out.ptr<int32_t>(0)) != AVB_OK) die("avb_render_batch");
+    return out;
+}
+}  // namespace ark
+
 // ---- ark::RTree data side (RTree.cpp:2967-3061, 3452-3510) ----------------------------------------------------------
 namespace ark {
 namespace {
@@ -395,6 +608,59 @@ void RTree::attach(avb_fitter* fitter) const {
     avb_rtree_desc d{(int32_t)nodes.size(), (int32_t)leafBestMatch.size(), numParts, u.data(), v.data(), th.data(), l.data(), r.data(),
                      id.data(), leafBestMatch.data()};
     if (avb_fitter_set_rtree(fitter, &d) != AVB_OK) die("avb_fitter_set_rtree");
+}
+
+RTree::~RTree() {
+    if (fitter_) avb_fitter_destroy(fitter_);
+    if (dummy_) avb_model_destroy(dummy_);
+}
+// the RTree kernels need no body model; the C ABI hangs them on a fitter, so the tree owns one on a one-triangle model
+avb_fitter* RTree::device(size_t pixels) const {
+    if (!dummy_) {
+        static const double base[9] = {0, 0, 1, 1, 0, 1, 0, 1, 1}, jbase[3] = {0, 0, 1}, wgt[3] = {1, 1, 1};
+        static const int32_t parent[1] = {-1}, mesh[3] = {0, 1, 2}, start[4] = {0, 1, 2, 3}, joint[3] = {0, 0, 0};
+        avb_model_desc d{};
+        d.num_points = 3; d.num_joints = 1; d.num_shape_keys = 0; d.num_faces = 1;
+        d.base_cloud = base; d.joint_shape_reg_base = jbase; d.parent = parent; d.mesh = mesh;
+        d.assign_start = start; d.assign_joint = joint; d.assign_weight = wgt;
+        if (avb_model_create(&d, &dummy_) != AVB_OK) die("avb_model_create");
+    }
+    if (!fitter_) {
+        const int32_t pm[1] = {0};
+        avb_fitter_config cfg{0, 1, (int64_t)std::max<size_t>(pixels, 1 << 20), std::max(numParts, 1), pm};
+        cfg.num_parts = 1;
+        if (avb_fitter_create(dummy_, &cfg, &fitter_) != AVB_OK) die("avb_fitter_create");
+        attached_nodes_ = 0;
+    }
+    if (attached_nodes_ != nodes.size() && !nodes.empty()) {
+        attach(fitter_);
+        attached_nodes_ = nodes.size();
+    }
+    return fitter_;
+}
+cv::Mat RTree::predictBest(const cv::Mat& depth, int, int interval, cv::Point top_left, cv::Point bot_right, bool fill_in_gaps) {
+    cv::Mat result(depth.size(), CV_8U);
+    const bool whole = bot_right.x == -1;
+    const int32_t roi[4] = {top_left.x, top_left.y, whole ? depth.cols - 1 : bot_right.x, whole ? depth.rows - 1 : bot_right.y};
+    if (avb_rtree_predict_batch(device((size_t)depth.rows * depth.cols), 1, depth.ptr<float>(0), depth.cols, depth.rows, roi, interval,
+                                fill_in_gaps ? 1 : 0, result.ptr<uint8_t>(0)) != AVB_OK)
+        die("avb_rtree_predict_batch");
+    return result;
+}
+void RTree::postProcess(cv::Mat& image, Eigen::Matrix<double, 2, Eigen::Dynamic>& com_pre, int interval, int, cv::Point top_left,
+                        cv::Point bot_right, double dist_to_pre_weight) const {
+    if (bot_right.x == -1) {
+        bot_right.x = image.cols - 1;
+        bot_right.y = image.rows - 1;
+    }
+    if (com_pre.cols() != numParts) {   // RTree.cpp:3432-3436
+        com_pre.resize(2, numParts);
+        for (int i = 0; i < numParts; ++i) { com_pre(0, i) = -1.; com_pre(1, i) = 0.; }
+    }
+    const int32_t roi[4] = {top_left.x, top_left.y, bot_right.x, bot_right.y};
+    if (avb_rtree_postprocess_batch(device((size_t)image.rows * image.cols), 1, image.ptr<uint8_t>(0), image.cols, image.rows, roi, interval,
+                                    numParts, partMapType == 0 ? 0 : 1, com_pre.data(), dist_to_pre_weight) != AVB_OK)
+        die("avb_rtree_postprocess_batch");
 }
 
 }  // namespace ark

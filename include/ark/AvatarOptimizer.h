@@ -1,0 +1,4 @@
+// include/ark/AvatarOptimizer.h -- the reference's header name (include/AvatarOptimizer.h of sxyu/avatar), forwarding to the avatar_b200 facade so that
+// a caller's `#include "AvatarOptimizer.h"` resolves with -I<repo>/include/ark.
+#pragma once
+#include "../ark_b200/AvatarOptimizer.h"

@@ -33,6 +33,8 @@ struct GaussianMixture {
     Eigen::VectorXd weight;
     Eigen::Matrix<double, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor> mean;
     std::vector<Eigen::MatrixXd> cov;
+    /** GaussianMixture.cpp:116-132: a random sample (component by weight, then mean + cov_cho * N(0, I)) */
+    Eigen::VectorXd sample() const;
 };
 
 /** include/Avatar.h:64-151 */
@@ -74,6 +76,12 @@ class Avatar {
     explicit Avatar(const AvatarModel& model);
     ~Avatar();
     void update();                                 // Avatar.cpp:22-75 on the GPU
+    /** Avatar.cpp:77-126: random shape (N(0,1) per key), pose (a sample of the pose prior) and root position / rotation */
+    void randomize(bool randomize_pose = true, bool randomize_shape = true, bool randomize_root_pos_rot = true,
+                   uint32_t seed = -1);
+    /** Avatar.cpp:141-193: root position / per-joint rotations / shape key 0 that bring the skeleton onto 3 x 24 joint
+     *  positions (NaN entries = unknown joint) */
+    void alignToJoints(const CloudType& pos);
     Eigen::VectorXd smplParams() const;            // Avatar.cpp:128-137
     const AvatarModel& model;
     CloudType cloud;

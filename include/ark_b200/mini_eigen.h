@@ -19,6 +19,7 @@ class Matrix {
     Matrix() : r_(R == Dynamic ? 0 : R), c_(C == Dynamic ? 0 : C), d_((size_t)r_ * c_, S(0)) {}
     Matrix(long r, long c) : r_(r), c_(c), d_((size_t)r * c, S(0)) {}
     explicit Matrix(long n) : r_(C == 1 ? n : (R == Dynamic ? n : R)), c_(C == 1 ? 1 : n), d_((size_t)r_ * c_, S(0)) {}
+    Matrix(S x, S y, S z) : r_(R == Dynamic ? 3 : R), c_(C == Dynamic ? 1 : C), d_((size_t)r_ * c_, S(0)) { d_[0] = x; d_[1] = y; d_[2] = z; }
     long rows() const { return r_; }
     long cols() const { return c_; }
     long size() const { return r_ * c_; }
@@ -38,6 +39,20 @@ class Matrix {
     void setIdentity() { setZero(); for (long i = 0; i < (r_ < c_ ? r_ : c_); ++i) (*this)(i, i) = S(1); }
     static Matrix Identity() { Matrix m; m.setIdentity(); return m; }
     static Matrix Zero() { return Matrix(); }
+    struct Rowwise {   // dataCloud.rowwise().mean() (demo.cpp:254)
+        const Matrix& m;
+        Matrix<S, R, 1> mean() const {
+            Matrix<S, R, 1> out(m.rows());
+            for (long i = 0; i < m.rows(); ++i) {
+                S acc = S(0);
+                for (long j = 0; j < m.cols(); ++j) acc += m(i, j);
+                out(i) = acc / (S)m.cols();
+            }
+            return out;
+        }
+    };
+    Rowwise rowwise() const { return Rowwise{*this}; }
+    void setConstant(S v) { d_.assign(d_.size(), v); }
    private:
     long r_, c_;
     std::vector<S> d_;
@@ -61,6 +76,16 @@ class Quaterniond {
     Vector4d c_;
 };
 
+/** Eigen::AngleAxisd(angle, axis).toRotationMatrix() (Rodrigues), used by demo.cpp:259-261 */
+class AngleAxisd {
+   public:
+    AngleAxisd(double angle, const Vector3d& axis) : angle_(angle), axis_(axis) {}
+    Matrix3d toRotationMatrix() const;
+   private:
+    double angle_;
+    Vector3d axis_;
+};
+
 template <class S>
 struct SparseMatrix {  // placeholder for AvatarModel::jointRegressor / weights (CSC, column = vertex)
     long rows_ = 0, cols_ = 0;
@@ -71,10 +96,15 @@ struct SparseMatrix {  // placeholder for AvatarModel::jointRegressor / weights 
 };
 }  // namespace Eigen
 
-namespace cv {
-struct Size {
-    int width = 0, height = 0;
-    Size() {}
-    Size(int w, int h) : width(w), height(h) {}
-};
-}  // namespace cv
+inline Eigen::Matrix3d Eigen::AngleAxisd::toRotationMatrix() const {
+    Matrix3d R;
+    const double c = __builtin_cos(angle_), s = __builtin_sin(angle_), t = 1.0 - c;
+    const double x = axis_(0), y = axis_(1), z = axis_(2);
+    R(0, 0) = t * x * x + c;     R(0, 1) = t * x * y - s * z; R(0, 2) = t * x * z + s * y;
+    R(1, 0) = t * x * y + s * z; R(1, 1) = t * y * y + c;     R(1, 2) = t * y * z - s * x;
+    R(2, 0) = t * x * z - s * y; R(2, 1) = t * y * z + s * x; R(2, 2) = t * z * z + c;
+    return R;
+}
+
+#include "mini_cv.h"
+

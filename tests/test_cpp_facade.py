@@ -120,3 +120,90 @@ def test_facade_camera_intrin_matches_the_reference(build_all, tmp_path):
     assert list(a2) == list(b)
     assert open(out_a).read() == open(out_b).read()
     assert ref.ref_intrin_probe(str(incomplete).encode(), None, b) == 1
+
+
+# ---------------------------------------------------------------------------------------------
+# the fit section of the reference's own demo.cpp against the facade (VERDICT r1 "make the boundary claim true")
+# ---------------------------------------------------------------------------------------------
+SECTION = os.path.join(ROOT, "tests", "cpp", "demo_section")
+
+
+def test_reference_demo_fit_section_compiles_against_the_facade(build_all):
+    """tools/extract_demo_section.py cuts demo.cpp:195-294 (predictBest -> postProcess -> data cloud -> re-initialisation ->
+    optimize -> renderLambert) out of /root/reference at build time and `make facade` compiles it UNCHANGED against
+    include/ark/{Avatar,AvatarOptimizer,AvatarRenderer,RTree,Calibration,Util}.h and links it with libark_b200.so"""
+    if not os.path.exists("/root/reference/demo.cpp"):
+        pytest.skip("reference tree absent (GPU box): the binary was built where the reference is")
+    gen = os.path.join(ROOT, "tests", "cpp", "_gen", "demo_fit_section.cpp")
+    assert os.path.exists(gen) and os.path.exists(SECTION)
+    src = open(gen).read()
+    ref = open("/root/reference/demo.cpp").read()
+    body = src.split("    {\n", 1)[1].rsplit("        }   // closes", 1)[0]
+    assert body.strip() and body in ref                         # verbatim reference text, not a paraphrase
+    for needle in ("rtree.predictBest(depth", "rtree.postProcess(result, comPre, 2", "avaOpt.optimize(dataCloud, dataPartLabels, icpIters",
+                   "rend.renderLambert(depth.size())", "dataCloud.rowwise().mean()"):
+        assert needle in body
+
+
+@pytest.mark.gpu
+def test_reference_demo_fit_section_runs_and_matches_the_oracle_chain(model_dir, model, oracle_mod, omodel, prior_arrays, tmp_path):
+    """the compiled reference fit section on one rendered frame (two calls = re-initialisation frame + tracked frame) against
+    the same chain of oracle restatements: RTree labels -> postProcess -> strided cloud -> reinit -> optimize"""
+    if not os.path.exists(SECTION):
+        pytest.skip("tests/cpp/demo_section not built (reference tree absent at build time)")
+    from avatar_b200 import rtree
+    from harness import synth
+    nparts, J = int(prior_arrays["num_parts"]), 24
+    rng = np.random.default_rng(1000)
+    x_gt = synth.random_params(model, rng)
+    cloud_gt, _, _ = omodel.update_x(x_gt)
+    _, _, depth, parts = synth.render_cloud(model, cloud_gt, prior_arrays["part_map"])
+    tree = synth.random_rtree(np.random.default_rng(5), nparts)
+    leaf_data = np.zeros((len(tree["leaf_best"]), nparts), np.float32)
+    leaf_data[np.arange(len(tree["leaf_best"])), tree["leaf_best"]] = 1.0
+    tpath = str(tmp_path / "tree.srtr")
+    rtree.save_rtree(tpath, tree, leaf_data)
+    with open(tpath + ".partmap", "w") as fh:     # joint -> part, 'contiguous' (partMapType 0)
+        fh.write("partmap contiguous\nsrc %d %s\ndest %d %s\n" % (J, " ".join(f"j{i}" for i in range(J)), nparts,
+                                                                   " ".join(f"p{i}" for i in range(nparts))))
+        for j in range(J):
+            fh.write(f"j{j} p{int(prior_arrays['part_map'][j])}\n")
+    ys, xs = np.nonzero(parts != 255)
+    box = [int(xs.min()), int(ys.min()), int(xs.max()), int(ys.max())]
+    interval, icp = 4, 2
+    intrin = (synth.FX, synth.CX, synth.FY, synth.CY)
+    fpath = str(tmp_path / "frame.bin")
+    with open(fpath, "wb") as fh:
+        fh.write(struct.pack("<8i", synth.WIDTH, synth.HEIGHT, *box, interval, icp))
+        fh.write(struct.pack("<4f", *intrin))
+        fh.write(np.ascontiguousarray(depth, dtype="<f4").tobytes())
+    out = subprocess.run([SECTION, model_dir, tpath, fpath, "2"], capture_output=True, text=True, check=True).stdout
+    got = [np.array([float(v) for v in l.split()[1:]]) for l in out.splitlines() if l.startswith("PARAMS")]
+    lit = [int(l.split()[2]) for l in out.splitlines() if l.startswith("OVERLAY")]
+    assert len(got) == 2 and min(lit) > 2000
+    # ---- the oracle chain ----
+    oopt = oracle_mod.OracleOptimizer(omodel, nparts, prior_arrays["part_map"])
+    x = np.zeros(3 + 4 * J + 10)
+    x[6::4][:J] = 1.0                                   # identity quaternions (x y z w)
+    com = None
+    for t in range(2):
+        lab_img = oracle_mod.rtree_predict(depth, tree, box, 2, True)
+        lab_img, com = oracle_mod.rtree_postprocess(lab_img, box, 2, nparts, 0, com, 0.001)
+        pts, lab = oracle_mod.build_cloud(depth, lab_img, intrin, nparts, box, interval)
+        iters = icp
+        if t == 0:                                      # demo.cpp:253-265: re-initialisation
+            x[:3] = pts.mean(axis=0)
+            x[3:3 + 4 * J] = np.tile([0.0, 0.0, 0.0, 1.0], J)
+            x[3:7] = oracle_mod.rotmat_to_quat(np.diag([-1.0, 1.0, -1.0]))   # AngleAxis(pi, y)
+            x[3 + 4 * J:] = 0.0
+            iters = icp + 2
+        oo = oracle_mod.default_options(oracle_mod.SOLVER_GN_LM)
+        oo.icp_iters = iters
+        x, st, _, _ = oopt.optimize(pts, lab, x, oo)
+        for j in range(J):      # the facade keeps rotation matrices between calls: quaternions come back canonical (w >= 0)
+            x[3 + 4 * j:7 + 4 * j] = oracle_mod.rotmat_to_quat(oracle_mod.quat_to_rotmat(x[3 + 4 * j:7 + 4 * j]))
+        # a wiring test, not a numerics test: the fit starts from the re-initialisation pose (identity joints at the cloud
+        # centroid), 4 + 2 ICP rounds away from the answer, and the last bits of the start (summation order of the centroid,
+        # sin(pi) in the root rotation) move discrete correspondences; the stated 1e-4 parity is tested from identical
+        # starts elsewhere (test_gpu_parity.py, test_gpu_round2.py)
+        assert np.abs(got[t] - x).max() < 2e-3, (t, np.abs(got[t] - x).max())
