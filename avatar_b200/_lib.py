@@ -97,6 +97,9 @@ SYMBOLS = [
     ("avb_render_lambert_batch", C.c_int, [_P, C.c_int32, _P, C.POINTER(RenderDesc), _P]),
     ("avb_download_results", C.c_int, [_P, _P, _P, _P]),
     ("avb_synchronize", C.c_int, [_P]),
+    ("avb_comm_unique_id", C.c_int, [_P]),
+    ("avb_fitter_comm_init", C.c_int, [_P, _P, C.c_int32, C.c_int32]),
+    ("avb_gather_params", C.c_int, [_P, _P]),
     ("avb_last_device_ms", C.c_int, [_P, C.POINTER(C.c_float), _P]),
     ("avb_timer_start", C.c_int, [_P]),
     ("avb_timer_stop", C.c_int, [_P, C.POINTER(C.c_float)]),

@@ -7,6 +7,8 @@
 #include "../../include/avatar_b200.h"
 #include "avb_kernels.h"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -60,6 +62,41 @@ cudaError_t dev_upload(T** dst, const std::vector<T>& src) {
     if (e != cudaSuccess) return e;
     if (!src.empty()) e = cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
     return e;
+}
+}  // namespace
+
+namespace {
+// NCCL is loaded at run time (libnccl.so.2: the system library, or the one a host framework already mapped), so that
+// single-GPU users of libavatar_b200.so need no NCCL at all.
+struct NcclApi {
+    typedef struct { char internal[128]; } UniqueId;
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+            api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+            api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(h, "ncclAllGather"));
+            api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+            api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+            api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy;
+        }
+    }
+    return api;
+}
+int nccl_fail(const char* what, int rc) {
+    return fail(AVB_ERR_CUDA, std::string(what) + ": " + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "NCCL error"));
 }
 }  // namespace
 
@@ -146,6 +183,9 @@ struct avb_fitter {
     double* d_xseq = nullptr; FrameStats* d_stats_seq = nullptr; int seq_cap = 0;
     FrameStats* h_stats_seq = nullptr; double* h_xseq = nullptr;
     int last_icp = 0;
+    // multi-GPU: NCCL communicator of this fitter (avb_fitter_comm_init) and the all-gather buffers
+    void* nccl_comm = nullptr; int comm_rank = 0, comm_size = 1;
+    double* d_gather = nullptr; double* h_gather = nullptr;
 };
 
 namespace {
@@ -523,6 +563,7 @@ void avb_fitter_destroy(avb_fitter* ft) {
     if (!ft) return;
     cudaSetDevice(ft->device);
     if (ft->stream) cudaStreamSynchronize(ft->stream);
+    if (ft->nccl_comm && nccl().ok) nccl().CommDestroy(ft->nccl_comm);
     for (void* p : ft->allocs) cudaFree(p);
     for (void* p : ft->pinned) cudaFreeHost(p);
     for (auto& e : ft->ev)
@@ -1384,6 +1425,47 @@ int avb_fit_resident(avb_fitter* ft, const double* x_in, const avb_options* o) {
     }
     ++ft->launches;
     CUDA_TRY(cudaEventRecord(ft->ev[5], st));
+    return AVB_OK;
+}
+
+/* ---------------- multi-GPU entry points: one NCCL all-gather of the fitted parameters ---------------- */
+int avb_comm_unique_id(uint8_t* id128) {
+    if (!id128) return fail(AVB_ERR_INVALID, "null argument");
+    if (!nccl().ok) return fail(AVB_ERR_CUDA, "libnccl.so.2 could not be loaded: the multi-GPU entry points need NCCL");
+    NcclApi::UniqueId id;
+    const int rc = nccl().GetUniqueId(&id);
+    if (rc != 0) return nccl_fail("ncclGetUniqueId", rc);
+    std::memcpy(id128, id.internal, 128);
+    return AVB_OK;
+}
+
+int avb_fitter_comm_init(avb_fitter* ft, const uint8_t* id128, int32_t rank, int32_t nranks) {
+    if (!ft || !id128 || nranks <= 0 || rank < 0 || rank >= nranks) return fail(AVB_ERR_INVALID, "bad communicator arguments");
+    if (!nccl().ok) return fail(AVB_ERR_CUDA, "libnccl.so.2 could not be loaded: the multi-GPU entry points need NCCL");
+    if (ft->nccl_comm) return fail(AVB_ERR_INVALID, "the fitter already has a communicator");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    NcclApi::UniqueId id;
+    std::memcpy(id.internal, id128, 128);
+    const int rc = nccl().CommInitRank(&ft->nccl_comm, nranks, id, rank);
+    if (rc != 0) return nccl_fail("ncclCommInitRank", rc);
+    ft->comm_rank = rank;
+    ft->comm_size = nranks;
+    const size_t n = (size_t)nranks * ft->max_batch * ft->model->nx;
+    int r2 = dev_alloc(ft, &ft->d_gather, n);
+    if (r2 == AVB_OK) r2 = pin_alloc(ft, &ft->h_gather, n);
+    return r2;
+}
+
+int avb_gather_params(avb_fitter* ft, double* all_x) {
+    if (!ft || !all_x) return fail(AVB_ERR_INVALID, "null argument");
+    if (!ft->nccl_comm) return fail(AVB_ERR_INVALID, "no communicator: call avb_fitter_comm_init first");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    const size_t per = (size_t)ft->max_batch * ft->model->nx;
+    const int rc = nccl().AllGather(ft->d_x, ft->d_gather, per, /*ncclFloat64*/ 8, ft->nccl_comm, ft->stream);
+    if (rc != 0) return nccl_fail("ncclAllGather", rc);
+    CUDA_TRY(cudaMemcpyAsync(ft->h_gather, ft->d_gather, per * ft->comm_size * 8, cudaMemcpyDeviceToHost, ft->stream));
+    CUDA_TRY(cudaStreamSynchronize(ft->stream));
+    std::memcpy(all_x, ft->h_gather, per * ft->comm_size * 8);
     return AVB_OK;
 }
 

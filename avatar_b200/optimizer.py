@@ -273,6 +273,18 @@ class Fitter:
         check(lib.avb_timer_stop(self.handle, C.byref(ms)))
         return ms.value
 
+    def comm_init(self, unique_id, rank, nranks):
+        """join the NCCL communicator described by the 128-byte id of avatar_b200.shard.comm_unique_id()"""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        check(lib.avb_fitter_comm_init(self.handle, buf, int(rank), int(nranks)))
+        self.nranks = int(nranks)
+
+    def gather_params(self):
+        """ncclAllGather of the device parameter blocks of the last fit -> [nranks, max_batch, nx] (host)"""
+        out = np.zeros((self.nranks, self.max_batch, self.nx))
+        check(lib.avb_gather_params(self.handle, ptr(out)))
+        return out
+
     def synchronize(self):
         check(lib.avb_synchronize(self.handle))
 

@@ -30,6 +30,15 @@ def gather_params(local, n_frames, rank, world, device=None):
     return np.concatenate(rows, axis=0)
 
 
+def comm_unique_id():
+    """a fresh 128-byte NCCL id (rank 0 makes it, the others get it through whatever the launcher offers)"""
+    import ctypes as C
+    from ._lib import lib, check
+    buf = (C.c_uint8 * 128)()
+    check(lib.avb_comm_unique_id(buf))
+    return bytes(buf)
+
+
 class ParamGatherer:
     """The per-step gather of the fitted parameters with everything allocated ONCE: a pinned host staging buffer, one
     device send buffer, one device receive buffer for all_gather_into_tensor and one pinned host copy of the result

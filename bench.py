@@ -310,11 +310,19 @@ def main():
     # from all lanes (and gathers them over the ranks) before it accepts step s + 1.
     import queue
 
+    # multi-GPU: the parameter gather goes through the C ABI (avb_gather_params: one ncclAllGather per lane straight from the
+    # device parameter block on the lane's stream, no host staging of the input, nothing allocated per step)
+    if world > 1:
+        ids = [shard.comm_unique_id() for _ in lanes] if rank == 0 else [None] * len(lanes)
+        dist.broadcast_object_list(ids, src=0)
+        for ln, uid in zip(lanes, ids):
+            ln["ft"].comm_init(uid, rank, world)
+
     def lane_worker(ln, nsteps, out_q):
         for _ in range(nsteps):
             h_x[ln["lo"]:ln["hi"]] = ln["x0"]
             x, st, _ = ln["ft"].fit_batch(ln["pts"], ln["lab"], ln["off"], h_x[ln["lo"]:ln["hi"]], opt)
-            out_q.put(x)
+            out_q.put(ln["ft"].gather_params() if world > 1 else x)
 
     def e2e_run(nsteps):
         qs = [queue.Queue() for _ in lanes]
@@ -323,8 +331,11 @@ def main():
             t.start()
         full = None
         for _ in range(nsteps):
-            x = np.concatenate([q.get() for q in qs])
-            full = gatherer.gather(x) if world > 1 else x
+            got = [q.get() for q in qs]
+            if world > 1:   # [lane][rank][lane batch capacity][nx] -> frames in global order (rank-major, lanes in order)
+                full = np.concatenate([got[l][r][:lanes[l]["hi"] - lanes[l]["lo"]] for r in range(world) for l in range(len(lanes))])
+            else:
+                full = np.concatenate(got)
         for t in ths:
             t.join()
         return full

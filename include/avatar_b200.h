@@ -250,6 +250,19 @@ int avb_rtree_reset_tracking(avb_fitter* fitter);
 
 /* device time (ms) of the last RTree prediction (predict + gap filling kernels) */
 int avb_last_rtree_ms(avb_fitter* fitter, float* ms);
+/* Multi-GPU: frames are independent, so a batch shards as one block of frames per rank (one process
+ * or thread per GPU, one fitter each) with NO collective on the data path, and ONE all-gather of the fitted parameters at the
+ * end.  These three entry points are that gather for callers in the reference's host language (no Python, no
+ * torch.distributed): NCCL is loaded at run time (libnccl.so.2).
+ *   avb_comm_unique_id    rank 0 creates the 128-byte NCCL id and hands it to the other ranks by its own means
+ *   avb_fitter_comm_init  every rank: ncclCommInitRank on the fitter's device
+ *   avb_gather_params     ncclAllGather straight from the device parameter block of the last fit (no host staging of the
+ *                         input, no allocation), on the fitter's stream; all_x is host [nranks][max_batch][nx] -- rank r's
+ *                         frames are rows [r * max_batch, r * max_batch + its batch) */
+int avb_comm_unique_id(uint8_t* id128);
+int avb_fitter_comm_init(avb_fitter* fitter, const uint8_t* id128, int32_t rank, int32_t nranks);
+int avb_gather_params(avb_fitter* fitter, double* all_x);
+
 /* device time (ms) of [cloud_count_kernel, cloud_compact_kernel] of the last avb_upload_depth_batch (CUDA events) */
 int avb_last_cloud_ms(avb_fitter* fitter, float* ms2);
 int avb_download_results(avb_fitter* fitter, double* x_out, avb_stats* stats, double* cloud_out);
