@@ -136,11 +136,12 @@ struct avb_fitter {
     double *d_xt = nullptr, *d_tab = nullptr, *d_part = nullptr, *d_cpart = nullptr, *d_gcur = nullptr;
     unsigned short* d_mlist = nullptr; int4* d_chunks = nullptr; int2* d_gruns = nullptr; LmState* d_state = nullptr;
     float* d_rec = nullptr; int* d_gstart = nullptr; int maxrb = 0, rec_stride = 0, rec_rs = 0;
-    int maxc = 0, tabD = 0, max_nj = 0, chunk_verts = 256;
+    int maxc = 0, tabD = 0, max_nj = 0, chunk_verts = 192;
     long long pstride = 0;
     // lm_flow_kernel work queue
     unsigned long long* d_qslots = nullptr; unsigned int* d_qctrl = nullptr; int *d_rows_left = nullptr, *d_gram_left = nullptr;
     unsigned long long* d_qprof = nullptr; unsigned int qcap = 0; bool use_flow = true;
+    int flow_occ_default[2] = {3, 2};   // CTAs per SM of the flow kernel: [fp64 path, tensor path] (measured best)
     unsigned int* h_qctrl = nullptr;
     std::vector<int> group_nj, group_nv;   // Jacobian column groups: joints and model vertices per group
     int *d_chunk_frame = nullptr, *d_chunk_count = nullptr, *d_chunk_qblock = nullptr, *d_frame_qblock = nullptr;
@@ -668,12 +669,13 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     TRY(dev_put(ft, &dm.gmm_prec, m->gmm_prec));
     TRY(dev_put(ft, &dm.gmm_clog, m->gmm_clog));
     {
-        const size_t PP = (size_t)m->P * m->P;
+        const size_t PT = (size_t)m->P * (m->P + 1) / 2;   // packed lower triangle, row major (the solve's storage)
         const int D = m->gmmD;
-        std::vector<double> pfull((size_t)std::max(m->gmmC, 1) * PP, 0.0);
+        std::vector<double> pfull((size_t)std::max(m->gmmC, 1) * PT, 0.0);
         for (int c = 0; c < m->gmmC; ++c)
             for (int r = 0; r < D; ++r)
-                for (int q = 0; q < D; ++q) pfull[c * PP + (size_t)(6 + r) * m->P + 6 + q] = m->gmm_prec[((size_t)c * D + r) * D + q];
+                for (int q = 0; q <= r; ++q)
+                    pfull[c * PT + (size_t)(6 + r) * (6 + r + 1) / 2 + 6 + q] = m->gmm_prec[((size_t)c * D + r) * D + q];
         TRY(dev_put(ft, &dm.gmm_pfull, pfull));
     }
 
@@ -1365,10 +1367,17 @@ int enqueue_solve(avb_fitter* ft, const LmBuf& la, const avb_options* o, int rou
     ++ft->launches;
     if (la.q.prof) CUDA_TRY(cudaMemsetAsync(ft->d_qprof, 0, 128, st));
     if (la.q.slots) {
-        int ctas = std::min(lm_flow_ctas_per_sm(la.tensor != 0) * ft->num_sms, std::max(1, ft->batch * 16));
+        // CTAs per SM: what the shared memory of the variant allows (227 KB per SM, 1 KB reserved per CTA), capped by the
+        // register budget the kernel variants are compiled for; AVB_FLOW_OCC overrides
+        const size_t fsm = lm_flow_smem_bytes(ft->dm, ft->max_nj, la.chunk_verts, la.tensor != 0);
+        const int occ_cap = (int)std::min<size_t>(la.tensor ? 4 : 3, (227 * 1024) / (fsm + 1024));
+        int occ = ft->flow_occ_default[la.tensor ? 1 : 0];
+        if (const char* e = std::getenv("AVB_FLOW_OCC")) occ = std::atoi(e);
+        occ = std::max(2, std::min(occ, occ_cap));
+        int ctas = std::min(occ * ft->num_sms, std::max(1, ft->batch * 16));
         if (const char* e = std::getenv("AVB_FLOW_CTAS")) ctas = std::max(1, std::min(ctas, std::atoi(e)));
         ProfScope ps(ft, KC_FLOW);
-        CUDA_TRY(launch_lm_flow(ft->dm, ft->dp, la, ft->max_nj, ctas, st));
+        CUDA_TRY(launch_lm_flow(ft->dm, ft->dp, la, ft->max_nj, ctas, occ, st));
         ++ft->launches;
         (void)rounds;
         return AVB_OK;

@@ -35,7 +35,7 @@ struct DevModel {
     const double* gmm_mean;    // [C][D]
     const double* gmm_prec;    // [C][D][D]   Sigma^-1 = prec_cho prec_cho^T (full symmetric)
     const double* gmm_clog;    // [C]         consts_log
-    const double* gmm_pfull;   // [C][P][P]   Sigma^-1 zero padded to the tangent layout (rows/cols 6..6+D)
+    const double* gmm_pfull;   // [C][P(P+1)/2] Sigma^-1 zero padded to the tangent layout (rows/cols 6..6+D), packed lower triangle
 };
 
 // Per-optimizer part tables (AvatarOptimizer.cpp:1213-1244) and the static column-group schedule

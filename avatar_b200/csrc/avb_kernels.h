@@ -171,13 +171,13 @@ cudaError_t launch_lm_prep(const DevModel& M, const DevParts& Pt, const LmBuf& a
 cudaError_t launch_lm_eval_part(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, int max_nj, bool tensor,
                                 int part, cudaStream_t st);
 // the same evaluations as one persistent data-flow kernel (launch_lm_prep with a.q set seeds the queue)
-cudaError_t launch_lm_flow(const DevModel& M, const DevParts& Pt, const LmBuf& a, int max_nj, int ctas, cudaStream_t st);
+cudaError_t launch_lm_flow(const DevModel& M, const DevParts& Pt, const LmBuf& a, int max_nj, int ctas, int occ, cudaStream_t st);
+size_t lm_flow_smem_bytes(const DevModel& M, int max_nj, int chunk_verts, bool tensor);
 long long lm_part_stride(int max_nj, int J, int K);
 int lm_tab_doubles(int J, int K);
 int lm_rec_floats(int max_nj, int K);
 int lm_rec_slots(int V);
 size_t lm_gram_smem_bytes(int max_nj, int K, int chunk_verts, bool tensor);
 bool lm_tensor_supported(int max_nj, int K);
-int lm_flow_ctas_per_sm(bool tensor);
 
 }  // namespace avb

@@ -1078,24 +1078,35 @@ struct SolveSmem {
 };
 // table scratch of the solve: the joint tables of the retraction, earlier the joint rotations of the basis change and
 // the column-major panel of the factorisation (8 x ((P + 4) & ~3) + 8 doubles)
-__host__ __device__ inline int solve_tb_doubles(int J, int K) {
-    const int P = 3 + 3 * J + K, t = tables_doubles(J, K, true), pnl = 8 * ((P + 4) & ~3) + 8;
-    return t > pnl ? t : pnl;
+// packed lower triangle, row major: entry (i, k), k <= i, at tri(i) + k.  The solve keeps J^T J (+ priors, + damping) and
+// its Cholesky factor in this form: 29 KB instead of 58 KB for P = 85, which is what lets three or four CTAs share an SM.
+__host__ __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
+__host__ __device__ inline int solve_tb_doubles(int J, int K, int C) {
+    // early phases: joint rotations G (9 J) | gradient moments (3 + 6 J + K) | pos (3 J) | C (3 J K); prior: dcomp | ycomp;
+    // factorisation: column-major panel (8 x ((P + 5) & ~3) + 8).  The joint tables of the retraction alias the matrix.
+    const int P = 3 + 3 * J + K, D = 3 * (J - 1);
+    int t = 9 * J + ((tc_gacc(J, K) + 1) & ~1) + 3 * J + 3 * J * K;
+    const int pnl = 8 * ((P + 5) & ~3) + 8, gm = 2 * (C > 0 ? C : 1) * ((D + 8) & ~7);
+    t = t > pnl ? t : pnl;
+    return ((t > gm ? t : gm) + 1) & ~1;
+}
+__host__ __device__ inline int solve_h_doubles(int J, int K) {
+    const int P = 3 + 3 * J + K, h = tri(P + 1) + 2, t = tables_doubles(J, K, true);
+    return ((h > t ? h : t) + 1) & ~1;
 }
 __host__ __device__ inline size_t solve_smem_bytes(int J, int K, int C) {
     const int P = 3 + 3 * J + K, nx = 3 + 4 * J + K, D = 3 * (J - 1);
-    size_t d = 2 * ((nx + 1) & ~1) + solve_tb_doubles(J, K) + (size_t)(P + 2) * P + 5 * ((P + 1) & ~1) + 8 * kNBsq + ((D + 1) & ~1) +
-               2 * (size_t)(C > 0 ? C : 1) * ((D + 8) & ~7) + 64;
+    size_t d = 2 * ((nx + 1) & ~1) + solve_tb_doubles(J, K, C) + solve_h_doubles(J, K) + 5 * ((P + 1) & ~1) + 8 * kNBsq + ((D + 1) & ~1) + 64;
     return d * 8 + 64 * 4 + 128;
 }
 __device__ inline SolveSmem carve_solve(unsigned char* raw, const DevModel& M) {
     SolveSmem S;
-    const int P = M.P, nx = M.nx, D = 3 * (M.J - 1), C = M.gmmC > 0 ? M.gmmC : 1;
+    const int P = M.P, nx = M.nx, D = 3 * (M.J - 1);
     double* d = reinterpret_cast<double*>(raw);
     S.xs = d; d += (nx + 1) & ~1;
     S.xt = d; d += (nx + 1) & ~1;
-    S.tb = d; d += solve_tb_doubles(M.J, M.K);
-    S.Hs = d; d += (size_t)(P + 2) * P;   // + the augmented right-hand-side row (and one row of padding)
+    S.tb = d; d += solve_tb_doubles(M.J, M.K, M.gmmC);
+    S.Hs = d; d += solve_h_doubles(M.J, M.K);   // packed lower triangle + the augmented right-hand-side row P
     S.gs = d; d += (P + 1) & ~1;
     S.glo = d; d += (P + 1) & ~1;
     S.gcur = d; d += (P + 1) & ~1;
@@ -1103,14 +1114,14 @@ __device__ inline SolveSmem carve_solve(unsigned char* raw, const DevModel& M) {
     S.dd = d; d += (P + 1) & ~1;
     S.wscr = d; d += 8 * kNBsq;
     S.aa = d; d += (D + 1) & ~1;
-    S.ycomp = d; d += (size_t)C * ((D + 8) & ~7);
-    S.dcomp = d; d += (size_t)C * ((D + 8) & ~7);
+    S.dcomp = S.tb;                                        // the prior's scratch shares the table scratch (disjoint in time)
+    S.ycomp = S.tb + (size_t)(M.gmmC > 0 ? M.gmmC : 1) * ((D + 8) & ~7);
     S.scr = d; d += 64;
     S.iscr = reinterpret_cast<int*>(d);
     return S;
 }
 
-// CTA-wide blocked right-looking Cholesky of the leading P x P lower triangle of W (row-major, leading dimension P),
+// CTA-wide blocked right-looking Cholesky of the leading P x P lower triangle of W (PACKED lower, row major: tri(i) + k),
 // carried through R >= P rows: rows P..R-1 enter as right-hand sides b^T and leave as (L^-1 b)^T, i.e. the forward
 // substitution comes for free.  Panels of 8 columns: every warp factors the 8x8 diagonal block redundantly in
 // registers (one row per lane, shuffles), solves its share of the rows below against it, and all threads apply the
@@ -1153,7 +1164,7 @@ __device__ bool aug_cholesky(double* W, int P, int R, double* dinv, double* wscr
         double a[kNB];
 #pragma unroll
         for (int c = 0; c < kNB; ++c)
-            a[c] = (r < nb && c <= r) ? W[(size_t)(j0 + r) * P + j0 + c] : ((c == r) ? 1.0 : 0.0);
+            a[c] = (r < nb && c <= r) ? W[tri(j0 + r) + j0 + c] : ((c == r) ? 1.0 : 0.0);
         bool ok = true;
         double myinv = 1.0;
 #pragma unroll
@@ -1182,7 +1193,7 @@ __device__ bool aug_cholesky(double* W, int P, int R, double* dinv, double* wscr
         //      per column (x_c = w_c / L_cc - sum_k x_k L_ck / L_cc) ----
         const int t0 = j0 + nb;
         for (int i = t0 + tid; i < R; i += nthr) {
-            double* wi = W + (size_t)i * P + j0;
+            double* wi = W + tri(i) + j0;
             double x[kNB];
 #pragma unroll
             for (int c = 0; c < kNB; ++c) x[c] = (c < nb) ? wi[c] * Lw[c * kNB + c] : 0.0;
@@ -1202,7 +1213,7 @@ __device__ bool aug_cholesky(double* W, int P, int R, double* dinv, double* wscr
         if (wid == 0 && lane < nb) {   // L11 itself (nobody reads the diagonal block any more)
 #pragma unroll
             for (int c = 0; c < kNB; ++c)
-                if (c <= lane) W[(size_t)(j0 + lane) * P + j0 + c] = a[c];
+                if (c <= lane) W[tri(j0 + lane) + j0 + c] = a[c];
         }
         const int mrow = R - t0, mcol = P - t0;
         if (mcol > 0) {
@@ -1241,7 +1252,7 @@ __device__ bool aug_cholesky(double* W, int P, int R, double* dinv, double* wscr
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int i = i0 + q, k = k0 + u;
-                        if (i < R && k < P && k <= i) W[(size_t)i * P + k] -= acc[q][u];
+                        if (i < R && k < P && k <= i) W[tri(i) + k] -= acc[q][u];
                     }
             }
         }
@@ -1261,7 +1272,7 @@ __device__ void warp_back_solve(const double* L, const double* dinv, int P, cons
     __syncwarp();
 #pragma unroll 1
     for (int i = P - 1; i >= 0; --i) {
-        const double* Li = L + (size_t)i * P;
+        const double* Li = L + tri(i);
         const double l0 = (lane < i) ? Li[lane] : 0.0, l1 = (lane + 32 < i) ? Li[lane + 32] : 0.0;
         const double xi = x[i] * dinv[i];
         __syncwarp();
@@ -1280,7 +1291,8 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
     LmState& gst = a.state[f];
     const int P = M.P, nx = M.nx, J = M.J, K = M.K;
     SolveSmem S = carve_solve(smem_raw, M);
-    double* Hcur = a.Hcur + (size_t)f * P * P;
+    const int nTri = tri(P);   // packed entries of the P x P lower triangle
+    double* Hcur = a.Hcur + (size_t)f * P * P;   // (packed: the first tri(P) doubles of the frame's slot)
     double* gcur_g = a.gcur + (size_t)f * P;
     const LmState st = load_state(&gst);  // snapshot (only thread 0 writes it back at the end)
     unsigned long long tp = phase_begin(a.q);
@@ -1296,7 +1308,7 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         S.gs[i] = 0.0;
     }
 #pragma unroll 4
-    for (int i = tid; i < P * P; i += kSolveThreads) S.Hs[i] = 0.0;
+    for (int i = tid; i < nTri; i += kSolveThreads) S.Hs[i] = 0.0;
     double* Gs9 = S.tb;   // global joint rotations of the trial point (the table scratch is free until the retraction)
 #pragma unroll 1
     for (int i = tid; i < 9 * J; i += kSolveThreads) Gs9[i] = ldg2(a.tab + (size_t)f * a.tabD + i);
@@ -1342,8 +1354,7 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
                         S.gs[ca] += val[u];
                     } else {
                         const int cb = rb < 3 ? rb : (rb < 3 + 3 * nj ? 3 + 3 * gj[(rb - 3) / 3] + (rb - 3) % 3 : rb + 3 * (J - nj));
-                        S.Hs[(size_t)ca * P + cb] += val[u];
-                        if (ca != cb) S.Hs[(size_t)cb * P + ca] += val[u];
+                        S.Hs[ca >= cb ? tri(ca) + cb : tri(cb) + ca] += val[u];
                     }
                 }
             }
@@ -1414,36 +1425,80 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
     phase_lap(a.q, 5, tp);
     // ---- eta -> delta coordinates: H = T^T Ht T, g = T^T gt, T_j = G_parent(j) at the trial point ----
     if (!last) {
+        // One pass over the blocks of the lower triangle, every block owned by one thread (in place):
+        //   joint x joint (3 x 3, A >= B; the diagonal blocks are symmetric and stored as six entries), joint rows x p columns
+        //   (left factor only), shape rows x joint columns (1 x 3 strips, right factor only).  Root joint, p, shape: T = I.
+        const int nJJ = (J * (J + 1)) >> 1, nItems = nJJ + J + K * J;
 #pragma unroll 1
-    for (int i = tid; i < P * (J - 1); i += kSolveThreads) {
-        const int j = 1 + i / P, c = i % P;
-        const double* Gp = Gs9 + 9 * M.parent[j];
-        double* h = S.Hs + (size_t)(3 + 3 * j) * P + c;
-        const double h0 = h[0], h1 = h[P], h2 = h[2 * P];
-        h[0] = Gp[0] * h0 + Gp[3] * h1 + Gp[6] * h2;
-        h[P] = Gp[1] * h0 + Gp[4] * h1 + Gp[7] * h2;
-        h[2 * P] = Gp[2] * h0 + Gp[5] * h1 + Gp[8] * h2;
-    }
-    __syncthreads();
+        for (int it = tid; it < nItems; it += kSolveThreads) {
+            if (it < nJJ) {
+                int A = (int)((sqrtf(8.f * (float)it + 1.f) - 1.f) * 0.5f);
+                while (tri(A + 1) <= it) ++A;
+                while (tri(A) > it) --A;
+                const int B = it - tri(A);
+                if (A == 0) continue;                       // root x root: identity on both sides
+                const double* TA = Gs9 + 9 * M.parent[A];
+                const int ra = 3 + 3 * A, cb = 3 + 3 * B;
+                double X[3][3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int rr = ra + r, cc = cb + c;
+                        X[r][c] = S.Hs[rr >= cc ? tri(rr) + cc : tri(cc) + rr];   // mirrors the diagonal block
+                    }
+                double Y[3][3];   // T_A^T X
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) Y[r][c] = TA[r] * X[0][c] + TA[3 + r] * X[1][c] + TA[6 + r] * X[2][c];
+                if (B > 0) {      // ... T_B
+                    const double* TB = Gs9 + 9 * M.parent[B];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const double y0 = Y[r][0], y1 = Y[r][1], y2 = Y[r][2];
+                        Y[r][0] = y0 * TB[0] + y1 * TB[3] + y2 * TB[6];
+                        Y[r][1] = y0 * TB[1] + y1 * TB[4] + y2 * TB[7];
+                        Y[r][2] = y0 * TB[2] + y1 * TB[5] + y2 * TB[8];
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        if (A != B || c <= r) S.Hs[tri(ra + r) + cb + c] = Y[r][c];
+            } else if (it < nJJ + J) {
+                const int A = it - nJJ;
+                if (A == 0) continue;
+                const double* TA = Gs9 + 9 * M.parent[A];
+                const int ra = 3 + 3 * A;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const double x0 = S.Hs[tri(ra) + c], x1 = S.Hs[tri(ra + 1) + c], x2 = S.Hs[tri(ra + 2) + c];
+                    S.Hs[tri(ra) + c] = TA[0] * x0 + TA[3] * x1 + TA[6] * x2;
+                    S.Hs[tri(ra + 1) + c] = TA[1] * x0 + TA[4] * x1 + TA[7] * x2;
+                    S.Hs[tri(ra + 2) + c] = TA[2] * x0 + TA[5] * x1 + TA[8] * x2;
+                }
+            } else {
+                const int q = it - nJJ - J, m = q / J, B = q - m * J;
+                if (B == 0) continue;
+                const double* TB = Gs9 + 9 * M.parent[B];
+                double* h = S.Hs + tri(3 + 3 * J + m) + 3 + 3 * B;
+                const double h0 = h[0], h1 = h[1], h2 = h[2];
+                h[0] = h0 * TB[0] + h1 * TB[3] + h2 * TB[6];
+                h[1] = h0 * TB[1] + h1 * TB[4] + h2 * TB[7];
+                h[2] = h0 * TB[2] + h1 * TB[5] + h2 * TB[8];
+            }
+        }
 #pragma unroll 1
-    for (int i = tid; i < P * (J - 1); i += kSolveThreads) {
-        const int j = 1 + i / P, r = i % P;
-        const double* Gp = Gs9 + 9 * M.parent[j];
-        double* h = S.Hs + (size_t)r * P + 3 + 3 * j;
-        const double h0 = h[0], h1 = h[1], h2 = h[2];
-        h[0] = h0 * Gp[0] + h1 * Gp[3] + h2 * Gp[6];
-        h[1] = h0 * Gp[1] + h1 * Gp[4] + h2 * Gp[7];
-        h[2] = h0 * Gp[2] + h1 * Gp[5] + h2 * Gp[8];
-    }
-#pragma unroll 1
-    for (int j = 1 + tid; j < J; j += kSolveThreads) {
-        const double* Gp = Gs9 + 9 * M.parent[j];
-        double* gg = S.gs + 3 + 3 * j;
-        const double g0 = gg[0], g1 = gg[1], g2 = gg[2];
-        gg[0] = Gp[0] * g0 + Gp[3] * g1 + Gp[6] * g2;
-        gg[1] = Gp[1] * g0 + Gp[4] * g1 + Gp[7] * g2;
-        gg[2] = Gp[2] * g0 + Gp[5] * g1 + Gp[8] * g2;
-    }
+        for (int j = 1 + tid; j < J; j += kSolveThreads) {
+            const double* Gp = Gs9 + 9 * M.parent[j];
+            double* gg = S.gs + 3 + 3 * j;
+            const double g0 = gg[0], g1 = gg[1], g2 = gg[2];
+            gg[0] = Gp[0] * g0 + Gp[3] * g1 + Gp[6] * g2;
+            gg[1] = Gp[1] * g0 + Gp[4] * g1 + Gp[7] * g2;
+            gg[2] = Gp[2] * g0 + Gp[5] * g1 + Gp[8] * g2;
+        }
     }
     __syncthreads();
     phase_lap(a.q, 6, tp);
@@ -1525,15 +1580,15 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         const int best = S.iscr[0];
         const double hb = 0.5 * sbp * sbp;
         if (!last) {   // H += hb Sigma_best^-1, stored zero-padded to the P x P tangent layout: one flat pass, no index maths
-            const double* Pf = M.gmm_pfull + (size_t)best * P * P;
+            const double* Pf = M.gmm_pfull + (size_t)best * nTri;   // Sigma^-1 zero padded to the tangent layout, packed lower
 #pragma unroll 1
-            for (int i0 = tid; i0 < P * P; i0 += 8 * kSolveThreads) {
+            for (int i0 = tid; i0 < nTri; i0 += 8 * kSolveThreads) {
                 double t[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) t[u] = (i0 + u * kSolveThreads < P * P) ? __ldg(Pf + i0 + u * kSolveThreads) : 0.0;
+                for (int u = 0; u < 8; ++u) t[u] = (i0 + u * kSolveThreads < nTri) ? __ldg(Pf + i0 + u * kSolveThreads) : 0.0;
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
-                    if (i0 + u * kSolveThreads < P * P) S.Hs[i0 + u * kSolveThreads] = fma(hb, t[u], S.Hs[i0 + u * kSolveThreads]);
+                    if (i0 + u * kSolveThreads < nTri) S.Hs[i0 + u * kSolveThreads] = fma(hb, t[u], S.Hs[i0 + u * kSolveThreads]);
             }
         }
 #pragma unroll 1
@@ -1549,7 +1604,7 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         cost_t += 0.5 * sbs * sbs * sq;
 #pragma unroll 1
         for (int k = tid; k < K; k += kSolveThreads) {
-            S.Hs[(size_t)(3 + 3 * J + k) * P + 3 + 3 * J + k] += sbs * sbs;
+            S.Hs[tri(3 + 3 * J + k) + 3 + 3 * J + k] += sbs * sbs;
             S.gs[3 + 3 * J + k] += sbs * sbs * w[k];
         }
     }
@@ -1563,7 +1618,10 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
 #pragma unroll 1
         for (int i = tid; i < P; i += kSolveThreads) a.dump_grad[(size_t)f * P + i] = S.gs[i];
 #pragma unroll 1
-        for (int i = tid; i < P * P; i += kSolveThreads) a.dump_H[(size_t)f * P * P + i] = S.Hs[i];
+        for (int i = tid; i < P * P; i += kSolveThreads) {   // debug dump: the full symmetric matrix
+            const int r = i / P, c = i - r * P;
+            a.dump_H[(size_t)f * P * P + i] = S.Hs[r >= c ? tri(r) + c : tri(c) + r];
+        }
         return true;
     }
 
@@ -1612,7 +1670,7 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
 #pragma unroll 1
         for (int i = tid; i < nx; i += kSolveThreads) S.xs[i] = S.xt[i];
 #pragma unroll 4
-        for (int i = tid; i < (last ? 0 : P * P); i += kSolveThreads) Hcur[i] = S.Hs[i];
+        for (int i = tid; i < (last ? 0 : nTri); i += kSolveThreads) Hcur[i] = S.Hs[i];
 #pragma unroll 1
         for (int i = tid; i < (last ? 0 : P); i += kSolveThreads) S.gcur[i] = S.gs[i];
         __syncthreads();
@@ -1634,25 +1692,25 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         ++iters;
         if (!have_cur_in_smem) {
 #pragma unroll 1
-            for (int i = tid; i < P * P; i += kSolveThreads) S.Hs[i] = ldg2(Hcur + i);
+            for (int i = tid; i < nTri; i += kSolveThreads) S.Hs[i] = ldg2(Hcur + i);
             __syncthreads();
         }
         have_cur_in_smem = false;  // the factorisation below overwrites S.Hs
         // W = Hcur + D,  D_jj = clamp(s^2 h_jj, 1e-6, 1e32) / (s^2 radius),  s = 1 / (1 + sqrt(h_jj)); row P = -g^T
 #pragma unroll 1
         for (int j = tid; j < P; j += kSolveThreads) {
-            const double h = S.Hs[(size_t)j * P + j];
+            const double h = S.Hs[tri(j) + j];
             const double sj = 1.0 / (1.0 + sqrt(h));
             const double dj = fmin(fmax(sj * sj * h, 1e-6), 1e32) / (sj * sj * radius);
             S.dd[j] = dj;
-            S.Hs[(size_t)j * P + j] = h + dj;
-            S.Hs[(size_t)P * P + j] = -S.gcur[j];
+            S.Hs[tri(j) + j] = h + dj;
+            S.Hs[nTri + j] = -S.gcur[j];
         }
         __syncthreads();
         bool ok = aug_cholesky(S.Hs, P, P + 1, S.glo, S.wscr, S.tb);
         phase_lap(a.q, 9, tp);
         if (ok) {
-            if (tid < 32) warp_back_solve(S.Hs, S.glo, P, S.Hs + (size_t)P * P, S.delta);
+            if (tid < 32) warp_back_solve(S.Hs, S.glo, P, S.Hs + nTri, S.delta);
             __syncthreads();
             // model_cost_change = -delta^T (g + 1/2 H delta) with (H + D) delta = -g  =>  1/2 delta^T (D delta - g)
             double part = 0;
@@ -1698,7 +1756,7 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
             }
         }
         __syncthreads();
-        Tables T = carve_tables(S.tb, J, K, true);
+        Tables T = carve_tables(S.Hs, J, K, true);   // the factor is dead: the joint tables of the trial point take its place
         build_tables(M, S.xt, T, true);
         double* tab = a.tab + (size_t)f * a.tabD;
 #pragma unroll 1
@@ -1758,9 +1816,9 @@ lm_solve_kernel(DevModel M, DevParts Pt, LmBuf a) {
 // bodies run on the same data in the same per-frame order.
 // TC = true: the default path, fused record + Gram tasks on tcgen05 (fused_body); TC = false: fp64 DMMA Gram from fp32
 // records in HBM (rows_body + gram_body).
-constexpr int kFlowMinCtasTc = 2;
-template <bool TC>
-__global__ void __launch_bounds__(256, TC ? kFlowMinCtasTc : 2)
+// OCC: CTAs per SM the kernel is compiled for (register budget 128 / 80 / 64 per thread); the host picks the variant.
+template <bool TC, int OCC>
+__global__ void __launch_bounds__(256, OCC)
 lm_flow_kernel(DevModel M, DevParts Pt, LmBuf a) {
     extern __shared__ __align__(1024) unsigned char smem_flow[];
     unsigned char* const smem_raw = smem_flow;
@@ -1927,22 +1985,27 @@ size_t lm_flow_smem(const DevModel& M, int max_nj, int chunk_verts, bool tensor)
     const size_t ssm = solve_smem_bytes(M.J, M.K, M.gmmC) + (tensor ? 1024 : 0);
     return b > ssm ? b : ssm;
 }
-cudaError_t launch_lm_flow(const DevModel& M, const DevParts& Pt, const LmBuf& a, int max_nj, int ctas, cudaStream_t st) {
-    const size_t sm = lm_flow_smem(M, max_nj, a.chunk_verts, a.tensor != 0);
-    if (a.tensor) {
-        cudaError_t e = cudaFuncSetAttribute(lm_flow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        if (e != cudaSuccess) return e;
-        lm_flow_kernel<true><<<ctas, 256, sm, st>>>(M, Pt, a);
-    } else {
-        cudaError_t e = cudaFuncSetAttribute(lm_flow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        if (e != cudaSuccess) return e;
-        lm_flow_kernel<false><<<ctas, 256, sm, st>>>(M, Pt, a);
-    }
+template <bool TC, int OCC>
+static cudaError_t launch_flow_variant(const DevModel& M, const DevParts& Pt, const LmBuf& a, int ctas, size_t sm, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(lm_flow_kernel<TC, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+    lm_flow_kernel<TC, OCC><<<ctas, 256, sm, st>>>(M, Pt, a);
     return cudaGetLastError();
 }
+cudaError_t launch_lm_flow(const DevModel& M, const DevParts& Pt, const LmBuf& a, int max_nj, int ctas, int occ, cudaStream_t st) {
+    const size_t sm = lm_flow_smem(M, max_nj, a.chunk_verts, a.tensor != 0);
+    if (a.tensor) {
+        if (occ >= 4) return launch_flow_variant<true, 4>(M, Pt, a, ctas, sm, st);
+        if (occ == 3) return launch_flow_variant<true, 3>(M, Pt, a, ctas, sm, st);
+        return launch_flow_variant<true, 2>(M, Pt, a, ctas, sm, st);
+    }
+    if (occ >= 3) return launch_flow_variant<false, 3>(M, Pt, a, ctas, sm, st);
+    return launch_flow_variant<false, 2>(M, Pt, a, ctas, sm, st);
+}
+size_t lm_flow_smem_bytes(const DevModel& M, int max_nj, int chunk_verts, bool tensor) { return lm_flow_smem(M, max_nj, chunk_verts, tensor); }
 // the tensor path needs every column group to fit the tile (record fields) and the gradient scratch (columns)
 bool lm_tensor_supported(int max_nj, int K) { return tc_fields(max_nj, K) <= kTcRows; }
-int lm_flow_ctas_per_sm(bool tensor) { return tensor ? kFlowMinCtasTc : 2; }
+
 
 long long lm_part_stride(int max_nj, int J, int K) {   // [ J^T J triangle | J^T r (fp64 path) or P | R | M | T (tensor path) ]
     const int Lg = group_L(max_nj, K), ga = tc_gacc(J, K);
