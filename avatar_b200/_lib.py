@@ -83,6 +83,7 @@ SYMBOLS = [
     ("avb_fit_batch", C.c_int, [_P, C.c_int32, _P, _P, _P, _P, C.POINTER(Options), _P, _P]),
     ("avb_track_sequence", C.c_int, [_P, C.c_int32, _P, _P, _P, _P, C.POINTER(Options), _P, _P]),
     ("avb_upload_batch", C.c_int, [_P, C.c_int32, _P, _P, _P]),
+    ("avb_upload_batch_f32", C.c_int, [_P, C.c_int32, _P, _P, _P]),
     ("avb_fit_resident", C.c_int, [_P, _P, C.POINTER(Options)]),
     ("avb_upload_depth_batch", C.c_int, [_P, C.c_int32, _P, _P, _P, C.POINTER(ImageDesc), _P]),
     ("avb_download_batch", C.c_int, [_P, _P, _P, _P]),

@@ -136,7 +136,9 @@ struct avb_fitter {
     double *d_xt = nullptr, *d_tab = nullptr, *d_part = nullptr, *d_cpart = nullptr, *d_gcur = nullptr;
     unsigned short* d_mlist = nullptr; int4* d_chunks = nullptr; int2* d_gruns = nullptr; LmState* d_state = nullptr;
     float* d_rec = nullptr; int* d_gstart = nullptr; int maxrb = 0, rec_stride = 0, rec_rs = 0;
-    int maxc = 0, tabD = 0, max_nj = 0, chunk_verts = 192;
+    int nn_stage_cap = 0;
+    float* d_data_f32 = nullptr;   // avb_upload_batch_f32 staging
+    int maxc = 0, tabD = 0, max_nj = 0, chunk_verts = 192, chunk_verts_tc = 256;   // vertices per Gram chunk: fp64 path (3 CTAs/SM) / tensor path
     long long pstride = 0;
     // lm_flow_kernel work queue
     unsigned long long* d_qslots = nullptr; unsigned int* d_qctrl = nullptr; int *d_rows_left = nullptr, *d_gram_left = nullptr;
@@ -606,10 +608,6 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     if (prop.major < 10) return fail(AVB_ERR_CUDA, "avatar_b200 kernels are built for sm_100a only");
     {   // the kernels' shared-memory budgets, checked here instead of failing as an opaque launch error at fit time
         const size_t optin = (size_t)prop.sharedMemPerBlockOptin;
-        if (nn_smem_bytes(m->V) > optin)
-            return fail(AVB_ERR_INVALID, "model too large for nn_kernel: the visible model cloud of a frame (24 B per vertex) must fit the " +
-                                             std::to_string(optin / 1024) + " KB of shared memory of one CTA (V <= " +
-                                             std::to_string((optin - 256) / 24) + ")");
         if (pose_smem_bytes(m->V, m->J, m->K) > optin)
             return fail(AVB_ERR_INVALID, "model too large for pose_visibility_kernel (one visibility byte per vertex in shared memory)");
     }
@@ -689,6 +687,14 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     }
     part_start[NP] = (int)part_verts.size();
     for (int p = NP - 1; p >= 0; --p) first_part_at[part_start[p]] = p;
+    {   // nn_kernel stages a prefix of the frame's visible model cloud in shared memory: as much as lets two CTAs share an
+        // SM (about 4600 vertices; back-face culling leaves roughly half of the model visible), never more than V
+        cudaDeviceProp pr2;
+        CUDA_TRY_FT(cudaGetDeviceProperties(&pr2, cfg->device));
+        const size_t per_cta = std::min<size_t>(pr2.sharedMemPerBlockOptin, (pr2.sharedMemPerMultiprocessor - 2 * 1024 - 2 * 8192) / 2);
+        ft->nn_stage_cap = (int)std::min<size_t>((size_t)V, (per_cta - 256) / 24);
+        if (const char* e = std::getenv("AVB_NN_STAGE")) ft->nn_stage_cap = std::max(0, std::min(std::atoi(e), (int)((pr2.sharedMemPerBlockOptin - 256) / 24)));
+    }
     DevParts& dp = ft->dp;
     dp.numParts = NP;
     {   // part of every vertex: part_map[assignedJoints[v][0]] (the renderer's part mask, AvatarHelpers.cpp:162-169)
@@ -750,9 +756,12 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     TRY(dev_alloc(ft, &ft->d_Hcur, B * P * P));
     TRY(dev_alloc(ft, &ft->d_stats, B));
     for (int g : gnj) ft->max_nj = std::max(ft->max_nj, g);
-    if (const char* e = std::getenv("AVB_CHUNK")) ft->chunk_verts = std::max(128, std::min(256, std::atoi(e) / 64 * 64));
+    if (const char* e = std::getenv("AVB_CHUNK")) ft->chunk_verts = ft->chunk_verts_tc = std::max(128, std::min(256, std::atoi(e) / 64 * 64));
     while (ft->chunk_verts > 128 && lm_gram_smem_bytes(ft->max_nj, m->K, ft->chunk_verts, false) > 112 * 1024) ft->chunk_verts -= 64;
-    ft->maxc = (V + ft->chunk_verts - 1) / ft->chunk_verts + dp.numGroups + 1;
+    {
+        const int cmin = std::min(ft->chunk_verts, ft->chunk_verts_tc);
+        ft->maxc = (V + cmin - 1) / cmin + dp.numGroups + 1;
+    }
     ft->tabD = lm_tab_doubles(m->J, m->K);
     ft->pstride = lm_part_stride(ft->max_nj, m->J, m->K);
     TRY(dev_alloc(ft, &ft->d_xt, B * nx));
@@ -869,6 +878,28 @@ int avb_upload_batch(avb_fitter* ft, int32_t batch, const double* clouds, const 
         const int64_t o0 = offsets[0];
         CUDA_TRY(cudaMemcpyAsync(ft->d_data, clouds + 3 * o0, (size_t)total * 24, cudaMemcpyHostToDevice, ft->stream));
         CUDA_TRY(cudaMemcpyAsync(ft->d_labels, labels + o0, (size_t)total * 4, cudaMemcpyHostToDevice, ft->stream));
+    }
+    return AVB_OK;
+}
+
+int avb_upload_batch_f32(avb_fitter* ft, int32_t batch, const float* clouds, const int32_t* labels, const int64_t* offsets) {
+    if (!ft || !offsets || batch <= 0) return fail(AVB_ERR_INVALID, "null argument or empty batch");
+    if (batch > ft->max_batch) return fail(AVB_ERR_CAPACITY, "batch exceeds fitter capacity");
+    const int64_t total = offsets[batch] - offsets[0];
+    if (total < 0 || total > ft->max_points) return fail(AVB_ERR_CAPACITY, "point count exceeds fitter capacity");
+    if (total > 0 && (!clouds || !labels)) return fail(AVB_ERR_INVALID, "null cloud or labels");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    if (!ft->d_data_f32) {   // float staging of the cloud, allocated on first use (16-byte aligned by cudaMalloc)
+        int rc0 = dev_alloc(ft, &ft->d_data_f32, 3 * (size_t)ft->max_points + 4);
+        if (rc0 != AVB_OK) return rc0;
+    }
+    int rc = schedule_batch(ft, batch, offsets);
+    if (rc != AVB_OK) return rc;
+    if (total > 0) {
+        const int64_t o0 = offsets[0];
+        CUDA_TRY(cudaMemcpyAsync(ft->d_data_f32, clouds + 3 * o0, (size_t)total * 12, cudaMemcpyHostToDevice, ft->stream));
+        CUDA_TRY(cudaMemcpyAsync(ft->d_labels, labels + o0, (size_t)total * 4, cudaMemcpyHostToDevice, ft->stream));
+        CUDA_TRY(launch_widen_points(ft->d_data_f32, ft->d_data, 3 * (long long)total, ft->num_sms, ft->stream));
     }
     return AVB_OK;
 }
@@ -1304,6 +1335,7 @@ int enqueue_correspond(avb_fitter* ft, const double* dx, const avb_options* o, c
     na.sum = ft->d_sum;
     na.qpart = ft->d_qpart;
     na.range_flag = ft->d_range;
+    na.stage_cap = ft->nn_stage_cap;
     {
         ProfScope ps(ft, KC_NN);
         CUDA_TRY(launch_nn(ft->dp, na, ft->num_chunks, st));
@@ -1332,7 +1364,7 @@ LmBuf lm_buf(avb_fitter* ft, double* dx, const avb_options* o) {
     a.state = ft->d_state;
     a.maxc = ft->maxc;
     a.tabD = ft->tabD;
-    a.chunk_verts = ft->chunk_verts;
+    a.chunk_verts = o->jtj_precision == AVB_JTJ_BF16_TENSOR ? ft->chunk_verts_tc : ft->chunk_verts;   // the chunk tables are rebuilt by every lm_prep_kernel
     a.pstride = ft->pstride;
     a.cnt = ft->d_cnt;
     a.sum = ft->d_sum;
@@ -1374,7 +1406,7 @@ int enqueue_solve(avb_fitter* ft, const LmBuf& la, const avb_options* o, int rou
         int occ = ft->flow_occ_default[la.tensor ? 1 : 0];
         if (const char* e = std::getenv("AVB_FLOW_OCC")) occ = std::atoi(e);
         occ = std::max(2, std::min(occ, occ_cap));
-        int ctas = std::min(occ * ft->num_sms, std::max(1, ft->batch * 16));
+        int ctas = std::min(occ * ft->num_sms, std::max(1, ft->batch * std::max(16, ft->maxc)));
         if (const char* e = std::getenv("AVB_FLOW_CTAS")) ctas = std::max(1, std::min(ctas, std::atoi(e)));
         ProfScope ps(ft, KC_FLOW);
         CUDA_TRY(launch_lm_flow(ft->dm, ft->dp, la, ft->max_nj, ctas, occ, st));
@@ -1822,7 +1854,9 @@ int avb_track_sequence(avb_fitter* ft, int32_t T, const double* clouds, const in
     }
     c0[T] = nc;
     q0[T] = qb;
-    if (qb > ft->max_qblocks) return fail(AVB_ERR_CAPACITY, "too many |d|^2 blocks");
+    // every frame is "frame 0" of a batch of one and its |d|^2 partials start at d_qpart[0]: the largest frame must fit
+    for (int t = 0; t < T; ++t)
+        if (q0[t + 1] - q0[t] > ft->max_qblocks) return fail(AVB_ERR_CAPACITY, "too many |d|^2 blocks");
     if (nc > 0) {
         CUDA_TRY(cudaMemcpyAsync(ft->d_chunk_frame, ft->h_chunk_frame, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(ft->d_chunk_begin, ft->h_chunk_begin, (size_t)nc * 8, cudaMemcpyHostToDevice, st));

@@ -21,6 +21,8 @@
 
 #include <math.h>
 
+#include <algorithm>
+
 namespace avb {
 
 // ---------------------------------------------------------------------------------------------
@@ -147,23 +149,29 @@ pose_visibility_kernel(DevModel M, DevParts Pt, PoseArgs a) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(512, 1)
+// Shared memory holds the first a.stage_cap compacted vertices (host: what lets TWO CTAs share an SM; back-face culling
+// leaves about half of the model visible, so a frame's whole visible cloud normally fits); a part whose range ends beyond
+// the staged prefix is scanned from global memory (L2) instead -- same arithmetic, same order.
+__global__ void __launch_bounds__(512, 2)
 nn_kernel(DevParts Pt, NNArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ int s_start[kMaxParts + 1];
     __shared__ double s_wsum[16];
+    __shared__ int s_hist[kMaxParts + 1];
+    __shared__ unsigned short s_perm[512];
+    __shared__ double s_q2[512];
     const int tid = threadIdx.x;
     const int c = blockIdx.x;
     const int f = a.chunk_frame[c];
     const long long begin = a.chunk_begin[c];
     const int count = a.chunk_count[c];
-    double* mxyz = reinterpret_cast<double*>(smem_raw);
+    double* mstage = reinterpret_cast<double*>(smem_raw);
 
     const int* pv_start = a.pv_start + (size_t)f * (Pt.numParts + 1);
     if (tid <= Pt.numParts) s_start[tid] = pv_start[tid];
-    const int nvis = pv_start[Pt.numParts];
-    // one TMA bulk copy of the frame's compacted model cloud (nvis * 24 B, rounded up to 16 B)
+    const int nvis = min(pv_start[Pt.numParts], a.stage_cap);
+    // one TMA bulk copy of the (staged prefix of the) frame's compacted model cloud (nvis * 24 B, rounded up to 16 B)
     const uint32_t bytes = (uint32_t)(((size_t)nvis * 24 + 15) & ~(size_t)15);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
@@ -179,7 +187,7 @@ nn_kernel(DevParts Pt, NNArgs a) {
             const uint32_t n = min(bytes - off, 65536u);
             asm volatile(
                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                    smem_u32(reinterpret_cast<unsigned char*>(mxyz) + off)),
+                    smem_u32(reinterpret_cast<unsigned char*>(mstage) + off)),
                 "l"(reinterpret_cast<const unsigned char*>(src) + off), "r"(n), "r"(smem_u32(&mbar))
                 : "memory");
             off += n;
@@ -201,19 +209,38 @@ nn_kernel(DevParts Pt, NNArgs a) {
     int* cnt = a.cnt + (size_t)f * a.V;
     unsigned long long* sum = a.sum + (size_t)f * 3 * a.V;
     const int lane = tid & 31, wid = tid >> 5;
-    // passes of 512 points = two deterministic |d|^2 blocks of kQBlock (256) points
+    // passes of 512 points = two deterministic |d|^2 blocks of kQBlock (256) points.  Inside a pass the points are dealt
+    // to the threads SORTED BY PART LABEL (a counting sort in shared memory): image-ordered clouds put two or more labels
+    // into most warps, and a warp whose lanes scan different parts runs those scans one after the other.  Which thread
+    // handles which point does not matter for the result: the index goes back to the point's own slot, the per-vertex
+    // sums are integer atomics, and |d|^2 returns to the point's original position before the block sums.
     for (int base = 0; base < count; base += 512) {
-        const int li = base + tid;
+        if (tid <= kMaxParts) s_hist[tid] = 0;
+        __syncthreads();
+        const int li0 = base + tid;
+        int mylab = kMaxParts;   // bucket of "nothing to scan"
+        if (li0 < count) {
+            const int label = a.labels[begin + li0];
+            if (label >= 0 && label < Pt.numParts) mylab = label;
+            else atomicOr(a.range_flag + f, 2);   // out of range is UB in the reference (:1279)
+        }
+        const int slot = atomicAdd(&s_hist[mylab], 1);
+        __syncthreads();
+        int pos = slot;
+        for (int l = 0; l < mylab; ++l) pos += s_hist[l];
+        s_perm[pos] = (unsigned short)tid;
+        __syncthreads();
+        const int src = s_perm[tid], li = base + src;
         double q2 = 0.0;
         if (li < count) {
             const long long gi = begin + li;
             const double q0 = a.data[3 * gi], q1 = a.data[3 * gi + 1], qz = a.data[3 * gi + 2];
             const int label = a.labels[gi];
-            const bool lab_ok = label >= 0 && label < Pt.numParts;  // out of range is UB in the reference (:1279)
-            if (!lab_ok) atomicOr(a.range_flag + f, 2);
+            const bool lab_ok = label >= 0 && label < Pt.numParts;
             const int s = lab_ok ? s_start[label] : 0, e = lab_ok ? s_start[label + 1] : 0;
             double best = 1.79769313486231570e308;
             int bi = -1;
+            const double* mxyz = (e <= a.stage_cap) ? mstage : a.pv_xyz + (size_t)f * a.pv_stride;
 #pragma unroll 4
             for (int k = s; k < e; ++k) {
                 // nanoflann L2_Simple: sum_c (a_c - b_c)^2, c = 0,1,2 (nanoflann.hpp:423-445); strict '<'
@@ -247,20 +274,47 @@ nn_kernel(DevParts Pt, NNArgs a) {
             }
             a.nn_idx[gi] = vtx;
         }
-        // deterministic per-256-point partial of sum |d|^2
-        q2 = warp_sum(q2);
+        s_q2[src] = q2;
         __syncthreads();
+        // deterministic per-256-point partial of sum |d|^2, in the points' own order
+        q2 = warp_sum(s_q2[tid]);
         if (lane == 0) s_wsum[wid] = q2;
         __syncthreads();
         if (tid < 2) {
             const int blk = (base / kQBlock) + tid;  // block index inside this chunk
             if (blk * kQBlock < count) {
-                double s = 0;
-                for (int q = 0; q < 8; ++q) s += s_wsum[8 * tid + q];
-                a.qpart[a.chunk_qblock[c] + blk] = s;
+                double sacc = 0;
+                for (int q = 0; q < 8; ++q) sacc += s_wsum[8 * tid + q];
+                a.qpart[a.chunk_qblock[c] + blk] = sacc;
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// float -> double widening of an uploaded cloud (avb_upload_batch_f32): depth cameras deliver float points
+// (CameraIntrin::to3D, Calibration.cpp:68-95), so shipping them as floats halves the PCIe bytes and the widened
+// doubles are bit-identical to what the reference's Eigen::Vector3f -> double cast produces on the host (demo.cpp:241)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+widen_points_kernel(const float4* __restrict__ in, double* __restrict__ out, long long n4, const float* __restrict__ tail_in, int tail) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = __ldcs(in + i);
+        double2* o = reinterpret_cast<double2*>(out + 4 * i);
+        o[0] = make_double2((double)v.x, (double)v.y);
+        o[1] = make_double2((double)v.z, (double)v.w);
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < tail) out[4 * n4 + threadIdx.x] = (double)tail_in[threadIdx.x];
+}
+
+cudaError_t launch_widen_points(const float* in, double* out, long long n, int num_sms, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const long long n4 = n / 4;
+    const int tail = (int)(n - 4 * n4);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((n4 + 255) / 256, (long long)num_sms * 8));
+    widen_points_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(in), out, n4, in + 4 * n4, tail);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -271,7 +325,7 @@ size_t pose_smem_bytes(int V, int J, int K) {
     return (size_t)(((nx + 1) & ~1) + tables_doubles(J, K, false)) * 8 + 64 * 4 + (size_t)V + 64;
 }
 
-size_t nn_smem_bytes(int V) { return (((size_t)V * 24 + 15) & ~(size_t)15) + 128; }
+size_t nn_smem_bytes(int stage_cap) { return (((size_t)stage_cap * 24 + 15) & ~(size_t)15) + 128; }
 
 cudaError_t launch_pose_visibility(const DevModel& M, const DevParts& Pt, const PoseArgs& a, int batch, cudaStream_t st) {
     const size_t smem = pose_smem_bytes(M.V, M.J, M.K);
@@ -284,7 +338,7 @@ cudaError_t launch_pose_visibility(const DevModel& M, const DevParts& Pt, const 
 }
 
 cudaError_t launch_nn(const DevParts& Pt, const NNArgs& a, int num_chunks, cudaStream_t st) {
-    const size_t smem = nn_smem_bytes(a.V);
+    const size_t smem = nn_smem_bytes(a.stage_cap);
     {   // per device/context attribute: set on every launch (cheap host call)
         cudaError_t e = cudaFuncSetAttribute(nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

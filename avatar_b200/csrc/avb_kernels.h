@@ -38,6 +38,7 @@ struct NNArgs {
     unsigned long long* sum;     // [batch][V][3] fixed point 2^36
     double* qpart;               // [total q blocks]
     int* range_flag;             // [batch]
+    int stage_cap;               // compacted model vertices staged in shared memory (the rest is read through L2)
 };
 
 struct CloudArgs {  // data-cloud construction from depth + part-label images (avb_cloud.cu)
@@ -163,7 +164,8 @@ int cloud_strip_rows();
 cudaError_t launch_cloud_count(const CloudArgs& a, int strips, int batch, cudaStream_t st);
 cudaError_t launch_cloud_compact(const CloudArgs& a, int strips, int batch, cudaStream_t st);
 size_t pose_smem_bytes(int V, int J, int K);
-size_t nn_smem_bytes(int V);
+size_t nn_smem_bytes(int stage_cap);
+cudaError_t launch_widen_points(const float* in, double* out, long long n, int num_sms, cudaStream_t st);
 cudaError_t launch_pose_visibility(const DevModel& M, const DevParts& Pt, const PoseArgs& a, int batch, cudaStream_t st);
 cudaError_t launch_nn(const DevParts& Pt, const NNArgs& a, int num_chunks, cudaStream_t st);
 cudaError_t launch_lm_prep(const DevModel& M, const DevParts& Pt, const LmBuf& a, int batch, cudaStream_t st);

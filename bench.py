@@ -213,12 +213,15 @@ def main():
     ap.add_argument("--jtj", default="fp64", choices=["fp64", "tensor"],
                     help="J^T J path: fp64 (default, parity path: DMMA Gram of fp32 records) or tensor (split-bf16 tcgen05 with "
                          "fp32 TMEM accumulation, J^T r and cost in fp64; not a parity path)")
+    ap.add_argument("--upload", default="f32", choices=["f32", "f64"],
+                    help="e2e arm: ship the clouds as float32 (avb_upload_batch_f32; lossless for depth-camera clouds, which are "
+                         "float by construction, Calibration.cpp:68-95) or as float64 (avb_fit_batch)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --frames per GPU (default); strong: --frames in total, sharded over the ranks (BASELINE.json configs[2])")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity sample printed on the line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--lanes", type=int, default=int(os.environ.get("AVB_LANES", "3")),
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("AVB_LANES", "2")),
                     help="split the rank's batch over this many fitters (streams) that run concurrently")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -259,6 +262,9 @@ def main():
     h_x = pinned_array(_lib.lib, (F, nx), np.float64)
     h_pts[:] = np.concatenate(pts)
     h_lab[:] = np.concatenate(labs)
+    h_pts32 = pinned_array(_lib.lib, (total, 3), np.float32)
+    h_pts32[:] = h_pts
+    use_f32 = args.upload == "f32" and bool(np.array_equal(h_pts32.astype(np.float64), h_pts))   # only when the floats ARE the cloud
     # lanes: contiguous sub-batches, one fitter (device buffers + stream) each; their kernels overlap on the GPU
     NL = max(1, min(args.lanes, F))
     bounds = [shard.frame_range(F, l, NL) for l in range(NL)]
@@ -266,7 +272,7 @@ def main():
     for lo, hi in bounds:
         npts = int(off[hi] - off[lo])
         lanes.append(dict(ft=Fitter(model, num_parts, part_map, hi - lo, npts + 16, local_rank), lo=lo, hi=hi,
-                          pts=h_pts[off[lo]:off[hi]], lab=h_lab[off[lo]:off[hi]], off=(off[lo:hi + 1] - off[lo]).copy(),
+                          pts=h_pts[off[lo]:off[hi]], pts32=h_pts32[off[lo]:off[hi]], lab=h_lab[off[lo]:off[hi]], off=(off[lo:hi + 1] - off[lo]).copy(),
                           x0=np.ascontiguousarray(x0[lo:hi])))
     ft = lanes[0]["ft"]
     opt = default_options()
@@ -321,7 +327,12 @@ def main():
     def lane_worker(ln, nsteps, out_q):
         for _ in range(nsteps):
             h_x[ln["lo"]:ln["hi"]] = ln["x0"]
-            x, st, _ = ln["ft"].fit_batch(ln["pts"], ln["lab"], ln["off"], h_x[ln["lo"]:ln["hi"]], opt)
+            if use_f32:   # split form of the same call: avb_upload_batch_f32 + avb_fit_resident + avb_download_results
+                ln["ft"].upload(ln["pts32"], ln["lab"], ln["off"])
+                ln["ft"].fit_resident(h_x[ln["lo"]:ln["hi"]], opt)
+                x, st, _ = ln["ft"].download()
+            else:
+                x, st, _ = ln["ft"].fit_batch(ln["pts"], ln["lab"], ln["off"], h_x[ln["lo"]:ln["hi"]], opt)
             out_q.put(ln["ft"].gather_params() if world > 1 else x)
 
     def e2e_run(nsteps):
@@ -350,7 +361,7 @@ def main():
     e2e_s = shard.max_over_ranks(t3 - t2, dev)
     e2e_value = F_total * args.steps / e2e_s
     clocks = sampler.stop(t0, t3) if sampler else None
-    h2d = total * 24 + total * 4 + F * nx * 8 + (F + 1) * 8
+    h2d = total * (12 if use_f32 else 24) + total * 4 + F * nx * 8 + (F + 1) * 8
     d2h = F * nx * 8 + F * 40
 
     if rank != 0:
@@ -408,8 +419,8 @@ def main():
     traffic = None
     traffic_src = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this kernel
-        tag = {"fp64": "r2_ncu_flow_fp64_raw.csv", "tensor": "r2_ncu_flow_tensor_raw.csv"}[args.jtj] if dom == "lm_flow_kernel" else \
-            "r1_ncu_%s_kernel_raw.csv" % dom.split("_kernel")[0].replace("lm_", "")
+        tag = {"fp64": "r2_ncu_flow_fp64_kernel_raw.csv", "tensor": "r2_ncu_flow_tensor_kernel_raw.csv"}[args.jtj] if dom == "lm_flow_kernel" else \
+            "r2_ncu_%s_kernel_raw.csv" % dom.split("_kernel")[0].replace("lm_", "")
         with open(os.path.join(ROOT, "profiles", tag)) as fh:
             vals = {r.split(",")[0]: r.strip().split(",") for r in fh}
         mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -467,7 +478,8 @@ def main():
                        "lanes": NL,
                        "l2": "inputs larger than L2: %.0f MB of clouds+labels per step" % (total * 28 / 1e6)},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_s / args.steps, "timer": "wall clock around the K steps (barrier + synchronize on both sides); lanes free-running"},
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "timer": "wall clock around the K steps (barrier + synchronize on both sides); lanes free-running",
+                    "upload": "float32 points (avb_upload_batch_f32, widened on the device; bit-identical results)" if use_f32 else "float64 points (avb_fit_batch)"},
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks, "roofline": roofline, "roofline_fp64": roofline_fp64,
             "wall_ms_per_step_resident": 1e3 * (t1 - t0) / args.steps}
@@ -534,7 +546,7 @@ def main():
     # ---- secondary configs (BASELINE.json configs[1] and configs[3]), N=1 only: single-frame latency through
     #      avb_fit and a warm-started tracking sequence through avb_track_sequence ----
     if world == 1 and not args.no_extras:
-        f1 = Fitter(model, num_parts, part_map, 1, int(npts.max()) * 64 + 64, local_rank)
+        f1 = Fitter(model, num_parts, part_map, 1, int(npts.max()) + 64, local_rank)
         o1 = default_options()
         o1.function_tolerance = 0.0
         lat = []
@@ -542,18 +554,149 @@ def main():
             tA = time.perf_counter()
             f1.fit_batch(pts[i % 8], labs[i % 8], np.array([0, len(pts[i % 8])]), x0[i % 8][None], o1)
             lat.append(time.perf_counter() - tA)
-        T = 60
-        seq_off = np.cumsum([0] + [len(pts[0])] * T)
-        seq_pts = np.concatenate([pts[0]] * T)
-        seq_lab = np.concatenate([labs[0]] * T)
-        f1.track_sequence(seq_pts[:seq_off[3]], seq_lab[:seq_off[3]], seq_off[:4], x0[0], o1)
-        tA = time.perf_counter()
-        f1.track_sequence(seq_pts, seq_lab, seq_off, x0[0], o1)
-        trk = time.perf_counter() - tA
         line["secondary"] = {"single_frame_fit_ms_median": 1e3 * float(np.median(lat[2:])),
                              "single_frame_points": int(len(pts[0])),
-                             "tracking_frames_per_s": T / trk, "tracking_frames": T,
                              "note": "host buffers in, parameters out, icp_iters=1, 10 LM iterations; wall clock"}
+        # ---- BASELINE.json configs[3]: tracking, 300 DISTINCT frames of a slerped ground-truth motion, every frame warm-started
+        #      from the previous fit (avb_track_sequence: uploads run ahead on a copy stream) ----
+        try:
+            from harness import synth
+            T = 300
+            xs_gt = synth.slerp_sequence(model, np.random.default_rng(2024), T)
+            fseq = Fitter(model, num_parts, part_map, T, 16, local_rank)
+            seq_gt, _, _ = fseq.avatar_update(xs_gt)
+            fseq.close()
+            sp, sl, so = render_frames(model, part_map, seq_gt)
+            seq_pts = pinned_array(_lib.lib, (int(so[-1]), 3), np.float64)
+            seq_lab = pinned_array(_lib.lib, (int(so[-1]),), np.int32)
+            seq_pts[:] = np.concatenate(sp)
+            seq_lab[:] = np.concatenate(sl)
+            x_start = synth.perturbed_start(model, xs_gt[0], np.random.default_rng(7))
+            ftr = Fitter(model, num_parts, part_map, 1, int(so[-1]) + 64, local_rank)
+            ftr.track_sequence(seq_pts[:so[3]], seq_lab[:so[3]], so[:4], x_start, o1)
+            walls = []
+            for _ in range(3):
+                tA = time.perf_counter()
+                x_trk, st_trk = ftr.track_sequence(seq_pts, seq_lab, so, x_start, o1)
+                walls.append(time.perf_counter() - tA)
+            trk = float(np.median(walls))
+            ftr.close()
+            fchk = Fitter(model, num_parts, part_map, T, 16, local_rank)
+            trk_cloud, _, _ = fchk.avatar_update(x_trk)
+            fchk.close()
+            verr = np.linalg.norm(trk_cloud - seq_gt, axis=2).mean(axis=1)       # mean vertex distance to the ground truth, per frame
+            n_seq = np.diff(so)
+            inner_t = float(np.mean([s_.iterations for s_ in st_trk]))
+            alg_t = float(sum(20.0 * n + inner_t * (16.0 * n + 4.0 * P * P + 4.0 * P) + 2 * 12.0 * V for n in n_seq))
+            sec_trk = {"what": "BASELINE.json configs[3]: avb_track_sequence over %d distinct frames of a slerped smplsynth-style motion "
+                               "(key pose every 30 frames), warm start from the previous fit, icp_iters=1, 10 LM iterations" % T,
+                       "frames": T, "frames_per_s": T / trk, "ms_per_frame": 1e3 * trk / T, "mean_points_per_frame": float(n_seq.mean()),
+                       "timer": "wall clock, host buffers in (pinned), parameters out; median of 3 runs",
+                       "mean_vertex_error_mm": {"median": 1e3 * float(np.median(verr)), "max": 1e3 * float(verr.max()),
+                                                "last_frame": 1e3 * float(verr[-1])},
+                       "roofline": {"bound": "hbm", "achieved": alg_t / trk / 1e9, "peak": peak, "unit": "GB/s",
+                                    "frac": alg_t / trk / 1e9 / peak,
+                                    "note": "SURVEY 8(d) bytes (20 N + iterations x (16 N + 4 P^2 + 4 P) + 24 V per frame) over the wall "
+                                            "time; one frame at a time is latency bound: 11 sequential evaluations, each ending in one "
+                                            "85 x 85 solve on a single CTA (profiles/r2_single_fit_fp64.json)"}}
+            if not args.no_parity:   # the oracle tracks the first frames the same way (each fit starts from ITS previous fit)
+                import oracle as orc_t
+                om_t = orc_t.OracleModel(os.path.join(GOLD, "model_synth.npz"), pr)
+                oo_t = orc_t.OracleOptimizer(om_t, num_parts, part_map)
+                oopt_t = orc_t.default_options(orc_t.SOLVER_GN_LM)
+                oopt_t.function_tolerance, oopt_t.num_threads = 0.0, 8
+                xo, errs_t = x_start, []
+                for t in range(6):
+                    xo = oo_t.optimize(sp[t], sl[t], xo, oopt_t)[0]
+                    errs_t.append(float(np.abs(xo - x_trk[t]).max()))
+                sec_trk["parity"] = {"frames_checked": 6, "max_param_err": max(errs_t), "per_frame": errs_t, "tolerance": 1e-4,
+                                     "oracle": "oracle gn_lm tracking the same frames sequentially"}
+            line["secondary"]["tracking"] = sec_trk
+        except Exception as exc:
+            line["secondary"]["tracking_error"] = repr(exc)
+        # ---- BASELINE.json configs[4]: stress, one 200k-point cloud, 50 LM iterations, J^T J on tcgen05 (split bf16, fp32
+        #      TMEM accumulate); the fp64 path on the same cloud beside it; parity of both against the oracle ----
+        try:
+            from harness import synth
+            sc = 4.6
+            big, big_l, _, _ = synth.render_cloud(model, clouds_gt[0], part_map, width=int(synth.WIDTH * sc), height=int(synth.HEIGHT * sc),
+                                                  fx=synth.FX * sc, fy=synth.FY * sc, cx=synth.CX * sc, cy=synth.CY * sc)
+            NBIG = 200_000
+            if len(big) < NBIG:
+                raise RuntimeError("stress cloud has only %d points" % len(big))
+            keep = np.sort(np.random.default_rng(9).choice(len(big), NBIG, replace=False))
+            big, big_l = np.ascontiguousarray(big[keep]), np.ascontiguousarray(big_l[keep])
+            fbig = Fitter(model, num_parts, part_map, 1, NBIG + 64, local_rank)
+            fbig.upload(big, big_l, np.array([0, NBIG], dtype=np.int64))
+            sec_st = {"what": "BASELINE.json configs[4]: one %d-point cloud (the first bench frame rendered at %.1fx resolution), "
+                              "icp_iters=1, 50 LM iterations (function_tolerance=0)" % (NBIG, sc), "points": NBIG}
+            x_by = {}
+            for name, prec in (("tensor", _lib.JTJ_BF16_TENSOR), ("fp64", _lib.JTJ_FP64)):
+                ob = default_options()
+                ob.function_tolerance, ob.max_iters_per_icp, ob.jtj_precision = 0.0, 50, prec
+                fbig.fit_resident(x0[0][None], ob)
+                ms_l = []
+                for _ in range(5):
+                    fbig.timer_start()
+                    fbig.fit_resident(x0[0][None], ob)
+                    ms_l.append(fbig.timer_stop())
+                xb, stb, _ = fbig.download()
+                x_by[name] = xb[0]
+                fbig.set_profiling(True)
+                fbig.fit_resident(x0[0][None], ob)
+                fbig.synchronize()
+                km = {k: round(v[0], 4) for k, v in fbig.kernel_ms().items()}
+                fbig.set_profiling(False)
+                ms = float(np.median(ms_l))
+                itb = stb[0].iterations
+                alg_b = 20.0 * NBIG + itb * (16.0 * NBIG + 4.0 * P * P + 4.0 * P) + 2 * 12.0 * V
+                sec_st[name] = {"fit_ms": ms, "fits_per_s": 1e3 / ms, "iterations": int(itb), "matched_vertices": int(stb[0].num_matched_vertices),
+                                "final_cost": float(stb[0].final_cost), "kernel_ms": km,
+                                "roofline": {"bound": "hbm", "achieved": alg_b / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                             "frac": alg_b / (ms * 1e-3) / 1e9 / peak,
+                                             "note": "SURVEY 8(d) bytes over the device time of the whole fit (CUDA events); a single "
+                                                     "frame is a chain of 51 evaluations x (chunk tasks on <= 36 CTAs, then one solve)"}}
+            sec_st["tensor_vs_fp64_max_param_diff"] = float(np.abs(x_by["tensor"] - x_by["fp64"]).max())
+            if not args.no_parity:
+                import oracle as orc_s
+                om_s = orc_s.OracleModel(os.path.join(GOLD, "model_synth.npz"), pr)
+                oo_s = orc_s.OracleOptimizer(om_s, num_parts, part_map)
+                oopt_s = orc_s.default_options(orc_s.SOLVER_GN_LM)
+                oopt_s.function_tolerance, oopt_s.num_threads, oopt_s.max_iters_per_icp = 0.0, 8, 50
+                tA = time.perf_counter()
+                xo_s, st_s = oo_s.optimize(big, big_l, x0[0], oopt_s)[:2]
+                sec_st["parity"] = {"oracle": "oracle gn_lm, 50 iterations, same cloud", "oracle_s": time.perf_counter() - tA,
+                                    "oracle_iterations": int(st_s.iterations),
+                                    "fp64_max_param_err": float(np.abs(x_by["fp64"] - xo_s).max()),
+                                    "tensor_max_param_err": float(np.abs(x_by["tensor"] - xo_s).max()),
+                                    "tolerance_fp64_path": 1e-4,
+                                    "note": "the tensor path is not a parity path (fp32 accumulation inside the tensor core truncates; "
+                                            "DESIGN.md section 5): its error is reported, not gated"}
+            fbig.close()
+            # the same cloud as a batch (throughput of the stress shape; every frame starts from a slightly different point)
+            BB = 32
+            fbb = Fitter(model, num_parts, part_map, BB, BB * NBIG + 64, local_rank)
+            fbb.upload(np.concatenate([big] * BB), np.concatenate([big_l] * BB), np.arange(BB + 1, dtype=np.int64) * NBIG)
+            xb0 = np.tile(x0[0], (BB, 1))
+            xb0[:, :3] += np.random.default_rng(3).normal(0.0, 0.005, (BB, 3))
+            for name, prec in (("tensor", _lib.JTJ_BF16_TENSOR), ("fp64", _lib.JTJ_FP64)):
+                ob = default_options()
+                ob.function_tolerance, ob.max_iters_per_icp, ob.jtj_precision = 0.0, 50, prec
+                fbb.fit_resident(xb0, ob)
+                fbb.timer_start()
+                for _ in range(3):
+                    fbb.fit_resident(xb0, ob)
+                ms = fbb.timer_stop() / 3
+                _, stbb, _ = fbb.download()
+                itm = float(np.mean([s_.iterations for s_ in stbb]))
+                alg_bb = BB * (20.0 * NBIG + itm * (16.0 * NBIG + 4.0 * P * P + 4.0 * P) + 2 * 12.0 * V)
+                sec_st[name]["batch%d" % BB] = {"frames_per_s": BB / (ms * 1e-3), "ms_per_batch": ms, "mean_iterations": itm,
+                                                "roofline": {"bound": "hbm", "achieved": alg_bb / (ms * 1e-3) / 1e9, "peak": peak,
+                                                             "unit": "GB/s", "frac": alg_bb / (ms * 1e-3) / 1e9 / peak}}
+            fbb.close()
+            line["secondary"]["stress_200k"] = sec_st
+        except Exception as exc:
+            line["secondary"]["stress_200k_error"] = repr(exc)
         f1.close()
         # SURVEY 8(d) secondary mode: ten ICP iterations (visibility + NN each) of one solver iteration, same resident batch
         try:

@@ -123,6 +123,38 @@ def perturbed_start(model, x_gt, rng, rot_sigma=0.1):
     return x
 
 
+def slerp_sequence(model, rng, frames, key_every=30, pose_scale=0.6):
+    """BASELINE.json configs[3]: ground-truth parameters of a smooth motion -- random key poses (Avatar::randomize style) every
+    `key_every` frames, root translation interpolated linearly, every joint rotation by spherical linear interpolation,
+    shape constant.  Returns [frames][nx]."""
+    J = model.numJoints()
+    nkeys = (frames + key_every - 1) // key_every + 1
+    keys = [random_params(model, rng, pose_scale=pose_scale) for _ in range(nkeys)]
+    for k in range(1, nkeys):                       # same shape, nearby root, same hemisphere for every quaternion
+        keys[k][3 + 4 * J:] = keys[0][3 + 4 * J:]
+        keys[k][:3] = keys[k - 1][:3] + rng.uniform(-0.15, 0.15, 3)
+        q_up = _aa_quat([0, 1, 0], rng.normal(0.0, 0.3))
+        keys[k][3:7] = _qmul(q_up, keys[k - 1][3:7])
+        for j in range(J):
+            a, b = keys[k - 1][3 + 4 * j:7 + 4 * j], keys[k][3 + 4 * j:7 + 4 * j]
+            if np.dot(a, b) < 0:
+                keys[k][3 + 4 * j:7 + 4 * j] = -b
+    out = np.zeros((frames, keys[0].shape[0]))
+    for t in range(frames):
+        k, u = divmod(t, key_every)
+        u = u / key_every
+        a, b = keys[k], keys[k + 1]
+        x = (1 - u) * a + u * b                       # translation and shape
+        for j in range(J):
+            qa, qb = a[3 + 4 * j:7 + 4 * j], b[3 + 4 * j:7 + 4 * j]
+            d = float(np.clip(np.dot(qa, qb), -1.0, 1.0))
+            th = np.arccos(d)
+            q = qa if th < 1e-9 else (np.sin((1 - u) * th) * qa + np.sin(u * th) * qb) / np.sin(th)
+            x[3 + 4 * j:7 + 4 * j] = q / np.linalg.norm(q)
+        out[t] = x
+    return out
+
+
 def vertex_parts(model, part_map):
     return np.array([part_map[pairs[0][1]] for pairs in model.assignedJoints], dtype=np.int32)
 

@@ -163,6 +163,12 @@ int avb_track_sequence(avb_fitter* fitter, int32_t T, const double* data_clouds,
  * (bench.py `value`): upload once, fit many times from different warm starts, download. */
 int avb_upload_batch(avb_fitter* fitter, int32_t batch, const double* data_clouds,
                      const int32_t* data_part_labels, const int64_t* offsets);
+/* The same with the cloud as FLOATS (12 instead of 24 bytes per point over PCIe).  Depth cameras deliver float points
+ * (CameraIntrin::to3D / depthToXYZ compute in float, Calibration.cpp:68-95) and the reference widens them on the host
+ * when it fills the Eigen cloud (demo.cpp:241-243); here the widening runs on the device and yields the same doubles,
+ * so every result is bit-identical to avb_upload_batch of the widened cloud. */
+int avb_upload_batch_f32(avb_fitter* fitter, int32_t batch, const float* data_clouds,
+                         const int32_t* data_part_labels, const int64_t* offsets);
 int avb_fit_resident(avb_fitter* fitter, const double* x_in, const avb_options* opt);  /* async enqueue */
 
 /* Data-cloud construction on the device.  Replaces the caller-side loops of
