@@ -526,6 +526,24 @@ def main():
                               "frames_checked": ns, "max_param_err": max(errs), "median_param_err": float(np.median(errs)),
                               "tolerance": 1e-4, "iterations_and_accepts_equal": bool(it_eq),
                               "nn_mismatches": nn_bad, "nn_points_checked": int(offp[min(4, ns)]), "jtj": args.jtj}
+            try:   # the same frames through the REFERENCE's own AvatarOptimizer.cpp (oracle/_ref/libref_avatar.so, prebuilt)
+                if orc_p.ref_avatar_available():
+                    import tempfile
+                    with tempfile.TemporaryDirectory() as td:
+                        ppath = os.path.join(td, "pose_prior.txt")
+                        orc_p.write_prior_text(ppath, pr["weights"], pr["means"], pr["covs"])
+                        ro_p = orc_p.RefOptimizer(os.path.join(GOLD, "model_synth.npz"), om_p, ppath, num_parts, part_map)
+                        errs_r = []
+                        for i, b in enumerate(sample[:4]):
+                            x_r, _ = ro_p.optimize(x0[b], pts[b], labs[b], icp_iters=1, max_iters=10, function_tolerance=0.0)
+                            errs_r.append(float(np.abs(x_mine[b] - x_r).max()))
+                    line["parity"]["reference_source"] = {
+                        "what": "the reference's own AvatarOptimizer.cpp / Avatar.cpp / GaussianMixture.cpp compiled against stand-in "
+                                "Eigen / Ceres headers (oracle/shim): its visibility, findNN, cost functors and parameterization, "
+                                "driven by a restated Levenberg-Marquardt loop (Ceres is absent)",
+                        "frames_checked": len(errs_r), "max_param_err": max(errs_r)}
+            except Exception as exc:
+                line["parity"]["reference_source"] = {"error": repr(exc)}
             if world > 1:   # frames of rank 1 refitted on this GPU == the gathered result of rank 1, bit for bit
                 lo1, hi1 = gatherer.ranges[1]
                 nchk = min(8, hi1 - lo1)

@@ -410,3 +410,152 @@ def ref_nanoflann_nn(points, queries, fma=False):
     out = np.zeros(queries.shape[0], dtype=np.int32)
     lib.ref_nanoflann_nn(_p(points), points.shape[0], _p(queries), queries.shape[0], _p(out))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the reference's OWN Avatar.cpp + GaussianMixture.cpp (oracle/_ref/libref_avatar.so, compiled from /root/reference
+# against the Eigen stand-in in oracle/shim): what the oracle's restatement of Avatar::update / GaussianMixture is
+# pinned against
+# ---------------------------------------------------------------------------------------------------------------
+REF_AVATAR_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libref_avatar.so")
+_ref_avatar = None
+
+
+def _ref_avatar_lib():
+    global _ref_avatar
+    if _ref_avatar is None:
+        if not os.path.exists(REF_AVATAR_PATH):
+            return None
+        L = C.CDLL(REF_AVATAR_PATH)
+        L.ref_gmm_load.restype = _P
+        L.ref_gmm_load.argtypes = [C.c_char_p]
+        L.ref_gmm_free.argtypes = [_P]
+        L.ref_gmm_dims.argtypes = [_P, _P, _P]
+        L.ref_gmm_residual.restype = C.c_int
+        L.ref_gmm_residual.argtypes = [_P, _P, _P]
+        L.ref_gmm_pdf.restype = C.c_double
+        L.ref_gmm_pdf.argtypes = [_P, _P]
+        L.ref_gmm_tables.argtypes = [_P, _P, _P]
+        L.ref_model_create.restype = _P
+        L.ref_model_create.argtypes = [C.c_int] * 3 + [_P] * 5
+        L.ref_model_free.argtypes = [_P]
+        L.ref_avatar_update.argtypes = [_P] * 7
+        L.ref_avatar_align.argtypes = [_P] * 6
+        L.ref_model2_create.restype = _P
+        L.ref_model2_create.argtypes = [C.c_int] * 4 + [_P] * 6 + [C.c_int] + [_P] * 5 + [C.c_char_p]
+        L.ref_model2_free.argtypes = [_P]
+        L.ref_opt_create.restype = _P
+        L.ref_opt_create.argtypes = [_P, C.c_int, _P]
+        L.ref_opt_free.argtypes = [_P]
+        L.ref_opt_run.restype = C.c_int
+        L.ref_opt_run.argtypes = [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                  C.c_int, _P, _P, _P, _P, _P]
+        _ref_avatar = L
+    return _ref_avatar
+
+
+def write_prior_text(path, weights, means, covs):
+    """the reference's pose_prior.txt layout (GaussianMixture.cpp:12-44): nComps nDims, weights, means, covariances"""
+    with open(path, "w") as fh:
+        fh.write("%d %d\n" % means.shape)
+        fh.write(" ".join(repr(float(v)) for v in weights) + "\n")
+        for m in means:
+            fh.write(" ".join(repr(float(v)) for v in m) + "\n")
+        for c in covs:
+            for row in c:
+                fh.write(" ".join(repr(float(v)) for v in row) + "\n")
+
+
+class RefGaussianMixture:
+    """ark::GaussianMixture of the reference, loaded from a pose_prior.txt"""
+
+    def __init__(self, path):
+        L = _ref_avatar_lib()
+        self.h = L.ref_gmm_load(path.encode())
+        c, d = C.c_int(), C.c_int()
+        L.ref_gmm_dims(self.h, C.byref(c), C.byref(d))
+        self.C, self.D = c.value, d.value
+
+    def residual(self, x):
+        out = np.zeros(self.D + 1)
+        comp = _ref_avatar_lib().ref_gmm_residual(self.h, _p(_f64(x)), _p(out))
+        return out, comp
+
+    def pdf(self, x):
+        return _ref_avatar_lib().ref_gmm_pdf(self.h, _p(_f64(x)))
+
+    def tables(self):
+        pc, cl = np.zeros((self.C, self.D, self.D)), np.zeros(self.C)
+        _ref_avatar_lib().ref_gmm_tables(self.h, _p(pc), _p(cl))
+        return pc, cl
+
+
+class RefAvatar:
+    """ark::Avatar of the reference over an AvatarModel filled from the npz arrays"""
+
+    def __init__(self, npz_path):
+        z = np.load(npz_path)
+        vt, sd = _f64(z["v_template"]), _f64(z["shapedirs"])
+        jr, wt = _f64(z["J_regressor"]), _f64(z["weights"])
+        parents = np.ascontiguousarray(z["kintree_table"][0].astype(np.uint32).astype(np.int32))
+        self.V, self.J, self.K = vt.shape[0], parents.shape[0], sd.shape[2]
+        self.h = _ref_avatar_lib().ref_model_create(self.V, self.J, self.K, _p(vt), _p(sd), _p(jr), _p(wt), _p(parents))
+
+    def update(self, p, R, w):
+        cloud, jp, jt = np.zeros((self.V, 3)), np.zeros((self.J, 3)), np.zeros((self.J, 12))
+        _ref_avatar_lib().ref_avatar_update(self.h, _p(_f64(p)), _p(_f64(R)), _p(_f64(w)), _p(cloud), _p(jp), _p(jt))
+        return cloud, jp, jt
+
+    def align_to_joints(self, pos):
+        p, R, w0, smpl = np.zeros(3), np.zeros((self.J, 3, 3)), np.zeros(1), np.zeros(3 * (self.J - 1))
+        _ref_avatar_lib().ref_avatar_align(self.h, _p(_f64(pos)), _p(p), _p(R), _p(w0), _p(smpl))
+        return p, R, float(w0[0]), smpl
+
+
+def ref_avatar_available():
+    return _ref_avatar_lib() is not None
+
+
+class RefOptimizer:
+    """ark::AvatarOptimizer of the reference (AvatarOptimizer.cpp compiled from /root/reference): its own prologue, visibility,
+    findNN over nanoflann, cost functors, evaluation callback and quaternion parameterization.  The solver loop is the
+    Levenberg-Marquardt restatement of oracle/ref_optimizer.cpp (Ceres is absent).  The model's derived tables (joint shape
+    regressor, assigned joints) are taken from the oracle model: AvatarModel.cpp's loaders are not compiled."""
+
+    def __init__(self, npz_path, omodel, prior_text_path, num_parts, part_map):
+        L = _ref_avatar_lib()
+        z = np.load(npz_path)
+        vt, sd = _f64(z["v_template"]), _f64(z["shapedirs"])
+        jr, wt = _f64(z["J_regressor"]), _f64(z["weights"])
+        parents = np.ascontiguousarray(z["kintree_table"][0].astype(np.uint32).astype(np.int32))
+        faces = np.ascontiguousarray(np.asarray(z["f"]).astype(np.int64).astype(np.int32))
+        self.V, self.J, self.K, self.F = vt.shape[0], parents.shape[0], sd.shape[2], faces.shape[0]
+        base, reg, _init = omodel.joint_reg()
+        start, joint, weight = omodel.assigned()
+        self._keep = (vt, sd, jr, wt, parents, faces, base, reg, start, joint, weight)
+        self.hm = L.ref_model2_create(self.V, self.J, self.K, self.F, _p(vt), _p(sd), _p(jr), _p(wt), _p(parents), _p(faces), 1,
+                                      _p(_f64(base)), _p(_f64(reg)), _p(start), _p(joint), _p(_f64(weight)),
+                                      (prior_text_path or "").encode())
+        self.part_map = np.ascontiguousarray(part_map, dtype=np.int32)
+        self.h = L.ref_opt_create(self.hm, int(num_parts), _p(self.part_map))
+        self.nx, self.P = 3 + 4 * self.J + self.K, 3 + 3 * self.J + self.K
+
+    def _run(self, x, data, labels, icp_iters, max_iters, ftol, beta_pose, beta_shape, occlusion, threads, mode):
+        x = np.array(x, dtype=np.float64, copy=True)
+        data, labels = _f64(data), np.ascontiguousarray(labels, dtype=np.int32)
+        cost, grad, H = np.zeros(1), np.zeros(self.P), np.zeros((self.P, self.P))
+        stats, costs = np.zeros(3, np.int32), np.zeros(2)
+        _ref_avatar_lib().ref_opt_run(self.h, _p(x), _p(data), _p(labels), data.shape[0], icp_iters, max_iters, ftol, beta_pose,
+                                      beta_shape, int(occlusion), threads, mode, _p(cost), _p(grad), _p(H), _p(stats), _p(costs))
+        return x, float(cost[0]), grad, H, stats, costs
+
+    def evaluate(self, x, data, labels, beta_pose=0.1, beta_shape=1.0, occlusion=True):
+        """cost, gradient [P] and J^T J [P, P] of the reference's residual blocks at x (its own correspondences)"""
+        _, cost, grad, H, stats, _ = self._run(x, data, labels, 1, 0, 0.0, beta_pose, beta_shape, occlusion, 1, 1)
+        return cost, grad, H, int(stats[2])
+
+    def optimize(self, x, data, labels, icp_iters=1, max_iters=10, function_tolerance=1e-4, beta_pose=0.1, beta_shape=1.0,
+                 occlusion=True, threads=4):
+        x, _, _, _, stats, costs = self._run(x, data, labels, icp_iters, max_iters, function_tolerance, beta_pose, beta_shape,
+                                             occlusion, threads, 0)
+        return x, {"iterations": int(stats[0]), "accepted": int(stats[1]), "initial_cost": float(costs[0]), "final_cost": float(costs[1])}

@@ -46,6 +46,11 @@ struct Vec3f {
     float operator[](int i) const { return val[i]; }
     float& operator[](int i) { return val[i]; }
 };
+struct Vec3b {
+    unsigned char val[3] = {0, 0, 0};
+    unsigned char operator[](int i) const { return val[i]; }
+    unsigned char& operator[](int i) { return val[i]; }
+};
 struct Vec4d {
     double val[4] = {0, 0, 0, 0};
     double operator[](int i) const { return val[i]; }
@@ -60,6 +65,16 @@ public:
     Mat(Size s, int type) : rows(s.height), cols(s.width), elem(type == CV_32FC3 ? 12 : (type == CV_8U ? 1 : 4)) {   // owning
         own.assign((size_t)rows * cols * elem, 0);
         data = own.data();
+    }
+    Mat(const Mat& o) : rows(o.rows), cols(o.cols), elem(o.elem), data(o.data), own(o.own) { if (!own.empty()) data = own.data(); }
+    Mat(Mat&& o) noexcept : rows(o.rows), cols(o.cols), elem(o.elem), data(o.data), own(std::move(o.own)) { if (!own.empty()) data = own.data(); }
+    Mat& operator=(const Mat& o) { rows = o.rows; cols = o.cols; elem = o.elem; own = o.own; data = own.empty() ? o.data : own.data(); return *this; }
+    Mat& operator=(Mat&& o) noexcept { rows = o.rows; cols = o.cols; elem = o.elem; own = std::move(o.own); data = own.empty() ? o.data : own.data(); return *this; }
+    bool empty() const { return rows == 0 || cols == 0; }
+    static Mat zeros(Size s, int type) { return Mat(s, type); }
+    template <class V> void setTo(V v) {   // 8-bit and 32-bit integer images only (what AvatarRenderer.cpp fills)
+        if (elem == 1) std::memset(data, (int)v, (size_t)rows * cols);
+        else for (size_t i = 0; i < (size_t)rows * cols; ++i) reinterpret_cast<int32_t*>(data)[i] = (int32_t)v;
     }
     Size size() const { return Size(cols, rows); }
     template <class T> T* ptr(int r) { return reinterpret_cast<T*>(data + (size_t)r * cols * elem); }

@@ -26,6 +26,26 @@ int main(int argc, char** argv) {
         return 0;
     }
     Avatar ava(model);
+    if (std::string(argv[2]) == "--align") {  // host-only: Avatar::alignToJoints + smplParams on 24 joint positions from a file
+        FILE* fj = std::fopen(argv[3], "rb");
+        if (!fj) return 3;
+        std::vector<double> jp(3 * 24);
+        if (std::fread(jp.data(), 8, jp.size(), fj) != jp.size()) return 3;
+        std::fclose(fj);
+        CloudType pos(3, 24);
+        for (int j = 0; j < 24; ++j)
+            for (int c = 0; c < 3; ++c) pos(c, j) = jp[3 * (size_t)j + c];
+        ava.alignToJoints(pos);
+        std::printf("P %.17g %.17g %.17g\nW0 %.17g\nR", ava.p(0), ava.p(1), ava.p(2), ava.w(0));
+        for (int j = 0; j < 24; ++j)
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) std::printf(" %.17g", ava.r[(size_t)j](a, b));
+        const Eigen::VectorXd sp = ava.smplParams();
+        std::printf("\nSMPL");
+        for (long i = 0; i < sp.rows(); ++i) std::printf(" %.17g", sp(i));
+        std::printf("\n");
+        return 0;
+    }
     FILE* fp = std::fopen(argv[2], "rb");
     if (!fp) return 3;
     int32_t hdr[4];  // N, J, K, numParts

@@ -412,3 +412,46 @@ def test_float32_upload_is_bit_identical(model, omodel, prior_arrays):
         out.append(ft.download()[0])
     ft.close()
     assert np.array_equal(out[0], out[1]) and np.array_equal(out[0], out[2])
+
+
+def test_device_matches_reference_source(model, oracle_mod, omodel, prior_arrays, tmp_path):
+    """The device against the reference's OWN AvatarOptimizer.cpp (oracle/_ref/libref_avatar.so: its visibility, findNN, cost
+    functors and parameterization; Levenberg-Marquardt loop restated because Ceres is absent): cost / J^T r / J^T J at the start
+    point, and the fitted parameters after one ICP iteration of ten LM steps."""
+    if not oracle_mod.ref_avatar_available():
+        pytest.skip("oracle/_ref/libref_avatar.so not built")
+    from avatar_b200 import Fitter
+    part_map, num_parts = prior_arrays["part_map"], int(prior_arrays["num_parts"])
+    path = str(tmp_path / "pose_prior.txt")
+    oracle_mod.write_prior_text(path, prior_arrays["weights"], prior_arrays["means"], prior_arrays["covs"])
+    import os
+    from conftest import GOLDEN
+    ro = oracle_mod.RefOptimizer(os.path.join(GOLDEN, "model_synth.npz"), omodel, path, num_parts, part_map)
+    fr = [_frame(model, omodel, prior_arrays, s) for s in (1000, 1001, 1002, 1003)]
+    pts = np.concatenate([f[2] for f in fr])
+    lab = np.concatenate([f[3] for f in fr])
+    off = np.cumsum([0] + [len(f[2]) for f in fr]).astype(np.int64)
+    J = model.numJoints()
+    x0 = np.stack([f[1] for f in fr])
+    for b in range(len(fr)):      # the reference's prologue goes through rotation matrices (:1250-1254)
+        for j in range(J):
+            x0[b, 3 + 4 * j:7 + 4 * j] = oracle_mod.rotmat_to_quat(oracle_mod.quat_to_rotmat(x0[b, 3 + 4 * j:7 + 4 * j]))
+    ft = Fitter(model, num_parts, part_map, len(fr), int(off[-1]) + 64)
+    ft.upload(pts, lab, off)
+    o = _opts(function_tolerance=0.0)
+    ft.debug_correspond(x0, o)
+    cost, grad, H = ft.debug_evaluate(x0, o)
+    xg, st, _ = ft.fit_batch(pts, lab, off, x0, o)
+    ft.close()
+    for b in range(len(fr)):
+        p, l = pts[off[b]:off[b + 1]], lab[off[b]:off[b + 1]]
+        c_r, g_r, H_r, _ = ro.evaluate(x0[b], p, l, o.beta_pose, o.beta_shape)
+        assert abs(cost[b] - c_r) <= 1e-9 * c_r
+        assert np.abs(grad[b] - g_r).max() <= 2e-6 * np.abs(g_r).max()   # fp32 Jacobian records
+        scale = np.sqrt(np.outer(np.diag(H_r), np.diag(H_r)))
+        assert (np.abs(H[b] - H_r) / scale).max() <= 2e-5          # fp32 Jacobian records (DESIGN.md section 5)
+        x_r, st_r = ro.optimize(x0[b], p, l, icp_iters=1, max_iters=10, function_tolerance=0.0)
+        err = np.abs(xg[b] - x_r).max()
+        print(f"device vs reference source, frame {b}: max parameter difference {err:.2e}, iterations {st[b].iterations} / {st_r['iterations']}")
+        assert err < 1e-4
+        assert st[b].iterations == st_r["iterations"] and st[b].accepted_steps == st_r["accepted"]

@@ -694,3 +694,149 @@ def test_rtree_postprocess_oracle_small_cases(oracle_mod):
                 sizes = ndimage.sum(img == p, lbl, range(1, n + 1))
                 keep = int(np.argmax(sizes)) + 1          # first maximum = first in raster order of its first pixel
                 assert np.array_equal(got == p, lbl == keep)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the oracle against the reference's OWN Avatar.cpp / GaussianMixture.cpp (compiled into oracle/_ref/libref_avatar.so)
+# ---------------------------------------------------------------------------------------------------------------
+def _need_ref_avatar(oracle_mod):
+    if not oracle_mod.ref_avatar_available():
+        pytest.skip("oracle/_ref/libref_avatar.so not built (reference tree absent and no prebuilt library)")
+
+
+def test_avatar_update_matches_reference_source(oracle_mod, omodel, prior_arrays):
+    """Avatar::update (Avatar.cpp:22-75), the reference's code itself: cloud, joint positions and joint transforms of the
+    oracle's restatement agree to rounding (the stand-in Eigen sums in index order, the oracle in its own order)"""
+    _need_ref_avatar(oracle_mod)
+    from harness import synth
+    ref = oracle_mod.RefAvatar(os.path.join(GOLDEN, "model_synth.npz"))
+    hm = synth.HostModel(os.path.join(GOLDEN, "model_synth.npz"), prior_arrays)
+    worst = 0.0
+    for seed in range(6):
+        rng = np.random.default_rng(400 + seed)
+        x = synth.random_params(hm, rng)
+        J = omodel.J
+        R = np.stack([oracle_mod.quat_to_rotmat(x[3 + 4 * j:7 + 4 * j]) for j in range(J)])
+        w = x[3 + 4 * J:] * (0.0 if seed == 0 else 1.0)
+        c_o, jp_o, jt_o = omodel.update(x[:3], R, w)
+        c_r, jp_r, jt_r = ref.update(x[:3], R, w)
+        worst = max(worst, np.abs(c_o - c_r).max(), np.abs(jp_o - jp_r).max(), np.abs(jt_o - jt_r).max())
+    print(f"Avatar::update, oracle vs reference source: max abs difference {worst:.2e}")
+    assert worst < 1e-12
+
+
+def test_gaussian_mixture_matches_reference_source(oracle_mod, omodel, prior_arrays, tmp_path):
+    """GaussianMixture::load / residual / pdf (GaussianMixture.cpp:12-114), the reference's code itself, against the
+    oracle's prior tables and residual: prec_cho = chol(inv(cov)), consts_log, the min-component residual and its index"""
+    _need_ref_avatar(oracle_mod)
+    path = str(tmp_path / "pose_prior.txt")
+    oracle_mod.write_prior_text(path, prior_arrays["weights"], prior_arrays["means"], prior_arrays["covs"])
+    ref = oracle_mod.RefGaussianMixture(path)
+    assert (ref.C, ref.D) == (omodel.C, omodel.D)
+    pc_r, cl_r = ref.tables()
+    pc_o, cl_o = omodel.prior()
+    scale = np.abs(pc_r).max()
+    assert np.abs(pc_o - pc_r).max() < 1e-9 * scale      # inverse + Cholesky of a covariance: conditioning, not rounding order
+    assert np.abs(cl_o - cl_r).max() < 1e-9 * np.abs(cl_r).max()
+    rng = np.random.default_rng(12)
+    for k in range(20):
+        comp = rng.integers(0, ref.C)
+        x = prior_arrays["means"][comp] + 0.3 * rng.standard_normal(ref.D)
+        r_r, c_r = ref.residual(x)
+        r_o, c_o = omodel.gmm_residual(x)
+        assert c_r == c_o
+        assert np.abs(r_r - r_o).max() < 1e-9 * max(1.0, np.abs(r_r).max())
+        assert ref.pdf(x) >= 0.0
+
+
+def test_facade_align_to_joints_matches_reference_source(oracle_mod, omodel, prior_arrays, build_all, tmp_path):
+    """Avatar::alignToJoints + smplParams (Avatar.cpp:128-193): the facade's host code (avatar_b200/cpp/ark_b200.cpp) against
+    the reference's own source on the joints of random poses, incl. a NaN joint (the reference keeps identity there)"""
+    _need_ref_avatar(oracle_mod)
+    import shutil
+    import subprocess
+    from harness import synth
+    from avatar_b200 import GaussianMixture
+    d = tmp_path / "avatar-model"
+    d.mkdir()
+    shutil.copy(os.path.join(GOLDEN, "model_synth.npz"), str(d / "model.npz"))
+    GaussianMixture.from_arrays(prior_arrays["weights"], prior_arrays["means"], prior_arrays["covs"]).save(str(d / "pose_prior.txt"))
+    ref = oracle_mod.RefAvatar(os.path.join(GOLDEN, "model_synth.npz"))
+    hm = synth.HostModel(os.path.join(GOLDEN, "model_synth.npz"), prior_arrays)
+    J = omodel.J
+    for seed in range(3):
+        x = synth.random_params(hm, np.random.default_rng(77 + seed))
+        R = np.stack([oracle_mod.quat_to_rotmat(x[3 + 4 * j:7 + 4 * j]) for j in range(J)])
+        _, jp, _ = ref.update(x[:3], R, np.zeros(omodel.K))
+        if seed == 2:
+            jp[20] = np.nan                               # an undetected joint
+        p_r, R_r, w0_r, smpl_r = ref.align_to_joints(jp)
+        path = str(tmp_path / "joints.bin")
+        np.ascontiguousarray(jp, dtype="<f8").tofile(path)
+        out = subprocess.run([os.path.join(ROOT, "tests", "cpp", "facade_demo"), str(d), "--align", path], capture_output=True,
+                             text=True, check=True).stdout
+        lines = {l.split()[0]: np.array([float(v) for v in l.split()[1:]]) for l in out.strip().splitlines()}
+        assert np.allclose(lines["P"], p_r, atol=1e-14, equal_nan=True)
+        assert np.allclose(lines["W0"][0], w0_r, rtol=1e-12, equal_nan=True)
+        R_f = lines["R"].reshape(J, 3, 3)
+        assert np.array_equal(np.isnan(R_f), np.isnan(R_r))       # a NaN joint poisons the same rotations in both
+        assert np.nanmax(np.abs(R_f - R_r)) < 1e-12
+        assert np.array_equal(np.isnan(lines["SMPL"]), np.isnan(smpl_r))
+        assert np.nanmax(np.abs(lines["SMPL"] - smpl_r)) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the oracle against the reference's OWN AvatarOptimizer.cpp (cost functors, visibility, findNN, parameterization)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ref_opt(oracle_mod, omodel, prior_arrays, tmp_path_factory):
+    _need_ref_avatar(oracle_mod)
+    path = str(tmp_path_factory.mktemp("prior") / "pose_prior.txt")
+    oracle_mod.write_prior_text(path, prior_arrays["weights"], prior_arrays["means"], prior_arrays["covs"])
+    return oracle_mod.RefOptimizer(os.path.join(GOLDEN, "model_synth.npz"), omodel, path, int(prior_arrays["num_parts"]),
+                                   prior_arrays["part_map"])
+
+
+def _prologue(oracle_mod, x, J):
+    """AvatarOptimizer::optimize starts from rotation matrices (:1250-1254): quaternion -> matrix -> quaternion"""
+    x = x.copy()
+    for j in range(J):
+        x[3 + 4 * j:7 + 4 * j] = oracle_mod.rotmat_to_quat(oracle_mod.quat_to_rotmat(x[3 + 4 * j:7 + 4 * j]))
+    return x
+
+
+def test_reference_cost_functors_match_oracle_evaluate(oracle_mod, omodel, oopt, ref_opt, frames):
+    """AvatarICPCostFunctor + AvatarPosePriorCostFunctor + AvatarShapePriorCostFunctor evaluated by the reference's own code
+    (AvatarOptimizer.cpp:463-723 with its evaluation callback :162-460, its visibility :1347-1362 and findNN :841-920), projected
+    to the tangent space by its FakeQuaternionParameterization: cost, J^T r and J^T J equal the oracle's evaluate() to
+    rounding.  This is what pins rows a4-a9 of SURVEY.md section 8 to the reference instead of to a restatement."""
+    for k, (x_gt, x0, pts, lab) in enumerate(frames):
+        x0 = _prologue(oracle_mod, x0, omodel.J)
+        bp, bs = [(0.1, 1.0), (0.05, 0.12), (0.0, 0.0)][k % 3]
+        c_r, g_r, H_r, nblocks = ref_opt.evaluate(x0, pts, lab, bp, bs)
+        cloud = omodel.update_x(x0)[0]
+        nn = oopt.find_nn(cloud, oopt.visibility(cloud), pts, lab, 1)
+        c_o, g_o, H_o = oopt.evaluate(x0, pts, nn, bp, bs)
+        assert abs(c_o - c_r) <= 1e-12 * c_r
+        assert np.abs(g_o - g_r).max() <= 1e-11 * np.abs(g_r).max()
+        scale = np.sqrt(np.outer(np.diag(H_r), np.diag(H_r))) + 1e-300
+        assert (np.abs(H_o - H_r) / scale).max() <= 1e-11
+        assert nblocks >= 1000
+
+
+def test_reference_optimize_matches_oracle_fit(oracle_mod, omodel, oopt, ref_opt, frames):
+    """the reference's whole AvatarOptimizer::optimize (its code for everything but the solver: Ceres is absent, the loop is the
+    Levenberg-Marquardt restatement in oracle/ref_optimizer.cpp) against the oracle's gn_lm fit: one ICP iteration of ten LM
+    steps, and three ICP iterations with the default function tolerance (the correspondences are recomputed by the
+    reference's own findNN in between)"""
+    x_gt, x0, pts, lab = frames[0]
+    x0 = _prologue(oracle_mod, x0, omodel.J)
+    for icp, ftol in ((1, 0.0), (3, 1e-4)):
+        x_r, st_r = ref_opt.optimize(x0, pts, lab, icp_iters=icp, max_iters=10, function_tolerance=ftol)
+        op = oracle_mod.default_options(oracle_mod.SOLVER_GN_LM)
+        op.icp_iters, op.function_tolerance, op.num_threads = icp, ftol, 4
+        x_o, st_o = oopt.optimize(pts, lab, x0, op)[:2]
+        assert np.abs(x_r - x_o).max() < 1e-9
+        if icp == 1:   # (the oracle reports the counts of the last ICP iteration, the capture sums them)
+            assert st_r["iterations"] == st_o.iterations and st_r["accepted"] == st_o.accepted_steps
+        assert abs(st_r["final_cost"] - st_o.final_cost) <= 1e-10 * st_o.final_cost
