@@ -450,6 +450,7 @@ def _ref_avatar_lib():
         L.ref_opt_run.restype = C.c_int
         L.ref_opt_run.argtypes = [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                   C.c_int, _P, _P, _P, _P, _P]
+        L.ref_render.argtypes = [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P]
         _ref_avatar = L
     return _ref_avatar
 
@@ -548,6 +549,16 @@ class RefOptimizer:
         _ref_avatar_lib().ref_opt_run(self.h, _p(x), _p(data), _p(labels), data.shape[0], icp_iters, max_iters, ftol, beta_pose,
                                       beta_shape, int(occlusion), threads, mode, _p(cost), _p(grad), _p(H), _p(stats), _p(costs))
         return x, float(cost[0]), grad, H, stats, costs
+
+    def render(self, cloud, width, height, intrin):
+        """the reference's own AvatarRenderer::renderDepth / renderPartMask / renderFaces / renderLambert on a posed cloud"""
+        cloud = _f64(cloud)
+        k = np.ascontiguousarray(intrin, dtype=np.float32)
+        out = dict(depth=np.zeros((height, width), np.float32), parts=np.zeros((height, width), np.uint8),
+                   faces=np.zeros((height, width), np.int32), lambert=np.zeros((height, width), np.uint8))
+        _ref_avatar_lib().ref_render(self.hm, _p(cloud), _p(k), width, height, _p(self.part_map), _p(out["depth"]), _p(out["parts"]),
+                                     _p(out["faces"]), _p(out["lambert"]))
+        return out
 
     def evaluate(self, x, data, labels, beta_pose=0.1, beta_shape=1.0, occlusion=True):
         """cost, gradient [P] and J^T J [P, P] of the reference's residual blocks at x (its own correspondences)"""

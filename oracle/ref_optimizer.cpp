@@ -23,6 +23,7 @@
 
 #include "Avatar.h"
 #include "AvatarOptimizer.h"
+#include "AvatarRenderer.h"
 #include "Calibration.h"
 
 namespace {
@@ -418,6 +419,42 @@ int ref_opt_run(void* h, double* x, const double* data, const int32_t* labels, i
     costs[0] = g_cap.initial_cost;
     costs[1] = g_cap.final_cost;
     return 0;
+}
+
+// The reference's own AvatarRenderer (AvatarRenderer.cpp: projection, painter's ordering, the four render* functions over the
+// painters of AvatarHelpers.cpp) on a posed cloud [V][3]; intrin = fx, cx, fy, cy.  Any output may be null.
+void ref_render(void* model, const double* cloud, const float* intrin, int width, int height, const int32_t* part_map,
+                float* depth, uint8_t* parts, int32_t* faces, uint8_t* lambert) {
+    auto* rm = static_cast<RefModel2*>(model);
+    ark::Avatar ava(rm->m);
+    const int V = rm->m.numPoints(), J = rm->m.numJoints();
+    ava.cloud.resize(3, V);
+    for (int v = 0; v < V; ++v)
+        for (int c = 0; c < 3; ++c) ava.cloud(c, v) = cloud[(size_t)v * 3 + c];
+    ava.jointPos.resize(3, J);
+    ark::CameraIntrin K;
+    K.clear();
+    K.fx = intrin[0]; K.cx = intrin[1]; K.fy = intrin[2]; K.cy = intrin[3];
+    ark::AvatarRenderer rend(ava, K);
+    const cv::Size sz(width, height);
+    const size_t npx = (size_t)width * height;
+    if (depth) {
+        cv::Mat m = rend.renderDepth(sz);
+        std::memcpy(depth, m.data, npx * 4);
+    }
+    if (parts) {
+        std::vector<int> pm(part_map, part_map + J);
+        cv::Mat m = rend.renderPartMask(sz, pm);
+        std::memcpy(parts, m.data, npx);
+    }
+    if (faces) {
+        cv::Mat m = rend.renderFaces(sz, 1);
+        std::memcpy(faces, m.data, npx * 4);
+    }
+    if (lambert) {
+        cv::Mat m = rend.renderLambert(sz);
+        std::memcpy(lambert, m.data, npx);
+    }
 }
 
 }  // extern "C"

@@ -840,3 +840,33 @@ def test_reference_optimize_matches_oracle_fit(oracle_mod, omodel, oopt, ref_opt
         if icp == 1:   # (the oracle reports the counts of the last ICP iteration, the capture sums them)
             assert st_r["iterations"] == st_o.iterations and st_r["accepted"] == st_o.accepted_steps
         assert abs(st_r["final_cost"] - st_o.final_cost) <= 1e-10 * st_o.final_cost
+
+
+def test_renderer_matches_reference_source(oracle_mod, omodel, ref_opt, prior_arrays):
+    """AvatarRenderer.cpp of the reference itself (projection, painter's ordering, renderDepth / renderPartMask / renderFaces /
+    renderLambert over its own painters) against the oracle's restatement on posed clouds: depth, part mask and the Lambert
+    image are bit-identical; the face-index image may differ only where two faces have EQUAL sort keys (the reference orders
+    with std::sort, whose order among equal keys is unspecified; the oracle and the device keep the mesh order)."""
+    from harness import synth
+    hm = synth.HostModel(os.path.join(GOLDEN, "model_synth.npz"), prior_arrays)
+    vp = synth.vertex_parts(hm, prior_arrays["part_map"])
+    mesh = np.ascontiguousarray(hm.mesh, dtype=np.int32)
+    intrin = (synth.FX, synth.CX, synth.FY, synth.CY)
+    W, H = synth.WIDTH // 2, synth.HEIGHT // 2
+    k2 = (synth.FX / 2, synth.CX / 2, synth.FY / 2, synth.CY / 2)
+    for seed, (w, h, k) in zip((5, 6, 7), ((synth.WIDTH, synth.HEIGHT, intrin), (W, H, k2), (W, H, k2))):
+        x = synth.random_params(hm, np.random.default_rng(seed))
+        cloud = omodel.update_x(x)[0]
+        r = ref_opt.render(cloud, w, h, k)
+        o = oracle_mod.render(cloud, mesh, vp, w, h, k)
+        lam = oracle_mod.render_lambert(cloud, mesh, w, h, k)
+        assert (r["depth"] > 0).sum() > 1000
+        assert np.array_equal(r["depth"], o["depth"])
+        assert np.array_equal(r["parts"], o["parts"])
+        assert np.array_equal(r["lambert"], lam)
+        diff = r["faces"] != o["faces"]
+        if diff.any():
+            key = np.array([np.float32((cloud[mesh[f, 0], 2] + cloud[mesh[f, 1], 2] + cloud[mesh[f, 2], 2]) / 3.0) for f in o["order"]],
+                           dtype=np.float32)
+            assert np.array_equal(key[r["faces"][diff]], key[o["faces"][diff]])
+            assert diff.sum() < 0.01 * (o["faces"] >= 0).sum()
