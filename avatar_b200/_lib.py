@@ -101,6 +101,8 @@ SYMBOLS = [
     ("avb_comm_unique_id", C.c_int, [_P]),
     ("avb_fitter_comm_init", C.c_int, [_P, _P, C.c_int32, C.c_int32]),
     ("avb_gather_params", C.c_int, [_P, _P]),
+    ("avb_gather_params_begin", C.c_int, [_P]),
+    ("avb_gather_params_end", C.c_int, [_P, _P]),
     ("avb_last_device_ms", C.c_int, [_P, C.POINTER(C.c_float), _P]),
     ("avb_timer_start", C.c_int, [_P]),
     ("avb_timer_stop", C.c_int, [_P, C.POINTER(C.c_float)]),

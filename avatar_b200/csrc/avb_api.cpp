@@ -188,7 +188,8 @@ struct avb_fitter {
     int last_icp = 0;
     // multi-GPU: NCCL communicator of this fitter (avb_fitter_comm_init) and the all-gather buffers
     void* nccl_comm = nullptr; int comm_rank = 0, comm_size = 1;
-    double* d_gather = nullptr; double* h_gather = nullptr;
+    double* d_gather = nullptr; double* h_gather = nullptr; double* d_send = nullptr;
+    cudaStream_t gather_stream = nullptr; cudaEvent_t ev_send = nullptr, ev_gdone = nullptr; bool gather_pending = false;
 };
 
 namespace {
@@ -566,6 +567,9 @@ void avb_fitter_destroy(avb_fitter* ft) {
     if (!ft) return;
     cudaSetDevice(ft->device);
     if (ft->stream) cudaStreamSynchronize(ft->stream);
+    if (ft->gather_stream) { cudaStreamSynchronize(ft->gather_stream); cudaStreamDestroy(ft->gather_stream); }
+    if (ft->ev_send) cudaEventDestroy(ft->ev_send);
+    if (ft->ev_gdone) cudaEventDestroy(ft->ev_gdone);
     if (ft->nccl_comm && nccl().ok) nccl().CommDestroy(ft->nccl_comm);
     for (void* p : ft->allocs) cudaFree(p);
     for (void* p : ft->pinned) cudaFreeHost(p);
@@ -1138,7 +1142,11 @@ int enqueue_postprocess(avb_fitter* ft, int batch, int width, int height, const 
     a.stack = ft->d_pp_stack;
     a.cap = (long long)ft->pp_cap;
     a.overflow = ft->d_pp_ovf;
+    if (!ft->rev[0])
+        for (auto& e : ft->rev) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaEventRecord(ft->rev[0], ft->stream));   // avb_last_rtree_ms after a stand-alone postProcess call: this kernel
     CUDA_TRY(launch_rtree_postprocess(a, batch, ft->stream));
+    CUDA_TRY(cudaEventRecord(ft->rev[1], ft->stream));
     return AVB_OK;
 }
 int ensure_com_state(avb_fitter* ft, int num_parts, bool reset) {
@@ -1494,20 +1502,50 @@ int avb_fitter_comm_init(avb_fitter* ft, const uint8_t* id128, int32_t rank, int
     const size_t n = (size_t)nranks * ft->max_batch * ft->model->nx;
     int r2 = dev_alloc(ft, &ft->d_gather, n);
     if (r2 == AVB_OK) r2 = pin_alloc(ft, &ft->h_gather, n);
-    return r2;
+    if (r2 == AVB_OK) r2 = dev_alloc(ft, &ft->d_send, (size_t)ft->max_batch * ft->model->nx);
+    if (r2 != AVB_OK) return r2;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ft->gather_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ft->ev_send, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ft->ev_gdone, cudaEventDisableTiming));
+    return AVB_OK;
+}
+
+// The gather runs on its OWN stream behind a snapshot of d_x: the caller's host thread (and the fitter's stream) go on with
+// the next batch while NCCL's kernel waits for an SM slot (the persistent lm_flow_kernel of a neighbouring fitter may hold
+// every slot for milliseconds) and for the peers.  begin / end must alternate.
+int avb_gather_params_begin(avb_fitter* ft) {
+    if (!ft) return fail(AVB_ERR_INVALID, "null fitter");
+    if (!ft->nccl_comm) return fail(AVB_ERR_INVALID, "no communicator: call avb_fitter_comm_init first");
+    if (ft->gather_pending) return fail(AVB_ERR_INVALID, "a gather is already in flight: call avb_gather_params_end first");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    const size_t per = (size_t)ft->max_batch * ft->model->nx;
+    CUDA_TRY(cudaMemcpyAsync(ft->d_send, ft->d_x, per * 8, cudaMemcpyDeviceToDevice, ft->stream));
+    CUDA_TRY(cudaEventRecord(ft->ev_send, ft->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ft->gather_stream, ft->ev_send, 0));
+    const int rc = nccl().AllGather(ft->d_send, ft->d_gather, per, /*ncclFloat64*/ 8, ft->nccl_comm, ft->gather_stream);
+    if (rc != 0) return nccl_fail("ncclAllGather", rc);
+    CUDA_TRY(cudaMemcpyAsync(ft->h_gather, ft->d_gather, per * ft->comm_size * 8, cudaMemcpyDeviceToHost, ft->gather_stream));
+    CUDA_TRY(cudaEventRecord(ft->ev_gdone, ft->gather_stream));
+    // (the next snapshot cannot overwrite d_send early: begin / end alternate, and end waits for ev_gdone on the host.  No
+    //  wait is put on the fitter's stream here -- it would chain the next upload and fit behind the collective.)
+    ft->gather_pending = true;
+    return AVB_OK;
+}
+
+int avb_gather_params_end(avb_fitter* ft, double* all_x) {
+    if (!ft || !all_x) return fail(AVB_ERR_INVALID, "null argument");
+    if (!ft->gather_pending) return fail(AVB_ERR_INVALID, "no gather in flight: call avb_gather_params_begin first");
+    CUDA_TRY(cudaSetDevice(ft->device));
+    CUDA_TRY(cudaEventSynchronize(ft->ev_gdone));
+    ft->gather_pending = false;
+    std::memcpy(all_x, ft->h_gather, (size_t)ft->max_batch * ft->model->nx * ft->comm_size * 8);
+    return AVB_OK;
 }
 
 int avb_gather_params(avb_fitter* ft, double* all_x) {
     if (!ft || !all_x) return fail(AVB_ERR_INVALID, "null argument");
-    if (!ft->nccl_comm) return fail(AVB_ERR_INVALID, "no communicator: call avb_fitter_comm_init first");
-    CUDA_TRY(cudaSetDevice(ft->device));
-    const size_t per = (size_t)ft->max_batch * ft->model->nx;
-    const int rc = nccl().AllGather(ft->d_x, ft->d_gather, per, /*ncclFloat64*/ 8, ft->nccl_comm, ft->stream);
-    if (rc != 0) return nccl_fail("ncclAllGather", rc);
-    CUDA_TRY(cudaMemcpyAsync(ft->h_gather, ft->d_gather, per * ft->comm_size * 8, cudaMemcpyDeviceToHost, ft->stream));
-    CUDA_TRY(cudaStreamSynchronize(ft->stream));
-    std::memcpy(all_x, ft->h_gather, per * ft->comm_size * 8);
-    return AVB_OK;
+    const int rc = avb_gather_params_begin(ft);
+    return rc != AVB_OK ? rc : avb_gather_params_end(ft, all_x);
 }
 
 int avb_synchronize(avb_fitter* ft) {
@@ -1776,7 +1814,9 @@ int avb_render_lambert_batch(avb_fitter* ft, int32_t batch, const double* x, con
     a.vlam = ft->d_vlam;
     a.win_lambert = ft->d_win_l;
     a.lambert_out = ft->d_rlam;
+    CUDA_TRY(cudaEventRecord(ft->nev[0], st));   // avb_last_render_ms after a Lambert call: {all kernels, 0, 0}
     CUDA_TRY(launch_render_lambert(a, batch, st));
+    for (int k = 1; k < 4; ++k) CUDA_TRY(cudaEventRecord(ft->nev[k], st));
     CUDA_TRY(cudaMemcpyAsync(gray_out, ft->d_rlam, npx, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return AVB_OK;

@@ -289,6 +289,15 @@ class Fitter:
         check(lib.avb_gather_params(self.handle, ptr(out)))
         return out
 
+    def gather_begin(self):
+        """first half of gather_params: snapshot + collective on its own stream, returns at once"""
+        check(lib.avb_gather_params_begin(self.handle))
+
+    def gather_end(self):
+        out = np.zeros((self.nranks, self.max_batch, self.nx))
+        check(lib.avb_gather_params_end(self.handle, ptr(out)))
+        return out
+
     def synchronize(self):
         check(lib.avb_synchronize(self.handle))
 

@@ -204,6 +204,7 @@ def run_reference(args, rank, world):
 
 
 def main():
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's own log lines (e.g. "NCCL version ...") off stdout: one JSON line there
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -216,6 +217,7 @@ def main():
     ap.add_argument("--upload", default="f32", choices=["f32", "f64"],
                     help="e2e arm: ship the clouds as float32 (avb_upload_batch_f32; lossless for depth-camera clouds, which are "
                          "float by construction, Calibration.cpp:68-95) or as float64 (avb_fit_batch)")
+    ap.add_argument("--no-gather", action="store_true", help="diagnostic: multi-GPU e2e without the per-step NCCL gather")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --frames per GPU (default); strong: --frames in total, sharded over the ranks (BASELINE.json configs[2])")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity sample printed on the line")
@@ -236,6 +238,11 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL prints its version banner on fd 1 at the first communicator: stdout must carry ONE JSON line, so everything
+        # written to fd 1 from here on goes to stderr and the result line is written to the saved descriptor
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     model, pr = make_model()
     part_map, num_parts = pr["part_map"], int(pr["num_parts"])
@@ -325,15 +332,26 @@ def main():
             ln["ft"].comm_init(uid, rank, world)
 
     def lane_worker(ln, nsteps, out_q):
+        pending = False
         for _ in range(nsteps):
             h_x[ln["lo"]:ln["hi"]] = ln["x0"]
+            if world > 1 and not args.no_gather:   # upload + fit enqueue only; the result of the step is the gathered parameter block of all ranks
+                ln["ft"].upload(ln["pts32"] if use_f32 else ln["pts"], ln["lab"], ln["off"])
+                ln["ft"].fit_resident(h_x[ln["lo"]:ln["hi"]], opt)
+                if pending:   # the previous step's gather has long finished: this is the one-step-behind result read
+                    out_q.put(ln["ft"].gather_end())
+                ln["ft"].gather_begin()
+                pending = True
+                continue
             if use_f32:   # split form of the same call: avb_upload_batch_f32 + avb_fit_resident + avb_download_results
                 ln["ft"].upload(ln["pts32"], ln["lab"], ln["off"])
                 ln["ft"].fit_resident(h_x[ln["lo"]:ln["hi"]], opt)
                 x, st, _ = ln["ft"].download()
             else:
                 x, st, _ = ln["ft"].fit_batch(ln["pts"], ln["lab"], ln["off"], h_x[ln["lo"]:ln["hi"]], opt)
-            out_q.put(ln["ft"].gather_params() if world > 1 else x)
+            out_q.put(x)
+        if pending:
+            out_q.put(ln["ft"].gather_end())
 
     def e2e_run(nsteps):
         qs = [queue.Queue() for _ in lanes]
@@ -343,7 +361,7 @@ def main():
         full = None
         for _ in range(nsteps):
             got = [q.get() for q in qs]
-            if world > 1:   # [lane][rank][lane batch capacity][nx] -> frames in global order (rank-major, lanes in order)
+            if world > 1 and not args.no_gather:   # [lane][rank][lane batch capacity][nx] -> frames in global order (rank-major, lanes in order)
                 full = np.concatenate([got[l][r][:lanes[l]["hi"] - lanes[l]["lo"]] for r in range(world) for l in range(len(lanes))])
             else:
                 full = np.concatenate(got)
@@ -362,7 +380,7 @@ def main():
     e2e_value = F_total * args.steps / e2e_s
     clocks = sampler.stop(t0, t3) if sampler else None
     h2d = total * (12 if use_f32 else 24) + total * 4 + F * nx * 8 + (F + 1) * 8
-    d2h = F * nx * 8 + F * 40
+    d2h = F * nx * 8 + F * 40 if world == 1 else world * F_max * nx * 8   # multi-GPU: the gathered parameters of all ranks
 
     if rank != 0:
         if world > 1:
@@ -819,6 +837,36 @@ def main():
                 "cpu_oracle_ms_per_frame_1thread": 1e3 * rcpu,
                 "note": "prepare = projection + 16384-key bitonic sort per frame in shared memory (latency bound), cover = per-face "
                         "atomicMax of the paint rank, resolve = per-pixel value of the winning face"}
+            try:   # ---- the two rows added this round: renderLambert and RTree::postProcess on the device ----
+                fc.render_lambert(xg[:NR], synth.WIDTH, synth.HEIGHT, intrin)
+                lms = []
+                for _ in range(3):
+                    fc.render_lambert(xg[:NR], synth.WIDTH, synth.HEIGHT, intrin)
+                    lms.append(fc.render_ms()["prepare"])
+                tA = time.perf_counter()
+                for i in range(4):
+                    orc_c.render_lambert(clouds_gt[i], mesh, synth.WIDTH, synth.HEIGHT, intrin)
+                line["renderer"]["lambert"] = {"what": "avb_render_lambert_batch: AvatarRenderer::renderLambert (AvatarRenderer.cpp:103-172), %d models" % NR,
+                                               "kernel_ms_all": float(np.median(lms)), "frames_per_s_kernels": NR / (float(np.median(lms)) * 1e-3),
+                                               "cpu_oracle_ms_per_frame_1thread": 1e3 * (time.perf_counter() - tA) / 4}
+                lab_img = fc.rtree_predict(dimg[:NR], None, 2, True)
+                fc.rtree_postprocess(lab_img, None, 2, num_parts)
+                pms = []
+                for _ in range(3):
+                    fc.rtree_postprocess(lab_img, None, 2, num_parts)
+                    pms.append(fc.rtree_ms())
+                tA = time.perf_counter()
+                for i in range(4):
+                    orc_c.rtree_postprocess(lab_img[i], None, 2, num_parts)
+                line["rtree_prediction"]["postprocess"] = {
+                    "what": "avb_rtree_postprocess_batch: RTree::postProcess (RTree.cpp:3422-3450; largest-component filter per part + "
+                            "gap filling) on %d label images of a random tree (worst case: thousands of tiny components)" % NR,
+                    "kernel_ms": float(np.median(pms)), "frames_per_s_kernel": NR / (float(np.median(pms)) * 1e-3),
+                    "cpu_oracle_ms_per_frame_1thread": 1e3 * (time.perf_counter() - tA) / 4,
+                    "note": "one warp per frame, lane 0 walks the flood fill exactly in the reference's order (a sequential algorithm "
+                            "whose result depends on visiting order); frames run in parallel"}
+            except Exception as exc:
+                line["renderer"]["lambert_postprocess_error"] = repr(exc)
             fc.close()
             line["cloud_construction"] = {
                 "what": "avb_upload_depth_batch: depth + part-label images -> data clouds on the device (demo.cpp:215-250, "
@@ -848,7 +896,11 @@ def main():
                                           "oracle bfgs_wolfe restating the reference's Ceres line-search BFGS "
                                           "(reference defaults incl. function_tolerance=1e-4); CPU restatement of "
                                           "sxyu/avatar, not the Ceres binary"}
-    print(json.dumps(line), flush=True)
+    if world > 1:
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())   # the real stdout (fd 1 was pointed at stderr for NCCL's banner)
+    else:
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

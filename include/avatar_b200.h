@@ -263,11 +263,17 @@ int avb_last_rtree_ms(avb_fitter* fitter, float* ms);
  *   avb_comm_unique_id    rank 0 creates the 128-byte NCCL id and hands it to the other ranks by its own means
  *   avb_fitter_comm_init  every rank: ncclCommInitRank on the fitter's device
  *   avb_gather_params     ncclAllGather straight from the device parameter block of the last fit (no host staging of the
- *                         input, no allocation), on the fitter's stream; all_x is host [nranks][max_batch][nx] -- rank r's
- *                         frames are rows [r * max_batch, r * max_batch + its batch) */
+ *                         input, no allocation); all_x is host [nranks][max_batch][nx] -- rank r's frames are rows
+ *                         [r * max_batch, r * max_batch + its batch)
+ *   avb_gather_params_begin / _end   the same in two halves: begin snapshots the parameter block and enqueues the collective
+ *                         on a stream of its own and returns at once, so the caller can upload and fit the next batch while
+ *                         the collective waits for the peers (and for an SM: a persistent fit kernel of another fitter on the
+ *                         same GPU may hold every slot for milliseconds); end waits and copies out.  They must alternate. */
 int avb_comm_unique_id(uint8_t* id128);
 int avb_fitter_comm_init(avb_fitter* fitter, const uint8_t* id128, int32_t rank, int32_t nranks);
 int avb_gather_params(avb_fitter* fitter, double* all_x);
+int avb_gather_params_begin(avb_fitter* fitter);
+int avb_gather_params_end(avb_fitter* fitter, double* all_x);
 
 /* device time (ms) of [cloud_count_kernel, cloud_compact_kernel] of the last avb_upload_depth_batch (CUDA events) */
 int avb_last_cloud_ms(avb_fitter* fitter, float* ms2);
