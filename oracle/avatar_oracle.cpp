@@ -2,8 +2,12 @@
  *
  * CPU restatement of the sxyu/avatar fitting path.  Parity status: forward model / visibility /
  * NN / residuals / Jacobians / priors follow the reference source line by line (citations at
- * each function, relative to /root/reference); the solver (Ceres 1.14, not vendored, not
- * installed) is restated from its published algorithm and is PARITY UNPINNED.
+ * each function, relative to /root/reference) and are PINNED against the reference's own code:
+ * Avatar.cpp, GaussianMixture.cpp, AvatarOptimizer.cpp and AvatarRenderer.cpp compile unchanged into
+ * oracle/_ref/libref_avatar.so (stand-in Eigen / Ceres / boost / OpenCV headers in oracle/shim) and
+ * tests/test_oracle.py compares cost, gradient, J^T J (1e-15) and whole fits (1e-12) with them.
+ * The solver POLICY (Ceres 1.14, not vendored, not installed) is restated from its published
+ * algorithm and stays PARITY UNPINNED.
  */
 #include "avatar_oracle.h"
 

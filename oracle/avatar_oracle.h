@@ -13,7 +13,9 @@
  *   - the widened rows: the renderer's painters and CameraIntrin::depthToXYZ are pinned against the reference's own
  *     AvatarHelpers.cpp / Calibration.cpp compiled into oracle/_ref with container-only stand-ins (oracle/shim);
  *     RTree::predictBest is restated from source (RTree.cpp needs the full Eigen/OpenCV stack);
- *   - the solver trajectory (Ceres 1.14, external, un-vendored) is PARITY UNPINNED.
+ *   - the solver trajectory (Ceres 1.14, external, un-vendored) is PARITY UNPINNED; everything the solver calls
+ *     (residuals, Jacobians, priors, parameterization, visibility, NN, Avatar::update) is pinned against the
+ *     reference's own sources compiled into oracle/_ref/libref_avatar.so (oracle/ref_optimizer.cpp).
  * Every function cites the reference file:line it follows (paths relative to /root/reference).
  */
 #ifndef AVATAR_ORACLE_H_
