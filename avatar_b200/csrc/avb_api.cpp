@@ -137,6 +137,8 @@ struct avb_fitter {
     unsigned short* d_mlist = nullptr; int4* d_chunks = nullptr; int2* d_gruns = nullptr; LmState* d_state = nullptr;
     float* d_rec = nullptr; int* d_gstart = nullptr; int maxrb = 0, rec_stride = 0, rec_rs = 0;
     int nn_stage_cap = 0;
+    int fused64 = 0;               // fp64 flow path, AVB_FUSED=1: fused record + Gram tasks (no d_rec round trip).  Measured NOT
+                                   // faster (60.5 k vs 61.2 k frames/s): a chunk fills 75 % of the CTA's threads, DESIGN.md 5.4
     float* d_data_f32 = nullptr;   // avb_upload_batch_f32 staging
     int maxc = 0, tabD = 0, max_nj = 0, chunk_verts = 192, chunk_verts_tc = 256;   // vertices per Gram chunk: fp64 path (3 CTAs/SM) / tensor path
     long long pstride = 0;
@@ -760,6 +762,7 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     TRY(dev_alloc(ft, &ft->d_Hcur, B * P * P));
     TRY(dev_alloc(ft, &ft->d_stats, B));
     for (int g : gnj) ft->max_nj = std::max(ft->max_nj, g);
+    if (const char* e = std::getenv("AVB_FUSED")) ft->fused64 = std::atoi(e) != 0;
     if (const char* e = std::getenv("AVB_CHUNK")) ft->chunk_verts = ft->chunk_verts_tc = std::max(128, std::min(256, std::atoi(e) / 64 * 64));
     while (ft->chunk_verts > 128 && lm_gram_smem_bytes(ft->max_nj, m->K, ft->chunk_verts, false) > 112 * 1024) ft->chunk_verts -= 64;
     {
@@ -1387,6 +1390,7 @@ LmBuf lm_buf(avb_fitter* ft, double* dx, const avb_options* o) {
     // one persistent data-flow kernel for the whole inner solve (the staged kernels, AVB_FLOW=0, exist for the fp64 path only)
     a.tensor = o->jtj_precision == AVB_JTJ_BF16_TENSOR ? 1 : 0;
     if (ft->use_flow || a.tensor) {
+        a.fused = a.tensor ? 0 : ft->fused64;
         a.q.slots = ft->d_qslots;
         a.q.ctrl = ft->d_qctrl;
         a.q.rows_left = ft->d_rows_left;

@@ -150,6 +150,7 @@ struct LmBuf {
     int trace_cap;
     FrameStats* stats;           // [batch]
     int tensor;                  // 1: fused record + Gram tasks on tcgen05 (lm_flow_kernel<true>); 0: fp64 DMMA path
+    int fused;                   // fp64 path of lm_flow_kernel: 1 = one fused record + Gram task per chunk (no d_rec round trip)
     FlowQueue q;
 };
 

@@ -229,7 +229,7 @@ lm_prep_kernel(DevModel M, DevParts Pt, LmBuf a) {
         fs.final_cost = 0;
         fs.status = a.range_flag[f] ? 4 : 0;
         if (a.q.slots && !st.done) {   // lm_flow_kernel: the frame's first tasks
-            if (a.tensor) {             // fused record + Gram tasks, one per chunk
+            if (a.tensor || a.fused) {  // fused record + Gram tasks, one per chunk
                 a.q.gram_left[f] = st.nchunks;
                 __threadfence();
                 atomicAdd(&a.q.ctrl[2], 1u);
@@ -256,6 +256,109 @@ lm_prep_kernel(DevModel M, DevParts Pt, LmBuf a) {
 // starting on a multiple of four (gap slots hold kNoVertex in mlist and are never read by the Gram kernels).
 __host__ __device__ inline int rec_floats(int nj, int K) { return 3 * nj + 3 * K + 7; }
 
+// One matched vertex: its compact Jacobian record (fields at rec[q * RS]: the global SoA of the staged / two-task schedule,
+// or a column of the shared-memory tile of the fused task) and its cost term x . (c x - 2 s).
+__device__ __forceinline__ double record_vertex(const DevModel& M, const DevParts& Pt, const LmBuf& a, int f, int v, int g,
+                                                float* rec, size_t RS, bool cost_only, const double* tab, const double* w) {
+    const int J = M.J, K = M.K;
+    const double* G = tab;
+    const double* pos = tab + 9 * J;
+    const double* tau = tab + 12 * J;
+    const double* C = tab + 15 * J;
+    double costv = 0.0;
+    const int nj = Pt.gnj[g];
+    const int* gj = Pt.gjoints + g * kMaxJ;
+    const float* sd = M.sd + (size_t)v * 3 * K;
+    double v0[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double s = 0;
+        for (int k = 0; k < K; ++k) s += (double)sd[c * K + k] * w[k];
+        v0[c] = M.vt[3 * (size_t)v + c] + s;
+    }
+    const int n = M.sk_n[v];
+    double xk[AVB_MAX_ASSIGN_][3], wk[AVB_MAX_ASSIGN_];
+    int jk[AVB_MAX_ASSIGN_];
+    uint32_t mk[AVB_MAX_ASSIGN_];
+    double x[3] = {0, 0, 0}, B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
+        if (q < n) {
+            const int k = M.sk_j[4 * (size_t)v + q];
+            const double wt = M.sk_w[4 * (size_t)v + q];
+            const double* Gk = G + 9 * k;
+            jk[q] = k;
+            wk[q] = wt;
+            mk[q] = M.anc_mask[k];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                xk[q][c] = Gk[3 * c] * v0[0] + Gk[3 * c + 1] * v0[1] + Gk[3 * c + 2] * v0[2] + tau[3 * k + c];
+                x[c] += wt * xk[q][c];
+            }
+#pragma unroll
+            for (int e = 0; e < 9; ++e) B[e] += wt * Gk[e];
+        } else {
+            jk[q] = 0; wk[q] = 0; mk[q] = 0;
+            xk[q][0] = xk[q][1] = xk[q][2] = 0;
+        }
+    }
+    const double cn = (double)a.cnt[(size_t)f * M.V + v];
+    const double sc = sqrt(cn), s2 = 2.0 * sc;
+    // the evaluation that only decides the last accept / reject needs the cost, not the Jacobian records
+    for (int gi = 0; gi < (cost_only ? 0 : nj); ++gi) {
+        const int j = gj[gi];
+        double y0 = 0, y1 = 0, y2 = 0, W = 0;
+#pragma unroll
+        for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
+            if ((mk[q] >> j) & 1u) {
+                W += wk[q];
+                y0 += wk[q] * xk[q][0];
+                y1 += wk[q] * xk[q][1];
+                y2 += wk[q] * xk[q][2];
+            }
+        }
+        rec[(3 * gi) * RS] = (float)((y0 - W * pos[3 * j]) * s2);
+        rec[(3 * gi + 1) * RS] = (float)((y1 - W * pos[3 * j + 1]) * s2);
+        rec[(3 * gi + 2) * RS] = (float)((y2 - W * pos[3 * j + 2]) * s2);
+    }
+    // shape: sum_k w_k (G_k (Delta_v - S_k) + H_k) = B Delta_v + sum_k w_k C_k  (AvatarOptimizer.cpp:568-580)
+    float* rr = rec + (size_t)(3 * nj) * RS;   // sc | rho_hi | rho_lo
+    float* rs = rr + 7 * RS;
+    for (int m = 0; m < (cost_only ? 0 : K); ++m) {
+        const double d0 = sd[m], d1 = sd[K + m], d2 = sd[2 * K + m];
+        double e0 = B[0] * d0 + B[1] * d1 + B[2] * d2;
+        double e1 = B[3] * d0 + B[4] * d1 + B[5] * d2;
+        double e2 = B[6] * d0 + B[7] * d1 + B[8] * d2;
+#pragma unroll
+        for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
+            if (q < n) {
+                const double* Cq = C + (size_t)jk[q] * 3 * K;
+                e0 += wk[q] * Cq[m];
+                e1 += wk[q] * Cq[K + m];
+                e2 += wk[q] * Cq[2 * K + m];
+            }
+        }
+        rs[m * RS] = (float)(e0 * sc);
+        rs[(K + m) * RS] = (float)(e1 * sc);
+        rs[(2 * K + m) * RS] = (float)(e2 * sc);
+    }
+    // residual sum of the vertex's correspondences, c x - sum d (AvatarOptimizer.cpp:632-639), split hi/lo
+    const unsigned long long* sumv = a.sum + 3 * ((size_t)f * M.V + v);
+    if (!cost_only) rr[0] = (float)sc;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double sr = (double)(long long)sumv[c] * kFixInv;
+        if (!cost_only) {
+            const double rho = (cn * x[c] - sr) / sc;
+            const float hi = (float)rho;
+            rr[(1 + c) * RS] = hi;
+            rr[(4 + c) * RS] = (float)(rho - (double)hi);
+        }
+        costv += x[c] * (cn * x[c] - 2.0 * sr);  // sum_i |x - d_i|^2 - sum_i |d_i|^2 = x . (c x - 2 s)
+    }
+    return costv;
+}
+
 __device__ void rows_body(const DevModel& M, const DevParts& Pt, const LmBuf& a, int f, int blk, int nslots,
                           bool cost_only, unsigned char* smem_raw) {
     const int tid = threadIdx.x;
@@ -274,107 +377,11 @@ __device__ void rows_body(const DevModel& M, const DevParts& Pt, const LmBuf& a,
     s_v[tid] = (i < nslots) ? (int)a.mlist[(size_t)f * a.rec_rs + i] : (int)kNoVertex;
     __syncthreads();
     phase_lap(a.q, 12, tp);
-    const double* G = tab;
-    const double* pos = tab + 9 * J;
-    const double* tau = tab + 12 * J;
-    const double* C = tab + 15 * J;
     double costv = 0.0;
     if (s_v[tid] != (int)kNoVertex) {
         int g = 0;
         while (g + 1 < Pt.numGroups && i >= gstart[g + 1]) ++g;
-        const int nj = Pt.gnj[g];
-        const int* gj = Pt.gjoints + g * kMaxJ;
-        const int v = s_v[tid];
-        float* rec = a.rec + (size_t)f * a.rec_stride * a.rec_rs + i;   // SoA: field q of slot i at rec[q * rec_rs]
-        const size_t RS = (size_t)a.rec_rs;
-        const float* sd = M.sd + (size_t)v * 3 * K;
-        double v0[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            double s = 0;
-            for (int k = 0; k < K; ++k) s += (double)sd[c * K + k] * w[k];
-            v0[c] = M.vt[3 * (size_t)v + c] + s;
-        }
-        const int n = M.sk_n[v];
-        double xk[AVB_MAX_ASSIGN_][3], wk[AVB_MAX_ASSIGN_];
-        int jk[AVB_MAX_ASSIGN_];
-        uint32_t mk[AVB_MAX_ASSIGN_];
-        double x[3] = {0, 0, 0}, B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-        for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
-            if (q < n) {
-                const int k = M.sk_j[4 * (size_t)v + q];
-                const double wt = M.sk_w[4 * (size_t)v + q];
-                const double* Gk = G + 9 * k;
-                jk[q] = k;
-                wk[q] = wt;
-                mk[q] = M.anc_mask[k];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    xk[q][c] = Gk[3 * c] * v0[0] + Gk[3 * c + 1] * v0[1] + Gk[3 * c + 2] * v0[2] + tau[3 * k + c];
-                    x[c] += wt * xk[q][c];
-                }
-#pragma unroll
-                for (int e = 0; e < 9; ++e) B[e] += wt * Gk[e];
-            } else {
-                jk[q] = 0; wk[q] = 0; mk[q] = 0;
-                xk[q][0] = xk[q][1] = xk[q][2] = 0;
-            }
-        }
-        const double cn = (double)a.cnt[(size_t)f * M.V + v];
-        const double sc = sqrt(cn), s2 = 2.0 * sc;
-        // the evaluation that only decides the last accept / reject needs the cost, not the Jacobian records
-        for (int gi = 0; gi < (cost_only ? 0 : nj); ++gi) {
-            const int j = gj[gi];
-            double y0 = 0, y1 = 0, y2 = 0, W = 0;
-#pragma unroll
-            for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
-                if ((mk[q] >> j) & 1u) {
-                    W += wk[q];
-                    y0 += wk[q] * xk[q][0];
-                    y1 += wk[q] * xk[q][1];
-                    y2 += wk[q] * xk[q][2];
-                }
-            }
-            rec[(3 * gi) * RS] = (float)((y0 - W * pos[3 * j]) * s2);
-            rec[(3 * gi + 1) * RS] = (float)((y1 - W * pos[3 * j + 1]) * s2);
-            rec[(3 * gi + 2) * RS] = (float)((y2 - W * pos[3 * j + 2]) * s2);
-        }
-        // shape: sum_k w_k (G_k (Delta_v - S_k) + H_k) = B Delta_v + sum_k w_k C_k  (AvatarOptimizer.cpp:568-580)
-        float* rr = rec + (size_t)(3 * nj) * RS;   // sc | rho_hi | rho_lo
-        float* rs = rr + 7 * RS;
-        for (int m = 0; m < (cost_only ? 0 : K); ++m) {
-            const double d0 = sd[m], d1 = sd[K + m], d2 = sd[2 * K + m];
-            double e0 = B[0] * d0 + B[1] * d1 + B[2] * d2;
-            double e1 = B[3] * d0 + B[4] * d1 + B[5] * d2;
-            double e2 = B[6] * d0 + B[7] * d1 + B[8] * d2;
-#pragma unroll
-            for (int q = 0; q < AVB_MAX_ASSIGN_; ++q) {
-                if (q < n) {
-                    const double* Cq = C + (size_t)jk[q] * 3 * K;
-                    e0 += wk[q] * Cq[m];
-                    e1 += wk[q] * Cq[K + m];
-                    e2 += wk[q] * Cq[2 * K + m];
-                }
-            }
-            rs[m * RS] = (float)(e0 * sc);
-            rs[(K + m) * RS] = (float)(e1 * sc);
-            rs[(2 * K + m) * RS] = (float)(e2 * sc);
-        }
-        // residual sum of the vertex's correspondences, c x - sum d (AvatarOptimizer.cpp:632-639), split hi/lo
-        const unsigned long long* sumv = a.sum + 3 * ((size_t)f * M.V + v);
-        if (!cost_only) rr[0] = (float)sc;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const double sr = (double)(long long)sumv[c] * kFixInv;
-            if (!cost_only) {
-                const double rho = (cn * x[c] - sr) / sc;
-                const float hi = (float)rho;
-                rr[(1 + c) * RS] = hi;
-                rr[(4 + c) * RS] = (float)(rho - (double)hi);
-            }
-            costv += x[c] * (cn * x[c] - 2.0 * sr);  // sum_i |x - d_i|^2 - sum_i |d_i|^2 = x . (c x - 2 s)
-        }
+        costv = record_vertex(M, Pt, a, f, s_v[tid], g, a.rec + (size_t)f * a.rec_stride * a.rec_rs + i, (size_t)a.rec_rs, cost_only, tab, w);
     }
     const double cs = block_sum(costv, scr);
     if (tid == 0) a.cpart[(size_t)f * a.maxrb + blk] = cs;
@@ -504,27 +511,11 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 __device__ __forceinline__ uint32_t smem_u32_lm(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ void gram_body(const DevModel& M, const DevParts& Pt, const LmBuf& a, int f, int c, unsigned char* smem_raw) {
+// Gram matrix of a field-major fp32 tile T[nfp][ldt] in shared memory (cnt4 vertices, a multiple of 4) on the fp64 tensor
+// path, expanded into the chunk's partial.  The tile memory is reused for the Gram matrix.
+__device__ void gram_contract(const LmBuf& a, float* T, int ldt, int cnt4, int n, int nj, int K, double* part, bool wait_async,
+                              unsigned long long& tp) {
     const int tid = threadIdx.x;
-    const int K = M.K;
-    unsigned long long tp = phase_begin(a.q);
-    const int4 ch = a.chunks[(size_t)f * a.maxc + c];
-    const int g = ch.x, start = ch.y, count = ch.z;
-    const int nj = Pt.gnj[g];
-    const int nf = rec_floats(nj, K), nfp = (nf + 7) & ~7, n = nfp >> 3;
-    const int ldt = a.chunk_verts + 4;              // ldt % 32 == 4: conflict-free fragment loads
-    const int cnt4 = (count + 3) & ~3, ng = cnt4 >> 2;
-    float* T = reinterpret_cast<float*>(smem_raw);  // [nfp][ldt] field-major tile
-    const float* recs = a.rec + (size_t)f * a.rec_stride * a.rec_rs + start;
-    for (int e = tid; e < nf * ng; e += kGramThreads) {   // 16-byte granules; bytes past `count` are zero-filled
-        const int q = e / ng, i = e - q * ng;
-        const int valid = min(4, count - 4 * i) * 4;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32_lm(T + (size_t)q * ldt + 4 * i)),
-                     "l"(recs + (size_t)q * a.rec_rs + 4 * i), "r"(valid) : "memory");
-    }
-    for (int e = tid; e < (nfp - nf) * cnt4; e += kGramThreads) T[(size_t)(nf + e / cnt4) * ldt + e % cnt4] = 0.f;
-    asm volatile("cp.async.commit_group;" ::: "memory");
-
     // warp roles: 2x2-block tiles of the upper block triangle, round robin over the warps
     const int wid = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
     const int n2 = (n + 1) >> 1, nwt = num_pairs(n2);
@@ -549,7 +540,7 @@ __device__ void gram_body(const DevModel& M, const DevParts& Pt, const LmBuf& a,
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[s][q][0] = acc[s][q][1] = 0.0;
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (wait_async) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     phase_lap(a.q, 14, tp);
 
@@ -569,7 +560,7 @@ __device__ void gram_body(const DevModel& M, const DevParts& Pt, const LmBuf& a,
     }
     __syncthreads();   // every warp is done with the tile: reuse it for the Gram matrix
     phase_lap(a.q, 15, tp);
-    double* Gs = reinterpret_cast<double*>(smem_raw);
+    double* Gs = reinterpret_cast<double*>(T);
 #pragma unroll
     for (int s = 0; s < kGramSlots; ++s) {
 #pragma unroll
@@ -582,7 +573,69 @@ __device__ void gram_body(const DevModel& M, const DevParts& Pt, const LmBuf& a,
         }
     }
     __syncthreads();
-    emit_partial(Gs, n, nj, K, a.part + ((size_t)f * a.maxc + c) * a.pstride, tid, kGramThreads);
+    emit_partial(Gs, n, nj, K, part, tid, kGramThreads);
+}
+
+__device__ void gram_body(const DevModel& M, const DevParts& Pt, const LmBuf& a, int f, int c, unsigned char* smem_raw) {
+    const int tid = threadIdx.x;
+    const int K = M.K;
+    unsigned long long tp = phase_begin(a.q);
+    const int4 ch = a.chunks[(size_t)f * a.maxc + c];
+    const int g = ch.x, start = ch.y, count = ch.z;
+    const int nj = Pt.gnj[g];
+    const int nf = rec_floats(nj, K), nfp = (nf + 7) & ~7, n = nfp >> 3;
+    const int ldt = a.chunk_verts + 4;              // ldt % 32 == 4: conflict-free fragment loads
+    const int cnt4 = (count + 3) & ~3, ng = cnt4 >> 2;
+    float* T = reinterpret_cast<float*>(smem_raw);  // [nfp][ldt] field-major tile
+    const float* recs = a.rec + (size_t)f * a.rec_stride * a.rec_rs + start;
+    for (int e = tid; e < nf * ng; e += kGramThreads) {   // 16-byte granules; bytes past `count` are zero-filled
+        const int q = e / ng, i = e - q * ng;
+        const int valid = min(4, count - 4 * i) * 4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32_lm(T + (size_t)q * ldt + 4 * i)),
+                     "l"(recs + (size_t)q * a.rec_rs + 4 * i), "r"(valid) : "memory");
+    }
+    for (int e = tid; e < (nfp - nf) * cnt4; e += kGramThreads) T[(size_t)(nf + e / cnt4) * ldt + e % cnt4] = 0.f;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    gram_contract(a, T, ldt, cnt4, n, nj, K, a.part + ((size_t)f * a.maxc + c) * a.pstride, true, tp);
+}
+
+// Fused record + Gram task of the fp64 path of lm_flow_kernel: the records of one chunk (<= chunk_verts <= 256 matched vertices
+// of one column group, one thread each) go straight into the shared-memory tile the contraction reads -- no d_rec round trip
+// through HBM, no second queue hop.  Same arithmetic as rows_body + gram_body (record_vertex / gram_contract are shared).
+__host__ __device__ inline size_t fused64_head_bytes(int tabD, int K) { return (((size_t)(tabD + ((K + 1) & ~1) + 32) * 8) + 127) & ~(size_t)127; }
+__device__ void fused64_body(const DevModel& M, const DevParts& Pt, const LmBuf& a, int f, int c, bool cost_only, unsigned char* smem_raw) {
+    const int tid = threadIdx.x;
+    const int J = M.J, K = M.K;
+    unsigned long long tp = phase_begin(a.q);
+    const int4 ch = a.chunks[(size_t)f * a.maxc + c];
+    const int g = ch.x, start = ch.y, count = ch.z;
+    const int nj = Pt.gnj[g];
+    const int nf = rec_floats(nj, K), nfp = (nf + 7) & ~7, n = nfp >> 3;
+    const int ldt = a.chunk_verts + 4;
+    const int cnt4 = (count + 3) & ~3;
+    double* tab = reinterpret_cast<double*>(smem_raw);
+    double* w = tab + a.tabD;
+    double* scr = w + ((K + 1) & ~1);
+    float* T = reinterpret_cast<float*>(smem_raw + fused64_head_bytes(a.tabD, K));
+    const double* gtab = a.tab + (size_t)f * a.tabD;
+    for (int q = tid; q < a.tabD; q += 256) tab[q] = ldg2(gtab + q);
+    for (int q = tid; q < K; q += 256) w[q] = ldg2(a.xt + (size_t)f * M.nx + 3 + 4 * J + q);
+    const int v = (tid < count) ? (int)a.mlist[(size_t)f * a.rec_rs + start + tid] : (int)kNoVertex;
+    if (!cost_only) {   // rows nf..nfp-1 and the columns of the last granule past `count` are zero (as the cp.async zero fill was)
+        for (int e = tid; e < (nfp - nf) * cnt4; e += 256) T[(size_t)(nf + e / cnt4) * ldt + e % cnt4] = 0.f;
+        if (tid < cnt4 && v == (int)kNoVertex)
+            for (int q = 0; q < nf; ++q) T[(size_t)q * ldt + tid] = 0.f;
+    }
+    __syncthreads();
+    phase_lap(a.q, 12, tp);
+    double costv = 0.0;
+    if (v != (int)kNoVertex) costv = record_vertex(M, Pt, a, f, v, g, T + tid, (size_t)ldt, cost_only, tab, w);
+    const double cs = block_sum(costv, scr);
+    if (tid == 0) a.cpart[(size_t)f * a.maxrb + c] = cs;
+    phase_lap(a.q, 13, tp);
+    if (cost_only) return;
+    gram_contract(a, T, ldt, cnt4, n, nj, K, a.part + ((size_t)f * a.maxc + c) * a.pstride, false, tp);
 }
 
 __global__ void __launch_bounds__(kGramThreads, 2)
@@ -1363,7 +1416,7 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
     }
     double csum = 0.0;   // cost partials in record-block order, eight loads in flight
     {
-        const int nb = a.tensor ? st.nchunks : (st.nslots + 255) >> 8;   // one cost partial per fused task / per record block
+        const int nb = (a.tensor || a.fused) ? st.nchunks : (st.nslots + 255) >> 8;   // one cost partial per fused task / per record block
 #pragma unroll 1
         for (int b = 0; b < nb; b += 8) {
             double t[8];
@@ -1873,6 +1926,15 @@ lm_flow_kernel(DevModel M, DevParts Pt, LmBuf a) {
                 s_last = atomicSub(&a.q.gram_left[f], 1) == 1;
                 lap(1);
             }
+        } else if (type == kTaskFused) {
+            const bool cost_only = ldg2(&a.state[f].last) != 0;
+            fused64_body(M, Pt, a, f, idx, cost_only, smem_raw);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                s_last = atomicSub(&a.q.gram_left[f], 1) == 1;
+                lap(1);
+            }
         } else if (type == kTaskRows) {
             const int nslots = ldg2(&a.state[f].nslots);
             const bool cost_only = ldg2(&a.state[f].last) != 0;
@@ -1912,7 +1974,7 @@ lm_flow_kernel(DevModel M, DevParts Pt, LmBuf a) {
             if (tid == 0) {
                 if (done) {
                     atomicSub(&a.q.ctrl[2], 1u);
-                } else if (TC) {
+                } else if (TC || a.fused) {
                     const int nch = ldg2(&a.state[f].nchunks);
                     atomicExch(&a.q.gram_left[f], nch);
                     __threadfence();
@@ -1981,7 +2043,11 @@ cudaError_t launch_lm_eval_part(const DevModel& M, const DevParts& Pt, const LmB
 
 size_t lm_flow_smem(const DevModel& M, int max_nj, int chunk_verts, bool tensor) {
     size_t b = tensor ? tc_smem_bytes(M.J, M.K) : lm_gram_smem(M, max_nj, chunk_verts, false);
-    if (!tensor) b = b > lm_rows_smem(M) ? b : lm_rows_smem(M);
+    if (!tensor) {   // (the fused fp64 task keeps the joint tables in front of the tile)
+        const size_t fused = fused64_head_bytes(tab_doubles(M.J, M.K), M.K) + lm_gram_smem(M, max_nj, chunk_verts, false);
+        b = b > lm_rows_smem(M) ? b : lm_rows_smem(M);
+        b = b > fused ? b : fused;
+    }
     const size_t ssm = solve_smem_bytes(M.J, M.K, M.gmmC) + (tensor ? 1024 : 0);
     return b > ssm ? b : ssm;
 }

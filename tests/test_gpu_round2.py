@@ -455,3 +455,27 @@ def test_device_matches_reference_source(model, oracle_mod, omodel, prior_arrays
         print(f"device vs reference source, frame {b}: max parameter difference {err:.2e}, iterations {st[b].iterations} / {st_r['iterations']}")
         assert err < 1e-4
         assert st[b].iterations == st_r["iterations"] and st[b].accepted_steps == st_r["accepted"]
+
+
+def test_fused_fp64_tasks_match_the_two_task_schedule(model, omodel, prior_arrays, monkeypatch):
+    """AVB_FUSED=1 (fp64 flow path with one fused record + Gram task per chunk, no d_rec round trip) against the default
+    schedule (record blocks through HBM, then Gram chunks): the same J^T J partials per chunk, the cost summed per chunk
+    instead of per record block -> fitted parameters equal to rounding"""
+    from avatar_b200 import Fitter
+    part_map, num_parts = prior_arrays["part_map"], int(prior_arrays["num_parts"])
+    fr = [_frame(model, omodel, prior_arrays, s) for s in (1000, 1001, 1002)]
+    pts = np.concatenate([f[2] for f in fr])
+    lab = np.concatenate([f[3] for f in fr])
+    off = np.cumsum([0] + [len(f[2]) for f in fr]).astype(np.int64)
+    x0 = np.stack([f[1] for f in fr])
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("AVB_FUSED", mode)
+        ft = Fitter(model, num_parts, part_map, 3, int(off[-1]) + 64)
+        out[mode] = ft.fit_batch(pts, lab, off, x0, _opts(function_tolerance=0.0, icp_iters=2))
+        ft.close()
+    (xa, sa, _), (xb, sb, _) = out["0"], out["1"]
+    assert np.abs(xa - xb).max() < 1e-9
+    for a, b in zip(sa, sb):
+        assert a.iterations == b.iterations and a.accepted_steps == b.accepted_steps
+        assert abs(a.final_cost - b.final_cost) <= 1e-12 * a.final_cost
