@@ -548,15 +548,14 @@ def main():
                 if orc_p.ref_avatar_available():
                     import tempfile
                     with tempfile.TemporaryDirectory() as td:
-                        ppath = os.path.join(td, "pose_prior.txt")
-                        orc_p.write_prior_text(ppath, pr["weights"], pr["means"], pr["covs"])
-                        ro_p = orc_p.RefOptimizer(os.path.join(GOLD, "model_synth.npz"), om_p, ppath, num_parts, part_map)
+                        mdir = orc_p.write_model_dir(os.path.join(td, "avatar-model"), os.path.join(GOLD, "model_synth.npz"), pr)
+                        ro_p = orc_p.RefOptimizer(mdir, num_parts, part_map)
                         errs_r = []
                         for i, b in enumerate(sample[:4]):
                             x_r, _ = ro_p.optimize(x0[b], pts[b], labs[b], icp_iters=1, max_iters=10, function_tolerance=0.0)
                             errs_r.append(float(np.abs(x_mine[b] - x_r).max()))
                     line["parity"]["reference_source"] = {
-                        "what": "the reference's own AvatarOptimizer.cpp / Avatar.cpp / GaussianMixture.cpp compiled against stand-in "
+                        "what": "the reference's own AvatarModel.cpp (loader) / AvatarOptimizer.cpp / Avatar.cpp / GaussianMixture.cpp compiled against stand-in "
                                 "Eigen / Ceres headers (oracle/shim): its visibility, findNN, cost functors and parameterization, "
                                 "driven by a restated Levenberg-Marquardt loop (Ceres is absent)",
                         "frames_checked": len(errs_r), "max_param_err": max(errs_r)}

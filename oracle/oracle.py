@@ -436,14 +436,13 @@ def _ref_avatar_lib():
         L.ref_gmm_pdf.restype = C.c_double
         L.ref_gmm_pdf.argtypes = [_P, _P]
         L.ref_gmm_tables.argtypes = [_P, _P, _P]
-        L.ref_model_create.restype = _P
-        L.ref_model_create.argtypes = [C.c_int] * 3 + [_P] * 5
+        L.ref_model_load.restype = _P
+        L.ref_model_load.argtypes = [C.c_char_p]
+        L.ref_model_dims.argtypes = [_P, _P]
+        L.ref_model_tables.argtypes = [_P] * 11
         L.ref_model_free.argtypes = [_P]
         L.ref_avatar_update.argtypes = [_P] * 7
         L.ref_avatar_align.argtypes = [_P] * 6
-        L.ref_model2_create.restype = _P
-        L.ref_model2_create.argtypes = [C.c_int] * 4 + [_P] * 6 + [C.c_int] + [_P] * 5 + [C.c_char_p]
-        L.ref_model2_free.argtypes = [_P]
         L.ref_opt_create.restype = _P
         L.ref_opt_create.argtypes = [_P, C.c_int, _P]
         L.ref_opt_free.argtypes = [_P]
@@ -491,16 +490,43 @@ class RefGaussianMixture:
         return pc, cl
 
 
-class RefAvatar:
-    """ark::Avatar of the reference over an AvatarModel filled from the npz arrays"""
+def write_model_dir(path, npz_path, prior_arrays):
+    """data/avatar-model layout of the reference (AvatarModel.cpp:18-23): model.npz + pose_prior.txt"""
+    import io
+    import zipfile
+    os.makedirs(path, exist_ok=True)
+    # re-packed without the zip64 local headers numpy >= 1.x writes for every member: the reference's vendored cnpy
+    # (cnpy.cpp) predates them and reads the 32-bit size fields only.  Same arrays, same dtypes, stored uncompressed.
+    z = np.load(npz_path)
+    with zipfile.ZipFile(os.path.join(path, "model.npz"), "w", zipfile.ZIP_STORED, allowZip64=False) as zf:
+        for name in z.files:
+            buf = io.BytesIO()
+            np.lib.format.write_array(buf, np.ascontiguousarray(z[name]), version=(1, 0))
+            zf.writestr(name + ".npy", buf.getvalue())
+    write_prior_text(os.path.join(path, "pose_prior.txt"), prior_arrays["weights"], prior_arrays["means"], prior_arrays["covs"])
+    return path
 
-    def __init__(self, npz_path):
-        z = np.load(npz_path)
-        vt, sd = _f64(z["v_template"]), _f64(z["shapedirs"])
-        jr, wt = _f64(z["J_regressor"]), _f64(z["weights"])
-        parents = np.ascontiguousarray(z["kintree_table"][0].astype(np.uint32).astype(np.int32))
-        self.V, self.J, self.K = vt.shape[0], parents.shape[0], sd.shape[2]
-        self.h = _ref_avatar_lib().ref_model_create(self.V, self.J, self.K, _p(vt), _p(sd), _p(jr), _p(wt), _p(parents))
+
+class RefAvatar:
+    """ark::AvatarModel loaded by the reference's OWN AvatarModel.cpp (+ cnpy.cpp) from a model directory, and ark::Avatar
+    over it"""
+
+    def __init__(self, model_dir):
+        L = _ref_avatar_lib()
+        self.h = L.ref_model_load(model_dir.encode())
+        d = np.zeros(8, np.int32)
+        L.ref_model_dims(self.h, _p(d))
+        self.V, self.J, self.K, self.F, self.C, self.D, self.use_jsr, self.n_assigned = (int(v) for v in d)
+
+    def tables(self):
+        """what the reference's loader derived: dict(parent, base, key, jsr_base, jsr, init_pos, mesh, asg_start, asg_joint, asg_weight)"""
+        t = dict(parent=np.zeros(self.J, np.int32), base=np.zeros(3 * self.V), key=np.zeros((3 * self.V, self.K)),
+                 jsr_base=np.zeros(3 * self.J), jsr=np.zeros((3 * self.J, self.K)), init_pos=np.zeros((self.J, 3)),
+                 mesh=np.zeros((self.F, 3), np.int32), asg_start=np.zeros(self.V + 1, np.int32),
+                 asg_joint=np.zeros(self.n_assigned, np.int32), asg_weight=np.zeros(self.n_assigned))
+        _ref_avatar_lib().ref_model_tables(self.h, *(_p(t[k]) for k in ("parent", "base", "key", "jsr_base", "jsr", "init_pos", "mesh",
+                                                                     "asg_start", "asg_joint", "asg_weight")))
+        return t
 
     def update(self, p, R, w):
         cloud, jp, jt = np.zeros((self.V, 3)), np.zeros((self.J, 3)), np.zeros((self.J, 12))
@@ -519,24 +545,15 @@ def ref_avatar_available():
 
 class RefOptimizer:
     """ark::AvatarOptimizer of the reference (AvatarOptimizer.cpp compiled from /root/reference): its own prologue, visibility,
-    findNN over nanoflann, cost functors, evaluation callback and quaternion parameterization.  The solver loop is the
-    Levenberg-Marquardt restatement of oracle/ref_optimizer.cpp (Ceres is absent).  The model's derived tables (joint shape
-    regressor, assigned joints) are taken from the oracle model: AvatarModel.cpp's loaders are not compiled."""
+    findNN over nanoflann, cost functors, evaluation callback and quaternion parameterization, over a model loaded by the
+    reference's own AvatarModel.cpp.  The solver loop is the Levenberg-Marquardt restatement of oracle/ref_optimizer.cpp
+    (Ceres is absent)."""
 
-    def __init__(self, npz_path, omodel, prior_text_path, num_parts, part_map):
+    def __init__(self, model_dir, num_parts, part_map):
         L = _ref_avatar_lib()
-        z = np.load(npz_path)
-        vt, sd = _f64(z["v_template"]), _f64(z["shapedirs"])
-        jr, wt = _f64(z["J_regressor"]), _f64(z["weights"])
-        parents = np.ascontiguousarray(z["kintree_table"][0].astype(np.uint32).astype(np.int32))
-        faces = np.ascontiguousarray(np.asarray(z["f"]).astype(np.int64).astype(np.int32))
-        self.V, self.J, self.K, self.F = vt.shape[0], parents.shape[0], sd.shape[2], faces.shape[0]
-        base, reg, _init = omodel.joint_reg()
-        start, joint, weight = omodel.assigned()
-        self._keep = (vt, sd, jr, wt, parents, faces, base, reg, start, joint, weight)
-        self.hm = L.ref_model2_create(self.V, self.J, self.K, self.F, _p(vt), _p(sd), _p(jr), _p(wt), _p(parents), _p(faces), 1,
-                                      _p(_f64(base)), _p(_f64(reg)), _p(start), _p(joint), _p(_f64(weight)),
-                                      (prior_text_path or "").encode())
+        self.avatar = RefAvatar(model_dir)      # the reference's own loader
+        self.hm = self.avatar.h
+        self.V, self.J, self.K, self.F = self.avatar.V, self.avatar.J, self.avatar.K, self.avatar.F
         self.part_map = np.ascontiguousarray(part_map, dtype=np.int32)
         self.h = L.ref_opt_create(self.hm, int(num_parts), _p(self.part_map))
         self.nx, self.P = 3 + 4 * self.J + self.K, 3 + 3 * self.J + self.K

@@ -2,8 +2,9 @@
 // which oracle/Makefile compiles from /root/reference (never copied) against the Eigen stand-in under oracle/shim.  The
 // tests use it to check that the oracle's restatement of Avatar::update (Avatar.cpp:22-75), GaussianMixture::load / residual /
 // pdf (GaussianMixture.cpp:12-114), Avatar::smplParams (:128-137) and Avatar::alignToJoints (:141-193) computes what the
-// reference's code computes.  AvatarModel's file loader (AvatarModel.cpp: cnpy, PCD readers) is not compiled; its
-// constructor is defined here as "empty model" and the fields are filled from arrays.
+// reference's code computes.  The model is built by the reference's own loader: AvatarModel.cpp (+ its vendored cnpy.cpp)
+// reads <dir>/model.npz and pose_prior.txt; ref_model_tables hands out what it derived so that the oracle's restatement of the
+// loader (assigned joints, joint shape regressor, mesh, kinematic tree) can be compared with it.
 #include <cstdint>
 #include <cstdio>
 #include <random>
@@ -14,24 +15,10 @@
 #include "GaussianMixture.h"
 #include "Util.h"
 
-namespace ark {
-AvatarModel::AvatarModel(const std::string& model_dir, bool) : MODEL_DIR(model_dir) {
-    useJointShapeRegressor = false;
-    posePrior.nComps = -1;
-}
-namespace random_util {   // Util.cpp is not compiled; deterministic stand-ins (the tests do not sample)
-static std::mt19937& gen() { static std::mt19937 g(12345); return g; }
-float uniform(float a, float b) { return std::uniform_real_distribution<float>(a, b)(gen()); }
-float randn(float m, float v) { return std::normal_distribution<float>(m, v)(gen()); }
-float uniform(std::mt19937& rg, float a, float b) { return std::uniform_real_distribution<float>(a, b)(rg); }
-float randn(std::mt19937& rg, float m, float v) { return std::normal_distribution<float>(m, v)(rg); }
-}  // namespace random_util
-}  // namespace ark
-
 namespace {
-struct RefModel {
+struct RefModel {   // an ark::AvatarModel built by the reference's own constructor (AvatarModel.cpp) from a model directory
     ark::AvatarModel m;
-    RefModel() : m("") {}
+    explicit RefModel(const char* dir) : m(dir) {}
 };
 }  // namespace
 
@@ -77,33 +64,44 @@ void ref_gmm_tables(void* h, double* prec_cho, double* consts_log) {
     }
 }
 
-// ---- AvatarModel from arrays: v_template [V][3], shapedirs [V][3][K], j_regressor [J][V], weights [V][J], parent [J] ----
-void* ref_model_create(int V, int J, int K, const double* v_template, const double* shapedirs, const double* j_regressor,
-                       const double* weights, const int32_t* parent) {
-    auto* rm = new RefModel;
-    ark::AvatarModel& m = rm->m;
-    m.baseCloud.resize(3 * V);
-    for (int i = 0; i < 3 * V; ++i) m.baseCloud[i] = v_template[i];
-    m.keyClouds.resize(3 * V, K);
-    for (int i = 0; i < 3 * V; ++i)
-        for (int k = 0; k < K; ++k) m.keyClouds(i, k) = shapedirs[(size_t)i * K + k];
-    m.parent.resize(J);
-    for (int j = 0; j < J; ++j) m.parent[j] = parent[j];
-    std::vector<Eigen::Triplet<double>> tj, tw;
+// ---- AvatarModel through the reference's own loader: <dir>/model.npz (+ pose_prior.txt) ----
+void* ref_model_load(const char* dir) { return new RefModel(dir); }
+void ref_model_dims(void* h, int32_t* out8) {
+    ark::AvatarModel& m = static_cast<RefModel*>(h)->m;
+    int total = 0;
+    for (auto& a : m.assignedJoints) total += (int)a.size();
+    out8[0] = m.numPoints(); out8[1] = m.numJoints(); out8[2] = m.numShapeKeys(); out8[3] = m.numFaces();
+    out8[4] = m.posePrior.nComps; out8[5] = m.posePrior.nDims; out8[6] = m.useJointShapeRegressor ? 1 : 0; out8[7] = total;
+}
+// the tables the loader derives: parent [J], baseCloud [3V], keyClouds [3V][K] row-major, jointShapeRegBase [3J],
+// jointShapeReg [3J][K] row-major, initialJointPos [J][3], mesh [F][3], assigned CSR (start [V+1], joint, weight)
+void ref_model_tables(void* h, int32_t* parent, double* base, double* key, double* jsr_base, double* jsr, double* init_pos,
+                      int32_t* mesh, int32_t* asg_start, int32_t* asg_joint, double* asg_weight) {
+    ark::AvatarModel& m = static_cast<RefModel*>(h)->m;
+    const int V = m.numPoints(), J = m.numJoints(), K = m.numShapeKeys(), F = m.numFaces();
+    for (int j = 0; j < J; ++j) parent[j] = m.parent[j];
+    for (int i = 0; i < 3 * V; ++i) {
+        base[i] = m.baseCloud[i];
+        for (int k = 0; k < K; ++k) key[(size_t)i * K + k] = m.keyClouds(i, k);
+    }
+    for (int i = 0; i < 3 * J; ++i) {
+        jsr_base[i] = m.jointShapeRegBase[i];
+        for (int k = 0; k < K; ++k) jsr[(size_t)i * K + k] = m.jointShapeReg(i, k);
+    }
     for (int j = 0; j < J; ++j)
-        for (int v = 0; v < V; ++v)
-            if (j_regressor[(size_t)j * V + v] != 0.0) tj.emplace_back(v, j, j_regressor[(size_t)j * V + v]);
-    m.jointRegressor.resize(V, J);
-    m.jointRegressor.setFromTriplets(tj.begin(), tj.end());
-    for (int v = 0; v < V; ++v)
-        for (int j = 0; j < J; ++j)
-            if (weights[(size_t)v * J + j] != 0.0) tw.emplace_back(j, v, weights[(size_t)v * J + j]);
-    m.weights.resize(J, V);
-    m.weights.setFromTriplets(tw.begin(), tw.end());
-    // AvatarModel.cpp: initialJointPos = baseCloud (as 3 x V) * jointRegressor
-    Eigen::Map<ark::CloudType> base(m.baseCloud.data(), 3, V);
-    m.initialJointPos = base * m.jointRegressor;
-    return rm;
+        for (int c = 0; c < 3; ++c) init_pos[3 * j + c] = m.initialJointPos(c, j);
+    for (int f = 0; f < F; ++f)
+        for (int c = 0; c < 3; ++c) mesh[3 * f + c] = m.mesh(c, f);
+    int e = 0;
+    for (int v = 0; v < V; ++v) {
+        asg_start[v] = e;
+        for (auto& wj : m.assignedJoints[(size_t)v]) {
+            asg_weight[e] = wj.first;
+            asg_joint[e] = wj.second;
+            ++e;
+        }
+    }
+    asg_start[V] = e;
 }
 void ref_model_free(void* h) { delete static_cast<RefModel*>(h); }
 

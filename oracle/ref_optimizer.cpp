@@ -273,9 +273,9 @@ void Solve(const Solver::Options& options, Problem* problem, Solver::Summary* su
 }  // namespace ceres
 
 namespace {
-struct RefModel2 {
+struct RefModel2 {   // same layout as RefModel of ref_avatar.cpp: the model loaded by the reference's own AvatarModel.cpp
     ark::AvatarModel m;
-    RefModel2() : m("") {}
+    explicit RefModel2(const char* dir) : m(dir) {}
 };
 struct RefOpt {
     RefModel2* model;
@@ -295,62 +295,6 @@ void quiet_update(ark::Avatar& ava) {
 }  // namespace
 
 extern "C" {
-
-// AvatarModel filled from arrays; the derived tables (joint shape regressor, assigned joints) come from the caller
-// (AvatarModel.cpp's loaders are not compiled).  assigned_*: CSR over points, (weight, joint) sorted by descending weight.
-void* ref_model2_create(int V, int J, int K, int F, const double* v_template, const double* shapedirs, const double* j_regressor,
-                        const double* weights, const int32_t* parent, const int32_t* faces, int use_jsr, const double* jsr_base,
-                        const double* jsr, const int32_t* asg_start, const int32_t* asg_joint, const double* asg_weight,
-                        const char* prior_path) {
-    auto* rm = new RefModel2;
-    ark::AvatarModel& m = rm->m;
-    m.baseCloud.resize(3 * V);
-    for (int i = 0; i < 3 * V; ++i) m.baseCloud[i] = v_template[i];
-    m.keyClouds.resize(3 * V, K);
-    for (int i = 0; i < 3 * V; ++i)
-        for (int k = 0; k < K; ++k) m.keyClouds(i, k) = shapedirs[(size_t)i * K + k];
-    m.parent.resize(J);
-    for (int j = 0; j < J; ++j) m.parent[j] = parent[j];
-    m.mesh.resize(3, F);
-    for (int f = 0; f < F; ++f)
-        for (int c = 0; c < 3; ++c) m.mesh(c, f) = faces[(size_t)f * 3 + c];
-    std::vector<Eigen::Triplet<double>> tj, tw;
-    for (int j = 0; j < J; ++j)
-        for (int v = 0; v < V; ++v)
-            if (j_regressor[(size_t)j * V + v] != 0.0) tj.emplace_back(v, j, j_regressor[(size_t)j * V + v]);
-    m.jointRegressor.resize(V, J);
-    m.jointRegressor.setFromTriplets(tj.begin(), tj.end());
-    for (int v = 0; v < V; ++v)
-        for (int j = 0; j < J; ++j)
-            if (weights[(size_t)v * J + j] != 0.0) tw.emplace_back(j, v, weights[(size_t)v * J + j]);
-    m.weights.resize(J, V);
-    m.weights.setFromTriplets(tw.begin(), tw.end());
-    m.useJointShapeRegressor = use_jsr != 0;
-    if (use_jsr) {
-        m.jointShapeRegBase.resize(3 * J);
-        m.jointShapeReg.resize(3 * J, K);
-        for (int i = 0; i < 3 * J; ++i) {
-            m.jointShapeRegBase[i] = jsr_base[i];
-            for (int k = 0; k < K; ++k) m.jointShapeReg(i, k) = jsr[(size_t)i * K + k];
-        }
-        m.initialJointPos.resize(3, J);
-        for (int j = 0; j < J; ++j)
-            for (int c = 0; c < 3; ++c) m.initialJointPos(c, j) = jsr_base[3 * j + c];
-    } else {
-        Eigen::Map<ark::CloudType> base(m.baseCloud.data(), 3, V);
-        m.initialJointPos = base * m.jointRegressor;
-    }
-    m.assignedJoints.resize((size_t)V);
-    m.assignedPoints.resize((size_t)J);
-    for (int v = 0; v < V; ++v)
-        for (int e = asg_start[v]; e < asg_start[v + 1]; ++e) {
-            m.assignedJoints[(size_t)v].emplace_back(asg_weight[e], asg_joint[e]);
-            m.assignedPoints[(size_t)asg_joint[e]].emplace_back(asg_weight[e], v);
-        }
-    if (prior_path && prior_path[0]) m.posePrior.load(prior_path);
-    return rm;
-}
-void ref_model2_free(void* h) { delete static_cast<RefModel2*>(h); }
 
 void* ref_opt_create(void* model, int num_parts, const int32_t* part_map) {
     auto* rm = static_cast<RefModel2*>(model);

@@ -229,7 +229,7 @@ struct Triplet {
     Index col() const { return c; }
     T value() const { return v; }
 };
-template <class T, int Opt = ColMajor>
+template <class T, int Opt>
 class SparseMatrix {
 public:
     typedef T Scalar;
@@ -256,6 +256,29 @@ public:
             val[(size_t)k] = i->value();
         }
     }
+    void makeCompressed() {}
+    Index outerSize() const { return c; }
+    template <class X> void reserve(const X&) {}
+    T& insert(Index i, Index j) {   // keeps the row indices of a column ascending
+        Index k = start[(size_t)j];
+        while (k < start[(size_t)j + 1] && idx[(size_t)k] < i) ++k;
+        idx.insert(idx.begin() + k, i);
+        val.insert(val.begin() + k, T(0));
+        for (Index q = j + 1; q <= c; ++q) ++start[(size_t)q];
+        return val[(size_t)k];
+    }
+    class InnerIterator {
+        const SparseMatrix& m;
+        Index k, e, outer;
+    public:
+        InnerIterator(const SparseMatrix& m_, Index j) : m(m_), k(m_.start[(size_t)j]), e(m_.start[(size_t)j + 1]), outer(j) {}
+        operator bool() const { return k < e; }
+        InnerIterator& operator++() { ++k; return *this; }
+        Index row() const { return m.idx[(size_t)k]; }
+        Index col() const { return outer; }
+        Index index() const { return m.idx[(size_t)k]; }
+        T value() const { return m.val[(size_t)k]; }
+    };
     SparseCol<T> col(Index j) const { return SparseCol<T>{&idx, &val, start[(size_t)j], start[(size_t)j + 1], r}; }
     T coeff(Index i, Index j) const {
         T s = 0;
@@ -276,6 +299,18 @@ inline Matrix<T, Dynamic, Dynamic, ColMajor> operator*(const Base<A, T>& a, cons
     Matrix<T, Dynamic, Dynamic, ColMajor> o(a.d().rows(), 1);
     for (Index k = s.b; k < s.e; ++k)
         for (Index i = 0; i < o.rows(); ++i) o.ref(i, 0) += a.d().coeff(i, (*s.idx)[(size_t)k]) * (*s.val)[(size_t)k];
+    return o;
+}
+template <class D, class T> SparseMatrix<T, ColMajor> Base<D, T>::sparseView() const {
+    SparseMatrix<T, ColMajor> o(d().rows(), d().cols());
+    for (Index j = 0; j < d().cols(); ++j) {
+        for (Index i = 0; i < d().rows(); ++i)
+            if (d().coeff(i, j) != T(0)) {
+                o.idx.push_back(i);
+                o.val.push_back(d().coeff(i, j));
+            }
+        o.start[(size_t)j + 1] = (Index)o.idx.size();
+    }
     return o;
 }
 template <class A, class T, int Opt>

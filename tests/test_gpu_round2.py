@@ -422,11 +422,10 @@ def test_device_matches_reference_source(model, oracle_mod, omodel, prior_arrays
         pytest.skip("oracle/_ref/libref_avatar.so not built")
     from avatar_b200 import Fitter
     part_map, num_parts = prior_arrays["part_map"], int(prior_arrays["num_parts"])
-    path = str(tmp_path / "pose_prior.txt")
-    oracle_mod.write_prior_text(path, prior_arrays["weights"], prior_arrays["means"], prior_arrays["covs"])
     import os
     from conftest import GOLDEN
-    ro = oracle_mod.RefOptimizer(os.path.join(GOLDEN, "model_synth.npz"), omodel, path, num_parts, part_map)
+    mdir = oracle_mod.write_model_dir(str(tmp_path / "avatar-model"), os.path.join(GOLDEN, "model_synth.npz"), prior_arrays)
+    ro = oracle_mod.RefOptimizer(mdir, num_parts, part_map)
     fr = [_frame(model, omodel, prior_arrays, s) for s in (1000, 1001, 1002, 1003)]
     pts = np.concatenate([f[2] for f in fr])
     lab = np.concatenate([f[3] for f in fr])

@@ -704,12 +704,39 @@ def _need_ref_avatar(oracle_mod):
         pytest.skip("oracle/_ref/libref_avatar.so not built (reference tree absent and no prebuilt library)")
 
 
-def test_avatar_update_matches_reference_source(oracle_mod, omodel, prior_arrays):
+@pytest.fixture(scope="module")
+def ref_model_dir(oracle_mod, prior_arrays, tmp_path_factory):
+    """model.npz + pose_prior.txt, the layout the reference's own AvatarModel.cpp reads"""
+    _need_ref_avatar(oracle_mod)
+    return oracle_mod.write_model_dir(str(tmp_path_factory.mktemp("avatar-model")), os.path.join(GOLDEN, "model_synth.npz"),
+                                      prior_arrays)
+
+
+def test_model_loader_matches_reference_source(oracle_mod, omodel, ref_model_dir):
+    """AvatarModel::AvatarModel, npz branch (AvatarModel.cpp:23-127 + the reference's vendored cnpy.cpp), the reference's code
+    itself: kinematic tree, template, shape keys, mesh, the assigned (weight, joint) lists with their order and the 1e-12
+    threshold, and the derived joint shape regressor, against the oracle's restatement of the loader"""
+    ref = oracle_mod.RefAvatar(ref_model_dir)
+    assert (ref.V, ref.J, ref.K, ref.F, ref.C, ref.D, ref.use_jsr) == (omodel.V, omodel.J, omodel.K, omodel.F, omodel.C, omodel.D, 1)
+    t = ref.tables()
+    assert np.array_equal(t["parent"], omodel.parents)
+    assert np.array_equal(t["mesh"], omodel.faces)
+    base, reg, init = omodel.joint_reg()
+    assert np.abs(t["jsr_base"] - base).max() < 1e-13 and np.abs(t["jsr"] - reg).max() < 1e-13
+    assert np.abs(t["init_pos"].reshape(-1) - init).max() < 1e-13
+    start, joint, weight = omodel.assigned()
+    assert np.array_equal(t["asg_start"], start) and np.array_equal(t["asg_joint"], joint) and np.array_equal(t["asg_weight"], weight)
+    z = np.load(os.path.join(GOLDEN, "model_synth.npz"))
+    assert np.array_equal(t["base"], np.asarray(z["v_template"], np.float64).reshape(-1))
+    assert np.array_equal(t["key"], np.asarray(z["shapedirs"], np.float64).reshape(-1, omodel.K))
+
+
+def test_avatar_update_matches_reference_source(oracle_mod, omodel, prior_arrays, ref_model_dir):
     """Avatar::update (Avatar.cpp:22-75), the reference's code itself: cloud, joint positions and joint transforms of the
     oracle's restatement agree to rounding (the stand-in Eigen sums in index order, the oracle in its own order)"""
     _need_ref_avatar(oracle_mod)
     from harness import synth
-    ref = oracle_mod.RefAvatar(os.path.join(GOLDEN, "model_synth.npz"))
+    ref = oracle_mod.RefAvatar(ref_model_dir)
     hm = synth.HostModel(os.path.join(GOLDEN, "model_synth.npz"), prior_arrays)
     worst = 0.0
     for seed in range(6):
@@ -749,7 +776,7 @@ def test_gaussian_mixture_matches_reference_source(oracle_mod, omodel, prior_arr
         assert ref.pdf(x) >= 0.0
 
 
-def test_facade_align_to_joints_matches_reference_source(oracle_mod, omodel, prior_arrays, build_all, tmp_path):
+def test_facade_align_to_joints_matches_reference_source(oracle_mod, omodel, prior_arrays, build_all, tmp_path, ref_model_dir):
     """Avatar::alignToJoints + smplParams (Avatar.cpp:128-193): the facade's host code (avatar_b200/cpp/ark_b200.cpp) against
     the reference's own source on the joints of random poses, incl. a NaN joint (the reference keeps identity there)"""
     _need_ref_avatar(oracle_mod)
@@ -761,7 +788,7 @@ def test_facade_align_to_joints_matches_reference_source(oracle_mod, omodel, pri
     d.mkdir()
     shutil.copy(os.path.join(GOLDEN, "model_synth.npz"), str(d / "model.npz"))
     GaussianMixture.from_arrays(prior_arrays["weights"], prior_arrays["means"], prior_arrays["covs"]).save(str(d / "pose_prior.txt"))
-    ref = oracle_mod.RefAvatar(os.path.join(GOLDEN, "model_synth.npz"))
+    ref = oracle_mod.RefAvatar(ref_model_dir)
     hm = synth.HostModel(os.path.join(GOLDEN, "model_synth.npz"), prior_arrays)
     J = omodel.J
     for seed in range(3):
@@ -789,12 +816,8 @@ def test_facade_align_to_joints_matches_reference_source(oracle_mod, omodel, pri
 # the oracle against the reference's OWN AvatarOptimizer.cpp (cost functors, visibility, findNN, parameterization)
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
-def ref_opt(oracle_mod, omodel, prior_arrays, tmp_path_factory):
-    _need_ref_avatar(oracle_mod)
-    path = str(tmp_path_factory.mktemp("prior") / "pose_prior.txt")
-    oracle_mod.write_prior_text(path, prior_arrays["weights"], prior_arrays["means"], prior_arrays["covs"])
-    return oracle_mod.RefOptimizer(os.path.join(GOLDEN, "model_synth.npz"), omodel, path, int(prior_arrays["num_parts"]),
-                                   prior_arrays["part_map"])
+def ref_opt(oracle_mod, prior_arrays, ref_model_dir):
+    return oracle_mod.RefOptimizer(ref_model_dir, int(prior_arrays["num_parts"]), prior_arrays["part_map"])
 
 
 def _prologue(oracle_mod, x, J):
