@@ -137,6 +137,8 @@ struct avb_fitter {
     unsigned short* d_mlist = nullptr; int4* d_chunks = nullptr; int2* d_gruns = nullptr; LmState* d_state = nullptr;
     float* d_rec = nullptr; int* d_gstart = nullptr; int maxrb = 0, rec_stride = 0, rec_rs = 0;
     int nn_stage_cap = 0;
+    int nn_f32 = 1;                // nn_kernel: fp32 pre-scan with exact fp64 fallback (AVB_NN_F32=0: plain fp64 scan)
+    float4* d_pv_f32 = nullptr; float* d_pv_rmax = nullptr;
     int fused64 = 0;               // fp64 flow path, AVB_FUSED=1: fused record + Gram tasks (no d_rec round trip).  Measured NOT
                                    // faster (60.5 k vs 61.2 k frames/s): a chunk fills 75 % of the CTA's threads, DESIGN.md 5.4
     float* d_data_f32 = nullptr;   // avb_upload_batch_f32 staging
@@ -697,9 +699,11 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
         // SM (about 4600 vertices; back-face culling leaves roughly half of the model visible), never more than V
         cudaDeviceProp pr2;
         CUDA_TRY_FT(cudaGetDeviceProperties(&pr2, cfg->device));
-        const size_t per_cta = std::min<size_t>(pr2.sharedMemPerBlockOptin, (pr2.sharedMemPerMultiprocessor - 2 * 1024 - 2 * 8192) / 2);
-        ft->nn_stage_cap = (int)std::min<size_t>((size_t)V, (per_cta - 256) / 24);
-        if (const char* e = std::getenv("AVB_NN_STAGE")) ft->nn_stage_cap = std::max(0, std::min(std::atoi(e), (int)((pr2.sharedMemPerBlockOptin - 256) / 24)));
+        const size_t per_cta = std::min<size_t>(pr2.sharedMemPerBlockOptin, (pr2.sharedMemPerMultiprocessor - 2 * 1024 - 2 * 24576) / 2);
+        if (const char* e = std::getenv("AVB_NN_F32")) ft->nn_f32 = std::atoi(e) != 0;
+        const size_t bpv = ft->nn_f32 ? 16 : 24;
+        ft->nn_stage_cap = (int)std::min<size_t>((size_t)V, (per_cta - 256) / bpv);
+        if (const char* e = std::getenv("AVB_NN_STAGE")) ft->nn_stage_cap = std::max(0, std::min(std::atoi(e), (int)((pr2.sharedMemPerBlockOptin - 256) / bpv)));
     }
     DevParts& dp = ft->dp;
     dp.numParts = NP;
@@ -755,6 +759,10 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     TRY(dev_alloc(ft, &ft->d_pv_idx, B * V));
     TRY(dev_alloc(ft, &ft->d_pv_xyz, B * (size_t)ft->pv_stride));
     TRY(dev_alloc(ft, &ft->d_pv_start, B * (NP + 1)));
+    if (ft->nn_f32) {
+        TRY(dev_alloc(ft, &ft->d_pv_f32, B * (size_t)V));
+        TRY(dev_alloc(ft, &ft->d_pv_rmax, B));
+    }
     TRY(dev_alloc(ft, &ft->d_nn, NT));
     TRY(dev_alloc(ft, &ft->d_cnt, B * V));
     TRY(dev_alloc(ft, &ft->d_sum, B * 3 * V));
@@ -1313,6 +1321,8 @@ PoseArgs pose_args(avb_fitter* ft, const double* dx, bool vis, const avb_options
     a.pv_xyz = ft->d_pv_xyz;
     a.pv_start = ft->d_pv_start;
     a.pv_stride = ft->pv_stride;
+    a.pv_f32 = vis ? ft->d_pv_f32 : nullptr;
+    a.pv_rmax = ft->d_pv_rmax;
     return a;
 }
 
@@ -1341,6 +1351,10 @@ int enqueue_correspond(avb_fitter* ft, const double* dx, const avb_options* o, c
     na.pv_xyz = ft->d_pv_xyz;
     na.pv_start = ft->d_pv_start;
     na.pv_stride = ft->pv_stride;
+    na.pv_f32 = ft->d_pv_f32;
+    na.pv_rmax = ft->d_pv_rmax;
+    na.x = dx;
+    na.nx = ft->model->nx;
     na.nn_idx = ft->d_nn;
     na.cnt = ft->d_cnt;
     na.sum = ft->d_sum;

@@ -105,6 +105,7 @@ pose_visibility_kernel(DevModel M, DevParts Pt, PoseArgs a) {
     int* pv_start = a.pv_start + (size_t)f * (Pt.numParts + 1);
     const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     int base = 0;
+    float rmax = 0.f;   // a NaN coordinate makes fmaxf skip it; nn_kernel tests its own bound for finiteness
     for (int i0 = 0; i0 < V; i0 += nt) {
         const int i = i0 + tid;
         int v = -1, flag = 0;
@@ -128,9 +129,15 @@ pose_visibility_kernel(DevModel M, DevParts Pt, PoseArgs a) {
                 for (; p < Pt.numParts && Pt.part_start[p] == i; ++p) pv_start[p] = pos;
             if (flag) {
                 pv_idx[pos] = v;
-                pv_xyz[3 * (size_t)pos] = cloud[3 * (size_t)v];
-                pv_xyz[3 * (size_t)pos + 1] = cloud[3 * (size_t)v + 1];
-                pv_xyz[3 * (size_t)pos + 2] = cloud[3 * (size_t)v + 2];
+                const double c0 = cloud[3 * (size_t)v], c1 = cloud[3 * (size_t)v + 1], c2 = cloud[3 * (size_t)v + 2];
+                pv_xyz[3 * (size_t)pos] = c0;
+                pv_xyz[3 * (size_t)pos + 1] = c1;
+                pv_xyz[3 * (size_t)pos + 2] = c2;
+                if (a.pv_f32) {   // relative to the root translation: |m - p| stays within the body's extent
+                    const float f0 = (float)(c0 - xs[0]), f1 = (float)(c1 - xs[1]), f2 = (float)(c2 - xs[2]);
+                    a.pv_f32[(size_t)f * V + pos] = make_float4(f0, f1, f2, 0.f);
+                    rmax = fmaxf(rmax, fmaxf(fabsf(f0), fmaxf(fabsf(f1), fabsf(f2))));
+                }
             }
         }
         base += tot;
@@ -142,6 +149,19 @@ pose_visibility_kernel(DevModel M, DevParts Pt, PoseArgs a) {
             for (; p < Pt.numParts && Pt.part_start[p] == V; ++p) pv_start[p] = base;
         pv_start[Pt.numParts] = base;
     }
+    if (a.pv_f32) {   // frame maximum of |float coordinate|
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+        __syncthreads();
+        float* fscr = reinterpret_cast<float*>(iscr);
+        if (lane == 0) fscr[wid] = rmax;
+        __syncthreads();
+        if (tid == 0) {
+            float r = 0.f;
+            for (int q = 0; q < nw; ++q) r = fmaxf(r, fscr[q]);
+            a.pv_rmax[f] = r;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -152,15 +172,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // Shared memory holds the first a.stage_cap compacted vertices (host: what lets TWO CTAs share an SM; back-face culling
 // leaves about half of the model visible, so a frame's whole visible cloud normally fits); a part whose range ends beyond
 // the staged prefix is scanned from global memory (L2) instead -- same arithmetic, same order.
+constexpr int kNNPer = 4;               // points per thread between two CTA barriers
+constexpr int kNNPass = 512 * kNNPer;
+
 __global__ void __launch_bounds__(512, 2)
 nn_kernel(DevParts Pt, NNArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ int s_start[kMaxParts + 1];
-    __shared__ double s_wsum[16];
-    __shared__ int s_hist[kMaxParts + 1];
-    __shared__ unsigned short s_perm[512];
-    __shared__ double s_q2[512];
+    __shared__ double s_wsum[16 * kNNPer];
+    __shared__ int s_hist[kMaxParts + 1], s_off[kMaxParts + 1];
+    __shared__ unsigned short s_perm[kNNPass];
+    __shared__ double s_q2[kNNPass];
     const int tid = threadIdx.x;
     const int c = blockIdx.x;
     const int f = a.chunk_frame[c];
@@ -170,9 +193,10 @@ nn_kernel(DevParts Pt, NNArgs a) {
 
     const int* pv_start = a.pv_start + (size_t)f * (Pt.numParts + 1);
     if (tid <= Pt.numParts) s_start[tid] = pv_start[tid];
+    const bool fast = a.pv_f32 != nullptr;   // stage the float copy (16 B per vertex) for the pre-scan instead of the doubles
     const int nvis = min(pv_start[Pt.numParts], a.stage_cap);
-    // one TMA bulk copy of the (staged prefix of the) frame's compacted model cloud (nvis * 24 B, rounded up to 16 B)
-    const uint32_t bytes = (uint32_t)(((size_t)nvis * 24 + 15) & ~(size_t)15);
+    // one TMA bulk copy of the (staged prefix of the) frame's compacted model cloud (nvis * 24 B or 16 B, rounded up to 16 B)
+    const uint32_t bytes = (uint32_t)(((size_t)nvis * (fast ? 16 : 24) + 15) & ~(size_t)15);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -181,7 +205,7 @@ nn_kernel(DevParts Pt, NNArgs a) {
     if (tid == 0 && bytes > 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes)
                      : "memory");
-        const double* src = a.pv_xyz + (size_t)f * a.pv_stride;
+        const void* src = fast ? static_cast<const void*>(a.pv_f32 + (size_t)f * a.V) : static_cast<const void*>(a.pv_xyz + (size_t)f * a.pv_stride);
         uint32_t off = 0;
         while (off < bytes) {  // <= 64 KiB per bulk copy
             const uint32_t n = min(bytes - off, 65536u);
@@ -209,28 +233,44 @@ nn_kernel(DevParts Pt, NNArgs a) {
     int* cnt = a.cnt + (size_t)f * a.V;
     unsigned long long* sum = a.sum + (size_t)f * 3 * a.V;
     const int lane = tid & 31, wid = tid >> 5;
-    // passes of 512 points = two deterministic |d|^2 blocks of kQBlock (256) points.  Inside a pass the points are dealt
-    // to the threads SORTED BY PART LABEL (a counting sort in shared memory): image-ordered clouds put two or more labels
-    // into most warps, and a warp whose lanes scan different parts runs those scans one after the other.  Which thread
-    // handles which point does not matter for the result: the index goes back to the point's own slot, the per-vertex
-    // sums are integer atomics, and |d|^2 returns to the point's original position before the block sums.
-    for (int base = 0; base < count; base += 512) {
+    // passes of kNNPass = 2048 points = eight deterministic |d|^2 blocks of kQBlock (256) points, four points per thread.
+    // Inside a pass the points are dealt to the threads SORTED BY PART LABEL (a counting sort in shared memory): image-ordered
+    // clouds put two or more labels into most warps, and a warp whose lanes scan different parts runs those scans one after
+    // the other.  Thread t takes the sorted positions t, t + 512, ... so every warp works through four different label runs
+    // between two CTA barriers: parts differ tenfold in size, and with one point per thread a fifth of the kernel was spent
+    // waiting for the warp that drew the largest part.  Which thread handles which point does not matter for the result: the
+    // index goes back to the point's own slot, the per-vertex sums are integer atomics, and |d|^2 returns to the point's
+    // original position before the block sums.
+    for (int base = 0; base < count; base += kNNPass) {
         if (tid <= kMaxParts) s_hist[tid] = 0;
         __syncthreads();
-        const int li0 = base + tid;
-        int mylab = kMaxParts;   // bucket of "nothing to scan"
-        if (li0 < count) {
-            const int label = a.labels[begin + li0];
-            if (label >= 0 && label < Pt.numParts) mylab = label;
-            else atomicOr(a.range_flag + f, 2);   // out of range is UB in the reference (:1279)
+        int mylab[kNNPer], slot[kNNPer];
+#pragma unroll
+        for (int j = 0; j < kNNPer; ++j) {
+            const int li0 = base + j * 512 + tid;
+            mylab[j] = kMaxParts;   // bucket of "nothing to scan"
+            if (li0 < count) {
+                const int label = a.labels[begin + li0];
+                if (label >= 0 && label < Pt.numParts) mylab[j] = label;
+                else atomicOr(a.range_flag + f, 2);   // out of range is UB in the reference (:1279)
+            }
+            slot[j] = atomicAdd(&s_hist[mylab[j]], 1);
         }
-        const int slot = atomicAdd(&s_hist[mylab], 1);
         __syncthreads();
-        int pos = slot;
-        for (int l = 0; l < mylab; ++l) pos += s_hist[l];
-        s_perm[pos] = (unsigned short)tid;
+        if (tid == 0) {   // exclusive prefix over the label buckets
+            int run = 0;
+            for (int l = 0; l <= kMaxParts; ++l) {
+                s_off[l] = run;
+                run += s_hist[l];
+            }
+        }
         __syncthreads();
-        const int src = s_perm[tid], li = base + src;
+#pragma unroll
+        for (int j = 0; j < kNNPer; ++j) s_perm[s_off[mylab[j]] + slot[j]] = (unsigned short)(j * 512 + tid);
+        __syncthreads();
+#pragma unroll 1
+        for (int j = 0; j < kNNPer; ++j) {
+        const int src = s_perm[j * 512 + tid], li = base + src;
         double q2 = 0.0;
         if (li < count) {
             const long long gi = begin + li;
@@ -240,9 +280,42 @@ nn_kernel(DevParts Pt, NNArgs a) {
             const int s = lab_ok ? s_start[label] : 0, e = lab_ok ? s_start[label + 1] : 0;
             double best = 1.79769313486231570e308;
             int bi = -1;
-            const double* mxyz = (e <= a.stage_cap) ? mstage : a.pv_xyz + (size_t)f * a.pv_stride;
+            bool need_exact = e > s;
+            if (fast && e > s && e <= a.stage_cap) {
+                // ---- fp32 pre-scan (exact RESULT, inexact SEARCH): best and second-best float distance to the staged float
+                //      copy (coordinates relative to the root translation p).  If the two are separated by more than the
+                //      rigorous error bound of the float pipeline, the best candidate IS the exact nearest neighbour and no
+                //      fp64 distance is ever evaluated; otherwise (near-ties, non-finite input) the exact scan below runs.
+                //      Error of one float coordinate difference: conversions of q - p and m - p (2^-24 relative each) and the
+                //      subtraction (2^-24 of the result) <= 2^-24 (|q-p| + |m-p| + |diff|) <= e = 2^-22 R, R >= every
+                //      |coordinate|.  Hence |d~ - d| <= 2 sqrt(3 d) e + 3 e^2 + 2^-21 d~ =: E(d~) (products and sums: 3 ulp).
+                const float4* fst = reinterpret_cast<const float4*>(mstage);
+                const double* px = a.x + (size_t)f * a.nx;
+                const float qx = (float)(q0 - px[0]), qy = (float)(q1 - px[1]), qw = (float)(qz - px[2]);
+                const float R = fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fmaxf(fabsf(qw), a.pv_rmax[f]));
+                const float eb = 2.4e-7f * R;   // 2^-22 R, rounded up
+                float b1 = __int_as_float(0x7f800000), b2 = b1;
+                int i1 = -1;
 #pragma unroll 4
-            for (int k = s; k < e; ++k) {
+                for (int k = s; k < e; ++k) {
+                    const float4 m = fst[k];
+                    const float dx = qx - m.x, dy = qy - m.y, dz = qw - m.z;
+                    const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    b2 = fminf(b2, fmaxf(d, b1));
+                    if (d < b1) i1 = k;
+                    b1 = fminf(b1, d);
+                }
+                const float E1 = (3.4642f * sqrtf(b1) * eb + 3.f * eb * eb + 4.8e-7f * b1) * 1.01f;
+                const float E2 = (3.4642f * sqrtf(b2) * eb + 3.f * eb * eb + 4.8e-7f * b2) * 1.01f;
+                // x - E(x) is increasing for x > 3 e^2, so every other candidate's exact distance exceeds b2 - E(b2)
+                if (i1 >= 0 && b2 > 4.f * eb * eb && b2 - E2 > b1 + E1) {   // false for NaN / inf anywhere
+                    bi = i1;
+                    need_exact = false;
+                }
+            }
+            const double* mxyz = (!fast && e <= a.stage_cap) ? mstage : a.pv_xyz + (size_t)f * a.pv_stride;
+#pragma unroll 4
+            for (int k = s; k < (need_exact ? e : s); ++k) {
                 // nanoflann L2_Simple: sum_c (a_c - b_c)^2, c = 0,1,2 (nanoflann.hpp:423-445); strict '<'
                 const double d0 = q0 - mxyz[3 * k], d1 = q1 - mxyz[3 * k + 1], d2 = qz - mxyz[3 * k + 2];
                 // ((d0^2 + d1^2) + d2^2) with every product and sum rounded: the reference is built without -march
@@ -275,16 +348,20 @@ nn_kernel(DevParts Pt, NNArgs a) {
             a.nn_idx[gi] = vtx;
         }
         s_q2[src] = q2;
+        }   // points of this thread
         __syncthreads();
-        // deterministic per-256-point partial of sum |d|^2, in the points' own order
-        q2 = warp_sum(s_q2[tid]);
-        if (lane == 0) s_wsum[wid] = q2;
+        // deterministic per-256-point partials of sum |d|^2, in the points' own order
+#pragma unroll
+        for (int j = 0; j < kNNPer; ++j) {
+            const double v = warp_sum(s_q2[j * 512 + tid]);
+            if (lane == 0) s_wsum[j * 16 + wid] = v;
+        }
         __syncthreads();
-        if (tid < 2) {
+        if (tid < 2 * kNNPer) {
             const int blk = (base / kQBlock) + tid;  // block index inside this chunk
             if (blk * kQBlock < count) {
                 double sacc = 0;
-                for (int q = 0; q < 8; ++q) sacc += s_wsum[8 * tid + q];
+                for (int q = 0; q < 8; ++q) sacc += s_wsum[(tid >> 1) * 16 + (tid & 1) * 8 + q];
                 a.qpart[a.chunk_qblock[c] + blk] = sacc;
             }
         }
@@ -325,7 +402,7 @@ size_t pose_smem_bytes(int V, int J, int K) {
     return (size_t)(((nx + 1) & ~1) + tables_doubles(J, K, false)) * 8 + 64 * 4 + (size_t)V + 64;
 }
 
-size_t nn_smem_bytes(int stage_cap) { return (((size_t)stage_cap * 24 + 15) & ~(size_t)15) + 128; }
+size_t nn_smem_bytes(int stage_cap, bool f32) { return (((size_t)stage_cap * (f32 ? 16 : 24) + 15) & ~(size_t)15) + 128; }
 
 cudaError_t launch_pose_visibility(const DevModel& M, const DevParts& Pt, const PoseArgs& a, int batch, cudaStream_t st) {
     const size_t smem = pose_smem_bytes(M.V, M.J, M.K);
@@ -338,7 +415,7 @@ cudaError_t launch_pose_visibility(const DevModel& M, const DevParts& Pt, const 
 }
 
 cudaError_t launch_nn(const DevParts& Pt, const NNArgs& a, int num_chunks, cudaStream_t st) {
-    const size_t smem = nn_smem_bytes(a.stage_cap);
+    const size_t smem = nn_smem_bytes(a.stage_cap, a.pv_f32 != nullptr);
     {   // per device/context attribute: set on every launch (cheap host call)
         cudaError_t e = cudaFuncSetAttribute(nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -19,6 +19,8 @@ struct PoseArgs {
     double* pv_xyz;        // [batch][pv_stride] compacted positions
     int* pv_start;         // [batch][numParts+1]
     long long pv_stride;   // doubles per frame (even, >= 3V + 2)
+    float4* pv_f32;        // nullable [batch][V]: the compacted positions relative to the root translation p, as floats (nn_kernel's pre-scan)
+    float* pv_rmax;        // [batch]: max |coordinate| of pv_f32 of the frame (error bound of the pre-scan)
 };
 
 struct NNArgs {
@@ -33,6 +35,10 @@ struct NNArgs {
     const double* pv_xyz;
     const int* pv_start;
     long long pv_stride;
+    const float4* pv_f32;        // nullable: float copy relative to x[f][0..2] (pose_visibility_kernel); null = plain fp64 scan
+    const float* pv_rmax;        // [batch]
+    const double* x;             // [batch][nx] the parameters the cloud was posed with (root translation = centre of pv_f32)
+    int nx;
     int* nn_idx;                 // [total points]
     int* cnt;                    // [batch][V]
     unsigned long long* sum;     // [batch][V][3] fixed point 2^36
@@ -165,7 +171,7 @@ int cloud_strip_rows();
 cudaError_t launch_cloud_count(const CloudArgs& a, int strips, int batch, cudaStream_t st);
 cudaError_t launch_cloud_compact(const CloudArgs& a, int strips, int batch, cudaStream_t st);
 size_t pose_smem_bytes(int V, int J, int K);
-size_t nn_smem_bytes(int stage_cap);
+size_t nn_smem_bytes(int stage_cap, bool f32);
 cudaError_t launch_widen_points(const float* in, double* out, long long n, int num_sms, cudaStream_t st);
 cudaError_t launch_pose_visibility(const DevModel& M, const DevParts& Pt, const PoseArgs& a, int batch, cudaStream_t st);
 cudaError_t launch_nn(const DevParts& Pt, const NNArgs& a, int num_chunks, cudaStream_t st);

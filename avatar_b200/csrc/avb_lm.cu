@@ -258,12 +258,11 @@ __host__ __device__ inline int rec_floats(int nj, int K) { return 3 * nj + 3 * K
 
 // One matched vertex: its compact Jacobian record (fields at rec[q * RS]: the global SoA of the staged / two-task schedule,
 // or a column of the shared-memory tile of the fused task) and its cost term x . (c x - 2 s).
-// KT > 0: the number of shape keys is a compile-time constant (SMPL: 10), so the loops over them unroll and the 3 K shapedirs
-// loads of the vertex are issued back to back instead of one L2 round trip per loop iteration.
-template <int KT>
+// (Rolled loops over the K shape keys on purpose: a K = 10 specialisation that unrolls them was measured 2 % SLOWER -- 2.7 x
+// the code, index arrays demoted to local memory -- tasks run cold, code size is time.)
 __device__ __forceinline__ double record_vertex(const DevModel& M, const DevParts& Pt, const LmBuf& a, int f, int v, int g,
                                                 float* rec, size_t RS, bool cost_only, const double* tab, const double* w) {
-    const int J = M.J, K = KT > 0 ? KT : M.K;
+    const int J = M.J, K = M.K;
     const double* G = tab;
     const double* pos = tab + 9 * J;
     const double* tau = tab + 12 * J;
@@ -276,8 +275,7 @@ __device__ __forceinline__ double record_vertex(const DevModel& M, const DevPart
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         double s = 0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) s += (double)__ldg(sd + c * K + k) * w[k];
+        for (int k = 0; k < K; ++k) s += (double)sd[c * K + k] * w[k];
         v0[c] = M.vt[3 * (size_t)v + c] + s;
     }
     const int n = M.sk_n[v];
@@ -328,10 +326,8 @@ __device__ __forceinline__ double record_vertex(const DevModel& M, const DevPart
     // shape: sum_k w_k (G_k (Delta_v - S_k) + H_k) = B Delta_v + sum_k w_k C_k  (AvatarOptimizer.cpp:568-580)
     float* rr = rec + (size_t)(3 * nj) * RS;   // sc | rho_hi | rho_lo
     float* rs = rr + 7 * RS;
-#pragma unroll
-    for (int m = 0; m < K; ++m) {
-        if (cost_only) break;
-        const double d0 = __ldg(sd + m), d1 = __ldg(sd + K + m), d2 = __ldg(sd + 2 * K + m);
+    for (int m = 0; m < (cost_only ? 0 : K); ++m) {
+        const double d0 = sd[m], d1 = sd[K + m], d2 = sd[2 * K + m];
         double e0 = B[0] * d0 + B[1] * d1 + B[2] * d2;
         double e1 = B[3] * d0 + B[4] * d1 + B[5] * d2;
         double e2 = B[6] * d0 + B[7] * d1 + B[8] * d2;
@@ -388,8 +384,7 @@ __device__ void rows_body(const DevModel& M, const DevParts& Pt, const LmBuf& a,
         int g = 0;
         while (g + 1 < Pt.numGroups && i >= gstart[g + 1]) ++g;
         float* rec = a.rec + (size_t)f * a.rec_stride * a.rec_rs + i;
-        costv = M.K == 10 ? record_vertex<10>(M, Pt, a, f, s_v[tid], g, rec, (size_t)a.rec_rs, cost_only, tab, w)
-                          : record_vertex<0>(M, Pt, a, f, s_v[tid], g, rec, (size_t)a.rec_rs, cost_only, tab, w);
+        costv = record_vertex(M, Pt, a, f, s_v[tid], g, rec, (size_t)a.rec_rs, cost_only, tab, w);
     }
     const double cs = block_sum(costv, scr);
     if (tid == 0) a.cpart[(size_t)f * a.maxrb + blk] = cs;
@@ -639,8 +634,7 @@ __device__ void fused64_body(const DevModel& M, const DevParts& Pt, const LmBuf&
     phase_lap(a.q, 12, tp);
     double costv = 0.0;
     if (v != (int)kNoVertex)
-        costv = M.K == 10 ? record_vertex<10>(M, Pt, a, f, v, g, T + tid, (size_t)ldt, cost_only, tab, w)
-                          : record_vertex<0>(M, Pt, a, f, v, g, T + tid, (size_t)ldt, cost_only, tab, w);
+        costv = record_vertex(M, Pt, a, f, v, g, T + tid, (size_t)ldt, cost_only, tab, w);
     const double cs = block_sum(costv, scr);
     if (tid == 0) a.cpart[(size_t)f * a.maxrb + c] = cs;
     phase_lap(a.q, 13, tp);
