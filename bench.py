@@ -455,6 +455,15 @@ def main():
                 "algorithmic_bytes": "SURVEY 8(d): inner solve = iterations x frames x (16 N + 4 P^2 + 4 P) B; whole step = 180 N + 0.91 MB per frame",
                 "step": {"algorithmic_bytes": alg_step_total, "achieved": alg_step_total / (dev_ms / args.steps * 1e-3) / 1e9,
                          "frac": alg_step_total / (dev_ms / args.steps * 1e-3) / 1e9 / peak},
+                "front": {"kernels": "pose_visibility_kernel + nn_kernel (LBS + visibility + correspondence)",
+                          "algorithmic_bytes": alg_step["pose_visibility_kernel"] + alg_step["nn_kernel"],
+                          "ms_per_step": kms["pose_visibility_kernel"] + kms["nn_kernel"],
+                          "achieved": (alg_step["pose_visibility_kernel"] + alg_step["nn_kernel"]) /
+                                      ((kms["pose_visibility_kernel"] + kms["nn_kernel"]) * 1e-3) / 1e9,
+                          "frac": (alg_step["pose_visibility_kernel"] + alg_step["nn_kernel"]) /
+                                  ((kms["pose_visibility_kernel"] + kms["nn_kernel"]) * 1e-3) / 1e9 / peak,
+                          "note": "SURVEY 8(d): 20 N + 12 V bytes per frame; the kernels are compute bound (fp32 / fp64 distance "
+                                  "evaluations), not HBM bound (DESIGN.md section 5.2)"},
                 "avg_launch_ms": avg_launch_ms, "launches_per_step": dom_launches,
                 "kernel_ms_per_step": {k: round(v, 4) for k, v in kms.items()},
                 "kernel_share": {k: round(v / tot_ms, 4) for k, v in kms.items()},
