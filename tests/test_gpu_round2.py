@@ -478,3 +478,19 @@ def test_fused_fp64_tasks_match_the_two_task_schedule(model, omodel, prior_array
     for a, b in zip(sa, sb):
         assert a.iterations == b.iterations and a.accepted_steps == b.accepted_steps
         assert abs(a.final_cost - b.final_cost) <= 1e-9 * a.final_cost
+
+
+def test_gather_entry_points_without_communicator(model, prior_arrays):
+    """avb_gather_params / _begin / _end report AVB_ERR_INVALID (not a crash, not stale data) on a fitter that never joined a
+    communicator, and _end without _begin likewise"""
+    import ctypes as C
+    from avatar_b200 import Fitter, _lib
+    ft = Fitter(model, int(prior_arrays["num_parts"]), prior_arrays["part_map"], 2, 4096)
+    out = np.zeros((1, 2, ft.nx))
+    for fn, args in ((_lib.lib.avb_gather_params, (ft.handle, out.ctypes.data_as(C.c_void_p))),
+                     (_lib.lib.avb_gather_params_begin, (ft.handle,)),
+                     (_lib.lib.avb_gather_params_end, (ft.handle, out.ctypes.data_as(C.c_void_p)))):
+        rc = fn(*args)
+        assert rc != 0
+        assert b"communicator" in _lib.lib.avb_last_error() or b"gather" in _lib.lib.avb_last_error()
+    ft.close()
