@@ -743,6 +743,34 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     TRY(dev_put(ft, &dp.gvstart, gvstart));
     TRY(dev_put(ft, &dp.gjoints, gjoints));
     TRY(dev_put(ft, &dp.gnj, gnj));
+    {   // scatter table of the partial reduction (lm_solve): group column -> tangent column [ p | 3 per joint | shape ]
+        const int J = m->J, K = m->K, Pn = m->P, nTri = Pn * (Pn + 1) / 2;
+        std::vector<int> gdoff(gnj.size() + 1, 0), gdest;
+        for (size_t g = 0; g < gnj.size(); ++g) {
+            const int nj = gnj[g], Lg = 3 + 3 * nj + K, nH = ((Lg + 1) >> 1) * (Lg + 1);   // tri_count(Lg), tri_decode order
+            auto col = [&](int r) { return r < 3 ? r : (r < 3 + 3 * nj ? 3 + 3 * gjoints[g * kMaxJ + (r - 3) / 3] + (r - 3) % 3 : r + 3 * (J - nj)); };
+            for (int idx = 0; idx < nH + Lg; ++idx) {
+                int dest = -1;
+                if (idx < nH) {
+                    const int r = idx / (Lg + 1), c = idx - r * (Lg + 1);
+                    int ra, rb;
+                    bool ok = true;
+                    if (c < Lg - r) { ra = r; rb = r + c; }
+                    else { ra = Lg - 1 - r; rb = ra + (c - (Lg - r)); ok = ra != r; }
+                    if (ok) {
+                        const int ca = col(ra), cb = col(rb);
+                        dest = ca >= cb ? ca * (ca + 1) / 2 + cb : cb * (cb + 1) / 2 + ca;
+                    }
+                } else {
+                    dest = nTri + col(idx - nH);
+                }
+                gdest.push_back(dest);
+            }
+            gdoff[g + 1] = (int)gdest.size();
+        }
+        TRY(dev_put(ft, &dp.gdoff, gdoff));
+        TRY(dev_put(ft, &dp.gdest, gdest));
+    }
 
     // ---- batch buffers ----
     const size_t B = (size_t)cfg->max_batch, NT = (size_t)cfg->max_total_points;

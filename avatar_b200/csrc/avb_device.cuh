@@ -49,6 +49,9 @@ struct DevParts {
     const int* gvstart;        // [numGroups+1] into gorder
     const int* gjoints;        // [numGroups][kMaxJ] joint ids of the group's column set (ascending)
     const int* gnj;            // [numGroups]
+    const int* gdoff;          // [numGroups+1] into gdest
+    const int* gdest;          // per group, per entry of a chunk partial [ J^T J triangle | J^T r ]: where the solve adds it --
+                               // index into the packed P x P lower triangle, tri(P) + column for the gradient, -1 = unused slot
 };
 
 struct FrameStats {  // mirrors avb_stats

@@ -1138,14 +1138,18 @@ struct SolveSmem {
 // packed lower triangle, row major: entry (i, k), k <= i, at tri(i) + k.  The solve keeps J^T J (+ priors, + damping) and
 // its Cholesky factor in this form: 29 KB instead of 58 KB for P = 85, which is what lets three or four CTAs share an SM.
 __host__ __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
+// leading dimension of the column-major Cholesky panel Lp[c][row - t0]: rows padded to whole 8-row tiles, = 4 (mod 8) so
+// that the fragment loads of the tensor-path trailing update (lane -> column lane & 3, row lane >> 2) are bank-conflict free
+__host__ __device__ __forceinline__ int chol_ldp(int R) { return ((R + 7) & ~7) + 4; }
 __host__ __device__ inline int solve_tb_doubles(int J, int K, int C) {
-    // early phases: joint rotations G (9 J) | gradient moments (3 + 6 J + K) | pos (3 J) | C (3 J K); prior: dcomp | ycomp;
-    // factorisation: column-major panel (8 x ((P + 5) & ~3) + 8).  The joint tables of the retraction alias the matrix.
+    // early phases: joint rotations G (9 J) | gradient moments (3 + 6 J + K) | pos (3 J) | C (3 J K);
+    // factorisation: column-major panel (8 x chol_ldp(P + 1) + 8).  The joint tables of the retraction alias the matrix.
+    // (The prior's dcomp | ycomp have their own scratch: the prior is evaluated next to the partial reduction.)
     const int P = 3 + 3 * J + K, D = 3 * (J - 1);
     int t = 9 * J + ((tc_gacc(J, K) + 1) & ~1) + 3 * J + 3 * J * K;
-    const int pnl = 8 * ((P + 5) & ~3) + 8, gm = 2 * (C > 0 ? C : 1) * ((D + 8) & ~7);
-    t = t > pnl ? t : pnl;
-    return ((t > gm ? t : gm) + 1) & ~1;
+    const int pnl = 8 * chol_ldp(P + 1) + 8;
+    (void)C; (void)D;
+    return ((t > pnl ? t : pnl) + 1) & ~1;
 }
 __host__ __device__ inline int solve_h_doubles(int J, int K) {
     const int P = 3 + 3 * J + K, h = tri(P + 1) + 2, t = tables_doubles(J, K, true);
@@ -1153,7 +1157,8 @@ __host__ __device__ inline int solve_h_doubles(int J, int K) {
 }
 __host__ __device__ inline size_t solve_smem_bytes(int J, int K, int C) {
     const int P = 3 + 3 * J + K, nx = 3 + 4 * J + K, D = 3 * (J - 1);
-    size_t d = 2 * ((nx + 1) & ~1) + solve_tb_doubles(J, K, C) + solve_h_doubles(J, K) + 5 * ((P + 1) & ~1) + 8 * kNBsq + ((D + 1) & ~1) + 64;
+    size_t d = 2 * ((nx + 1) & ~1) + solve_tb_doubles(J, K, C) + solve_h_doubles(J, K) + 5 * ((P + 1) & ~1) + 8 * kNBsq + ((D + 1) & ~1) + 64 +
+               2 * (size_t)(C > 0 ? C : 1) * ((D + 8) & ~7);
     return d * 8 + 64 * 4 + 128;
 }
 __device__ inline SolveSmem carve_solve(unsigned char* raw, const DevModel& M) {
@@ -1171,29 +1176,42 @@ __device__ inline SolveSmem carve_solve(unsigned char* raw, const DevModel& M) {
     S.dd = d; d += (P + 1) & ~1;
     S.wscr = d; d += 8 * kNBsq;
     S.aa = d; d += (D + 1) & ~1;
-    S.dcomp = S.tb;                                        // the prior's scratch shares the table scratch (disjoint in time)
-    S.ycomp = S.tb + (size_t)(M.gmmC > 0 ? M.gmmC : 1) * ((D + 8) & ~7);
     S.scr = d; d += 64;
+    S.dcomp = d; d += (size_t)(M.gmmC > 0 ? M.gmmC : 1) * ((D + 8) & ~7);
+    S.ycomp = d; d += (size_t)(M.gmmC > 0 ? M.gmmC : 1) * ((D + 8) & ~7);
     S.iscr = reinterpret_cast<int*>(d);
     return S;
 }
 
 // CTA-wide blocked right-looking Cholesky of the leading P x P lower triangle of W (PACKED lower, row major: tri(i) + k),
 // carried through R >= P rows: rows P..R-1 enter as right-hand sides b^T and leave as (L^-1 b)^T, i.e. the forward
-// substitution comes for free.  Panels of 8 columns: every warp factors the 8x8 diagonal block redundantly in
-// registers (one row per lane, shuffles), solves its share of the rows below against it, and all threads apply the
-// rank-8 update to the trailing matrix as 4x4 register tiles: two CTA barriers per panel.  dinv receives 1 / L_jj.
-// Returns false (uniformly) when a pivot is not positive.
+// substitution comes for free.  dinv receives 1 / L_jj.  Returns false (uniformly) when a pivot is not positive.
+//
+// The factorisation is a chain of P dependent pivots; everything else is throughput.  So warp 0 runs the chain AHEAD of
+// the trailing update (measured, tools/ubench/chol_ubench.cu: 54.0 k -> 31.5 k cycles for P = 85 on one CTA):
+//   warp 0, panel j:  its eight rows of the panel (x = w L11^-T) -> bar.arrive -> update of the NEXT diagonal block from
+//                     those rows (registers) -> its factorisation (one row per lane, shuffles) -> L11 of panel j + 1
+//   warps 1..7:       the other rows of the panel -> bar.sync -> trailing update S -= X X^T on 8 x 8 tiles with the fp64
+//                     tensor path (mma.m8n8k4, two k-steps per tile, two tiles in flight), every tile except warp 0's
+//   one CTA barrier per panel.  Pivot step: a_c -= (a_k a_ck) / d with 1 / d from the fp64 MUFU seed (2^-20) and one
+//   cubic Newton step (three dependent fp64 operations); the square roots are taken after the chain.
 constexpr int kNB = 8;
-// 1 / sqrt(d) for a pivot: single-precision seed and two Newton steps in fp64 (full double accuracy up to rounding),
-// without the special-case handling of rsqrt(double); pivots outside the float range take the library path
+// 1 / d for a pivot in the guarded range: 2^-20 seed, one cubic step (error e^3 = 2^-60)
+__device__ __forceinline__ double pivot_rcp(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double e = fma(-d, y, 1.0);
+    const double p = fma(e, e, e);
+    return fma(y, p, y);
+}
+// 1 / sqrt(d): 2^-19 seed, one cubic step and one linear fix-up (full double accuracy up to rounding)
 __device__ __forceinline__ double pivot_rsqrt(double d) {
-    if (!(d > 1e-30 && d < 1e30)) return rsqrt(d);
-    double y = (double)rsqrtf((float)d);
-    const double h = 0.5 * d;
-    y = fma(y, fma(-h * y, y, 0.5), y);
-    y = fma(y, fma(-h * y, y, 0.5), y);
-    return y;
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d * y, y, 1.0);
+    y = fma(y, fma(0.375 * e, e, 0.5 * e), y);
+    e = fma(-d * y, y, 1.0);
+    return fma(0.5 * y, e, y);
 }
 #ifdef AVB_UBENCH_PHASES
 __device__ long long g_chol_cyc[4];
@@ -1201,127 +1219,185 @@ __device__ long long g_chol_cyc[4];
 #else
 #define CHOL_T(k) do { } while (0)
 #endif
+// one warp, lane & 7 = row: factor the nb x nb block whose row r (entries c <= r; rows >= nb: identity) the lane holds in a[].
+// Writes L to W, the row-scaled copy Lw[c][k] = L_ck / L_cc (diagonal: 1 / L_cc) and dinv.
+__device__ __forceinline__ bool diag_factor(double (&a)[kNB], double* W, int j0, int nb, double* Lw, double* dinv, int lane) {
+    const int r = lane & 7;
+    bool ok = true;
+    double mydiag = 1.0;
+#pragma unroll
+    for (int k = 0; k < kNB; ++k) {
+        const double d = __shfl_sync(0xffffffffu, a[k], k);
+        if (!(d > 1e-300) || !(d < 1e300)) ok = false;   // not positive, not finite, or outside the seed's range
+        const double inv = pivot_rcp(d);
+        if (r == k) mydiag = d;
+#pragma unroll
+        for (int c = k + 1; c < kNB; ++c) {
+            const double ack = __shfl_sync(0xffffffffu, a[k], c);
+            a[c] = fma(-(a[k] * ack), inv, a[c]);
+        }
+    }
+    if (!ok) return false;   // uniform over the warp
+    const double myrs = pivot_rsqrt(mydiag);
+#pragma unroll
+    for (int k = 0; k < kNB; ++k) {
+        const double rsk = __shfl_sync(0xffffffffu, myrs, k);
+        a[k] *= rsk;   // L_rk = a_rk / sqrt(d_k); k == r: sqrt(d_r)
+    }
+    if (lane < kNB) {
+#pragma unroll
+        for (int k = 0; k < kNB; ++k) {
+            Lw[r * kNB + k] = (k < r) ? a[k] * myrs : ((k == r) ? myrs : 0.0);
+            if (r < nb && k <= r) W[tri(j0 + r) + j0 + k] = a[k];
+        }
+    }
+    if (lane < nb) dinv[j0 + lane] = myrs;
+    return true;
+}
+// row i of the panel: x L11^T = W[i][j0 .. j0 + nb), column-oriented (one fma on the critical path per column)
+__device__ __forceinline__ void panel_row(double* W, int i, int j0, int nb, int t0, const double* Lw, double* Lp, int ldp,
+                                          double (&x)[kNB], bool store) {
+    double* wi = W + tri(i) + j0;
+#pragma unroll
+    for (int c = 0; c < kNB; ++c) x[c] = (c < nb) ? wi[c] * Lw[c * kNB + c] : 0.0;
+#pragma unroll
+    for (int k = 0; k < kNB - 1; ++k)
+#pragma unroll
+        for (int c = k + 1; c < kNB; ++c) x[c] = fma(-x[k], Lw[c * kNB + k], x[c]);
+    if (store) {
+#pragma unroll
+        for (int c = 0; c < kNB; ++c) {
+            if (c < nb) wi[c] = x[c];
+            Lp[c * ldp + (i - t0)] = x[c];   // columns beyond nb hold zeros
+        }
+    }
+}
+// wscr: Lw[2][64] | flag[2] (needs 2 * 64 + 1 doubles); panel: 8 * chol_ldp(R) + 4 doubles
 __device__ bool aug_cholesky(double* W, int P, int R, double* dinv, double* wscr, double* panel) {
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nthr = blockDim.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nthr = blockDim.x, nwarp = nthr >> 5;
 #ifdef AVB_UBENCH_PHASES
     long long tph = clock64();
 #endif
-    double* Lw = wscr + wid * (kNB * kNB);   // this warp's copy of L11 scaled by rows: L[c][k] / L[c][c], diagonal 1 / L[c][c]
-    // the current panel, column-major Lp[c][row - t0] (leading dimension ldp, 32-byte aligned): the trailing update
-    // reads four consecutive rows of a column with two 16-byte loads, conflict-free across a warp (the row-major
-    // matrix gives eight-way bank conflicts here: a 4-row tile step is a multiple of eight banks)
-    double* Lp = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(panel) + 31) & ~(uintptr_t)31);   // needs 8 * ldp + 4 doubles
-    const int ldp = (R + 3) & ~3;
-    for (int e = tid; e < kNB * ldp; e += nthr) Lp[e] = 0.0;
-    __syncthreads();
+    int* flag = reinterpret_cast<int*>(wscr + 2 * kNB * kNB);
+    double* Lp = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(panel) + 31) & ~(uintptr_t)31);
+    const int ldp = chol_ldp(R);
     const int r = lane & 7;
-    for (int j0 = 0; j0 < P; j0 += kNB) {
-        const int nb = min(kNB, P - j0);
-        // ---- A: diagonal block (rows beyond nb are identity rows) ----
+    for (int e = tid; e < kNB * ldp; e += nthr) Lp[e] = 0.0;
+    if (wid == 0) {
+        const int nb0 = min(kNB, P);
         double a[kNB];
 #pragma unroll
-        for (int c = 0; c < kNB; ++c)
-            a[c] = (r < nb && c <= r) ? W[tri(j0 + r) + j0 + c] : ((c == r) ? 1.0 : 0.0);
-        bool ok = true;
-        double myinv = 1.0;
-#pragma unroll
-        for (int k = 0; k < kNB; ++k) {
-            const double d = __shfl_sync(0xffffffffu, a[k], k);
-            if (!(d > 0.0) || !isfinite(d)) ok = false;
-            const double inv = pivot_rsqrt(d);
-            const double lk = (r == k) ? d * inv : a[k] * inv;
-            a[k] = lk;
-            if (r == k) myinv = inv;
-#pragma unroll
-            for (int c = k + 1; c < kNB; ++c) {
-                const double lc = __shfl_sync(0xffffffffu, lk, c);
-                a[c] -= lk * lc;
-            }
-        }
-        if (!ok) return false;   // every warp factors the same block: uniform over the CTA
-        CHOL_T(0);
-        if (lane < kNB) {
-#pragma unroll
-            for (int c = 0; c < kNB; ++c) Lw[lane * kNB + c] = (c < lane) ? a[c] * myinv : ((c == lane) ? myinv : 0.0);
-            if (wid == 0 && lane < nb) dinv[j0 + lane] = myinv;
-        }
-        __syncwarp();
-        // ---- B: rows below the block, x L11^T = W[i][j0 .. j0+nb), column-oriented: one fma on the critical path
-        //      per column (x_c = w_c / L_cc - sum_k x_k L_ck / L_cc) ----
-        const int t0 = j0 + nb;
-        for (int i = t0 + tid; i < R; i += nthr) {
-            double* wi = W + tri(i) + j0;
+        for (int c = 0; c < kNB; ++c) a[c] = (r < nb0 && c <= r) ? W[tri(r) + c] : ((c == r) ? 1.0 : 0.0);
+        const bool ok = diag_factor(a, W, 0, nb0, wscr, dinv, lane);
+        if (lane == 0) flag[0] = ok ? 1 : 0;
+    }
+    __syncthreads();
+    CHOL_T(0);
+    int pb = 0;
+    for (int j0 = 0; j0 < P; j0 += kNB, pb ^= 1) {
+        if (!flag[pb]) return false;   // written before the barrier every thread has just passed: uniform
+        const int nb = min(kNB, P - j0), t0 = j0 + nb;
+        const double* Lw = wscr + pb * (kNB * kNB);
+        const int mrow = R - t0, mcol = P - t0;
+        if (wid == 0) {
             double x[kNB];
+            const int i = t0 + r;
+            const bool have = i < R;
+            panel_row(W, min(i, R - 1), j0, nb, t0, Lw, Lp, ldp, x, have && lane < kNB);
+            if (!have) {
 #pragma unroll
-            for (int c = 0; c < kNB; ++c) x[c] = (c < nb) ? wi[c] * Lw[c * kNB + c] : 0.0;
+                for (int c = 0; c < kNB; ++c) x[c] = 0.0;
+            }
+            __syncwarp();
+            asm volatile("bar.arrive 1, %0;" ::"r"(nthr) : "memory");   // the panel rows of this warp are in Lp
+            if (mcol > 0) {
+                // rows t0 .. t0 + 7 x columns t0 .. t0 + nbn - 1: the next diagonal block and (at the end of the matrix) the
+                // right-hand-side rows that share its 8-row tile
+                const int nbn = min(kNB, mcol);
+                double a[kNB];
 #pragma unroll
-            for (int k = 0; k < kNB - 1; ++k)
+                for (int c = 0; c < kNB; ++c) a[c] = (have && c < nbn && c <= r) ? W[tri(i) + t0 + c] : 0.0;
 #pragma unroll
-                for (int c = k + 1; c < kNB; ++c) x[c] = fma(-x[k], Lw[c * kNB + k], x[c]);
+                for (int k = 0; k < kNB; ++k) {
+                    const double4 lo = *reinterpret_cast<const double4*>(Lp + k * ldp), hi = *reinterpret_cast<const double4*>(Lp + k * ldp + 4);
+                    const double xc[kNB] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-            for (int c = 0; c < kNB; ++c) {
-                if (c < nb) wi[c] = x[c];
-                Lp[c * ldp + (i - t0)] = x[c];
+                    for (int c = 0; c < kNB; ++c) a[c] = fma(-x[k], xc[c], a[c]);
+                }
+                if (r >= nbn) {   // not a row of the diagonal block: store, and present an identity row to the factorisation
+#pragma unroll
+                    for (int c = 0; c < kNB; ++c) {
+                        if (have && lane < kNB && c < nbn) W[tri(i) + t0 + c] = a[c];
+                        a[c] = (c == r) ? 1.0 : 0.0;
+                    }
+                }
+                const bool ok = diag_factor(a, W, t0, nbn, wscr + (pb ^ 1) * (kNB * kNB), dinv, lane);
+                if (lane == 0) flag[pb ^ 1] = ok ? 1 : 0;
+            } else if (lane == 0) {
+                flag[pb ^ 1] = 1;
+            }
+        } else {
+            for (int i = t0 + kNB + (tid - 32); i < R; i += nthr - 32) {
+                double x[kNB];
+                panel_row(W, i, j0, nb, t0, Lw, Lp, ldp, x, true);
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+            if (mcol > 0) {
+                // S[i][k] -= sum_c X[i][c] X[k][c] on 8 x 8 tiles of the lower triangle, row-block order (row block ti holds
+                // min(ti + 1, Tc) tiles); tile 0 is warp 0's.  The walk is incremental: no division, no square root.
+                const int Tb = (mrow + 7) >> 3, Tc = (mcol + 7) >> 3;
+                const int ntri = Tc * (Tc + 1) / 2, ntile = ntri + (Tb - Tc) * Tc;
+                const int g = lane >> 2, q = lane & 3, step = nwarp - 1;
+                auto advance = [&](int& ti, int& tk, int n) {
+                    tk += n;
+                    for (int len = min(ti + 1, Tc); tk >= len; len = min(ti + 1, Tc)) {
+                        tk -= len;
+                        ++ti;
+                    }
+                };
+                int ti0 = 0, tk0 = 0;
+                advance(ti0, tk0, wid);
+                for (int t = wid; t < ntile; t += 2 * step) {
+                    int ti1 = ti0, tk1 = tk0;
+                    const bool two = t + step < ntile;
+                    if (two) advance(ti1, tk1, step);
+                    const double a00 = -Lp[q * ldp + 8 * ti0 + g], a01 = -Lp[(4 + q) * ldp + 8 * ti0 + g];
+                    const double b00 = Lp[q * ldp + 8 * tk0 + g], b01 = Lp[(4 + q) * ldp + 8 * tk0 + g];
+                    const double a10 = -Lp[q * ldp + 8 * ti1 + g], a11 = -Lp[(4 + q) * ldp + 8 * ti1 + g];
+                    const double b10 = Lp[q * ldp + 8 * tk1 + g], b11 = Lp[(4 + q) * ldp + 8 * tk1 + g];
+                    const int i0 = t0 + 8 * ti0 + g, k0 = t0 + 8 * tk0 + 2 * q;
+                    const int i1 = t0 + 8 * ti1 + g, k1 = t0 + 8 * tk1 + 2 * q;
+                    const bool v00 = i0 < R && k0 < P && k0 <= i0, v01 = i0 < R && k0 + 1 < P && k0 + 1 <= i0;
+                    const bool v10 = two && i1 < R && k1 < P && k1 <= i1, v11 = two && i1 < R && k1 + 1 < P && k1 + 1 <= i1;
+                    double* w0 = W + tri(min(i0, R - 1)) + k0;
+                    double* w1 = W + tri(min(i1, R - 1)) + k1;
+                    double c00 = v00 ? w0[0] : 0.0, c01 = v01 ? w0[1] : 0.0, c10 = v10 ? w1[0] : 0.0, c11 = v11 ? w1[1] : 0.0;
+                    double e00 = 0.0, e01 = 0.0, e10 = 0.0, e11 = 0.0;
+                    dmma884(c00, c01, a00, b00);
+                    dmma884(e00, e01, a01, b01);
+                    dmma884(c10, c11, a10, b10);
+                    dmma884(e10, e11, a11, b11);
+                    if (v00) w0[0] = c00 + e00;
+                    if (v01) w0[1] = c01 + e01;
+                    if (v10) w1[0] = c10 + e10;
+                    if (v11) w1[1] = c11 + e11;
+                    ti0 = ti1;
+                    tk0 = tk1;
+                    if (t + 2 * step < ntile) advance(ti0, tk0, step);
+                }
             }
         }
         __syncthreads();
         CHOL_T(1);
-        // ---- C: trailing update W[i][k] -= sum_c L[i][c] L[k][c] on 4x4 tiles of the lower triangle ----
-        if (wid == 0 && lane < nb) {   // L11 itself (nobody reads the diagonal block any more)
-#pragma unroll
-            for (int c = 0; c < kNB; ++c)
-                if (c <= lane) W[tri(j0 + lane) + j0 + c] = a[c];
-        }
-        const int mrow = R - t0, mcol = P - t0;
-        if (mcol > 0) {
-            const int Tc = (mcol + 3) >> 2, Tr = (mrow + 3) >> 2;
-            const int ntri = Tc * (Tc + 1) / 2, ntile = ntri + (Tr - Tc) * Tc;
-            for (int t = tid; t < ntile; t += nthr) {
-                int ti, tk;
-                if (t < ntri) {
-                    ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
-                    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-                    while (ti * (ti + 1) / 2 > t) --ti;
-                    tk = t - ti * (ti + 1) / 2;
-                } else {
-                    ti = Tc + (t - ntri) / Tc;
-                    tk = (t - ntri) % Tc;
-                }
-                const int i0 = t0 + 4 * ti, k0 = t0 + 4 * tk;
-                double acc[4][4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) acc[q][u] = 0.0;
-#pragma unroll
-                for (int c = 0; c < kNB; ++c) {   // columns beyond nb hold zeros
-                    const double2* pa = reinterpret_cast<const double2*>(Lp + c * ldp + 4 * ti);
-                    const double2* pb = reinterpret_cast<const double2*>(Lp + c * ldp + 4 * tk);
-                    const double2 a01 = pa[0], a23 = pa[1], b01 = pb[0], b23 = pb[1];
-                    const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) acc[q][u] = fma(av[q], bv[u], acc[q][u]);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = i0 + q, k = k0 + u;
-                        if (i < R && k < P && k <= i) W[tri(i) + k] -= acc[q][u];
-                    }
-            }
-        }
-        __syncthreads();
-        CHOL_T(2);
     }
-    return true;
+    return flag[pb] != 0;
 }
 
 // x = L^-T y with one warp, in place in shared memory (x and y may alias).  Column-oriented: step i fixes x_i and
 // subtracts L[i][e] x_i from the entries e < i.  Deliberately a tight rolled loop: the solve is executed once per
-// task from a cold instruction cache, where every 128 B of straight-line code costs an L2 round trip.
+// task from a cold instruction cache, and a single warp pays for every instruction it issues (a variant that keeps the
+// unknowns in registers and takes x_i by shuffle issues 75 instructions per step and measured 19.9 k cycles against
+// 13.5 k for this one, tools/ubench/chol_ubench.cu).
 __device__ void warp_back_solve(const double* L, const double* dinv, int P, const double* y, double* x) {
     const int lane = threadIdx.x & 31;
 #pragma unroll 1
@@ -1371,53 +1447,138 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
     for (int i = tid; i < 9 * J; i += kSolveThreads) Gs9[i] = ldg2(a.tab + (size_t)f * a.tabD + i);
     __syncthreads();
     phase_lap(a.q, 4, tp);
-    // ---- reduce the chunk partials, group by group (chunks of a group share one layout), chunks in order ----
+    // ---- two independent latency-bound jobs run side by side on the two halves of the CTA (named barriers 2 and 3):
+    //      threads 0..127 reduce the chunk partials, threads 128..255 evaluate the pose prior at the trial point ----
     const bool last = st.last != 0;   // cost-only evaluation: it decides the final accept / reject, no step follows
+    const double sbp = st.sbp, sbs = st.sbs;
+    const bool do_prior = sbp > 0.0 && M.gmmC > 0;
+    const int nred = do_prior ? kSolveThreads / 2 : kSolveThreads;
+    if (tid < nred) {
+        // reduce the chunk partials, group by group (chunks of a group share one layout), chunks in order
 #pragma unroll 1
-    for (int g = 0; g < (last ? 0 : Pt.numGroups); ++g) {
-        const int2 run = a.gruns[(size_t)f * kMaxGroups + g];
-        if (run.y <= 0) continue;   // uniform
-        const int nj = Pt.gnj[g], Lg = group_L(nj, K), nH = tri_count(Lg);
-        const int nE = nH + (a.tensor ? 0 : Lg);   // tensor path: the gradient is assembled from the moment accumulators below
-        const int* gj = Pt.gjoints + g * kMaxJ;
-        const double* part = a.part + ((size_t)f * a.maxc + run.x) * a.pstride;
-        constexpr int kB = 8;   // independent loads in flight per thread
+        for (int g = 0; g < (last ? 0 : Pt.numGroups); ++g) {
+            const int2 run = a.gruns[(size_t)f * kMaxGroups + g];
+            if (run.y <= 0) continue;   // uniform
+            const int nj = Pt.gnj[g], Lg = group_L(nj, K), nH = tri_count(Lg);
+            const int nE = nH + (a.tensor ? 0 : Lg);   // tensor path: the gradient is assembled from the moment accumulators below
+            const int* dest = Pt.gdest + Pt.gdoff[g];  // static scatter table: entry -> packed tangent index (gradient: nTri + column)
+            const double* part = a.part + ((size_t)f * a.maxc + run.x) * a.pstride;
+            constexpr int kB = 8;   // independent loads in flight per thread
 #pragma unroll 1
-        for (int i0 = tid; i0 < nE; i0 += kSolveThreads * kB) {
-            double val[kB];
-#pragma unroll
-            for (int u = 0; u < kB; ++u) {
-                const int idx = i0 + u * kSolveThreads;
-                val[u] = (idx < nE) ? ldg2(part + idx) : 0.0;
-            }
-#pragma unroll 1
-            for (int cc = 1; cc < run.y; ++cc) {   // further chunks of the group, in chunk order
+            for (int i0 = tid; i0 < nE; i0 += nred * kB) {
+                double val[kB];
+                int dst[kB];
 #pragma unroll
                 for (int u = 0; u < kB; ++u) {
-                    const int idx = i0 + u * kSolveThreads;
-                    if (idx < nE) val[u] += ldg2(part + (size_t)cc * a.pstride + idx);
+                    const int idx = i0 + u * nred;
+                    val[u] = (idx < nE) ? ldg2(part + idx) : 0.0;
+                    dst[u] = (idx < nE) ? __ldg(dest + idx) : -1;
                 }
-            }
+#pragma unroll 1
+                for (int cc = 1; cc < run.y; ++cc) {   // further chunks of the group, in chunk order
 #pragma unroll
-            for (int u = 0; u < kB; ++u) {
-                const int idx = i0 + u * kSolveThreads;
-                int ra = idx - nH, rb = -1;
-                bool ok = idx < nE;
-                if (idx < nH) ok = tri_decode(idx, Lg, ra, rb);
-                if (ok) {
-                    // group column -> tangent column: [ p | 3 per group joint | shape ]
-                    const int ca = ra < 3 ? ra : (ra < 3 + 3 * nj ? 3 + 3 * gj[(ra - 3) / 3] + (ra - 3) % 3 : ra + 3 * (J - nj));
-                    if (rb < 0) {
-                        S.gs[ca] += val[u];
-                    } else {
-                        const int cb = rb < 3 ? rb : (rb < 3 + 3 * nj ? 3 + 3 * gj[(rb - 3) / 3] + (rb - 3) % 3 : rb + 3 * (J - nj));
-                        S.Hs[ca >= cb ? tri(ca) + cb : tri(cb) + ca] += val[u];
+                    for (int u = 0; u < kB; ++u) {
+                        const int idx = i0 + u * nred;
+                        if (idx < nE) val[u] += ldg2(part + (size_t)cc * a.pstride + idx);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kB; ++u) {
+                    if (dst[u] >= 0) {
+                        double* o = dst[u] < nTri ? S.Hs + dst[u] : S.gs + (dst[u] - nTri);
+                        *o += val[u];
                     }
                 }
             }
+            asm volatile("bar.sync 2, %0;" ::"r"(nred) : "memory");
         }
-        __syncthreads();
+    } else {
+        // pose prior (AvatarOptimizer.cpp:661-692, GaussianMixture.cpp:95-114): component of least
+        // p_c = 1/2 (x - mu_c)^T Sigma_c^-1 (x - mu_c) - consts_log[c], its value and y = Sigma^-1 (x - mu)
+        const int t = tid - nred, nt = kSolveThreads - nred;
+        const int D = M.gmmD, C = M.gmmC, Dp = (D + 8) & ~7;   // row stride: zero padded to 8, slot D of ycomp holds p_c
+#pragma unroll 1
+        for (int j = 1 + t; j < J; j += nt) {  // Eigen AngleAxisd(Quaterniond)
+            const double* q = S.xt + 3 + 4 * j;
+            double nn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+            double s = 0.0;
+            if (nn != 0.0) {
+                const double ang = 2.0 * atan2(nn, fabs(q[3]));
+                if (q[3] < 0) nn = -nn;
+                s = ang / nn;
+            }
+            S.aa[3 * (j - 1)] = q[0] * s;
+            S.aa[3 * (j - 1) + 1] = q[1] * s;
+            S.aa[3 * (j - 1) + 2] = q[2] * s;
+        }
+        asm volatile("bar.sync 3, %0;" ::"r"(nt) : "memory");
+#pragma unroll 1
+        for (int i = t; i < C * Dp; i += nt) {
+            const int cc = i / Dp, k = i - cc * Dp;
+            S.dcomp[i] = (k < D) ? S.aa[k] - M.gmm_mean[cc * D + k] : 0.0;
+        }
+        asm volatile("bar.sync 3, %0;" ::"r"(nt) : "memory");
+#pragma unroll 1
+        for (int i = t; i < C * D; i += 2 * nt) {  // y_c = Sigma_c^-1 (x - mu_c), two rows per thread at a time
+            // the precision matrices are symmetric (symmetrised at load): walk column r so that consecutive
+            // threads read consecutive addresses; sixteen loads in flight per thread (the walk is L2-latency bound)
+            const int i2 = i + nt;
+            const bool two = i2 < C * D;
+            const int ca = i / D, ra = i - ca * D;
+            const int cb = two ? i2 / D : ca, rb = two ? i2 - cb * D : ra;
+            const double* Pa = M.gmm_prec + (size_t)ca * D * D + ra;
+            const double* Pb = M.gmm_prec + (size_t)cb * D * D + rb;
+            const double* da = S.dcomp + ca * Dp;
+            const double* db = S.dcomp + cb * Dp;
+            double sa0 = 0, sa1 = 0, sb0 = 0, sb1 = 0;
+#pragma unroll 1
+            for (int k = 0; k < D; k += 8) {
+                double ta[8], tb[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    ta[u] = (k + u < D) ? __ldg(Pa + (size_t)(k + u) * D) : 0.0;
+                    tb[u] = (k + u < D) ? __ldg(Pb + (size_t)(k + u) * D) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) {
+                    sa0 = fma(ta[u], da[k + u], sa0);          // dcomp rows are zero padded to a multiple of 8
+                    sa1 = fma(ta[u + 1], da[k + u + 1], sa1);
+                    sb0 = fma(tb[u], db[k + u], sb0);
+                    sb1 = fma(tb[u + 1], db[k + u + 1], sb1);
+                }
+            }
+            S.ycomp[ca * Dp + ra] = sa0 + sa1;
+            if (two) S.ycomp[cb * Dp + rb] = sb0 + sb1;
+        }
+        asm volatile("bar.sync 3, %0;" ::"r"(nt) : "memory");
+        // p_c, one warp per component; first minimum wins (strict <)
+#pragma unroll 1
+        for (int cc = t >> 5; cc < C; cc += nt >> 5) {
+            double sp = 0;
+#pragma unroll 1
+            for (int k = t & 31; k < D; k += 32) sp += S.dcomp[cc * Dp + k] * S.ycomp[cc * Dp + k];
+            sp = 0.5 * warp_sum(sp);
+            if ((t & 31) == 0) S.ycomp[cc * Dp + D] = sp;
+        }
+        asm volatile("bar.sync 3, %0;" ::"r"(nt) : "memory");
+        if (t == 0) {
+            double bestp = 1.79769313486231570e308, bestsq = 0;
+            int best = 0;
+#pragma unroll 1
+            for (int cc = 0; cc < C; ++cc) {
+                const double sq = S.ycomp[cc * Dp + D];
+                const double pc = sq - M.gmm_clog[cc];
+                if (pc < bestp) {
+                    bestp = pc;
+                    bestsq = sq;
+                    best = cc;
+                }
+            }
+            S.iscr[0] = best;
+            S.scr[40] = 0.5 * sbp * sbp * (bestsq - M.gmm_clog[best]);
+        }
     }
+    __syncthreads();
     double csum = 0.0;   // cost partials in record-block order, eight loads in flight
     {
         const int nb = (a.tensor || a.fused) ? st.nchunks : (st.nslots + 255) >> 8;   // one cost partial per fused task / per record block
@@ -1559,81 +1720,10 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
     }
     __syncthreads();
     phase_lap(a.q, 6, tp);
-    // ---- pose prior (AvatarOptimizer.cpp:661-692, GaussianMixture.cpp:95-114) ----
-    const double sbp = st.sbp, sbs = st.sbs;
+    // ---- pose prior, second half: add the winning component (evaluated above, next to the partial reduction) ----
     const double* w = S.xt + 3 + 4 * J;
-    if (sbp > 0.0 && M.gmmC > 0) {
-        const int D = M.gmmD, C = M.gmmC, Dp = (D + 8) & ~7;   // row stride: zero padded to 8, slot D of ycomp holds p_c
-#pragma unroll 1
-        for (int j = 1 + tid; j < J; j += kSolveThreads) {  // Eigen AngleAxisd(Quaterniond)
-            const double* q = S.xt + 3 + 4 * j;
-            double nn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
-            double s = 0.0;
-            if (nn != 0.0) {
-                const double ang = 2.0 * atan2(nn, fabs(q[3]));
-                if (q[3] < 0) nn = -nn;
-                s = ang / nn;
-            }
-            S.aa[3 * (j - 1)] = q[0] * s;
-            S.aa[3 * (j - 1) + 1] = q[1] * s;
-            S.aa[3 * (j - 1) + 2] = q[2] * s;
-        }
-        __syncthreads();
-#pragma unroll 1
-        for (int i = tid; i < C * Dp; i += kSolveThreads) {
-            const int cc = i / Dp, k = i - cc * Dp;
-            S.dcomp[i] = (k < D) ? S.aa[k] - M.gmm_mean[cc * D + k] : 0.0;
-        }
-        __syncthreads();
-#pragma unroll 1
-        for (int i = tid; i < C * D; i += kSolveThreads) {  // y_c = Sigma_c^-1 (x - mu_c)
-            // the precision matrices are symmetric (symmetrised at load): walk column r so that consecutive
-            // threads read consecutive addresses; eight loads in flight per thread (the walk is L2-latency bound)
-            const int cc = i / D, r = i - cc * D;
-            const double* Pm = M.gmm_prec + (size_t)cc * D * D + r;
-            const double* dc = S.dcomp + cc * Dp;
-            double s0 = 0, s1 = 0;
-#pragma unroll 1
-            for (int k = 0; k < D; k += 8) {
-                double t[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) t[u] = (k + u < D) ? __ldg(Pm + (size_t)(k + u) * D) : 0.0;
-#pragma unroll
-                for (int u = 0; u < 8; u += 2) {
-                    s0 = fma(t[u], dc[k + u], s0);          // dcomp rows are zero padded to a multiple of 8
-                    s1 = fma(t[u + 1], dc[k + u + 1], s1);
-                }
-            }
-            S.ycomp[cc * Dp + r] = s0 + s1;
-        }
-        __syncthreads();
-        // p_c = 1/2 (x-mu)^T Sigma^-1 (x-mu) - consts_log[c], one warp per component; first minimum wins (strict <)
-#pragma unroll 1
-        for (int cc = tid >> 5; cc < C; cc += kSolveThreads >> 5) {
-            double sp = 0;
-#pragma unroll 1
-            for (int k = tid & 31; k < D; k += 32) sp += S.dcomp[cc * Dp + k] * S.ycomp[cc * Dp + k];
-            sp = 0.5 * warp_sum(sp);
-            if ((tid & 31) == 0) S.ycomp[cc * Dp + D] = sp;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            double bestp = 1.79769313486231570e308, bestsq = 0;
-            int best = 0;
-#pragma unroll 1
-            for (int cc = 0; cc < C; ++cc) {
-                const double sq = S.ycomp[cc * Dp + D];
-                const double pc = sq - M.gmm_clog[cc];
-                if (pc < bestp) {
-                    bestp = pc;
-                    bestsq = sq;
-                    best = cc;
-                }
-            }
-            S.iscr[0] = best;
-            S.scr[40] = 0.5 * sbp * sbp * (bestsq - M.gmm_clog[best]);
-        }
-        __syncthreads();
+    if (do_prior) {
+        const int D = M.gmmD, Dp = (D + 8) & ~7;
         const int best = S.iscr[0];
         const double hb = 0.5 * sbp * sbp;
         if (!last) {   // H += hb Sigma_best^-1, stored zero-padded to the P x P tangent layout: one flat pass, no index maths
