@@ -666,6 +666,16 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
     TRY(dev_put(ft, &dm.anc_mask, m->anc_mask));
     TRY(dev_put(ft, &dm.parent, m->parent));
     TRY(dev_put(ft, &dm.depth, m->depth));
+    {   // joints level by level (build_tables sweeps the kinematic tree one level per barrier)
+        std::vector<int> lvl_start(m->max_depth + 2, 0), lvl_joint;
+        for (int d = 0; d <= m->max_depth; ++d) {
+            for (int j = 0; j < m->J; ++j)
+                if (m->depth[j] == d) lvl_joint.push_back(j);
+            lvl_start[d + 1] = (int)lvl_joint.size();
+        }
+        TRY(dev_put(ft, &dm.lvl_start, lvl_start));
+        TRY(dev_put(ft, &dm.lvl_joint, lvl_joint));
+    }
     TRY(dev_put(ft, &dm.jbase, m->jbase));
     TRY(dev_put(ft, &dm.jreg, m->jreg));
     TRY(dev_put(ft, &dm.Sp, m->Sp));

@@ -27,6 +27,8 @@ struct DevModel {
     const uint32_t* anc_mask;  // [J]         bit a set <=> a is j or an ancestor of j
     const int* parent;         // [J]
     const int* depth;          // [J]
+    const int* lvl_start;      // [max_depth+2] into lvl_joint
+    const int* lvl_joint;      // [J]         joints sorted by (depth, id)
     const double* jbase;       // [3J]        jointShapeRegBase
     const double* jreg;        // [3J][K]     jointShapeReg  (S_j = rows 3j..3j+2)
     const double* Sp;          // [J][3][K]   S_j - S_parent(j)   (AvatarOptimizer.cpp:240-243)

@@ -45,31 +45,39 @@ __device__ inline void build_tables(const DevModel& M, const double* xs, Tables 
 #pragma unroll 1
     for (int j = tid; j < J; j += nt) quat_to_rot(xs + 3 + 4 * j, T.Rq + 9 * j);
     __syncthreads();
+    // one sweep over the kinematic tree, level by level (joints of a level listed in M.lvl_joint): 64 threads per joint,
+    // thread e < 9: entry of G_j = G_parent R_j, 9 <= e < 12: pos_j, 12 <= e < 12 + 3K: row of H[j] (needs G_parent only);
+    // one CTA barrier per level instead of two sweeps of max_depth barriers each (3 K <= 48: AVB_MAX_SHAPE_KEYS = 16)
+    const int per = 3 * K, nitems = 12 + (with_shape ? per : 0);
 #pragma unroll 1
     for (int d = 0; d <= M.max_depth; ++d) {
+        const int l0 = M.lvl_start[d], l1 = M.lvl_start[d + 1];
 #pragma unroll 1
-        for (int j = tid; j < J; j += nt) {
-            if (M.depth[j] != d) continue;
-            const int pa = M.parent[j];
-            double* Gj = T.G + 9 * j;
+        for (int jj = l0 + (tid >> 6); jj < l1; jj += nt >> 6) {
+            const int e = tid & 63;
+            if (e >= nitems) continue;
+            const int j = M.lvl_joint[jj], pa = M.parent[j];
             const double* R = T.Rq + 9 * j;
             if (pa < 0) {
-#pragma unroll 1
-                for (int e = 0; e < 9; ++e) Gj[e] = R[e];
-#pragma unroll 1
-                for (int c = 0; c < 3; ++c) T.pos[3 * j + c] = xs[c];
+                if (e < 9) T.G[9 * j + e] = R[e];
+                else if (e < 12) T.pos[3 * j + (e - 9)] = xs[e - 9];
+                else T.Hj[j * per + (e - 12)] = 0.0;
             } else {
                 const double* Gp = T.G + 9 * pa;
-#pragma unroll 1
-                for (int r = 0; r < 3; ++r)
-#pragma unroll 1
-                    for (int c = 0; c < 3; ++c)
-                        Gj[3 * r + c] = Gp[3 * r] * R[c] + Gp[3 * r + 1] * R[3 + c] + Gp[3 * r + 2] * R[6 + c];
-                const double v0 = T.Jr[3 * j] - T.Jr[3 * pa], v1 = T.Jr[3 * j + 1] - T.Jr[3 * pa + 1],
-                             v2 = T.Jr[3 * j + 2] - T.Jr[3 * pa + 2];
-#pragma unroll 1
-                for (int r = 0; r < 3; ++r)
+                if (e < 9) {
+                    const int r = e / 3, c = e - 3 * r;
+                    T.G[9 * j + e] = Gp[3 * r] * R[c] + Gp[3 * r + 1] * R[3 + c] + Gp[3 * r + 2] * R[6 + c];
+                } else if (e < 12) {
+                    const int r = e - 9;
+                    const double v0 = T.Jr[3 * j] - T.Jr[3 * pa], v1 = T.Jr[3 * j + 1] - T.Jr[3 * pa + 1],
+                                 v2 = T.Jr[3 * j + 2] - T.Jr[3 * pa + 2];
                     T.pos[3 * j + r] = Gp[3 * r] * v0 + Gp[3 * r + 1] * v1 + Gp[3 * r + 2] * v2 + T.pos[3 * pa + r];
+                } else {
+                    const int i = e - 12, r = i / K, m = i - r * K;
+                    const double* sp = M.Sp + (size_t)j * per;
+                    T.Hj[j * per + i] = Gp[3 * r] * sp[m] + Gp[3 * r + 1] * sp[K + m] + Gp[3 * r + 2] * sp[2 * K + m] +
+                                        T.Hj[pa * per + r * K + m];
+                }
             }
         }
         __syncthreads();
@@ -83,25 +91,6 @@ __device__ inline void build_tables(const DevModel& M, const double* xs, Tables 
                                (Gj[3 * r] * T.Jr[3 * j] + Gj[3 * r + 1] * T.Jr[3 * j + 1] + Gj[3 * r + 2] * T.Jr[3 * j + 2]);
     }
     if (with_shape) {
-        const int per = 3 * K;
-#pragma unroll 1
-        for (int i = tid; i < J * per; i += nt)
-            if (M.depth[i / per] == 0) T.Hj[i] = 0.0;
-        __syncthreads();
-#pragma unroll 1
-        for (int d = 1; d <= M.max_depth; ++d) {
-#pragma unroll 1
-            for (int i = tid; i < J * per; i += nt) {
-                const int j = i / per;
-                if (M.depth[j] != d) continue;
-                const int r = (i % per) / K, m = i % K, pa = M.parent[j];
-                const double* Gp = T.G + 9 * pa;
-                const double* sp = M.Sp + (size_t)j * per;
-                T.Hj[i] = Gp[3 * r] * sp[m] + Gp[3 * r + 1] * sp[K + m] + Gp[3 * r + 2] * sp[2 * K + m] +
-                          T.Hj[pa * per + r * K + m];
-            }
-            __syncthreads();
-        }
 #pragma unroll 1
         for (int i = tid; i < J * per; i += nt) {
             const int j = i / per, r = (i % per) / K, m = i % K;
