@@ -1147,7 +1147,9 @@ __host__ __device__ inline int solve_tb_doubles(int J, int K, int C) {
     // (The prior's dcomp | ycomp have their own scratch: the prior is evaluated next to the partial reduction.)
     const int P = 3 + 3 * J + K, D = 3 * (J - 1);
     int t = 9 * J + ((tc_gacc(J, K) + 1) & ~1) + 3 * J + 3 * J * K;
-    const int pnl = 8 * chol_ldp(P + 1) + 8;
+    int pnl = 8 * chol_ldp(P + 1) + 8;
+    const int ninv = kNBsq * ((P + 7) >> 3);   // block inverses of the back substitution
+    pnl = pnl > ninv ? pnl : ninv;
     (void)C; (void)D;
     return ((t > pnl ? t : pnl) + 1) & ~1;
 }
@@ -1393,27 +1395,67 @@ __device__ bool aug_cholesky(double* W, int P, int R, double* dinv, double* wscr
     return flag[pb] != 0;
 }
 
-// x = L^-T y with one warp, in place in shared memory (x and y may alias).  Column-oriented: step i fixes x_i and
-// subtracts L[i][e] x_i from the entries e < i.  Deliberately a tight rolled loop: the solve is executed once per
-// task from a cold instruction cache, and a single warp pays for every instruction it issues (a variant that keeps the
-// unknowns in registers and takes x_i by shuffle issues 75 instructions per step and measured 19.9 k cycles against
-// 13.5 k for this one, tools/ubench/chol_ubench.cu).
-__device__ void warp_back_solve(const double* L, const double* dinv, int P, const double* y, double* x) {
+// x = L^-T y, blocked by the 8 x 8 diagonal blocks of the factor (85 dependent steps become 11):
+//   block_inverses   every warp inverts diagonal blocks (lane c: column c of N = L_bb^-1 by forward substitution, 1 / L_rr from
+//                    dinv) and stores them transposed, NT[b][c][r] = N[r][c]   (needs 64 * ceil(P / 8) doubles; CTA-wide, the
+//                    caller synchronises)
+//   warp_back_solve  one warp, blocks last to first: x_b = N_b^T y_b (eight independent dot products, no chain), then
+//                    y_e -= sum_c L[j0 + c][e] x_{j0 + c} for the entries e < j0 (rows of L are contiguous in e).
+// In place in shared memory (x and y may alias).  Measured against the column-by-column loop: 10.5 -> 6.4 us per solve (a variant with the
+// update unrolled over four predicated entries per lane measured 11.4: a single warp pays for every instruction it issues).
+__device__ void block_inverses(const double* L, const double* dinv, int P, double* NT) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int c = lane & 7;
+#pragma unroll 1
+    for (int b = wid; b * kNB < P; b += nwarp) {
+        const int j0 = b * kNB, nb = min(kNB, P - j0);
+        double n[kNB];   // n[r] = N[r][c], r >= c
+#pragma unroll
+        for (int r = 0; r < kNB; ++r) {
+            double acc = 0.0;
+            const double* Lr = L + tri(j0 + min(r, nb - 1)) + j0;
+#pragma unroll
+            for (int m = 0; m < kNB; ++m)
+                if (m < r) acc = fma(Lr[m], (m >= c) ? n[m] : 0.0, acc);
+            const double di = dinv[j0 + min(r, nb - 1)];
+            n[r] = (r == c) ? di : ((r > c && r < nb) ? -acc * di : 0.0);
+        }
+        if (lane < kNB) {
+#pragma unroll
+            for (int r = 0; r < kNB; ++r) NT[b * (kNB * kNB) + c * kNB + r] = n[r];
+        }
+    }
+}
+__device__ void warp_back_solve(const double* L, const double* NT, int P, const double* y, double* x) {
     const int lane = threadIdx.x & 31;
 #pragma unroll 1
     for (int e = lane; e < P; e += 32) x[e] = y[e];
     __syncwarp();
 #pragma unroll 1
-    for (int i = P - 1; i >= 0; --i) {
-        const double* Li = L + tri(i);
-        const double l0 = (lane < i) ? Li[lane] : 0.0, l1 = (lane + 32 < i) ? Li[lane + 32] : 0.0;
-        const double xi = x[i] * dinv[i];
+    for (int b = (P - 1) / kNB; b >= 0; --b) {
+        const int j0 = b * kNB, nb = min(kNB, P - j0);
+        const int c = lane & 7;
+        const double* nt = NT + b * (kNB * kNB) + c * kNB;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < kNB; r += 2) {   // N[r][c] = 0 for r < c and for the rows beyond nb
+            s0 = fma(nt[r], (r < nb) ? x[j0 + r] : 0.0, s0);
+            s1 = fma(nt[r + 1], (r + 1 < nb) ? x[j0 + r + 1] : 0.0, s1);
+        }
+        const double xc = s0 + s1;
         __syncwarp();
-        if (lane < i) x[lane] = fma(-l0, xi, x[lane]);
-        if (lane + 32 < i) x[lane + 32] = fma(-l1, xi, x[lane + 32]);
+        if (lane < nb) x[j0 + lane] = xc;
+        double xb[kNB];
+#pragma unroll
+        for (int q = 0; q < kNB; ++q) xb[q] = __shfl_sync(0xffffffffu, xc, q);
 #pragma unroll 1
-        for (int e = lane + 64; e < i; e += 32) x[e] = fma(-Li[e], xi, x[e]);
-        if (lane == 0) x[i] = xi;
+        for (int e = lane; e < j0; e += 32) {
+            double acc = x[e];
+#pragma unroll
+            for (int q = 0; q < kNB; ++q)
+                if (q < nb) acc = fma(-L[tri(j0 + q) + e], xb[q], acc);
+            x[e] = acc;
+        }
         __syncwarp();
     }
 }
@@ -1857,7 +1899,9 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         bool ok = aug_cholesky(S.Hs, P, P + 1, S.glo, S.wscr, S.tb);
         phase_lap(a.q, 9, tp);
         if (ok) {
-            if (tid < 32) warp_back_solve(S.Hs, S.glo, P, S.Hs + nTri, S.delta);
+            block_inverses(S.Hs, S.glo, P, S.tb);   // (the panel of the factorisation is dead: its place takes the block inverses)
+            __syncthreads();
+            if (tid < 32) warp_back_solve(S.Hs, S.tb, P, S.Hs + nTri, S.delta);
             __syncthreads();
             // model_cost_change = -delta^T (g + 1/2 H delta) with (H + D) delta = -g  =>  1/2 delta^T (D delta - g)
             double part = 0;

@@ -19,6 +19,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--jtj", default="fp64")
     ap.add_argument("--frames", type=int, default=4)
+    ap.add_argument("--beta-pose", type=float, default=None, help="override beta_pose (0 switches the pose prior off)")
     args = ap.parse_args()
     from avatar_b200 import Fitter, default_options, _lib
     model, pr = bench.make_model()
@@ -31,6 +32,8 @@ def main():
     ft = Fitter(model, num_parts, part_map, 1, int(max(len(p) for p in pts)) + 64, 0)
     opt = default_options()
     opt.function_tolerance = 0.0
+    if args.beta_pose is not None:
+        opt.beta_pose = args.beta_pose
     opt.jtj_precision = {"fp64": _lib.JTJ_FP64, "tensor": _lib.JTJ_BF16_TENSOR}[args.jtj]
     out = {"jtj": args.jtj, "points": [len(p) for p in pts]}
     wall = []

@@ -24,7 +24,9 @@ __global__ void __launch_bounds__(256, 2) k_solve(const double* A, int P, long l
         long long t0 = clock64();
         bool ok = aug_cholesky(W, P, P + 1, dinv, wscr, panel);
         long long t1 = clock64();
-        if (threadIdx.x < 32) warp_back_solve(W, dinv, P, W + nTri, x);
+        block_inverses(W, dinv, P, panel);
+        __syncthreads();
+        if (threadIdx.x < 32) warp_back_solve(W, panel, P, W + nTri, x);
         __syncthreads();
         long long t2 = clock64();
         if (r == 0) { tc0 = t1 - t0; tb0 = t2 - t1; } else { tc += t1 - t0; tb += t2 - t1; }
