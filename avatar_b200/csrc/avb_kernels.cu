@@ -45,15 +45,29 @@ pose_visibility_kernel(DevModel M, DevParts Pt, PoseArgs a) {
 
     double* cloud = a.cloud + (size_t)f * 3 * V;
     const double* w = xs + 3 + 4 * J;
-#pragma unroll 2
     for (int v = tid; v < V; v += nt) {
         // shape blend (Avatar.cpp:26) then LBS with the assignedJoints weights (AvatarOptimizer.cpp:507-514)
         const float* sd = M.sdT + v;   // component-major: consecutive threads read consecutive addresses
         double v0[3];
-        for (int c = 0; c < 3; ++c) {
-            double s = 0;
-            for (int k = 0; k < K; ++k) s += (double)sd[(size_t)(c * K + k) * V] * w[k];
-            v0[c] = M.vt[3 * (size_t)v + c] + s;
+        if (K == 10) {   // the SMPL shape space: all thirty key-cloud loads of the vertex in flight (they are L2 hits: latency, not bytes)
+            float t[30];
+#pragma unroll
+            for (int i = 0; i < 30; ++i) t[i] = __ldg(sd + (size_t)i * V);
+            const double b0 = M.vt[3 * (size_t)v], b1 = M.vt[3 * (size_t)v + 1], b2 = M.vt[3 * (size_t)v + 2];
+            const double bb[3] = {b0, b1, b2};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                double s = 0;
+#pragma unroll
+                for (int k = 0; k < 10; ++k) s += (double)t[c * 10 + k] * w[k];   // same order as the generic loop
+                v0[c] = bb[c] + s;
+            }
+        } else {
+            for (int c = 0; c < 3; ++c) {
+                double s = 0;
+                for (int k = 0; k < K; ++k) s += (double)sd[(size_t)(c * K + k) * V] * w[k];
+                v0[c] = M.vt[3 * (size_t)v + c] + s;
+            }
         }
         double x0 = 0, x1 = 0, x2 = 0;
         const int n = M.sk_n[v];
