@@ -1487,6 +1487,16 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
     double* Gs9 = S.tb;   // global joint rotations of the trial point (the table scratch is free until the retraction)
 #pragma unroll 1
     for (int i = tid; i < 9 * J; i += kSolveThreads) Gs9[i] = ldg2(a.tab + (size_t)f * a.tabD + i);
+    // the frame's chunk runs and the static group tables: one round trip here instead of one per group in the reduction
+    int* s_run = S.iscr + 8;                 // [numGroups][4]: first chunk, #chunks, entries of a partial, offset into gdest
+    if (tid < Pt.numGroups) {
+        const int2 run = a.gruns[(size_t)f * kMaxGroups + tid];
+        const int Lg = group_L(Pt.gnj[tid], K);
+        s_run[4 * tid] = run.x;
+        s_run[4 * tid + 1] = run.y;
+        s_run[4 * tid + 2] = tri_count(Lg) + (a.tensor ? 0 : Lg);   // tensor path: the gradient comes from the moment accumulators
+        s_run[4 * tid + 3] = Pt.gdoff[tid];
+    }
     __syncthreads();
     phase_lap(a.q, 4, tp);
     // ---- two independent latency-bound jobs run side by side on the two halves of the CTA (named barriers 2 and 3):
@@ -1499,13 +1509,12 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         // reduce the chunk partials, group by group (chunks of a group share one layout), chunks in order
 #pragma unroll 1
         for (int g = 0; g < (last ? 0 : Pt.numGroups); ++g) {
-            const int2 run = a.gruns[(size_t)f * kMaxGroups + g];
+            const int2 run = make_int2(s_run[4 * g], s_run[4 * g + 1]);
             if (run.y <= 0) continue;   // uniform
-            const int nj = Pt.gnj[g], Lg = group_L(nj, K), nH = tri_count(Lg);
-            const int nE = nH + (a.tensor ? 0 : Lg);   // tensor path: the gradient is assembled from the moment accumulators below
-            const int* dest = Pt.gdest + Pt.gdoff[g];  // static scatter table: entry -> packed tangent index (gradient: nTri + column)
+            const int nE = s_run[4 * g + 2];
+            const int* dest = Pt.gdest + s_run[4 * g + 3];  // static scatter table: entry -> packed tangent index (gradient: nTri + column)
             const double* part = a.part + ((size_t)f * a.maxc + run.x) * a.pstride;
-            constexpr int kB = 8;   // independent loads in flight per thread
+            constexpr int kB = 8;   // entries per thread per pass (one pass covers a group of up to 9 joints on 128 threads)
 #pragma unroll 1
             for (int i0 = tid; i0 < nE; i0 += nred * kB) {
                 double val[kB];
@@ -1534,6 +1543,7 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
             }
             asm volatile("bar.sync 2, %0;" ::"r"(nred) : "memory");
         }
+        phase_lap(a.q, 5, tp);   // (thread 0 is on this side: 'reduce' is the reduction alone, the wait for the prior side counts as 'prior')
     } else {
         // pose prior (AvatarOptimizer.cpp:661-692, GaussianMixture.cpp:95-114): component of least
         // p_c = 1/2 (x - mu_c)^T Sigma_c^-1 (x - mu_c) - consts_log[c], its value and y = Sigma^-1 (x - mu)
@@ -1621,6 +1631,7 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         }
     }
     __syncthreads();
+    phase_lap(a.q, 7, tp);
     double csum = 0.0;   // cost partials in record-block order, eight loads in flight
     {
         const int nb = (a.tensor || a.fused) ? st.nchunks : (st.nslots + 255) >> 8;   // one cost partial per fused task / per record block
