@@ -145,7 +145,7 @@ struct avb_fitter {
     int maxc = 0, tabD = 0, max_nj = 0, chunk_verts = 192, chunk_verts_tc = 256;   // vertices per Gram chunk: fp64 path (3 CTAs/SM) / tensor path
     long long pstride = 0;
     // lm_flow_kernel work queue
-    unsigned long long* d_qslots = nullptr; unsigned int* d_qctrl = nullptr; int *d_rows_left = nullptr, *d_gram_left = nullptr;
+    unsigned long long* d_qslots = nullptr; unsigned int* d_qctrl = nullptr; int *d_rows_left = nullptr, *d_gram_left = nullptr; double* d_prior_out = nullptr; int prior_stride = 0; int prior_task_max = 32;
     unsigned long long* d_qprof = nullptr; unsigned int qcap = 0; bool use_flow = true;
     int flow_occ_default[2] = {3, 2};   // CTAs per SM of the flow kernel: [fp64 path, tensor path] (measured best)
     unsigned int* h_qctrl = nullptr;
@@ -839,6 +839,9 @@ int avb_fitter_create(const avb_model* m, const avb_fitter_config* cfg, avb_fitt
         TRY(dev_alloc(ft, &ft->d_qctrl, 8));
         TRY(dev_alloc(ft, &ft->d_rows_left, B));
         TRY(dev_alloc(ft, &ft->d_gram_left, B));
+        ft->prior_stride = ((std::max(m->gmmD, 1) + 8) & ~7) + 8;
+        TRY(dev_alloc(ft, &ft->d_prior_out, B * (size_t)ft->prior_stride));
+        if (const char* e = std::getenv("AVB_PRIOR_TASK")) ft->prior_task_max = std::atoi(e);   // largest batch that runs the prior as its own task (0: never)
         TRY(dev_alloc(ft, &ft->d_qprof, 16));
         CUDA_TRY_FT(cudaMemset(ft->d_qslots, 0xFF, (size_t)ft->qcap * 8));
         CUDA_TRY_FT(cudaMemset(ft->d_qctrl, 0, 32));
@@ -1448,6 +1451,10 @@ LmBuf lm_buf(avb_fitter* ft, double* dx, const avb_options* o) {
         a.q.rows_left = ft->d_rows_left;
         a.q.gram_left = ft->d_gram_left;
         a.q.cap_mask = ft->qcap - 1;
+        // small batches leave most SMs idle: the pose prior of a trial point runs as its own task next to the record / Gram tasks
+        a.prior_task = (ft->batch <= ft->prior_task_max && o->beta_pose > 0.0 && ft->model->gmmC > 0) ? 1 : 0;
+        a.prior_out = ft->d_prior_out;
+        a.prior_stride = ft->prior_stride;
     }
     a.q.prof = ft->profile ? ft->d_qprof : nullptr;   // per-phase CTA time (also with the staged kernels)
     return a;

@@ -157,6 +157,10 @@ struct LmBuf {
     FrameStats* stats;           // [batch]
     int tensor;                  // 1: fused record + Gram tasks on tcgen05 (lm_flow_kernel<true>); 0: fp64 DMMA path
     int fused;                   // fp64 path of lm_flow_kernel: 1 = one fused record + Gram task per chunk (no d_rec round trip)
+    int prior_task;              // lm_flow_kernel, small batches: the pose prior of a trial point is its own task, evaluated next to the
+                                 // record / Gram tasks on another SM (same arithmetic; the solve only adds the result)
+    double* prior_out;           // [batch][prior_stride]: prior cost | winning component | y = Sigma^-1 (x - mu) of that component
+    int prior_stride;
     FlowQueue q;
 };
 

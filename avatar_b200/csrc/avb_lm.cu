@@ -52,7 +52,7 @@ __device__ __forceinline__ LmState load_state(const LmState* p) {
 // ---------------------------------------------------------------------------------------------
 // work queue of lm_flow_kernel (tasks are pushed only when their inputs are complete, so no task ever waits)
 // ---------------------------------------------------------------------------------------------
-enum { kTaskRows = 0, kTaskGram = 1, kTaskFused = 2 };
+enum { kTaskRows = 0, kTaskGram = 1, kTaskFused = 2, kTaskPrior = 3 };
 __device__ __forceinline__ unsigned make_task(int type, int f, int idx) {
     return ((unsigned)type << 30) | ((unsigned)f << 12) | (unsigned)idx;
 }
@@ -94,6 +94,25 @@ __device__ void flow_leave(const FlowQueue& q) {
         q.ctrl[0] = *reinterpret_cast<volatile unsigned*>(&q.ctrl[1]);
         __threadfence();
     }
+}
+
+// one thread: the tasks that open an evaluation of frame f (its state and trial point are written and fenced).  The frame's
+// solve runs when gram_left[f] reaches zero: one count per Gram / fused task (cost-only evaluation of the two-task schedule:
+// one for "all record tasks done") plus one for the prior task, if the prior runs as a task.
+__device__ void flow_push_eval(const LmBuf& a, int f, int nslots, int nchunks, bool cost_only, bool want_prior) {
+    const int extra = want_prior ? 1 : 0;
+    if (a.tensor || a.fused) {
+        atomicExch(&a.q.gram_left[f], nchunks + extra);
+        __threadfence();
+        flow_push(a.q, kTaskFused, f, nchunks);
+    } else {
+        const int nrb = (nslots + 255) >> 8;
+        atomicExch(&a.q.rows_left[f], nrb);
+        atomicExch(&a.q.gram_left[f], (cost_only ? 1 : nchunks) + extra);
+        __threadfence();
+        flow_push(a.q, kTaskRows, f, nrb);
+    }
+    if (want_prior) flow_push(a.q, kTaskPrior, f, 1);
 }
 
 // avb_set_profiling: thread 0 adds the nanoseconds since *t_prev to phase counter `cls` (prof[4..15]: sub-phases)
@@ -229,18 +248,9 @@ lm_prep_kernel(DevModel M, DevParts Pt, LmBuf a) {
         fs.final_cost = 0;
         fs.status = a.range_flag[f] ? 4 : 0;
         if (a.q.slots && !st.done) {   // lm_flow_kernel: the frame's first tasks
-            if (a.tensor || a.fused) {  // fused record + Gram tasks, one per chunk
-                a.q.gram_left[f] = st.nchunks;
-                __threadfence();
-                atomicAdd(&a.q.ctrl[2], 1u);
-                flow_push(a.q, kTaskFused, f, st.nchunks);
-            } else {
-                const int nrb = (base + 255) >> 8;
-                a.q.rows_left[f] = nrb;
-                __threadfence();
-                atomicAdd(&a.q.ctrl[2], 1u);
-                flow_push(a.q, kTaskRows, f, nrb);
-            }
+            __threadfence();
+            atomicAdd(&a.q.ctrl[2], 1u);
+            flow_push_eval(a, f, base, st.nchunks, false, a.prior_task && st.sbp > 0.0);
         }
     }
 }
@@ -1460,6 +1470,123 @@ __device__ void warp_back_solve(const double* L, const double* NT, int P, const 
     }
 }
 
+// Pose prior at the trial point xt (AvatarOptimizer.cpp:661-692, GaussianMixture.cpp:95-114), by threads t = 0..nt-1 (whole
+// warps, named barrier 3): the component of least p_c = 1/2 (x - mu_c)^T Sigma_c^-1 (x - mu_c) - consts_log[c] (first minimum
+// wins), its cost 1/2 sbp^2 p_c -> *cost_out and y_c = Sigma_c^-1 (x - mu_c) of EVERY component -> ycomp (row stride (D + 8) & ~7).
+// The caller synchronises before it reads the results.
+__device__ void prior_eval(const DevModel& M, const double* xt, double sbp, int t, int nt, double* aa, double* dcomp, double* ycomp,
+                           int* best_out, double* cost_out) {
+    const int J = M.J;
+    // pose prior (AvatarOptimizer.cpp:661-692, GaussianMixture.cpp:95-114): component of least
+    // p_c = 1/2 (x - mu_c)^T Sigma_c^-1 (x - mu_c) - consts_log[c], its value and y = Sigma^-1 (x - mu)
+    const int D = M.gmmD, C = M.gmmC, Dp = (D + 8) & ~7;   // row stride: zero padded to 8, slot D of ycomp holds p_c
+#pragma unroll 1
+    for (int j = 1 + t; j < J; j += nt) {  // Eigen AngleAxisd(Quaterniond)
+        const double* q = xt + 3 + 4 * j;
+        double nn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+        double s = 0.0;
+        if (nn != 0.0) {
+            const double ang = 2.0 * atan2(nn, fabs(q[3]));
+            if (q[3] < 0) nn = -nn;
+            s = ang / nn;
+        }
+        aa[3 * (j - 1)] = q[0] * s;
+        aa[3 * (j - 1) + 1] = q[1] * s;
+        aa[3 * (j - 1) + 2] = q[2] * s;
+    }
+    asm volatile("bar.sync 3, %0;" ::"r"(nt) : "memory");
+#pragma unroll 1
+    for (int i = t; i < C * Dp; i += nt) {
+        const int cc = i / Dp, k = i - cc * Dp;
+        dcomp[i] = (k < D) ? aa[k] - M.gmm_mean[cc * D + k] : 0.0;
+    }
+    asm volatile("bar.sync 3, %0;" ::"r"(nt) : "memory");
+#pragma unroll 1
+    for (int i = t; i < C * D; i += 2 * nt) {  // y_c = Sigma_c^-1 (x - mu_c), two rows per thread at a time
+        // the precision matrices are symmetric (symmetrised at load): walk column r so that consecutive
+        // threads read consecutive addresses; sixteen loads in flight per thread (the walk is L2-latency bound)
+        const int i2 = i + nt;
+        const bool two = i2 < C * D;
+        const int ca = i / D, ra = i - ca * D;
+        const int cb = two ? i2 / D : ca, rb = two ? i2 - cb * D : ra;
+        const double* Pa = M.gmm_prec + (size_t)ca * D * D + ra;
+        const double* Pb = M.gmm_prec + (size_t)cb * D * D + rb;
+        const double* da = dcomp + ca * Dp;
+        const double* db = dcomp + cb * Dp;
+        double sa0 = 0, sa1 = 0, sb0 = 0, sb1 = 0;
+#pragma unroll 1
+        for (int k = 0; k < D; k += 8) {
+            double ta[8], tb[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                ta[u] = (k + u < D) ? __ldg(Pa + (size_t)(k + u) * D) : 0.0;
+                tb[u] = (k + u < D) ? __ldg(Pb + (size_t)(k + u) * D) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) {
+                sa0 = fma(ta[u], da[k + u], sa0);          // dcomp rows are zero padded to a multiple of 8
+                sa1 = fma(ta[u + 1], da[k + u + 1], sa1);
+                sb0 = fma(tb[u], db[k + u], sb0);
+                sb1 = fma(tb[u + 1], db[k + u + 1], sb1);
+            }
+        }
+        ycomp[ca * Dp + ra] = sa0 + sa1;
+        if (two) ycomp[cb * Dp + rb] = sb0 + sb1;
+    }
+    asm volatile("bar.sync 3, %0;" ::"r"(nt) : "memory");
+    // p_c, one warp per component; first minimum wins (strict <)
+#pragma unroll 1
+    for (int cc = t >> 5; cc < C; cc += nt >> 5) {
+        double sp = 0;
+#pragma unroll 1
+        for (int k = t & 31; k < D; k += 32) sp += dcomp[cc * Dp + k] * ycomp[cc * Dp + k];
+        sp = 0.5 * warp_sum(sp);
+        if ((t & 31) == 0) ycomp[cc * Dp + D] = sp;
+    }
+    asm volatile("bar.sync 3, %0;" ::"r"(nt) : "memory");
+    if (t == 0) {
+        double bestp = 1.79769313486231570e308, bestsq = 0;
+        int best = 0;
+#pragma unroll 1
+        for (int cc = 0; cc < C; ++cc) {
+            const double sq = ycomp[cc * Dp + D];
+            const double pc = sq - M.gmm_clog[cc];
+            if (pc < bestp) {
+                bestp = pc;
+                bestsq = sq;
+                best = cc;
+            }
+        }
+        *best_out = best;
+        *cost_out = 0.5 * sbp * sbp * (bestsq - M.gmm_clog[best]);
+    }
+}
+
+// the prior as a task of lm_flow_kernel (small batches): evaluate at the frame's trial point, leave cost | component | y in HBM
+__device__ void prior_body(const DevModel& M, const LmBuf& a, int f, unsigned char* smem_raw) {
+    const int tid = threadIdx.x, D = M.gmmD, C = M.gmmC, Dp = (D + 8) & ~7, nx = M.nx;
+    double* xt = reinterpret_cast<double*>(smem_raw);
+    double* aa = xt + ((nx + 1) & ~1);
+    double* dcomp = aa + ((D + 1) & ~1);
+    double* ycomp = dcomp + (size_t)C * Dp;
+    double* res = ycomp + (size_t)C * Dp;   // [0] cost, [1] component (as int)
+    for (int i = tid; i < nx; i += 256) xt[i] = ldg2(a.xt + (size_t)f * nx + i);
+    const double sbp = ldg2(&a.state[f].sbp);
+    __syncthreads();
+    prior_eval(M, xt, sbp, tid, 256, aa, dcomp, ycomp, reinterpret_cast<int*>(res + 1), res);
+    __syncthreads();
+    double* out = a.prior_out + (size_t)f * a.prior_stride;
+    const int best = *reinterpret_cast<int*>(res + 1);
+    if (tid == 0) {
+        out[0] = res[0];
+        out[1] = (double)best;
+    }
+    for (int r = tid; r < D; r += 256) out[2 + r] = ycomp[best * Dp + r];
+}
+__host__ __device__ inline size_t prior_task_smem(int nx, int C, int D) {
+    return (size_t)(((nx + 1) & ~1) + ((D + 1) & ~1) + 2 * (size_t)(C > 0 ? C : 1) * ((D + 8) & ~7) + 4) * 8;
+}
+
 // returns true when the frame has finished (uniform over the CTA)
 __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a, int f, unsigned char* smem_raw) {
     const int tid = threadIdx.x;
@@ -1504,7 +1631,18 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
     const bool last = st.last != 0;   // cost-only evaluation: it decides the final accept / reject, no step follows
     const double sbp = st.sbp, sbs = st.sbs;
     const bool do_prior = sbp > 0.0 && M.gmmC > 0;
-    const int nred = do_prior ? kSolveThreads / 2 : kSolveThreads;
+    const bool prior_ready = do_prior && a.prior_task;   // evaluated by a prior task of this evaluation (lm_flow_kernel, small batches)
+    const int nred = (do_prior && !prior_ready) ? kSolveThreads / 2 : kSolveThreads;
+    if (prior_ready) {
+        const double* po = a.prior_out + (size_t)f * a.prior_stride;
+        const int D = M.gmmD, Dp = (D + 8) & ~7, best = (int)ldg2(po + 1);
+        if (tid == 0) {
+            S.iscr[0] = best;
+            S.scr[40] = ldg2(po);
+        }
+#pragma unroll 1
+        for (int r = tid; r < D; r += kSolveThreads) S.ycomp[best * Dp + r] = ldg2(po + 2 + r);
+    }
     if (tid < nred) {
         // reduce the chunk partials, group by group (chunks of a group share one layout), chunks in order
 #pragma unroll 1
@@ -1545,90 +1683,7 @@ __device__ bool solve_body(const DevModel& M, const DevParts& Pt, const LmBuf& a
         }
         phase_lap(a.q, 5, tp);   // (thread 0 is on this side: 'reduce' is the reduction alone, the wait for the prior side counts as 'prior')
     } else {
-        // pose prior (AvatarOptimizer.cpp:661-692, GaussianMixture.cpp:95-114): component of least
-        // p_c = 1/2 (x - mu_c)^T Sigma_c^-1 (x - mu_c) - consts_log[c], its value and y = Sigma^-1 (x - mu)
-        const int t = tid - nred, nt = kSolveThreads - nred;
-        const int D = M.gmmD, C = M.gmmC, Dp = (D + 8) & ~7;   // row stride: zero padded to 8, slot D of ycomp holds p_c
-#pragma unroll 1
-        for (int j = 1 + t; j < J; j += nt) {  // Eigen AngleAxisd(Quaterniond)
-            const double* q = S.xt + 3 + 4 * j;
-            double nn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
-            double s = 0.0;
-            if (nn != 0.0) {
-                const double ang = 2.0 * atan2(nn, fabs(q[3]));
-                if (q[3] < 0) nn = -nn;
-                s = ang / nn;
-            }
-            S.aa[3 * (j - 1)] = q[0] * s;
-            S.aa[3 * (j - 1) + 1] = q[1] * s;
-            S.aa[3 * (j - 1) + 2] = q[2] * s;
-        }
-        asm volatile("bar.sync 3, %0;" ::"r"(nt) : "memory");
-#pragma unroll 1
-        for (int i = t; i < C * Dp; i += nt) {
-            const int cc = i / Dp, k = i - cc * Dp;
-            S.dcomp[i] = (k < D) ? S.aa[k] - M.gmm_mean[cc * D + k] : 0.0;
-        }
-        asm volatile("bar.sync 3, %0;" ::"r"(nt) : "memory");
-#pragma unroll 1
-        for (int i = t; i < C * D; i += 2 * nt) {  // y_c = Sigma_c^-1 (x - mu_c), two rows per thread at a time
-            // the precision matrices are symmetric (symmetrised at load): walk column r so that consecutive
-            // threads read consecutive addresses; sixteen loads in flight per thread (the walk is L2-latency bound)
-            const int i2 = i + nt;
-            const bool two = i2 < C * D;
-            const int ca = i / D, ra = i - ca * D;
-            const int cb = two ? i2 / D : ca, rb = two ? i2 - cb * D : ra;
-            const double* Pa = M.gmm_prec + (size_t)ca * D * D + ra;
-            const double* Pb = M.gmm_prec + (size_t)cb * D * D + rb;
-            const double* da = S.dcomp + ca * Dp;
-            const double* db = S.dcomp + cb * Dp;
-            double sa0 = 0, sa1 = 0, sb0 = 0, sb1 = 0;
-#pragma unroll 1
-            for (int k = 0; k < D; k += 8) {
-                double ta[8], tb[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    ta[u] = (k + u < D) ? __ldg(Pa + (size_t)(k + u) * D) : 0.0;
-                    tb[u] = (k + u < D) ? __ldg(Pb + (size_t)(k + u) * D) : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; u += 2) {
-                    sa0 = fma(ta[u], da[k + u], sa0);          // dcomp rows are zero padded to a multiple of 8
-                    sa1 = fma(ta[u + 1], da[k + u + 1], sa1);
-                    sb0 = fma(tb[u], db[k + u], sb0);
-                    sb1 = fma(tb[u + 1], db[k + u + 1], sb1);
-                }
-            }
-            S.ycomp[ca * Dp + ra] = sa0 + sa1;
-            if (two) S.ycomp[cb * Dp + rb] = sb0 + sb1;
-        }
-        asm volatile("bar.sync 3, %0;" ::"r"(nt) : "memory");
-        // p_c, one warp per component; first minimum wins (strict <)
-#pragma unroll 1
-        for (int cc = t >> 5; cc < C; cc += nt >> 5) {
-            double sp = 0;
-#pragma unroll 1
-            for (int k = t & 31; k < D; k += 32) sp += S.dcomp[cc * Dp + k] * S.ycomp[cc * Dp + k];
-            sp = 0.5 * warp_sum(sp);
-            if ((t & 31) == 0) S.ycomp[cc * Dp + D] = sp;
-        }
-        asm volatile("bar.sync 3, %0;" ::"r"(nt) : "memory");
-        if (t == 0) {
-            double bestp = 1.79769313486231570e308, bestsq = 0;
-            int best = 0;
-#pragma unroll 1
-            for (int cc = 0; cc < C; ++cc) {
-                const double sq = S.ycomp[cc * Dp + D];
-                const double pc = sq - M.gmm_clog[cc];
-                if (pc < bestp) {
-                    bestp = pc;
-                    bestsq = sq;
-                    best = cc;
-                }
-            }
-            S.iscr[0] = best;
-            S.scr[40] = 0.5 * sbp * sbp * (bestsq - M.gmm_clog[best]);
-        }
+        prior_eval(M, S.xt, sbp, tid - nred, kSolveThreads - nred, S.aa, S.dcomp, S.ycomp, &S.iscr[0], &S.scr[40]);
     }
     __syncthreads();
     phase_lap(a.q, 7, tp);
@@ -2063,7 +2118,15 @@ lm_flow_kernel(DevModel M, DevParts Pt, LmBuf a) {
         const int task = s_task;
         if (task == -1) break;
         const int type = (int)((unsigned)task >> 30), f = (task >> 12) & 0x3FFFF, idx = task & 0xFFF;
-        if (TC) {
+        if (type == kTaskPrior) {
+            prior_body(M, a, f, smem_raw);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                s_last = atomicSub(&a.q.gram_left[f], 1) == 1;
+                lap(2);
+            }
+        } else if (TC) {
             const bool cost_only = ldg2(&a.state[f].last) != 0;
             if (M.K == 10)
                 fused_body<10>(M, Pt, a, f, idx, cost_only, smem_raw, tmem_d, &s_mbar, mma_phase);
@@ -2094,13 +2157,10 @@ lm_flow_kernel(DevModel M, DevParts Pt, LmBuf a) {
                 s_last = 0;
                 if (atomicSub(&a.q.rows_left[f], 1) == 1) {
                     __threadfence();
-                    if (cost_only) {
-                        s_last = 1;   // no Gram tasks: this CTA finishes the frame
-                    } else {
-                        const int nch = ldg2(&a.state[f].nchunks);
-                        atomicExch(&a.q.gram_left[f], nch);
-                        __threadfence();
-                        flow_push(a.q, kTaskGram, f, nch);
+                    if (cost_only) {   // no Gram tasks: the records were the evaluation (gram_left counts them as one)
+                        s_last = atomicSub(&a.q.gram_left[f], 1) == 1;
+                    } else {           // (gram_left was set when the evaluation was opened, flow_push_eval)
+                        flow_push(a.q, kTaskGram, f, ldg2(&a.state[f].nchunks));
                     }
                 }
                 lap(0);
@@ -2123,16 +2183,9 @@ lm_flow_kernel(DevModel M, DevParts Pt, LmBuf a) {
             if (tid == 0) {
                 if (done) {
                     atomicSub(&a.q.ctrl[2], 1u);
-                } else if (TC || a.fused) {
-                    const int nch = ldg2(&a.state[f].nchunks);
-                    atomicExch(&a.q.gram_left[f], nch);
-                    __threadfence();
-                    flow_push(a.q, kTaskFused, f, nch);
                 } else {
-                    const int nrb = (ldg2(&a.state[f].nslots) + 255) >> 8;
-                    atomicExch(&a.q.rows_left[f], nrb);
-                    __threadfence();
-                    flow_push(a.q, kTaskRows, f, nrb);
+                    flow_push_eval(a, f, ldg2(&a.state[f].nslots), ldg2(&a.state[f].nchunks), ldg2(&a.state[f].last) != 0,
+                                   a.prior_task && ldg2(&a.state[f].sbp) > 0.0);
                 }
                 lap(2);
             }
