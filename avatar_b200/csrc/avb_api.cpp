@@ -1356,6 +1356,9 @@ PoseArgs pose_args(avb_fitter* ft, const double* dx, bool vis, const avb_options
     a.joint_pos = nullptr;
     a.joint_trans = nullptr;
     a.do_visibility = vis ? 1 : 0;
+    a.do_lbs = 1;
+    // small batches: a forward-only launch spreads the vertices of a frame over several CTAs (every CTA rebuilds the joint tables)
+    a.slices = ft->batch * 8 <= ft->num_sms ? 8 : (ft->batch * 4 <= ft->num_sms ? 4 : (ft->batch * 2 <= ft->num_sms ? 2 : 1));
     a.enable_occlusion = o ? o->enable_occlusion : 1;
     a.visible = ft->d_vis;
     a.pv_idx = ft->d_pv_idx;
@@ -1373,6 +1376,14 @@ int enqueue_correspond(avb_fitter* ft, const double* dx, const avb_options* o, c
     PoseArgs pa = pose_args(ft, dx, true, o);
     {
         ProfScope ps(ft, KC_POSE);
+        if (pa.slices > 1) {   // small batch: pose the cloud with several CTAs per frame, then visibility + compaction per frame
+            PoseArgs fwd = pa;
+            fwd.do_visibility = 0;
+            fwd.pv_f32 = nullptr;
+            CUDA_TRY(launch_pose_visibility(ft->dm, ft->dp, fwd, B, st));
+            ++ft->launches;
+            pa.do_lbs = 0;
+        }
         CUDA_TRY(launch_pose_visibility(ft->dm, ft->dp, pa, B, st));
     }
     ++ft->launches;

@@ -31,7 +31,8 @@ namespace avb {
 __global__ void __launch_bounds__(512)
 pose_visibility_kernel(DevModel M, DevParts Pt, PoseArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int f = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int S = a.slices > 1 ? a.slices : 1;   // > 1 only for forward-only launches (small batches: most SMs would idle)
+    const int f = blockIdx.x / S, slice = blockIdx.x - f * S, tid = threadIdx.x, nt = blockDim.x;
     const int V = M.V, J = M.J, K = M.K;
     double* xs = reinterpret_cast<double*>(smem_raw);
     double* tb = xs + ((M.nx + 1) & ~1);
@@ -41,11 +42,11 @@ pose_visibility_kernel(DevModel M, DevParts Pt, PoseArgs a) {
 
     for (int i = tid; i < M.nx; i += nt) xs[i] = a.x[(size_t)f * M.nx + i];
     __syncthreads();
-    build_tables(M, xs, T, false);
+    if (a.do_lbs) build_tables(M, xs, T, false);
 
     double* cloud = a.cloud + (size_t)f * 3 * V;
     const double* w = xs + 3 + 4 * J;
-    for (int v = tid; v < V; v += nt) {
+    for (int v = a.do_lbs ? slice * nt + tid : V; v < V; v += nt * S) {
         // shape blend (Avatar.cpp:26) then LBS with the assignedJoints weights (AvatarOptimizer.cpp:507-514)
         const float* sd = M.sdT + v;   // component-major: consecutive threads read consecutive addresses
         double v0[3];
@@ -83,9 +84,9 @@ pose_visibility_kernel(DevModel M, DevParts Pt, PoseArgs a) {
         cloud[3 * (size_t)v + 1] = x1;
         cloud[3 * (size_t)v + 2] = x2;
     }
-    if (a.joint_pos)
+    if (a.joint_pos && slice == 0 && a.do_lbs)
         for (int i = tid; i < 3 * J; i += nt) a.joint_pos[(size_t)f * 3 * J + i] = T.pos[i];
-    if (a.joint_trans)  // 3x4 column-major per joint: [G_j | tau_j] (Avatar.cpp:59-64)
+    if (a.joint_trans && slice == 0 && a.do_lbs)  // 3x4 column-major per joint: [G_j | tau_j] (Avatar.cpp:59-64)
         for (int i = tid; i < 12 * J; i += nt) {
             const int j = i / 12, e = i % 12, c = e / 3, r = e % 3;
             a.joint_trans[(size_t)f * 12 * J + i] = (c < 3) ? T.G[9 * j + 3 * r + c] : T.tau[3 * j + r];
@@ -424,7 +425,10 @@ cudaError_t launch_pose_visibility(const DevModel& M, const DevParts& Pt, const 
         cudaError_t e = cudaFuncSetAttribute(pose_visibility_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    pose_visibility_kernel<<<batch, 512, smem, st>>>(M, Pt, a);
+    const int S = (a.slices > 1 && !a.do_visibility) ? a.slices : 1;
+    PoseArgs b = a;
+    b.slices = S;
+    pose_visibility_kernel<<<batch * S, 512, smem, st>>>(M, Pt, b);
     return cudaGetLastError();
 }
 

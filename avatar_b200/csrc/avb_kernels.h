@@ -13,6 +13,8 @@ struct PoseArgs {
     double* joint_pos;     // nullable [batch][3J]
     double* joint_trans;   // nullable [batch][12J]
     int do_visibility;     // 0: forward only (final ava.update())
+    int do_lbs;            // 0: the cloud is already posed (a sliced forward-only launch ran before): visibility + compaction only
+    int slices;            // forward-only launches of small batches: CTAs per frame, each poses a slice of the vertices (grid = batch * slices)
     int enable_occlusion;
     uint8_t* visible;      // [batch][V]
     int* pv_idx;           // [batch][V]       compacted (part, vertex id) order -> vertex id

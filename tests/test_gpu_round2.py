@@ -494,3 +494,31 @@ def test_gather_entry_points_without_communicator(model, prior_arrays):
         assert rc != 0
         assert b"communicator" in _lib.lib.avb_last_error() or b"gather" in _lib.lib.avb_last_error()
     ft.close()
+
+
+def test_prior_task_schedule_is_bit_identical(model, omodel, prior_arrays, monkeypatch):
+    """Small batches run the pose prior of a trial point as its own task of lm_flow_kernel (next to the record / Gram tasks);
+    large ones evaluate it inside the solve.  The arithmetic is the same code on the same data: fitted parameters, costs and
+    iteration counts must not depend on the schedule, bit for bit -- on the fp64 path, the fused fp64 path and the tensor path,
+    with early exits (function_tolerance > 0) and with the cost-only last evaluation (function_tolerance = 0)."""
+    from avatar_b200 import Fitter, _lib
+    part_map, num_parts = prior_arrays["part_map"], int(prior_arrays["num_parts"])
+    fr = [_frame(model, omodel, prior_arrays, s) for s in (1000, 1001, 1002)]
+    pts = np.concatenate([f[2] for f in fr])
+    lab = np.concatenate([f[3] for f in fr])
+    off = np.cumsum([0] + [len(f[2]) for f in fr]).astype(np.int64)
+    x0 = np.stack([f[1] for f in fr])
+    for fused, jtj, ftol in (("0", _lib.JTJ_FP64, 0.0), ("0", _lib.JTJ_FP64, 1e-4), ("1", _lib.JTJ_FP64, 0.0), ("0", _lib.JTJ_BF16_TENSOR, 0.0)):
+        out = {}
+        for mode in ("0", "32"):   # largest batch that takes the task schedule
+            monkeypatch.setenv("AVB_PRIOR_TASK", mode)
+            monkeypatch.setenv("AVB_FUSED", fused)
+            ft = Fitter(model, num_parts, part_map, 3, int(off[-1]) + 64)
+            o = _opts(function_tolerance=ftol, icp_iters=2)
+            o.jtj_precision = jtj
+            out[mode] = ft.fit_batch(pts, lab, off, x0, o)
+            ft.close()
+        (xa, sa, _), (xb, sb, _) = out["0"], out["32"]
+        assert np.array_equal(xa, xb), (fused, jtj, ftol)
+        for a, b in zip(sa, sb):
+            assert a.iterations == b.iterations and a.accepted_steps == b.accepted_steps and a.final_cost == b.final_cost
