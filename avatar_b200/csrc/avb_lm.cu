@@ -1256,6 +1256,7 @@ __device__ __forceinline__ bool diag_factor(double (&a)[kNB], double* W, int j0,
         const double rsk = __shfl_sync(0xffffffffu, myrs, k);
         a[k] *= rsk;   // L_rk = a_rk / sqrt(d_k); k == r: sqrt(d_r)
     }
+    __syncwarp();   // the duplicate lanes (8..31) have read the rows that lanes 0..7 overwrite now
     if (lane < kNB) {
 #pragma unroll
         for (int k = 0; k < kNB; ++k) {
@@ -1268,7 +1269,7 @@ __device__ __forceinline__ bool diag_factor(double (&a)[kNB], double* W, int j0,
 }
 // row i of the panel: x L11^T = W[i][j0 .. j0 + nb), column-oriented (one fma on the critical path per column)
 __device__ __forceinline__ void panel_row(double* W, int i, int j0, int nb, int t0, const double* Lw, double* Lp, int ldp,
-                                          double (&x)[kNB], bool store) {
+                                          double (&x)[kNB], bool store, bool sync_warp) {
     double* wi = W + tri(i) + j0;
 #pragma unroll
     for (int c = 0; c < kNB; ++c) x[c] = (c < nb) ? wi[c] * Lw[c * kNB + c] : 0.0;
@@ -1276,6 +1277,7 @@ __device__ __forceinline__ void panel_row(double* W, int i, int j0, int nb, int 
     for (int k = 0; k < kNB - 1; ++k)
 #pragma unroll
         for (int c = k + 1; c < kNB; ++c) x[c] = fma(-x[k], Lw[c * kNB + k], x[c]);
+    if (sync_warp) __syncwarp();   // warp 0: duplicate lanes read the row another lane is about to overwrite
     if (store) {
 #pragma unroll
         for (int c = 0; c < kNB; ++c) {
@@ -1315,7 +1317,7 @@ __device__ bool aug_cholesky(double* W, int P, int R, double* dinv, double* wscr
             double x[kNB];
             const int i = t0 + r;
             const bool have = i < R;
-            panel_row(W, min(i, R - 1), j0, nb, t0, Lw, Lp, ldp, x, have && lane < kNB);
+            panel_row(W, min(i, R - 1), j0, nb, t0, Lw, Lp, ldp, x, have && lane < kNB, true);
             if (!have) {
 #pragma unroll
                 for (int c = 0; c < kNB; ++c) x[c] = 0.0;
@@ -1336,6 +1338,7 @@ __device__ bool aug_cholesky(double* W, int P, int R, double* dinv, double* wscr
 #pragma unroll
                     for (int c = 0; c < kNB; ++c) a[c] = fma(-x[k], xc[c], a[c]);
                 }
+                __syncwarp();     // (duplicate lanes read the same rows of W)
                 if (r >= nbn) {   // not a row of the diagonal block: store, and present an identity row to the factorisation
 #pragma unroll
                     for (int c = 0; c < kNB; ++c) {
@@ -1351,7 +1354,7 @@ __device__ bool aug_cholesky(double* W, int P, int R, double* dinv, double* wscr
         } else {
             for (int i = t0 + kNB + (tid - 32); i < R; i += nthr - 32) {
                 double x[kNB];
-                panel_row(W, i, j0, nb, t0, Lw, Lp, ldp, x, true);
+                panel_row(W, i, j0, nb, t0, Lw, Lp, ldp, x, true, false);
             }
             asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
             if (mcol > 0) {
