@@ -601,6 +601,15 @@ def main():
         line["secondary"] = {"single_frame_fit_ms_median": 1e3 * float(np.median(lat[2:])),
                              "single_frame_points": int(len(pts[0])),
                              "note": "host buffers in, parameters out, icp_iters=1, 10 LM iterations; wall clock"}
+        # the reference's own live regime (demo.cpp:58 data-interval 12: about a thousand points per frame): every 12th point
+        lat = []
+        for i in range(12):
+            ps, ls = np.ascontiguousarray(pts[i % 8][::12]), np.ascontiguousarray(labs[i % 8][::12])
+            tA = time.perf_counter()
+            f1.fit_batch(ps, ls, np.array([0, len(ps)]), x0[i % 8][None], o1)
+            lat.append(time.perf_counter() - tA)
+        line["secondary"]["single_frame_sparse"] = {"fit_ms_median": 1e3 * float(np.median(lat[2:])), "points": int(len(pts[0][::12])),
+                                                    "note": "every 12th point of the same frames (the reference demo's data-interval 12 regime)"}
         # ---- BASELINE.json configs[3]: tracking, 300 DISTINCT frames of a slerped ground-truth motion, every frame warm-started
         #      from the previous fit (avb_track_sequence: uploads run ahead on a copy stream) ----
         try:
