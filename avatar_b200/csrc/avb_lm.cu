@@ -282,11 +282,25 @@ __device__ __forceinline__ double record_vertex(const DevModel& M, const DevPart
     const int* gj = Pt.gjoints + g * kMaxJ;
     const float* sd = M.sd + (size_t)v * 3 * K;
     double v0[3];
+    if ((K & 1) == 0) {   // even K: the vertex's 3 K floats start on an 8-byte boundary: half as many (8-byte) L2 loads, same order of sums
+        const float2* sd2 = reinterpret_cast<const float2*>(sd);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        double s = 0;
-        for (int k = 0; k < K; ++k) s += (double)sd[c * K + k] * w[k];
-        v0[c] = M.vt[3 * (size_t)v + c] + s;
+        for (int c = 0; c < 3; ++c) {
+            double s = 0;
+            for (int k = 0; k < K; k += 2) {
+                const float2 t = sd2[(c * K + k) >> 1];
+                s += (double)t.x * w[k];
+                s += (double)t.y * w[k + 1];
+            }
+            v0[c] = M.vt[3 * (size_t)v + c] + s;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double s = 0;
+            for (int k = 0; k < K; ++k) s += (double)sd[c * K + k] * w[k];
+            v0[c] = M.vt[3 * (size_t)v + c] + s;
+        }
     }
     const int n = M.sk_n[v];
     double xk[AVB_MAX_ASSIGN_][3], wk[AVB_MAX_ASSIGN_];
@@ -382,7 +396,14 @@ __device__ void rows_body(const DevModel& M, const DevParts& Pt, const LmBuf& a,
     double* scr = w + ((K + 1) & ~1);
     int* gstart = reinterpret_cast<int*>(scr + 32);
     const double* gtab = a.tab + (size_t)f * a.tabD;
-    for (int q = tid; q < a.tabD; q += 256) tab[q] = ldg2(gtab + q);
+    if ((a.tabD & 1) == 0) {   // 16-byte loads, all of a thread's loads in flight (the table comes from L2: latency, not bytes)
+        const double2* g2 = reinterpret_cast<const double2*>(gtab);
+        double2* t2 = reinterpret_cast<double2*>(tab);
+#pragma unroll 4
+        for (int q = tid; q < (a.tabD >> 1); q += 256) t2[q] = __ldcg(g2 + q);
+    } else {
+        for (int q = tid; q < a.tabD; q += 256) tab[q] = ldg2(gtab + q);
+    }
     for (int q = tid; q < K; q += 256) w[q] = ldg2(a.xt + (size_t)f * M.nx + 3 + 4 * J + q);
     for (int q = tid; q <= Pt.numGroups; q += 256) gstart[q] = a.gstart[(size_t)f * (kMaxGroups + 1) + q];
     int* s_v = reinterpret_cast<int*>(gstart + kMaxGroups + 2);
