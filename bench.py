@@ -344,9 +344,16 @@ def main():
                 pending = True
                 continue
             if use_f32:   # split form of the same call: avb_upload_batch_f32 + avb_fit_resident + avb_download_results
+                tr = ln.setdefault("trace", []) if os.environ.get("AVB_BENCH_TRACE") else None
+                if tr is not None:
+                    tr.append(time.perf_counter())
                 ln["ft"].upload(ln["pts32"], ln["lab"], ln["off"])
                 ln["ft"].fit_resident(h_x[ln["lo"]:ln["hi"]], opt)
+                if tr is not None:
+                    tr.append(time.perf_counter())
                 x, st, _ = ln["ft"].download()
+                if tr is not None:
+                    tr.append(time.perf_counter())
             else:
                 x, st, _ = ln["ft"].fit_batch(ln["pts"], ln["lab"], ln["off"], h_x[ln["lo"]:ln["hi"]], opt)
             out_q.put(x)
@@ -376,6 +383,11 @@ def main():
     full = e2e_run(args.steps)
     barrier()
     t3 = time.perf_counter()
+    if os.environ.get("AVB_BENCH_TRACE"):   # development aid: host time stamps of every lane step (enqueue / wait split)
+        for li, ln in enumerate(lanes):
+            tr = np.array(ln.get("trace", []))[-3 * args.steps:].reshape(-1, 3)
+            print(f"lane {li}: enqueue ms median {1e3 * np.median(tr[:, 1] - tr[:, 0]):.3f}, wait ms median {1e3 * np.median(tr[:, 2] - tr[:, 1]):.3f}, "
+                  f"period ms median {1e3 * np.median(np.diff(tr[:, 0])):.3f}, gap after download ms median {1e3 * np.median(tr[1:, 0] - tr[:-1, 2]):.3f}", file=sys.stderr)
     e2e_s = shard.max_over_ranks(t3 - t2, dev)
     e2e_value = F_total * args.steps / e2e_s
     clocks = sampler.stop(t0, t3) if sampler else None
