@@ -141,7 +141,8 @@ struct avb_fitter {
     float4* d_pv_f32 = nullptr; float* d_pv_rmax = nullptr;
     int fused64 = 0;               // fp64 flow path, AVB_FUSED=1: fused record + Gram tasks (no d_rec round trip).  Measured NOT
                                    // faster (60.5 k vs 61.2 k frames/s): a chunk fills 75 % of the CTA's threads, DESIGN.md 5.4
-    float* d_data_f32 = nullptr;   // avb_upload_batch_f32 staging
+    float* d_data_f32 = nullptr;   // avb_upload_batch_f32: the cloud as uploaded floats
+    bool data_is_f32 = false;      // the resident cloud lives in d_data_f32 (nn_kernel widens on load); d_data is filled on demand
     int maxc = 0, tabD = 0, max_nj = 0, chunk_verts = 192, chunk_verts_tc = 256;   // vertices per Gram chunk: fp64 path (3 CTAs/SM) / tensor path
     long long pstride = 0;
     // lm_flow_kernel work queue
@@ -933,6 +934,7 @@ int avb_upload_batch(avb_fitter* ft, int32_t batch, const double* clouds, const 
     if (total > 0) {
         const int64_t o0 = offsets[0];
         CUDA_TRY(cudaMemcpyAsync(ft->d_data, clouds + 3 * o0, (size_t)total * 24, cudaMemcpyHostToDevice, ft->stream));
+        ft->data_is_f32 = false;
         CUDA_TRY(cudaMemcpyAsync(ft->d_labels, labels + o0, (size_t)total * 4, cudaMemcpyHostToDevice, ft->stream));
     }
     return AVB_OK;
@@ -955,7 +957,7 @@ int avb_upload_batch_f32(avb_fitter* ft, int32_t batch, const float* clouds, con
         const int64_t o0 = offsets[0];
         CUDA_TRY(cudaMemcpyAsync(ft->d_data_f32, clouds + 3 * o0, (size_t)total * 12, cudaMemcpyHostToDevice, ft->stream));
         CUDA_TRY(cudaMemcpyAsync(ft->d_labels, labels + o0, (size_t)total * 4, cudaMemcpyHostToDevice, ft->stream));
-        CUDA_TRY(launch_widen_points(ft->d_data_f32, ft->d_data, 3 * (long long)total, ft->num_sms, ft->stream));
+        ft->data_is_f32 = true;   // nn_kernel reads the floats and widens on load (exact): no separate pass over the cloud
     }
     return AVB_OK;
 }
@@ -1093,6 +1095,7 @@ int avb_upload_depth_batch(avb_fitter* ft, int32_t batch, const float* depth, co
     a.strip_offset = ft->d_strip_offset;
     a.bad_label = ft->d_bad_label;
     a.cloud = ft->d_data;
+    ft->data_is_f32 = false;   // the cloud kernels write doubles
     a.labels = ft->d_labels;
     if (!ft->cev[0])
         for (auto& e : ft->cev) CUDA_TRY(cudaEventCreate(&e));
@@ -1302,8 +1305,11 @@ int avb_download_batch(avb_fitter* ft, double* clouds, int32_t* labels, int64_t*
     if (!ft) return fail(AVB_ERR_INVALID, "null fitter");
     if (ft->batch <= 0) return fail(AVB_ERR_INVALID, "no batch uploaded");
     CUDA_TRY(cudaSetDevice(ft->device));
-    if (clouds && ft->total_points > 0)
+    if (clouds && ft->total_points > 0) {
+        if (ft->data_is_f32)   // the resident cloud is the float upload: widen it for the caller
+            CUDA_TRY(launch_widen_points(ft->d_data_f32, ft->d_data, 3 * (long long)ft->total_points, ft->num_sms, ft->stream));
         CUDA_TRY(cudaMemcpyAsync(clouds, ft->d_data, (size_t)ft->total_points * 24, cudaMemcpyDeviceToHost, ft->stream));
+    }
     if (labels && ft->total_points > 0)
         CUDA_TRY(cudaMemcpyAsync(labels, ft->d_labels, (size_t)ft->total_points * 4, cudaMemcpyDeviceToHost, ft->stream));
     CUDA_TRY(cudaStreamSynchronize(ft->stream));
@@ -1394,6 +1400,7 @@ int enqueue_correspond(avb_fitter* ft, const double* dx, const avb_options* o, c
     NNArgs na{};
     na.V = V;
     na.data = ft->d_data;
+    na.data_f32 = ft->data_is_f32 ? ft->d_data_f32 : nullptr;
     na.labels = ft->d_labels;
     na.chunk_frame = ft->d_chunk_frame;
     na.chunk_begin = ft->d_chunk_begin;
@@ -1979,6 +1986,7 @@ int avb_track_sequence(avb_fitter* ft, int32_t T, const double* clouds, const in
     }
     std::memcpy(ft->h_x, x0, nx * 8);
     CUDA_TRY(cudaMemcpyAsync(ft->d_x, ft->h_x, nx * 8, cudaMemcpyHostToDevice, st));
+    ft->data_is_f32 = false;
     // uploads run ahead on the copy stream, one event per frame
     for (int t = 0; t < T; ++t) {
         const int64_t n = offsets[t + 1] - offsets[t], b = offsets[t] - o0;

@@ -289,7 +289,16 @@ nn_kernel(DevParts Pt, NNArgs a) {
         double q2 = 0.0;
         if (li < count) {
             const long long gi = begin + li;
-            const double q0 = a.data[3 * gi], q1 = a.data[3 * gi + 1], qz = a.data[3 * gi + 2];
+            double q0, q1, qz;
+            if (a.data_f32) {   // float upload: widened here (exact), no separate pass over the cloud
+                q0 = (double)a.data_f32[3 * gi];
+                q1 = (double)a.data_f32[3 * gi + 1];
+                qz = (double)a.data_f32[3 * gi + 2];
+            } else {
+                q0 = a.data[3 * gi];
+                q1 = a.data[3 * gi + 1];
+                qz = a.data[3 * gi + 2];
+            }
             const int label = a.labels[gi];
             const bool lab_ok = label >= 0 && label < Pt.numParts;
             const int s = lab_ok ? s_start[label] : 0, e = lab_ok ? s_start[label + 1] : 0;

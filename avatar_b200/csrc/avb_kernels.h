@@ -28,6 +28,7 @@ struct PoseArgs {
 struct NNArgs {
     int V;
     const double* data;          // [3 * total points]
+    const float* data_f32;       // nullable: the same cloud as uploaded floats (avb_upload_batch_f32); widened on load, bit-identical
     const int* labels;           // [total points]
     const int* chunk_frame;      // [chunks]
     const long long* chunk_begin;  // [chunks] first global point of the chunk

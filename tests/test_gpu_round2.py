@@ -410,6 +410,13 @@ def test_float32_upload_is_bit_identical(model, omodel, prior_arrays):
         ft.upload(cloud, lab, off)
         ft.fit_resident(x0, _opts(function_tolerance=0.0))
         out.append(ft.download()[0])
+        # the resident batch reads back as the doubles the caller would have uploaded (after a float upload nn_kernel reads
+        # the floats directly; avb_download_batch widens on demand)
+        dp, dl, do = ft.download_batch()
+        assert np.array_equal(dp, pts) and np.array_equal(dl, lab) and np.array_equal(do, off)
+    # a double upload after a float upload must not leave the fitter reading stale floats
+    ft.upload(pts[::-1].copy(), lab[::-1].copy(), np.array([0, len(pts)], dtype=np.int64))
+    assert np.array_equal(ft.download_batch()[0], pts[::-1])
     ft.close()
     assert np.array_equal(out[0], out[1]) and np.array_equal(out[0], out[2])
 
