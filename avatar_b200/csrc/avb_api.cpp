@@ -1380,12 +1380,16 @@ int enqueue_correspond(avb_fitter* ft, const double* dx, const avb_options* o, c
     cudaStream_t st = ft->stream;
     const int B = ft->batch, V = ft->model->V;
     PoseArgs pa = pose_args(ft, dx, true, o);
+    pa.zero_cnt = ft->d_cnt;   // zeroed by the kernel's visibility pass: no memset launches between pose and nn
+    pa.zero_sum = ft->d_sum;
+    pa.zero_range = ft->d_range;
     {
         ProfScope ps(ft, KC_POSE);
         if (pa.slices > 1) {   // small batch: pose the cloud with several CTAs per frame, then visibility + compaction per frame
             PoseArgs fwd = pa;
             fwd.do_visibility = 0;
             fwd.pv_f32 = nullptr;
+            fwd.zero_cnt = nullptr;
             CUDA_TRY(launch_pose_visibility(ft->dm, ft->dp, fwd, B, st));
             ++ft->launches;
             pa.do_lbs = 0;
@@ -1394,9 +1398,6 @@ int enqueue_correspond(avb_fitter* ft, const double* dx, const avb_options* o, c
     }
     ++ft->launches;
     if (after_pose) CUDA_TRY(cudaEventRecord(after_pose, st));
-    CUDA_TRY(cudaMemsetAsync(ft->d_cnt, 0, (size_t)B * V * 4, st));
-    CUDA_TRY(cudaMemsetAsync(ft->d_sum, 0, (size_t)B * V * 24, st));
-    CUDA_TRY(cudaMemsetAsync(ft->d_range, 0, (size_t)B * 4, st));
     NNArgs na{};
     na.V = V;
     na.data = ft->d_data;

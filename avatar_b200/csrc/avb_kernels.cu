@@ -113,6 +113,13 @@ pose_visibility_kernel(DevModel M, DevParts Pt, PoseArgs a) {
     }
     uint8_t* gvis = a.visible + (size_t)f * V;
     for (int v = tid; v < V; v += nt) gvis[v] = vis[v];
+    if (a.zero_cnt) {   // the accumulators of the correspondence search that follows
+        int* zc = a.zero_cnt + (size_t)f * V;
+        unsigned long long* zs = a.zero_sum + (size_t)f * 3 * V;
+        for (int v = tid; v < V; v += nt) zc[v] = 0;
+        for (int v = tid; v < 3 * V; v += nt) zs[v] = 0ull;
+        if (tid == 0) a.zero_range[f] = 0;
+    }
 
     // ---- compaction per part, ascending vertex id inside a part (AvatarOptimizer.cpp:860-880) ----
     int* pv_idx = a.pv_idx + (size_t)f * V;
@@ -190,6 +197,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 constexpr int kNNPer = 4;               // points per thread between two CTA barriers
 constexpr int kNNPass = 512 * kNNPer;
 
+template <bool F32DATA>   // the data cloud is the float upload (a.data_f32) / the doubles (a.data)
 __global__ void __launch_bounds__(512, 2)
 nn_kernel(DevParts Pt, NNArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -290,7 +298,7 @@ nn_kernel(DevParts Pt, NNArgs a) {
         if (li < count) {
             const long long gi = begin + li;
             double q0, q1, qz;
-            if (a.data_f32) {   // float upload: widened here (exact), no separate pass over the cloud
+            if (F32DATA) {   // float upload: widened here (exact), no separate pass over the cloud
                 q0 = (double)a.data_f32[3 * gi];
                 q1 = (double)a.data_f32[3 * gi + 1];
                 qz = (double)a.data_f32[3 * gi + 2];
@@ -444,10 +452,14 @@ cudaError_t launch_pose_visibility(const DevModel& M, const DevParts& Pt, const 
 cudaError_t launch_nn(const DevParts& Pt, const NNArgs& a, int num_chunks, cudaStream_t st) {
     const size_t smem = nn_smem_bytes(a.stage_cap, a.pv_f32 != nullptr);
     {   // per device/context attribute: set on every launch (cheap host call)
-        cudaError_t e = cudaFuncSetAttribute(nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = a.data_f32 ? cudaFuncSetAttribute(nn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                   : cudaFuncSetAttribute(nn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    if (num_chunks > 0) nn_kernel<<<num_chunks, 512, smem, st>>>(Pt, a);
+    if (num_chunks > 0) {
+        if (a.data_f32) nn_kernel<true><<<num_chunks, 512, smem, st>>>(Pt, a);
+        else nn_kernel<false><<<num_chunks, 512, smem, st>>>(Pt, a);
+    }
     return cudaGetLastError();
 }
 

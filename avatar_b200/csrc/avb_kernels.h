@@ -23,6 +23,9 @@ struct PoseArgs {
     long long pv_stride;   // doubles per frame (even, >= 3V + 2)
     float4* pv_f32;        // nullable [batch][V]: the compacted positions relative to the root translation p, as floats (nn_kernel's pre-scan)
     float* pv_rmax;        // [batch]: max |coordinate| of pv_f32 of the frame (error bound of the pre-scan)
+    int* zero_cnt;                   // nullable [batch][V]: the correspondence counters nn_kernel adds into, zeroed here with the
+    unsigned long long* zero_sum;    // [batch][V][3] sums and the frame's range flag (instead of three memset launches per fit)
+    int* zero_range;                 // [batch]
 };
 
 struct NNArgs {

@@ -295,7 +295,7 @@ def main():
 
     # ---- value: inputs resident in HBM ----
     for ln in lanes:
-        ln["ft"].upload(ln["pts"], ln["lab"], ln["off"])
+        ln["ft"].upload(ln["pts32"] if use_f32 else ln["pts"], ln["lab"], ln["off"])   # the same resident format the e2e arm leaves in HBM
     for _ in range(args.warmup):
         for ln in lanes:
             ln["ft"].fit_resident(ln["x0"], opt)
