@@ -1192,7 +1192,7 @@ __host__ __device__ inline size_t solve_smem_bytes(int J, int K, int C) {
     const int P = 3 + 3 * J + K, nx = 3 + 4 * J + K, D = 3 * (J - 1);
     size_t d = 2 * ((nx + 1) & ~1) + solve_tb_doubles(J, K, C) + solve_h_doubles(J, K) + 5 * ((P + 1) & ~1) + 8 * kNBsq + ((D + 1) & ~1) + 64 +
                2 * (size_t)(C > 0 ? C : 1) * ((D + 8) & ~7);
-    return d * 8 + 64 * 4 + 128;
+    return d * 8 + (8 + 4 * kMaxGroups + 8) * 4 + 128;   // + iscr: 8 scalars | the group runs staged by the solve ([kMaxGroups][4])
 }
 __device__ inline SolveSmem carve_solve(unsigned char* raw, const DevModel& M) {
     SolveSmem S;
