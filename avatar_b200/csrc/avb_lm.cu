@@ -653,7 +653,14 @@ __device__ void fused64_body(const DevModel& M, const DevParts& Pt, const LmBuf&
     double* scr = w + ((K + 1) & ~1);
     float* T = reinterpret_cast<float*>(smem_raw + fused64_head_bytes(a.tabD, K));
     const double* gtab = a.tab + (size_t)f * a.tabD;
-    for (int q = tid; q < a.tabD; q += 256) tab[q] = ldg2(gtab + q);
+    if ((a.tabD & 1) == 0) {   // 16-byte loads, all of a thread's loads in flight (as in rows_body)
+        const double2* g2 = reinterpret_cast<const double2*>(gtab);
+        double2* t2 = reinterpret_cast<double2*>(tab);
+#pragma unroll 4
+        for (int q = tid; q < (a.tabD >> 1); q += 256) t2[q] = __ldcg(g2 + q);
+    } else {
+        for (int q = tid; q < a.tabD; q += 256) tab[q] = ldg2(gtab + q);
+    }
     for (int q = tid; q < K; q += 256) w[q] = ldg2(a.xt + (size_t)f * M.nx + 3 + 4 * J + q);
     const int v = (tid < count) ? (int)a.mlist[(size_t)f * a.rec_rs + start + tid] : (int)kNoVertex;
     if (!cost_only) {   // rows nf..nfp-1 and the columns of the last granule past `count` are zero (as the cp.async zero fill was)
